@@ -1,0 +1,245 @@
+/* svol_b200 -- C ABI of the B200-native SVOL hot path (libsvol_b200.so, sm_100a).
+ *
+ * Drop-in boundary for the reference's lib/modeling path (SVANet.forward ->
+ * PerFrameMatcher / HungarianMatcher -> SetCriterion).  The reference has no native layer of
+ * its own; every op below replaces a PyTorch / scipy call of the reference, cited per entry.
+ * Host code (svol_b200/*.py here, or the reference's own train.py / test.py through
+ * INTEGRATION.md's stubs) binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named h_*.
+ *   - the caller (PyTorch) owns every buffer; nothing is allocated, freed or retained.
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and asynchronous.
+ *   - return value: 0 on success; negative SVOL_ERR_* for argument errors; positive values
+ *     are cudaError_t codes.  svol_last_error() returns a message for the calling thread.
+ *   - bf16 buffers are raw uint16 storage (torch.bfloat16); row-major unless stated.
+ *   - there is no CPU fallback: every entry point launches sm_100a kernels.
+ */
+#ifndef SVOL_B200_H_
+#define SVOL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVOL_ABI_VERSION 1
+
+enum {
+  SVOL_OK = 0,
+  SVOL_ERR_SHAPE = -1,     /* unsupported or inconsistent sizes / alignment */
+  SVOL_ERR_NULL = -2,      /* required pointer missing */
+  SVOL_ERR_DRIVER = -3,    /* driver entry point (cuTensorMapEncodeTiled) unavailable / failed */
+  SVOL_ERR_DEVICE = -4     /* device is not compute capability 10.x */
+};
+
+enum { SVOL_ACT_NONE = 0, SVOL_ACT_RELU = 1, SVOL_ACT_GELU = 2 };
+
+typedef uint16_t svol_bf16;
+
+int svol_abi_version(void);
+const char* svol_last_error(void);
+/* 0 if the current device can run this library (sm_100), SVOL_ERR_DEVICE otherwise. */
+int svol_device_check(void);
+/* sizeof() of the argument structures as this library was compiled (0 gemm_args, 1 attn_args,
+ * 2 match_args, 3 criterion_args, 4 gemm_epilogue) -- lets a foreign-language binding verify its
+ * struct layout before the first launch. */
+int svol_sizeof_args(int which);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense projections.  out = epilogue(A[M,K] x W[N,K]^T), bf16 operands, fp32 accumulation in
+ * TMEM (tcgen05.mma).  Replaces nn.Linear (+ F.relu / F.gelu / residual add / nn.LayerNorm):
+ *   input projections        lib/modeling/svanet.py:49-60,159-181
+ *   attention in/out proj    lib/modeling/cross_modal_transformer.py:88-97,137-141,145-156
+ *   FFN fc1/GELU/fc2 + norm  lib/modeling/cross_modal_transformer.py:142-143,157-158,163-179
+ *   box-head hidden layers   lib/modeling/svanet.py:144-156
+ * Epilogue order: +bias -> act -> +residual -> LayerNorm(ln_weight, ln_bias, ln_eps) -> stores.
+ * Requirements: N % 256 == 0, K % 64 == 0; LayerNorm and the transposed store need N == 256;
+ * A, W, out*, residual 16-byte aligned with row pitches (in elements) multiple of 8.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct svol_gemm_epilogue {
+  const float* bias;          /* [N] or NULL */
+  int32_t act;                /* SVOL_ACT_* */
+  int32_t ld_res;
+  const svol_bf16* residual;  /* [M, ld_res] or NULL */
+  const float* ln_weight;     /* [N] or NULL (no LayerNorm) */
+  const float* ln_bias;       /* [N] */
+  float ln_eps;
+  int32_t ld_out;
+  svol_bf16* out;             /* [M, ld_out] or NULL */
+  svol_bf16* out_pos;         /* [M, ld_out] second output = result + pos, or NULL */
+  const float* pos;           /* [*, ld_pos] fp32 */
+  int32_t ld_pos;
+  int32_t pos_row_mod;        /* pos row = row % pos_row_mod (0: pos row = row) */
+  svol_bf16* out_vt;          /* per-head transposed output [(M / vt_len) * N, vt_pitch] or NULL */
+  int32_t vt_len;             /* tokens per sample (row = b * vt_len + l) */
+  int32_t vt_pitch;           /* row pitch of out_vt in elements (multiple of 8, >= vt_len) */
+} svol_gemm_epilogue;
+
+typedef struct svol_gemm_args {
+  const svol_bf16* A;  /* [M, lda] */
+  const svol_bf16* W;  /* [N, ldw] */
+  int32_t M, N, K, lda, ldw;
+  int32_t reserved;
+  svol_gemm_epilogue ep;
+} svol_gemm_args;
+
+int svol_gemm_bf16(const svol_gemm_args* args, void* stream);
+/* Same contract, plain SIMT kernel (one warp per row).  Test / triangulation aid only. */
+int svol_gemm_bf16_plain(const svol_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-head attention core, flash style (scores never leave the SM): tcgen05 QK^T and PV
+ * with TMEM accumulators, TMA-fed K / V^T ring, online softmax in registers.
+ * Replaces the softmax(QK^T/sqrt(dh) + mask) V part of nn.MultiheadAttention at
+ * lib/modeling/cross_modal_transformer.py:139 (video self-attention), :147 (query
+ * self-attention) and :154 (query -> video cross-attention with key_padding_mask).
+ *   q   [B*Lq, ldq]  head h at columns [h*32, h*32+32); ALREADY scaled by log2(e)/sqrt(32)
+ *   k   [B*Lk, ldk]  same head layout
+ *   vt  [B*H*32, vt_pitch]  V transposed per head (row (b*H+h)*32+d, column = key index);
+ *                     columns [Lk, vt_pitch) must be zero
+ *   key_mask [B, Lk] float, nonzero = valid key, or NULL (all valid)
+ *   out [B*Lq, ldo]  heads concatenated (the input of out_proj)
+ * head_dim is fixed at 32 (hidden_dim 256 / 8 heads, lib/configs.py:117-120).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct svol_attn_args {
+  const svol_bf16* q;
+  const svol_bf16* k;
+  const svol_bf16* vt;
+  const float* key_mask;
+  svol_bf16* out;
+  int32_t B, H, Lq, Lk, ldq, ldk, ldo, vt_pitch;
+} svol_attn_args;
+
+int svol_attention_bf16(const svol_attn_args* args, void* stream);
+int svol_attention_bf16_plain(const svol_attn_args* args, void* stream);   /* SIMT, tests only */
+
+/* ------------------------------------------------------------------------------------------
+ * Row-wise / memory-bound pieces of the head.
+ * ------------------------------------------------------------------------------------------ */
+/* y = LayerNorm(x) rows of `cols` fp32 -> bf16.  First op of LinearLayer (svanet.py:174-176). */
+int svol_layernorm_f32_to_bf16(const float* x, const float* weight, const float* bias, svol_bf16* y,
+                               int32_t rows, int32_t cols, float eps, void* stream);
+
+/* y = [ReLU](Linear(LayerNorm(x))) in fp32 for a handful of rows: the sketch branch of the input
+ * projection (svanet.py:56-60,87), one call per LinearLayer.  x [rows,in], w [out,in], y [rows,out]. */
+int svol_ln_linear_f32(const float* x, const float* ln_weight, const float* ln_bias, const float* w,
+                       const float* b, int32_t relu, float* y, int32_t rows, int32_t in_dim,
+                       int32_t out_dim, float eps, void* stream);
+
+/* Sine positional encoding, PositionEmbeddingSine(normalize=True) (position_encoding.py:51-71).
+ * mask [B,L] float (nonzero = valid) -> pos [B,L,d] fp32. */
+int svol_posenc_sine(const float* mask, float* pos, int32_t B, int32_t L, int32_t d, void* stream);
+
+/* out[r,:] = bf16(x[r % mod,:] (+ pos[r % mod,:])) : broadcast the query embedding over the batch
+ * (cross_modal_transformer.py:52-56) and build x + pos operands. */
+int svol_add_pos_bf16(const float* x, const float* pos, svol_bf16* out, int32_t rows, int32_t cols,
+                      int32_t mod, void* stream);
+
+/* Sketch-conditioned gate (cross_modal_transformer.py:122-127): the sketch->video attention only
+ * contributes its head-averaged weights, so K is never materialised:
+ *   u[b,h,:]  = (1/sqrt(dh)) * Wk_h^T (Wq_h s_b + bq_h)            svol_gate_vectors
+ *   s[b,h,l]  = (x+pos)[b,l,:] . u[b,h,:]                            svol_gate_scores
+ *   att[b,l]  = mean_h softmax_l(s[b,h,:])                           (inside svol_gate_apply)
+ *   mem       = LayerNorm1(x * (1 + att));  also emits mem + pos     svol_gate_apply
+ * in_proj_weight [3d,d], in_proj_bias [3d] are the fp32 parameters of sketch_video_cross_attn. */
+int svol_gate_vectors(const float* sketch, const float* in_proj_weight, const float* in_proj_bias,
+                      float* u, int32_t B, int32_t d, int32_t H, void* stream);
+int svol_gate_scores(const svol_bf16* xpos, const float* u, float* scores, int32_t B, int32_t L,
+                     int32_t d, int32_t H, void* stream);
+int svol_gate_apply(const svol_bf16* x, const float* scores, const float* ln_weight, const float* ln_bias,
+                    const float* pos, svol_bf16* mem, svol_bf16* mem_pos, float* att_out /* [B,L] or NULL */,
+                    int32_t B, int32_t L, int32_t d, int32_t H, float eps, void* stream);
+
+/* Output heads (svanet.py:125-127): logits = class_embed(hs); boxes = sigmoid(bbox_embed.layers.2(h2))
+ * where h2 is the output of the two hidden box-MLP layers (svol_gemm_bf16 with ReLU).
+ * hs, h2 [rows, d] bf16; wc [2,d], bc [2], wb [4,d], bb [4] fp32; logits [rows,2], boxes [rows,4] fp32. */
+int svol_heads(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const float* bc, const float* wb,
+               const float* bb, float* logits, float* boxes, int32_t rows, int32_t d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Hungarian matching (lib/modeling/matcher.py) for ALL decoder layers in one launch.
+ *
+ * A "problem" is one assignment: rows = `rows_per_problem` consecutive queries of one video,
+ * columns = the targets [tgt_off[p], tgt_off[p+1]).  PerFrameMatcher (matcher.py:38-119):
+ * problems_per_video = T, rows_per_problem = queries per frame.  HungarianMatcher (:131-159):
+ * problems_per_video = 1, rows_per_problem = Q.
+ *
+ * Cost block (only the block-diagonal entries the reference ever reads, matcher.py:92-93) in the
+ * reference's fp32 operation order:  C = w_bbox*L1 + w_giou*(-GIoU) + w_class*(-softmax(logits)[0])
+ * (matcher.py:59-85, box_utils.py:9-13,24-61), then scipy.optimize.linear_sum_assignment's
+ * algorithm (Crouse 2016 shortest augmenting paths on fp64-promoted costs, identical
+ * tie-breaking; matcher.py:93,158) run by one warp per problem.
+ *
+ *   logits [NL,B,Q,2], boxes [NL,B,Q,4] fp32 (cxcywh); tgt_boxes [S,4] fp32 (cxcywh)
+ *   tgt_off   [P+1] int32, P = B*problems_per_video : target range of problem p
+ *   match_off [P+1] int32 : output range of problem p (min(rows, cols) entries)
+ *   cost_ws   fp32 workspace, cost_off[p] (int64, [P+1]) = offset of problem p's block inside one
+ *             layer's slab of cost_off[P] floats; total NL*cost_off[P] floats
+ *   pred_idx, tgt_idx [NL, K] int64, K = match_off[P]: query index inside the video, GLOBAL target
+ *             index (localised by svol_match_localize)
+ *   status    [1] int32, set nonzero on NaN / -inf costs or infeasible problems
+ * ------------------------------------------------------------------------------------------ */
+typedef struct svol_match_args {
+  const float* logits;
+  const float* boxes;
+  const float* tgt_boxes;
+  const int32_t* tgt_off;
+  const int32_t* match_off;
+  const int64_t* cost_off;
+  float* cost_ws;
+  int64_t* pred_idx;
+  int64_t* tgt_idx;
+  int32_t* status;
+  int32_t NL, B, Q, problems_per_video, rows_per_problem, max_cols;
+  float w_class, w_bbox, w_giou;
+  int32_t reserved;
+} svol_match_args;
+
+int svol_match(const svol_match_args* args, void* stream);
+
+/* PerFrameMatcher's localisation quirk (matcher.py:114-115): per (layer, video) subtract the minimum
+ * matched global target index.  video_match_off [B+1] int32 = output range of each video. */
+int svol_match_localize(int64_t* tgt_idx, const int32_t* video_match_off, int32_t NL, int32_t B,
+                        int32_t K, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SetCriterion losses (lib/modeling/loss.py:39-60,76-103) for ALL decoder layers in one launch.
+ *   losses [NL,4] fp32 = (loss_label, class_error, loss_bbox, loss_giou) per layer
+ *   pred_idx / tgt_idx [NL,K] int64 as produced above (tgt_idx video-local),
+ *   match_video [K] int32 = video of each matched pair, video_tgt_off [B+1] int32.
+ * svol_criterion_backward writes d(sum_i w_i * loss_i)/d(logits, boxes) with per-layer weights
+ * grad_w [NL,3] = (w_label, w_bbox, w_giou) (train.py:227-228).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct svol_criterion_args {
+  const float* logits;
+  const float* boxes;
+  const float* tgt_boxes;
+  const int64_t* pred_idx;
+  const int64_t* tgt_idx;
+  const int32_t* match_video;
+  const int32_t* video_tgt_off;
+  float* losses;
+  int32_t NL, B, Q, K;
+  float eos_coef;
+  int32_t reserved;
+} svol_criterion_args;
+
+int svol_criterion(const svol_criterion_args* args, void* stream);
+int svol_criterion_backward(const svol_criterion_args* args, const float* grad_w, float* grad_logits,
+                            float* grad_boxes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Inference post-processing (test.py:133-158): foreground score = softmax(logits)[0],
+ * clamp(cxcywh->xyxy, 0, 1), per-frame groups of q_per_frame queries sorted by score
+ * (descending, stable).  out [B, Q, 5] fp32 = (x0,y0,x1,y1,score) in sorted order,
+ * order [B, Q] int32 = source query (within its frame) of each output row.
+ * ------------------------------------------------------------------------------------------ */
+int svol_postprocess(const float* logits, const float* boxes, float* out, int32_t* order, int32_t B,
+                     int32_t Q, int32_t q_per_frame, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVOL_B200_H_ */

@@ -1,0 +1,144 @@
+"""ctypes binding of ``libsvol_b200.so`` (the C ABI declared in ``include/svol_b200.h``).
+
+There is no fallback: if the shared object is missing or the device is not a B200-class GPU,
+every entry point raises.  The structures below mirror the header field for field.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libsvol_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+ABI_VERSION = 1
+
+# every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "svol_abi_version", "svol_last_error", "svol_device_check", "svol_sizeof_args",
+    "svol_gemm_bf16", "svol_gemm_bf16_plain", "svol_attention_bf16", "svol_attention_bf16_plain",
+    "svol_layernorm_f32_to_bf16", "svol_ln_linear_f32", "svol_posenc_sine", "svol_add_pos_bf16",
+    "svol_gate_vectors", "svol_gate_scores", "svol_gate_apply", "svol_heads",
+    "svol_match", "svol_match_localize", "svol_criterion", "svol_criterion_backward", "svol_postprocess",
+]
+
+
+class GemmEpilogue(C.Structure):
+    _fields_ = [
+        ("bias", C.c_void_p), ("act", C.c_int32), ("ld_res", C.c_int32), ("residual", C.c_void_p),
+        ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p), ("ln_eps", C.c_float), ("ld_out", C.c_int32),
+        ("out", C.c_void_p), ("out_pos", C.c_void_p), ("pos", C.c_void_p), ("ld_pos", C.c_int32),
+        ("pos_row_mod", C.c_int32), ("out_vt", C.c_void_p), ("vt_len", C.c_int32), ("vt_pitch", C.c_int32),
+    ]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("W", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("lda", C.c_int32), ("ldw", C.c_int32), ("reserved", C.c_int32), ("ep", GemmEpilogue),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("vt", C.c_void_p), ("key_mask", C.c_void_p), ("out", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32), ("ldq", C.c_int32),
+        ("ldk", C.c_int32), ("ldo", C.c_int32), ("vt_pitch", C.c_int32),
+    ]
+
+
+class MatchArgs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("boxes", C.c_void_p), ("tgt_boxes", C.c_void_p), ("tgt_off", C.c_void_p),
+        ("match_off", C.c_void_p), ("cost_off", C.c_void_p), ("cost_ws", C.c_void_p), ("pred_idx", C.c_void_p),
+        ("tgt_idx", C.c_void_p), ("status", C.c_void_p),
+        ("NL", C.c_int32), ("B", C.c_int32), ("Q", C.c_int32), ("problems_per_video", C.c_int32),
+        ("rows_per_problem", C.c_int32), ("max_cols", C.c_int32),
+        ("w_class", C.c_float), ("w_bbox", C.c_float), ("w_giou", C.c_float), ("reserved", C.c_int32),
+    ]
+
+
+class CriterionArgs(C.Structure):
+    _fields_ = [
+        ("logits", C.c_void_p), ("boxes", C.c_void_p), ("tgt_boxes", C.c_void_p), ("pred_idx", C.c_void_p),
+        ("tgt_idx", C.c_void_p), ("match_video", C.c_void_p), ("video_tgt_off", C.c_void_p), ("losses", C.c_void_p),
+        ("NL", C.c_int32), ("B", C.c_int32), ("Q", C.c_int32), ("K", C.c_int32),
+        ("eos_coef", C.c_float), ("reserved", C.c_int32),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+_i32, _f32, _vp = C.c_int32, C.c_float, C.c_void_p
+
+
+def _declare(lib: C.CDLL) -> None:
+    lib.svol_abi_version.restype = C.c_int
+    lib.svol_last_error.restype = C.c_char_p
+    lib.svol_device_check.restype = C.c_int
+    sigs = {
+        "svol_gemm_bf16": [C.POINTER(GemmArgs), _vp],
+        "svol_gemm_bf16_plain": [C.POINTER(GemmArgs), _vp],
+        "svol_attention_bf16": [C.POINTER(AttnArgs), _vp],
+        "svol_attention_bf16_plain": [C.POINTER(AttnArgs), _vp],
+        "svol_layernorm_f32_to_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
+        "svol_ln_linear_f32": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f32, _vp],
+        "svol_posenc_sine": [_vp, _vp, _i32, _i32, _i32, _vp],
+        "svol_add_pos_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
+        "svol_gate_vectors": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
+        "svol_gate_scores": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
+        "svol_gate_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
+        "svol_heads": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp],
+        "svol_match": [C.POINTER(MatchArgs), _vp],
+        "svol_match_localize": [_vp, _vp, _i32, _i32, _i32, _vp],
+        "svol_criterion": [C.POINTER(CriterionArgs), _vp],
+        "svol_criterion_backward": [C.POINTER(CriterionArgs), _vp, _vp, _vp, _vp],
+        "svol_postprocess": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+
+
+def get_lib() -> C.CDLL:
+    """Loads the shared object (once).  Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with svol_b200/csrc/build.sh "
+                "(or __graft_entry__.build()); svol_b200 has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        _declare(lib)
+        if lib.svol_abi_version() != ABI_VERSION:
+            raise ImportError("libsvol_b200.so ABI version mismatch; rebuild it")
+        for which, struct in enumerate((GemmArgs, AttnArgs, MatchArgs, CriterionArgs, GemmEpilogue)):
+            if lib.svol_sizeof_args(which) != C.sizeof(struct):
+                raise ImportError(f"ctypes layout of {struct.__name__} does not match libsvol_b200.so")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = get_lib().svol_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"svol_b200 {what} failed (code {rc}): {msg}")
+
+
+def require_device() -> None:
+    """Fails loudly unless the current CUDA device can run the sm_100a kernels."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("svol_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    check(get_lib().svol_device_check(), "device check")
+
+
+def ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,221 @@
+// extern "C" entry points of libsvol_b200.so, error plumbing and TMA descriptor construction.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "svol_internal.h"
+
+namespace svol {
+
+static thread_local char g_err[512] = "";
+
+int svol_fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int svol_fail_cuda(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return static_cast<int>(e);
+}
+int svol_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return svol_fail_cuda(e, what);
+  return SVOL_OK;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      cached = 148;
+  }
+  return cached;
+}
+
+// cuTensorMapEncodeTiled is a driver API; resolve it through the runtime so the library does not
+// link against libcuda (absent on the build machine).
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tensor_map_2d(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld,
+                       int box_inner, int box_outer, int swizzle_bytes) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return svol_fail(SVOL_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16 != 0)
+    return svol_fail(SVOL_ERR_SHAPE, "tensor map: base must be 16-byte aligned and the row pitch a multiple of 8 elements");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(outer)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_outer)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed with CUresult %d (inner %lld outer %lld ld %lld box %dx%d)",
+             static_cast<int>(r), (long long)inner, (long long)outer, (long long)ld, box_inner, box_outer);
+    return svol_fail(SVOL_ERR_DRIVER, msg);
+  }
+  return SVOL_OK;
+}
+
+// rowwise.cu
+int launch_layernorm_f32_to_bf16(const float*, const float*, const float*, svol_bf16*, int, int, float, cudaStream_t);
+int launch_ln_linear_f32(const float*, const float*, const float*, const float*, const float*, int, float*, int, int, int,
+                         float, cudaStream_t);
+int launch_posenc_sine(const float*, float*, int, int, int, cudaStream_t);
+int launch_add_pos_bf16(const float*, const float*, svol_bf16*, int, int, int, cudaStream_t);
+int launch_gate_vectors(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
+int launch_gate_scores(const svol_bf16*, const float*, float*, int, int, int, int, cudaStream_t);
+int launch_gate_apply(const svol_bf16*, const float*, const float*, const float*, const float*, svol_bf16*, svol_bf16*,
+                      float*, int, int, int, int, float, cudaStream_t);
+int launch_heads(const svol_bf16*, const svol_bf16*, const float*, const float*, const float*, const float*, float*,
+                 float*, int, int, cudaStream_t);
+int launch_postprocess(const float*, const float*, float*, int32_t*, int, int, int, cudaStream_t);
+
+}  // namespace svol
+
+using namespace svol;
+
+#define SVOL_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define SVOL_REQUIRE(p)                                                   \
+  do {                                                                    \
+    if (!(p)) return svol_fail(SVOL_ERR_NULL, "required pointer is NULL: " #p); \
+  } while (0)
+
+extern "C" {
+
+int svol_abi_version(void) { return SVOL_ABI_VERSION; }
+const char* svol_last_error(void) { return g_err; }
+
+int svol_sizeof_args(int which) {
+  switch (which) {
+    case 0: return static_cast<int>(sizeof(svol_gemm_args));
+    case 1: return static_cast<int>(sizeof(svol_attn_args));
+    case 2: return static_cast<int>(sizeof(svol_match_args));
+    case 3: return static_cast<int>(sizeof(svol_criterion_args));
+    case 4: return static_cast<int>(sizeof(svol_gemm_epilogue));
+    default: return -1;
+  }
+}
+
+int svol_device_check(void) {
+  int dev = 0, major = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return svol_fail_cuda(e, "cudaGetDevice");
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return svol_fail_cuda(e, "cudaDeviceGetAttribute");
+  if (major != 10) return svol_fail(SVOL_ERR_DEVICE, "svol_b200 needs a compute capability 10.x (B200) device");
+  return SVOL_OK;
+}
+
+int svol_gemm_bf16(const svol_gemm_args* a, void* stream) {
+  SVOL_REQUIRE(a); SVOL_REQUIRE(a->A); SVOL_REQUIRE(a->W);
+  return launch_gemm_bf16_tc(*a, SVOL_STREAM(stream));
+}
+int svol_gemm_bf16_plain(const svol_gemm_args* a, void* stream) {
+  SVOL_REQUIRE(a); SVOL_REQUIRE(a->A); SVOL_REQUIRE(a->W);
+  return launch_gemm_bf16_plain(*a, SVOL_STREAM(stream));
+}
+int svol_attention_bf16(const svol_attn_args* a, void* stream) {
+  SVOL_REQUIRE(a); SVOL_REQUIRE(a->q); SVOL_REQUIRE(a->k); SVOL_REQUIRE(a->vt); SVOL_REQUIRE(a->out);
+  return launch_attention_tc(*a, SVOL_STREAM(stream));
+}
+int svol_attention_bf16_plain(const svol_attn_args* a, void* stream) {
+  SVOL_REQUIRE(a); SVOL_REQUIRE(a->q); SVOL_REQUIRE(a->k); SVOL_REQUIRE(a->vt); SVOL_REQUIRE(a->out);
+  return launch_attention_plain(*a, SVOL_STREAM(stream));
+}
+
+int svol_layernorm_f32_to_bf16(const float* x, const float* w, const float* b, svol_bf16* y, int32_t rows,
+                               int32_t cols, float eps, void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
+  return launch_layernorm_f32_to_bf16(x, w, b, y, rows, cols, eps, SVOL_STREAM(stream));
+}
+int svol_ln_linear_f32(const float* x, const float* lw, const float* lb, const float* w, const float* b, int32_t relu,
+                       float* y, int32_t rows, int32_t in_dim, int32_t out_dim, float eps, void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
+  return launch_ln_linear_f32(x, lw, lb, w, b, relu, y, rows, in_dim, out_dim, eps, SVOL_STREAM(stream));
+}
+int svol_posenc_sine(const float* mask, float* pos, int32_t B, int32_t L, int32_t d, void* stream) {
+  SVOL_REQUIRE(mask); SVOL_REQUIRE(pos);
+  return launch_posenc_sine(mask, pos, B, L, d, SVOL_STREAM(stream));
+}
+int svol_add_pos_bf16(const float* x, const float* pos, svol_bf16* out, int32_t rows, int32_t cols, int32_t mod,
+                      void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(out);
+  return launch_add_pos_bf16(x, pos, out, rows, cols, mod, SVOL_STREAM(stream));
+}
+int svol_gate_vectors(const float* sketch, const float* w, const float* b, float* u, int32_t B, int32_t d, int32_t H,
+                      void* stream) {
+  SVOL_REQUIRE(sketch); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(u);
+  return launch_gate_vectors(sketch, w, b, u, B, d, H, SVOL_STREAM(stream));
+}
+int svol_gate_scores(const svol_bf16* xpos, const float* u, float* scores, int32_t B, int32_t L, int32_t d, int32_t H,
+                     void* stream) {
+  SVOL_REQUIRE(xpos); SVOL_REQUIRE(u); SVOL_REQUIRE(scores);
+  return launch_gate_scores(xpos, u, scores, B, L, d, H, SVOL_STREAM(stream));
+}
+int svol_gate_apply(const svol_bf16* x, const float* scores, const float* lw, const float* lb, const float* pos,
+                    svol_bf16* mem, svol_bf16* mem_pos, float* att_out, int32_t B, int32_t L, int32_t d, int32_t H,
+                    float eps, void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(scores); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(pos); SVOL_REQUIRE(mem);
+  SVOL_REQUIRE(mem_pos);
+  return launch_gate_apply(x, scores, lw, lb, pos, mem, mem_pos, att_out, B, L, d, H, eps, SVOL_STREAM(stream));
+}
+int svol_heads(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const float* bc, const float* wb,
+               const float* bb, float* logits, float* boxes, int32_t rows, int32_t d, void* stream) {
+  SVOL_REQUIRE(hs); SVOL_REQUIRE(h2); SVOL_REQUIRE(wc); SVOL_REQUIRE(bc); SVOL_REQUIRE(wb); SVOL_REQUIRE(bb);
+  SVOL_REQUIRE(logits); SVOL_REQUIRE(boxes);
+  return launch_heads(hs, h2, wc, bc, wb, bb, logits, boxes, rows, d, SVOL_STREAM(stream));
+}
+
+int svol_match(const svol_match_args* a, void* stream) {
+  SVOL_REQUIRE(a); SVOL_REQUIRE(a->logits); SVOL_REQUIRE(a->boxes); SVOL_REQUIRE(a->tgt_boxes); SVOL_REQUIRE(a->tgt_off);
+  SVOL_REQUIRE(a->match_off); SVOL_REQUIRE(a->cost_off); SVOL_REQUIRE(a->cost_ws); SVOL_REQUIRE(a->pred_idx);
+  SVOL_REQUIRE(a->tgt_idx); SVOL_REQUIRE(a->status);
+  return launch_match(*a, SVOL_STREAM(stream));
+}
+int svol_match_localize(int64_t* tgt_idx, const int32_t* video_match_off, int32_t NL, int32_t B, int32_t K,
+                        void* stream) {
+  SVOL_REQUIRE(tgt_idx); SVOL_REQUIRE(video_match_off);
+  return launch_match_localize(tgt_idx, video_match_off, NL, B, K, SVOL_STREAM(stream));
+}
+int svol_criterion(const svol_criterion_args* a, void* stream) {
+  SVOL_REQUIRE(a); SVOL_REQUIRE(a->logits); SVOL_REQUIRE(a->boxes); SVOL_REQUIRE(a->tgt_boxes); SVOL_REQUIRE(a->pred_idx);
+  SVOL_REQUIRE(a->tgt_idx); SVOL_REQUIRE(a->match_video); SVOL_REQUIRE(a->video_tgt_off); SVOL_REQUIRE(a->losses);
+  return launch_criterion(*a, SVOL_STREAM(stream));
+}
+int svol_criterion_backward(const svol_criterion_args* a, const float* grad_w, float* grad_logits, float* grad_boxes,
+                            void* stream) {
+  SVOL_REQUIRE(a); SVOL_REQUIRE(grad_w); SVOL_REQUIRE(grad_logits); SVOL_REQUIRE(grad_boxes);
+  return launch_criterion_backward(*a, grad_w, grad_logits, grad_boxes, SVOL_STREAM(stream));
+}
+int svol_postprocess(const float* logits, const float* boxes, float* out, int32_t* order, int32_t B, int32_t Q,
+                     int32_t q_per_frame, void* stream) {
+  SVOL_REQUIRE(logits); SVOL_REQUIRE(boxes); SVOL_REQUIRE(out); SVOL_REQUIRE(order);
+  return launch_postprocess(logits, boxes, out, order, B, Q, q_per_frame, SVOL_STREAM(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,423 @@
+// Memory-bound row-wise kernels of the SVOL head (sm_100a): LayerNorm of the input features, the
+// fp32 sketch branch, the sine positional table, the sketch-conditioned gate, the output heads and
+// the inference post-processing.  All are coalesced, 16-byte vectorised, warp-per-row kernels with
+// shuffle reductions; none of them has data reuse that would justify tensor cores.
+#include "common.cuh"
+#include "svol_internal.h"
+
+namespace svol {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm fp32 -> bf16, one warp per row (first op of LinearLayer, svanet.py:174-176)
+// ---------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 8;   // float4 per lane -> cols <= 1024
+
+__global__ void __launch_bounds__(256) layernorm_f32_to_bf16_kernel(const float* __restrict__ x,
+                                                                     const float* __restrict__ w,
+                                                                     const float* __restrict__ b,
+                                                                     __nv_bfloat16* __restrict__ y, int rows,
+                                                                     int cols, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * cols);
+  const int nv = cols >> 2;
+  float4 buf[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = i * 32 + lane;
+    if (idx < nv) {
+      buf[i] = __ldcs(xr + idx);       // streamed once
+      s += (buf[i].x + buf[i].y) + (buf[i].z + buf[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / cols;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = i * 32 + lane;
+    if (idx < nv) {
+      const float a = buf[i].x - mean, c = buf[i].y - mean, d = buf[i].z - mean, e = buf[i].w - mean;
+      ss += (a * a + c * c) + (d * d + e * e);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / cols + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * cols);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int idx = i * 32 + lane;
+    if (idx < nv) {
+      const float4 g = __ldg(w4 + idx), o = __ldg(b4 + idx);
+      uint2 q;
+      q.x = pack_bf16x2((buf[i].x - mean) * rstd * g.x + o.x, (buf[i].y - mean) * rstd * g.y + o.y);
+      q.y = pack_bf16x2((buf[i].z - mean) * rstd * g.z + o.z, (buf[i].w - mean) * rstd * g.w + o.w);
+      yr[idx] = q;
+    }
+  }
+}
+
+int launch_layernorm_f32_to_bf16(const float* x, const float* w, const float* b, svol_bf16* y, int rows, int cols,
+                                 float eps, cudaStream_t stream) {
+  if (cols % 4 != 0 || cols > LN_MAXV * 128 || rows <= 0) return svol_fail(SVOL_ERR_SHAPE, "layernorm: cols % 4 == 0, cols <= 1024");
+  const int wpb = 8;
+  layernorm_f32_to_bf16_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
+      x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps);
+  return svol_check_launch("layernorm_f32_to_bf16");
+}
+
+// ---------------------------------------------------------------------------------------------
+// y = [ReLU](Linear(LayerNorm(x))) in fp32, one CTA per row (sketch branch, B rows only)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ lw,
+                                                            const float* __restrict__ lb, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, int relu,
+                                                            float* __restrict__ y, int in_dim, int out_dim, float eps) {
+  extern __shared__ float xs[];   // in_dim normalised inputs + 16 scratch
+  float* red = xs + in_dim;
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xr = x + static_cast<size_t>(row) * in_dim;
+  float s = 0.f;
+  for (int i = tid; i < in_dim; i += blockDim.x) { const float v = xr[i]; xs[i] = v; s += v; }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float mean = tot / in_dim;
+  __syncthreads();
+  float ss = 0.f;
+  for (int i = tid; i < in_dim; i += blockDim.x) { const float d = xs[i] - mean; ss += d * d; }
+  ss = warp_sum(ss);
+  if (lane == 0) red[warp] = ss;
+  __syncthreads();
+  tot = 0.f;
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / in_dim + eps);
+  for (int i = tid; i < in_dim; i += blockDim.x) xs[i] = (xs[i] - mean) * rstd * lw[i] + lb[i];
+  __syncthreads();
+  for (int o = warp; o < out_dim; o += 8) {
+    const float* wr = w + static_cast<size_t>(o) * in_dim;
+    float acc = 0.f;
+    for (int i = lane; i < in_dim; i += 32) acc = fmaf(xs[i], __ldg(wr + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      acc += bias[o];
+      y[static_cast<size_t>(row) * out_dim + o] = relu ? fmaxf(acc, 0.f) : acc;
+    }
+  }
+}
+
+int launch_ln_linear_f32(const float* x, const float* lw, const float* lb, const float* w, const float* b, int relu,
+                         float* y, int rows, int in_dim, int out_dim, float eps, cudaStream_t stream) {
+  if (rows <= 0 || in_dim <= 0 || in_dim > 8192) return svol_fail(SVOL_ERR_SHAPE, "ln_linear: bad sizes");
+  ln_linear_f32_kernel<<<rows, 256, (in_dim + 16) * sizeof(float), stream>>>(x, lw, lb, w, b, relu, y, in_dim, out_dim, eps);
+  return svol_check_launch("ln_linear_f32");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sine positional table (position_encoding.py:51-71).  Each CTA owns 32 token rows of one sample
+// and recomputes the mask prefix sum it needs from the (L2-resident) mask row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) posenc_sine_kernel(const float* __restrict__ mask, float* __restrict__ pos,
+                                                          int L, int d) {
+  __shared__ float red[2][8];
+  __shared__ float xrow[32];
+  const int b = blockIdx.y, l0 = blockIdx.x * 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* mrow = mask + static_cast<size_t>(b) * L;
+  float before = 0.f, total = 0.f;
+  for (int l = tid; l < L; l += blockDim.x) {
+    const float m = mrow[l] != 0.f ? 1.f : 0.f;
+    total += m;
+    if (l < l0) before += m;
+  }
+  before = warp_sum(before); total = warp_sum(total);
+  if (lane == 0) { red[0][warp] = before; red[1][warp] = total; }
+  __syncthreads();
+  if (tid < 32) {
+    float bsum = 0.f, tsum = 0.f;
+    for (int i = 0; i < 8; ++i) { bsum += red[0][i]; tsum += red[1][i]; }
+    float cum = bsum;                                      // exact: sums of 0/1 below 2^24
+    for (int t = 0; t <= tid; ++t) if (l0 + t < L) cum += (mrow[l0 + t] != 0.f ? 1.f : 0.f);
+    // x_embed / (x_embed[:, -1:] + eps) * scale, left to right in fp32
+    xrow[tid] = __fmul_rn(__fdiv_rn(cum, __fadd_rn(tsum, 1e-6f)), 6.283185307179586f);
+  }
+  __syncthreads();
+  const int rows = min(32, L - l0);
+  for (int e = tid; e < rows * d; e += blockDim.x) {
+    const int r = e / d, i = e - r * d;
+    const float expo = __fdiv_rn(__fmul_rn(2.f, static_cast<float>(i >> 1)), static_cast<float>(d));
+    const float dim_t = powf(10000.f, expo);
+    const float a = __fdiv_rn(xrow[r], dim_t);
+    pos[(static_cast<size_t>(b) * L + l0 + r) * d + i] = (i & 1) ? cosf(a) : sinf(a);
+  }
+}
+
+int launch_posenc_sine(const float* mask, float* pos, int B, int L, int d, cudaStream_t stream) {
+  if (B <= 0 || L <= 0 || d <= 0) return svol_fail(SVOL_ERR_SHAPE, "posenc: bad sizes");
+  posenc_sine_kernel<<<dim3((L + 31) / 32, B), 256, 0, stream>>>(mask, pos, L, d);
+  return svol_check_launch("posenc_sine");
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[r,:] = bf16(x[r % mod,:] + pos[r % mod,:])
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) add_pos_bf16_kernel(const float* __restrict__ x, const float* __restrict__ pos,
+                                                           __nv_bfloat16* __restrict__ out, long long total4,
+                                                           int cols4, int mod) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total4) return;
+  const long long r = i / cols4;
+  const int c = static_cast<int>(i - r * cols4);
+  const long long src = (mod > 0 ? r % mod : r) * cols4 + c;
+  float4 v = __ldg(reinterpret_cast<const float4*>(x) + src);
+  if (pos) {
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos) + src);
+    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+  }
+  uint2 q;
+  q.x = pack_bf16x2(v.x, v.y); q.y = pack_bf16x2(v.z, v.w);
+  reinterpret_cast<uint2*>(out)[i] = q;
+}
+
+int launch_add_pos_bf16(const float* x, const float* pos, svol_bf16* out, int rows, int cols, int mod,
+                        cudaStream_t stream) {
+  if (cols % 4 != 0 || rows <= 0) return svol_fail(SVOL_ERR_SHAPE, "add_pos: cols % 4 == 0");
+  const long long total4 = static_cast<long long>(rows) * (cols / 4);
+  add_pos_bf16_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, stream>>>(
+      x, pos, reinterpret_cast<__nv_bfloat16*>(out), total4, cols / 4, mod);
+  return svol_check_launch("add_pos_bf16");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sketch-conditioned gate (cross_modal_transformer.py:122-127)
+// ---------------------------------------------------------------------------------------------
+// u[b,h,:] = (1/sqrt(dh)) * sum_j (Wq[h*dh+j,:] . s_b + bq[h*dh+j]) * Wk[h*dh+j,:]
+// (the key bias adds the same constant to every token's score and cancels in the softmax)
+__global__ void __launch_bounds__(256) gate_vectors_kernel(const float* __restrict__ sketch,
+                                                           const float* __restrict__ w, const float* __restrict__ bias,
+                                                           float* __restrict__ u, int d, int H) {
+  extern __shared__ float sm[];          // d sketch values + dh q values
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int dh = d / H;
+  float* s = sm;
+  float* q = sm + d;
+  for (int i = tid; i < d; i += blockDim.x) s[i] = sketch[static_cast<size_t>(b) * d + i];
+  __syncthreads();
+  for (int j = warp; j < dh; j += 8) {
+    const float* wr = w + static_cast<size_t>(h * dh + j) * d;
+    float acc = 0.f;
+    for (int i = lane; i < d; i += 32) acc = fmaf(s[i], __ldg(wr + i), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) q[j] = (acc + bias[h * dh + j]) * rsqrtf(static_cast<float>(dh));
+  }
+  __syncthreads();
+  for (int c = tid; c < d; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < dh; ++j) acc = fmaf(q[j], __ldg(w + static_cast<size_t>(d + h * dh + j) * d + c), acc);
+    u[(static_cast<size_t>(b) * H + h) * d + c] = acc;
+  }
+}
+
+int launch_gate_vectors(const float* sketch, const float* w, const float* b, float* u, int B, int d, int H,
+                        cudaStream_t stream) {
+  if (B <= 0 || d <= 0 || H <= 0 || d % H != 0) return svol_fail(SVOL_ERR_SHAPE, "gate_vectors: bad sizes");
+  gate_vectors_kernel<<<dim3(H, B), 256, (d + d / H) * sizeof(float), stream>>>(sketch, w, b, u, d, H);
+  return svol_check_launch("gate_vectors");
+}
+
+// scores[b,h,l] = (x+pos)[b,l,:] . u[b,h,:]; one warp per token, d = 256 (8 bf16 per lane), H = 8
+constexpr int GATE_D = 256, GATE_H = 8, GATE_ROWS = 64;
+
+__global__ void __launch_bounds__(256) gate_scores_kernel(const __nv_bfloat16* __restrict__ xpos,
+                                                          const float* __restrict__ u, float* __restrict__ scores,
+                                                          int L) {
+  __shared__ float us[GATE_H][GATE_D];
+  const int b = blockIdx.y, l0 = blockIdx.x * GATE_ROWS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < GATE_H * GATE_D; i += 256) us[i / GATE_D][i % GATE_D] = u[static_cast<size_t>(b) * GATE_H * GATE_D + i];
+  __syncthreads();
+  for (int r = warp; r < GATE_ROWS; r += 8) {
+    const int l = l0 + r;
+    if (l >= L) break;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(xpos + (static_cast<size_t>(b) * L + l) * GATE_D) + lane);
+    float xv[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+    float mine = 0.f;
+#pragma unroll
+    for (int h = 0; h < GATE_H; ++h) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc = fmaf(xv[i], us[h][lane * 8 + i], acc);
+      acc = warp_sum(acc);
+      if (lane == h) mine = acc;
+    }
+    if (lane < GATE_H) scores[(static_cast<size_t>(b) * GATE_H + lane) * L + l] = mine;
+  }
+}
+
+int launch_gate_scores(const svol_bf16* xpos, const float* u, float* scores, int B, int L, int d, int H,
+                       cudaStream_t stream) {
+  if (d != GATE_D || H != GATE_H || B <= 0 || L <= 0) return svol_fail(SVOL_ERR_SHAPE, "gate_scores: hidden_dim 256 / 8 heads only");
+  gate_scores_kernel<<<dim3((L + GATE_ROWS - 1) / GATE_ROWS, B), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(xpos), u, scores, L);
+  return svol_check_launch("gate_scores");
+}
+
+// att[b,l] = mean_h softmax_l(scores[b,h,:]); mem = LN1(x + att*x); mem_pos = mem + pos
+__global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                         const float* __restrict__ scores,
+                                                         const float* __restrict__ lw, const float* __restrict__ lb,
+                                                         const float* __restrict__ pos, __nv_bfloat16* __restrict__ mem,
+                                                         __nv_bfloat16* __restrict__ mem_pos, float* __restrict__ att_out,
+                                                         int L, float eps) {
+  __shared__ float smax[GATE_H], sinv[GATE_H];
+  const int b = blockIdx.y, l0 = blockIdx.x * GATE_ROWS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    // warp h: softmax statistics of head h over all L tokens of this sample (L2-resident re-read)
+    const float* sr = scores + (static_cast<size_t>(b) * GATE_H + warp) * L;
+    float m = -INFINITY;
+    for (int l = lane; l < L; l += 32) m = fmaxf(m, sr[l]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int l = lane; l < L; l += 32) s += expf(sr[l] - m);
+    s = warp_sum(s);
+    if (lane == 0) { smax[warp] = m; sinv[warp] = 1.f / s; }
+  }
+  __syncthreads();
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(lw) + lane * 2), g1 = __ldg(reinterpret_cast<const float4*>(lw) + lane * 2 + 1);
+  const float4 o0 = __ldg(reinterpret_cast<const float4*>(lb) + lane * 2), o1 = __ldg(reinterpret_cast<const float4*>(lb) + lane * 2 + 1);
+  const float gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float gb[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+  for (int r = warp; r < GATE_ROWS; r += 8) {
+    const int l = l0 + r;
+    if (l >= L) break;
+    const size_t row = static_cast<size_t>(b) * L + l;
+    float a = 0.f;
+    if (lane < GATE_H) a = expf(scores[(static_cast<size_t>(b) * GATE_H + lane) * L + l] - smax[lane]) * sinv[lane];
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    const float att = __shfl_sync(0xffffffffu, a, 0) * (1.0f / GATE_H);
+    if (att_out && lane == 0) att_out[row] = att;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + row * GATE_D) + lane);
+    float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = v[i] + att * v[i]; s += v[i]; }
+    const float mean = warp_sum(s) * (1.0f / GATE_D);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float dlt = v[i] - mean; ss += dlt * dlt; }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / GATE_D) + eps);
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + row * GATE_D) + lane * 2);
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + row * GATE_D) + lane * 2 + 1);
+    const float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = (v[i] - mean) * rstd * gw[i] + gb[i];
+    uint4 o, op;
+    o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]); o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+    op.x = pack_bf16x2(y[0] + pp[0], y[1] + pp[1]); op.y = pack_bf16x2(y[2] + pp[2], y[3] + pp[3]);
+    op.z = pack_bf16x2(y[4] + pp[4], y[5] + pp[5]); op.w = pack_bf16x2(y[6] + pp[6], y[7] + pp[7]);
+    reinterpret_cast<uint4*>(mem + row * GATE_D)[lane] = o;
+    reinterpret_cast<uint4*>(mem_pos + row * GATE_D)[lane] = op;
+  }
+}
+
+int launch_gate_apply(const svol_bf16* x, const float* scores, const float* lw, const float* lb, const float* pos,
+                      svol_bf16* mem, svol_bf16* mem_pos, float* att_out, int B, int L, int d, int H, float eps,
+                      cudaStream_t stream) {
+  if (d != GATE_D || H != GATE_H || B <= 0 || L <= 0) return svol_fail(SVOL_ERR_SHAPE, "gate_apply: hidden_dim 256 / 8 heads only");
+  gate_apply_kernel<<<dim3((L + GATE_ROWS - 1) / GATE_ROWS, B), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), scores, lw, lb, pos, reinterpret_cast<__nv_bfloat16*>(mem),
+      reinterpret_cast<__nv_bfloat16*>(mem_pos), att_out, L, eps);
+  return svol_check_launch("gate_apply");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Output heads (svanet.py:125-127): class logits and sigmoid of the last box-MLP layer
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ hs,
+                                                    const __nv_bfloat16* __restrict__ h2, const float* __restrict__ wc,
+                                                    const float* __restrict__ bc, const float* __restrict__ wb,
+                                                    const float* __restrict__ bb, float* __restrict__ logits,
+                                                    float* __restrict__ boxes, int rows) {
+  __shared__ float w[6][GATE_D];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 2 * GATE_D; i += 256) w[i / GATE_D][i % GATE_D] = wc[i];
+  for (int i = tid; i < 4 * GATE_D; i += 256) w[2 + i / GATE_D][i % GATE_D] = wb[i];
+  __syncthreads();
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const uint4 qa = __ldg(reinterpret_cast<const uint4*>(hs + static_cast<size_t>(row) * GATE_D) + lane);
+  const uint4 qb = __ldg(reinterpret_cast<const uint4*>(h2 + static_cast<size_t>(row) * GATE_D) + lane);
+  const float a[8] = {bf16_lo(qa.x), bf16_hi(qa.x), bf16_lo(qa.y), bf16_hi(qa.y), bf16_lo(qa.z), bf16_hi(qa.z), bf16_lo(qa.w), bf16_hi(qa.w)};
+  const float c[8] = {bf16_lo(qb.x), bf16_hi(qb.x), bf16_lo(qb.y), bf16_hi(qb.y), bf16_lo(qb.z), bf16_hi(qb.z), bf16_lo(qb.w), bf16_hi(qb.w)};
+  float acc[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(j < 2 ? a[i] : c[i], w[j][lane * 8 + i], s);
+    acc[j] = warp_sum(s);
+  }
+  if (lane == 0) {
+    logits[static_cast<size_t>(row) * 2 + 0] = acc[0] + bc[0];
+    logits[static_cast<size_t>(row) * 2 + 1] = acc[1] + bc[1];
+    float4 o;
+    o.x = 1.f / (1.f + expf(-(acc[2] + bb[0]))); o.y = 1.f / (1.f + expf(-(acc[3] + bb[1])));
+    o.z = 1.f / (1.f + expf(-(acc[4] + bb[2]))); o.w = 1.f / (1.f + expf(-(acc[5] + bb[3])));
+    reinterpret_cast<float4*>(boxes)[row] = o;
+  }
+}
+
+int launch_heads(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const float* bc, const float* wb,
+                 const float* bb, float* logits, float* boxes, int rows, int d, cudaStream_t stream) {
+  if (d != GATE_D || rows <= 0) return svol_fail(SVOL_ERR_SHAPE, "heads: hidden_dim 256 only");
+  heads_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hs),
+                                                   reinterpret_cast<const __nv_bfloat16*>(h2), wc, bc, wb, bb, logits,
+                                                   boxes, rows);
+  return svol_check_launch("heads");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inference post-processing (test.py:133-158): one CTA per (video, frame)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) postprocess_kernel(const float* __restrict__ logits,
+                                                          const float* __restrict__ boxes, float* __restrict__ out,
+                                                          int32_t* __restrict__ order, int Q, int qf) {
+  extern __shared__ float sc[];   // qf scores
+  const int frame = blockIdx.x, b = blockIdx.y;
+  const size_t base = static_cast<size_t>(b) * Q + static_cast<size_t>(frame) * qf;
+  for (int i = threadIdx.x; i < qf; i += blockDim.x) {
+    const float l0 = logits[(base + i) * 2], l1 = logits[(base + i) * 2 + 1];
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+    sc[i] = __fdiv_rn(e0, __fadd_rn(e0, e1));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < qf; i += blockDim.x) {
+    const float s = sc[i];
+    int rank = 0;
+    for (int j = 0; j < qf; ++j) rank += (sc[j] > s) || (sc[j] == s && j < i);   // stable, descending
+    const float4 bx = reinterpret_cast<const float4*>(boxes)[base + i];
+    const float hw = __fmul_rn(0.5f, bx.z), hh = __fmul_rn(0.5f, bx.w);
+    float* o = out + (base + rank) * 5;
+    o[0] = fminf(fmaxf(__fsub_rn(bx.x, hw), 0.f), 1.f);
+    o[1] = fminf(fmaxf(__fsub_rn(bx.y, hh), 0.f), 1.f);
+    o[2] = fminf(fmaxf(__fadd_rn(bx.x, hw), 0.f), 1.f);
+    o[3] = fminf(fmaxf(__fadd_rn(bx.y, hh), 0.f), 1.f);
+    o[4] = s;
+    order[base + rank] = i;
+  }
+}
+
+int launch_postprocess(const float* logits, const float* boxes, float* out, int32_t* order, int B, int Q, int qf,
+                       cudaStream_t stream) {
+  if (B <= 0 || Q <= 0 || qf <= 0 || Q % qf != 0 || qf > 8192) return svol_fail(SVOL_ERR_SHAPE, "postprocess: Q % q_per_frame == 0");
+  postprocess_kernel<<<dim3(Q / qf, B), 128, qf * sizeof(float), stream>>>(logits, boxes, out, order, Q, qf);
+  return svol_check_launch("postprocess");
+}
+
+}  // namespace svol

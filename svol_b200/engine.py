@@ -1,0 +1,356 @@
+"""Launch plan of the SVANet head forward on the CUDA C ABI.
+
+``HeadEngine`` turns one ``SVANet`` module (reference-compatible parameters, see
+``svol_b200/modeling/svanet.py``) into a static sequence of ``libsvol_b200.so`` calls:
+
+  * weights are packed once into engine-owned bf16 / fp32 buffers (q rows pre-scaled by
+    log2(e)/sqrt(d_head) so the attention softmax is a bare ex2) and re-packed when a parameter's
+    version counter or storage changes;
+  * activations live in a per-(batch, video length) workspace whose addresses never change, so the
+    whole forward can be captured in one CUDA graph and replayed (``use_graph=True``);
+  * activations are batch-major ``[B*L, 256]`` bf16 row matrices; attention V operands are stored
+    transposed per head (``[B*8*32, L_pad]``) directly by the projection GEMM's epilogue.
+
+PyTorch is used for memory, streams and graph capture only -- every arithmetic step of the forward
+is a kernel of this repository.  Reference call order: ``SVANet.forward`` (lib/modeling/svanet.py:65-141)
+-> ``CrossModalTransformer.forward`` (lib/modeling/cross_modal_transformer.py:27-81) ->
+``CrossModalTransformerLayer.forward`` (:105-160).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, AttnArgs, GemmArgs
+
+LN_EPS = 1e-5
+HEAD_DIM = 32
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class _Plan:
+    """A recorded list of C-ABI calls plus the buffers they touch."""
+
+    def __init__(self):
+        self.calls: List[Tuple[str, object, tuple]] = []
+        self.ln_in_index = 0
+        self.keep: List[object] = []        # ctypes structs must outlive the plan
+        self.buf: Dict[str, torch.Tensor] = {}
+        self.graph = None
+
+    def run(self, stream: int) -> None:
+        for name, fn, args in self.calls:
+            rc = fn(*args, stream)
+            if rc != 0:
+                _lib.check(rc, name)
+
+
+class HeadEngine:
+    def __init__(self, module, use_graph: bool = False):
+        self.module = module
+        self.use_graph = use_graph
+        self.plain = os.environ.get("SVOL_B200_PLAIN", "0") == "1"   # debug: SIMT kernels instead of tcgen05
+        self._w: Dict[str, torch.Tensor] = {}
+        self._wstate = None
+        self._plans: Dict[Tuple[int, int, int], _Plan] = {}
+        self.launches_per_forward = 0
+
+    # ------------------------------------------------------------------ weights
+    def _param_state(self):
+        return tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+
+    @torch.no_grad()
+    def _pack_weights(self) -> None:
+        m = self.module
+        dev = next(m.parameters()).device
+        d = m.transformer.d_model
+        if d != 256 or m.transformer.nhead != 8:
+            raise NotImplementedError("svol_b200 kernels are built for hidden_dim 256 / 8 heads (head_dim 32)")
+        qscale = math.log2(math.e) / math.sqrt(HEAD_DIM)
+        new: Dict[str, torch.Tensor] = {}
+
+        def put(name, t, dtype):
+            t = t.detach().to(device=dev, dtype=dtype).contiguous()
+            old = self._w.get(name)
+            if old is not None and old.shape == t.shape and old.dtype == t.dtype and old.device == t.device:
+                old.copy_(t)            # keep the address: plans and graphs stay valid
+                new[name] = old
+            else:
+                new[name] = t.clone()
+                self._plans.clear()
+
+        bf, f32 = torch.bfloat16, torch.float32
+        for which in ("video", "sketch"):
+            seq = getattr(m, f"input_{which}_proj")
+            for i, lin in enumerate(seq):
+                put(f"in_{which}.{i}.ln_w", lin.LayerNorm.weight, f32)
+                put(f"in_{which}.{i}.ln_b", lin.LayerNorm.bias, f32)
+                put(f"in_{which}.{i}.w", lin.net[1].weight, bf if which == "video" else f32)
+                put(f"in_{which}.{i}.b", lin.net[1].bias, f32)
+        put("query_embed", m.query_embed.weight, f32)
+        for li, layer in enumerate(m.transformer.layers):
+            p = f"l{li}."
+            g = layer.sketch_video_cross_attn
+            put(p + "gate.w", g.in_proj_weight, f32)
+            put(p + "gate.b", g.in_proj_bias, f32)
+            for tag, att in (("sa", layer.content_self_attn), ("ta", layer.token_self_attn)):
+                W, b = att.in_proj_weight, att.in_proj_bias
+                put(p + tag + ".wqk", torch.cat([W[:d] * qscale, W[d:2 * d]]), bf)
+                put(p + tag + ".bqk", torch.cat([b[:d] * qscale, b[d:2 * d]]), f32)
+                put(p + tag + ".wv", W[2 * d:], bf)
+                put(p + tag + ".bv", b[2 * d:], f32)
+                put(p + tag + ".wo", att.out_proj.weight, bf)
+                put(p + tag + ".bo", att.out_proj.bias, f32)
+            ca = layer.content_token_cross_attn
+            W, b = ca.in_proj_weight, ca.in_proj_bias
+            put(p + "ca.wq", W[:d] * qscale, bf)
+            put(p + "ca.bq", b[:d] * qscale, f32)
+            put(p + "ca.wk", W[d:2 * d], bf)
+            put(p + "ca.bk", b[d:2 * d], f32)
+            put(p + "ca.wv", W[2 * d:], bf)
+            put(p + "ca.bv", b[2 * d:], f32)
+            put(p + "ca.wo", ca.out_proj.weight, bf)
+            put(p + "ca.bo", ca.out_proj.bias, f32)
+            for n in range(1, 7):
+                norm = getattr(layer, f"norm{n}")
+                put(p + f"n{n}.w", norm.weight, f32)
+                put(p + f"n{n}.b", norm.bias, f32)
+            for tag, mlp in (("mlp1", layer.mlp1), ("mlp2", layer.mlp2)):
+                put(p + tag + ".w1", mlp.fc1.weight, bf)
+                put(p + tag + ".b1", mlp.fc1.bias, f32)
+                put(p + tag + ".w2", mlp.fc2.weight, bf)
+                put(p + tag + ".b2", mlp.fc2.bias, f32)
+        for i in range(2):
+            put(f"box.{i}.w", m.bbox_embed.layers[i].weight, bf)
+            put(f"box.{i}.b", m.bbox_embed.layers[i].bias, f32)
+        put("box.2.w", m.bbox_embed.layers[2].weight, f32)
+        put("box.2.b", m.bbox_embed.layers[2].bias, f32)
+        put("cls.w", m.class_embed.weight, f32)
+        put("cls.b", m.class_embed.bias, f32)
+        self._w = new
+
+    def _weights(self) -> Dict[str, torch.Tensor]:
+        st = self._param_state()
+        if st != self._wstate:
+            self._pack_weights()
+            self._wstate = st
+        return self._w
+
+    # ------------------------------------------------------------------ plan
+    def _build_plan(self, B: int, L: int, d_in: int) -> _Plan:
+        m, w = self.module, self._w
+        lib = _lib.get_lib()
+        dev = w["cls.w"].device
+        d, H, ff = 256, 8, m.transformer.layers[0].mlp1.fc1.weight.shape[0]
+        Q = m.num_queries
+        NL = len(m.transformer.layers)
+        n_proj = len(m.input_video_proj)
+        d_sk = m.input_sketch_proj[0].net[1].weight.shape[1]
+        M, MQ = B * L, B * Q
+        Lp, Qp = _round_up(L, 8), _round_up(Q, 8)
+        plan = _Plan()
+        bf, f32 = torch.bfloat16, torch.float32
+
+        def buf(name, shape, dtype, zero=False):
+            t = (torch.zeros if zero else torch.empty)(shape, device=dev, dtype=dtype)
+            plan.buf[name] = t
+            return t
+
+        # inputs (static addresses; HeadEngine.forward copies the caller's tensors in)
+        x_in = buf("src_video", (B, L, d_in), f32)
+        s_in = buf("src_sketch", (B, d_sk), f32)
+        vmask = buf("src_video_mask", (B, L), f32)
+        # activations
+        xn = buf("xn", (M, d_in), bf)
+        ha, hb = buf("ha", (M, d), bf), buf("hb", (M, d), bf)
+        pos = buf("pos", (M, d), f32)
+        X, Xp = buf("X", (M, d), bf), buf("Xp", (M, d), bf)
+        mem, memp = buf("mem", (M, d), bf), buf("memp", (M, d), bf)
+        mem2 = buf("mem2", (M, d), bf)
+        qk = buf("qk", (M, 2 * d), bf)
+        vt = buf("vt", (B * d, Lp), bf, zero=True)
+        att = buf("att", (M, d), bf)
+        hid = buf("hid", (M, ff), bf)
+        sk_a, sk_b = buf("sk_a", (B, d), f32), buf("sk_b", (B, d), f32)
+        u = buf("u", (B, H, d), f32)
+        scores = buf("scores", (B, H, L), f32)
+        zeros_q = buf("zeros_q", (MQ, d), bf, zero=True)
+        qe_bf = buf("qe_bf", (MQ, d), bf)
+        o1, o1p = buf("o1", (MQ, d), bf), buf("o1p", (MQ, d), bf)
+        o2 = buf("o2", (MQ, d), bf)
+        outp = buf("outp", (MQ, d), bf)
+        qkq = buf("qkq", (MQ, 2 * d), bf)
+        vtq = buf("vtq", (B * d, Qp), bf, zero=True)
+        attq = buf("attq", (MQ, d), bf)
+        qc = buf("qc", (MQ, d), bf)
+        kc = buf("kc", (M, d), bf)
+        hidq = buf("hidq", (MQ, ff), bf)
+        hs = buf("hs", (NL, MQ, d), bf)
+        h1, h2 = buf("h1", (NL * MQ, d), bf), buf("h2", (NL * MQ, d), bf)
+        logits = buf("logits", (NL, B, Q, 2), f32)
+        boxes = buf("boxes", (NL, B, Q, 4), f32)
+
+        P = _lib.ptr
+        gemm_fn = lib.svol_gemm_bf16_plain if self.plain else lib.svol_gemm_bf16
+        attn_fn = lib.svol_attention_bf16_plain if self.plain else lib.svol_attention_bf16
+
+        def gemm(name, A, W, bias, out=None, act=ACT_NONE, residual=None, ln=None, out_pos=None, pos_t=None,
+                 pos_mod=0, out_vt=None, vt_len=0, vt_pitch=0):
+            a = GemmArgs()
+            a.A, a.W = P(A), P(W)
+            a.M, a.K = A.shape
+            a.N = W.shape[0]
+            assert W.shape[1] == a.K
+            a.lda, a.ldw = A.stride(0), W.stride(0)
+            e = a.ep
+            e.bias, e.act = P(bias), act
+            e.residual, e.ld_res = P(residual), (residual.stride(0) if residual is not None else 0)
+            if ln is not None:
+                e.ln_weight, e.ln_bias, e.ln_eps = P(ln[0]), P(ln[1]), LN_EPS
+            e.out = P(out)
+            e.out_pos = P(out_pos)
+            ld_o = out.stride(0) if out is not None else (out_pos.stride(0) if out_pos is not None else 0)
+            e.ld_out = ld_o
+            if out_pos is not None:
+                e.pos, e.ld_pos, e.pos_row_mod = P(pos_t), pos_t.stride(0), pos_mod
+            if out_vt is not None:
+                e.out_vt, e.vt_len, e.vt_pitch = P(out_vt), vt_len, vt_pitch
+            plan.keep.append(a)
+            plan.calls.append((name, gemm_fn, (C.byref(a),)))
+
+        def attention(name, q, k, vt_t, out, Lq, Lk, ldq, ldk, pitch, mask=None):
+            a = AttnArgs()
+            a.q, a.k, a.vt, a.key_mask, a.out = P(q), P(k), P(vt_t), P(mask), P(out)
+            a.B, a.H, a.Lq, a.Lk, a.ldq, a.ldk, a.ldo, a.vt_pitch = B, H, Lq, Lk, ldq, ldk, out.stride(0), pitch
+            plan.keep.append(a)
+            plan.calls.append((name, attn_fn, (C.byref(a),)))
+
+        def call(name, fn, *args):
+            plan.calls.append((name, fn, args))
+
+        # ---- input projection of the frame tokens (svanet.py:49-55,83): LN -> Linear -> ReLU -> LN -> Linear
+        plan.ln_in_index = len(plan.calls)
+        call("ln_in", lib.svol_layernorm_f32_to_bf16, P(x_in), P(w["in_video.0.ln_w"]), P(w["in_video.0.ln_b"]), P(xn),
+             M, d_in, LN_EPS)
+        call("posenc", lib.svol_posenc_sine, P(vmask), P(pos), B, L, d)
+        cur = xn
+        for i in range(n_proj):
+            last = i == n_proj - 1
+            dst = X if last else (ha if cur is not ha else hb)
+            gemm(f"in_proj{i}", cur, w[f"in_video.{i}.w"], w[f"in_video.{i}.b"], out=dst,
+                 act=ACT_NONE if last else ACT_RELU,
+                 ln=None if last else (w[f"in_video.{i + 1}.ln_w"], w[f"in_video.{i + 1}.ln_b"]),
+                 out_pos=Xp if last else None, pos_t=pos if last else None)
+            cur = dst
+        # ---- sketch branch (svanet.py:56-60,87), fp32, B rows
+        s_cur = s_in
+        for i in range(n_proj):
+            s_dst = sk_a if s_cur is not sk_a else sk_b
+            dim_in = d_sk if i == 0 else d
+            call(f"sk_proj{i}", lib.svol_ln_linear_f32, P(s_cur), P(w[f"in_sketch.{i}.ln_w"]), P(w[f"in_sketch.{i}.ln_b"]),
+                 P(w[f"in_sketch.{i}.w"]), P(w[f"in_sketch.{i}.b"]), 0 if i == n_proj - 1 else 1, P(s_dst), B, dim_in, d,
+                 LN_EPS)
+            s_cur = s_dst
+        # ---- query side: out0 = 0, q/k operand = query_embed broadcast (cross_modal_transformer.py:52-56)
+        call("qe_bcast", lib.svol_add_pos_bf16, P(w["query_embed"]), None, P(qe_bf), MQ, d, Q)
+        out_cur, outp_cur = zeros_q, qe_bf
+        x_cur, xp_cur = X, Xp
+        for li in range(NL):
+            p = f"l{li}."
+            # (a) sketch-conditioned gate + norm1                                        :122-127
+            call(p + "gate_vec", lib.svol_gate_vectors, P(s_cur), P(w[p + "gate.w"]), P(w[p + "gate.b"]), P(u), B, d, H)
+            call(p + "gate_scores", lib.svol_gate_scores, P(xp_cur), P(u), P(scores), B, L, d, H)
+            call(p + "gate_apply", lib.svol_gate_apply, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]), P(pos),
+                 P(mem), P(memp), None, B, L, d, H, LN_EPS)
+            # (b) video self-attention + norm2, FFN + norm3                               :137-143
+            gemm(p + "sa_qk", memp, w[p + "sa.wqk"], w[p + "sa.bqk"], out=qk)
+            gemm(p + "sa_v", mem, w[p + "sa.wv"], w[p + "sa.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)
+            attention(p + "sa_attn", qk, qk[:, d:], vt, att, L, L, 2 * d, 2 * d, Lp)
+            gemm(p + "sa_out", att, w[p + "sa.wo"], w[p + "sa.bo"], out=mem2, residual=mem, ln=(w[p + "n2.w"], w[p + "n2.b"]))
+            gemm(p + "ffn1_up", mem2, w[p + "mlp1.w1"], w[p + "mlp1.b1"], out=hid, act=ACT_GELU)
+            gemm(p + "ffn1_down", hid, w[p + "mlp1.w2"], w[p + "mlp1.b2"], out=X, residual=mem2,
+                 ln=(w[p + "n3.w"], w[p + "n3.b"]), out_pos=Xp, pos_t=pos)
+            x_cur, xp_cur = X, Xp            # layer output mem (and mem + pos)
+            # (c) query self-attention + norm4                                            :145-149
+            gemm(p + "ta_qk", outp_cur, w[p + "ta.wqk"], w[p + "ta.bqk"], out=qkq)
+            gemm(p + "ta_v", out_cur, w[p + "ta.wv"], w[p + "ta.bv"], out_vt=vtq, vt_len=Q, vt_pitch=Qp)
+            attention(p + "ta_attn", qkq, qkq[:, d:], vtq, attq, Q, Q, 2 * d, 2 * d, Qp)
+            gemm(p + "ta_out", attq, w[p + "ta.wo"], w[p + "ta.bo"], out=o1, residual=out_cur,
+                 ln=(w[p + "n4.w"], w[p + "n4.b"]), out_pos=o1p, pos_t=w["query_embed"], pos_mod=Q)
+            # (d) query -> video cross-attention (padded keys masked) + norm5, FFN + norm6 :151-158
+            gemm(p + "ca_q", o1p, w[p + "ca.wq"], w[p + "ca.bq"], out=qc)
+            gemm(p + "ca_k", Xp, w[p + "ca.wk"], w[p + "ca.bk"], out=kc)
+            gemm(p + "ca_v", X, w[p + "ca.wv"], w[p + "ca.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)
+            attention(p + "ca_attn", qc, kc, vt, attq, Q, L, d, d, Lp, mask=vmask)
+            gemm(p + "ca_out", attq, w[p + "ca.wo"], w[p + "ca.bo"], out=o2, residual=o1, ln=(w[p + "n5.w"], w[p + "n5.b"]))
+            gemm(p + "ffn2_up", o2, w[p + "mlp2.w1"], w[p + "mlp2.b1"], out=hidq, act=ACT_GELU)
+            gemm(p + "ffn2_down", hidq, w[p + "mlp2.w2"], w[p + "mlp2.b2"], out=hs[li], residual=o2,
+                 ln=(w[p + "n6.w"], w[p + "n6.b"]), out_pos=outp, pos_t=w["query_embed"], pos_mod=Q)
+            out_cur, outp_cur = hs[li], outp
+        # ---- heads on every layer's queries (svanet.py:125-127)
+        hs_all = hs.view(NL * MQ, d)
+        gemm("box0", hs_all, w["box.0.w"], w["box.0.b"], out=h1, act=ACT_RELU)
+        gemm("box1", h1, w["box.1.w"], w["box.1.b"], out=h2, act=ACT_RELU)
+        call("heads", lib.svol_heads, P(hs_all), P(h2), P(w["cls.w"]), P(w["cls.b"]), P(w["box.2.w"]), P(w["box.2.b"]),
+             P(logits), P(boxes), NL * MQ, d)
+        return plan
+
+    # ------------------------------------------------------------------ run
+    def plan_for(self, B: int, L: int, d_in: int) -> _Plan:
+        self._weights()
+        key = (B, L, d_in)
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._build_plan(B, L, d_in)
+            self._plans[key] = plan
+        self.launches_per_forward = len(plan.calls)
+        return plan
+
+    @torch.no_grad()
+    def forward(self, src_sketch, src_sketch_mask, src_video, src_video_mask):
+        """Returns (logits [NL,B,Q,2], boxes [NL,B,Q,4]) fp32, views of the plan's static output buffers
+        (overwritten by the next forward of the same shape)."""
+        _lib.require_device()
+        B, L, d_in = src_video.shape
+        plan = self.plan_for(B, L, d_in)
+        b = plan.buf
+        if src_video.data_ptr() != b["src_video"].data_ptr():
+            if (not self.use_graph and src_video.is_cuda and src_video.dtype == torch.float32
+                    and src_video.is_contiguous() and src_video.data_ptr() % 16 == 0):
+                # zero-copy: point the first kernel (LayerNorm of the frame tokens) at the caller's tensor
+                name, fn, args = plan.calls[plan.ln_in_index]
+                plan.calls[plan.ln_in_index] = (name, fn, (src_video.data_ptr(),) + tuple(args[1:]))
+            else:
+                b["src_video"].copy_(src_video, non_blocking=True)
+                name, fn, args = plan.calls[plan.ln_in_index]
+                plan.calls[plan.ln_in_index] = (name, fn, (b["src_video"].data_ptr(),) + tuple(args[1:]))
+        if src_sketch.data_ptr() != b["src_sketch"].data_ptr():
+            if src_sketch.dim() == 3 and src_sketch.shape[1] != 1:
+                raise NotImplementedError("svol_b200 supports one sketch token per pair (L_sketch == 1)")
+            b["src_sketch"].copy_(src_sketch.reshape(B, -1), non_blocking=True)
+        if src_video_mask.data_ptr() != b["src_video_mask"].data_ptr():
+            b["src_video_mask"].copy_(src_video_mask, non_blocking=True)
+        self.run_plan(plan)
+        return b["logits"], b["boxes"]
+
+    def run_plan(self, plan: _Plan) -> None:
+        if self.use_graph:
+            if plan.graph is None:
+                # warm-up run outside capture (sets function attributes, loads modules)
+                plan.run(torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    plan.run(torch.cuda.current_stream().cuda_stream)
+                plan.graph = g
+            plan.graph.replay()
+        else:
+            plan.run(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,127 @@
+"""Functional wrappers over the C ABI (one Python function per ``svol_*`` entry point that takes
+torch CUDA tensors).  The launch plan in ``engine.py`` records the same calls with pre-built argument
+structures; these wrappers are the convenient form for tests, notebooks and one-off use."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU  # noqa: F401  (re-exported)
+
+_P = _lib.ptr
+
+
+def gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+         residual: Optional[torch.Tensor] = None, ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+         pos: Optional[torch.Tensor] = None, pos_mod: int = 0, want_out: bool = True, vt_len: int = 0,
+         plain: bool = False, eps: float = 1e-5):
+    """out = epilogue(A @ W.T).  A [M,K] bf16, W [N,K] bf16.  Returns a dict with 'out' [M,N] bf16,
+    'out_pos' (when ``pos`` is given) and 'out_vt' [(M/vt_len)*N, round_up(vt_len,8)] (when ``vt_len``)."""
+    _lib.require_device()
+    lib = _lib.get_lib()
+    M, K = A.shape
+    N = W.shape[0]
+    res = {}
+    a = _lib.GemmArgs()
+    a.A, a.W, a.M, a.N, a.K, a.lda, a.ldw = _P(A), _P(W), M, N, K, A.stride(0), W.stride(0)
+    e = a.ep
+    e.bias, e.act = _P(bias), act
+    if residual is not None:
+        e.residual, e.ld_res = _P(residual), residual.stride(0)
+    if ln is not None:
+        e.ln_weight, e.ln_bias, e.ln_eps = _P(ln[0]), _P(ln[1]), eps
+    e.ld_out = N
+    if want_out:
+        res["out"] = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
+        e.out = _P(res["out"])
+    if pos is not None:
+        res["out_pos"] = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
+        e.out_pos, e.pos, e.ld_pos, e.pos_row_mod = _P(res["out_pos"]), _P(pos), pos.stride(0), pos_mod
+    if vt_len:
+        pitch = (vt_len + 7) // 8 * 8
+        res["out_vt"] = torch.zeros(((M // vt_len) * N, pitch), device=A.device, dtype=torch.bfloat16)
+        e.out_vt, e.vt_len, e.vt_pitch = _P(res["out_vt"]), vt_len, pitch
+    fn = lib.svol_gemm_bf16_plain if plain else lib.svol_gemm_bf16
+    _lib.check(fn(C.byref(a), _lib.stream_ptr()), "gemm")
+    return res
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, B: int, H: int, Lq: int, Lk: int,
+              key_mask: Optional[torch.Tensor] = None, plain: bool = False) -> torch.Tensor:
+    """q [B*Lq, >=H*32] (pre-scaled by log2(e)/sqrt(32)), k [B*Lk, >=H*32], vt [B*H*32, pitch] bf16."""
+    _lib.require_device()
+    lib = _lib.get_lib()
+    out = torch.empty((B * Lq, H * 32), device=q.device, dtype=torch.bfloat16)
+    a = _lib.AttnArgs()
+    a.q, a.k, a.vt, a.key_mask, a.out = _P(q), _P(k), _P(vt), _P(key_mask), _P(out)
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.ldq, a.ldk, a.ldo, a.vt_pitch = q.stride(0), k.stride(0), out.stride(0), vt.stride(0)
+    fn = lib.svol_attention_bf16_plain if plain else lib.svol_attention_bf16
+    _lib.check(fn(C.byref(a), _lib.stream_ptr()), "attention")
+    return out
+
+
+def layernorm_to_bf16(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    _lib.require_device()
+    rows, cols = x.shape
+    y = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.get_lib().svol_layernorm_f32_to_bf16(_P(x), _P(w), _P(b), _P(y), rows, cols, eps, _lib.stream_ptr()),
+               "layernorm")
+    return y
+
+
+def ln_linear_f32(x, ln_w, ln_b, w, b, relu: bool, eps: float = 1e-5) -> torch.Tensor:
+    _lib.require_device()
+    rows, in_dim = x.shape
+    out_dim = w.shape[0]
+    y = torch.empty((rows, out_dim), device=x.device, dtype=torch.float32)
+    _lib.check(_lib.get_lib().svol_ln_linear_f32(_P(x), _P(ln_w), _P(ln_b), _P(w), _P(b), int(relu), _P(y), rows, in_dim,
+                                                 out_dim, eps, _lib.stream_ptr()), "ln_linear")
+    return y
+
+
+def posenc_sine(mask: torch.Tensor, d: int) -> torch.Tensor:
+    _lib.require_device()
+    B, L = mask.shape
+    pos = torch.empty((B, L, d), device=mask.device, dtype=torch.float32)
+    _lib.check(_lib.get_lib().svol_posenc_sine(_P(mask), _P(pos), B, L, d, _lib.stream_ptr()), "posenc")
+    return pos
+
+
+def add_pos_bf16(x: torch.Tensor, pos: Optional[torch.Tensor], rows: int, mod: int = 0) -> torch.Tensor:
+    _lib.require_device()
+    cols = x.shape[-1]
+    out = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.get_lib().svol_add_pos_bf16(_P(x), _P(pos), _P(out), rows, cols, mod, _lib.stream_ptr()), "add_pos")
+    return out
+
+
+def gate(x: torch.Tensor, xpos: torch.Tensor, sketch: torch.Tensor, in_w: torch.Tensor, in_b: torch.Tensor,
+         ln_w: torch.Tensor, ln_b: torch.Tensor, pos: torch.Tensor, B: int, L: int, H: int = 8, eps: float = 1e-5):
+    """The three gate kernels in sequence.  Returns (mem, mem_pos, att [B,L], scores [B,H,L])."""
+    _lib.require_device()
+    lib = _lib.get_lib()
+    d = x.shape[-1]
+    s = _lib.stream_ptr()
+    u = torch.empty((B, H, d), device=x.device, dtype=torch.float32)
+    scores = torch.empty((B, H, L), device=x.device, dtype=torch.float32)
+    att = torch.empty((B, L), device=x.device, dtype=torch.float32)
+    mem, mem_pos = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(lib.svol_gate_vectors(_P(sketch), _P(in_w), _P(in_b), _P(u), B, d, H, s), "gate_vectors")
+    _lib.check(lib.svol_gate_scores(_P(xpos), _P(u), _P(scores), B, L, d, H, s), "gate_scores")
+    _lib.check(lib.svol_gate_apply(_P(x), _P(scores), _P(ln_w), _P(ln_b), _P(pos), _P(mem), _P(mem_pos), _P(att), B, L, d,
+                                   H, eps, s), "gate_apply")
+    return mem, mem_pos, att, scores
+
+
+def heads(hs: torch.Tensor, h2: torch.Tensor, wc, bc, wb, bb):
+    _lib.require_device()
+    rows, d = hs.shape
+    logits = torch.empty((rows, 2), device=hs.device, dtype=torch.float32)
+    boxes = torch.empty((rows, 4), device=hs.device, dtype=torch.float32)
+    _lib.check(_lib.get_lib().svol_heads(_P(hs), _P(h2), _P(wc), _P(bc), _P(wb), _P(bb), _P(logits), _P(boxes), rows, d,
+                                         _lib.stream_ptr()), "heads")
+    return logits, boxes

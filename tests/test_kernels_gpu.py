@@ -1,0 +1,240 @@
+"""GPU parity of the individual kernels, called through the C ABI (svol_b200.ops) and compared with
+the CPU oracle's functions on the same seeded inputs.  bf16 tolerances are stated per test: operands
+are rounded to bf16 on both sides, so what remains is fp32 accumulation order plus the bf16 rounding
+of the stored result (relative 2^-8) -- and, for attention, of the probabilities."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import svol_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+BF16_REL = 2.0 ** -8
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _bf16(x: np.ndarray) -> torch.Tensor:
+    return torch.from_numpy(x).to(torch.bfloat16)
+
+
+def _f(t: torch.Tensor) -> np.ndarray:
+    return t.detach().float().cpu().numpy()
+
+
+def _assert_close(got, ref, rel=BF16_REL, atol=2e-3, what=""):
+    err = np.abs(got - ref)
+    bound = rel * np.abs(ref) + atol
+    bad = err > bound
+    assert not bad.any(), f"{what}: {bad.sum()} / {bad.size} outside tolerance, max err {err.max():.4g} at ref {ref.flat[err.argmax()]:.4g}"
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+GEMM_CASES = [
+    # M, N, K, flags
+    (128, 256, 64, dict()),
+    (300, 256, 256, dict(bias=True)),
+    (1000, 512, 256, dict(bias=True)),
+    (517, 2048, 256, dict(bias=True, act="gelu")),
+    (640, 256, 2048, dict(bias=True, residual=True, ln=True, pos=True)),
+    (392, 256, 512, dict(bias=True, act="relu", ln=True)),
+    (3136, 256, 256, dict(bias=True, residual=True, ln=True, pos=True, pos_mod=320)),
+    (2 * 196, 256, 256, dict(bias=True, vt_len=196)),
+    (40000, 256, 256, dict(bias=True)),          # > 148 tiles: persistent loop, both TMEM stages, phase wrap
+]
+
+
+@pytest.mark.parametrize("plain", [False, True], ids=["tcgen05", "plain"])
+@pytest.mark.parametrize("M,N,K,flags", GEMM_CASES)
+def test_gemm_epilogues(M, N, K, flags, plain):
+    from svol_b200 import ops
+    if plain and M > 5000:
+        pytest.skip("plain kernel: small cases only")
+    rng = np.random.RandomState(M + N + K)
+    A = _bf16(rng.standard_normal((M, K)).astype(np.float32))
+    W = _bf16((rng.standard_normal((N, K)) / math.sqrt(K)).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32)) if flags.get("bias") else None
+    res_t = _bf16(rng.standard_normal((M, N)).astype(np.float32)) if flags.get("residual") else None
+    ln = None
+    if flags.get("ln"):
+        ln = (torch.from_numpy((1 + 0.1 * rng.standard_normal(N)).astype(np.float32)),
+              torch.from_numpy((0.1 * rng.standard_normal(N)).astype(np.float32)))
+    pos_mod = flags.get("pos_mod", 0)
+    pos = torch.from_numpy(rng.standard_normal((pos_mod or M, N)).astype(np.float32)) if flags.get("pos") else None
+    act = {"relu": ops.ACT_RELU, "gelu": ops.ACT_GELU}.get(flags.get("act"), ops.ACT_NONE)
+    vt_len = flags.get("vt_len", 0)
+
+    d = _dev()
+    cu = lambda t: None if t is None else t.to(d)
+    out = ops.gemm(cu(A), cu(W), cu(bias), act=act, residual=cu(res_t), ln=None if ln is None else (cu(ln[0]), cu(ln[1])),
+                   pos=cu(pos), pos_mod=pos_mod, vt_len=vt_len, plain=plain)
+    torch.cuda.synchronize()
+
+    ref = A.float().numpy() @ W.float().numpy().T
+    if bias is not None:
+        ref = ref + bias.numpy()
+    if flags.get("act") == "relu":
+        ref = np.maximum(ref, 0)
+    elif flags.get("act") == "gelu":
+        ref = orc.gelu(ref.astype(np.float32))
+    if res_t is not None:
+        ref = ref + res_t.float().numpy()
+    if ln is not None:
+        ref = orc.layer_norm(ref.astype(np.float32), ln[0].numpy(), ln[1].numpy())
+    _assert_close(_f(out["out"]), ref, what="out")
+    if pos is not None:
+        prow = np.arange(M) % pos_mod if pos_mod else np.arange(M)
+        _assert_close(_f(out["out_pos"]), ref + pos.numpy()[prow], what="out_pos")
+    if vt_len:
+        B = M // vt_len
+        vt = _f(out["out_vt"]).reshape(B, N, -1)
+        want = ref.reshape(B, vt_len, N).transpose(0, 2, 1)
+        _assert_close(vt[:, :, :vt_len], want, what="out_vt")
+        assert (vt[:, :, vt_len:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ attention
+ATTN_CASES = [
+    # B, Lq, Lk, masked
+    (1, 128, 128, False),
+    (2, 128, 256, False),
+    (2, 320, 320, False),       # query self-attention shape
+    (2, 200, 392, False),       # ragged tails on both sides
+    (2, 320, 1568, True),       # cross-attention with padded keys
+    (1, 1568, 1568, False),     # video self-attention shape
+]
+
+
+@pytest.mark.parametrize("plain", [False, True], ids=["tcgen05", "plain"])
+@pytest.mark.parametrize("B,Lq,Lk,masked", ATTN_CASES)
+def test_attention(B, Lq, Lk, masked, plain):
+    from svol_b200 import ops
+    H, dh = 8, 32
+    rng = np.random.RandomState(Lq * 7 + Lk)
+    scale = math.log2(math.e) / math.sqrt(dh)
+    q = _bf16((rng.standard_normal((B * Lq, H * dh)) * scale * 1.5).astype(np.float32))
+    k = _bf16(rng.standard_normal((B * Lk, H * dh)).astype(np.float32))
+    v = _bf16(rng.standard_normal((B * Lk, H * dh)).astype(np.float32))
+    pitch = (Lk + 7) // 8 * 8
+    vt = torch.zeros((B * H * dh, pitch), dtype=torch.bfloat16)
+    vt[:, :Lk] = v.view(B, Lk, H * dh).permute(0, 2, 1).reshape(B * H * dh, Lk)
+    mask = None
+    if masked:
+        mask = np.ones((B, Lk), np.float32)
+        mask[0, Lk - 300:] = 0
+        mask[1, Lk - 49:] = 0
+    d = _dev()
+    out = ops.attention(q.to(d), k.to(d), vt.to(d), B, H, Lq, Lk,
+                        key_mask=None if mask is None else torch.from_numpy(mask).to(d), plain=plain)
+    torch.cuda.synchronize()
+    qf = q.float().numpy().reshape(B, Lq, H, dh).transpose(0, 2, 1, 3)
+    kf = k.float().numpy().reshape(B, Lk, H, dh).transpose(0, 2, 1, 3)
+    vf = v.float().numpy().reshape(B, Lk, H, dh).transpose(0, 2, 1, 3)
+    s = (qf @ kf.transpose(0, 1, 3, 2)) * math.log(2.0)        # kernel works in base 2
+    if mask is not None:
+        s = np.where(mask[:, None, None, :] != 0, s, -np.inf)
+    ref = (orc.softmax(s.astype(np.float32)) @ vf).transpose(0, 2, 1, 3).reshape(B * Lq, H * dh)
+    got = _f(out)
+    err = np.abs(got - ref)
+    # probabilities are rounded to bf16 before P V (relative 2^-9 each) and the result to bf16
+    assert err.max() < 2.5e-2, f"max err {err.max()}"
+    assert err.mean() < 2.5e-3, f"mean err {err.mean()}"
+
+
+# ------------------------------------------------------------------------------------------ row-wise kernels
+@pytest.mark.parametrize("rows,cols", [(1000, 512), (77, 768), (64, 64), (5, 1024)])
+def test_layernorm_to_bf16(rows, cols):
+    from svol_b200 import ops
+    rng = np.random.RandomState(rows)
+    x = (rng.standard_normal((rows, cols)) * 2 + 0.5).astype(np.float32)
+    w = (1 + 0.1 * rng.standard_normal(cols)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(cols)).astype(np.float32)
+    d = _dev()
+    y = ops.layernorm_to_bf16(torch.from_numpy(x).to(d), torch.from_numpy(w).to(d), torch.from_numpy(b).to(d))
+    _assert_close(_f(y), orc.layer_norm(x, w, b), rel=2.0 ** -8, atol=1e-5, what="layernorm")
+
+
+def test_ln_linear_f32():
+    from svol_b200 import ops
+    rng = np.random.RandomState(3)
+    x = rng.standard_normal((7, 512)).astype(np.float32)
+    lw, lb = (1 + 0.1 * rng.standard_normal(512)).astype(np.float32), (0.1 * rng.standard_normal(512)).astype(np.float32)
+    w, b = (rng.standard_normal((256, 512)) / 22).astype(np.float32), rng.standard_normal(256).astype(np.float32)
+    d = _dev()
+    t = lambda a: torch.from_numpy(a).to(d)
+    for relu in (False, True):
+        y = _f(ops.ln_linear_f32(t(x), t(lw), t(lb), t(w), t(b), relu))
+        ref = orc.linear(orc.layer_norm(x, lw, lb), w, b)
+        ref = np.maximum(ref, 0) if relu else ref
+        assert np.abs(y - ref).max() < 2e-5
+
+
+@pytest.mark.parametrize("B,L", [(2, 1568), (3, 32), (2, 100)])
+def test_posenc_sine(B, L):
+    from svol_b200 import ops
+    mask = np.ones((B, L), np.float32)
+    mask[0, L - L // 5:] = 0
+    pos = _f(ops.posenc_sine(torch.from_numpy(mask).to(_dev()), 256))
+    ref = orc.position_embedding_sine(mask != 0, 256)
+    # sin/cos of arguments up to 2*pi: one fp32 ulp of the argument (4.8e-7) bounds the difference
+    assert np.abs(pos - ref).max() < 2e-6
+
+
+def test_add_pos_broadcast():
+    from svol_b200 import ops
+    rng = np.random.RandomState(0)
+    x = rng.standard_normal((320, 256)).astype(np.float32)
+    p = rng.standard_normal((320, 256)).astype(np.float32)
+    d = _dev()
+    y = _f(ops.add_pos_bf16(torch.from_numpy(x).to(d), None, 960, mod=320))
+    assert np.array_equal(y, np.tile(_f(_bf16(x)), (3, 1)))
+    y2 = _f(ops.add_pos_bf16(torch.from_numpy(x).to(d), torch.from_numpy(p).to(d), 640, mod=320))
+    assert np.array_equal(y2, np.tile(_f(_bf16(x + p)), (2, 1)))
+
+
+@pytest.mark.parametrize("B,L", [(2, 1568), (3, 70)])
+def test_gate(B, L):
+    """Sketch-conditioned gate vs the oracle's full multi-head attention weights (the CUDA path never
+    forms K; the key bias cancels in the softmax)."""
+    from svol_b200 import ops
+    rng = np.random.RandomState(L)
+    d_model, H = 256, 8
+    x = _bf16(rng.standard_normal((B, L, d_model)).astype(np.float32))
+    mask = np.ones((B, L), bool)
+    pos = orc.position_embedding_sine(mask, d_model)
+    xpos = _bf16(x.float().numpy() + pos)
+    skch = rng.standard_normal((B, d_model)).astype(np.float32)
+    in_w = (rng.standard_normal((3 * d_model, d_model)) * 0.08).astype(np.float32)
+    in_b = (rng.standard_normal(3 * d_model) * 0.05).astype(np.float32)
+    lw, lb = (1 + 0.1 * rng.standard_normal(d_model)).astype(np.float32), (0.1 * rng.standard_normal(d_model)).astype(np.float32)
+    dv = _dev()
+    t = lambda a: torch.from_numpy(a).to(dv)
+    mem, mem_pos, att, _ = ops.gate(x.reshape(B * L, d_model).to(dv), xpos.reshape(B * L, d_model).to(dv), t(skch), t(in_w),
+                                    t(in_b), t(lw), t(lb), t(pos.reshape(B * L, d_model)), B, L, H)
+    xf, xpf = x.float().numpy(), xpos.float().numpy()
+    _, att_ref = orc.multihead_attention(skch[:, None, :], xpf, xpf, in_w, in_b, np.eye(d_model, dtype=np.float32),
+                                         np.zeros(d_model, np.float32), H)
+    att_ref = att_ref[:, 0, :]
+    assert np.abs(_f(att) - att_ref).max() < 1e-3 * att_ref.max() + 1e-7
+    mem_ref = orc.layer_norm(xf + att_ref[..., None] * xf, lw, lb)
+    _assert_close(_f(mem).reshape(B, L, d_model), mem_ref, atol=1e-3, what="mem")
+    _assert_close(_f(mem_pos).reshape(B, L, d_model), mem_ref + pos, atol=2e-3, what="mem_pos")
+
+
+def test_heads():
+    from svol_b200 import ops
+    rng = np.random.RandomState(5)
+    rows = 1000
+    hs, h2 = _bf16(rng.standard_normal((rows, 256)).astype(np.float32)), _bf16(np.abs(rng.standard_normal((rows, 256))).astype(np.float32))
+    wc, bc = (rng.standard_normal((2, 256)) / 16).astype(np.float32), rng.standard_normal(2).astype(np.float32)
+    wb, bb = (rng.standard_normal((4, 256)) / 16).astype(np.float32), rng.standard_normal(4).astype(np.float32)
+    dv = _dev()
+    t = lambda a: torch.from_numpy(a).to(dv)
+    logits, boxes = ops.heads(hs.to(dv), h2.to(dv), t(wc), t(bc), t(wb), t(bb))
+    assert np.abs(_f(logits) - orc.linear(hs.float().numpy(), wc, bc)).max() < 1e-4
+    assert np.abs(_f(boxes) - orc.sigmoid(orc.linear(h2.float().numpy(), wb, bb))).max() < 1e-5

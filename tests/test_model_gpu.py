@@ -1,0 +1,133 @@
+"""GPU parity of the whole head (SVANet.forward on the launch plan) and of the forward -> match ->
+criterion chain, against the CPU oracle and the reference's golden outputs.
+
+Tolerances (north_star: 1e-3 relative for an fp32-accumulate path, "the bf16 path's tolerance is
+stated separately" -- this is the bf16 path): operands and stored activations are bf16 (relative
+rounding 2^-9 per element), accumulation, LayerNorm statistics, softmax and the heads are fp32.
+Through 2-4 transformer layers that gives absolute errors of a few 1e-2 on O(1) logits and of a few
+1e-3 on sigmoid boxes; the bounds below are ~3x the errors observed on these seeds."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import svol_oracle as orc
+from svol_b200 import synth
+from svol_b200.modeling import build_loss, build_svanet
+
+pytestmark = pytest.mark.gpu
+C = synth.CONFIGS
+DEV = "cuda:0"
+LOGIT_ATOL, BOX_ATOL = 6e-2, 1.5e-2
+
+
+def _model(cfg, seed, use_graph=False):
+    ns = cfg.to_namespace()
+    ns.use_cuda_graph = use_graph
+    m = build_svanet(ns)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.random_state_dict(cfg, seed).items()}, strict=True)
+    return m.to(DEV).eval()
+
+
+def _run(model, inp):
+    t = lambda k: torch.from_numpy(inp[k]).to(DEV)
+    with torch.no_grad():
+        out = model(t("src_sketch"), t("src_sketch_mask"), t("src_video"), t("src_video_mask"))
+    torch.cuda.synchronize()
+    logits = torch.stack([a["pred_logits"] for a in out["aux_outputs"]] + [out["pred_logits"]]).cpu().numpy()
+    boxes = torch.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]]).cpu().numpy()
+    return out, logits, boxes
+
+
+HEAD_CASES = [("tiny", "tiny", False), ("tiny_pad", "tiny", True), ("C1a", "C1a", False), ("C1b", "C1b", False),
+              ("C1b_pad", "C1b", True)]
+
+
+@pytest.mark.parametrize("case,cfgname,padded", HEAD_CASES)
+def test_head_forward_matches_reference_golden(golden_dir, case, cfgname, padded):
+    g = np.load(os.path.join(golden_dir, f"head_{case}.npz"))
+    cfg = C[cfgname]
+    batch, seed = int(g["batch"]), int(g["seed"])
+    inp = synth.make_inputs(cfg, batch, seed, padded=padded)
+    out, logits, boxes = _run(_model(cfg, seed), inp)
+    assert out["pred_logits"].shape == (batch, cfg.num_queries, 2) and out["pred_boxes"].shape == (batch, cfg.num_queries, 4)
+    assert len(out["aux_outputs"]) == cfg.num_layers - 1
+    el, eb = np.abs(logits - g["logits_f64"]), np.abs(boxes - g["boxes_f64"])
+    print(f"{case}: max |dlogit| {el.max():.4g} mean {el.mean():.4g}; max |dbox| {eb.max():.4g} mean {eb.mean():.4g}")
+    assert np.isfinite(logits).all() and np.isfinite(boxes).all()
+    assert el.max() < LOGIT_ATOL and eb.max() < BOX_ATOL
+    assert el.mean() < LOGIT_ATOL / 5 and eb.mean() < BOX_ATOL / 5
+
+
+def test_head_forward_plain_kernels_agree():
+    """Triangulation at the script config: tcgen05 path vs SIMT path on the same weights and inputs."""
+    cfg = C["C1b"]
+    inp = synth.make_inputs(cfg, 2, 3, padded=True)
+    m = _model(cfg, 3)
+    _, lg_tc, bx_tc = _run(m, inp)
+    m.engine.plain = True
+    m.engine._plans.clear()
+    _, lg_pl, bx_pl = _run(m, inp)
+    assert np.abs(lg_tc - lg_pl).max() < 3e-2 and np.abs(bx_tc - bx_pl).max() < 8e-3
+
+
+def test_cuda_graph_replay_is_identical():
+    cfg = C["C1b"]
+    inp = synth.make_inputs(cfg, 2, 5)
+    _, lg, bx = _run(_model(cfg, 5), inp)
+    mg = _model(cfg, 5, use_graph=True)
+    for _ in range(3):
+        _, lg_g, bx_g = _run(mg, inp)
+    assert np.array_equal(lg, lg_g) and np.array_equal(bx, bx_g)
+
+
+def test_forward_match_criterion_chain(golden_dir):
+    """forward -> PerFrameMatcher -> SetCriterion on the GPU vs the same chain in the oracle fed with the
+    GPU's own logits/boxes (isolates matcher+criterion: indices must be identical) and vs the reference's
+    end-to-end golden losses (forward error included: loose tolerance)."""
+    cfg = C["C1b"]
+    g = np.load(os.path.join(golden_dir, "crit_C1b_e2e.npz"))
+    inp = synth.make_inputs(cfg, 2, 0)
+    targets_np = synth.make_targets(cfg, 2, 0)
+    targets = synth.targets_to_torch(targets_np)
+    out, logits, boxes = _run(_model(cfg, 0), inp)
+    crit = build_loss(cfg.to_namespace()).to(DEV)
+    losses = {k: float(v) for k, v in crit(out, targets).items()}
+    crit.check_status()
+    ref_out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1],
+               "aux_outputs": [{"pred_logits": a, "pred_boxes": b} for a, b in zip(logits[:-1], boxes[:-1])]}
+    ref_losses, ref_idx = orc.set_criterion(ref_out, targets_np, cfg, return_indices=True)
+    n = cfg.num_layers
+    mismatched_frames = 0
+    for slot, idx in enumerate(ref_idx):
+        layer = n - 1 if slot == 0 else slot - 1
+        got = crit.indices(layer)
+        for (gp, gt), (rp, rt) in zip(got, idx):
+            if not (np.array_equal(gp.numpy(), rp) and np.array_equal(gt.numpy(), rt)):
+                mismatched_frames += 1
+    assert mismatched_frames == 0, f"{mismatched_frames} videos with differing assignments on identical inputs"
+    for k, v in ref_losses.items():
+        assert abs(losses[k] - float(v)) <= 2e-5 * max(1.0, abs(float(v))), k
+    for k in ("loss_bbox", "loss_giou", "loss_label"):
+        assert abs(losses[k] - float(g["loss/" + k])) < 0.05 * max(1.0, abs(float(g["loss/" + k]))), k
+
+
+@pytest.mark.parametrize("layers", [2, 4])
+def test_headline_config_full_size_properties(layers):
+    """BASELINE configs[1] at full size (B=32, L=1568, Q=320): too large for the numpy oracle in a unit
+    test, so check size-independent properties -- batch-permutation equivariance (pairs are
+    independent), agreement of each pair with its own batch-1 forward, finite outputs, boxes in (0,1)."""
+    cfg = C["C2"] if layers == 2 else C["C2n4"]
+    B = 32
+    inp = synth.make_inputs(cfg, B, 7, padded=True)
+    m = _model(cfg, 7)
+    _, lg, bx = _run(m, inp)
+    assert np.isfinite(lg).all() and (bx > 0).all() and (bx < 1).all()
+    perm = np.random.RandomState(0).permutation(B)
+    inp_p = {k: v[perm] for k, v in inp.items()}
+    _, lg_p, bx_p = _run(m, inp_p)
+    assert np.array_equal(lg_p, lg[:, perm]) and np.array_equal(bx_p, bx[:, perm])
+    one = {k: v[5:6] for k, v in inp.items()}
+    _, lg1, bx1 = _run(m, one)
+    assert np.abs(lg1[:, 0] - lg[:, 5]).max() < 2e-2 and np.abs(bx1[:, 0] - bx[:, 5]).max() < 5e-3
