@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""Benchmark of the SVOL hot path: sketch-video pairs/s for head forward + Hungarian matching + set
+criterion (BASELINE.json metric), on N GPUs of one node, one process per GPU.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5                       # this repo's CUDA path
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...                                 # the reference's CPU path (oracle port)
+
+One step = one pass of the hot path over one batch of B synthetic pairs per GPU (weak scaling,
+pairs are independent: no data-path collective).  Prints ONE JSON line on rank 0:
+
+  value        pairs/s, device-timed (CUDA events over exactly K steps, max over ranks), inputs and
+               flattened targets already resident in HBM
+  e2e          pairs/s through the public API with HOST inputs: every step copies the step's frame
+               features, sketch feature, masks and target boxes from pinned host memory, runs
+               forward + criterion, and reads the losses back
+  roofline     the dominant kernel of the step, timed live per launch with CUDA events
+  cpu_baseline the CPU oracle (numpy port of the reference path) on a bounded sample, rank 0, N=1
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "sketch-video pairs/s fwd+match"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step")
+    ap.add_argument("--layers", type=int, default=2)
+    ap.add_argument("--config", default="C2", help="svol_b200.synth.CONFIGS key (C2 = BASELINE configs[1])")
+    ap.add_argument("--graph", type=int, default=0, help="replay the forward as one CUDA graph")
+    ap.add_argument("--ref-batch", type=int, default=2, help="pairs per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default="", help="write the per-kernel time table to this file")
+    return ap.parse_args()
+
+
+def workload_config(args, cfg):
+    return {"workload": f"{args.config}: SVOL head forward + PerFrameMatcher + SetCriterion (all decoder layers), "
+                        f"B={args.batch} pairs/GPU, T={cfg.num_frames}, L={cfg.video_len}, D_in={cfg.input_vid_dim}, "
+                        f"Q={cfg.num_queries}, layers={cfg.num_layers}",
+            "pairs_per_gpu_per_step": args.batch, "layers": cfg.num_layers,
+            "l2": "two alternating input sets (2 x %.0f MB frame features) and a >1 GB per-step activation stream: "
+                  "no step finds its inputs in the 126 MB L2" % (args.batch * cfg.video_len * cfg.input_vid_dim * 4 / 1e6),
+            "parallelism": f"dp{args.gpus} (independent pairs, no collective)"}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_step_fn(cfg, batch, seed=0):
+    """One step of the reference's CPU path (the oracle port: numpy/BLAS on all host threads):
+    forward + matcher + criterion on `batch` pairs."""
+    from oracle import lsap, svol_oracle as orc
+    from svol_b200 import synth
+    try:
+        lsap.build()
+    except Exception:
+        pass
+    sd = synth.random_state_dict(cfg, seed)
+    inp = synth.make_inputs(cfg, batch, seed, padded=True)
+    targets = synth.make_targets(cfg, batch, seed, frame_mask=inp["frame_mask"])
+
+    def step():
+        out = orc.svanet_forward(sd, inp["src_sketch"], inp["src_sketch_mask"], inp["src_video"], inp["src_video_mask"],
+                                 nheads=cfg.nheads, dtype=np.float32)
+        return orc.set_criterion(out, targets, cfg)
+    return step
+
+
+def time_cpu(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    return (time.perf_counter() - t0) / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from svol_b200 import synth
+    from dataclasses import replace
+    cfg = replace(synth.CONFIGS[args.config], num_layers=args.layers)
+    b = args.ref_batch
+    step = cpu_reference_step_fn(cfg, b)
+    sec = time_cpu(step, args.steps, args.warmup)
+    value = b / sec
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {**workload_config(args, cfg), "pairs_per_step_cpu": b},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"{b} pairs per step x {args.steps} steps of the same workload "
+                                       f"(oracle port of the reference's CPU path, numpy/BLAS threads)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from dataclasses import replace
+    from svol_b200 import synth
+    from svol_b200.modeling import build_loss, build_svanet
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = replace(synth.CONFIGS[args.config], num_layers=args.layers)
+    B = args.batch
+    ns = cfg.to_namespace()
+    ns.use_cuda_graph = bool(args.graph)
+    model = build_svanet(ns)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.random_state_dict(cfg, 0).items()}, strict=True)
+    model = model.to(dev).eval()
+    criterion = build_loss(ns).to(dev)
+
+    # two alternating synthetic input sets per rank (different pairs on every rank)
+    sets = []
+    for s in range(2):
+        inp = synth.make_inputs(cfg, B, seed=100 * rank + s, padded=True)
+        tg = synth.targets_to_torch(synth.make_targets(cfg, B, seed=100 * rank + s, frame_mask=inp["frame_mask"]))
+        host = {k: torch.from_numpy(inp[k]).pin_memory() for k in ("src_sketch", "src_sketch_mask", "src_video", "src_video_mask")}
+        devt = {k: v.to(dev) for k, v in host.items()}
+        sets.append({"host": host, "dev": devt, "targets": tg})
+
+    def step_resident(i):
+        s = sets[i & 1]
+        d = s["dev"]
+        out = model(d["src_sketch"], d["src_sketch_mask"], d["src_video"], d["src_video_mask"])
+        return criterion(out, s["targets"])
+
+    stage = {k: torch.empty_like(v, device=dev) for k, v in sets[0]["host"].items()}
+    loss_host = torch.empty((cfg.num_layers, 4), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        s = sets[i & 1]
+        for k, v in s["host"].items():
+            stage[k].copy_(v, non_blocking=True)                       # H2D of this step's inputs
+        criterion.matcher._cache._key = None                           # targets are new every step: re-walk + H2D
+        out = model(stage["src_sketch"], stage["src_sketch_mask"], stage["src_video"], stage["src_video_mask"])
+        losses = criterion(out, s["targets"])
+        vals = torch.stack([losses[k] for k in losses])                # views of one [NL,4] tensor
+        loss_host.view(-1)[: vals.numel()].copy_(vals, non_blocking=True)  # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+        return loss_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for i in range(warmup):
+                fn(i)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                fn(i)
+            e1.record()
+            barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_step = timed(step_resident, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, 3)
+    with torch.no_grad():
+        step_resident(0)
+    criterion.check_status()
+
+    flat = criterion.last_indices[2]
+    h2d = sum(v.numel() * v.element_size() for v in sets[0]["host"].values()) + flat.tgt_boxes.numel() * 4 + \
+        (flat.tgt_off.numel() + flat.match_off.numel() + flat.video_tgt_off.numel() + flat.video_match_off.numel()
+         + flat.match_video.numel()) * 4 + flat.cost_off.numel() * 8
+    d2h = cfg.num_layers * 4 * 4
+    launches_per_step = model.engine.launches_per_forward + (3 if flat.per_frame else 2)
+
+    roofline, breakdown = None, None
+    cpu_baseline = None
+    if rank == 0:
+        roofline, breakdown = kernel_breakdown(model, sets[0], cfg, B, dev)
+        if args.breakdown:
+            with open(args.breakdown, "w") as f:
+                f.write(breakdown)
+        if world == 1 and not args.no_cpu_baseline:
+            b = args.ref_batch
+            sec = time_cpu(cpu_reference_step_fn(cfg, b), 4, 1)
+            cpu_baseline = {"value": b / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                            "sample": f"{b} pairs per step x 4 steps (1 warm-up) of the same workload, oracle port "
+                                      f"(numpy/BLAS, all host threads), {sec * 1e3:.0f} ms per step"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    pairs = B * world
+    line = {"metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, cfg),
+            "clocks": clocks,
+            "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "tflops_algorithmic": synth.algorithmic_flops_per_pair(cfg) * pairs / (ms_step * 1e-3) / 1e12}
+    print(json.dumps(line))
+
+
+def kernel_breakdown(model, inset, cfg, B, dev):
+    """Times every launch of the forward plan individually (CUDA events on the launching stream, 5 repeats
+    after a warm-up, median) and derives the roofline entry of the dominant kernel family."""
+    import torch
+    from svol_b200 import synth
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_src": "fallback"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks.update(json.load(open(pk)))
+        peaks["_src"] = "measured"
+    eng = model.engine
+    plan = eng.plan_for(B, cfg.video_len, cfg.input_vid_dim)
+    stream = torch.cuda.current_stream().cuda_stream
+    reps = 5
+    times = {}
+    with torch.no_grad():
+        plan.run(stream)
+        torch.cuda.synchronize()
+        for _ in range(reps):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(plan.calls) + 1)]
+            evs[0].record()
+            for i, (name, fn, a) in enumerate(plan.calls):
+                rc = fn(*a, stream)
+                assert rc == 0, name
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            for i, (name, _, _) in enumerate(plan.calls):
+                times.setdefault(name, []).append(evs[i].elapsed_time(evs[i + 1]))
+    med = {k: float(np.median(v)) for k, v in times.items()}
+    total = sum(med.values())
+    L, Q, d, ff, D = cfg.video_len, cfg.num_queries, cfg.hidden_dim, cfg.dim_feedforward, cfg.input_vid_dim
+    M, MQ, NL = B * L, B * Q, cfg.num_layers
+
+    def fam(name):
+        n = name.split(".")[-1]
+        return {"sa_attn": "attention(video self)", "ta_attn": "attention(query self)", "ca_attn": "attention(cross)",
+                "ffn1_up": "gemm ffn1_up+GELU", "ffn1_down": "gemm ffn1_down+res+LN", "ffn2_up": "gemm ffn2_up+GELU",
+                "ffn2_down": "gemm ffn2_down+res+LN"}.get(n, n)
+    flops = {"attention(video self)": 4.0 * L * L * d * B, "attention(query self)": 4.0 * Q * Q * d * B,
+             "attention(cross)": 4.0 * Q * L * d * B, "gemm ffn1_up+GELU": 2.0 * M * d * ff, "gemm ffn1_down+res+LN": 2.0 * M * d * ff,
+             "gemm ffn2_up+GELU": 2.0 * MQ * d * ff, "gemm ffn2_down+res+LN": 2.0 * MQ * d * ff,
+             "sa_qk": 2.0 * M * d * 2 * d, "sa_v": 2.0 * M * d * d, "sa_out": 2.0 * M * d * d, "in_proj0": 2.0 * M * D * d,
+             "in_proj1": 2.0 * M * d * d, "ca_k": 2.0 * M * d * d, "ca_v": 2.0 * M * d * d}
+    agg = {}
+    for name, t in med.items():
+        f = fam(name)
+        a = agg.setdefault(f, [0.0, 0])
+        a[0] += t
+        a[1] += 1
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][0])
+    lines = [f"per-kernel-family device time, B={B} L={L} layers={NL} (median of {reps}, CUDA events between launches)",
+             f"{'family':34s} {'launches':>8s} {'ms total':>10s} {'share':>7s} {'TFLOP/s':>9s}"]
+    for f, (t, n) in rows:
+        tf = flops.get(f, 0.0) * (n if f in flops else 0) / (t * 1e-3) / 1e12 if t > 0 else 0.0
+        lines.append(f"{f:34s} {n:8d} {t:10.4f} {100 * t / total:6.1f}% {tf:9.1f}")
+    lines.append(f"{'TOTAL':34s} {len(med):8d} {total:10.4f}")
+    top, (t_top, n_top) = rows[0]
+    per_launch_ms = t_top / n_top
+    if top in flops:
+        achieved = flops[top] / (per_launch_ms * 1e-3) / 1e12
+        peak = float(peaks["bf16_tflops_sustained"])
+        roof = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "ms_per_launch": per_launch_ms, "share_of_forward": t_top / total,
+                "peak_source": f"{peaks['_src']} bf16_tflops_sustained (kernel timed inside the step)",
+                "algorithmic_flops_per_launch": flops[top]}
+    else:
+        roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s", "frac": None,
+                "traffic": None, "ms_per_launch": per_launch_ms, "share_of_forward": t_top / total}
+    return roof, "\n".join(lines) + "\n"
+
+
+if __name__ == "__main__":
+    main()

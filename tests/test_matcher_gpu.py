@@ -109,7 +109,7 @@ def test_nan_cost_raises_like_scipy():
     cfg = C["tiny"]
     targets = synth.targets_to_torch(synth.make_targets(cfg, 2, 0))
     logits, boxes = synth.make_predictions(cfg, 2, 0, layers=1)
-    logits[0, 0, 0, 0] = np.nan
+    logits[0, :, :, 0] = np.nan          # every frame, so at least one frame with targets sees it
     m = build_matcher(cfg.to_namespace())
     with pytest.raises(ValueError, match="invalid numeric entries"):
         m({"pred_logits": torch.from_numpy(logits[0]).to(DEV), "pred_boxes": torch.from_numpy(boxes[0]).to(DEV)}, targets)
