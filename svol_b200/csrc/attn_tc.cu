@@ -4,16 +4,23 @@
 // lib/modeling/cross_modal_transformer.py:139 (video self-attention, L x L), :147 (query
 // self-attention, Q x Q) and :154 (query -> video cross-attention, Q x L, padded keys masked).
 // The reference materialises the (B*8, Lq, Lk) score tensor (2.5 GB at the headline config); here
-// scores only ever exist as one 128 x 128 fp32 tile in tensor memory.
+// scores only ever exist as 128 x 128 fp32 tiles in tensor memory.
 //
-// One CTA per (128-query tile, head, sample); 192 threads; two CTAs are co-resident per SM so one
-// CTA's softmax overlaps the other's MMAs:
-//   warps 0..3  softmax: thread = query row.  S tile TMEM -> registers (two passes: row max, then
-//               exp2), P tile -> shared memory as bf16 in the 128B-swizzled K-major layout the MMA
-//               reads, running max / sum / 32-wide output accumulator in registers.
-//   warp 4      TMA producer: Q tile once, then a 3-stage ring of K tiles (128 x 32, 64B swizzle)
-//               and V^T tiles (32 x 128, 128B swizzle).
-//   warp 5      MMA issuer: S = Q K^T (M128 N128 K32) and O_tile = P V (M128 N32 K128), fp32 in TMEM.
+// One CTA per (pair of 128-query tiles, head, sample), one CTA per SM, 384 threads (warps 10-11 idle, so
+// that setmaxnreg can move registers from the TMA/MMA warpgroup to the softmax warpgroups):
+//   warps 0..3  softmax warpgroup A: thread = query row of tile A
+//   warps 4..7  softmax warpgroup B: thread = query row of tile B
+//               per key tile: S tile TMEM -> 128 registers in ONE pass (the TMEM buffer is released
+//               to the MMA warp immediately, so the next QK^T overlaps this tile's exponentials),
+//               row max, ex2, bf16 P tile -> shared memory in the 128B-swizzled K-major layout the MMA
+//               reads; running max / sum / 32-wide output accumulator stay in registers.
+//   warp 8      TMA producer: both Q tiles once, then a 3-stage ring of K tiles (128 x 32, 64B swizzle)
+//               and V^T tiles (32 x 128, 128B swizzle) shared by the two query tiles.
+//   warp 9      MMA issuer: S = Q K^T (M128 N128 K32) and O_tile = P V (M128 N32 K128) for both tiles,
+//               fp32 accumulators in TMEM (S_A, S_B, O_A, O_B = 320 of 512 columns).
+// The two warpgroups ping-pong on the tensor pipe: while A exponentiates tile j, the MMA warp computes
+// B's scores and A's previous P V.  With head_dim 32 the kernel is bound by the 16 ex2/clk/SM of the
+// MUFU pipe (128 tensor FLOPs per exponential), not by the tensor pipe; see DESIGN.md.
 // Q is pre-scaled by log2(e)/sqrt(dh) when it is produced, so the softmax is a bare ex2.
 #include "common.cuh"
 #include "svol_internal.h"
@@ -22,19 +29,20 @@ namespace svol {
 
 namespace attn {
 constexpr int BQ = 128, BKV = 128, DH = 32, STAGES = 3;
-constexpr int Q_BYTES = BQ * DH * 2;            // 8192
+constexpr int Q_BYTES = BQ * DH * 2;            // 8192 per query tile
 constexpr int K_BYTES = BKV * DH * 2;           // 8192
 constexpr int VT_BYTES = DH * BKV * 2;          // 8192 = 2 k-blocks of 32 rows x 128 B
 constexpr int P_BYTES = BQ * BKV * 2;           // 32768 = 2 k-blocks of 128 rows x 128 B
-constexpr int OFF_K = Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES, OFF_P = OFF_VT + STAGES * VT_BYTES;
-constexpr int OFF_BAR = OFF_P + P_BYTES;
+constexpr int OFF_K = 2 * Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES, OFF_P = OFF_VT + STAGES * VT_BYTES;
+constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-constexpr int THREADS = 192;
-constexpr uint32_t TMEM_COLS = 256, TMEM_O = 128;
+constexpr int THREADS = 384;   // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle warps}
+constexpr uint32_t TMEM_COLS = 512, TMEM_O = 256;   // S_A [0,128) S_B [128,256) O_A [256,288) O_B [288,320)
 }  // namespace attn
 
 struct AttnBars {
-  uint64_t q_full, s_full, s_free, p_ready, o_full;
+  uint64_t q_full;
+  uint64_t s_full[2], s_free[2], p_ready[2], o_full[2];
   uint64_t kv_full[attn::STAGES], kv_empty[attn::STAGES];
   uint32_t tmem_base, pad;
 };
@@ -45,7 +53,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(attn::THREADS, 2)
+__global__ void __launch_bounds__(attn::THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, const float* __restrict__ key_mask,
                     __nv_bfloat16* __restrict__ out, int H, int Lq, int Lk, int ldo) {
@@ -55,81 +63,99 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem + OFF_BAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * (2 * BQ), h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (Lk + BKV - 1) / BKV;
+  const int n_q = (q0 + BQ < Lq) ? 2 : 1;          // is the second query tile of this CTA populated?
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
     mbar_init(&bars->q_full, 1);
-    mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->s_free, 4);
-    mbar_init(&bars->p_ready, 4);
-    mbar_init(&bars->o_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&bars->s_full[t], 1);
+      mbar_init(&bars->s_free[t], 4);
+      mbar_init(&bars->p_ready[t], 4);
+      mbar_init(&bars->o_full[t], 1);
+    }
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == 9) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 4) {
+  // register re-split: the softmax warpgroups hold a 128-wide score row + accumulators per thread
+  // (each role branch starts with its own setmaxnreg so that it dominates the role's code)
+  if (warp >= 8) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      mbar_arrive_expect_tx(&bars->q_full, Q_BYTES);
-      tma_load_2d(smem, &tmQ, &bars->q_full, h * DH, b * Lq + q0);
+      mbar_arrive_expect_tx(&bars->q_full, n_q * Q_BYTES);
+      for (int t = 0; t < n_q; ++t)
+        tma_load_2d(smem + t * Q_BYTES, &tmQ, &bars->q_full, h * DH, b * Lq + q0 + t * BQ);
+      const int vrow = (b * H + h) * DH;
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % STAGES;
-        const uint32_t use = j / STAGES;
-        mbar_wait(&bars->kv_empty[s], (use & 1) ^ 1);
+        mbar_wait(&bars->kv_empty[s], ((j / STAGES) & 1) ^ 1);
         mbar_arrive_expect_tx(&bars->kv_full[s], K_BYTES + VT_BYTES);
         tma_load_2d(smem + OFF_K + s * K_BYTES, &tmK, &bars->kv_full[s], h * DH, b * Lk + j * BKV);
-        const int vrow = (b * H + h) * DH;
         tma_load_2d(smem + OFF_VT + s * VT_BYTES, &tmVt, &bars->kv_full[s], j * BKV, vrow);
         tma_load_2d(smem + OFF_VT + s * VT_BYTES + VT_BYTES / 2, &tmVt, &bars->kv_full[s], j * BKV + 64, vrow);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH);
-      const uint32_t sQ = smem_u32(smem), sP = smem_u32(smem + OFF_P);
       auto issue_pv = [&](int j) {
-        const int s = j % STAGES;
-        mbar_wait(&bars->p_ready, j & 1);
-        tcgen05_fence_after();
-        const uint32_t sV = smem_u32(smem + OFF_VT + s * VT_BYTES);
+        const uint32_t sV = smem_u32(smem + OFF_VT + (j % STAGES) * VT_BYTES);
+        for (int t = 0; t < n_q; ++t) {
+          mbar_wait(&bars->p_ready[t], j & 1);
+          tcgen05_fence_after();
+          const uint32_t sP = smem_u32(smem + OFF_P + t * P_BYTES);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t a_desc = make_kmajor_desc<128>(sP + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32);
-          const uint64_t b_desc = make_kmajor_desc<128>(sV + (k >> 2) * (VT_BYTES / 2) + (k & 3) * 32);
-          umma_bf16_ss(tmem_base + TMEM_O, a_desc, b_desc, idesc_o, k != 0);
+          for (int k = 0; k < BKV / 16; ++k) {
+            const uint64_t a_desc = make_kmajor_desc<128>(sP + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32);
+            const uint64_t b_desc = make_kmajor_desc<128>(sV + (k >> 2) * (VT_BYTES / 2) + (k & 3) * 32);
+            umma_bf16_ss(tmem_base + TMEM_O + t * DH, a_desc, b_desc, idesc_o, k != 0);
+          }
+          umma_commit(&bars->o_full[t]);
         }
-        umma_commit(&bars->o_full);
-        umma_commit(&bars->kv_empty[s]);
+        umma_commit(&bars->kv_empty[j % STAGES]);
       };
       mbar_wait(&bars->q_full, 0);
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % STAGES;
         mbar_wait(&bars->kv_full[s], (j / STAGES) & 1);
-        if (j > 0) mbar_wait(&bars->s_free, (j - 1) & 1);
-        tcgen05_fence_after();
         const uint32_t sK = smem_u32(smem + OFF_K + s * K_BYTES);
+        for (int t = 0; t < n_q; ++t) {
+          if (j > 0) mbar_wait(&bars->s_free[t], (j - 1) & 1);
+          tcgen05_fence_after();
+          const uint32_t sQ = smem_u32(smem + t * Q_BYTES);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_bf16_ss(tmem_base, make_kmajor_desc<64>(sQ + k * 32), make_kmajor_desc<64>(sK + k * 32), idesc_s, k != 0);
-        umma_commit(&bars->s_full);
+          for (int k = 0; k < DH / 16; ++k)
+            umma_bf16_ss(tmem_base + t * BKV, make_kmajor_desc<64>(sQ + k * 32), make_kmajor_desc<64>(sK + k * 32),
+                         idesc_s, k != 0);
+          umma_commit(&bars->s_full[t]);
+        }
         if (j > 0) issue_pv(j - 1);
       }
       issue_pv(n_tiles - 1);
     }
+   }
   } else {
-    // ------------------------------------------------------------------ softmax (4 warps)
-    const int r = warp * 32 + lane;                    // row inside the tile == TMEM lane
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    uint8_t* p_row = smem + OFF_P + (r >> 3) * 1024 + (r & 7) * 128;
+   asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+   if ((warp >> 2) < n_q) {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int t = warp >> 2;                            // query tile of this warpgroup
+    const int quarter = warp & 3;                       // TMEM lane quarter == warp % 4
+    const int r = quarter * 32 + lane;                  // row inside the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_s = t_lane + t * BKV, t_o = t_lane + TMEM_O + t * DH;
+    uint8_t* p_row = smem + OFF_P + t * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
     const float* mrow = key_mask ? key_mask + static_cast<size_t>(b) * Lk : nullptr;
     float m_run = -INFINITY, l_run = 0.f, alpha_pending = 0.f;
     float acc[DH];
@@ -138,69 +164,59 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     for (int j = 0; j < n_tiles; ++j) {
       const int kv0 = j * BKV;
-      const bool masked_tile = (mrow != nullptr) || (kv0 + BKV > Lk);
-      mbar_wait(&bars->s_full, j & 1);
+      mbar_wait(&bars->s_full[t], j & 1);
       tcgen05_fence_after();
-      // pass 1: row maximum
-      float mx = -INFINITY;
+      uint32_t s[BKV];
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, v);
-        tmem_ld_wait();
-        if (masked_tile) {
+      for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
+      tmem_ld_wait();
+      // scores are in registers: hand the TMEM buffer back so the next QK^T can start now
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_free[t]);
+
+      // validity of this tile's 128 keys as four 32-bit words (ragged tail and key_padding_mask)
+      if (mrow != nullptr || kv0 + BKV > Lk) {
+        uint32_t words[BKV / 32];
+        bool all_valid = true;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kv = kv0 + c * 32 + i;
-            const bool ok = kv < Lk && (mrow == nullptr || __ldg(mrow + kv) != 0.f);
-            mx = fmaxf(mx, ok ? __uint_as_float(v[i]) : -INFINITY);
-          }
-        } else {
+        for (int c = 0; c < BKV / 32; ++c) {
+          const int kv = kv0 + c * 32 + lane;
+          const bool ok = kv < Lk && (mrow == nullptr || __ldg(mrow + kv) != 0.f);
+          words[c] = __ballot_sync(0xffffffffu, ok);
+          all_valid &= words[c] == 0xffffffffu;
+        }
+        if (!all_valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int c = 0; c < BKV / 32; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (!((words[c] >> i) & 1u)) s[c * 32 + i] = 0xff800000u;   // -inf
         }
       }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BKV; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
       const float m_new = fmaxf(m_run, mx);
       const float m_use = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ex2_approx(m_run - m_use);
-      // pass 2: p = 2^(s - m), packed to bf16
-      uint32_t p[BKV / 2];
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < BKV / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0, e1;
-          if (masked_tile) {
-            const int kv = kv0 + c * 32 + i;
-            const bool ok0 = kv < Lk && (mrow == nullptr || __ldg(mrow + kv) != 0.f);
-            const bool ok1 = kv + 1 < Lk && (mrow == nullptr || __ldg(mrow + kv + 1) != 0.f);
-            e0 = ok0 ? ex2_approx(__uint_as_float(v[i]) - m_use) : 0.f;
-            e1 = ok1 ? ex2_approx(__uint_as_float(v[i + 1]) - m_use) : 0.f;
-          } else {
-            e0 = ex2_approx(__uint_as_float(v[i]) - m_use);
-            e1 = ex2_approx(__uint_as_float(v[i + 1]) - m_use);
-          }
-          rs += e0 + e1;
-          p[c * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
-        }
+      for (int i = 0; i < BKV; i += 2) {
+        const float e0 = ex2_approx(__uint_as_float(s[i]) - m_use);
+        const float e1 = ex2_approx(__uint_as_float(s[i + 1]) - m_use);
+        rs += e0 + e1;
+        s[i >> 1] = pack_bf16x2(e0, e1);            // P packed in place: s[0..63]
       }
-      // S has been consumed: the MMA warp may overwrite it with the next tile's scores
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_free);
       l_run = l_run * alpha + rs;
       m_run = m_new;
 
       if (j > 0) {
-        // fold in the previous tile's P V (this also guarantees the MMA is done reading P)
-        mbar_wait(&bars->o_full, (j - 1) & 1);
+        // fold in the previous tile's P V (this also guarantees the MMA is done reading the P buffer)
+        mbar_wait(&bars->o_full[t], (j - 1) & 1);
         tcgen05_fence_after();
         uint32_t o[32];
-        tmem_ld_32x32b_x32(t_row + TMEM_O, o);
+        tmem_ld_32x32b_x32(t_o, o);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < DH; ++i) acc[i] = acc[i] * alpha_pending + __uint_as_float(o[i]);
@@ -210,25 +226,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
       for (int ch = 0; ch < 16; ++ch) {
         const int kb = ch >> 3, jj = ch & 7;
-        uint4 q = make_uint4(p[ch * 4], p[ch * 4 + 1], p[ch * 4 + 2], p[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(p_row + kb * (P_BYTES / 2) + ((jj ^ (r & 7)) << 4)) = q;
+        *reinterpret_cast<uint4*>(p_row + kb * (P_BYTES / 2) + ((jj ^ (r & 7)) << 4)) =
+            make_uint4(s[ch * 4], s[ch * 4 + 1], s[ch * 4 + 2], s[ch * 4 + 3]);
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->p_ready);
+      if (lane == 0) mbar_arrive(&bars->p_ready[t]);
     }
     // last tile
-    mbar_wait(&bars->o_full, (n_tiles - 1) & 1);
+    mbar_wait(&bars->o_full[t], (n_tiles - 1) & 1);
     tcgen05_fence_after();
     {
       uint32_t o[32];
-      tmem_ld_32x32b_x32(t_row + TMEM_O, o);
+      tmem_ld_32x32b_x32(t_o, o);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < DH; ++i) acc[i] = acc[i] * alpha_pending + __uint_as_float(o[i]);
     }
-    const int q = q0 + r;
+    const int q = q0 + t * BQ + r;
     if (q < Lq) {
       const float inv = 1.0f / l_run;
       uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * Lq + q) * ldo + h * DH);
@@ -242,11 +258,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         op[i] = w;
       }
     }
+   }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tcgen05_fence_after();
     tmem_dealloc<attn::TMEM_COLS>(tmem_base);
   }
@@ -270,7 +287,7 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return svol_fail_cuda(e, "attention: cudaFuncSetAttribute");
     configured = true;
   }
-  dim3 grid((a.Lq + BQ - 1) / BQ, a.H, a.B);
+  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
   attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask,
                                                             reinterpret_cast<__nv_bfloat16*>(a.out), a.H, a.Lq, a.Lk, a.ldo);
   return svol_check_launch("attention_tc");

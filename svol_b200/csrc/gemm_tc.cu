@@ -6,62 +6,137 @@
 // reference's nn.Linear / nn.LayerNorm / F.gelu / F.relu calls turn into
 // (lib/modeling/svanet.py:159-181, lib/modeling/cross_modal_transformer.py:88-100,137-158,163-179).
 //
-// Structure (one CTA per SM, 320 threads):
-//   warp 0      TMA producer : A tile 128x64 and W tile 256x64 per k-block, 4-stage smem ring
+// Structure (one CTA per SM, 384 threads = 3 warpgroups; warps 2-3 idle so that setmaxnreg can re-split
+// the register file per warpgroup):
+//   warp 0      TMA producer
 //   warp 1      MMA issuer   : tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16, fp32
 //                              accumulators in TMEM, two accumulator stages (2 x 256 columns)
-//   warps 2..9  epilogue     : tcgen05.ld -> registers (TMEM stage released immediately) ->
+//   warps 4..11 epilogue     : tcgen05.ld -> registers (TMEM stage released immediately) ->
 //                              +bias -> ReLU | GELU(erf) -> +residual -> LayerNorm over the
 //                              256-wide row -> bf16 store, optional second output (x + pos),
 //                              optional per-head transposed store for the attention V operand.
 // The epilogue of tile i overlaps the mainloop of tile i+1.
+//
+// Two operand-feed variants (measured: the 128x256 tile streamed from L2 is bound by L2->SM
+// bandwidth, ~48 KB per 64-wide k-block per SM, long before the tensor pipe):
+//   kResidentW = true  (K == 256, every projection except three): each CTA owns one 256-row block
+//                of W, loads its 128 KB ONCE into shared memory and then streams only A tiles
+//                (16 KB per k-block, 4-stage ring) -- 3x less L2 traffic per tile.
+//   kResidentW = false (K = 512 input projection, K = 2048 FFN down-projection): A and W tiles are
+//                both streamed through a 4-stage ring of 48 KB.
 #include "common.cuh"
 #include "svol_internal.h"
 
 namespace svol {
 
 namespace gemm {
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_WARPS = 8, THREADS = 64 + EPI_WARPS * 32;
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+constexpr int EPI_WARPS = 8, FIRST_EPI_WARP = 4, THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;   // 3 warpgroups
 constexpr int COLS_PER_THREAD = BN / (EPI_WARPS / 4);   // 128
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BM * 4 * 2 /*LN exchange*/;
+constexpr int RES_K = 256, RES_KB = RES_K / BK;         // resident-W variant: K fixed at 256
+constexpr int MAX_STAGES = 4;
+constexpr int STG_BYTES = 32 * 128;                     // per epilogue warp: 32 rows x 128 B
+
+template <bool kResidentW>
+struct Cfg {
+  static constexpr int STAGES = 4;
+  static constexpr int STAGE_BYTES = kResidentW ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int W_BYTES = kResidentW ? RES_KB * B_BYTES : 0;                  // 128 KB
+  static constexpr int OFF_STAGES = W_BYTES;
+  static constexpr int OFF_STG = OFF_STAGES + STAGES * STAGE_BYTES;                    // epilogue staging
+  static constexpr int OFF_TAIL = OFF_STG + EPI_WARPS * STG_BYTES;
+  static constexpr int SMEM_BYTES = OFF_TAIL + 256 /*barriers*/ + 2 * BM * 4 /*LN exchange*/ + 1024 /*align*/;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
 }  // namespace gemm
 
 struct GemmSmemTail {
-  uint64_t full[gemm::STAGES];
-  uint64_t empty[gemm::STAGES];
+  uint64_t full[gemm::MAX_STAGES];
+  uint64_t empty[gemm::MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t w_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
+static_assert(sizeof(GemmSmemTail) <= 256, "barrier block");
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Global <-> register transposition of a [32 rows x 128 B] block through a per-warp staging buffer.
+// In the epilogue a thread owns one ROW (that is how tcgen05.ld hands out the accumulator), so a direct
+// 16-byte access per thread touches 32 different cache lines per warp instruction; measured, that made
+// the epilogue L1-wavefront bound (~8 us per tile).  Staged, every global instruction covers 4 rows x 128
+// contiguous bytes.  16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4): conflict-free both ways.
+__device__ __forceinline__ void block_store(uint8_t* stg, const uint4 (&q)[8], uint8_t* gbase, size_t pitch,
+                                            int rows_valid, int lane) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = q[j];
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int row = k * 4 + (lane >> 3), ch = lane & 7;
+    const uint4 val = *reinterpret_cast<const uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+    if (row < rows_valid) *reinterpret_cast<uint4*>(gbase + static_cast<size_t>(row) * pitch + ch * 16) = val;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void block_load(uint8_t* stg, uint4 (&q)[8], const uint8_t* gbase, size_t pitch,
+                                           int rows_valid, int lane) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int row = k * 4 + (lane >> 3), ch = lane & 7;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (row < rows_valid) val = __ldg(reinterpret_cast<const uint4*>(gbase + static_cast<size_t>(row) * pitch + ch * 16));
+    *reinterpret_cast<uint4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4)) = val;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] = *reinterpret_cast<const uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
+  __syncwarp();
+}
+
+template <bool kResidentW>
 __global__ void __launch_bounds__(gemm::THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmEpilogue ep, int M, int N, int K) {
   using namespace gemm;
+  using C = Cfg<kResidentW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + STAGES * STAGE_BYTES);
-  float* ln_x = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // [2 halves][128 rows]
+  uint8_t* stages = smem + C::OFF_STAGES;
+  GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + C::OFF_TAIL);
+  float* ln_x = reinterpret_cast<float*>(smem + C::OFF_TAIL + 256);   // [2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_blocks = (M + BM - 1) / BM;
   const int n_blocks = N / BN;
-  const int num_tiles = m_blocks * n_blocks;
   const int num_kb = K / BK;
+  // tile schedule.  streaming: tile = blockIdx.x + i*grid, n fastest.  resident: this CTA's n block is
+  // fixed (grid is a multiple of n_blocks) and it walks m blocks with stride grid / n_blocks.
+  const int my_n = kResidentW ? static_cast<int>(blockIdx.x) % n_blocks : 0;
+  const int m_first = kResidentW ? static_cast<int>(blockIdx.x) / n_blocks : 0;
+  const int m_stride = kResidentW ? static_cast<int>(gridDim.x) / n_blocks : 0;
+  const int num_tiles = m_blocks * n_blocks;
+  const int my_tiles = kResidentW ? (m_blocks > m_first ? (m_blocks - m_first + m_stride - 1) / m_stride : 0)
+                                  : (num_tiles > static_cast<int>(blockIdx.x)
+                                         ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                                         : 0);
+  auto tile_coords = [&](int it, int& m_blk, int& n_blk) {
+    if (kResidentW) { m_blk = m_first + it * m_stride; n_blk = my_n; }
+    else { const int tile = blockIdx.x + it * gridDim.x; m_blk = tile / n_blocks; n_blk = tile % n_blocks; }
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tail->tmem_full[s], 1); mbar_init(&tail->tmem_empty[s], EPI_WARPS); }
+    mbar_init(&tail->w_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tail->tmem_base);
@@ -70,19 +145,30 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = tail->tmem_base;
 
-  if (warp == 0) {
+  // Register re-split between warpgroups (each SM sub-partition holds one warp of warpgroup 0 and two
+  // epilogue warps): the producer / MMA warpgroup keeps 40 registers, the epilogue warps get 232 so the
+  // 128-wide accumulator row, its residual and its pos operand stay in registers.
+  // (the setmaxnreg must dominate the role's code, so each role branch starts with its own).
+  if (warp < FIRST_EPI_WARP) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
+      if (kResidentW && my_tiles > 0) {
+        mbar_arrive_expect_tx(&tail->w_full, C::W_BYTES);
+        for (int kb = 0; kb < RES_KB; ++kb) tma_load_2d(smem + kb * B_BYTES, &tmB, &tail->w_full, kb * BK, my_n * BN);
+      }
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+      for (int it = 0; it < my_tiles; ++it) {
+        int m_blk, n_blk;
+        tile_coords(it, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail->empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&tail->full[stage], STAGE_BYTES);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&tail->full[stage], C::STAGE_BYTES);
+          uint8_t* sa = stages + stage * C::STAGE_BYTES;
           tma_load_2d(sa, &tmA, &tail->full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sa + A_BYTES, &tmB, &tail->full[stage], kb * BK, n_blk * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (!kResidentW) tma_load_2d(sa + A_BYTES, &tmB, &tail->full[stage], kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -90,8 +176,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      int stage = 0; uint32_t phase = 0; int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      int stage = 0; uint32_t phase = 0;
+      if (kResidentW && my_tiles > 0) mbar_wait(&tail->w_full, 0);
+      for (int it = 0; it < my_tiles; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1);
@@ -100,51 +187,55 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&tail->full[stage], phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
           const uint64_t a_desc = make_kmajor_desc<128>(sa);
-          const uint64_t b_desc = make_kmajor_desc<128>(sa + A_BYTES);
+          const uint64_t b_desc = make_kmajor_desc<128>(kResidentW ? smem_u32(smem + kb * B_BYTES) : sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
           umma_commit(&tail->empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tail->tmem_full[acc]);
       }
     }
+   }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     const int quarter = warp & 3;               // TMEM lane quarter this warp may read
-    const int half = (warp - 2) >> 2;           // which 128 of the tile's 256 columns
+    const int half = (warp - FIRST_EPI_WARP) >> 2;           // which 128 of the tile's 256 columns
     const int r_in_tile = quarter * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+    uint8_t* stg = smem + C::OFF_STG + (warp - FIRST_EPI_WARP) * STG_BYTES;
+    for (int it = 0; it < my_tiles; ++it) {
+      int m_blk, n_blk;
+      tile_coords(it, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m_blk * BM + r_in_tile;
       const int col0 = n_blk * BN + half * COLS_PER_THREAD;
       const bool row_ok = row < M;
+      const int slab_row0 = m_blk * BM + quarter * 32;             // first row of this warp's 32-row slab
+      const int rows_valid = min(32, max(0, M - slab_row0));
 
       mbar_wait(&tail->tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       float v[COLS_PER_THREAD];
       {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * COLS_PER_THREAD;
+        uint32_t raw[COLS_PER_THREAD / 32][32];
 #pragma unroll
-        for (int c = 0; c < COLS_PER_THREAD / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
-          tmem_ld_wait();
+        for (int c = 0; c < COLS_PER_THREAD / 32; ++c) tmem_ld_32x32b_x32(taddr + c * 32, raw[c]);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[c * 32 + i] = __uint_as_float(r[i]);
-        }
+        for (int c = 0; c < COLS_PER_THREAD / 32; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[c * 32 + i] = __uint_as_float(raw[c][i]);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
 
-      // bias
       if (ep.bias) {
         const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
 #pragma unroll
@@ -158,17 +249,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < COLS_PER_THREAD; ++i) v[i] = fmaxf(v[i], 0.f);
       } else if (ep.act == SVOL_ACT_GELU) {
 #pragma unroll
-        for (int i = 0; i < COLS_PER_THREAD; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < COLS_PER_THREAD; ++i) v[i] = gelu_erf_fast(v[i]);
       }
-      if (ep.residual && row_ok) {
-        const uint4* rp = reinterpret_cast<const uint4*>(ep.residual + static_cast<size_t>(row) * ep.ld_res + col0);
+      if (ep.residual) {
+        const uint8_t* rbase = reinterpret_cast<const uint8_t*>(ep.residual + static_cast<size_t>(slab_row0) * ep.ld_res + col0);
 #pragma unroll
-        for (int i = 0; i < COLS_PER_THREAD / 8; ++i) {
-          const uint4 q = __ldg(rp + i);
-          v[8 * i + 0] += bf16_lo(q.x); v[8 * i + 1] += bf16_hi(q.x);
-          v[8 * i + 2] += bf16_lo(q.y); v[8 * i + 3] += bf16_hi(q.y);
-          v[8 * i + 4] += bf16_lo(q.z); v[8 * i + 5] += bf16_hi(q.z);
-          v[8 * i + 6] += bf16_lo(q.w); v[8 * i + 7] += bf16_hi(q.w);
+        for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
+          uint4 q[8];
+          block_load(stg, q, rbase + blk * 128, static_cast<size_t>(ep.ld_res) * 2, rows_valid, lane);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float* vv = &v[blk * 64 + j * 8];
+            vv[0] += bf16_lo(q[j].x); vv[1] += bf16_hi(q[j].x); vv[2] += bf16_lo(q[j].y); vv[3] += bf16_hi(q[j].y);
+            vv[4] += bf16_lo(q[j].z); vv[5] += bf16_hi(q[j].z); vv[6] += bf16_lo(q[j].w); vv[7] += bf16_hi(q[j].w);
+          }
         }
       }
       if (ep.ln_weight) {
@@ -200,34 +294,56 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
         }
       }
-      if (row_ok && ep.out) {
-        uint4* op = reinterpret_cast<uint4*>(ep.out + static_cast<size_t>(row) * ep.ld_out + col0);
+      if (ep.out) {
+        uint8_t* obase = reinterpret_cast<uint8_t*>(ep.out + static_cast<size_t>(slab_row0) * ep.ld_out + col0);
 #pragma unroll
-        for (int i = 0; i < COLS_PER_THREAD / 8; ++i) {
-          uint4 q;
-          q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-          q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-          op[i] = q;
+        for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
+          uint4 q[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float* vv = &v[blk * 64 + j * 8];
+            q[j] = make_uint4(pack_bf16x2(vv[0], vv[1]), pack_bf16x2(vv[2], vv[3]), pack_bf16x2(vv[4], vv[5]), pack_bf16x2(vv[6], vv[7]));
+          }
+          block_store(stg, q, obase + blk * 128, static_cast<size_t>(ep.ld_out) * 2, rows_valid, lane);
         }
       }
-      if (row_ok && ep.out_pos) {
-        // second output: x + pos (the q/k operand of the next attention block)
+      if (ep.out_pos) {
+        // second output: x + pos (the q/k operand of the next attention block).  pos rows follow the output
+        // rows (pos_row_mod == 0) or repeat with period pos_row_mod (query embedding broadcast over the batch);
+        // the broadcast case is read directly (its 320 x 256 table stays in L1/L2).
+        uint8_t* obase = reinterpret_cast<uint8_t*>(ep.out_pos + static_cast<size_t>(slab_row0) * ep.ld_out + col0);
         const int prow = ep.pos_row_mod > 0 ? row % ep.pos_row_mod : row;
-        const float4* pp = reinterpret_cast<const float4*>(ep.pos + static_cast<size_t>(prow) * ep.ld_pos + col0);
-        uint4* op = reinterpret_cast<uint4*>(ep.out_pos + static_cast<size_t>(row) * ep.ld_out + col0);
 #pragma unroll
-        for (int i = 0; i < COLS_PER_THREAD / 8; ++i) {
-          const float4 p0 = __ldg(pp + 2 * i), p1 = __ldg(pp + 2 * i + 1);
-          uint4 q;
-          q.x = pack_bf16x2(v[8 * i + 0] + p0.x, v[8 * i + 1] + p0.y);
-          q.y = pack_bf16x2(v[8 * i + 2] + p0.z, v[8 * i + 3] + p0.w);
-          q.z = pack_bf16x2(v[8 * i + 4] + p1.x, v[8 * i + 5] + p1.y);
-          q.w = pack_bf16x2(v[8 * i + 6] + p1.z, v[8 * i + 7] + p1.w);
-          op[i] = q;
+        for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
+          uint4 q[8];
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            uint4 pq[8];                                              // 32 fp32 pos values of this row
+            if (ep.pos_row_mod > 0) {
+              const uint4* pp = reinterpret_cast<const uint4*>(ep.pos + static_cast<size_t>(prow) * ep.ld_pos + col0 + blk * 64 + sub * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pq[j] = row_ok ? __ldg(pp + j) : make_uint4(0u, 0u, 0u, 0u);
+            } else {
+              block_load(stg, pq, reinterpret_cast<const uint8_t*>(ep.pos + static_cast<size_t>(slab_row0) * ep.ld_pos + col0 + blk * 64 + sub * 32),
+                         static_cast<size_t>(ep.ld_pos) * 4, rows_valid, lane);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float* vv = &v[blk * 64 + sub * 32 + j * 8];
+              const uint4 a = pq[2 * j], c = pq[2 * j + 1];
+              q[sub * 4 + j] = make_uint4(pack_bf16x2(vv[0] + __uint_as_float(a.x), vv[1] + __uint_as_float(a.y)),
+                                          pack_bf16x2(vv[2] + __uint_as_float(a.z), vv[3] + __uint_as_float(a.w)),
+                                          pack_bf16x2(vv[4] + __uint_as_float(c.x), vv[5] + __uint_as_float(c.y)),
+                                          pack_bf16x2(vv[6] + __uint_as_float(c.z), vv[7] + __uint_as_float(c.w)));
+            }
+          }
+          block_store(stg, q, obase + blk * 128, static_cast<size_t>(ep.ld_out) * 2, rows_valid, lane);
         }
       }
       if (row_ok && ep.out_vt) {
-        // per-head transposed store: Vt[(b*H + h)*dh + d][l], row = b*L + l, col = h*dh + d
+        // per-head transposed store: Vt[(b*H + h)*dh + d][l], row = b*L + l, col = h*dh + d.
+        // Consecutive lanes hold consecutive tokens l, so each store instruction writes 64
+        // contiguous bytes per output row.
         const int b = row / ep.vt_len, l = row - b * ep.vt_len;
         __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ep.out_vt) + (static_cast<size_t>(b) * N + col0) * ep.vt_pitch + l;
 #pragma unroll
@@ -248,6 +364,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+template <bool kResidentW>
+static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t stream) {
+  using namespace gemm;
+  using C = Cfg<kResidentW>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<kResidentW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return svol_fail_cuda(e, "gemm: cudaFuncSetAttribute");
+    configured = true;
+  }
+  const int m_blocks = (a.M + BM - 1) / BM, n_blocks = a.N / BN;
+  const int tiles = m_blocks * n_blocks;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  if (kResidentW) grid = grid / n_blocks * n_blocks;       // every CTA owns one n block
+  gemm_bf16_tc_kernel<kResidentW><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, a.ep, a.M, a.N, a.K);
+  return svol_check_launch("gemm_bf16_tc");
+}
+
 int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   using namespace gemm;
   if (a.N % BN != 0 || a.K % BK != 0 || a.M <= 0) return svol_fail(SVOL_ERR_SHAPE, "gemm: need N % 256 == 0, K % 64 == 0, M > 0");
@@ -258,17 +392,8 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_tensor_map_2d(&tmB, a.W, a.K, a.N, a.ldw, BK, BN, 128);
   if (rc) return rc;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return svol_fail_cuda(e, "gemm: cudaFuncSetAttribute");
-    configured = true;
-  }
-  const int m_blocks = (a.M + BM - 1) / BM;
-  const int tiles = m_blocks * (a.N / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, a.ep, a.M, a.N, a.K);
-  return svol_check_launch("gemm_bf16_tc");
+  const bool resident = a.K == RES_K && a.N / BN <= sm_count();
+  return resident ? launch_variant<true>(a, tmA, tmB, stream) : launch_variant<false>(a, tmA, tmB, stream);
 }
 
 }  // namespace svol

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(256) ln_linear_f32_kernel(const float* __restr
   const float rstd = rsqrtf(tot / in_dim + eps);
   for (int i = tid; i < in_dim; i += blockDim.x) xs[i] = (xs[i] - mean) * rstd * lw[i] + lb[i];
   __syncthreads();
-  for (int o = warp; o < out_dim; o += 8) {
+  const int o_end = min(out_dim, static_cast<int>(blockIdx.y + 1) * 32);
+  for (int o = blockIdx.y * 32 + warp; o < o_end; o += 8) {
     const float* wr = w + static_cast<size_t>(o) * in_dim;
     float acc = 0.f;
     for (int i = lane; i < in_dim; i += 32) acc = fmaf(xs[i], __ldg(wr + i), acc);
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256) ln_linear_f32_kernel(const float* __restr
 int launch_ln_linear_f32(const float* x, const float* lw, const float* lb, const float* w, const float* b, int relu,
                          float* y, int rows, int in_dim, int out_dim, float eps, cudaStream_t stream) {
   if (rows <= 0 || in_dim <= 0 || in_dim > 8192) return svol_fail(SVOL_ERR_SHAPE, "ln_linear: bad sizes");
-  ln_linear_f32_kernel<<<rows, 256, (in_dim + 16) * sizeof(float), stream>>>(x, lw, lb, w, b, relu, y, in_dim, out_dim, eps);
+  ln_linear_f32_kernel<<<dim3(rows, (out_dim + 31) / 32), 256, (in_dim + 16) * sizeof(float), stream>>>(x, lw, lb, w, b, relu, y, in_dim, out_dim, eps);
   return svol_check_launch("ln_linear_f32");
 }
 
@@ -145,19 +146,22 @@ __global__ void __launch_bounds__(256) posenc_sine_kernel(const float* __restric
     xrow[tid] = __fmul_rn(__fdiv_rn(cum, __fadd_rn(tsum, 1e-6f)), 6.283185307179586f);
   }
   __syncthreads();
+  // dim_t[i] = 10000^(2*(i/2)/d): one powf per column per CTA instead of one per element
+  extern __shared__ float dim_t[];
+  for (int i = tid; i < d; i += blockDim.x)
+    dim_t[i] = powf(10000.f, __fdiv_rn(__fmul_rn(2.f, static_cast<float>(i >> 1)), static_cast<float>(d)));
+  __syncthreads();
   const int rows = min(32, L - l0);
   for (int e = tid; e < rows * d; e += blockDim.x) {
     const int r = e / d, i = e - r * d;
-    const float expo = __fdiv_rn(__fmul_rn(2.f, static_cast<float>(i >> 1)), static_cast<float>(d));
-    const float dim_t = powf(10000.f, expo);
-    const float a = __fdiv_rn(xrow[r], dim_t);
+    const float a = __fdiv_rn(xrow[r], dim_t[i]);
     pos[(static_cast<size_t>(b) * L + l0 + r) * d + i] = (i & 1) ? cosf(a) : sinf(a);
   }
 }
 
 int launch_posenc_sine(const float* mask, float* pos, int B, int L, int d, cudaStream_t stream) {
   if (B <= 0 || L <= 0 || d <= 0) return svol_fail(SVOL_ERR_SHAPE, "posenc: bad sizes");
-  posenc_sine_kernel<<<dim3((L + 31) / 32, B), 256, 0, stream>>>(mask, pos, L, d);
+  posenc_sine_kernel<<<dim3((L + 31) / 32, B), 256, d * sizeof(float), stream>>>(mask, pos, L, d);
   return svol_check_launch("posenc_sine");
 }
 
@@ -234,24 +238,37 @@ constexpr int GATE_D = 256, GATE_H = 8, GATE_ROWS = 64;
 __global__ void __launch_bounds__(256) gate_scores_kernel(const __nv_bfloat16* __restrict__ xpos,
                                                           const float* __restrict__ u, float* __restrict__ scores,
                                                           int L) {
-  __shared__ float us[GATE_H][GATE_D];
   const int b = blockIdx.y, l0 = blockIdx.x * GATE_ROWS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < GATE_H * GATE_D; i += 256) us[i / GATE_D][i % GATE_D] = u[static_cast<size_t>(b) * GATE_H * GATE_D + i];
-  __syncthreads();
+  // this lane's 8 columns of every head's gate vector stay in registers for the CTA's 64 rows
+  float ur[GATE_H][8];
+#pragma unroll
+  for (int h = 0; h < GATE_H; ++h) {
+    const float4* up = reinterpret_cast<const float4*>(u + (static_cast<size_t>(b) * GATE_H + h) * GATE_D) + lane * 2;
+    const float4 a = __ldg(up), c = __ldg(up + 1);
+    ur[h][0] = a.x; ur[h][1] = a.y; ur[h][2] = a.z; ur[h][3] = a.w;
+    ur[h][4] = c.x; ur[h][5] = c.y; ur[h][6] = c.z; ur[h][7] = c.w;
+  }
   for (int r = warp; r < GATE_ROWS; r += 8) {
     const int l = l0 + r;
     if (l >= L) break;
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(xpos + (static_cast<size_t>(b) * L + l) * GATE_D) + lane);
-    float xv[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-    float mine = 0.f;
+    const float xv[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+    float acc[GATE_H];
 #pragma unroll
     for (int h = 0; h < GATE_H; ++h) {
-      float acc = 0.f;
+      float a = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc = fmaf(xv[i], us[h][lane * 8 + i], acc);
-      acc = warp_sum(acc);
-      if (lane == h) mine = acc;
+      for (int i = 0; i < 8; ++i) a = fmaf(xv[i], ur[h][i], a);
+      acc[h] = a;
     }
+    // 8 interleaved butterfly reductions (independent shuffles pipeline)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int h = 0; h < GATE_H; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], o);
+    float mine = 0.f;
+#pragma unroll
+    for (int h = 0; h < GATE_H; ++h) if (lane == h) mine = acc[h];
     if (lane < GATE_H) scores[(static_cast<size_t>(b) * GATE_H + lane) * L + l] = mine;
   }
 }
