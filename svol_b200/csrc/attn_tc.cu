@@ -31,13 +31,17 @@ namespace attn {
 constexpr int BQ = 128, BKV = 128, DH = 32, STAGES = 3;
 constexpr int Q_BYTES = BQ * DH * 2;            // 8192 per query tile
 constexpr int K_BYTES = BKV * DH * 2;           // 8192
-constexpr int VT_BYTES = DH * BKV * 2;          // 8192 = 2 k-blocks of 32 rows x 128 B
+constexpr int NV = DH + 16;                     // V^T rows fed to the P V MMA: 32 value rows, one row of ones
+                                                // (-> column 32 of the product is the softmax row sum), 15 zero rows
+constexpr int VT_KB_BYTES = NV * 128;           // one 64-key k-block of V^T: 48 rows x 128 B (TMA fills rows 0..31)
+constexpr int VT_BYTES = 2 * VT_KB_BYTES;       // 12288
 constexpr int P_BYTES = BQ * BKV * 2;           // 32768 = 2 k-blocks of 128 rows x 128 B
 constexpr int OFF_K = 2 * Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES, OFF_P = OFF_VT + STAGES * VT_BYTES;
 constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 384;   // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle warps}
-constexpr uint32_t TMEM_COLS = 512, TMEM_O = 256;   // S_A [0,128) S_B [128,256) O_A [256,288) O_B [288,320)
+constexpr uint32_t TMEM_COLS = 512, TMEM_O = 256, TMEM_O_STRIDE = 64;   // S_A [0,128) S_B [128,256) O_A [256,304) O_B [320,368)
+constexpr int TMA_VT_BYTES = 2 * DH * 128;      // bytes the two V^T TMA boxes deliver per stage
 }  // namespace attn
 
 struct AttnBars {
@@ -51,6 +55,36 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t& r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Row maximum of the 128 scores a thread holds; kMasked additionally overwrites invalid keys with -inf.
+template <bool kMasked>
+__device__ __forceinline__ float tile_row_max(uint32_t (&s)[attn::BKV], const uint32_t (&words)[attn::BKV / 32]) {
+  if (kMasked) {
+#pragma unroll
+    for (int c = 0; c < attn::BKV / 32; ++c)
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (!((words[c] >> i) & 1u)) s[c * 32 + i] = 0xff800000u;   // -inf
+  }
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < attn::BKV; i += 4) {
+    m0 = fmaxf(m0, __uint_as_float(s[i + 0])); m1 = fmaxf(m1, __uint_as_float(s[i + 1]));
+    m2 = fmaxf(m2, __uint_as_float(s[i + 2])); m3 = fmaxf(m3, __uint_as_float(s[i + 3]));
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
 __global__ void __launch_bounds__(attn::THREADS, 1)
@@ -80,6 +114,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  {
+    // rows 32..47 of every V^T k-block buffer are constant: row 32 = 1.0 (bf16), rows 33..47 = 0.  TMA only ever
+    // writes rows 0..31, so this is done once.  (A row of equal values is invariant under the 128B swizzle.)
+    constexpr int kRegions = STAGES * 2, kChunks = (NV - DH) * 128 / 16;      // 16-byte chunks per region
+    for (int idx = threadIdx.x; idx < kRegions * kChunks; idx += THREADS) {
+      const int region = idx / kChunks, off = idx % kChunks;
+      const uint32_t v = off < 8 ? 0x3F803F80u : 0u;
+      *reinterpret_cast<uint4*>(smem + OFF_VT + (region >> 1) * VT_BYTES + (region & 1) * VT_KB_BYTES + DH * 128 + off * 16) =
+          make_uint4(v, v, v, v);
+    }
+    fence_proxy_async_smem();
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -99,17 +145,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int j = 0; j < n_tiles; ++j) {
         const int s = j % STAGES;
         mbar_wait(&bars->kv_empty[s], ((j / STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars->kv_full[s], K_BYTES + VT_BYTES);
+        mbar_arrive_expect_tx(&bars->kv_full[s], K_BYTES + TMA_VT_BYTES);
         tma_load_2d(smem + OFF_K + s * K_BYTES, &tmK, &bars->kv_full[s], h * DH, b * Lk + j * BKV);
         tma_load_2d(smem + OFF_VT + s * VT_BYTES, &tmVt, &bars->kv_full[s], j * BKV, vrow);
-        tma_load_2d(smem + OFF_VT + s * VT_BYTES + VT_BYTES / 2, &tmVt, &bars->kv_full[s], j * BKV + 64, vrow);
+        tma_load_2d(smem + OFF_VT + s * VT_BYTES + VT_KB_BYTES, &tmVt, &bars->kv_full[s], j * BKV + 64, vrow);
       }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
-      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH);
+      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, NV);
       auto issue_pv = [&](int j) {
         const uint32_t sV = smem_u32(smem + OFF_VT + (j % STAGES) * VT_BYTES);
         for (int t = 0; t < n_q; ++t) {
@@ -119,8 +165,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
             const uint64_t a_desc = make_kmajor_desc<128>(sP + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32);
-            const uint64_t b_desc = make_kmajor_desc<128>(sV + (k >> 2) * (VT_BYTES / 2) + (k & 3) * 32);
-            umma_bf16_ss(tmem_base + TMEM_O + t * DH, a_desc, b_desc, idesc_o, k != 0);
+            const uint64_t b_desc = make_kmajor_desc<128>(sV + (k >> 2) * VT_KB_BYTES + (k & 3) * 32);
+            umma_bf16_ss(tmem_base + TMEM_O + t * TMEM_O_STRIDE, a_desc, b_desc, idesc_o, k != 0);
           }
           umma_commit(&bars->o_full[t]);
         }
@@ -154,13 +200,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int quarter = warp & 3;                       // TMEM lane quarter == warp % 4
     const int r = quarter * 32 + lane;                  // row inside the tile == TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    const uint32_t t_s = t_lane + t * BKV, t_o = t_lane + TMEM_O + t * DH;
+    const uint32_t t_s = t_lane + t * BKV, t_o = t_lane + TMEM_O + t * TMEM_O_STRIDE;
     uint8_t* p_row = smem + OFF_P + t * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
     const float* mrow = key_mask ? key_mask + static_cast<size_t>(b) * Lk : nullptr;
     float m_run = -INFINITY, l_run = 0.f, alpha_pending = 0.f;
     float acc[DH];
 #pragma unroll
     for (int i = 0; i < DH; ++i) acc[i] = 0.f;
+
+    // Ping-pong between the two softmax warpgroups (named barriers 1 and 2): the exponential section of
+    // one warpgroup saturates the MUFU pipe on its own, so the two sections are made mutually exclusive and
+    // each warpgroup's TMEM loads, row max, accumulator fold and P store run under the other's exponentials.
+    const bool pingpong = n_q == 2;
+    const int my_turn = 1 + t, other_turn = 2 - t;
+    if (pingpong && t == 1) named_bar_arrive(1, 256);        // warpgroup A goes first
+    const uint32_t p_row_addr = smem_u32(p_row);
+    const uint32_t swz = static_cast<uint32_t>(r & 7) << 4;
 
     for (int j = 0; j < n_tiles; ++j) {
       const int kv0 = j * BKV;
@@ -175,59 +230,56 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_free[t]);
 
-      // validity of this tile's 128 keys as four 32-bit words (ragged tail and key_padding_mask)
+      // validity of this tile's 128 keys as four 32-bit words (ragged tail and key_padding_mask); the
+      // masked variant of the row-max code is a separate instantiation so full tiles pay nothing for it
+      float mx;
+      bool masked = false;
+      uint32_t words[BKV / 32];
       if (mrow != nullptr || kv0 + BKV > Lk) {
-        uint32_t words[BKV / 32];
-        bool all_valid = true;
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c) {
           const int kv = kv0 + c * 32 + lane;
           const bool ok = kv < Lk && (mrow == nullptr || __ldg(mrow + kv) != 0.f);
           words[c] = __ballot_sync(0xffffffffu, ok);
-          all_valid &= words[c] == 0xffffffffu;
-        }
-        if (!all_valid) {
-#pragma unroll
-          for (int c = 0; c < BKV / 32; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (!((words[c] >> i) & 1u)) s[c * 32 + i] = 0xff800000u;   // -inf
+          masked |= words[c] != 0xffffffffu;
         }
       }
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < BKV; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      if (masked) mx = tile_row_max<true>(s, words);
+      else mx = tile_row_max<false>(s, words);
       const float m_new = fmaxf(m_run, mx);
       const float m_use = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ex2_approx(m_run - m_use);
-      float rs = 0.f;
+
+      if (pingpong) named_bar_sync(my_turn, 256);
+      // one MUFU ex2 per probability (ex2.approx.ftz.bf16x2 was tried: on sm_100 it is issued as two
+      // MUFU.EX2.BF16 ops plus a PRMT, so it saves nothing and only costs precision)
 #pragma unroll
-      for (int i = 0; i < BKV; i += 2) {
-        const float e0 = ex2_approx(__uint_as_float(s[i]) - m_use);
-        const float e1 = ex2_approx(__uint_as_float(s[i + 1]) - m_use);
-        rs += e0 + e1;
-        s[i >> 1] = pack_bf16x2(e0, e1);            // P packed in place: s[0..63]
-      }
-      l_run = l_run * alpha + rs;
+      for (int i = 0; i < BKV; i += 2)
+        s[i >> 1] = pack_bf16x2(ex2_approx(__uint_as_float(s[i]) - m_use), ex2_approx(__uint_as_float(s[i + 1]) - m_use));
+      if (pingpong) named_bar_arrive(other_turn, 256);
       m_run = m_new;
 
       if (j > 0) {
-        // fold in the previous tile's P V (this also guarantees the MMA is done reading the P buffer)
+        // fold in the previous tile's P V (this also guarantees the MMA is done reading the P buffer);
+        // column 32 of the product is that tile's row sum of the SAME bf16 probabilities (ones row of V^T)
         mbar_wait(&bars->o_full[t], (j - 1) & 1);
         tcgen05_fence_after();
-        uint32_t o[32];
+        uint32_t o[32], rsum;
         tmem_ld_32x32b_x32(t_o, o);
+        tmem_ld_32x32b_x1(t_o + DH, rsum);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < DH; ++i) acc[i] = acc[i] * alpha_pending + __uint_as_float(o[i]);
+        l_run = l_run * alpha_pending + __uint_as_float(rsum);
       }
       alpha_pending = alpha;
       // P tile -> shared memory (K-major, 128B swizzle: 16B chunk index XOR (row & 7))
 #pragma unroll
       for (int ch = 0; ch < 16; ++ch) {
-        const int kb = ch >> 3, jj = ch & 7;
-        *reinterpret_cast<uint4*>(p_row + kb * (P_BYTES / 2) + ((jj ^ (r & 7)) << 4)) =
-            make_uint4(s[ch * 4], s[ch * 4 + 1], s[ch * 4 + 2], s[ch * 4 + 3]);
+        const uint32_t addr = p_row_addr + (ch >> 3) * (P_BYTES / 2) + ((static_cast<uint32_t>(ch & 7) << 4) ^ swz);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(s[ch * 4]), "r"(s[ch * 4 + 1]),
+                     "r"(s[ch * 4 + 2]), "r"(s[ch * 4 + 3])
+                     : "memory");
       }
       fence_proxy_async_smem();
       tcgen05_fence_before();
@@ -238,11 +290,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_wait(&bars->o_full[t], (n_tiles - 1) & 1);
     tcgen05_fence_after();
     {
-      uint32_t o[32];
+      uint32_t o[32], rsum;
       tmem_ld_32x32b_x32(t_o, o);
+      tmem_ld_32x32b_x1(t_o + DH, rsum);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < DH; ++i) acc[i] = acc[i] * alpha_pending + __uint_as_float(o[i]);
+      l_run = l_run * alpha_pending + __uint_as_float(rsum);
     }
     const int q = q0 + t * BQ + r;
     if (q < Lq) {

@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Runs one kernel of the hot path at the headline (C2) shapes a few times -- the target command for
+`ncu --set full` captures:   python tools/run_kernel.py attn_self | attn_cross | gemm_ffn_up | gemm_ffn_down | gemm_qk"""
+import math
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from svol_b200 import ops
+
+which = sys.argv[1] if len(sys.argv) > 1 else "attn_self"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = torch.device("cuda:0")
+B, L, Q, H, d, ff = 32, 1568, 320, 8, 256, 2048
+g = torch.Generator(device="cpu").manual_seed(0)
+rnd = lambda *s: torch.randn(*s, generator=g)
+
+if which.startswith("attn"):
+    Lq, Lk = (L, L) if which == "attn_self" else ((Q, L) if which == "attn_cross" else (Q, Q))
+    q = (rnd(B * Lq, d) * math.log2(math.e) / math.sqrt(32)).to(torch.bfloat16).to(dev)
+    k = rnd(B * Lk, d).to(torch.bfloat16).to(dev)
+    pitch = (Lk + 7) // 8 * 8
+    vt = torch.zeros(B * d, pitch, dtype=torch.bfloat16)
+    vt[:, :Lk] = rnd(B * d, Lk).to(torch.bfloat16)
+    vt = vt.to(dev)
+    mask = torch.ones(B, Lk, device=dev) if which == "attn_cross" else None
+    fn = lambda: ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask)
+else:
+    M = B * L
+    if which == "gemm_ffn_up":
+        K, N, kw = d, ff, dict(act=ops.ACT_GELU)
+    elif which == "gemm_ffn_down":
+        K, N, kw = ff, d, dict(residual=True, ln=True, pos=True)
+    else:
+        K, N, kw = d, 2 * d, dict()
+    A = rnd(M, K).to(torch.bfloat16).to(dev)
+    W = (rnd(N, K) / math.sqrt(K)).to(torch.bfloat16).to(dev)
+    bias = rnd(N).to(dev)
+    res = rnd(M, N).to(torch.bfloat16).to(dev) if kw.pop("residual", False) else None
+    ln = (torch.ones(N, device=dev), torch.zeros(N, device=dev)) if kw.pop("ln", False) else None
+    pos = rnd(M, N).to(dev) if kw.pop("pos", False) else None
+    fn = lambda: ops.gemm(A, W, bias, residual=res, ln=ln, pos=pos, **kw)
+
+for _ in range(reps):
+    fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(reps):
+    fn()
+e1.record()
+torch.cuda.synchronize()
+print(f"{which}: {e0.elapsed_time(e1) / reps * 1e3:.1f} us per launch")
