@@ -12,15 +12,18 @@
 //   warps 4..7  softmax warpgroup B: thread = query row of tile B
 //               per key tile: S tile TMEM -> 128 registers in ONE pass (the TMEM buffer is released
 //               to the MMA warp immediately, so the next QK^T overlaps this tile's exponentials),
-//               row max, ex2, bf16 P tile -> shared memory in the 128B-swizzled K-major layout the MMA
-//               reads; running max / sum / 32-wide output accumulator stay in registers.
+//               row max, ex2, bf16 P tile -> TENSOR MEMORY (tcgen05.st; the P V MMA reads its A operand
+//               from TMEM, so probabilities never touch shared memory and no generic->async proxy fence
+//               is needed); running max / sum / 32-wide output accumulator stay in registers.
 //   warp 8      TMA producer: both Q tiles once, then a 3-stage ring of K tiles (128 x 32, 64B swizzle)
 //               and V^T tiles (32 x 128, 128B swizzle) shared by the two query tiles.
-//   warp 9      MMA issuer: S = Q K^T (M128 N128 K32) and O_tile = P V (M128 N32 K128) for both tiles,
-//               fp32 accumulators in TMEM (S_A, S_B, O_A, O_B = 320 of 512 columns).
-// The two warpgroups ping-pong on the tensor pipe: while A exponentiates tile j, the MMA warp computes
-// B's scores and A's previous P V.  With head_dim 32 the kernel is bound by the 16 ex2/clk/SM of the
-// MUFU pipe (128 tensor FLOPs per exponential), not by the tensor pipe; see DESIGN.md.
+//   warp 9      MMA issuer: S = Q K^T (M128 N128 K32, both operands in shared memory) and
+//               O_tile = P V (M128 N48 K128, A = P in TMEM, B = V^T in shared memory) for both tiles,
+//               fp32 accumulators in TMEM.
+// TMEM map (512 columns): S_A [0,128) S_B [128,256) P_A [256,320) P_B [320,384) O_A [384,432) O_B [448,496).
+// Each SM sub-partition hosts one warp of A and one of B; while one of them is in its ex2 section the other
+// loads / reduces / stores, which keeps the MUFU pipe (16 ex2/clk/SM) -- the binding unit at head_dim 32:
+// 128 tensor FLOPs per exponential -- busy.  See DESIGN.md.
 // Q is pre-scaled by log2(e)/sqrt(dh) when it is produced, so the softmax is a bare ex2.
 #include "common.cuh"
 #include "svol_internal.h"
@@ -35,12 +38,11 @@ constexpr int NV = DH + 16;                     // V^T rows fed to the P V MMA: 
                                                 // (-> column 32 of the product is the softmax row sum), 15 zero rows
 constexpr int VT_KB_BYTES = NV * 128;           // one 64-key k-block of V^T: 48 rows x 128 B (TMA fills rows 0..31)
 constexpr int VT_BYTES = 2 * VT_KB_BYTES;       // 12288
-constexpr int P_BYTES = BQ * BKV * 2;           // 32768 = 2 k-blocks of 128 rows x 128 B
-constexpr int OFF_K = 2 * Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES, OFF_P = OFF_VT + STAGES * VT_BYTES;
-constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+constexpr int OFF_K = 2 * Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES;
+constexpr int OFF_BAR = OFF_VT + STAGES * VT_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 384;   // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle warps}
-constexpr uint32_t TMEM_COLS = 512, TMEM_O = 256, TMEM_O_STRIDE = 64;   // S_A [0,128) S_B [128,256) O_A [256,304) O_B [320,368)
+constexpr uint32_t TMEM_COLS = 512, TMEM_P = 256, TMEM_P_STRIDE = 64, TMEM_O = 384, TMEM_O_STRIDE = 64;
 constexpr int TMA_VT_BYTES = 2 * DH * 128;      // bytes the two V^T TMA boxes deliver per stage
 }  // namespace attn
 
@@ -50,6 +52,21 @@ struct AttnBars {
   uint64_t kv_full[attn::STAGES], kv_empty[attn::STAGES];
   uint32_t tmem_base, pad;
 };
+
+#ifdef SVOL_ATTN_TRACE
+// Debug build only (-DSVOL_ATTN_TRACE): CTA (0,0,0) records clock64() at phase boundaries of every key tile.
+__device__ long long g_attn_trace[4][64][8];
+#define SVOL_TR(role, j, slot)                                                             \
+  do {                                                                                     \
+    if (trace_on && (j) < 64) {                                                            \
+      long long c_;                                                                        \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)::"memory");                          \
+      g_attn_trace[role][j][slot] = c_;                                                    \
+    }                                                                                      \
+  } while (0)
+#else
+#define SVOL_TR(role, j, slot) do {} while (0)
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -61,11 +78,29 @@ __device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
 }
-__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : A is a 128-lane x (K/2)-column block of packed bf16 pairs; ONE thread issues.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // Row maximum of the 128 scores a thread holds; kMasked additionally overwrites invalid keys with -inf.
@@ -100,6 +135,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int q0 = blockIdx.x * (2 * BQ), h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (Lk + BKV - 1) / BKV;
   const int n_q = (q0 + BQ < Lq) ? 2 : 1;          // is the second query tile of this CTA populated?
+#ifdef SVOL_ATTN_TRACE
+  const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+#endif
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
@@ -156,40 +194,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
       constexpr uint32_t idesc_o = make_idesc_bf16(BQ, NV);
-      auto issue_pv = [&](int j) {
-        const uint32_t sV = smem_u32(smem + OFF_VT + (j % STAGES) * VT_BYTES);
-        for (int t = 0; t < n_q; ++t) {
-          mbar_wait(&bars->p_ready[t], j & 1);
-          tcgen05_fence_after();
-          const uint32_t sP = smem_u32(smem + OFF_P + t * P_BYTES);
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            const uint64_t a_desc = make_kmajor_desc<128>(sP + (k >> 2) * (P_BYTES / 2) + (k & 3) * 32);
-            const uint64_t b_desc = make_kmajor_desc<128>(sV + (k >> 2) * VT_KB_BYTES + (k & 3) * 32);
-            umma_bf16_ss(tmem_base + TMEM_O + t * TMEM_O_STRIDE, a_desc, b_desc, idesc_o, k != 0);
-          }
-          umma_commit(&bars->o_full[t]);
-        }
-        umma_commit(&bars->kv_empty[j % STAGES]);
-      };
+      // descriptors differ only in their 14-bit start-address field (bytes >> 4): plain integer adds below
+      const uint64_t dQ = make_kmajor_desc<64>(smem_u32(smem));
+      const uint64_t dK = make_kmajor_desc<64>(smem_u32(smem + OFF_K));
+      const uint64_t dV = make_kmajor_desc<128>(smem_u32(smem + OFF_VT));
       mbar_wait(&bars->q_full, 0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % STAGES;
-        mbar_wait(&bars->kv_full[s], (j / STAGES) & 1);
-        const uint32_t sK = smem_u32(smem + OFF_K + s * K_BYTES);
-        for (int t = 0; t < n_q; ++t) {
-          if (j > 0) mbar_wait(&bars->s_free[t], (j - 1) & 1);
-          tcgen05_fence_after();
-          const uint32_t sQ = smem_u32(smem + t * Q_BYTES);
+      for (int j = 0; j <= n_tiles; ++j) {
+        if (j < n_tiles) {
+          const int s = j % STAGES;
+          SVOL_TR(2, j, 0);
+          mbar_wait(&bars->kv_full[s], (j / STAGES) & 1);
+          SVOL_TR(2, j, 1);
+          const uint64_t dKs = dK + static_cast<uint64_t>(s * (K_BYTES >> 4));
+          for (int t = 0; t < n_q; ++t) {
+            if (j > 0) mbar_wait(&bars->s_free[t], (j - 1) & 1);
+            SVOL_TR(2, j, 2 + t);
+            tcgen05_fence_after();
+            const uint64_t dQt = dQ + static_cast<uint64_t>(t * (Q_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k)
-            umma_bf16_ss(tmem_base + t * BKV, make_kmajor_desc<64>(sQ + k * 32), make_kmajor_desc<64>(sK + k * 32),
-                         idesc_s, k != 0);
-          umma_commit(&bars->s_full[t]);
+            for (int k = 0; k < DH / 16; ++k)
+              umma_bf16_ss(tmem_base + t * BKV, dQt + 2 * k, dKs + 2 * k, idesc_s, k != 0);
+            umma_commit(&bars->s_full[t]);
+          }
         }
-        if (j > 0) issue_pv(j - 1);
+        if (j > 0) {
+          const int jp = j - 1, sp = jp % STAGES;
+          const uint64_t dVs = dV + static_cast<uint64_t>(sp * (VT_BYTES >> 4));
+          for (int t = 0; t < n_q; ++t) {
+            mbar_wait(&bars->p_ready[t], jp & 1);
+            SVOL_TR(2, j, 4 + t);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int k = 0; k < BKV / 16; ++k)
+              umma_bf16_ts(tmem_base + TMEM_O + t * TMEM_O_STRIDE, tmem_base + TMEM_P + t * TMEM_P_STRIDE + k * 8,
+                           dVs + static_cast<uint64_t>((k >> 2) * (VT_KB_BYTES >> 4) + (k & 3) * 2), idesc_o, k != 0);
+            umma_commit(&bars->o_full[t]);
+          }
+          umma_commit(&bars->kv_empty[sp]);
+        }
       }
-      issue_pv(n_tiles - 1);
     }
    }
   } else {
@@ -201,30 +244,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int r = quarter * 32 + lane;                  // row inside the tile == TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t t_s = t_lane + t * BKV, t_o = t_lane + TMEM_O + t * TMEM_O_STRIDE;
-    uint8_t* p_row = smem + OFF_P + t * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+    const uint32_t t_p = t_lane + TMEM_P + t * TMEM_P_STRIDE;
     const float* mrow = key_mask ? key_mask + static_cast<size_t>(b) * Lk : nullptr;
     float m_run = -INFINITY, l_run = 0.f, alpha_pending = 0.f;
     float acc[DH];
 #pragma unroll
     for (int i = 0; i < DH; ++i) acc[i] = 0.f;
 
-    // Ping-pong between the two softmax warpgroups (named barriers 1 and 2): the exponential section of
-    // one warpgroup saturates the MUFU pipe on its own, so the two sections are made mutually exclusive and
-    // each warpgroup's TMEM loads, row max, accumulator fold and P store run under the other's exponentials.
-    const bool pingpong = n_q == 2;
-    const int my_turn = 1 + t, other_turn = 2 - t;
-    if (pingpong && t == 1) named_bar_arrive(1, 256);        // warpgroup A goes first
-    const uint32_t p_row_addr = smem_u32(p_row);
-    const uint32_t swz = static_cast<uint32_t>(r & 7) << 4;
+    // Stagger: warpgroup B starts half a period late (after A's first ex2 section), so that on every SM
+    // sub-partition one warp's ex2 section runs under the other's load / max / fold / store phases.  Both
+    // warpgroups have the same period, so the offset persists without further synchronisation.
+    if (n_q == 2 && t == 1) asm volatile("bar.sync 1, 256;" ::: "memory");
 
     for (int j = 0; j < n_tiles; ++j) {
       const int kv0 = j * BKV;
+#ifdef SVOL_ATTN_TRACE
+      const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && quarter == 0;
+#endif
+      SVOL_TR(t, j, 0);
       mbar_wait(&bars->s_full[t], j & 1);
+      SVOL_TR(t, j, 1);
       tcgen05_fence_after();
       uint32_t s[BKV];
 #pragma unroll
       for (int c = 0; c < BKV / 32; ++c) tmem_ld_32x32b_x32(t_s + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&s[c * 32]));
       tmem_ld_wait();
+      SVOL_TR(t, j, 2);
       // scores are in registers: hand the TMEM buffer back so the next QK^T can start now
       tcgen05_fence_before();
       __syncwarp();
@@ -249,20 +294,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_new = fmaxf(m_run, mx);
       const float m_use = m_new == -INFINITY ? 0.f : m_new;
       const float alpha = ex2_approx(m_run - m_use);
-
-      if (pingpong) named_bar_sync(my_turn, 256);
-      // one MUFU ex2 per probability (ex2.approx.ftz.bf16x2 was tried: on sm_100 it is issued as two
-      // MUFU.EX2.BF16 ops plus a PRMT, so it saves nothing and only costs precision)
-#pragma unroll
-      for (int i = 0; i < BKV; i += 2)
-        s[i >> 1] = pack_bf16x2(ex2_approx(__uint_as_float(s[i]) - m_use), ex2_approx(__uint_as_float(s[i + 1]) - m_use));
-      if (pingpong) named_bar_arrive(other_turn, 256);
       m_run = m_new;
+      SVOL_TR(t, j, 3);
+
+      // one MUFU ex2 per probability (ex2.approx.ftz.bf16x2 was tried: on sm_100 it is issued as two
+      // MUFU.EX2.BF16 ops plus a PRMT, so it saves nothing and only costs precision); the subtraction
+      // of the row max is a packed FADD2
+      const float2 neg_m = make_float2(-m_use, -m_use);
+#pragma unroll
+      for (int i = 0; i < BKV; i += 2) {
+        const float2 x = __fadd2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), neg_m);
+        s[i >> 1] = pack_bf16x2(ex2_approx(x.x), ex2_approx(x.y));
+      }
+      SVOL_TR(t, j, 5);
+      if (j == 0 && n_q == 2 && t == 0)   // (register inputs keep the ex2 section in front of the arrive)
+        asm volatile("bar.arrive 1, 256;" ::"r"(s[15]), "r"(s[31]), "r"(s[47]), "r"(s[63]) : "memory");
 
       if (j > 0) {
-        // fold in the previous tile's P V (this also guarantees the MMA is done reading the P buffer);
+        // fold in the previous tile's P V (this also guarantees the MMA is done reading the P columns);
         // column 32 of the product is that tile's row sum of the SAME bf16 probabilities (ones row of V^T)
         mbar_wait(&bars->o_full[t], (j - 1) & 1);
+        SVOL_TR(t, j, 6);
         tcgen05_fence_after();
         uint32_t o[32], rsum;
         tmem_ld_32x32b_x32(t_o, o);
@@ -273,18 +325,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         l_run = l_run * alpha_pending + __uint_as_float(rsum);
       }
       alpha_pending = alpha;
-      // P tile -> shared memory (K-major, 128B swizzle: 16B chunk index XOR (row & 7))
-#pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {
-        const uint32_t addr = p_row_addr + (ch >> 3) * (P_BYTES / 2) + ((static_cast<uint32_t>(ch & 7) << 4) ^ swz);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(s[ch * 4]), "r"(s[ch * 4 + 1]),
-                     "r"(s[ch * 4 + 2]), "r"(s[ch * 4 + 3])
-                     : "memory");
-      }
-      fence_proxy_async_smem();
+      // P tile -> tensor memory: lane = query row, 64 columns of packed bf16 pairs (the A operand of P V)
+      tmem_st_32x32b_x32(t_p, &s[0]);
+      tmem_st_32x32b_x32(t_p + 32, &s[32]);
+      tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_ready[t]);
+      SVOL_TR(t, j, 7);
     }
     // last tile
     mbar_wait(&bars->o_full[t], (n_tiles - 1) & 1);
@@ -348,3 +396,9 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace svol
+
+#ifdef SVOL_ATTN_TRACE
+extern "C" int svol_debug_attn_trace(long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, svol::g_attn_trace, sizeof(svol::g_attn_trace)));
+}
+#endif

@@ -60,13 +60,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait.  `parity` is the phase bit of the completion being waited for.
+// Bounded wait.  `parity` is the phase bit of the completion being waited for.  A wait that never completes
+// traps (the launch fails with an error instead of hanging the GPU); build with -DSVOL_DEBUG_TIMEOUT to also
+// print which barrier it was -- kept out of the default build because the printf argument marshalling costs
+// stack traffic in the register-starved TMA / MMA warps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > SVOL_SPIN_LIMIT) {
+#ifdef SVOL_DEBUG_TIMEOUT
       printf("svol_b200: mbarrier timeout block (%d,%d,%d) thread %d bar %u parity %u\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }
