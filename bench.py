@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step")
     ap.add_argument("--layers", type=int, default=2)
     ap.add_argument("--config", default="C2", help="svol_b200.synth.CONFIGS key (C2 = BASELINE configs[1])")
-    ap.add_argument("--graph", type=int, default=0, help="replay the forward as one CUDA graph")
+    ap.add_argument("--graph", type=int, default=1, help="replay the forward as one CUDA graph")
     ap.add_argument("--ref-batch", type=int, default=2, help="pairs per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-kernel time table to this file")
@@ -156,7 +156,7 @@ def main():
     import torch
     import torch.distributed as dist
     from dataclasses import replace
-    from svol_b200 import synth
+    from svol_b200 import comm, synth
     from svol_b200.modeling import build_loss, build_svanet
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,10 +253,7 @@ def main():
                     fn(i)
             e1.record()
             barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps
+        return comm.max_over_ranks(e0.elapsed_time(e1), device=dev) / steps      # slowest rank
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -364,16 +361,20 @@ def kernel_breakdown(model, inset, cfg, B, dev):
     lines.append(f"{'TOTAL':34s} {len(med):8d} {total:10.4f}")
     top, (t_top, n_top) = rows[0]
     per_launch_ms = t_top / n_top
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top, {}).get("bytes")
     if top in flops:
         achieved = flops[top] / (per_launch_ms * 1e-3) / 1e12
         peak = float(peaks["bf16_tflops_sustained"])
         roof = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "ms_per_launch": per_launch_ms, "share_of_forward": t_top / total,
+                "traffic": traffic, "ms_per_launch": per_launch_ms, "share_of_forward": t_top / total,
                 "peak_source": f"{peaks['_src']} bf16_tflops_sustained (kernel timed inside the step)",
                 "algorithmic_flops_per_launch": flops[top]}
     else:
         roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s", "frac": None,
-                "traffic": None, "ms_per_launch": per_launch_ms, "share_of_forward": t_top / total}
+                "traffic": traffic, "ms_per_launch": per_launch_ms, "share_of_forward": t_top / total}
     return roof, "\n".join(lines) + "\n"
 
 

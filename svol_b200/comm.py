@@ -1,0 +1,83 @@
+"""Data-parallel plumbing, mirror of lib/utils/comm.py:5-25 plus the pair sharding the reference leaves to its
+launch scripts (train_quickdraw.sh:34-37: one process per GPU; svol_dataloader.py:70: videos_per_gpu = bs // gpus).
+
+Sketch-video pairs are independent through forward, matching and per-pair loss terms, so the hot path needs NO
+data-path collective: every rank processes its own shard.  The only collectives are the ones the reference has
+(loss averaging for logging, comm.py:21-25) and the max-over-ranks of device timings in bench.py.  Works on any
+torch.distributed backend (NCCL on the B200 box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def is_distributed() -> bool:
+    return dist.is_available() and dist.is_initialized()
+
+
+def get_rank() -> int:                       # comm.py:5-10
+    return dist.get_rank() if is_distributed() else 0
+
+
+def get_world_size() -> int:                 # comm.py:13-18
+    return dist.get_world_size() if is_distributed() else 1
+
+
+def reduce_tensor(tensor: torch.Tensor, world_size: int = None) -> torch.Tensor:
+    """clone -> all_reduce(SUM) -> / world_size (comm.py:21-25)."""
+    world_size = world_size or get_world_size()
+    rt = tensor.clone()
+    if is_distributed():
+        dist.all_reduce(rt, op=dist.ReduceOp.SUM)
+    rt /= world_size
+    return rt
+
+
+def shard_range(n_items: int, rank: int = None, world_size: int = None) -> Tuple[int, int]:
+    """Contiguous, balanced [begin, end) of rank's items: the first n % world ranks get one extra.  Every item is
+    owned by exactly one rank, ranks keep global order (so concatenating rank results restores batch order)."""
+    rank = get_rank() if rank is None else rank
+    world_size = get_world_size() if world_size is None else world_size
+    base, extra = divmod(n_items, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """The slowest rank's value (device timings are reported as the max over ranks)."""
+    if not is_distributed():
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_loss_dict(loss_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """Averages every entry over ranks in ONE collective (train.py:240 reduces the summed loss per iteration;
+    folding all entries into one flat buffer keeps it to a single small all-reduce)."""
+    if not is_distributed() or not loss_dict:
+        return dict(loss_dict)
+    keys = sorted(loss_dict)
+    flat = torch.stack([loss_dict[k].detach().float().reshape(()) for k in keys])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= get_world_size()
+    return {k: flat[i] for i, k in enumerate(keys)}
+
+
+def all_gather_indices(local: torch.Tensor) -> torch.Tensor:
+    """Concatenates variable-length 1-D int64 tensors of all ranks in rank order (gathering matched indices of
+    the rank shards back into batch order for evaluation)."""
+    if not is_distributed():
+        return local
+    world = get_world_size()
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    m = int(max(int(s.item()) for s in sizes))
+    pad = torch.zeros(m, dtype=local.dtype, device=local.device)
+    pad[: local.numel()] = local
+    bufs = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    return torch.cat([b[: int(s.item())] for b, s in zip(bufs, sizes)])

@@ -7,7 +7,8 @@
     log2(e)/sqrt(d_head) so the attention softmax is a bare ex2) and re-packed when a parameter's
     version counter or storage changes;
   * activations live in a per-(batch, video length) workspace whose addresses never change, so the
-    whole forward can be captured in one CUDA graph and replayed (``use_graph=True``);
+    forward after its first kernel is captured in one CUDA graph and replayed (``use_graph=True``, the
+    default; the first kernel reads the caller's frame features in place);
   * activations are batch-major ``[B*L, 256]`` bf16 row matrices; attention V operands are stored
     transposed per head (``[B*8*32, L_pad]``) directly by the projection GEMM's epilogue.
 
@@ -46,15 +47,15 @@ class _Plan:
         self.buf: Dict[str, torch.Tensor] = {}
         self.graph = None
 
-    def run(self, stream: int) -> None:
-        for name, fn, args in self.calls:
+    def run(self, stream: int, start: int = 0) -> None:
+        for name, fn, args in self.calls[start:]:
             rc = fn(*args, stream)
             if rc != 0:
                 _lib.check(rc, name)
 
 
 class HeadEngine:
-    def __init__(self, module, use_graph: bool = False):
+    def __init__(self, module, use_graph: bool = True):
         self.module = module
         self.use_graph = use_graph
         self.plain = os.environ.get("SVOL_B200_PLAIN", "0") == "1"   # debug: SIMT kernels instead of tcgen05
@@ -322,35 +323,38 @@ class HeadEngine:
         B, L, d_in = src_video.shape
         plan = self.plan_for(B, L, d_in)
         b = plan.buf
-        if src_video.data_ptr() != b["src_video"].data_ptr():
-            if (not self.use_graph and src_video.is_cuda and src_video.dtype == torch.float32
-                    and src_video.is_contiguous() and src_video.data_ptr() % 16 == 0):
-                # zero-copy: point the first kernel (LayerNorm of the frame tokens) at the caller's tensor
-                name, fn, args = plan.calls[plan.ln_in_index]
-                plan.calls[plan.ln_in_index] = (name, fn, (src_video.data_ptr(),) + tuple(args[1:]))
-            else:
-                b["src_video"].copy_(src_video, non_blocking=True)
-                name, fn, args = plan.calls[plan.ln_in_index]
-                plan.calls[plan.ln_in_index] = (name, fn, (b["src_video"].data_ptr(),) + tuple(args[1:]))
+        # The first kernel (LayerNorm of the frame tokens, the only reader of the 100 MB fp32 input) always runs
+        # eagerly and reads the caller's tensor in place; everything after it works on plan-owned buffers and can
+        # be replayed as one CUDA graph.
+        src = src_video
+        if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and src.data_ptr() % 16 == 0):
+            b["src_video"].copy_(src_video, non_blocking=True)
+            src = b["src_video"]
         if src_sketch.data_ptr() != b["src_sketch"].data_ptr():
             if src_sketch.dim() == 3 and src_sketch.shape[1] != 1:
                 raise NotImplementedError("svol_b200 supports one sketch token per pair (L_sketch == 1)")
             b["src_sketch"].copy_(src_sketch.reshape(B, -1), non_blocking=True)
         if src_video_mask.data_ptr() != b["src_video_mask"].data_ptr():
             b["src_video_mask"].copy_(src_video_mask, non_blocking=True)
+        assert plan.ln_in_index == 0
+        name, fn, args = plan.calls[0]
+        rc = fn(src.data_ptr(), *args[1:], torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            _lib.check(rc, name)
         self.run_plan(plan)
         return b["logits"], b["boxes"]
 
     def run_plan(self, plan: _Plan) -> None:
+        """Runs calls[1:] of the plan (everything after the input LayerNorm), eagerly or as a graph replay."""
         if self.use_graph:
             if plan.graph is None:
                 # warm-up run outside capture (sets function attributes, loads modules)
-                plan.run(torch.cuda.current_stream().cuda_stream)
+                plan.run(torch.cuda.current_stream().cuda_stream, start=1)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    plan.run(torch.cuda.current_stream().cuda_stream)
+                    plan.run(torch.cuda.current_stream().cuda_stream, start=1)
                 plan.graph = g
             plan.graph.replay()
         else:
-            plan.run(torch.cuda.current_stream().cuda_stream)
+            plan.run(torch.cuda.current_stream().cuda_stream, start=1)

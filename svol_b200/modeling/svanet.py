@@ -37,7 +37,7 @@ class SVANet(nn.Module):
 
     def __init__(self, transformer, sketch_position_embed, video_position_embed, input_vid_dim, input_skch_dim,
                  num_queries, input_dropout=0.1, aux_loss=True, use_sketch_pos=True, n_input_proj=2, num_classes=2,
-                 vis_mode=None, use_graph=False):
+                 vis_mode=None, use_graph=True):
         super().__init__()
         self.num_queries = num_queries
         self.num_classes = num_classes
@@ -96,5 +96,5 @@ def build_svanet(args):
         input_vid_dim=args.input_vid_dim, input_skch_dim=args.input_skch_dim, num_queries=args.num_queries,
         input_dropout=args.input_dropout, aux_loss=args.aux_loss, use_sketch_pos=args.use_sketch_pos,
         n_input_proj=args.n_input_proj, vis_mode=args.vis_mode,
-        use_graph=bool(getattr(args, "use_cuda_graph", False)),
+        use_graph=bool(getattr(args, "use_cuda_graph", True)),
     )

@@ -32,23 +32,25 @@ for _ in range(3):
     ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask)
 torch.cuda.synchronize()
 lib = _lib.get_lib()
-buf = np.zeros((4, 64, 8), dtype=np.int64)
+buf = np.zeros((6, 64, 8), dtype=np.int64)
 rc = lib.svol_debug_attn_trace(C.c_void_p(buf.ctypes.data))
 assert rc == 0, rc
 n = (Lk + 127) // 128
 t0 = buf[buf > 0].min()
-names = {0: "softmax A (warp 0)", 1: "softmax B (warp 4)", 2: "MMA issuer"}
-slots = {0: ["top", "s_full", "S->reg", "max", "turn", "exp", "o_full", "P stored"],
-         2: ["top", "kv_full", "s_freeA", "s_freeB", "p_rdyA(j-1)", "p_rdyB(j-1)", "-", "-"]}
-for role in (0, 1, 2):
+names = {0: "softmax g0 (tile 0, keys lo)", 1: "softmax g1 (tile 0, keys hi)", 2: "softmax g2 (tile 1, keys lo)",
+         3: "softmax g3 (tile 1, keys hi)", 4: "MMA issuer tile 0", 5: "MMA issuer tile 1"}
+slots = {0: ["top", "s_full", "S->reg", "max", "-", "exp", "o_full", "P stored"],
+         4: ["top", "kv+s_free", "p_rdy lo", "p_rdy hi", "-", "-", "-", "-"]}
+for role in range(6):
     print(names[role])
-    sl = slots[2 if role == 2 else 0]
+    sl = slots[4 if role >= 4 else 0]
     print("  j " + " ".join(f"{s:>11}" for s in sl))
-    for j in range(n + (1 if role == 2 else 0)):
+    for j in range(n + (1 if role >= 4 else 0)):
         row = buf[role, j]
         print(f" {j:2d} " + " ".join(f"{(v - t0) if v > 0 else -1:11d}" for v in row))
-    if role < 2:
+    if role < 4:
         per = np.diff(buf[role, 1:n, 7]).mean()
         d_ = buf[role, 2:n, :].astype(np.float64)
+        pairs = [(0, 1), (1, 2), (2, 3), (3, 5), (5, 6), (6, 7)]
         print(f"  steady period {per:.0f} clk; mean phase lengths: "
-              + ", ".join(f"{sl[i]}->{sl[i + 1]} {np.mean(d_[:, i + 1] - d_[:, i]):.0f}" for i in range(7)))
+              + ", ".join(f"{sl[a]}->{sl[b_]} {np.mean(d_[:, b_] - d_[:, a]):.0f}" for a, b_ in pairs))
