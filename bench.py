@@ -37,7 +37,7 @@ UNIT = "pairs/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step")
@@ -62,14 +62,52 @@ def workload_config(args, cfg):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples the SM clock and the throttle reasons while the timed region runs.  NVML is queried in-process
+    (a thread, one sample every 10 ms): polling through a spawned `nvidia-smi -lms` loop was measured to slow the
+    timed steps themselves by ~20 % (driver lock contention with kernel / graph launches).  nvidia-smi is only
+    the fallback when the NVML binding is unavailable."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.thread, self.stop_flag, self.max_mhz = None, None, None, False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: `index` is the CUDA ordinal of this process
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((mhz, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
+        self.rows = []
+        if self.nvml is not None:
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -83,6 +121,13 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = [r[0] for r in self.rows]
+            reasons = sorted({k for r in self.rows for k in r[1]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml, 10 ms period, timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -92,7 +137,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
@@ -236,7 +281,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, whole_loop=False):
+    def timed(fn, steps, warmup, whole_loop=False, sampler=None):
         with torch.no_grad():
             if whole_loop:
                 fn(warmup)
@@ -244,6 +289,8 @@ def main():
                 for i in range(warmup):
                     fn(i)
             barrier()
+            if sampler is not None:
+                sampler.start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             if whole_loop:
@@ -255,10 +302,8 @@ def main():
             barrier()
         return comm.max_over_ranks(e0.elapsed_time(e1), device=dev) / steps      # slowest rank
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ms_step = timed(step_resident, args.steps, max(args.warmup, 3))
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step = timed(step_resident, args.steps, max(args.warmup, 3), sampler=sampler)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(run_e2e, args.steps, 3, whole_loop=True)
     with torch.no_grad():
@@ -339,11 +384,10 @@ def kernel_breakdown(model, inset, cfg, B, dev):
     def fam(name):
         n = name.split(".")[-1]
         return {"sa_attn": "attention(video self)", "ta_attn": "attention(query self)", "ca_attn": "attention(cross)",
-                "ffn1_up": "gemm ffn1_up+GELU", "ffn1_down": "gemm ffn1_down+res+LN", "ffn2_up": "gemm ffn2_up+GELU",
-                "ffn2_down": "gemm ffn2_down+res+LN"}.get(n, n)
+                "ffn1": "fused FFN (video tokens)", "ffn2": "fused FFN (queries)"}.get(n, n)
     flops = {"attention(video self)": 4.0 * L * L * d * B, "attention(query self)": 4.0 * Q * Q * d * B,
-             "attention(cross)": 4.0 * Q * L * d * B, "gemm ffn1_up+GELU": 2.0 * M * d * ff, "gemm ffn1_down+res+LN": 2.0 * M * d * ff,
-             "gemm ffn2_up+GELU": 2.0 * MQ * d * ff, "gemm ffn2_down+res+LN": 2.0 * MQ * d * ff,
+             "attention(cross)": 4.0 * Q * L * d * B, "fused FFN (video tokens)": 4.0 * M * d * ff,
+             "fused FFN (queries)": 4.0 * MQ * d * ff,
              "sa_qk": 2.0 * M * d * 2 * d, "sa_v": 2.0 * M * d * d, "sa_out": 2.0 * M * d * d, "in_proj0": 2.0 * M * D * d,
              "in_proj1": 2.0 * M * d * d, "ca_k": 2.0 * M * d * d, "ca_v": 2.0 * M * d * d}
     agg = {}

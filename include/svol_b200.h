@@ -43,7 +43,7 @@ const char* svol_last_error(void);
 /* 0 if the current device can run this library (sm_100), SVOL_ERR_DEVICE otherwise. */
 int svol_device_check(void);
 /* sizeof() of the argument structures as this library was compiled (0 gemm_args, 1 attn_args,
- * 2 match_args, 3 criterion_args, 4 gemm_epilogue) -- lets a foreign-language binding verify its
+ * 2 match_args, 3 criterion_args, 4 gemm_epilogue, 5 ffn_args) -- lets a foreign-language binding verify its
  * struct layout before the first launch. */
 int svol_sizeof_args(int which);
 
@@ -90,6 +90,36 @@ int svol_gemm_bf16(const svol_gemm_args* args, void* stream);
 int svol_gemm_bf16_plain(const svol_gemm_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused FFN block:  out = LayerNorm(x + fc2(GELU_erf(fc1(x))))   (and optionally out_pos = out + pos).
+ * Replaces MLP.forward + residual + norm3 / norm6 (lib/modeling/cross_modal_transformer.py:142-143,
+ * 157-158,163-179).  The [M, ff] hidden activation stays on the SM (tensor memory -> shared memory);
+ * bf16 operands, fp32 accumulation.  Requirements: d == 256, ff % 256 == 0, ff <= 2048, 16-byte aligned
+ * buffers with row pitches multiple of 8 elements.
+ *   x [M, ldx] bf16; w1 [ff, ldw1] bf16 (fc1.weight); b1 [ff] fp32; w2 [d, ldw2] bf16 (fc2.weight); b2 [d] fp32
+ *   ln_weight / ln_bias [d] fp32; out, out_pos [M, ld_out] bf16; pos fp32 rows (row, or row % pos_row_mod)
+ *   reserved must be 0.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct svol_ffn_args {
+  const svol_bf16* x;
+  const svol_bf16* w1;
+  const float* b1;
+  const svol_bf16* w2;
+  const float* b2;
+  const float* ln_weight;
+  const float* ln_bias;
+  svol_bf16* out;
+  svol_bf16* out_pos;       /* or NULL */
+  const float* pos;         /* fp32 table for out_pos (rows follow the output rows, or repeat with pos_row_mod) */
+  const float* pos_theta;   /* alternative to pos: fp32 [M] angles from svol_posenc_theta; the sine encoding
+                               (position_encoding.py:62-71) is then evaluated inside the kernel */
+  int32_t M, d, ff, ldx, ldw1, ldw2, ld_out, ld_pos, pos_row_mod;
+  float ln_eps;
+  int32_t reserved;
+} svol_ffn_args;
+
+int svol_ffn_bf16(const svol_ffn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Multi-head attention core, flash style (scores never leave the SM): tcgen05 QK^T and PV
  * with TMEM accumulators, TMA-fed K / V^T ring, online softmax in registers.
  * Replaces the softmax(QK^T/sqrt(dh) + mask) V part of nn.MultiheadAttention at
@@ -131,6 +161,10 @@ int svol_ln_linear_f32(const float* x, const float* ln_weight, const float* ln_b
 /* Sine positional encoding, PositionEmbeddingSine(normalize=True) (position_encoding.py:51-71).
  * mask [B,L] float (nonzero = valid) -> pos [B,L,d] fp32. */
 int svol_posenc_sine(const float* mask, float* pos, int32_t B, int32_t L, int32_t d, void* stream);
+
+/* theta[b,l] = cumsum(mask)[b,l] / (sum(mask[b]) + 1e-6) * 2 pi : the per-token angle of the normalised sine
+ * encoding (position_encoding.py:55-61); column pairs of the table are (sin, cos)(theta / dim_t).  [B*L] fp32. */
+int svol_posenc_theta(const float* mask, float* theta, int32_t B, int32_t L, void* stream);
 
 /* out[r,:] = bf16(x[r % mod,:] (+ pos[r % mod,:])) : broadcast the query embedding over the batch
  * (cross_modal_transformer.py:52-56) and build x + pos operands. */

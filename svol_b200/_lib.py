@@ -18,8 +18,8 @@ ABI_VERSION = 1
 # every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "svol_abi_version", "svol_last_error", "svol_device_check", "svol_sizeof_args",
-    "svol_gemm_bf16", "svol_gemm_bf16_plain", "svol_attention_bf16", "svol_attention_bf16_plain",
-    "svol_layernorm_f32_to_bf16", "svol_ln_linear_f32", "svol_posenc_sine", "svol_add_pos_bf16",
+    "svol_gemm_bf16", "svol_gemm_bf16_plain", "svol_ffn_bf16", "svol_attention_bf16", "svol_attention_bf16_plain",
+    "svol_layernorm_f32_to_bf16", "svol_ln_linear_f32", "svol_posenc_sine", "svol_posenc_theta", "svol_add_pos_bf16",
     "svol_gate_vectors", "svol_gate_scores", "svol_gate_apply", "svol_heads",
     "svol_match", "svol_match_localize", "svol_criterion", "svol_criterion_backward", "svol_postprocess",
 ]
@@ -38,6 +38,17 @@ class GemmArgs(C.Structure):
     _fields_ = [
         ("A", C.c_void_p), ("W", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("lda", C.c_int32), ("ldw", C.c_int32), ("reserved", C.c_int32), ("ep", GemmEpilogue),
+    ]
+
+
+class FfnArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+        ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p), ("out", C.c_void_p), ("out_pos", C.c_void_p),
+        ("pos", C.c_void_p), ("pos_theta", C.c_void_p),
+        ("M", C.c_int32), ("d", C.c_int32), ("ff", C.c_int32), ("ldx", C.c_int32), ("ldw1", C.c_int32),
+        ("ldw2", C.c_int32), ("ld_out", C.c_int32), ("ld_pos", C.c_int32), ("pos_row_mod", C.c_int32),
+        ("ln_eps", C.c_float), ("reserved", C.c_int32),
     ]
 
 
@@ -80,11 +91,13 @@ def _declare(lib: C.CDLL) -> None:
     sigs = {
         "svol_gemm_bf16": [C.POINTER(GemmArgs), _vp],
         "svol_gemm_bf16_plain": [C.POINTER(GemmArgs), _vp],
+        "svol_ffn_bf16": [C.POINTER(FfnArgs), _vp],
         "svol_attention_bf16": [C.POINTER(AttnArgs), _vp],
         "svol_attention_bf16_plain": [C.POINTER(AttnArgs), _vp],
         "svol_layernorm_f32_to_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
         "svol_ln_linear_f32": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f32, _vp],
         "svol_posenc_sine": [_vp, _vp, _i32, _i32, _i32, _vp],
+        "svol_posenc_theta": [_vp, _vp, _i32, _i32, _vp],
         "svol_add_pos_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],
         "svol_gate_vectors": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
         "svol_gate_scores": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
@@ -114,7 +127,7 @@ def get_lib() -> C.CDLL:
         _declare(lib)
         if lib.svol_abi_version() != ABI_VERSION:
             raise ImportError("libsvol_b200.so ABI version mismatch; rebuild it")
-        for which, struct in enumerate((GemmArgs, AttnArgs, MatchArgs, CriterionArgs, GemmEpilogue)):
+        for which, struct in enumerate((GemmArgs, AttnArgs, MatchArgs, CriterionArgs, GemmEpilogue, FfnArgs)):
             if lib.svol_sizeof_args(which) != C.sizeof(struct):
                 raise ImportError(f"ctypes layout of {struct.__name__} does not match libsvol_b200.so")
         _lib = lib

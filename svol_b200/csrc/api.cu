@@ -86,6 +86,7 @@ int launch_layernorm_f32_to_bf16(const float*, const float*, const float*, svol_
 int launch_ln_linear_f32(const float*, const float*, const float*, const float*, const float*, int, float*, int, int, int,
                          float, cudaStream_t);
 int launch_posenc_sine(const float*, float*, int, int, int, cudaStream_t);
+int launch_posenc_theta(const float*, float*, int, int, cudaStream_t);
 int launch_add_pos_bf16(const float*, const float*, svol_bf16*, int, int, int, cudaStream_t);
 int launch_gate_vectors(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 int launch_gate_scores(const svol_bf16*, const float*, float*, int, int, int, int, cudaStream_t);
@@ -117,6 +118,7 @@ int svol_sizeof_args(int which) {
     case 2: return static_cast<int>(sizeof(svol_match_args));
     case 3: return static_cast<int>(sizeof(svol_criterion_args));
     case 4: return static_cast<int>(sizeof(svol_gemm_epilogue));
+    case 5: return static_cast<int>(sizeof(svol_ffn_args));
     default: return -1;
   }
 }
@@ -138,6 +140,10 @@ int svol_gemm_bf16(const svol_gemm_args* a, void* stream) {
 int svol_gemm_bf16_plain(const svol_gemm_args* a, void* stream) {
   SVOL_REQUIRE(a); SVOL_REQUIRE(a->A); SVOL_REQUIRE(a->W);
   return launch_gemm_bf16_plain(*a, SVOL_STREAM(stream));
+}
+int svol_ffn_bf16(const svol_ffn_args* a, void* stream) {
+  SVOL_REQUIRE(a);
+  return launch_ffn_tc(*a, SVOL_STREAM(stream));
 }
 int svol_attention_bf16(const svol_attn_args* a, void* stream) {
   SVOL_REQUIRE(a); SVOL_REQUIRE(a->q); SVOL_REQUIRE(a->k); SVOL_REQUIRE(a->vt); SVOL_REQUIRE(a->out);
@@ -161,6 +167,10 @@ int svol_ln_linear_f32(const float* x, const float* lw, const float* lb, const f
 int svol_posenc_sine(const float* mask, float* pos, int32_t B, int32_t L, int32_t d, void* stream) {
   SVOL_REQUIRE(mask); SVOL_REQUIRE(pos);
   return launch_posenc_sine(mask, pos, B, L, d, SVOL_STREAM(stream));
+}
+int svol_posenc_theta(const float* mask, float* theta, int32_t B, int32_t L, void* stream) {
+  SVOL_REQUIRE(mask); SVOL_REQUIRE(theta);
+  return launch_posenc_theta(mask, theta, B, L, SVOL_STREAM(stream));
 }
 int svol_add_pos_bf16(const float* x, const float* pos, svol_bf16* out, int32_t rows, int32_t cols, int32_t mod,
                       void* stream) {

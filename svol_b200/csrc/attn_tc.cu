@@ -28,10 +28,14 @@
 //   warp 16      TMA producer: both Q tiles once, then a 3-stage ring of K tiles (128 x 32, 64B swizzle)
 //                and V^T tiles (32 x 128 as two 64-key blocks, 128B swizzle) shared by all warpgroups.
 //   warps 17,18  MMA issuers, one per query tile (independent instruction streams, so a late barrier of one
-//                tile never delays the other): S_t = Q_t K^T (M128 N128 K32, operands in shared memory) and
-//                O_g += P_g V_half (M128 N32 K64, A = P in TMEM, B = V^T block in shared memory).
+//                tile never delays the other): S_g = Q_t K_half^T (M128 N64 K32, operands in shared memory) and
+//                O_g += P_g V_half (M128 N32 K64, A = P in TMEM, B = V^T block in shared memory), issued in the
+//                order the staggered warpgroups make them ready: QK_lo(i), PV_hi(i-2), QK_hi(i), PV_lo(i-1).
 //   warp 19      idle (setmaxnreg works on whole warpgroups).
-// TMEM map (512 columns): S_0 [0,128) S_1 [128,256) P_g [256+32g, +32) O_g [384+32g, +32).
+// The four warpgroups are fully independent pipelines (own S / P / O columns and barriers).  They are started
+// a quarter of a key-tile period apart (g0, g2, g1, g3) so that on every sub-partition the ex2 sections of the
+// four resident warps interleave instead of colliding; equal periods keep the offsets.
+// TMEM map (512 columns): S_g [64g, +64) P_g [256+32g, +32) O_g [384+32g, +32).
 // Q is pre-scaled by log2(e)/sqrt(dh) when it is produced, so the softmax is a bare ex2.
 #include "common.cuh"
 #include "svol_internal.h"
@@ -39,7 +43,7 @@
 namespace svol {
 
 namespace attn {
-constexpr int BQ = 128, BKV = 128, HALF = 64, DH = 32, STAGES = 3;
+constexpr int BQ = 128, BKV = 128, HALF = 64, DH = 32, STAGES = 5;
 constexpr int Q_BYTES = BQ * DH * 2;            // 8192 per query tile
 constexpr int K_BYTES = BKV * DH * 2;           // 8192
 constexpr int VT_KB_BYTES = DH * 128;           // one 64-key block of V^T: 32 rows x 128 B
@@ -52,11 +56,15 @@ constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 640;   // 5 warpgroups: 4 x softmax, {TMA, MMA 0, MMA 1, idle}
 constexpr uint32_t TMEM_COLS = 512, TMEM_P = 256, TMEM_O = 384;
 constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
+#ifndef SVOL_ATTN_STAGGER
+#define SVOL_ATTN_STAGGER 550
+#endif
+constexpr int STAGGER_CLK = SVOL_ATTN_STAGGER;  // start offset between consecutive warpgroups (~ period / 4)
 }  // namespace attn
 
 struct AttnBars {
   uint64_t q_full;
-  uint64_t s_full[2], s_free[2];
+  uint64_t s_full[4], s_free[4];
   uint64_t p_ready[4], o_full[4];
   uint64_t kv_full[attn::STAGES], kv_empty[attn::STAGES];
   uint32_t tmem_base, pad;
@@ -74,8 +82,18 @@ __device__ long long g_attn_trace[6][64][8];
       g_attn_trace[role][j][slot] = c_;                                                    \
     }                                                                                      \
   } while (0)
+// same, but ordered after the computation of `val` (a float register)
+#define SVOL_TR_AFTER(role, j, slot, val)                                                  \
+  do {                                                                                     \
+    if (trace_on && (j) < 64) {                                                            \
+      long long c_;                                                                        \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_), "+f"(val)::"memory");               \
+      g_attn_trace[role][j][slot] = c_;                                                    \
+    }                                                                                      \
+  } while (0)
 #else
 #define SVOL_TR(role, j, slot) do {} while (0)
+#define SVOL_TR_AFTER(role, j, slot, val) do {} while (0)
 #endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -165,11 +183,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
     mbar_init(&bars->q_full, 1);
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&bars->s_full[t], 1);
-      mbar_init(&bars->s_free[t], 8);              // 8 warps read each score tile
-    }
     for (int g = 0; g < 4; ++g) {
+      mbar_init(&bars->s_full[g], 1);
+      mbar_init(&bars->s_free[g], 4);
       mbar_init(&bars->p_ready[g], 4);
       mbar_init(&bars->o_full[g], 1);
     }
@@ -209,44 +225,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // ------------------------------------------------------------------ MMA issuer of query tile t
       const int t = warp - 17;
       if (elect_one()) {
-        constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
+        constexpr uint32_t idesc_s = make_idesc_bf16(BQ, HALF);
         constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH);
         // descriptors differ only in their 14-bit start-address field (bytes >> 4): plain integer adds below
         const uint64_t dQ = make_kmajor_desc<64>(smem_u32(smem + t * Q_BYTES));
         const uint64_t dK = make_kmajor_desc<64>(smem_u32(smem + OFF_K));
         const uint64_t dV = make_kmajor_desc<128>(smem_u32(smem + OFF_VT));
-        const uint32_t tS = tmem_base + t * BKV;
+        auto issue_qk = [&](int j, int half) {          // S_g(j) = Q_t K_half(j)^T
+          const int g = 2 * t + half, s = j % STAGES;
+          if (half == 0) mbar_wait(&bars->kv_full[s], (j / STAGES) & 1);
+          if (j > 0) mbar_wait(&bars->s_free[g], (j - 1) & 1);
+          SVOL_TR(4 + t, j, half);
+          tcgen05_fence_after();
+          const uint64_t dKs = dK + static_cast<uint64_t>(s * (K_BYTES >> 4) + half * (HALF * DH * 2 >> 4));
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + g * HALF, dQ + 2 * k, dKs + 2 * k, idesc_s, k != 0);
+          umma_commit(&bars->s_full[g]);
+        };
+        auto issue_pv = [&](int j, int half) {          // O_g += P_g(j) V_half(j)
+          const int g = 2 * t + half, s = j % STAGES;
+          mbar_wait(&bars->p_ready[g], j & 1);
+          SVOL_TR(4 + t, j, 2 + half);
+          tcgen05_fence_after();
+          const uint64_t dVs = dV + static_cast<uint64_t>(s * (VT_BYTES >> 4) + half * (VT_KB_BYTES >> 4));
+#pragma unroll
+          for (int k = 0; k < HALF / 16; ++k)
+            umma_bf16_ts(tmem_base + TMEM_O + g * DH, tmem_base + TMEM_P + g * 32 + k * 8, dVs + 2 * k, idesc_o,
+                         (j > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&bars->o_full[g]);
+          if (half == 1) umma_commit(&bars->kv_empty[s]);   // last reader of stage s (covers every earlier MMA)
+        };
         mbar_wait(&bars->q_full, 0);
-        for (int j = 0; j <= n_tiles; ++j) {
-          if (j < n_tiles) {
-            const int s = j % STAGES;
-            SVOL_TR(4 + t, j, 0);
-            mbar_wait(&bars->kv_full[s], (j / STAGES) & 1);
-            if (j > 0) mbar_wait(&bars->s_free[t], (j - 1) & 1);
-            SVOL_TR(4 + t, j, 1);
-            tcgen05_fence_after();
-            const uint64_t dKs = dK + static_cast<uint64_t>(s * (K_BYTES >> 4));
-#pragma unroll
-            for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tS, dQ + 2 * k, dKs + 2 * k, idesc_s, k != 0);
-            umma_commit(&bars->s_full[t]);
-          }
-          if (j > 0) {
-            const int jp = j - 1, sp = jp % STAGES;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int g = 2 * t + half;
-              mbar_wait(&bars->p_ready[g], jp & 1);
-              SVOL_TR(4 + t, j, 2 + half);
-              tcgen05_fence_after();
-              const uint64_t dVs = dV + static_cast<uint64_t>(sp * (VT_BYTES >> 4) + half * (VT_KB_BYTES >> 4));
-#pragma unroll
-              for (int k = 0; k < HALF / 16; ++k)
-                umma_bf16_ts(tmem_base + TMEM_O + g * DH, tmem_base + TMEM_P + g * 32 + k * 8, dVs + 2 * k, idesc_o,
-                             (jp > 0 || k > 0) ? 1u : 0u);
-              umma_commit(&bars->o_full[g]);
-            }
-            umma_commit(&bars->kv_empty[sp]);
-          }
+        for (int i = 0; i <= n_tiles + 1; ++i) {
+          if (i < n_tiles) issue_qk(i, 0);
+          if (i >= 2) issue_pv(i - 2, 1);
+          if (i < n_tiles) issue_qk(i, 1);
+          if (i >= 1 && i <= n_tiles) issue_pv(i - 1, 0);
         }
       }
     }
@@ -259,16 +273,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int quarter = warp & 3;                       // TMEM lane quarter == warp % 4
       const int r = quarter * 32 + lane;                  // row inside the tile == TMEM lane
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-      const uint32_t t_s = t_lane + t * BKV + half * HALF;
+      const uint32_t t_s = t_lane + g * HALF;
       const uint32_t t_p = t_lane + TMEM_P + g * 32, t_o = t_lane + TMEM_O + g * DH;
       const float* mrow = key_mask ? key_mask + static_cast<size_t>(b) * Lk : nullptr;
       float m_ref = -INFINITY;      // reference maximum the stored probabilities / O / l are relative to
       float2 l2 = make_float2(0.f, 0.f);
 
+      // start offsets: g0, g2, g1, g3 a quarter period apart (lo before hi inside a tile, as the MMA issue order assumes)
+      {
+        const int slot = half * 2 + t;
+        const long long t_start = clock64();
+        while (clock64() - t_start < static_cast<long long>(slot) * STAGGER_CLK) {}
+      }
+
       for (int j = 0; j < n_tiles; ++j) {
         const int kv0 = j * BKV + half * HALF;
         SVOL_TR(g, j, 0);
-        mbar_wait(&bars->s_full[t], j & 1);
+        mbar_wait(&bars->s_full[g], j & 1);
         SVOL_TR(g, j, 1);
         tcgen05_fence_after();
         uint32_t s[HALF];
@@ -279,7 +300,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // scores are in registers: hand the TMEM buffer back so the next QK^T can start now
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->s_free[t]);
+        if (lane == 0) mbar_arrive(&bars->s_free[g]);
+        SVOL_TR(g, j, 4);
 
         // validity of this half tile's 64 keys as two 32-bit words (ragged tail and key_padding_mask); the
         // masked variant of the row-max code is a separate instantiation so full tiles pay nothing for it
@@ -297,6 +319,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         if (masked) mx = half_row_max<true>(s, words);
         else mx = half_row_max<false>(s, words);
+        SVOL_TR_AFTER(g, j, 3, mx);
 
         if (j == 0) {
           m_ref = mx;
@@ -321,8 +344,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             if (need) m_ref = mx;
           }
         }
-        const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
-        SVOL_TR(g, j, 3);
+        float m_use = m_ref == -INFINITY ? 0.f : m_ref;
 
         // one MUFU ex2 per probability (ex2.approx.ftz.bf16x2 was tried: on sm_100 it is issued as two
         // MUFU.EX2.BF16 ops plus a PRMT, so it saves nothing and only costs precision); the subtraction

@@ -1,0 +1,479 @@
+// Fused transformer FFN block on tcgen05 / TMEM / TMA (sm_100a):
+//
+//   y = LayerNorm( x + fc2( GELU_erf( fc1(x) ) ) )          (+ optional second output y + pos)
+//
+// replaces MLP.forward + residual + norm3 / norm6 of the reference
+// (lib/modeling/cross_modal_transformer.py:142-143,157-158,163-179): there it is two cuBLAS GEMMs, a GELU
+// kernel, an add and a LayerNorm, with the [tokens, 2048] hidden activation written to and re-read from HBM
+// (411 MB per layer at the headline config).  Here the hidden activation never leaves the SM: a CTA owns a
+// 128-token tile, walks the 2048 hidden units in 8 chunks of 256 and, per chunk,
+//     H_c   = GELU(x W1_c^T + b1_c)      MMA 1: M128 N256 K256  -> fp32 in TMEM -> epilogue -> bf16 in shared memory
+//     O    += H_c W2_c^T                 MMA 2: M128 N256 K256, accumulated in TMEM across the 8 chunks
+// and finishes with +b2, +x (the residual is the x tile that is already in shared memory), LayerNorm, bf16 stores
+// through TMA.  Tensor memory: H accumulator [0,256), O accumulator [256,512).
+//
+// Warp roles (384 threads = 3 warpgroups, one CTA per SM, persistent over token tiles):
+//   warp 0      weight producer: streams W1 / W2 as [256 x 32] bf16 blocks (16 KB, 64B swizzle) through a 5-stage ring
+//               in exactly the order the MMA warp consumes them: W1_0, then (W1_{c+1}, W2_c) for c = 0..7
+//   warp 1      MMA issuer
+//   warp 2      x-tile producer (4 TMA boxes of 128 x 64, 128B swizzle) -- separate from warp 0 so that weight
+//               prefetch for the next tile never waits for the previous tile's epilogue
+//   warp 3      idle
+//   warps 4-11  epilogue: thread = (token row, 128-column half).  Chunk epilogue: TMEM -> registers (accumulator
+//               released at once, so MMA 1 of the next chunk overlaps the GELU), +b1, GELU, bf16, swizzled store
+//               into the H operand buffer.  Tile epilogue: +b2, +x, LayerNorm (two-pass, halves exchanged through
+//               shared memory), bf16 tile staged in the (now free) H / x buffers and written with TMA stores.
+// GELU is the exact-erf form evaluated branch-free as  relu(t) -+ 0.5 t * 2^(|t| q(|t|))  with q a degree-4 minimax
+// polynomial of log2(erfc(|t|/sqrt 2))/|t| (max |error| 1.2e-6, far below the bf16 rounding of the hidden units):
+// 8 FMA-pipe, 3.5 ALU-pipe and 1 MUFU instruction per element.
+#include "common.cuh"
+#include "svol_internal.h"
+
+namespace svol {
+
+namespace ffn {
+constexpr int BM = 128, D = 256, CH = 256, BKX = 64, BKW = 32;
+constexpr int XKB_BYTES = BM * BKX * 2;                 // one 64-wide k-block of the x / H tile: 16 KB
+constexpr int X_BYTES = (D / BKX) * XKB_BYTES;          // 64 KB
+constexpr int H_BYTES = (CH / BKX) * XKB_BYTES;         // 64 KB
+constexpr int W_STAGE_BYTES = 256 * BKW * 2;            // 16 KB
+constexpr int W_STAGES = 5;
+constexpr int STAGES_PER_GEMM = 256 / BKW;              // 8 weight blocks per MMA 1 / MMA 2 of one chunk
+constexpr int MAX_FF = 2048;
+constexpr int OFF_X = 0, OFF_H = OFF_X + X_BYTES, OFF_W = OFF_H + H_BYTES;
+constexpr int OFF_B1 = OFF_W + W_STAGES * W_STAGE_BYTES;       // fp32 [MAX_FF]
+constexpr int OFF_P2 = OFF_B1 + MAX_FF * 4;                    // fp32 b2, ln_w, ln_b [3][256]
+constexpr int OFF_LN = OFF_P2 + 3 * D * 4;                     // fp32 [2][128] LayerNorm exchange
+constexpr int OFF_IDT = OFF_LN + 2 * BM * 4;                   // fp32 [128] 1 / dim_t of the sine positional encoding
+constexpr int OFF_BAR = OFF_IDT + (D / 2) * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+constexpr int EPI_WARPS = 8, FIRST_EPI_WARP = 4, THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
+constexpr int COLS = 128;                               // columns per epilogue thread
+constexpr uint32_t TMEM_H = 0, TMEM_O = 256;
+}  // namespace ffn
+
+struct FfnBars {
+  uint64_t w_full[ffn::W_STAGES], w_empty[ffn::W_STAGES];
+  uint64_t x_full, x_free;
+  uint64_t hacc_full, hacc_free;      // H accumulator (TMEM) written by MMA 1 / read out by the epilogue
+  uint64_t h_ready, h_free;           // H operand (shared memory) written by the epilogue / consumed by MMA 2
+  uint64_t oacc_full, oacc_free;      // O accumulator complete / read out
+  uint32_t tmem_base, pad;
+};
+static_assert(sizeof(FfnBars) <= 256, "barrier block");
+
+struct FfnParams {
+  const float* b1;
+  const float* b2;
+  const float* ln_w;
+  const float* ln_b;
+  const float* pos;         // fp32 [*, ld_pos] or nullptr
+  const float* pos_theta;   // fp32 [M] angles of the sine positional encoding, or nullptr (then `pos` is a table)
+  int ld_pos, pos_row_mod;
+  float ln_eps;
+  int M, FF;
+  int has_out_pos;
+};
+
+#ifdef SVOL_FFN_TRACE
+// Debug build only (-DSVOL_FFN_TRACE): CTA 0 records clock64() per chunk of its first tiles.
+// role 0: epilogue warp 4 (slots: top, hacc_full, acc->reg, gelu done, h_free, stored); role 1: MMA issuer
+// (slots: mma1 start, mma1 issued, h_ready, mma2 issued)
+__device__ long long g_ffn_trace[2][64][8];
+#define SVOL_FTR(role, idx, slot)                                                          \
+  do {                                                                                     \
+    if (ftrace_on && (idx) < 64) {                                                         \
+      long long c_;                                                                        \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)::"memory");                          \
+      g_ffn_trace[role][idx][slot] = c_;                                                   \
+    }                                                                                      \
+  } while (0)
+#else
+#define SVOL_FTR(role, idx, slot) do {} while (0)
+#endif
+
+// exact-erf GELU of two values (t = accumulator + bias), see the header comment.  The FMA-pipe part is written with
+// packed f32x2 instructions: the chunk epilogue is bound by instruction issue (measured: 13.6 scalar instructions
+// per element at 77 % issue utilisation), and packing halves the instruction count of the polynomial.
+__device__ __forceinline__ float2 gelu_erf_q4_x2(float2 t) {
+  constexpr float kClamp = 5.65685424949238f;                   // |t| clamped at z = |t| / sqrt 2 = 4
+  const float2 a = make_float2(fminf(fabsf(t.x), kClamp), fminf(fabsf(t.y), kClamp));
+  // q(a) = log2(erfc(a / sqrt 2)) / a, degree-4 minimax fit (max |erf error| 6.8e-7)
+  float2 q = __ffma2_rn(make_float2(-0.00052047055f, -0.00052047055f), a, make_float2(0.007397568f, 0.007397568f));
+  q = __ffma2_rn(q, a, make_float2(-0.052561324f, -0.052561324f));
+  q = __ffma2_rn(q, a, make_float2(-0.45925465f, -0.45925465f));
+  q = __ffma2_rn(q, a, make_float2(-1.1510913f, -1.1510913f));
+  const float2 u = __fmul2_rn(a, q);
+  float ex, ey;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(u.x));       // erfc(|t| / sqrt 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(u.y));
+  // -e for t > 0, +e for t < 0:   gelu(t) = relu(t) + 0.5 t * (-+ e)
+  const float2 se = make_float2(__uint_as_float(__float_as_uint(ex) ^ (~__float_as_uint(t.x) & 0x80000000u)),
+                                __uint_as_float(__float_as_uint(ey) ^ (~__float_as_uint(t.y) & 0x80000000u)));
+  const float2 hx = __fmul2_rn(t, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, se, make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f)));
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+__global__ void __launch_bounds__(ffn::THREADS, 1)
+ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
+              const __grid_constant__ CUtensorMap tmOutPos, const FfnParams p) {
+  using namespace ffn;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  FfnBars* bars = reinterpret_cast<FfnBars*>(smem + OFF_BAR);
+  float* s_b1 = reinterpret_cast<float*>(smem + OFF_B1);
+  float* s_p2 = reinterpret_cast<float*>(smem + OFF_P2);
+  float* ln_x = reinterpret_cast<float*>(smem + OFF_LN);
+  float* s_idt = reinterpret_cast<float*>(smem + OFF_IDT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef SVOL_FFN_TRACE
+  const bool ftrace_on = blockIdx.x == 0 && lane == 0 && (warp == ffn::FIRST_EPI_WARP || warp == 1);
+#endif
+  const int m_blocks = (p.M + BM - 1) / BM;
+  const int n_chunks = p.FF / CH;
+  const int my_tiles = m_blocks > static_cast<int>(blockIdx.x)
+                           ? (m_blocks - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
+                           : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmOut);
+    if (p.has_out_pos) tma_prefetch_desc(&tmOutPos);
+    for (int s = 0; s < W_STAGES; ++s) { mbar_init(&bars->w_full[s], 1); mbar_init(&bars->w_empty[s], 1); }
+    mbar_init(&bars->x_full, 1);    mbar_init(&bars->x_free, 1);
+    mbar_init(&bars->hacc_full, 1); mbar_init(&bars->hacc_free, EPI_WARPS);
+    mbar_init(&bars->h_ready, EPI_WARPS); mbar_init(&bars->h_free, 1);
+    mbar_init(&bars->oacc_full, 1); mbar_init(&bars->oacc_free, EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&bars->tmem_base);
+  // parameters used by every tile -> shared memory (read back as broadcasts)
+  for (int i = threadIdx.x; i < p.FF; i += THREADS) s_b1[i] = __ldg(p.b1 + i);
+  for (int i = threadIdx.x; i < D; i += THREADS) {
+    s_p2[i] = __ldg(p.b2 + i);
+    s_p2[D + i] = __ldg(p.ln_w + i);
+    s_p2[2 * D + i] = __ldg(p.ln_b + i);
+  }
+  if (p.pos_theta != nullptr)       // 1 / dim_t[2k] = 10000^(-2k/d)  (position_encoding.py:64-65)
+    for (int i = threadIdx.x; i < D / 2; i += THREADS)
+      s_idt[i] = 1.0f / powf(10000.f, __fdiv_rn(__fmul_rn(2.f, static_cast<float>(i)), static_cast<float>(D)));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp < FIRST_EPI_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // ------------------------------------------------------------------ weight producer
+      if (elect_one()) {
+        int stage = 0; uint32_t phase = 0;
+        auto load_blocks = [&](const CUtensorMap* tm, int k0, int n0) {
+          for (int kb = 0; kb < STAGES_PER_GEMM; ++kb) {
+            mbar_wait(&bars->w_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bars->w_full[stage], W_STAGE_BYTES);
+            tma_load_2d(smem + OFF_W + stage * W_STAGE_BYTES, tm, &bars->w_full[stage], k0 + kb * BKW, n0);
+            if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+          }
+        };
+        for (int it = 0; it < my_tiles; ++it) {
+          load_blocks(&tmW1, 0, 0);                                   // W1 chunk 0
+          for (int c = 0; c < n_chunks; ++c) {
+            if (c + 1 < n_chunks) load_blocks(&tmW1, 0, (c + 1) * CH);  // W1 chunk c+1: rows = hidden units
+            load_blocks(&tmW2, c * CH, 0);                            // W2 chunk c: k = hidden units
+          }
+        }
+      }
+    } else if (warp == 2) {
+      // ------------------------------------------------------------------ x-tile producer
+      if (elect_one()) {
+        for (int it = 0; it < my_tiles; ++it) {
+          const int m_blk = blockIdx.x + it * gridDim.x;
+          mbar_wait(&bars->x_free, (it & 1) ^ 1);
+          mbar_arrive_expect_tx(&bars->x_full, X_BYTES);
+          for (int kb = 0; kb < D / BKX; ++kb)
+            tma_load_2d(smem + OFF_X + kb * XKB_BYTES, &tmX, &bars->x_full, kb * BKX, m_blk * BM);
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(BM, 256);
+        const uint64_t dX = make_kmajor_desc<128>(smem_u32(smem + OFF_X));
+        const uint64_t dH = make_kmajor_desc<128>(smem_u32(smem + OFF_H));
+        const uint64_t dW = make_kmajor_desc<64>(smem_u32(smem + OFF_W));
+        int stage = 0; uint32_t phase = 0;
+        // one 128 x 256 x 256 GEMM: A = 4 k-blocks of 64 in shared memory, B = 8 streamed 32-wide weight blocks
+        auto gemm256 = [&](uint32_t d_tmem, uint64_t dA, bool fresh) {
+          for (int s = 0; s < STAGES_PER_GEMM; ++s) {
+            mbar_wait(&bars->w_full[stage], phase);
+            tcgen05_fence_after();
+            const uint64_t a = dA + static_cast<uint64_t>((s >> 1) * (XKB_BYTES >> 4) + (s & 1) * 4);
+            const uint64_t b = dW + static_cast<uint64_t>(stage * (W_STAGE_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < BKW / 16; ++k) umma_bf16_ss(d_tmem, a + 2 * k, b + 2 * k, idesc, (fresh && s == 0 && k == 0) ? 0u : 1u);
+            umma_commit(&bars->w_empty[stage]);
+            if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+          }
+        };
+        uint32_t n_h = 0;          // chunks whose MMA 1 has been issued (H accumulator uses)
+        uint32_t n_o = 0;          // chunks whose MMA 2 has been issued (H operand uses)
+        for (int it = 0; it < my_tiles; ++it) {
+          mbar_wait(&bars->x_full, it & 1);
+          auto mma1 = [&]() {
+            mbar_wait(&bars->hacc_free, (n_h & 1) ^ 1);       // epilogue has read out the previous chunk's accumulator
+            SVOL_FTR(1, n_h, 0);
+            tcgen05_fence_after();
+            gemm256(tmem_base + TMEM_H, dX, true);
+            umma_commit(&bars->hacc_full);
+            SVOL_FTR(1, n_h, 1);
+            ++n_h;
+          };
+          mma1();
+          for (int c = 0; c < n_chunks; ++c) {
+            if (c + 1 < n_chunks) mma1();
+            mbar_wait(&bars->h_ready, n_o & 1);                // H_c is in shared memory
+            if (c == 0) mbar_wait(&bars->oacc_free, (it & 1) ^ 1);   // previous tile's O has been read out
+            SVOL_FTR(1, n_o, 2);
+            tcgen05_fence_after();
+            gemm256(tmem_base + TMEM_O, dH, c == 0);
+            umma_commit(&bars->h_free);
+            SVOL_FTR(1, n_o, 3);
+            ++n_o;
+          }
+          umma_commit(&bars->oacc_full);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int quarter = warp & 3;                             // TMEM lane quarter this warp may read
+    const int half = (warp - FIRST_EPI_WARP) >> 2;            // which 128 of the 256 columns
+    const int r = quarter * 32 + lane;                        // row inside the tile
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    // this thread's row inside a [4 k-blocks][128 rows][128 B] operand tile: 16-byte chunk j of k-block kb lives at
+    // kb * 16 KB + r * 128 + ((j ^ (r & 7)) << 4); the thread owns k-blocks 2*half and 2*half + 1
+    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
+    const uint32_t swz = static_cast<uint32_t>(r & 7);
+    uint32_t n_h = 0, n_hs = 0;     // H accumulator read-outs / H operand stores so far
+    auto store_tile_half = [&](uint8_t* buf, const float (&v)[COLS]) {
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float* vv = &v[kb * 64 + j * 8];
+          const uint4 q = make_uint4(pack_bf16x2(vv[0], vv[1]), pack_bf16x2(vv[2], vv[3]), pack_bf16x2(vv[4], vv[5]),
+                                     pack_bf16x2(vv[6], vv[7]));
+          *reinterpret_cast<uint4*>(buf + (2 * half + kb) * XKB_BYTES + row_off + ((static_cast<uint32_t>(j) ^ swz) << 4)) = q;
+        }
+    };
+    auto load_acc = [&](uint32_t col0, float (&v)[COLS]) {
+      uint32_t raw[COLS / 32][32];
+#pragma unroll
+      for (int c = 0; c < COLS / 32; ++c) tmem_ld_32x32b_x32(t_lane + col0 + half * COLS + c * 32, raw[c]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < COLS / 32; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[c * 32 + i] = __uint_as_float(raw[c][i]);
+    };
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int m_blk = blockIdx.x + it * gridDim.x;
+      const int row = m_blk * BM + r;
+      for (int c = 0; c < n_chunks; ++c) {
+        // ---- chunk epilogue: H_c = GELU(acc + b1_c) -> bf16 -> shared memory operand of MMA 2
+        SVOL_FTR(0, n_h, 0);
+        mbar_wait(&bars->hacc_full, n_h & 1);
+        SVOL_FTR(0, n_h, 1);
+        tcgen05_fence_after();
+        float v[COLS];
+        load_acc(TMEM_H, v);
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->hacc_free);
+        SVOL_FTR(0, n_h, 2);
+        ++n_h;
+        const uint32_t bp = smem_u32(s_b1 + c * CH + half * COLS);
+#pragma unroll
+        for (int i = 0; i < COLS / 4; ++i) {
+          const float4 b = lds_f4(bp + i * 16);
+          const float2 g0 = gelu_erf_q4_x2(__fadd2_rn(make_float2(v[4 * i + 0], v[4 * i + 1]), make_float2(b.x, b.y)));
+          const float2 g1 = gelu_erf_q4_x2(__fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w)));
+          v[4 * i + 0] = g0.x; v[4 * i + 1] = g0.y; v[4 * i + 2] = g1.x; v[4 * i + 3] = g1.y;
+        }
+        // the H buffer is free once MMA 2 of the previous chunk has consumed it; at the start of a tile it also served as
+        // the staging buffer of the previous tile's output store (x_free is signalled only after those stores are read)
+        SVOL_FTR(0, n_hs, 3);
+        if (n_hs > 0) mbar_wait(&bars->h_free, (n_hs - 1) & 1);
+        SVOL_FTR(0, n_hs, 4);
+        store_tile_half(smem + OFF_H, v);
+        fence_proxy_async_smem();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->h_ready);
+        SVOL_FTR(0, n_hs, 5);
+        ++n_hs;
+      }
+
+      // ---- tile epilogue: y = LayerNorm(O + b2 + x)
+      mbar_wait(&bars->oacc_full, it & 1);
+      tcgen05_fence_after();
+      float v[COLS];
+      load_acc(TMEM_O, v);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->oacc_free);
+      {
+        const uint32_t bp = smem_u32(s_p2 + half * COLS);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 xq = *reinterpret_cast<const uint4*>(smem + OFF_X + (2 * half + kb) * XKB_BYTES + row_off +
+                                                             ((static_cast<uint32_t>(j) ^ swz) << 4));
+            const float4 b0 = lds_f4(bp + (kb * 16 + j * 2) * 16), b1 = lds_f4(bp + (kb * 16 + j * 2 + 1) * 16);
+            float* vv = &v[kb * 64 + j * 8];
+            vv[0] += b0.x + bf16_lo(xq.x); vv[1] += b0.y + bf16_hi(xq.x); vv[2] += b0.z + bf16_lo(xq.y); vv[3] += b0.w + bf16_hi(xq.y);
+            vv[4] += b1.x + bf16_lo(xq.z); vv[5] += b1.y + bf16_hi(xq.z); vv[6] += b1.z + bf16_lo(xq.w); vv[7] += b1.w + bf16_hi(xq.w);
+          }
+      }
+      // every epilogue warp has read its residual: the x buffer can be refilled with the next tile while this one finishes
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (warp == FIRST_EPI_WARP && lane == 0) mbar_arrive(&bars->x_free);
+      // LayerNorm over the 256-wide row: the two warps that share a row exchange partial sums (two-pass)
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < COLS; ++i) s += v[i];
+      ln_x[half * BM + r] = s;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      const float mean = (ln_x[r] + ln_x[BM + r]) * (1.0f / D);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < COLS; ++i) { const float d = v[i] - mean; ss += d * d; }
+      ln_x[half * BM + r] = ss;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      const float var = (ln_x[r] + ln_x[BM + r]) * (1.0f / D);
+      const float rstd = rsqrtf(var + p.ln_eps);
+      {
+        const uint32_t gp = smem_u32(s_p2 + D + half * COLS), bp = smem_u32(s_p2 + 2 * D + half * COLS);
+#pragma unroll
+        for (int i = 0; i < COLS / 4; ++i) {
+          const float4 g = lds_f4(gp + i * 16), b = lds_f4(bp + i * 16);
+          v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * g.x + b.x;
+          v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
+          v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g.z + b.z;
+          v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
+        }
+      }
+      // y -> H buffer (free: oacc_full implies the last MMA 2 of this tile has completed) -> TMA store
+      store_tile_half(smem + OFF_H, v);
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      if (warp == FIRST_EPI_WARP && lane == 0) {
+        for (int kb = 0; kb < D / BKX; ++kb) tma_store_2d(&tmOut, smem + OFF_H + kb * XKB_BYTES, kb * BKX, m_blk * BM);
+        tma_store_commit();
+      }
+      if (p.has_out_pos) {
+        // second output y + pos, staged in the same buffer once the first store has been read out of it
+        if (p.pos_theta != nullptr) {
+          // sine positional encoding evaluated in place (position_encoding.py:62-71): columns (2k, 2k+1) =
+          // (sin, cos)(theta_row / dim_t[2k]).  theta is in [0, 2 pi]: folded to [-pi, pi] for the MUFU sin / cos.
+          const float theta = row < p.M ? __ldg(p.pos_theta + row) : 0.f;
+          const uint32_t ip = smem_u32(s_idt + half * (COLS / 2));
+#pragma unroll
+          for (int i = 0; i < COLS / 8; ++i) {
+            const float4 w = lds_f4(ip + i * 16);
+            const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = theta * ws[e];
+              a = a > 3.14159265358979f ? a - 6.28318530717959f : a;
+              v[8 * i + 2 * e] += __sinf(a);
+              v[8 * i + 2 * e + 1] += __cosf(a);
+            }
+          }
+        } else if (row < p.M) {
+          const int prow = p.pos_row_mod > 0 ? row % p.pos_row_mod : row;
+          const float4* pp = reinterpret_cast<const float4*>(p.pos + static_cast<size_t>(prow) * p.ld_pos + half * COLS);
+#pragma unroll
+          for (int i = 0; i < COLS / 4; ++i) {
+            const float4 q = __ldg(pp + i);
+            v[4 * i + 0] += q.x; v[4 * i + 1] += q.y; v[4 * i + 2] += q.z; v[4 * i + 3] += q.w;
+          }
+        }
+        if (warp == FIRST_EPI_WARP && lane == 0) tma_store_wait_read<0>();
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+        store_tile_half(smem + OFF_H, v);
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 5, 256;" ::: "memory");
+        if (warp == FIRST_EPI_WARP && lane == 0) {
+          for (int kb = 0; kb < D / BKX; ++kb) tma_store_2d(&tmOutPos, smem + OFF_H + kb * XKB_BYTES, kb * BKX, m_blk * BM);
+          tma_store_commit();
+        }
+      }
+      if (warp == FIRST_EPI_WARP && lane == 0) tma_store_wait_read<0>();   // staging buffer read out by the TMA engine
+      asm volatile("bar.sync 5, 256;" ::: "memory");                       // ... and may be rewritten by the next tile's chunk 0
+    }
+    if (warp == FIRST_EPI_WARP && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
+  using namespace ffn;
+  if (a.M <= 0 || a.d != D || a.ff <= 0 || a.ff % CH != 0 || a.ff > MAX_FF)
+    return svol_fail(SVOL_ERR_SHAPE, "ffn: need d == 256 and ff a multiple of 256 (<= 2048)");
+  if (!a.x || !a.w1 || !a.b1 || !a.w2 || !a.b2 || !a.ln_weight || !a.ln_bias || !a.out)
+    return svol_fail(SVOL_ERR_NULL, "ffn: required pointer is NULL");
+  if (a.out_pos && !a.pos && !a.pos_theta) return svol_fail(SVOL_ERR_NULL, "ffn: out_pos needs pos or pos_theta");
+  CUtensorMap tmX, tmW1, tmW2, tmOut, tmOutPos;
+  int rc = make_tensor_map_2d(&tmX, a.x, D, a.M, a.ldx, BKX, BM, 128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tmW1, a.w1, D, a.ff, a.ldw1, BKW, 256, 64);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tmW2, a.w2, a.ff, D, a.ldw2, BKW, 256, 64);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tmOut, a.out, D, a.M, a.ld_out, BKX, BM, 128);
+  if (rc) return rc;
+  rc = make_tensor_map_2d(&tmOutPos, a.out_pos ? a.out_pos : a.out, D, a.M, a.ld_out, BKX, BM, 128);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return svol_fail_cuda(e, "ffn: cudaFuncSetAttribute");
+    configured = true;
+  }
+  FfnParams p;
+  p.b1 = a.b1; p.b2 = a.b2; p.ln_w = a.ln_weight; p.ln_b = a.ln_bias; p.pos = a.pos; p.pos_theta = a.pos_theta;
+  p.ld_pos = a.ld_pos; p.pos_row_mod = a.pos_row_mod; p.ln_eps = a.ln_eps; p.M = a.M; p.FF = a.ff;
+  p.has_out_pos = a.out_pos != nullptr;
+  const int m_blocks = (a.M + BM - 1) / BM;
+  const int grid = m_blocks < sm_count() ? m_blocks : sm_count();
+  ffn_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, tmOutPos, p);
+  return svol_check_launch("ffn_tc");
+}
+
+}  // namespace svol
+
+#ifdef SVOL_FFN_TRACE
+extern "C" int svol_debug_ffn_trace(long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, svol::g_ffn_trace, sizeof(svol::g_ffn_trace)));
+}
+#endif

@@ -62,6 +62,22 @@ struct GemmSmemTail {
 };
 static_assert(sizeof(GemmSmemTail) <= 256, "barrier block");
 
+#ifdef SVOL_GEMM_TRACE
+// Debug build only (-DSVOL_GEMM_TRACE): CTA 0 records clock64() at the phase boundaries of its first 32 tiles.
+// role 0: epilogue warp 4; role 1: MMA issuer.
+__device__ long long g_gemm_trace[2][32][8];
+#define SVOL_GTR(role, it, slot)                                                           \
+  do {                                                                                     \
+    if (gtrace_on && (it) < 32) {                                                          \
+      long long c_;                                                                        \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_)::"memory");                          \
+      g_gemm_trace[role][it][slot] = c_;                                                   \
+    }                                                                                      \
+  } while (0)
+#else
+#define SVOL_GTR(role, it, slot) do {} while (0)
+#endif
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
@@ -113,6 +129,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef SVOL_GEMM_TRACE
+  const bool gtrace_on = blockIdx.x == 0 && lane == 0 && (warp == gemm::FIRST_EPI_WARP || warp == 1);
+#endif
   const int m_blocks = (M + BM - 1) / BM;
   const int n_blocks = N / BN;
   const int num_kb = K / BK;
@@ -181,7 +200,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int it = 0; it < my_tiles; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        SVOL_GTR(1, it, 0);
         mbar_wait(&tail->tmem_empty[acc], acc_phase ^ 1);
+        SVOL_GTR(1, it, 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -197,6 +218,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tail->tmem_full[acc]);
+        SVOL_GTR(1, it, 2);
       }
     }
    }
@@ -218,7 +240,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int slab_row0 = m_blk * BM + quarter * 32;             // first row of this warp's 32-row slab
       const int rows_valid = min(32, max(0, M - slab_row0));
 
+      SVOL_GTR(0, it, 0);
       mbar_wait(&tail->tmem_full[acc], acc_phase);
+      SVOL_GTR(0, it, 1);
       tcgen05_fence_after();
       float v[COLS_PER_THREAD];
       {
@@ -235,6 +259,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
+      SVOL_GTR(0, it, 2);
 
       if (ep.bias) {
         const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
@@ -251,6 +276,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int i = 0; i < COLS_PER_THREAD; ++i) v[i] = gelu_erf_fast(v[i]);
       }
+      SVOL_GTR(0, it, 3);
       if (ep.residual) {
         const uint8_t* rbase = reinterpret_cast<const uint8_t*>(ep.residual + static_cast<size_t>(slab_row0) * ep.ld_res + col0);
 #pragma unroll
@@ -265,6 +291,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      SVOL_GTR(0, it, 4);
       if (ep.ln_weight) {
         // LayerNorm over the full 256-wide row: the two warps that share a row exchange partial
         // sums through shared memory (two-pass: mean, then centred second moment).
@@ -294,6 +321,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g.w + b.w;
         }
       }
+      SVOL_GTR(0, it, 5);
       if (ep.out) {
         uint8_t* obase = reinterpret_cast<uint8_t*>(ep.out + static_cast<size_t>(slab_row0) * ep.ld_out + col0);
 #pragma unroll
@@ -307,6 +335,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           block_store(stg, q, obase + blk * 128, static_cast<size_t>(ep.ld_out) * 2, rows_valid, lane);
         }
       }
+      SVOL_GTR(0, it, 6);
       if (ep.out_pos) {
         // second output: x + pos (the q/k operand of the next attention block).  pos rows follow the output
         // rows (pos_row_mod == 0) or repeat with period pos_row_mod (query embedding broadcast over the batch);
@@ -350,6 +379,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < COLS_PER_THREAD; ++i) base[static_cast<size_t>(i) * ep.vt_pitch] = __float2bfloat16_rn(v[i]);
       }
       __syncwarp();   // reconverge before the next tile's warp-collective tcgen05.ld
+      SVOL_GTR(0, it, 7);
     }
   }
 
@@ -397,3 +427,9 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace svol
+
+#ifdef SVOL_GEMM_TRACE
+extern "C" int svol_debug_gemm_trace(long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, svol::g_gemm_trace, sizeof(svol::g_gemm_trace)));
+}
+#endif

@@ -166,6 +166,34 @@ int launch_posenc_sine(const float* mask, float* pos, int B, int L, int d, cudaS
 }
 
 // ---------------------------------------------------------------------------------------------
+// theta[b,l] = cumsum(mask)[b,l] / (sum(mask[b]) + 1e-6) * 2 pi  (position_encoding.py:55-61), bit-identical to the
+// xrow values of posenc_sine_kernel.  One CTA per sample: per-thread runs of consecutive tokens + a block scan.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) posenc_theta_kernel(const float* __restrict__ mask, float* __restrict__ theta, int L) {
+  __shared__ float part[256];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* mrow = mask + static_cast<size_t>(b) * L;
+  const int per = (L + 255) / 256, l0 = tid * per, l1 = min(L, l0 + per);
+  float s = 0.f;
+  for (int l = l0; l < l1; ++l) s += mrow[l] != 0.f ? 1.f : 0.f;
+  part[tid] = s;
+  __syncthreads();
+  float before = 0.f, total = 0.f;                       // exact: sums of 0/1 below 2^24
+  for (int i = 0; i < 256; ++i) { const float v = part[i]; total += v; if (i < tid) before += v; }
+  float cum = before;
+  for (int l = l0; l < l1; ++l) {
+    cum += mrow[l] != 0.f ? 1.f : 0.f;
+    theta[static_cast<size_t>(b) * L + l] = __fmul_rn(__fdiv_rn(cum, __fadd_rn(total, 1e-6f)), 6.283185307179586f);
+  }
+}
+
+int launch_posenc_theta(const float* mask, float* theta, int B, int L, cudaStream_t stream) {
+  if (B <= 0 || L <= 0) return svol_fail(SVOL_ERR_SHAPE, "posenc_theta: bad sizes");
+  posenc_theta_kernel<<<B, 256, 0, stream>>>(mask, theta, L);
+  return svol_check_launch("posenc_theta");
+}
+
+// ---------------------------------------------------------------------------------------------
 // out[r,:] = bf16(x[r % mod,:] + pos[r % mod,:])
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) add_pos_bf16_kernel(const float* __restrict__ x, const float* __restrict__ pos,

@@ -27,7 +27,7 @@ from typing import Dict, List, Tuple
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, AttnArgs, GemmArgs
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, AttnArgs, FfnArgs, GemmArgs
 
 LN_EPS = 1e-5
 HEAD_DIM = 32
@@ -173,13 +173,13 @@ class HeadEngine:
         xn = buf("xn", (M, d_in), bf)
         ha, hb = buf("ha", (M, d), bf), buf("hb", (M, d), bf)
         pos = buf("pos", (M, d), f32)
+        theta = buf("theta", (M,), f32)
         X, Xp = buf("X", (M, d), bf), buf("Xp", (M, d), bf)
         mem, memp = buf("mem", (M, d), bf), buf("memp", (M, d), bf)
         mem2 = buf("mem2", (M, d), bf)
         qk = buf("qk", (M, 2 * d), bf)
         vt = buf("vt", (B * d, Lp), bf, zero=True)
         att = buf("att", (M, d), bf)
-        hid = buf("hid", (M, ff), bf)
         sk_a, sk_b = buf("sk_a", (B, d), f32), buf("sk_b", (B, d), f32)
         u = buf("u", (B, H, d), f32)
         scores = buf("scores", (B, H, L), f32)
@@ -193,7 +193,6 @@ class HeadEngine:
         attq = buf("attq", (MQ, d), bf)
         qc = buf("qc", (MQ, d), bf)
         kc = buf("kc", (M, d), bf)
-        hidq = buf("hidq", (MQ, ff), bf)
         hs = buf("hs", (NL, MQ, d), bf)
         h1, h2 = buf("h1", (NL * MQ, d), bf), buf("h2", (NL * MQ, d), bf)
         logits = buf("logits", (NL, B, Q, 2), f32)
@@ -227,6 +226,18 @@ class HeadEngine:
             plan.keep.append(a)
             plan.calls.append((name, gemm_fn, (C.byref(a),)))
 
+        def ffn(name, x, w1, b1, w2, b2, ln, out, out_pos=None, pos_t=None, pos_mod=0, theta_t=None):
+            a = FfnArgs()
+            a.x, a.w1, a.b1, a.w2, a.b2 = P(x), P(w1), P(b1), P(w2), P(b2)
+            a.ln_weight, a.ln_bias, a.out, a.out_pos = P(ln[0]), P(ln[1]), P(out), P(out_pos)
+            a.pos, a.pos_theta = P(pos_t), P(theta_t)
+            a.M, a.d, a.ff = x.shape[0], x.shape[1], w1.shape[0]
+            a.ldx, a.ldw1, a.ldw2, a.ld_out = x.stride(0), w1.stride(0), w2.stride(0), out.stride(0)
+            a.ld_pos, a.pos_row_mod = (pos_t.stride(0) if pos_t is not None else 0), pos_mod
+            a.ln_eps = LN_EPS
+            plan.keep.append(a)
+            plan.calls.append((name, lib.svol_ffn_bf16, (C.byref(a),)))
+
         def attention(name, q, k, vt_t, out, Lq, Lk, ldq, ldk, pitch, mask=None):
             a = AttnArgs()
             a.q, a.k, a.vt, a.key_mask, a.out = P(q), P(k), P(vt_t), P(mask), P(out)
@@ -242,6 +253,7 @@ class HeadEngine:
         call("ln_in", lib.svol_layernorm_f32_to_bf16, P(x_in), P(w["in_video.0.ln_w"]), P(w["in_video.0.ln_b"]), P(xn),
              M, d_in, LN_EPS)
         call("posenc", lib.svol_posenc_sine, P(vmask), P(pos), B, L, d)
+        call("posenc_theta", lib.svol_posenc_theta, P(vmask), P(theta), B, L)
         cur = xn
         for i in range(n_proj):
             last = i == n_proj - 1
@@ -276,9 +288,14 @@ class HeadEngine:
             gemm(p + "sa_v", mem, w[p + "sa.wv"], w[p + "sa.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)
             attention(p + "sa_attn", qk, qk[:, d:], vt, att, L, L, 2 * d, 2 * d, Lp)
             gemm(p + "sa_out", att, w[p + "sa.wo"], w[p + "sa.bo"], out=mem2, residual=mem, ln=(w[p + "n2.w"], w[p + "n2.b"]))
-            gemm(p + "ffn1_up", mem2, w[p + "mlp1.w1"], w[p + "mlp1.b1"], out=hid, act=ACT_GELU)
-            gemm(p + "ffn1_down", hid, w[p + "mlp1.w2"], w[p + "mlp1.b2"], out=X, residual=mem2,
-                 ln=(w[p + "n3.w"], w[p + "n3.b"]), out_pos=Xp, pos_t=pos)
+            if self.plain:
+                hid = plan.buf["hid"] if "hid" in plan.buf else buf("hid", (M, ff), bf)
+                gemm(p + "ffn1_up", mem2, w[p + "mlp1.w1"], w[p + "mlp1.b1"], out=hid, act=ACT_GELU)
+                gemm(p + "ffn1_down", hid, w[p + "mlp1.w2"], w[p + "mlp1.b2"], out=X, residual=mem2,
+                     ln=(w[p + "n3.w"], w[p + "n3.b"]), out_pos=Xp, pos_t=pos)
+            else:       # fused fc1 -> GELU -> fc2 -> +residual -> norm3, sine positions evaluated in the epilogue
+                ffn(p + "ffn1", mem2, w[p + "mlp1.w1"], w[p + "mlp1.b1"], w[p + "mlp1.w2"], w[p + "mlp1.b2"],
+                    (w[p + "n3.w"], w[p + "n3.b"]), out=X, out_pos=Xp, theta_t=theta)
             x_cur, xp_cur = X, Xp            # layer output mem (and mem + pos)
             # (c) query self-attention + norm4                                            :145-149
             gemm(p + "ta_qk", outp_cur, w[p + "ta.wqk"], w[p + "ta.bqk"], out=qkq)
@@ -292,9 +309,14 @@ class HeadEngine:
             gemm(p + "ca_v", X, w[p + "ca.wv"], w[p + "ca.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)
             attention(p + "ca_attn", qc, kc, vt, attq, Q, L, d, d, Lp, mask=vmask)
             gemm(p + "ca_out", attq, w[p + "ca.wo"], w[p + "ca.bo"], out=o2, residual=o1, ln=(w[p + "n5.w"], w[p + "n5.b"]))
-            gemm(p + "ffn2_up", o2, w[p + "mlp2.w1"], w[p + "mlp2.b1"], out=hidq, act=ACT_GELU)
-            gemm(p + "ffn2_down", hidq, w[p + "mlp2.w2"], w[p + "mlp2.b2"], out=hs[li], residual=o2,
-                 ln=(w[p + "n6.w"], w[p + "n6.b"]), out_pos=outp, pos_t=w["query_embed"], pos_mod=Q)
+            if self.plain:
+                hidq = plan.buf["hidq"] if "hidq" in plan.buf else buf("hidq", (MQ, ff), bf)
+                gemm(p + "ffn2_up", o2, w[p + "mlp2.w1"], w[p + "mlp2.b1"], out=hidq, act=ACT_GELU)
+                gemm(p + "ffn2_down", hidq, w[p + "mlp2.w2"], w[p + "mlp2.b2"], out=hs[li], residual=o2,
+                     ln=(w[p + "n6.w"], w[p + "n6.b"]), out_pos=outp, pos_t=w["query_embed"], pos_mod=Q)
+            else:
+                ffn(p + "ffn2", o2, w[p + "mlp2.w1"], w[p + "mlp2.b1"], w[p + "mlp2.w2"], w[p + "mlp2.b2"],
+                    (w[p + "n6.w"], w[p + "n6.b"]), out=hs[li], out_pos=outp, pos_t=w["query_embed"], pos_mod=Q)
             out_cur, outp_cur = hs[li], outp
         # ---- heads on every layer's queries (svanet.py:125-127)
         hs_all = hs.view(NL * MQ, d)

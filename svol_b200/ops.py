@@ -49,6 +49,29 @@ def gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return res
 
 
+def ffn(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+        ln: Tuple[torch.Tensor, torch.Tensor], pos: Optional[torch.Tensor] = None, pos_mod: int = 0, eps: float = 1e-5,
+        pos_theta: Optional[torch.Tensor] = None):
+    """LayerNorm(x + fc2(GELU(fc1(x)))) for x [M,256] bf16, w1 [ff,256] bf16, w2 [256,ff] bf16.
+    Returns {'out': [M,256] bf16, 'out_pos': out + pos (when ``pos`` is given)}."""
+    _lib.require_device()
+    M, d = x.shape
+    res = {"out": torch.empty((M, d), device=x.device, dtype=torch.bfloat16)}
+    a = _lib.FfnArgs()
+    a.x, a.w1, a.b1, a.w2, a.b2 = _P(x), _P(w1), _P(b1), _P(w2), _P(b2)
+    a.ln_weight, a.ln_bias, a.out = _P(ln[0]), _P(ln[1]), _P(res["out"])
+    a.M, a.d, a.ff, a.ldx, a.ldw1, a.ldw2, a.ld_out = M, d, w1.shape[0], x.stride(0), w1.stride(0), w2.stride(0), d
+    a.ln_eps = eps
+    if pos is not None:
+        res["out_pos"] = torch.empty((M, d), device=x.device, dtype=torch.bfloat16)
+        a.out_pos, a.pos, a.ld_pos, a.pos_row_mod = _P(res["out_pos"]), _P(pos), pos.stride(0), pos_mod
+    elif pos_theta is not None:
+        res["out_pos"] = torch.empty((M, d), device=x.device, dtype=torch.bfloat16)
+        a.out_pos, a.pos_theta = _P(res["out_pos"]), _P(pos_theta)
+    _lib.check(_lib.get_lib().svol_ffn_bf16(C.byref(a), _lib.stream_ptr()), "ffn")
+    return res
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, B: int, H: int, Lq: int, Lk: int,
               key_mask: Optional[torch.Tensor] = None, plain: bool = False) -> torch.Tensor:
     """q [B*Lq, >=H*32] (pre-scaled by log2(e)/sqrt(32)), k [B*Lk, >=H*32], vt [B*H*32, pitch] bf16."""
@@ -62,6 +85,15 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, B: int, H: int
     fn = lib.svol_attention_bf16_plain if plain else lib.svol_attention_bf16
     _lib.check(fn(C.byref(a), _lib.stream_ptr()), "attention")
     return out
+
+
+def posenc_theta(mask: torch.Tensor) -> torch.Tensor:
+    """mask [B,L] float -> theta [B,L] fp32 (angles of the normalised sine positional encoding)."""
+    _lib.require_device()
+    B, L = mask.shape
+    theta = torch.empty((B, L), device=mask.device, dtype=torch.float32)
+    _lib.check(_lib.get_lib().svol_posenc_theta(_P(mask), _P(theta), B, L, _lib.stream_ptr()), "posenc_theta")
+    return theta
 
 
 def layernorm_to_bf16(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:

@@ -238,3 +238,55 @@ def test_heads():
     logits, boxes = ops.heads(hs.to(dv), h2.to(dv), t(wc), t(bc), t(wb), t(bb))
     assert np.abs(_f(logits) - orc.linear(hs.float().numpy(), wc, bc)).max() < 1e-4
     assert np.abs(_f(boxes) - orc.sigmoid(orc.linear(h2.float().numpy(), wb, bb))).max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ fused FFN
+FFN_CASES = [
+    # M, ff, pos mode
+    (128, 256, None),
+    (300, 512, None),
+    (640, 2048, "full"),
+    (3136, 2048, "mod"),          # pos rows repeat with period 320 (query embedding)
+    (20000, 2048, "full"),        # > 148 tiles: persistent loop, barrier phase wrap across tiles
+    (2 * 1568, 2048, "theta"),    # sine positional encoding evaluated inside the kernel (padded second sample)
+]
+
+
+@pytest.mark.parametrize("M,ff,posmode", FFN_CASES)
+def test_ffn_fused(M, ff, posmode):
+    """LayerNorm(x + fc2(GELU(fc1(x)))) -- cross_modal_transformer.py:142-143,163-179 -- vs the oracle's fp32 path
+    on bf16-rounded operands; the hidden activation is rounded to bf16 on both sides."""
+    from svol_b200 import ops
+    d = 256
+    rng = np.random.RandomState(M + ff)
+    x = _bf16(rng.standard_normal((M, d)).astype(np.float32))
+    w1 = _bf16((rng.standard_normal((ff, d)) / math.sqrt(d)).astype(np.float32))
+    w2 = _bf16((rng.standard_normal((d, ff)) / math.sqrt(ff)).astype(np.float32))
+    b1 = torch.from_numpy((0.5 * rng.standard_normal(ff)).astype(np.float32))
+    b2 = torch.from_numpy((0.5 * rng.standard_normal(d)).astype(np.float32))
+    ln = (torch.from_numpy((1 + 0.1 * rng.standard_normal(d)).astype(np.float32)),
+          torch.from_numpy((0.1 * rng.standard_normal(d)).astype(np.float32)))
+    pos_mod = 320 if posmode == "mod" else 0
+    pos, theta = None, None
+    dv = _dev()
+    cu = lambda t: None if t is None else t.to(dv)
+    if posmode == "theta":
+        mask = np.ones((2, M // 2), np.float32)
+        mask[1, -300:] = 0
+        pos = torch.from_numpy(orc.position_embedding_sine(mask, d).reshape(M, d).astype(np.float32))
+        theta = ops.posenc_theta(torch.from_numpy(mask).to(dv)).reshape(-1)
+        out = ops.ffn(cu(x), cu(w1), cu(b1), cu(w2), cu(b2), (cu(ln[0]), cu(ln[1])), pos_theta=theta)
+    else:
+        if posmode is not None:
+            pos = torch.from_numpy(rng.standard_normal((pos_mod or M, d)).astype(np.float32))
+        out = ops.ffn(cu(x), cu(w1), cu(b1), cu(w2), cu(b2), (cu(ln[0]), cu(ln[1])), pos=cu(pos), pos_mod=pos_mod)
+    torch.cuda.synchronize()
+    xf = x.float().numpy()
+    h = orc.gelu((xf @ w1.float().numpy().T + b1.numpy()).astype(np.float32))
+    h = _bf16(h).float().numpy()                                   # the kernel keeps H in bf16
+    y = xf + h @ w2.float().numpy().T + b2.numpy()
+    ref = orc.layer_norm(y.astype(np.float32), ln[0].numpy(), ln[1].numpy())
+    _assert_close(_f(out["out"]), ref, what="out")
+    if pos is not None:
+        prow = np.arange(M) % pos_mod if pos_mod else np.arange(M)
+        _assert_close(_f(out["out_pos"]), ref + pos.numpy()[prow], what="out_pos")

@@ -39,8 +39,8 @@ n = (Lk + 127) // 128
 t0 = buf[buf > 0].min()
 names = {0: "softmax g0 (tile 0, keys lo)", 1: "softmax g1 (tile 0, keys hi)", 2: "softmax g2 (tile 1, keys lo)",
          3: "softmax g3 (tile 1, keys hi)", 4: "MMA issuer tile 0", 5: "MMA issuer tile 1"}
-slots = {0: ["top", "s_full", "S->reg", "max", "-", "exp", "o_full", "P stored"],
-         4: ["top", "kv+s_free", "p_rdy lo", "p_rdy hi", "-", "-", "-", "-"]}
+slots = {0: ["top", "s_full", "S->reg", "max", "s_free arr", "exp", "o_full", "P stored"],
+         4: ["QK lo", "QK hi", "PV lo", "PV hi", "-", "-", "-", "-"]}
 for role in range(6):
     print(names[role])
     sl = slots[4 if role >= 4 else 0]
@@ -51,6 +51,6 @@ for role in range(6):
     if role < 4:
         per = np.diff(buf[role, 1:n, 7]).mean()
         d_ = buf[role, 2:n, :].astype(np.float64)
-        pairs = [(0, 1), (1, 2), (2, 3), (3, 5), (5, 6), (6, 7)]
+        pairs = [(0, 1), (1, 2), (2, 4), (4, 3), (3, 5), (5, 6), (6, 7)]
         print(f"  steady period {per:.0f} clk; mean phase lengths: "
               + ", ".join(f"{sl[a]}->{sl[b_]} {np.mean(d_[:, b_] - d_[:, a]):.0f}" for a, b_ in pairs))

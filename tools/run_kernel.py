@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs one kernel of the hot path at the headline (C2) shapes a few times -- the target command for
-`ncu --set full` captures:   python tools/run_kernel.py attn_self | attn_cross | gemm_ffn_up | gemm_ffn_down | gemm_qk"""
+`ncu --set full` captures:   python tools/run_kernel.py attn_self | attn_cross | attn_q | ffn_video | ffn_query | gemm_ffn_up | gemm_ffn_down | gemm_qk"""
 import math
 import os
 import sys
@@ -27,6 +27,19 @@ if which.startswith("attn"):
     vt = vt.to(dev)
     mask = torch.ones(B, Lk, device=dev) if which == "attn_cross" else None
     fn = lambda: ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask)
+elif which.startswith("ffn"):
+    M = B * L if which == "ffn_video" else B * Q
+    x = rnd(M, d).to(torch.bfloat16).to(dev)
+    w1 = (rnd(ff, d) / math.sqrt(d)).to(torch.bfloat16).to(dev)
+    w2 = (rnd(d, ff) / math.sqrt(ff)).to(torch.bfloat16).to(dev)
+    b1, b2 = rnd(ff).to(dev), rnd(d).to(dev)
+    ln = (torch.ones(d, device=dev), torch.zeros(d, device=dev))
+    if which == "ffn_video":
+        theta = ops.posenc_theta(torch.ones(B, L, device=dev)).reshape(-1)
+        fn = lambda: ops.ffn(x, w1, b1, w2, b2, ln, pos_theta=theta)
+    else:
+        pos = rnd(Q, d).to(dev)
+        fn = lambda: ops.ffn(x, w1, b1, w2, b2, ln, pos=pos, pos_mod=Q)
 else:
     M = B * L
     if which == "gemm_ffn_up":
