@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 1
+#define SVOL_ABI_VERSION 2
 
 enum {
   SVOL_OK = 0,
@@ -75,6 +75,8 @@ typedef struct svol_gemm_epilogue {
   svol_bf16* out_vt;          /* per-head transposed output [(M / vt_len) * N, vt_pitch] or NULL */
   int32_t vt_len;             /* tokens per sample (row = b * vt_len + l) */
   int32_t vt_pitch;           /* row pitch of out_vt in elements (multiple of 8, >= vt_len) */
+  const float* pos_theta;     /* alternative to pos for out_pos: fp32 [M] angles from svol_posenc_theta; the sine
+                                 encoding is evaluated in the epilogue (needs N == 256), no table is read */
 } svol_gemm_epilogue;
 
 typedef struct svol_gemm_args {
@@ -185,6 +187,10 @@ int svol_gate_scores(const svol_bf16* xpos, const float* u, float* scores, int32
 int svol_gate_apply(const svol_bf16* x, const float* scores, const float* ln_weight, const float* ln_bias,
                     const float* pos, svol_bf16* mem, svol_bf16* mem_pos, float* att_out /* [B,L] or NULL */,
                     int32_t B, int32_t L, int32_t d, int32_t H, float eps, void* stream);
+/* Same, with the sine positions evaluated in place from theta [B*L] (svol_posenc_theta) instead of a table. */
+int svol_gate_apply_theta(const svol_bf16* x, const float* scores, const float* ln_weight, const float* ln_bias,
+                          const float* theta, svol_bf16* mem, svol_bf16* mem_pos, float* att_out, int32_t B, int32_t L,
+                          int32_t d, int32_t H, float eps, void* stream);
 
 /* Output heads (svanet.py:125-127): logits = class_embed(hs); boxes = sigmoid(bbox_embed.layers.2(h2))
  * where h2 is the output of the two hidden box-MLP layers (svol_gemm_bf16 with ReLU).

@@ -91,7 +91,7 @@ int launch_add_pos_bf16(const float*, const float*, svol_bf16*, int, int, int, c
 int launch_gate_vectors(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
 int launch_gate_scores(const svol_bf16*, const float*, float*, int, int, int, int, cudaStream_t);
 int launch_gate_apply(const svol_bf16*, const float*, const float*, const float*, const float*, svol_bf16*, svol_bf16*,
-                      float*, int, int, int, int, float, cudaStream_t);
+                      float*, int, int, int, int, float, bool, cudaStream_t);
 int launch_heads(const svol_bf16*, const svol_bf16*, const float*, const float*, const float*, const float*, float*,
                  float*, int, int, cudaStream_t);
 int launch_postprocess(const float*, const float*, float*, int32_t*, int, int, int, cudaStream_t);
@@ -192,7 +192,14 @@ int svol_gate_apply(const svol_bf16* x, const float* scores, const float* lw, co
                     float eps, void* stream) {
   SVOL_REQUIRE(x); SVOL_REQUIRE(scores); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(pos); SVOL_REQUIRE(mem);
   SVOL_REQUIRE(mem_pos);
-  return launch_gate_apply(x, scores, lw, lb, pos, mem, mem_pos, att_out, B, L, d, H, eps, SVOL_STREAM(stream));
+  return launch_gate_apply(x, scores, lw, lb, pos, mem, mem_pos, att_out, B, L, d, H, eps, false, SVOL_STREAM(stream));
+}
+int svol_gate_apply_theta(const svol_bf16* x, const float* scores, const float* lw, const float* lb, const float* theta,
+                          svol_bf16* mem, svol_bf16* mem_pos, float* att_out, int32_t B, int32_t L, int32_t d, int32_t H,
+                          float eps, void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(scores); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(theta); SVOL_REQUIRE(mem);
+  SVOL_REQUIRE(mem_pos);
+  return launch_gate_apply(x, scores, lw, lb, theta, mem, mem_pos, att_out, B, L, d, H, eps, true, SVOL_STREAM(stream));
 }
 int svol_heads(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const float* bc, const float* wb,
                const float* bb, float* logits, float* boxes, int32_t rows, int32_t d, void* stream) {

@@ -46,7 +46,7 @@ struct Cfg {
   static constexpr int OFF_STAGES = W_BYTES;
   static constexpr int OFF_STG = OFF_STAGES + STAGES * STAGE_BYTES;                    // epilogue staging
   static constexpr int OFF_TAIL = OFF_STG + EPI_WARPS * STG_BYTES;
-  static constexpr int SMEM_BYTES = OFF_TAIL + 256 /*barriers*/ + 2 * BM * 4 /*LN exchange*/ + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = OFF_TAIL + 256 /*barriers*/ + 2 * BM * 4 /*LN exchange*/ + 512 /*1/dim_t*/ + 1024 /*align*/;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 }  // namespace gemm
@@ -126,6 +126,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* stages = smem + C::OFF_STAGES;
   GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + C::OFF_TAIL);
   float* ln_x = reinterpret_cast<float*>(smem + C::OFF_TAIL + 256);   // [2 halves][128 rows]
+  float* s_idt = ln_x + 2 * BM;                                       // [128] 1 / dim_t of the sine positional encoding
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -159,6 +160,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tail->tmem_base);
+  if (ep.pos_theta != nullptr)      // 1 / dim_t[2k] = 10000^(-2k/256)  (position_encoding.py:64-65)
+    for (int i = threadIdx.x; i < BN / 2; i += THREADS)
+      s_idt[i] = 1.0f / powf(10000.f, __fdiv_rn(__fmul_rn(2.f, static_cast<float>(i)), static_cast<float>(BN)));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -342,13 +346,26 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // the broadcast case is read directly (its 320 x 256 table stays in L1/L2).
         uint8_t* obase = reinterpret_cast<uint8_t*>(ep.out_pos + static_cast<size_t>(slab_row0) * ep.ld_out + col0);
         const int prow = ep.pos_row_mod > 0 ? row % ep.pos_row_mod : row;
+        const float theta = (ep.pos_theta != nullptr && row_ok) ? __ldg(ep.pos_theta + row) : 0.f;
 #pragma unroll
         for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
           uint4 q[8];
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             uint4 pq[8];                                              // 32 fp32 pos values of this row
-            if (ep.pos_row_mod > 0) {
+            if (ep.pos_theta != nullptr) {
+              // sine encoding in place: columns (2k, 2k+1) = (sin, cos)(theta / dim_t[2k]); theta in [0, 2 pi] is folded
+              // to [-pi, pi] for the MUFU sin / cos
+              const float* it = s_idt + (half * COLS_PER_THREAD + blk * 64 + sub * 32) / 2;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float a0 = theta * it[2 * j], a1 = theta * it[2 * j + 1];
+                a0 = a0 > 3.14159265358979f ? a0 - 6.28318530717959f : a0;
+                a1 = a1 > 3.14159265358979f ? a1 - 6.28318530717959f : a1;
+                pq[j] = make_uint4(__float_as_uint(__sinf(a0)), __float_as_uint(__cosf(a0)), __float_as_uint(__sinf(a1)),
+                                   __float_as_uint(__cosf(a1)));
+              }
+            } else if (ep.pos_row_mod > 0) {
               const uint4* pp = reinterpret_cast<const uint4*>(ep.pos + static_cast<size_t>(prow) * ep.ld_pos + col0 + blk * 64 + sub * 32);
 #pragma unroll
               for (int j = 0; j < 8; ++j) pq[j] = row_ok ? __ldg(pp + j) : make_uint4(0u, 0u, 0u, 0u);
@@ -417,6 +434,8 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   if (a.N % BN != 0 || a.K % BK != 0 || a.M <= 0) return svol_fail(SVOL_ERR_SHAPE, "gemm: need N % 256 == 0, K % 64 == 0, M > 0");
   if (a.ep.ln_weight && a.N != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: fused LayerNorm needs N == 256");
   if (a.ep.out_vt && a.N != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: transposed-V store needs N == 256");
+  if (a.ep.pos_theta && a.N != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: in-epilogue sine positions need N == 256");
+  if (a.ep.out_pos && !a.ep.pos && !a.ep.pos_theta) return svol_fail(SVOL_ERR_NULL, "gemm: out_pos needs pos or pos_theta");
   CUtensorMap tmA, tmB;
   int rc = make_tensor_map_2d(&tmA, a.A, a.K, a.M, a.lda, BK, BM, 128);
   if (rc) return rc;

@@ -310,6 +310,9 @@ int launch_gate_scores(const svol_bf16* xpos, const float* u, float* scores, int
 }
 
 // att[b,l] = mean_h softmax_l(scores[b,h,:]); mem = LN1(x + att*x); mem_pos = mem + pos
+// kTheta: `pos` is the [B*L] angle array of svol_posenc_theta and the sine encoding is evaluated in place
+// (columns (2k, 2k+1) = (sin, cos)(theta / 10000^(2k/d))) instead of reading the 1 KB/token fp32 table.
+template <bool kTheta>
 __global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __restrict__ x,
                                                          const float* __restrict__ scores,
                                                          const float* __restrict__ lw, const float* __restrict__ lb,
@@ -334,6 +337,10 @@ __global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __
   const float4 o0 = __ldg(reinterpret_cast<const float4*>(lb) + lane * 2), o1 = __ldg(reinterpret_cast<const float4*>(lb) + lane * 2 + 1);
   const float gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
   const float gb[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+  float idt[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    idt[i] = 1.0f / powf(10000.f, __fdiv_rn(__fmul_rn(2.f, static_cast<float>(lane * 4 + i)), static_cast<float>(GATE_D)));
   for (int r = warp; r < GATE_ROWS; r += 8) {
     const int l = l0 + r;
     if (l >= L) break;
@@ -355,9 +362,21 @@ __global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const float dlt = v[i] - mean; ss += dlt * dlt; }
     const float rstd = rsqrtf(warp_sum(ss) * (1.0f / GATE_D) + eps);
-    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + row * GATE_D) + lane * 2);
-    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + row * GATE_D) + lane * 2 + 1);
-    const float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float pp[8];
+    if (kTheta) {
+      const float theta = __ldg(pos + row);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a = theta * idt[i];
+        a = a > 3.14159265358979f ? a - 6.28318530717959f : a;     // theta in [0, 2 pi] -> [-pi, pi] for MUFU sin / cos
+        pp[2 * i] = __sinf(a);
+        pp[2 * i + 1] = __cosf(a);
+      }
+    } else {
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + row * GATE_D) + lane * 2);
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + row * GATE_D) + lane * 2 + 1);
+      pp[0] = p0.x; pp[1] = p0.y; pp[2] = p0.z; pp[3] = p0.w; pp[4] = p1.x; pp[5] = p1.y; pp[6] = p1.z; pp[7] = p1.w;
+    }
     float y[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) y[i] = (v[i] - mean) * rstd * gw[i] + gb[i];
@@ -372,11 +391,17 @@ __global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __
 
 int launch_gate_apply(const svol_bf16* x, const float* scores, const float* lw, const float* lb, const float* pos,
                       svol_bf16* mem, svol_bf16* mem_pos, float* att_out, int B, int L, int d, int H, float eps,
-                      cudaStream_t stream) {
+                      bool pos_is_theta, cudaStream_t stream) {
   if (d != GATE_D || H != GATE_H || B <= 0 || L <= 0) return svol_fail(SVOL_ERR_SHAPE, "gate_apply: hidden_dim 256 / 8 heads only");
-  gate_apply_kernel<<<dim3((L + GATE_ROWS - 1) / GATE_ROWS, B), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), scores, lw, lb, pos, reinterpret_cast<__nv_bfloat16*>(mem),
-      reinterpret_cast<__nv_bfloat16*>(mem_pos), att_out, L, eps);
+  const dim3 grid((L + GATE_ROWS - 1) / GATE_ROWS, B);
+  if (pos_is_theta)
+    gate_apply_kernel<true><<<grid, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), scores, lw, lb, pos, reinterpret_cast<__nv_bfloat16*>(mem),
+        reinterpret_cast<__nv_bfloat16*>(mem_pos), att_out, L, eps);
+  else
+    gate_apply_kernel<false><<<grid, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), scores, lw, lb, pos, reinterpret_cast<__nv_bfloat16*>(mem),
+        reinterpret_cast<__nv_bfloat16*>(mem_pos), att_out, L, eps);
   return svol_check_launch("gate_apply");
 }
 

@@ -172,7 +172,9 @@ class HeadEngine:
         # activations
         xn = buf("xn", (M, d_in), bf)
         ha, hb = buf("ha", (M, d), bf), buf("hb", (M, d), bf)
-        pos = buf("pos", (M, d), f32)
+        # sine positions: the tcgen05 path evaluates them inside the consuming epilogues from one angle per token;
+        # the 1 KB/token fp32 table is only materialised for the SIMT debug path
+        pos = buf("pos", (M, d), f32) if self.plain else None
         theta = buf("theta", (M,), f32)
         X, Xp = buf("X", (M, d), bf), buf("Xp", (M, d), bf)
         mem, memp = buf("mem", (M, d), bf), buf("memp", (M, d), bf)
@@ -203,7 +205,7 @@ class HeadEngine:
         attn_fn = lib.svol_attention_bf16_plain if self.plain else lib.svol_attention_bf16
 
         def gemm(name, A, W, bias, out=None, act=ACT_NONE, residual=None, ln=None, out_pos=None, pos_t=None,
-                 pos_mod=0, out_vt=None, vt_len=0, vt_pitch=0):
+                 pos_mod=0, out_vt=None, vt_len=0, vt_pitch=0, theta_t=None):
             a = GemmArgs()
             a.A, a.W = P(A), P(W)
             a.M, a.K = A.shape
@@ -219,7 +221,9 @@ class HeadEngine:
             e.out_pos = P(out_pos)
             ld_o = out.stride(0) if out is not None else (out_pos.stride(0) if out_pos is not None else 0)
             e.ld_out = ld_o
-            if out_pos is not None:
+            if out_pos is not None and theta_t is not None:
+                e.pos_theta = P(theta_t)
+            elif out_pos is not None:
                 e.pos, e.ld_pos, e.pos_row_mod = P(pos_t), pos_t.stride(0), pos_mod
             if out_vt is not None:
                 e.out_vt, e.vt_len, e.vt_pitch = P(out_vt), vt_len, vt_pitch
@@ -252,7 +256,8 @@ class HeadEngine:
         plan.ln_in_index = len(plan.calls)
         call("ln_in", lib.svol_layernorm_f32_to_bf16, P(x_in), P(w["in_video.0.ln_w"]), P(w["in_video.0.ln_b"]), P(xn),
              M, d_in, LN_EPS)
-        call("posenc", lib.svol_posenc_sine, P(vmask), P(pos), B, L, d)
+        if self.plain:
+            call("posenc", lib.svol_posenc_sine, P(vmask), P(pos), B, L, d)
         call("posenc_theta", lib.svol_posenc_theta, P(vmask), P(theta), B, L)
         cur = xn
         for i in range(n_proj):
@@ -261,7 +266,8 @@ class HeadEngine:
             gemm(f"in_proj{i}", cur, w[f"in_video.{i}.w"], w[f"in_video.{i}.b"], out=dst,
                  act=ACT_NONE if last else ACT_RELU,
                  ln=None if last else (w[f"in_video.{i + 1}.ln_w"], w[f"in_video.{i + 1}.ln_b"]),
-                 out_pos=Xp if last else None, pos_t=pos if last else None)
+                 out_pos=Xp if last else None, pos_t=pos if last else None,
+                 theta_t=theta if (last and not self.plain) else None)
             cur = dst
         # ---- sketch branch (svanet.py:56-60,87), fp32, B rows
         s_cur = s_in
@@ -281,8 +287,12 @@ class HeadEngine:
             # (a) sketch-conditioned gate + norm1                                        :122-127
             call(p + "gate_vec", lib.svol_gate_vectors, P(s_cur), P(w[p + "gate.w"]), P(w[p + "gate.b"]), P(u), B, d, H)
             call(p + "gate_scores", lib.svol_gate_scores, P(xp_cur), P(u), P(scores), B, L, d, H)
-            call(p + "gate_apply", lib.svol_gate_apply, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]), P(pos),
-                 P(mem), P(memp), None, B, L, d, H, LN_EPS)
+            if self.plain:
+                call(p + "gate_apply", lib.svol_gate_apply, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]), P(pos),
+                     P(mem), P(memp), None, B, L, d, H, LN_EPS)
+            else:
+                call(p + "gate_apply", lib.svol_gate_apply_theta, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]),
+                     P(theta), P(mem), P(memp), None, B, L, d, H, LN_EPS)
             # (b) video self-attention + norm2, FFN + norm3                               :137-143
             gemm(p + "sa_qk", memp, w[p + "sa.wqk"], w[p + "sa.bqk"], out=qk)
             gemm(p + "sa_v", mem, w[p + "sa.wv"], w[p + "sa.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)

@@ -17,7 +17,7 @@ _P = _lib.ptr
 def gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
          pos: Optional[torch.Tensor] = None, pos_mod: int = 0, want_out: bool = True, vt_len: int = 0,
-         plain: bool = False, eps: float = 1e-5):
+         plain: bool = False, eps: float = 1e-5, pos_theta: Optional[torch.Tensor] = None):
     """out = epilogue(A @ W.T).  A [M,K] bf16, W [N,K] bf16.  Returns a dict with 'out' [M,N] bf16,
     'out_pos' (when ``pos`` is given) and 'out_vt' [(M/vt_len)*N, round_up(vt_len,8)] (when ``vt_len``)."""
     _lib.require_device()
@@ -40,6 +40,9 @@ def gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if pos is not None:
         res["out_pos"] = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
         e.out_pos, e.pos, e.ld_pos, e.pos_row_mod = _P(res["out_pos"]), _P(pos), pos.stride(0), pos_mod
+    elif pos_theta is not None:
+        res["out_pos"] = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
+        e.out_pos, e.pos_theta = _P(res["out_pos"]), _P(pos_theta)
     if vt_len:
         pitch = (vt_len + 7) // 8 * 8
         res["out_vt"] = torch.zeros(((M // vt_len) * N, pitch), device=A.device, dtype=torch.bfloat16)
@@ -132,8 +135,10 @@ def add_pos_bf16(x: torch.Tensor, pos: Optional[torch.Tensor], rows: int, mod: i
 
 
 def gate(x: torch.Tensor, xpos: torch.Tensor, sketch: torch.Tensor, in_w: torch.Tensor, in_b: torch.Tensor,
-         ln_w: torch.Tensor, ln_b: torch.Tensor, pos: torch.Tensor, B: int, L: int, H: int = 8, eps: float = 1e-5):
-    """The three gate kernels in sequence.  Returns (mem, mem_pos, att [B,L], scores [B,H,L])."""
+         ln_w: torch.Tensor, ln_b: torch.Tensor, pos: torch.Tensor, B: int, L: int, H: int = 8, eps: float = 1e-5,
+         pos_is_theta: bool = False):
+    """The three gate kernels in sequence.  Returns (mem, mem_pos, att [B,L], scores [B,H,L]).  ``pos`` is the fp32
+    table [B*L, d], or (``pos_is_theta``) the [B*L] angles of :func:`posenc_theta`."""
     _lib.require_device()
     lib = _lib.get_lib()
     d = x.shape[-1]
@@ -144,8 +149,9 @@ def gate(x: torch.Tensor, xpos: torch.Tensor, sketch: torch.Tensor, in_w: torch.
     mem, mem_pos = torch.empty_like(x), torch.empty_like(x)
     _lib.check(lib.svol_gate_vectors(_P(sketch), _P(in_w), _P(in_b), _P(u), B, d, H, s), "gate_vectors")
     _lib.check(lib.svol_gate_scores(_P(xpos), _P(u), _P(scores), B, L, d, H, s), "gate_scores")
-    _lib.check(lib.svol_gate_apply(_P(x), _P(scores), _P(ln_w), _P(ln_b), _P(pos), _P(mem), _P(mem_pos), _P(att), B, L, d,
-                                   H, eps, s), "gate_apply")
+    fn = lib.svol_gate_apply_theta if pos_is_theta else lib.svol_gate_apply
+    _lib.check(fn(_P(x), _P(scores), _P(ln_w), _P(ln_b), _P(pos), _P(mem), _P(mem_pos), _P(att), B, L, d, H, eps, s),
+               "gate_apply")
     return mem, mem_pos, att, scores
 
 

@@ -46,6 +46,7 @@ GEMM_CASES = [
     (3136, 256, 256, dict(bias=True, residual=True, ln=True, pos=True, pos_mod=320)),
     (2 * 196, 256, 256, dict(bias=True, vt_len=196)),
     (40000, 256, 256, dict(bias=True)),          # > 148 tiles: persistent loop, both TMEM stages, phase wrap
+    (2 * 392, 256, 256, dict(bias=True, theta=True)),   # out_pos with the sine encoding evaluated in the epilogue
 ]
 
 
@@ -53,8 +54,8 @@ GEMM_CASES = [
 @pytest.mark.parametrize("M,N,K,flags", GEMM_CASES)
 def test_gemm_epilogues(M, N, K, flags, plain):
     from svol_b200 import ops
-    if plain and M > 5000:
-        pytest.skip("plain kernel: small cases only")
+    if plain and (M > 5000 or flags.get("theta")):
+        pytest.skip("plain kernel: small cases, table positions only")
     rng = np.random.RandomState(M + N + K)
     A = _bf16(rng.standard_normal((M, K)).astype(np.float32))
     W = _bf16((rng.standard_normal((N, K)) / math.sqrt(K)).astype(np.float32))
@@ -71,8 +72,14 @@ def test_gemm_epilogues(M, N, K, flags, plain):
 
     d = _dev()
     cu = lambda t: None if t is None else t.to(d)
+    theta = None
+    if flags.get("theta"):
+        mask = np.ones((2, M // 2), np.float32)
+        mask[1, -100:] = 0
+        pos = torch.from_numpy(orc.position_embedding_sine(mask.astype(bool), N).reshape(M, N).astype(np.float32))
+        theta = ops.posenc_theta(torch.from_numpy(mask).to(d)).reshape(-1)
     out = ops.gemm(cu(A), cu(W), cu(bias), act=act, residual=cu(res_t), ln=None if ln is None else (cu(ln[0]), cu(ln[1])),
-                   pos=cu(pos), pos_mod=pos_mod, vt_len=vt_len, plain=plain)
+                   pos=None if theta is not None else cu(pos), pos_mod=pos_mod, vt_len=vt_len, plain=plain, pos_theta=theta)
     torch.cuda.synchronize()
 
     ref = A.float().numpy() @ W.float().numpy().T
@@ -197,8 +204,9 @@ def test_add_pos_broadcast():
     assert np.array_equal(y2, np.tile(_f(_bf16(x + p)), (2, 1)))
 
 
+@pytest.mark.parametrize("theta", [False, True], ids=["table", "theta"])
 @pytest.mark.parametrize("B,L", [(2, 1568), (3, 70)])
-def test_gate(B, L):
+def test_gate(B, L, theta):
     """Sketch-conditioned gate vs the oracle's full multi-head attention weights (the CUDA path never
     forms K; the key bias cancels in the softmax)."""
     from svol_b200 import ops
@@ -206,6 +214,7 @@ def test_gate(B, L):
     d_model, H = 256, 8
     x = _bf16(rng.standard_normal((B, L, d_model)).astype(np.float32))
     mask = np.ones((B, L), bool)
+    mask[-1, L - L // 5:] = False                 # one padded sample: its angles are normalised by the valid length
     pos = orc.position_embedding_sine(mask, d_model)
     xpos = _bf16(x.float().numpy() + pos)
     skch = rng.standard_normal((B, d_model)).astype(np.float32)
@@ -214,8 +223,9 @@ def test_gate(B, L):
     lw, lb = (1 + 0.1 * rng.standard_normal(d_model)).astype(np.float32), (0.1 * rng.standard_normal(d_model)).astype(np.float32)
     dv = _dev()
     t = lambda a: torch.from_numpy(a).to(dv)
+    pos_arg = ops.posenc_theta(t(mask.astype(np.float32))).reshape(-1) if theta else t(pos.reshape(B * L, d_model))
     mem, mem_pos, att, _ = ops.gate(x.reshape(B * L, d_model).to(dv), xpos.reshape(B * L, d_model).to(dv), t(skch), t(in_w),
-                                    t(in_b), t(lw), t(lb), t(pos.reshape(B * L, d_model)), B, L, H)
+                                    t(in_b), t(lw), t(lb), pos_arg, B, L, H, pos_is_theta=theta)
     xf, xpf = x.float().numpy(), xpos.float().numpy()
     _, att_ref = orc.multihead_attention(skch[:, None, :], xpf, xpf, in_w, in_b, np.eye(d_model, dtype=np.float32),
                                          np.zeros(d_model, np.float32), H)
