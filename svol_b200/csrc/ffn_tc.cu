@@ -115,12 +115,6 @@ __device__ __forceinline__ float2 gelu_erf_q4_x2(float2 t) {
   return __ffma2_rn(hx, se, make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f)));
 }
 
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-
 __global__ void __launch_bounds__(ffn::THREADS, 1)
 ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,

@@ -40,13 +40,14 @@ constexpr int STG_BYTES = 32 * 128;                     // per epilogue warp: 32
 
 template <bool kResidentW>
 struct Cfg {
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = kResidentW ? 3 : 4;
   static constexpr int STAGE_BYTES = kResidentW ? A_BYTES : A_BYTES + B_BYTES;
   static constexpr int W_BYTES = kResidentW ? RES_KB * B_BYTES : 0;                  // 128 KB
   static constexpr int OFF_STAGES = W_BYTES;
   static constexpr int OFF_STG = OFF_STAGES + STAGES * STAGE_BYTES;                    // epilogue staging
   static constexpr int OFF_TAIL = OFF_STG + EPI_WARPS * STG_BYTES;
-  static constexpr int SMEM_BYTES = OFF_TAIL + 256 /*barriers*/ + 2 * BM * 4 /*LN exchange*/ + 512 /*1/dim_t*/ + 1024 /*align*/;
+  static constexpr int PAR_BYTES = kResidentW ? 3 * BN * 4 : 0;     // bias, ln_w, ln_b of the CTA's fixed column block
+  static constexpr int SMEM_BYTES = OFF_TAIL + 256 /*barriers*/ + 2 * BM * 4 /*LN exchange*/ + 512 /*1/dim_t*/ + PAR_BYTES + 1024 /*align*/;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 }  // namespace gemm
@@ -102,6 +103,8 @@ __device__ __forceinline__ void block_store(uint8_t* stg, const uint4 (&q)[8], u
 }
 __device__ __forceinline__ void block_load(uint8_t* stg, uint4 (&q)[8], const uint8_t* gbase, size_t pitch,
                                            int rows_valid, int lane) {
+  if (lane == 0) tma_store_wait_read<0>();      // a TMA store may still be reading this warp's staging buffer
+  __syncwarp();
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int row = k * 4 + (lane >> 3), ch = lane & 7;
@@ -115,9 +118,27 @@ __device__ __forceinline__ void block_load(uint8_t* stg, uint4 (&q)[8], const ui
   __syncwarp();
 }
 
+// [32 rows x 64 bf16 columns] of this warp -> global through its staging buffer and ONE asynchronous TMA store
+// (box 64 x 32, 128B swizzle == the staging layout above): 8 STS per lane instead of 8 STS + 8 LDS + 8 STG, and the
+// warp does not wait for the global writes.  Rows beyond M are clipped by the tensor map.
+__device__ __forceinline__ void block_store_tma(uint8_t* stg, const uint4 (&q)[8], const CUtensorMap* tm, int col, int row0,
+                                                int lane) {
+  if (lane == 0) tma_store_wait_read<0>();      // the previous store has finished reading the staging buffer
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = q[j];
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tm, stg, col, row0);
+    tma_store_commit();
+  }
+}
+
 template <bool kResidentW>
 __global__ void __launch_bounds__(gemm::THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutPos,
                     const GemmEpilogue ep, int M, int N, int K) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
@@ -127,6 +148,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   GemmSmemTail* tail = reinterpret_cast<GemmSmemTail*>(smem + C::OFF_TAIL);
   float* ln_x = reinterpret_cast<float*>(smem + C::OFF_TAIL + 256);   // [2 halves][128 rows]
   float* s_idt = ln_x + 2 * BM;                                       // [128] 1 / dim_t of the sine positional encoding
+  float* s_par = s_idt + BN / 2;                                      // resident variant: bias | ln_w | ln_b of column block my_n
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,6 +182,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tail->tmem_base);
+  if (kResidentW) {                 // per-column parameters of this CTA's (fixed) column block -> shared memory
+    for (int i = threadIdx.x; i < BN; i += THREADS) {
+      s_par[i] = ep.bias ? __ldg(ep.bias + my_n * BN + i) : 0.f;
+      s_par[BN + i] = ep.ln_weight ? __ldg(ep.ln_weight + my_n * BN + i) : 1.f;
+      s_par[2 * BN + i] = ep.ln_weight ? __ldg(ep.ln_bias + my_n * BN + i) : 0.f;
+    }
+  }
   if (ep.pos_theta != nullptr)      // 1 / dim_t[2k] = 10000^(-2k/256)  (position_encoding.py:64-65)
     for (int i = threadIdx.x; i < BN / 2; i += THREADS)
       s_idt[i] = 1.0f / powf(10000.f, __fdiv_rn(__fmul_rn(2.f, static_cast<float>(i)), static_cast<float>(BN)));
@@ -266,11 +295,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       SVOL_GTR(0, it, 2);
 
       if (ep.bias) {
-        const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
+        if (kResidentW) {
+          const uint32_t bp = smem_u32(s_par + half * COLS_PER_THREAD);
 #pragma unroll
-        for (int i = 0; i < COLS_PER_THREAD / 4; ++i) {
-          const float4 b = __ldg(bp + i);
-          v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          for (int i = 0; i < COLS_PER_THREAD / 4; ++i) {
+            const float4 b = lds_f4(bp + i * 16);
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          }
+        } else {
+          const float4* bp = reinterpret_cast<const float4*>(ep.bias + col0);
+#pragma unroll
+          for (int i = 0; i < COLS_PER_THREAD / 4; ++i) {
+            const float4 b = __ldg(bp + i);
+            v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+          }
         }
       }
       if (ep.act == SVOL_ACT_RELU) {
@@ -316,9 +354,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const float rstd = rsqrtf(var + ep.ln_eps);
         const float4* gp = reinterpret_cast<const float4*>(ep.ln_weight + col0);
         const float4* bp = reinterpret_cast<const float4*>(ep.ln_bias + col0);
+        const uint32_t sgp = smem_u32(s_par + BN + half * COLS_PER_THREAD), sbp = smem_u32(s_par + 2 * BN + half * COLS_PER_THREAD);
 #pragma unroll
         for (int i = 0; i < COLS_PER_THREAD / 4; ++i) {
-          const float4 g = __ldg(gp + i), b = __ldg(bp + i);
+          const float4 g = kResidentW ? lds_f4(sgp + i * 16) : __ldg(gp + i);
+          const float4 b = kResidentW ? lds_f4(sbp + i * 16) : __ldg(bp + i);
           v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * g.x + b.x;
           v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g.y + b.y;
           v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g.z + b.z;
@@ -327,7 +367,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       SVOL_GTR(0, it, 5);
       if (ep.out) {
-        uint8_t* obase = reinterpret_cast<uint8_t*>(ep.out + static_cast<size_t>(slab_row0) * ep.ld_out + col0);
 #pragma unroll
         for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
           uint4 q[8];
@@ -336,7 +375,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const float* vv = &v[blk * 64 + j * 8];
             q[j] = make_uint4(pack_bf16x2(vv[0], vv[1]), pack_bf16x2(vv[2], vv[3]), pack_bf16x2(vv[4], vv[5]), pack_bf16x2(vv[6], vv[7]));
           }
-          block_store(stg, q, obase + blk * 128, static_cast<size_t>(ep.ld_out) * 2, rows_valid, lane);
+          block_store_tma(stg, q, &tmOut, col0 + blk * 64, slab_row0, lane);
         }
       }
       SVOL_GTR(0, it, 6);
@@ -344,7 +383,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // second output: x + pos (the q/k operand of the next attention block).  pos rows follow the output
         // rows (pos_row_mod == 0) or repeat with period pos_row_mod (query embedding broadcast over the batch);
         // the broadcast case is read directly (its 320 x 256 table stays in L1/L2).
-        uint8_t* obase = reinterpret_cast<uint8_t*>(ep.out_pos + static_cast<size_t>(slab_row0) * ep.ld_out + col0);
         const int prow = ep.pos_row_mod > 0 ? row % ep.pos_row_mod : row;
         const float theta = (ep.pos_theta != nullptr && row_ok) ? __ldg(ep.pos_theta + row) : 0.f;
 #pragma unroll
@@ -383,7 +421,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                           pack_bf16x2(vv[6] + __uint_as_float(c.z), vv[7] + __uint_as_float(c.w)));
             }
           }
-          block_store(stg, q, obase + blk * 128, static_cast<size_t>(ep.ld_out) * 2, rows_valid, lane);
+          block_store_tma(stg, q, &tmOutPos, col0 + blk * 64, slab_row0, lane);
         }
       }
       if (row_ok && ep.out_vt) {
@@ -398,6 +436,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();   // reconverge before the next tile's warp-collective tcgen05.ld
       SVOL_GTR(0, it, 7);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's TMA stores are complete
   }
 
   tcgen05_fence_before();
@@ -412,7 +451,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // host side
 // ---------------------------------------------------------------------------------------------
 template <bool kResidentW>
-static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t stream) {
+static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                          const CUtensorMap& tmOutPos, cudaStream_t stream) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
   static bool configured = false;
@@ -425,7 +465,7 @@ static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUten
   const int tiles = m_blocks * n_blocks;
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (kResidentW) grid = grid / n_blocks * n_blocks;       // every CTA owns one n block
-  gemm_bf16_tc_kernel<kResidentW><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, a.ep, a.M, a.N, a.K);
+  gemm_bf16_tc_kernel<kResidentW><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, a.ep, a.M, a.N, a.K);
   return svol_check_launch("gemm_bf16_tc");
 }
 
@@ -441,8 +481,19 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_tensor_map_2d(&tmB, a.W, a.K, a.N, a.ldw, BK, BN, 128);
   if (rc) return rc;
+  // outputs are written by TMA stores of [32 rows x 64 columns] boxes (rows beyond M clipped by the map)
+  CUtensorMap tmOut = tmA, tmOutPos = tmA;
+  if (a.ep.out) {
+    rc = make_tensor_map_2d(&tmOut, a.ep.out, a.N, a.M, a.ep.ld_out, 64, 32, 128);
+    if (rc) return rc;
+  }
+  if (a.ep.out_pos) {
+    rc = make_tensor_map_2d(&tmOutPos, a.ep.out_pos, a.N, a.M, a.ep.ld_out, 64, 32, 128);
+    if (rc) return rc;
+  }
   const bool resident = a.K == RES_K && a.N / BN <= sm_count();
-  return resident ? launch_variant<true>(a, tmA, tmB, stream) : launch_variant<false>(a, tmA, tmB, stream);
+  return resident ? launch_variant<true>(a, tmA, tmB, tmOut, tmOutPos, stream)
+                  : launch_variant<false>(a, tmA, tmB, tmOut, tmOutPos, stream);
 }
 
 }  // namespace svol
