@@ -4,7 +4,7 @@ criterion (BASELINE.json metric), on N GPUs of one node, one process per GPU.
 
   python bench.py --gpus 1 --steps 20 --warmup 5                       # this repo's CUDA path
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-  python bench.py --impl reference ...                                 # the reference's CPU path (oracle port)
+  python bench.py --impl reference ...                                 # the reference's CPU path (oracle/torch_port.py)
 
 One step = one pass of the hot path over one batch of B synthetic pairs per GPU (weak scaling,
 pairs are independent: no data-path collective).  Prints ONE JSON line on rank 0:
@@ -15,7 +15,8 @@ pairs are independent: no data-path collective).  Prints ONE JSON line on rank 0
                features, sketch feature, masks and target boxes from pinned host memory, runs
                forward + criterion, and reads the losses back
   roofline     the dominant kernel of the step, timed live per launch with CUDA events
-  cpu_baseline the CPU oracle (numpy port of the reference path) on a bounded sample, rank 0, N=1
+  cpu_baseline the reference's CPU path (oracle/torch_port.py: same ATen / scipy calls as the reference) on a bounded
+               sample, rank 0, N=1
 """
 import argparse
 import json
@@ -142,22 +143,25 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ CPU reference arm
 def cpu_reference_step_fn(cfg, batch, seed=0):
-    """One step of the reference's CPU path (the oracle port: numpy/BLAS on all host threads):
-    forward + matcher + criterion on `batch` pairs."""
-    from oracle import lsap, svol_oracle as orc
+    """One step of the reference's CPU path: forward + matcher + criterion on `batch` pairs, through
+    oracle/torch_port.py -- the reference's algorithm restated with the reference's own library calls (ATen
+    multi_head_attention_forward / layer_norm / gelu / cdist / cross_entropy on all host threads, one scipy
+    linear_sum_assignment per frame, the full cross-batch cost matrix).  The reference itself is Python and is not
+    shipped to the GPU box, hence "kind": "port"; the port is pinned to the reference's golden outputs in
+    tests/test_oracle_golden.py."""
+    import torch
+    from oracle import torch_port as tp
     from svol_b200 import synth
-    try:
-        lsap.build()
-    except Exception:
-        pass
-    sd = synth.random_state_dict(cfg, seed)
+    torch.set_num_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1; use every host core
+    sd = tp.state_dict_to_torch(synth.random_state_dict(cfg, seed))
     inp = synth.make_inputs(cfg, batch, seed, padded=True)
     targets = synth.make_targets(cfg, batch, seed, frame_mask=inp["frame_mask"])
+    t = {k: torch.from_numpy(inp[k]) for k in ("src_sketch", "src_sketch_mask", "src_video", "src_video_mask")}
 
     def step():
-        out = orc.svanet_forward(sd, inp["src_sketch"], inp["src_sketch_mask"], inp["src_video"], inp["src_video_mask"],
-                                 nheads=cfg.nheads, dtype=np.float32)
-        return orc.set_criterion(out, targets, cfg)
+        out = tp.svanet_forward(sd, t["src_sketch"], t["src_sketch_mask"], t["src_video"], t["src_video_mask"],
+                                nheads=cfg.nheads)
+        return tp.set_criterion(out, targets, cfg)
     return step
 
 
@@ -186,8 +190,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {**workload_config(args, cfg), "pairs_per_step_cpu": b},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{b} pairs per step x {args.steps} steps of the same workload "
-                                       f"(oracle port of the reference's CPU path, numpy/BLAS threads)"},
+                             "sample": f"{b} pairs per step x {args.steps} steps of the same workload (the reference's CPU path "
+                                       f"restated with its own ATen / scipy calls, oracle/torch_port.py, all host threads)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -328,8 +332,9 @@ def main():
             b = args.ref_batch
             sec = time_cpu(cpu_reference_step_fn(cfg, b), 4, 1)
             cpu_baseline = {"value": b / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                            "sample": f"{b} pairs per step x 4 steps (1 warm-up) of the same workload, oracle port "
-                                      f"(numpy/BLAS, all host threads), {sec * 1e3:.0f} ms per step"}
+                            "sample": f"{b} pairs per step x 4 steps (1 warm-up) of the same workload, the reference's CPU "
+                                      f"path restated with its own ATen / scipy calls (oracle/torch_port.py, all host "
+                                      f"threads), {sec * 1e3:.0f} ms per step"}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -131,3 +131,23 @@ def test_headline_config_full_size_properties(layers):
     one = {k: v[5:6] for k, v in inp.items()}
     _, lg1, bx1 = _run(m, one)
     assert np.abs(lg1[:, 0] - lg[:, 5]).max() < 2e-2 and np.abs(bx1[:, 0] - bx[:, 5]).max() < 5e-3
+
+
+def test_long_clip_config_properties():
+    """BASELINE configs[3] (4x frames: T=128, L=6272, Q=1280 -- 49 / 10 full key tiles per attention row): the
+    tcgen05 path against the SIMT path on the same weights and inputs, a padded sample against its own batch-1
+    forward, finite outputs.  (The numpy oracle needs ~10 GB of score tensors at this size.)"""
+    cfg = C["C4"]
+    inp = synth.make_inputs(cfg, 2, 11, padded=True)
+    inp["src_video_mask"][1, -5 * cfg.tokens_per_frame:] = 0          # make sure the cross-attention mask is exercised
+    m = _model(cfg, 11)
+    _, lg, bx = _run(m, inp)
+    assert lg.shape == (cfg.num_layers, 2, cfg.num_queries, 2)
+    assert np.isfinite(lg).all() and (bx > 0).all() and (bx < 1).all()
+    one = {k: v[1:2] for k, v in inp.items()}
+    _, lg1, bx1 = _run(m, one)
+    assert np.abs(lg1[:, 0] - lg[:, 1]).max() < 2e-2 and np.abs(bx1[:, 0] - bx[:, 1]).max() < 5e-3
+    m.engine.plain = True
+    m.engine._plans.clear()
+    _, lg_pl, bx_pl = _run(m, one)
+    assert np.abs(lg1 - lg_pl).max() < 3e-2 and np.abs(bx1 - bx_pl).max() < 8e-3

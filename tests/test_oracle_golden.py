@@ -141,3 +141,44 @@ def test_postprocess_matches_reference(golden_dir):
     srt, order = orc.postprocess(logits[0], boxes[0], cfg.num_frames)
     assert np.array_equal(order, g["order"])
     assert np.abs(srt - g["sorted"]).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------ torch restatement (CPU baseline)
+@pytest.mark.parametrize("case,cfgname,padded", [("tiny", "tiny", False), ("tiny_pad", "tiny", True), ("C1b_pad", "C1b", True)])
+def test_torch_port_head_matches_reference(golden_dir, case, cfgname, padded):
+    """oracle/torch_port.py (the reference's CPU path restated with the reference's own ATen calls; what
+    bench.py times as the CPU baseline) against the reference's fp32 golden outputs."""
+    import torch
+    from oracle import torch_port as tp
+    g = _load(golden_dir, "head_" + case)
+    cfg = C[cfgname]
+    batch, seed = int(g["batch"]), int(g["seed"])
+    sd = tp.state_dict_to_torch(synth.random_state_dict(cfg, seed))
+    inp = synth.make_inputs(cfg, batch, seed, padded=padded)
+    t = lambda k: torch.from_numpy(inp[k])
+    out = tp.svanet_forward(sd, t("src_sketch"), t("src_sketch_mask"), t("src_video"), t("src_video_mask"), nheads=cfg.nheads)
+    logits = torch.stack([a["pred_logits"] for a in out["aux_outputs"]] + [out["pred_logits"]]).numpy()
+    boxes = torch.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]]).numpy()
+    assert np.abs(logits - g["logits_f32"]).max() < 2e-5
+    assert np.abs(boxes - g["boxes_f32"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("case,cfg,mpf", [("tiny", C["tiny"], 2), ("C2_b4", C["C2"], 2),
+                                          ("C2_video", replace(C["C2"], matcher="video_matcher"), 2)])
+def test_torch_port_criterion_matches_reference(golden_dir, case, cfg, mpf):
+    import torch
+    from oracle import torch_port as tp
+    g = _load(golden_dir, "crit_" + case)
+    batch, seed = int(g["batch"]), int(g["seed"])
+    targets = synth.make_targets(cfg, batch, seed, max_per_frame=int(g["max_per_frame"]))
+    logits, boxes = synth.make_predictions(cfg, batch, seed)
+    tt = torch.from_numpy
+    outputs = {"pred_logits": tt(logits[-1]), "pred_boxes": tt(boxes[-1]),
+               "aux_outputs": [{"pred_logits": tt(a), "pred_boxes": tt(b)} for a, b in zip(logits[:-1], boxes[:-1])]}
+    losses, all_idx = tp.set_criterion(outputs, targets, cfg)
+    for li, idx in enumerate(all_idx):
+        assert np.array_equal(torch.cat([p for p, _ in idx]).numpy(), g[f"pred_idx_{li}"])
+        assert np.array_equal(torch.cat([t for _, t in idx]).numpy(), g[f"tgt_idx_{li}"])
+    for k in [k[5:] for k in g.files if k.startswith("loss/")]:
+        ref = float(g["loss/" + k])
+        assert abs(float(losses[k]) - ref) <= 2e-5 * max(1.0, abs(ref)), k
