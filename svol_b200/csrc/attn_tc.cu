@@ -102,6 +102,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 1.5e-4): x = n + r with
+// n = round(x), |r| <= 0.5; 2^r from the polynomial, 2^n by adding n to the exponent field.  EXPERIMENT, off by default:
+// with -DSVOL_ATTN_POLY_PER4=1|2 that many of every 4 probabilities bypass the MUFU pipe.  Measured on B200 (video
+// self-attention, B=32): 265.7 us (0) / 266.0 us (1) / 304.5 us (2) -- the kernel is not limited by raw MUFU
+// throughput but by the queueing of every other MIO-class instruction (tcgen05.ld/st, mbarrier ops) behind the
+// exponentials, so moving exponentials to the FMA pipe buys nothing; see DESIGN.md 4.1.
+#ifndef SVOL_ATTN_POLY_PER4
+#define SVOL_ATTN_POLY_PER4 0
+#endif
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);                                   // also maps masked scores (-inf) to 2^-126 ~ 0
+  const float t = __fadd_rn(x, 12582912.f);               // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float r = __fsub_rn(x, __fsub_rn(t, 12582912.f));
+  float p = fmaf(0.055170271545648575f, r, 0.2426079511642456f);
+  p = fmaf(p, r, 0.693260908126831f);
+  p = fmaf(p, r, 0.9999282956123352f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 // registers <-> TMEM: this warp's 32 lanes x N consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -286,10 +305,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         while (clock64() - t_start < static_cast<long long>(slot) * STAGGER_CLK) {}
       }
 
+      // Barrier probes are software-pipelined: a (non-blocking) mbarrier.test_wait is issued well before its result
+      // is needed and consumed after independent work; the blocking wait is only the fallback.
+      asm volatile(".reg .pred p_of, p_sf;");
+      uint32_t s_ready = 0;
+      const uint32_t a_sfull = smem_u32(&bars->s_full[g]), a_ofull = smem_u32(&bars->o_full[g]);
+
       for (int j = 0; j < n_tiles; ++j) {
         const int kv0 = j * BKV + half * HALF;
         SVOL_TR(g, j, 0);
-        mbar_wait(&bars->s_full[g], j & 1);
+        if (!s_ready) mbar_wait(&bars->s_full[g], j & 1);
         SVOL_TR(g, j, 1);
         tcgen05_fence_after();
         uint32_t s[HALF];
@@ -345,6 +370,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         float m_use = m_ref == -INFINITY ? 0.f : m_ref;
+        if (j > 0)   // probe: has the previous P V landed (P columns reusable)?  consumed after the exponentials
+          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_of, [%0], %1;" ::"r"(a_ofull), "r"((j - 1) & 1) : "memory");
 
         // one MUFU ex2 per probability (ex2.approx.ftz.bf16x2 was tried: on sm_100 it is issued as two
         // MUFU.EX2.BF16 ops plus a PRMT, so it saves nothing and only costs precision); the subtraction
@@ -355,8 +382,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int i = 0; i < HALF; i += 4) {
           const float2 x0 = __fadd2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), neg_m);
           const float2 x1 = __fadd2_rn(make_float2(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])), neg_m);
-          const float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
-          const float2 p1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+          const float2 p0 = make_float2(ex2_approx(x0.x), SVOL_ATTN_POLY_PER4 >= 2 ? ex2_poly(x0.y) : ex2_approx(x0.y));
+          const float2 p1 = make_float2(ex2_approx(x1.x), SVOL_ATTN_POLY_PER4 >= 1 ? ex2_poly(x1.y) : ex2_approx(x1.y));
           la = __fadd2_rn(la, p0);
           lb = __fadd2_rn(lb, p1);
           s[i >> 1] = pack_bf16x2(p0.x, p0.y);
@@ -367,9 +394,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
         // the previous P V must be done reading the P columns before they are overwritten
         if (j > 0) {
-          mbar_wait(&bars->o_full[g], (j - 1) & 1);
+          uint32_t ok;
+          asm volatile("selp.u32 %0, 1, 0, p_of;" : "=r"(ok));
+          if (!ok) mbar_wait(&bars->o_full[g], (j - 1) & 1);
           tcgen05_fence_after();
         }
+        if (j + 1 < n_tiles)   // probe the next score tile (its QK^T was issued when this tile's scores were read out)
+          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_sf, [%0], %1;" ::"r"(a_sfull), "r"((j + 1) & 1) : "memory");
         SVOL_TR(g, j, 6);
         // P half tile -> tensor memory: lane = query row, 32 columns of packed bf16 pairs (the A operand of P V)
         tmem_st_32x32b_x32(t_p, &s[0]);
@@ -377,6 +408,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_ready[g]);
+        s_ready = 0;
+        if (j + 1 < n_tiles) asm volatile("selp.u32 %0, 1, 0, p_sf;" : "=r"(s_ready));
         SVOL_TR(g, j, 7);
       }
 

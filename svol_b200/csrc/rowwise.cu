@@ -262,6 +262,7 @@ int launch_gate_vectors(const float* sketch, const float* w, const float* b, flo
 
 // scores[b,h,l] = (x+pos)[b,l,:] . u[b,h,:]; one warp per token, d = 256 (8 bf16 per lane), H = 8
 constexpr int GATE_D = 256, GATE_H = 8, GATE_ROWS = 64;
+constexpr int GATE_APPLY_ROWS = 128;   // rows per CTA of gate_apply: amortises the per-CTA softmax statistics pass
 
 __global__ void __launch_bounds__(256) gate_scores_kernel(const __nv_bfloat16* __restrict__ xpos,
                                                           const float* __restrict__ u, float* __restrict__ scores,
@@ -289,15 +290,29 @@ __global__ void __launch_bounds__(256) gate_scores_kernel(const __nv_bfloat16* _
       for (int i = 0; i < 8; ++i) a = fmaf(xv[i], ur[h][i], a);
       acc[h] = a;
     }
-    // 8 interleaved butterfly reductions (independent shuffles pipeline)
+    // reduce-scatter butterfly: 8 heads x 32 lanes -> one fully reduced head per lane in 4+2+1+1+1 = 9 shuffles
+    // (a plain butterfly per head needs 40): at offset 16 / 8 / 4 each lane hands the half of its values the partner
+    // keeps and keeps the other half; offsets 2 and 1 finish the one remaining value.
+    float a4[4], a2[2], a1;
+    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int i = 0; i < 4; ++i) {
+      const float send = b16 ? acc[i] : acc[i + 4], keep = b16 ? acc[i + 4] : acc[i];
+      a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
 #pragma unroll
-      for (int h = 0; h < GATE_H; ++h) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], o);
-    float mine = 0.f;
-#pragma unroll
-    for (int h = 0; h < GATE_H; ++h) if (lane == h) mine = acc[h];
-    if (lane < GATE_H) scores[(static_cast<size_t>(b) * GATE_H + lane) * L + l] = mine;
+    for (int i = 0; i < 2; ++i) {
+      const float send = b8 ? a4[i] : a4[i + 2], keep = b8 ? a4[i + 2] : a4[i];
+      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+      const float send = b4 ? a2[0] : a2[1], keep = b4 ? a2[1] : a2[0];
+      a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    const int head = (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0);      // every group of 4 lanes holds one head's score
+    if ((lane & 3) == 0) scores[(static_cast<size_t>(b) * GATE_H + head) * L + l] = a1;
   }
 }
 
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __
                                                          __nv_bfloat16* __restrict__ mem_pos, float* __restrict__ att_out,
                                                          int L, float eps) {
   __shared__ float smax[GATE_H], sinv[GATE_H];
-  const int b = blockIdx.y, l0 = blockIdx.x * GATE_ROWS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, l0 = blockIdx.x * GATE_APPLY_ROWS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   {
     // warp h: softmax statistics of head h over all L tokens of this sample (L2-resident re-read)
     const float* sr = scores + (static_cast<size_t>(b) * GATE_H + warp) * L;
@@ -341,7 +356,7 @@ __global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     idt[i] = 1.0f / powf(10000.f, __fdiv_rn(__fmul_rn(2.f, static_cast<float>(lane * 4 + i)), static_cast<float>(GATE_D)));
-  for (int r = warp; r < GATE_ROWS; r += 8) {
+  for (int r = warp; r < GATE_APPLY_ROWS; r += 8) {
     const int l = l0 + r;
     if (l >= L) break;
     const size_t row = static_cast<size_t>(b) * L + l;
@@ -393,7 +408,7 @@ int launch_gate_apply(const svol_bf16* x, const float* scores, const float* lw, 
                       svol_bf16* mem, svol_bf16* mem_pos, float* att_out, int B, int L, int d, int H, float eps,
                       bool pos_is_theta, cudaStream_t stream) {
   if (d != GATE_D || H != GATE_H || B <= 0 || L <= 0) return svol_fail(SVOL_ERR_SHAPE, "gate_apply: hidden_dim 256 / 8 heads only");
-  const dim3 grid((L + GATE_ROWS - 1) / GATE_ROWS, B);
+  const dim3 grid((L + GATE_APPLY_ROWS - 1) / GATE_APPLY_ROWS, B);
   if (pos_is_theta)
     gate_apply_kernel<true><<<grid, 256, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), scores, lw, lb, pos, reinterpret_cast<__nv_bfloat16*>(mem),

@@ -43,15 +43,34 @@ class _Plan:
     def __init__(self):
         self.calls: List[Tuple[str, object, tuple]] = []
         self.ln_in_index = 0
+        self.side_begin = self.side_end = self.join_index = 0
         self.keep: List[object] = []        # ctypes structs must outlive the plan
         self.buf: Dict[str, torch.Tensor] = {}
         self.graph = None
 
-    def run(self, stream: int, start: int = 0) -> None:
-        for name, fn, args in self.calls[start:]:
-            rc = fn(*args, stream)
-            if rc != 0:
-                _lib.check(rc, name)
+    def run(self, stream: int, start: int = 0, side=None) -> None:
+        """Launches calls[start:] in order.  With ``side`` (a torch stream) the calls in [side_begin, side_end) --
+        the sketch branch, the gate vectors of every layer and the query-embedding broadcast, which depend on the
+        inputs only -- are forked onto it and joined before the first call that consumes them, so these small
+        launch-latency-bound kernels overlap the input projection instead of preceding it."""
+        if side is None or self.side_end <= max(start, self.side_begin):
+            for name, fn, args in self.calls[start:]:
+                rc = fn(*args, stream)
+                if rc != 0:
+                    _lib.check(rc, name)
+            return
+        main = torch.cuda.current_stream()
+        assert main.cuda_stream == stream
+        for name, fn, args in self.calls[start:self.side_begin]:
+            _lib.check(fn(*args, stream), name)
+        side.wait_stream(main)
+        for name, fn, args in self.calls[self.side_begin:self.side_end]:
+            _lib.check(fn(*args, side.cuda_stream), name)
+        for name, fn, args in self.calls[self.side_end:self.join_index]:
+            _lib.check(fn(*args, stream), name)
+        main.wait_stream(side)
+        for name, fn, args in self.calls[self.join_index:]:
+            _lib.check(fn(*args, stream), name)
 
 
 class HeadEngine:
@@ -62,6 +81,7 @@ class HeadEngine:
         self._w: Dict[str, torch.Tensor] = {}
         self._wstate = None
         self._plans: Dict[Tuple[int, int, int], _Plan] = {}
+        self._side = None                  # second capture stream: fork/join branch of the forward graph
         self.launches_per_forward = 0
 
     # ------------------------------------------------------------------ weights
@@ -334,6 +354,16 @@ class HeadEngine:
         gemm("box1", h1, w["box.1.w"], w["box.1.b"], out=h2, act=ACT_RELU)
         call("heads", lib.svol_heads, P(hs_all), P(h2), P(w["cls.w"]), P(w["cls.b"]), P(w["box.2.w"]), P(w["box.2.b"]),
              P(logits), P(boxes), NL * MQ, d)
+        # order: [ln_in] [side: input-only small kernels] [pre: positions + input projection] [everything else]
+        is_side = lambda n: n.startswith("sk_proj") or n.endswith("gate_vec") or n == "qe_bcast"
+        first_consumer = next(i for i, c in enumerate(plan.calls) if c[0].endswith("gate_scores"))
+        head, rest = plan.calls[:1], plan.calls[1:]
+        side_calls = [c for c in rest if is_side(c[0])]
+        pre_calls = [c for c in plan.calls[1:first_consumer] if not is_side(c[0])]
+        post_calls = [c for c in plan.calls[first_consumer:] if not is_side(c[0])]
+        plan.calls = head + side_calls + pre_calls + post_calls
+        plan.side_begin, plan.side_end = 1, 1 + len(side_calls)
+        plan.join_index = plan.side_end + len(pre_calls)
         return plan
 
     # ------------------------------------------------------------------ run
@@ -383,9 +413,11 @@ class HeadEngine:
                 # warm-up run outside capture (sets function attributes, loads modules)
                 plan.run(torch.cuda.current_stream().cuda_stream, start=1)
                 torch.cuda.synchronize()
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    plan.run(torch.cuda.current_stream().cuda_stream, start=1)
+                    plan.run(torch.cuda.current_stream().cuda_stream, start=1, side=self._side)
                 plan.graph = g
             plan.graph.replay()
         else:
