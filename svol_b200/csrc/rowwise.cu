@@ -277,10 +277,20 @@ __global__ void __launch_bounds__(256) gate_scores_kernel(const __nv_bfloat16* _
     ur[h][0] = a.x; ur[h][1] = a.y; ur[h][2] = a.z; ur[h][3] = a.w;
     ur[h][4] = c.x; ur[h][5] = c.y; ur[h][6] = c.z; ur[h][7] = c.w;
   }
-  for (int r = warp; r < GATE_ROWS; r += 8) {
-    const int l = l0 + r;
+  // the loads of all of this warp's rows are issued up front (8 independent 16-byte loads per lane in flight):
+  // one row at a time the kernel was bound by the load -> reduce -> store latency chain, not by bandwidth
+  uint4 qrow[GATE_ROWS / 8];
+#pragma unroll
+  for (int i = 0; i < GATE_ROWS / 8; ++i) {
+    const int l = l0 + warp + i * 8;
+    qrow[i] = l < L ? __ldg(reinterpret_cast<const uint4*>(xpos + (static_cast<size_t>(b) * L + l) * GATE_D) + lane)
+                    : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int ri = 0; ri < GATE_ROWS / 8; ++ri) {
+    const int l = l0 + warp + ri * 8;
     if (l >= L) break;
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(xpos + (static_cast<size_t>(b) * L + l) * GATE_D) + lane);
+    const uint4 q = qrow[ri];
     const float xv[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
     float acc[GATE_H];
 #pragma unroll
@@ -356,18 +366,30 @@ __global__ void __launch_bounds__(256) gate_apply_kernel(const __nv_bfloat16* __
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     idt[i] = 1.0f / powf(10000.f, __fdiv_rn(__fmul_rn(2.f, static_cast<float>(lane * 4 + i)), static_cast<float>(GATE_D)));
+  // software pipeline: the next row's token and score loads are in flight while this row is normalised
+  auto load_row = [&](int l, uint4& q, float& sc) {
+    q = make_uint4(0u, 0u, 0u, 0u); sc = 0.f;
+    if (l < L) {
+      q = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * L + l) * GATE_D) + lane);
+      if (lane < GATE_H) sc = __ldg(scores + (static_cast<size_t>(b) * GATE_H + lane) * L + l);
+    }
+  };
+  uint4 q_next; float sc_next;
+  load_row(l0 + warp, q_next, sc_next);
   for (int r = warp; r < GATE_APPLY_ROWS; r += 8) {
     const int l = l0 + r;
     if (l >= L) break;
     const size_t row = static_cast<size_t>(b) * L + l;
+    const uint4 q = q_next;
+    const float sc = sc_next;
+    load_row(l + 8 < l0 + GATE_APPLY_ROWS ? l + 8 : L, q_next, sc_next);
     float a = 0.f;
-    if (lane < GATE_H) a = expf(scores[(static_cast<size_t>(b) * GATE_H + lane) * L + l] - smax[lane]) * sinv[lane];
+    if (lane < GATE_H) a = expf(sc - smax[lane]) * sinv[lane];
     a += __shfl_xor_sync(0xffffffffu, a, 4);
     a += __shfl_xor_sync(0xffffffffu, a, 2);
     a += __shfl_xor_sync(0xffffffffu, a, 1);
     const float att = __shfl_sync(0xffffffffu, a, 0) * (1.0f / GATE_H);
     if (att_out && lane == 0) att_out[row] = att;
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + row * GATE_D) + lane);
     float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
     float s = 0.f;
 #pragma unroll
