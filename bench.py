@@ -201,6 +201,9 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly one JSON line: library banners (NCCL prints its version to stdout) go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -213,6 +216,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_bound = comm.bind_to_gpu_numa_node(local)          # pinned staging buffers land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -347,10 +351,12 @@ def main():
             "clocks": clocks,
             "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e},
-            "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches": int(launches_per_step * args.steps), "host_numa_bound": bool(numa_bound),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "tflops_algorithmic": synth.algorithmic_flops_per_pair(cfg) * pairs / (ms_step * 1e-3) / 1e12}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
 
 
 def kernel_breakdown(model, inset, cfg, B, dev):
