@@ -75,7 +75,10 @@ __device__ __forceinline__ int warp_max_i(int v) {
 // One warp per problem.  Dynamic shared memory per warp (n_small = min(rows, cols), n_big = max):
 //   double u[n_small], v[n_big], spc[n_big]; int path[n_big], col4row[n_small], row4col[n_big],
 //   remaining[n_big]; uint8 SR[n_small], SC[n_big]
-__global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_small, int max_big) {
+// When a problem's cost block fits (cost_smem_floats > 0) it is also kept in shared memory: the solver re-reads
+// costs once per scanned column per path step, and from the global workspace every such read was an exposed L2
+// round trip (C5 stress: 482 us -> see profiles; the default 10 x n_f problems are launch-latency bound either way).
+__global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_small, int max_big, int cost_smem_floats) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
   const int lane = threadIdx.x;
   const int P = a.B * a.problems_per_video;
@@ -94,6 +97,9 @@ __global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_sm
   int* remaining = row4col + max_big;
   uint8_t* SR = reinterpret_cast<uint8_t*>(remaining + max_big);
   uint8_t* SC = SR + max_small;
+  float* Cs = reinterpret_cast<float*>(sm_raw + ((sizeof(double) * (max_small + 2 * max_big) + sizeof(int) * (3 * max_big + max_small) +
+                                                   (max_small + max_big) + 15) & ~static_cast<size_t>(15)));
+  const bool cost_in_smem = nrows * ncols <= cost_smem_floats;
 
   // ---- cost block, row-major nrows x ncols, in this layer's slab of the workspace
   const size_t q0 = (static_cast<size_t>(layer) * a.B + video) * a.Q + static_cast<size_t>(local) * nrows;
@@ -108,6 +114,7 @@ __global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_sm
     const float cost = pair_cost(fg_prob(lg.x, lg.y), pa, ta, a.w_class, a.w_bbox, a.w_giou);
     bad |= (cost != cost) || (cost == -CUDART_INF_F);
     C[e] = cost;
+    if (cost_in_smem) Cs[e] = cost;
   }
   if (__any_sync(0xffffffffu, bad)) {      // scipy: "matrix contains invalid numeric entries"
     if (lane == 0) atomicOr(a.status, 1);
@@ -119,8 +126,9 @@ __global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_sm
   const bool transposed = ncols < nrows;
   const int nr = transposed ? ncols : nrows;      // rows of the working problem
   const int nc = transposed ? nrows : ncols;
+  const float* Cr = cost_in_smem ? Cs : C;
   auto cost_at = [&](int i, int j) -> double {
-    return static_cast<double>(transposed ? C[j * ncols + i] : C[i * ncols + j]);
+    return static_cast<double>(transposed ? Cr[j * ncols + i] : Cr[i * ncols + j]);
   };
   for (int i = lane; i < nr; i += 32) { u[i] = 0.0; col4row[i] = -1; }
   for (int j = lane; j < nc; j += 32) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
@@ -219,8 +227,12 @@ int launch_match(const MatchArgs& a, cudaStream_t stream) {
   const int max_small = a.rows_per_problem < a.max_cols ? a.rows_per_problem : a.max_cols;
   const int max_big = a.rows_per_problem > a.max_cols ? a.rows_per_problem : a.max_cols;
   const int ms = (max_small + 1) & ~1, mb = (max_big + 1) & ~1;     // keep the int arrays 8-byte aligned
-  const size_t smem = sizeof(double) * (ms + 2 * mb) + sizeof(int) * (3 * mb + ms) + (ms + mb);
-  if (smem > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "match: problem too large for one warp's shared memory");
+  const size_t smem_solver = (sizeof(double) * (ms + 2 * mb) + sizeof(int) * (3 * mb + ms) + (ms + mb) + 15) & ~static_cast<size_t>(15);
+  if (smem_solver > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "match: problem too large for one warp's shared memory");
+  // cost block in shared memory when it fits in ~64 KB per warp (keeps >= 3 problems resident per SM)
+  const size_t cost_bytes = static_cast<size_t>(a.rows_per_problem) * static_cast<size_t>(a.max_cols) * sizeof(float);
+  const int cost_smem_floats = cost_bytes <= 64 * 1024 ? a.rows_per_problem * a.max_cols : 0;
+  const size_t smem = smem_solver + static_cast<size_t>(cost_smem_floats) * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -228,7 +240,7 @@ int launch_match(const MatchArgs& a, cudaStream_t stream) {
     configured = smem;
   }
   const int P = a.B * a.problems_per_video;
-  match_kernel<<<a.NL * P, 32, smem, stream>>>(a, ms, mb);
+  match_kernel<<<a.NL * P, 32, smem, stream>>>(a, ms, mb, cost_smem_floats);
   return svol_check_launch("match");
 }
 

@@ -14,6 +14,8 @@ which = sys.argv[1] if len(sys.argv) > 1 else "attn_self"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda:0")
 B, L, Q, H, d, ff = 32, 1568, 320, 8, 256, 2048
+if os.environ.get("SVOL_CONFIG") == "C4":      # long clip: T=128 -> L=6272, Q=1280
+    B, L, Q = 8, 6272, 1280
 g = torch.Generator(device="cpu").manual_seed(0)
 rnd = lambda *s: torch.randn(*s, generator=g)
 
