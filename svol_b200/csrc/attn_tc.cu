@@ -51,7 +51,9 @@ constexpr int VT_BYTES = 2 * VT_KB_BYTES;       // 8192
 constexpr int CMB_STRIDE = 35;                  // floats per row of the merge buffer: m, l, O[32] (+1: odd stride, no bank conflicts)
 constexpr int CMB_BYTES = 2 * BQ * CMB_STRIDE * 4;
 constexpr int OFF_K = 2 * Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES, OFF_CMB = OFF_VT + STAGES * VT_BYTES;
-constexpr int OFF_BAR = OFF_CMB + CMB_BYTES;
+constexpr int KMASK_WORDS = 256;                // key-padding bitmask of one sample: up to 8192 keys
+constexpr int OFF_KMASK = OFF_CMB + CMB_BYTES;
+constexpr int OFF_BAR = OFF_KMASK + KMASK_WORDS * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr int THREADS = 640;   // 5 warpgroups: 4 x softmax, {TMA, MMA 0, MMA 1, idle}
 constexpr uint32_t TMEM_COLS = 512, TMEM_P = 256, TMEM_O = 384;
@@ -287,6 +289,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int g = warp >> 2;                            // softmax warpgroup
     const int t = g >> 1, half = g & 1;                 // query tile, key half
+    // key_padding_mask of this sample as a bitmask in shared memory (built once, under the TMA / first-QK^T latency):
+    // reading the float mask inside the key loop put an L2 round trip on every tile's critical path
+    uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + OFF_KMASK);
+    const bool mask_in_smem = key_mask != nullptr && (Lk + 31) / 32 <= KMASK_WORDS;
+    if (mask_in_smem) {
+      const float* mr = key_mask + static_cast<size_t>(b) * Lk;
+      for (int w = warp; w < (Lk + 31) / 32; w += 16) {
+        const int kv = w * 32 + lane;
+        const uint32_t m = __ballot_sync(0xffffffffu, kv < Lk && __ldg(mr + kv) != 0.f);
+        if (lane == 0) kmask[w] = m;
+      }
+      asm volatile("bar.sync 3, 512;" ::: "memory");     // all 16 softmax warps
+    }
     if (t < n_q) {
       // ------------------------------------------------------------------ softmax warpgroups
       const int quarter = warp & 3;                       // TMEM lane quarter == warp % 4
@@ -333,7 +348,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         float mx;
         bool masked = false;
         uint32_t words[2];
-        if (mrow != nullptr || kv0 + HALF > Lk) {
+        if (mask_in_smem) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int w = (kv0 >> 5) + c;
+            words[c] = w * 32 < Lk ? kmask[w] : 0u;
+            masked |= words[c] != 0xffffffffu;
+          }
+        } else if (mrow != nullptr || kv0 + HALF > Lk) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const int kv = kv0 + c * 32 + lane;
