@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 2
+#define SVOL_ABI_VERSION 3
 
 enum {
   SVOL_OK = 0,
@@ -83,8 +83,14 @@ typedef struct svol_gemm_args {
   const svol_bf16* A;  /* [M, lda] */
   const svol_bf16* W;  /* [N, ldw] */
   int32_t M, N, K, lda, ldw;
-  int32_t reserved;
+  int32_t split_block; /* 0, or (K == 256 only) the first 256-column block that takes its A operand from A2 and writes
+                          the per-head transposed output out_vt (columns relative to the split); the blocks before it
+                          use A and write out / out_pos [M, split_block * 256].  One launch then computes e.g. the
+                          q/k projection of x + pos and the v projection of x (cross_modal_transformer.py:137-139). */
   svol_gemm_epilogue ep;
+  const svol_bf16* A2; /* [M, lda2] or NULL */
+  int32_t lda2;
+  int32_t reserved;
 } svol_gemm_args;
 
 int svol_gemm_bf16(const svol_gemm_args* args, void* stream);

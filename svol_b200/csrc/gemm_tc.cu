@@ -139,7 +139,7 @@ template <bool kResidentW>
 __global__ void __launch_bounds__(gemm::THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutPos,
-                    const GemmEpilogue ep, int M, int N, int K) {
+                    const __grid_constant__ CUtensorMap tmA2, const GemmEpilogue ep, int M, int N, int K, int split_block) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
   extern __shared__ uint8_t smem_raw[];
@@ -168,6 +168,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                   : (num_tiles > static_cast<int>(blockIdx.x)
                                          ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
                                          : 0);
+  // split launch (resident variant): column blocks >= split_block read A2 and write the transposed output
+  const bool second_part = kResidentW && split_block > 0 && my_n >= split_block;
+  const bool do_out = !second_part;                                  // out / out_pos columns belong to the first part
+  const bool do_vt = ep.out_vt != nullptr && (split_block == 0 || second_part);
+  const int vt_col_shift = second_part ? split_block * BN : 0;
   auto tile_coords = [&](int it, int& m_blk, int& n_blk) {
     if (kResidentW) { m_blk = m_first + it * m_stride; n_blk = my_n; }
     else { const int tile = blockIdx.x + it * gridDim.x; m_blk = tile / n_blocks; n_blk = tile % n_blocks; }
@@ -218,7 +223,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&tail->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&tail->full[stage], C::STAGE_BYTES);
           uint8_t* sa = stages + stage * C::STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &tail->full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sa, second_part ? &tmA2 : &tmA, &tail->full[stage], kb * BK, m_blk * BM);
           if (!kResidentW) tma_load_2d(sa + A_BYTES, &tmB, &tail->full[stage], kb * BK, n_blk * BN);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -366,7 +371,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       SVOL_GTR(0, it, 5);
-      if (ep.out) {
+      if (ep.out && do_out) {
 #pragma unroll
         for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
           uint4 q[8];
@@ -379,7 +384,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       SVOL_GTR(0, it, 6);
-      if (ep.out_pos) {
+      if (ep.out_pos && do_out) {
         // second output: x + pos (the q/k operand of the next attention block).  pos rows follow the output
         // rows (pos_row_mod == 0) or repeat with period pos_row_mod (query embedding broadcast over the batch);
         // the broadcast case is read directly (its 320 x 256 table stays in L1/L2).
@@ -424,12 +429,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           block_store_tma(stg, q, &tmOutPos, col0 + blk * 64, slab_row0, lane);
         }
       }
-      if (row_ok && ep.out_vt) {
+      if (row_ok && do_vt) {
         // per-head transposed store: Vt[(b*H + h)*dh + d][l], row = b*L + l, col = h*dh + d.
         // Consecutive lanes hold consecutive tokens l, so each store instruction writes 64
         // contiguous bytes per output row.
         const int b = row / ep.vt_len, l = row - b * ep.vt_len;
-        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ep.out_vt) + (static_cast<size_t>(b) * N + col0) * ep.vt_pitch + l;
+        const int n_vt = N - vt_col_shift;                       // columns of the transposed output
+        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ep.out_vt) +
+                              (static_cast<size_t>(b) * n_vt + (col0 - vt_col_shift)) * ep.vt_pitch + l;
 #pragma unroll
         for (int i = 0; i < COLS_PER_THREAD; ++i) base[static_cast<size_t>(i) * ep.vt_pitch] = __float2bfloat16_rn(v[i]);
       }
@@ -452,7 +459,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 template <bool kResidentW>
 static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                          const CUtensorMap& tmOutPos, cudaStream_t stream) {
+                          const CUtensorMap& tmOutPos, const CUtensorMap& tmA2, cudaStream_t stream) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
   static bool configured = false;
@@ -465,7 +472,8 @@ static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUten
   const int tiles = m_blocks * n_blocks;
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (kResidentW) grid = grid / n_blocks * n_blocks;       // every CTA owns one n block
-  gemm_bf16_tc_kernel<kResidentW><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, a.ep, a.M, a.N, a.K);
+  gemm_bf16_tc_kernel<kResidentW><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, tmA2, a.ep, a.M, a.N, a.K,
+                                                                            a.split_block);
   return svol_check_launch("gemm_bf16_tc");
 }
 
@@ -473,7 +481,10 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   using namespace gemm;
   if (a.N % BN != 0 || a.K % BK != 0 || a.M <= 0) return svol_fail(SVOL_ERR_SHAPE, "gemm: need N % 256 == 0, K % 64 == 0, M > 0");
   if (a.ep.ln_weight && a.N != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: fused LayerNorm needs N == 256");
-  if (a.ep.out_vt && a.N != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: transposed-V store needs N == 256");
+  const int split = a.split_block;
+  if (split != 0 && (split < 0 || split >= a.N / BN || a.K != RES_K || !a.A2 || !a.ep.out_vt || a.ep.ln_weight))
+    return svol_fail(SVOL_ERR_SHAPE, "gemm: split launch needs K == 256, 0 < split_block < N/256, A2 and out_vt, no LayerNorm");
+  if (a.ep.out_vt && (a.N - split * BN) != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: transposed-V store needs 256 columns");
   if (a.ep.pos_theta && a.N != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: in-epilogue sine positions need N == 256");
   if (a.ep.out_pos && !a.ep.pos && !a.ep.pos_theta) return svol_fail(SVOL_ERR_NULL, "gemm: out_pos needs pos or pos_theta");
   CUtensorMap tmA, tmB;
@@ -483,17 +494,24 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   // outputs are written by TMA stores of [32 rows x 64 columns] boxes (rows beyond M clipped by the map)
   CUtensorMap tmOut = tmA, tmOutPos = tmA;
+  const int n_out = split > 0 ? split * BN : a.N;          // columns of out / out_pos
+  CUtensorMap tmA2 = tmA;
   if (a.ep.out) {
-    rc = make_tensor_map_2d(&tmOut, a.ep.out, a.N, a.M, a.ep.ld_out, 64, 32, 128);
+    rc = make_tensor_map_2d(&tmOut, a.ep.out, n_out, a.M, a.ep.ld_out, 64, 32, 128);
     if (rc) return rc;
   }
   if (a.ep.out_pos) {
-    rc = make_tensor_map_2d(&tmOutPos, a.ep.out_pos, a.N, a.M, a.ep.ld_out, 64, 32, 128);
+    rc = make_tensor_map_2d(&tmOutPos, a.ep.out_pos, n_out, a.M, a.ep.ld_out, 64, 32, 128);
+    if (rc) return rc;
+  }
+  if (split > 0) {
+    rc = make_tensor_map_2d(&tmA2, a.A2, a.K, a.M, a.lda2, BK, BM, 128);
     if (rc) return rc;
   }
   const bool resident = a.K == RES_K && a.N / BN <= sm_count();
-  return resident ? launch_variant<true>(a, tmA, tmB, tmOut, tmOutPos, stream)
-                  : launch_variant<false>(a, tmA, tmB, tmOut, tmOutPos, stream);
+  if (split > 0 && !resident) return svol_fail(SVOL_ERR_SHAPE, "gemm: split launch needs the resident-weight variant");
+  return resident ? launch_variant<true>(a, tmA, tmB, tmOut, tmOutPos, tmA2, stream)
+                  : launch_variant<false>(a, tmA, tmB, tmOut, tmOutPos, tmA2, stream);
 }
 
 }  // namespace svol

@@ -130,6 +130,9 @@ class HeadEngine:
                 put(p + tag + ".bv", b[2 * d:], f32)
                 put(p + tag + ".wo", att.out_proj.weight, bf)
                 put(p + tag + ".bo", att.out_proj.bias, f32)
+                # one launch computes q | k from x + pos and v from x (split GEMM): [q * scale ; k ; v]
+                put(p + tag + ".wqkv", torch.cat([W[:d] * qscale, W[d:]]), bf)
+                put(p + tag + ".bqkv", torch.cat([b[:d] * qscale, b[d:]]), f32)
             ca = layer.content_token_cross_attn
             W, b = ca.in_proj_weight, ca.in_proj_bias
             put(p + "ca.wq", W[:d] * qscale, bf)
@@ -140,6 +143,8 @@ class HeadEngine:
             put(p + "ca.bv", b[2 * d:], f32)
             put(p + "ca.wo", ca.out_proj.weight, bf)
             put(p + "ca.bo", ca.out_proj.bias, f32)
+            put(p + "ca.wkv", W[d:], bf)                 # k from mem + pos, v from mem: one split launch
+            put(p + "ca.bkv", b[d:], f32)
             for n in range(1, 7):
                 norm = getattr(layer, f"norm{n}")
                 put(p + f"n{n}.w", norm.weight, f32)
@@ -225,7 +230,7 @@ class HeadEngine:
         attn_fn = lib.svol_attention_bf16_plain if self.plain else lib.svol_attention_bf16
 
         def gemm(name, A, W, bias, out=None, act=ACT_NONE, residual=None, ln=None, out_pos=None, pos_t=None,
-                 pos_mod=0, out_vt=None, vt_len=0, vt_pitch=0, theta_t=None):
+                 pos_mod=0, out_vt=None, vt_len=0, vt_pitch=0, theta_t=None, A2=None, split=0):
             a = GemmArgs()
             a.A, a.W = P(A), P(W)
             a.M, a.K = A.shape
@@ -247,6 +252,8 @@ class HeadEngine:
                 e.pos, e.ld_pos, e.pos_row_mod = P(pos_t), pos_t.stride(0), pos_mod
             if out_vt is not None:
                 e.out_vt, e.vt_len, e.vt_pitch = P(out_vt), vt_len, vt_pitch
+            if A2 is not None:
+                a.A2, a.lda2, a.split_block = P(A2), A2.stride(0), split
             plan.keep.append(a)
             plan.calls.append((name, gemm_fn, (C.byref(a),)))
 
@@ -314,8 +321,12 @@ class HeadEngine:
                 call(p + "gate_apply", lib.svol_gate_apply_theta, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]),
                      P(theta), P(mem), P(memp), None, B, L, d, H, LN_EPS)
             # (b) video self-attention + norm2, FFN + norm3                               :137-143
-            gemm(p + "sa_qk", memp, w[p + "sa.wqk"], w[p + "sa.bqk"], out=qk)
-            gemm(p + "sa_v", mem, w[p + "sa.wv"], w[p + "sa.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)
+            if self.plain:
+                gemm(p + "sa_qk", memp, w[p + "sa.wqk"], w[p + "sa.bqk"], out=qk)
+                gemm(p + "sa_v", mem, w[p + "sa.wv"], w[p + "sa.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)
+            else:
+                gemm(p + "sa_qkv", memp, w[p + "sa.wqkv"], w[p + "sa.bqkv"], out=qk, out_vt=vt, vt_len=L, vt_pitch=Lp,
+                     A2=mem, split=2)
             attention(p + "sa_attn", qk, qk[:, d:], vt, att, L, L, 2 * d, 2 * d, Lp)
             gemm(p + "sa_out", att, w[p + "sa.wo"], w[p + "sa.bo"], out=mem2, residual=mem, ln=(w[p + "n2.w"], w[p + "n2.b"]))
             if self.plain:
@@ -328,15 +339,22 @@ class HeadEngine:
                     (w[p + "n3.w"], w[p + "n3.b"]), out=X, out_pos=Xp, theta_t=theta)
             x_cur, xp_cur = X, Xp            # layer output mem (and mem + pos)
             # (c) query self-attention + norm4                                            :145-149
-            gemm(p + "ta_qk", outp_cur, w[p + "ta.wqk"], w[p + "ta.bqk"], out=qkq)
-            gemm(p + "ta_v", out_cur, w[p + "ta.wv"], w[p + "ta.bv"], out_vt=vtq, vt_len=Q, vt_pitch=Qp)
+            if self.plain:
+                gemm(p + "ta_qk", outp_cur, w[p + "ta.wqk"], w[p + "ta.bqk"], out=qkq)
+                gemm(p + "ta_v", out_cur, w[p + "ta.wv"], w[p + "ta.bv"], out_vt=vtq, vt_len=Q, vt_pitch=Qp)
+            else:
+                gemm(p + "ta_qkv", outp_cur, w[p + "ta.wqkv"], w[p + "ta.bqkv"], out=qkq, out_vt=vtq, vt_len=Q, vt_pitch=Qp,
+                     A2=out_cur, split=2)
             attention(p + "ta_attn", qkq, qkq[:, d:], vtq, attq, Q, Q, 2 * d, 2 * d, Qp)
             gemm(p + "ta_out", attq, w[p + "ta.wo"], w[p + "ta.bo"], out=o1, residual=out_cur,
                  ln=(w[p + "n4.w"], w[p + "n4.b"]), out_pos=o1p, pos_t=w["query_embed"], pos_mod=Q)
             # (d) query -> video cross-attention (padded keys masked) + norm5, FFN + norm6 :151-158
             gemm(p + "ca_q", o1p, w[p + "ca.wq"], w[p + "ca.bq"], out=qc)
-            gemm(p + "ca_k", Xp, w[p + "ca.wk"], w[p + "ca.bk"], out=kc)
-            gemm(p + "ca_v", X, w[p + "ca.wv"], w[p + "ca.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)
+            if self.plain:
+                gemm(p + "ca_k", Xp, w[p + "ca.wk"], w[p + "ca.bk"], out=kc)
+                gemm(p + "ca_v", X, w[p + "ca.wv"], w[p + "ca.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)
+            else:
+                gemm(p + "ca_kv", Xp, w[p + "ca.wkv"], w[p + "ca.bkv"], out=kc, out_vt=vt, vt_len=L, vt_pitch=Lp, A2=X, split=1)
             attention(p + "ca_attn", qc, kc, vt, attq, Q, L, d, d, Lp, mask=vmask)
             gemm(p + "ca_out", attq, w[p + "ca.wo"], w[p + "ca.bo"], out=o2, residual=o1, ln=(w[p + "n5.w"], w[p + "n5.b"]))
             if self.plain:

@@ -17,7 +17,8 @@ _P = _lib.ptr
 def gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
          residual: Optional[torch.Tensor] = None, ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
          pos: Optional[torch.Tensor] = None, pos_mod: int = 0, want_out: bool = True, vt_len: int = 0,
-         plain: bool = False, eps: float = 1e-5, pos_theta: Optional[torch.Tensor] = None):
+         plain: bool = False, eps: float = 1e-5, pos_theta: Optional[torch.Tensor] = None,
+         A2: Optional[torch.Tensor] = None, split_block: int = 0):
     """out = epilogue(A @ W.T).  A [M,K] bf16, W [N,K] bf16.  Returns a dict with 'out' [M,N] bf16,
     'out_pos' (when ``pos`` is given) and 'out_vt' [(M/vt_len)*N, round_up(vt_len,8)] (when ``vt_len``)."""
     _lib.require_device()
@@ -33,9 +34,12 @@ def gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         e.residual, e.ld_res = _P(residual), residual.stride(0)
     if ln is not None:
         e.ln_weight, e.ln_bias, e.ln_eps = _P(ln[0]), _P(ln[1]), eps
-    e.ld_out = N
+    n_out = split_block * 256 if split_block else N       # split launch: out covers the blocks before the split
+    if A2 is not None:
+        a.A2, a.lda2, a.split_block = _P(A2), A2.stride(0), split_block
+    e.ld_out = n_out
     if want_out:
-        res["out"] = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
+        res["out"] = torch.empty((M, n_out), device=A.device, dtype=torch.bfloat16)
         e.out = _P(res["out"])
     if pos is not None:
         res["out_pos"] = torch.empty((M, N), device=A.device, dtype=torch.bfloat16)
@@ -45,7 +49,8 @@ def gemm(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         e.out_pos, e.pos_theta = _P(res["out_pos"]), _P(pos_theta)
     if vt_len:
         pitch = (vt_len + 7) // 8 * 8
-        res["out_vt"] = torch.zeros(((M // vt_len) * N, pitch), device=A.device, dtype=torch.bfloat16)
+        res["out_vt"] = torch.zeros(((M // vt_len) * (N - (n_out if split_block else 0)), pitch), device=A.device,
+                                    dtype=torch.bfloat16)
         e.out_vt, e.vt_len, e.vt_pitch = _P(res["out_vt"]), vt_len, pitch
     fn = lib.svol_gemm_bf16_plain if plain else lib.svol_gemm_bf16
     _lib.check(fn(C.byref(a), _lib.stream_ptr()), "gemm")

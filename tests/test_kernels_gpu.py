@@ -105,6 +105,29 @@ def test_gemm_epilogues(M, N, K, flags, plain):
         assert (vt[:, :, vt_len:] == 0).all()
 
 
+def test_gemm_split_launch_qk_and_v():
+    """One launch: columns [0,512) = (x + pos) Wqk^T written row-major, columns [512,768) = x Wv^T written per-head
+    transposed (the q/k and v projections of cross_modal_transformer.py:137-139 share a kernel)."""
+    from svol_b200 import ops
+    rng = np.random.RandomState(11)
+    B, Lt, K = 2, 196, 256
+    M = B * Lt
+    x = _bf16(rng.standard_normal((M, K)).astype(np.float32))
+    xp = _bf16(rng.standard_normal((M, K)).astype(np.float32))
+    W = _bf16((rng.standard_normal((768, K)) / 16).astype(np.float32))
+    bias = torch.from_numpy(rng.standard_normal(768).astype(np.float32))
+    d = _dev()
+    out = ops.gemm(xp.to(d), W.to(d), bias.to(d), vt_len=Lt, A2=x.to(d), split_block=2)
+    torch.cuda.synchronize()
+    ref_qk = xp.float().numpy() @ W.float().numpy()[:512].T + bias.numpy()[:512]
+    ref_v = x.float().numpy() @ W.float().numpy()[512:].T + bias.numpy()[512:]
+    assert out["out"].shape == (M, 512)
+    _assert_close(_f(out["out"]), ref_qk, what="qk")
+    vt = _f(out["out_vt"]).reshape(B, 256, -1)
+    _assert_close(vt[:, :, :Lt], ref_v.reshape(B, Lt, 256).transpose(0, 2, 1), what="vt")
+    assert (vt[:, :, Lt:] == 0).all()
+
+
 # ------------------------------------------------------------------------------------------ attention
 ATTN_CASES = [
     # B, Lq, Lk, masked
