@@ -38,22 +38,30 @@ def _round_up(x: int, m: int) -> int:
 
 
 class _Plan:
-    """A recorded list of C-ABI calls plus the buffers they touch."""
+    """A recorded list of C-ABI calls plus the buffers they touch.
+
+    ``calls`` is a valid sequential order.  Every call also carries a branch tag -- 'v' (frame-token chain, the
+    launching stream), 'q' (object-query chain) or 'in' (kernels that depend on the inputs only: sketch branch, gate
+    vectors) -- and the names of the calls on OTHER branches it must wait for.  Replayed as a CUDA graph the three
+    branches run concurrently: in a decoder layer the query self-attention block (cross_modal_transformer.py:145-149)
+    does not depend on that layer's frame-token block (:122-143), only the cross-attention (:151-156) joins them, so
+    the small, launch-latency-bound query kernels (80 CTAs on 148 SMs) fill the tails of the large frame-token
+    kernels instead of extending the critical path."""
 
     def __init__(self):
         self.calls: List[Tuple[str, object, tuple]] = []
+        self.branch: Dict[str, str] = {}
+        self.after: Dict[str, List[str]] = {}
         self.ln_in_index = 0
-        self.side_begin = self.side_end = self.join_index = 0
         self.keep: List[object] = []        # ctypes structs must outlive the plan
         self.buf: Dict[str, torch.Tensor] = {}
         self.graph = None
 
     def run(self, stream: int, start: int = 0, side=None) -> None:
-        """Launches calls[start:] in order.  With ``side`` (a torch stream) the calls in [side_begin, side_end) --
-        the sketch branch, the gate vectors of every layer and the query-embedding broadcast, which depend on the
-        inputs only -- are forked onto it and joined before the first call that consumes them, so these small
-        launch-latency-bound kernels overlap the input projection instead of preceding it."""
-        if side is None or self.side_end <= max(start, self.side_begin):
+        """Launches calls[start:].  ``side`` = None: sequentially on ``stream``.  ``side`` = (query stream, input
+        stream): each call on its branch's stream with event edges for the cross-branch dependencies (fork at the
+        start, join at the end) -- used under CUDA-graph capture."""
+        if side is None:
             for name, fn, args in self.calls[start:]:
                 rc = fn(*args, stream)
                 if rc != 0:
@@ -61,16 +69,26 @@ class _Plan:
             return
         main = torch.cuda.current_stream()
         assert main.cuda_stream == stream
-        for name, fn, args in self.calls[start:self.side_begin]:
-            _lib.check(fn(*args, stream), name)
-        side.wait_stream(main)
-        for name, fn, args in self.calls[self.side_begin:self.side_end]:
-            _lib.check(fn(*args, side.cuda_stream), name)
-        for name, fn, args in self.calls[self.side_end:self.join_index]:
-            _lib.check(fn(*args, stream), name)
-        main.wait_stream(side)
-        for name, fn, args in self.calls[self.join_index:]:
-            _lib.check(fn(*args, stream), name)
+        streams = {"v": main, "q": side[0], "in": side[1]}
+        for st in side:
+            st.wait_stream(main)                                   # fork
+        launched = {name for name, _, _ in self.calls[:start]}
+        needed = {dep for deps in self.after.values() for dep in deps}
+        events: Dict[str, torch.cuda.Event] = {}
+        for name, fn, args in self.calls[start:]:
+            st = streams[self.branch.get(name, "v")]
+            for dep in self.after.get(name, ()):
+                if dep in launched and dep not in events:
+                    continue                                       # ran before the fork: already ordered
+                if self.branch.get(dep, "v") != self.branch.get(name, "v"):
+                    st.wait_event(events[dep])
+            _lib.check(fn(*args, st.cuda_stream), name)
+            if name in needed:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                events[name] = ev
+        for st in side:
+            main.wait_stream(st)                                   # join
 
 
 class HeadEngine:
@@ -81,7 +99,7 @@ class HeadEngine:
         self._w: Dict[str, torch.Tensor] = {}
         self._wstate = None
         self._plans: Dict[Tuple[int, int, int], _Plan] = {}
-        self._side = None                  # second capture stream: fork/join branch of the forward graph
+        self._side = None                  # (query, input) capture streams: the forked branches of the forward graph
         self.launches_per_forward = 0
 
     # ------------------------------------------------------------------ weights
@@ -206,9 +224,12 @@ class HeadEngine:
         mem2 = buf("mem2", (M, d), bf)
         qk = buf("qk", (M, 2 * d), bf)
         vt = buf("vt", (B * d, Lp), bf, zero=True)
+        # cross-attention K / V^T and the gate vectors are per layer: the frame-token branch of layer i+1 may be
+        # producing them while the query branch is still consuming layer i's
+        vt_ca = [buf(f"vt_ca{li}", (B * d, Lp), bf, zero=True) for li in range(NL)]
         att = buf("att", (M, d), bf)
         sk_a, sk_b = buf("sk_a", (B, d), f32), buf("sk_b", (B, d), f32)
-        u = buf("u", (B, H, d), f32)
+        u = [buf(f"u{li}", (B, H, d), f32) for li in range(NL)]
         scores = buf("scores", (B, H, L), f32)
         zeros_q = buf("zeros_q", (MQ, d), bf, zero=True)
         qe_bf = buf("qe_bf", (MQ, d), bf)
@@ -219,7 +240,7 @@ class HeadEngine:
         vtq = buf("vtq", (B * d, Qp), bf, zero=True)
         attq = buf("attq", (MQ, d), bf)
         qc = buf("qc", (MQ, d), bf)
-        kc = buf("kc", (M, d), bf)
+        kc = [buf(f"kc{li}", (M, d), bf) for li in range(NL)]
         hs = buf("hs", (NL, MQ, d), bf)
         h1, h2 = buf("h1", (NL * MQ, d), bf), buf("h2", (NL * MQ, d), bf)
         logits = buf("logits", (NL, B, Q, 2), f32)
@@ -279,6 +300,13 @@ class HeadEngine:
         def call(name, fn, *args):
             plan.calls.append((name, fn, args))
 
+        def tag(branch, after=()):
+            """Branch / cross-branch dependencies of the most recently added call."""
+            name = plan.calls[-1][0]
+            plan.branch[name] = branch
+            if after:
+                plan.after[name] = list(after)
+
         # ---- input projection of the frame tokens (svanet.py:49-55,83): LN -> Linear -> ReLU -> LN -> Linear
         plan.ln_in_index = len(plan.calls)
         call("ln_in", lib.svol_layernorm_f32_to_bf16, P(x_in), P(w["in_video.0.ln_w"]), P(w["in_video.0.ln_b"]), P(xn),
@@ -304,16 +332,20 @@ class HeadEngine:
             call(f"sk_proj{i}", lib.svol_ln_linear_f32, P(s_cur), P(w[f"in_sketch.{i}.ln_w"]), P(w[f"in_sketch.{i}.ln_b"]),
                  P(w[f"in_sketch.{i}.w"]), P(w[f"in_sketch.{i}.b"]), 0 if i == n_proj - 1 else 1, P(s_dst), B, dim_in, d,
                  LN_EPS)
+            tag("in")
             s_cur = s_dst
         # ---- query side: out0 = 0, q/k operand = query_embed broadcast (cross_modal_transformer.py:52-56)
         call("qe_bcast", lib.svol_add_pos_bf16, P(w["query_embed"]), None, P(qe_bf), MQ, d, Q)
+        tag("q")
         out_cur, outp_cur = zeros_q, qe_bf
         x_cur, xp_cur = X, Xp
         for li in range(NL):
             p = f"l{li}."
             # (a) sketch-conditioned gate + norm1                                        :122-127
-            call(p + "gate_vec", lib.svol_gate_vectors, P(s_cur), P(w[p + "gate.w"]), P(w[p + "gate.b"]), P(u), B, d, H)
-            call(p + "gate_scores", lib.svol_gate_scores, P(xp_cur), P(u), P(scores), B, L, d, H)
+            call(p + "gate_vec", lib.svol_gate_vectors, P(s_cur), P(w[p + "gate.w"]), P(w[p + "gate.b"]), P(u[li]), B, d, H)
+            tag("in")
+            call(p + "gate_scores", lib.svol_gate_scores, P(xp_cur), P(u[li]), P(scores), B, L, d, H)
+            tag("v", after=[p + "gate_vec"])
             if self.plain:
                 call(p + "gate_apply", lib.svol_gate_apply, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]), P(pos),
                      P(mem), P(memp), None, B, L, d, H, LN_EPS)
@@ -338,6 +370,17 @@ class HeadEngine:
                 ffn(p + "ffn1", mem2, w[p + "mlp1.w1"], w[p + "mlp1.b1"], w[p + "mlp1.w2"], w[p + "mlp1.b2"],
                     (w[p + "n3.w"], w[p + "n3.b"]), out=X, out_pos=Xp, theta_t=theta)
             x_cur, xp_cur = X, Xp            # layer output mem (and mem + pos)
+            # K / V^T of the cross-attention (:151-154) belong to the frame-token branch
+            if self.plain:
+                gemm(p + "ca_k", Xp, w[p + "ca.wk"], w[p + "ca.bk"], out=kc[li])
+                gemm(p + "ca_v", X, w[p + "ca.wv"], w[p + "ca.bv"], out_vt=vt_ca[li], vt_len=L, vt_pitch=Lp)
+                kv_done = p + "ca_v"
+            else:
+                gemm(p + "ca_kv", Xp, w[p + "ca.wkv"], w[p + "ca.bkv"], out=kc[li], out_vt=vt_ca[li], vt_len=L, vt_pitch=Lp,
+                     A2=X, split=1)
+                kv_done = p + "ca_kv"
+            # ---- object-query branch
+            q_first = len(plan.calls)
             # (c) query self-attention + norm4                                            :145-149
             if self.plain:
                 gemm(p + "ta_qk", outp_cur, w[p + "ta.wqk"], w[p + "ta.bqk"], out=qkq)
@@ -350,12 +393,8 @@ class HeadEngine:
                  ln=(w[p + "n4.w"], w[p + "n4.b"]), out_pos=o1p, pos_t=w["query_embed"], pos_mod=Q)
             # (d) query -> video cross-attention (padded keys masked) + norm5, FFN + norm6 :151-158
             gemm(p + "ca_q", o1p, w[p + "ca.wq"], w[p + "ca.bq"], out=qc)
-            if self.plain:
-                gemm(p + "ca_k", Xp, w[p + "ca.wk"], w[p + "ca.bk"], out=kc)
-                gemm(p + "ca_v", X, w[p + "ca.wv"], w[p + "ca.bv"], out_vt=vt, vt_len=L, vt_pitch=Lp)
-            else:
-                gemm(p + "ca_kv", Xp, w[p + "ca.wkv"], w[p + "ca.bkv"], out=kc, out_vt=vt, vt_len=L, vt_pitch=Lp, A2=X, split=1)
-            attention(p + "ca_attn", qc, kc, vt, attq, Q, L, d, d, Lp, mask=vmask)
+            attention(p + "ca_attn", qc, kc[li], vt_ca[li], attq, Q, L, d, d, Lp, mask=vmask)
+            plan.after[p + "ca_attn"] = [kv_done]
             gemm(p + "ca_out", attq, w[p + "ca.wo"], w[p + "ca.bo"], out=o2, residual=o1, ln=(w[p + "n5.w"], w[p + "n5.b"]))
             if self.plain:
                 hidq = plan.buf["hidq"] if "hidq" in plan.buf else buf("hidq", (MQ, ff), bf)
@@ -365,6 +404,8 @@ class HeadEngine:
             else:
                 ffn(p + "ffn2", o2, w[p + "mlp2.w1"], w[p + "mlp2.b1"], w[p + "mlp2.w2"], w[p + "mlp2.b2"],
                     (w[p + "n6.w"], w[p + "n6.b"]), out=hs[li], out_pos=outp, pos_t=w["query_embed"], pos_mod=Q)
+            for name, _, _ in plan.calls[q_first:]:
+                plan.branch[name] = "q"
             out_cur, outp_cur = hs[li], outp
         # ---- heads on every layer's queries (svanet.py:125-127)
         hs_all = hs.view(NL * MQ, d)
@@ -372,16 +413,8 @@ class HeadEngine:
         gemm("box1", h1, w["box.1.w"], w["box.1.b"], out=h2, act=ACT_RELU)
         call("heads", lib.svol_heads, P(hs_all), P(h2), P(w["cls.w"]), P(w["cls.b"]), P(w["box.2.w"]), P(w["box.2.b"]),
              P(logits), P(boxes), NL * MQ, d)
-        # order: [ln_in] [side: input-only small kernels] [pre: positions + input projection] [everything else]
-        is_side = lambda n: n.startswith("sk_proj") or n.endswith("gate_vec") or n == "qe_bcast"
-        first_consumer = next(i for i, c in enumerate(plan.calls) if c[0].endswith("gate_scores"))
-        head, rest = plan.calls[:1], plan.calls[1:]
-        side_calls = [c for c in rest if is_side(c[0])]
-        pre_calls = [c for c in plan.calls[1:first_consumer] if not is_side(c[0])]
-        post_calls = [c for c in plan.calls[first_consumer:] if not is_side(c[0])]
-        plan.calls = head + side_calls + pre_calls + post_calls
-        plan.side_begin, plan.side_end = 1, 1 + len(side_calls)
-        plan.join_index = plan.side_end + len(pre_calls)
+        for name in ("box0", "box1", "heads"):
+            plan.branch[name] = "q"
         return plan
 
     # ------------------------------------------------------------------ run
@@ -432,7 +465,7 @@ class HeadEngine:
                 plan.run(torch.cuda.current_stream().cuda_stream, start=1)
                 torch.cuda.synchronize()
                 if self._side is None:
-                    self._side = torch.cuda.Stream()
+                    self._side = (torch.cuda.Stream(), torch.cuda.Stream())
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     plan.run(torch.cuda.current_stream().cuda_stream, start=1, side=self._side)
