@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 3
+#define SVOL_ABI_VERSION 4
 
 enum {
   SVOL_OK = 0,
@@ -43,7 +43,7 @@ const char* svol_last_error(void);
 /* 0 if the current device can run this library (sm_100), SVOL_ERR_DEVICE otherwise. */
 int svol_device_check(void);
 /* sizeof() of the argument structures as this library was compiled (0 gemm_args, 1 attn_args,
- * 2 match_args, 3 criterion_args, 4 gemm_epilogue, 5 ffn_args) -- lets a foreign-language binding verify its
+ * 2 match_args, 3 criterion_args, 4 gemm_epilogue, 5 ffn_args, 6 attn_bwd_args) -- lets a foreign-language binding verify its
  * struct layout before the first launch. */
 int svol_sizeof_args(int which);
 
@@ -148,6 +148,9 @@ typedef struct svol_attn_args {
   const float* key_mask;
   svol_bf16* out;
   int32_t B, H, Lq, Lk, ldq, ldk, ldo, vt_pitch;
+  float* lse;          /* optional (training forward): base-2 log-sum-exp of the scaled scores, [B, H, lse_pitch] */
+  int32_t lse_pitch;   /* >= Lq */
+  int32_t reserved;
 } svol_attn_args;
 
 int svol_attention_bf16(const svol_attn_args* args, void* stream);
@@ -284,6 +287,97 @@ int svol_criterion_backward(const svol_criterion_args* args, const float* grad_w
  * ------------------------------------------------------------------------------------------ */
 int svol_postprocess(const float* logits, const float* boxes, float* out, int32_t* order, int32_t B,
                      int32_t Q, int32_t q_per_frame, void* stream);
+
+
+/* ==========================================================================================
+ * TRAINING STEP (train.py:216-232: forward in train mode, criterion, loss.backward(), AdamW).
+ * The reference gets its backward from torch.autograd over lib/modeling/svanet.py and
+ * lib/modeling/cross_modal_transformer.py; here every backward op is an explicit entry point.
+ * Dense gradients reuse svol_gemm_bf16:  dX = dY W  (W operand = the transposed weight) and
+ * dW = dY^T X  (both operands transposed by svol_transpose_bf16, contraction over the token rows).
+ * Activation gradients are bf16, parameter gradients fp32 (accumulated: zero them first).
+ * ========================================================================================== */
+
+/* y = LayerNorm(z) (and y_pos = y + pos), bf16 [rows, 256]; pos = fp32 table (row, or row % pos_mod) or theta
+ * (fp32 [rows] angles of svol_posenc_theta).  Training forward of norm1..norm6 / the input projection's second
+ * LayerNorm (cross_modal_transformer.py:127,141,143,149,156,158; svanet.py:174-176) when z must be kept. */
+int svol_layernorm_bf16(const svol_bf16* z, const float* weight, const float* bias, svol_bf16* y, svol_bf16* y_pos,
+                        const float* pos, int32_t pos_mod, const float* theta, int32_t rows, int32_t cols, float eps,
+                        void* stream);
+
+/* LayerNorm backward, cols = 256, 512, 768 or 1024.  z = forward input (bf16, or fp32 when z_is_f32), optionally times
+ * (1 + att[row]) (the sketch gate, cross_modal_transformer.py:124-126: then dx = dz * (1 + att) and
+ * datt[row] = sum_c dz * z_in).  dy = dy1 + dy2 + dy3 (dy2, dy3 optional).  dgamma / dbeta [cols] are accumulated. */
+int svol_layernorm_backward(const void* z, int32_t z_is_f32, const float* att, const svol_bf16* dy1,
+                            const svol_bf16* dy2, const svol_bf16* dy3, const float* gamma, svol_bf16* dx, float* datt,
+                            float* dgamma, float* dbeta, int32_t rows, int32_t cols, float eps, void* stream);
+
+/* y = GELU_erf(x) elementwise (F.gelu, cross_modal_transformer.py:163-179), n % 8 == 0. */
+int svol_gelu_bf16(const svol_bf16* x, svol_bf16* y, int64_t n, void* stream);
+/* out = dy * f'(saved).  mode SVOL_ACT_RELU: saved = activation output; SVOL_ACT_GELU: saved = pre-activation. */
+int svol_act_backward(const svol_bf16* dy, const svol_bf16* saved, svol_bf16* out, int64_t n, int32_t mode, void* stream);
+
+/* out[c, r] = in[r, c] (bf16; out pitch ld_out >= rows, columns >= rows untouched) and, if colsum != NULL,
+ * colsum[c] += sum_r in[r, c] (the bias gradient of the Linear whose output gradient `in` is). */
+int svol_transpose_bf16(const svol_bf16* in, int32_t ld_in, int32_t rows, int32_t cols, svol_bf16* out, int32_t ld_out,
+                        float* colsum, void* stream);
+int svol_colsum_bf16(const svol_bf16* in, int32_t ld_in, int32_t rows, int32_t cols, float* colsum, void* stream);
+
+/* Attention backward (autograd of nn.MultiheadAttention's core at cross_modal_transformer.py:139,147,154).
+ *   q [B*Lq, ldq] (pre-scaled as in svol_attention_bf16), k [B*Lk, ldk], v [B*Lk, ldv]: head h at columns [32h, 32h+32)
+ *   kt [B*8*32, kt_pitch], qt, d_ot [B*8*32, qt_pitch]: per-head transposed K, Q and dO (svol_gemm_bf16 out_vt);
+ *        columns beyond the sequence must be zero
+ *   o, d_o [B*Lq, 256]: forward output and its gradient;  lse [B, 8, stat_pitch]: from svol_attention_bf16, entries
+ *        [Lq, stat_pitch) must be +inf;  delta [B, 8, stat_pitch]: workspace, entries [Lq, stat_pitch) must be 0;
+ *        stat_pitch % 64 == 0
+ *   dq = gradient w.r.t. the UNSCALED query projection (x Wq^T + bq), dk, dv: [B*L, ld_*] bf16. */
+typedef struct svol_attn_bwd_args {
+  const svol_bf16* q;
+  const svol_bf16* k;
+  const svol_bf16* v;
+  const svol_bf16* kt;
+  const svol_bf16* qt;
+  const svol_bf16* o;
+  const svol_bf16* d_o;
+  const svol_bf16* d_ot;
+  const float* lse;
+  float* delta;
+  const float* key_mask;
+  svol_bf16* dq;
+  svol_bf16* dk;
+  svol_bf16* dv;
+  int32_t B, H, Lq, Lk, ldq, ldk, ldv, ld_o, ld_do, ld_dq, ld_dk, ld_dv, kt_pitch, qt_pitch, stat_pitch, reserved;
+} svol_attn_bwd_args;
+int svol_attention_backward_bf16(const svol_attn_bwd_args* args, void* stream);
+
+/* Backward of svol_heads: dhs_cls = dlogits Wc; dh2 = relu'(h2) * ((dboxes * boxes * (1 - boxes)) Wb);
+ * dwc [2,d], dbc [2], dwb [4,d], dbb [4] accumulated. */
+int svol_heads_backward(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const float* wb, const float* boxes,
+                        const float* dlogits, const float* dboxes, svol_bf16* dhs_cls, svol_bf16* dh2, float* dwc,
+                        float* dbc, float* dwb, float* dbb, int32_t rows, int32_t d, void* stream);
+
+/* Backward of the sketch gate from datt [B*L] (produced by svol_layernorm_backward with att):
+ *   dscores [B,H,L] workspace;  dx_out = dx_in + sum_h dscores u  (gradient w.r.t. the layer input x, through
+ *   both x * (1 + att) and the scores of x + pos);  du [B,H,d] accumulated. */
+int svol_gate_backward(const svol_bf16* xpos, const float* u, const float* scores, const float* datt,
+                       const svol_bf16* dx_in, svol_bf16* dx_out, float* dscores, float* du, int32_t B, int32_t L,
+                       int32_t d, int32_t H, void* stream);
+/* Backward of svol_gate_vectors: d_in_proj_weight [3d,d], d_in_proj_bias [3d], dsketch [B,d] accumulated. */
+int svol_gate_vectors_backward(const float* sketch, const float* in_proj_weight, const float* in_proj_bias,
+                               const float* du, float* d_in_proj_weight, float* d_in_proj_bias, float* dsketch,
+                               int32_t B, int32_t d, int32_t H, void* stream);
+/* Backward of svol_ln_linear_f32 (y = forward output).  dx [rows,in] (or NULL) written; parameter gradients accumulated. */
+int svol_ln_linear_f32_backward(const float* x, const float* ln_weight, const float* ln_bias, const float* w,
+                                const float* y, const float* dy, int32_t relu, float* dx, float* d_ln_weight,
+                                float* d_ln_bias, float* dw, float* db, int32_t rows, int32_t in_dim, int32_t out_dim,
+                                float eps, void* stream);
+/* acc[r % mod, :] += g[r, :] summed over rows (bf16 -> fp32, 256 columns): query-embedding gradient. */
+int svol_batch_sum(const svol_bf16* g, float* acc, int32_t rows, int32_t cols, int32_t mod, void* stream);
+/* dst[i] (+)= scale * src[i]: bf16 weight-gradient GEMM output -> fp32 parameter gradient. */
+int svol_accum_bf16(const svol_bf16* src, float* dst, int64_t n, float scale, int32_t accumulate, void* stream);
+/* Fused AdamW (torch.optim.AdamW, train.py:71-78) over one flat fp32 buffer; g is multiplied by grad_scale first. */
+int svol_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, int32_t step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -211,5 +211,47 @@ def set_criterion(outputs, targets, cfg):
     return losses, all_idx
 
 
+# ------------------------------------------------------------------------------------------ training step (autograd)
+def _stack_outputs(out):
+    logits = torch.stack([a["pred_logits"] for a in out.get("aux_outputs", [])] + [out["pred_logits"]])
+    boxes = torch.stack([a["pred_boxes"] for a in out.get("aux_outputs", [])] + [out["pred_boxes"]])
+    return logits, boxes
+
+
+def head_gradients(sd: Dict[str, torch.Tensor], src_sketch, src_sketch_mask, src_video, src_video_mask, grad_logits,
+                   grad_boxes, nheads=8, n_input_proj=2, dtype=torch.float32):
+    """Parameter gradients of the head for given upstream gradients w.r.t. the stacked (logits [NL,B,Q,2], boxes
+    [NL,B,Q,4]) of all decoder layers: what ``loss.backward()`` (train.py:229) propagates through
+    ``SVANet.forward`` in train mode with the input dropout at 0.  Returns ({name: grad}, logits, boxes)."""
+    names = [k for k, v in sd.items() if v.is_floating_point()]
+    leaf = {k: (sd[k].detach().to(dtype).clone().requires_grad_(True) if k in names else sd[k]) for k in sd}
+    c = lambda t: torch.as_tensor(t).to(dtype)
+    with torch.enable_grad():
+        out = svanet_forward.__wrapped__(leaf, c(src_sketch), c(src_sketch_mask), c(src_video), c(src_video_mask), nheads,
+                                         n_input_proj)
+        logits, boxes = _stack_outputs(out)
+        grads = torch.autograd.grad([logits, boxes], [leaf[k] for k in names], [c(grad_logits), c(grad_boxes)],
+                                    allow_unused=True)
+    return {k: g for k, g in zip(names, grads) if g is not None}, logits.detach(), boxes.detach()
+
+
+def training_step_gradients(sd: Dict[str, torch.Tensor], src_sketch, src_sketch_mask, src_video, src_video_mask, targets,
+                            cfg, weight_dict: Dict[str, float], dtype=torch.float32):
+    """train.py:222-229: outputs = model(...); loss_dict = criterion(outputs, targets); losses = sum(loss_dict[k] *
+    weight_dict[k]); losses.backward().  Returns ({name: grad}, {loss name: value}, matching indices)."""
+    names = [k for k, v in sd.items() if v.is_floating_point()]
+    leaf = {k: (sd[k].detach().to(dtype).clone().requires_grad_(True) if k in names else sd[k]) for k in sd}
+    c = lambda t: torch.as_tensor(t).to(dtype)
+    with torch.enable_grad():
+        out = svanet_forward.__wrapped__(leaf, c(src_sketch), c(src_sketch_mask), c(src_video), c(src_video_mask), cfg.nheads,
+                                         cfg.n_input_proj)
+        out32 = {"pred_logits": out["pred_logits"].float(), "pred_boxes": out["pred_boxes"].float(),
+                 "aux_outputs": [{k: v.float() for k, v in a.items()} for a in out["aux_outputs"]]}
+        losses, idx = set_criterion(out32, targets, cfg)
+        total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
+        grads = torch.autograd.grad(total, [leaf[k] for k in names], allow_unused=True)
+    return ({k: g for k, g in zip(names, grads) if g is not None}, {k: float(v) for k, v in losses.items()}, idx)
+
+
 def state_dict_to_torch(sd: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
     return {k: torch.from_numpy(np.ascontiguousarray(v)).float() for k, v in sd.items()}

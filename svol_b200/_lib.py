@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsvol_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -22,6 +22,10 @@ SYMBOLS = [
     "svol_layernorm_f32_to_bf16", "svol_ln_linear_f32", "svol_posenc_sine", "svol_posenc_theta", "svol_add_pos_bf16",
     "svol_gate_vectors", "svol_gate_scores", "svol_gate_apply", "svol_gate_apply_theta", "svol_heads",
     "svol_match", "svol_match_localize", "svol_criterion", "svol_criterion_backward", "svol_postprocess",
+    # training step
+    "svol_layernorm_bf16", "svol_layernorm_backward", "svol_gelu_bf16", "svol_act_backward", "svol_transpose_bf16",
+    "svol_colsum_bf16", "svol_attention_backward_bf16", "svol_heads_backward", "svol_gate_backward",
+    "svol_gate_vectors_backward", "svol_ln_linear_f32_backward", "svol_batch_sum", "svol_accum_bf16", "svol_adamw",
 ]
 
 
@@ -59,6 +63,19 @@ class AttnArgs(C.Structure):
         ("q", C.c_void_p), ("k", C.c_void_p), ("vt", C.c_void_p), ("key_mask", C.c_void_p), ("out", C.c_void_p),
         ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32), ("ldq", C.c_int32),
         ("ldk", C.c_int32), ("ldo", C.c_int32), ("vt_pitch", C.c_int32),
+        ("lse", C.c_void_p), ("lse_pitch", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("kt", C.c_void_p), ("qt", C.c_void_p),
+        ("o", C.c_void_p), ("d_o", C.c_void_p), ("d_ot", C.c_void_p), ("lse", C.c_void_p), ("delta", C.c_void_p),
+        ("key_mask", C.c_void_p), ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32), ("ldq", C.c_int32),
+        ("ldk", C.c_int32), ("ldv", C.c_int32), ("ld_o", C.c_int32), ("ld_do", C.c_int32), ("ld_dq", C.c_int32),
+        ("ld_dk", C.c_int32), ("ld_dv", C.c_int32), ("kt_pitch", C.c_int32), ("qt_pitch", C.c_int32),
+        ("stat_pitch", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -83,7 +100,7 @@ class CriterionArgs(C.Structure):
 
 
 _lib: Optional[C.CDLL] = None
-_i32, _f32, _vp = C.c_int32, C.c_float, C.c_void_p
+_i32, _i64, _f32, _vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 
 def _declare(lib: C.CDLL) -> None:
@@ -111,6 +128,20 @@ def _declare(lib: C.CDLL) -> None:
         "svol_criterion": [C.POINTER(CriterionArgs), _vp],
         "svol_criterion_backward": [C.POINTER(CriterionArgs), _vp, _vp, _vp, _vp],
         "svol_postprocess": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
+        "svol_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _f32, _vp],
+        "svol_layernorm_backward": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
+        "svol_gelu_bf16": [_vp, _vp, _i64, _vp],
+        "svol_act_backward": [_vp, _vp, _vp, _i64, _i32, _vp],
+        "svol_transpose_bf16": [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp],
+        "svol_colsum_bf16": [_vp, _i32, _i32, _i32, _vp, _vp],
+        "svol_attention_backward_bf16": [C.POINTER(AttnBwdArgs), _vp],
+        "svol_heads_backward": [_vp] * 13 + [_i32, _i32, _vp],
+        "svol_gate_backward": [_vp] * 8 + [_i32, _i32, _i32, _i32, _vp],
+        "svol_gate_vectors_backward": [_vp] * 7 + [_i32, _i32, _i32, _vp],
+        "svol_ln_linear_f32_backward": [_vp] * 6 + [_i32] + [_vp] * 5 + [_i32, _i32, _i32, _f32, _vp],
+        "svol_batch_sum": [_vp, _vp, _i32, _i32, _i32, _vp],
+        "svol_accum_bf16": [_vp, _vp, _i64, _f32, _i32, _vp],
+        "svol_adamw": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -130,7 +161,7 @@ def get_lib() -> C.CDLL:
         _declare(lib)
         if lib.svol_abi_version() != ABI_VERSION:
             raise ImportError("libsvol_b200.so ABI version mismatch; rebuild it")
-        for which, struct in enumerate((GemmArgs, AttnArgs, MatchArgs, CriterionArgs, GemmEpilogue, FfnArgs)):
+        for which, struct in enumerate((GemmArgs, AttnArgs, MatchArgs, CriterionArgs, GemmEpilogue, FfnArgs, AttnBwdArgs)):
             if lib.svol_sizeof_args(which) != C.sizeof(struct):
                 raise ImportError(f"ctypes layout of {struct.__name__} does not match libsvol_b200.so")
         _lib = lib

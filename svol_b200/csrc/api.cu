@@ -95,6 +95,27 @@ int launch_gate_apply(const svol_bf16*, const float*, const float*, const float*
 int launch_heads(const svol_bf16*, const svol_bf16*, const float*, const float*, const float*, const float*, float*,
                  float*, int, int, cudaStream_t);
 int launch_postprocess(const float*, const float*, float*, int32_t*, int, int, int, cudaStream_t);
+// train.cu / attn_bwd_tc.cu
+int launch_layernorm_bf16(const svol_bf16*, const float*, const float*, svol_bf16*, svol_bf16*, const float*, int, const float*,
+                          int, int, float, cudaStream_t);
+int launch_layernorm_backward(const void*, int, const float*, const svol_bf16*, const svol_bf16*, const svol_bf16*, const float*,
+                              svol_bf16*, float*, float*, float*, int, int, float, cudaStream_t);
+int launch_gelu_bf16(const svol_bf16*, svol_bf16*, long long, cudaStream_t);
+int launch_act_backward(const svol_bf16*, const svol_bf16*, svol_bf16*, long long, int, cudaStream_t);
+int launch_transpose_bf16(const svol_bf16*, int, int, int, svol_bf16*, int, float*, cudaStream_t);
+int launch_colsum_bf16(const svol_bf16*, int, int, int, float*, cudaStream_t);
+int launch_attention_backward_tc(const svol_attn_bwd_args&, cudaStream_t);
+int launch_heads_backward(const svol_bf16*, const svol_bf16*, const float*, const float*, const float*, const float*, const float*,
+                          svol_bf16*, svol_bf16*, float*, float*, float*, float*, int, int, cudaStream_t);
+int launch_gate_backward(const svol_bf16*, const float*, const float*, const float*, const svol_bf16*, svol_bf16*, float*, float*,
+                         int, int, int, int, cudaStream_t);
+int launch_gate_vectors_backward(const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int,
+                                 cudaStream_t);
+int launch_ln_linear_f32_backward(const float*, const float*, const float*, const float*, const float*, const float*, int, float*,
+                                  float*, float*, float*, float*, int, int, int, float, cudaStream_t);
+int launch_batch_sum(const svol_bf16*, float*, int, int, int, cudaStream_t);
+int launch_accum_bf16(const svol_bf16*, float*, long long, float, int, cudaStream_t);
+int launch_adamw(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
 
 }  // namespace svol
 
@@ -119,6 +140,7 @@ int svol_sizeof_args(int which) {
     case 3: return static_cast<int>(sizeof(svol_criterion_args));
     case 4: return static_cast<int>(sizeof(svol_gemm_epilogue));
     case 5: return static_cast<int>(sizeof(svol_ffn_args));
+    case 6: return static_cast<int>(sizeof(svol_attn_bwd_args));
     default: return -1;
   }
 }
@@ -233,6 +255,87 @@ int svol_postprocess(const float* logits, const float* boxes, float* out, int32_
                      int32_t q_per_frame, void* stream) {
   SVOL_REQUIRE(logits); SVOL_REQUIRE(boxes); SVOL_REQUIRE(out); SVOL_REQUIRE(order);
   return launch_postprocess(logits, boxes, out, order, B, Q, q_per_frame, SVOL_STREAM(stream));
+}
+
+
+// ---- training step
+int svol_layernorm_bf16(const svol_bf16* z, const float* w, const float* b, svol_bf16* y, svol_bf16* y_pos, const float* pos,
+                        int32_t pos_mod, const float* theta, int32_t rows, int32_t cols, float eps, void* stream) {
+  SVOL_REQUIRE(z); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
+  return launch_layernorm_bf16(z, w, b, y, y_pos, pos, pos_mod, theta, rows, cols, eps, SVOL_STREAM(stream));
+}
+int svol_layernorm_backward(const void* z, int32_t z_is_f32, const float* att, const svol_bf16* dy1, const svol_bf16* dy2,
+                            const svol_bf16* dy3, const float* gamma, svol_bf16* dx, float* datt, float* dgamma, float* dbeta,
+                            int32_t rows, int32_t cols, float eps, void* stream) {
+  SVOL_REQUIRE(z); SVOL_REQUIRE(dy1); SVOL_REQUIRE(gamma); SVOL_REQUIRE(dgamma); SVOL_REQUIRE(dbeta);
+  if (att && !datt) return svol_fail(SVOL_ERR_NULL, "layernorm_backward: att needs datt");
+  return launch_layernorm_backward(z, z_is_f32, att, dy1, dy2, dy3, gamma, dx, datt, dgamma, dbeta, rows, cols, eps,
+                                   SVOL_STREAM(stream));
+}
+int svol_gelu_bf16(const svol_bf16* x, svol_bf16* y, int64_t n, void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(y);
+  return launch_gelu_bf16(x, y, n, SVOL_STREAM(stream));
+}
+int svol_act_backward(const svol_bf16* dy, const svol_bf16* saved, svol_bf16* out, int64_t n, int32_t mode, void* stream) {
+  SVOL_REQUIRE(dy); SVOL_REQUIRE(saved); SVOL_REQUIRE(out);
+  return launch_act_backward(dy, saved, out, n, mode, SVOL_STREAM(stream));
+}
+int svol_transpose_bf16(const svol_bf16* in, int32_t ld_in, int32_t rows, int32_t cols, svol_bf16* out, int32_t ld_out,
+                        float* colsum, void* stream) {
+  SVOL_REQUIRE(in); SVOL_REQUIRE(out);
+  return launch_transpose_bf16(in, ld_in, rows, cols, out, ld_out, colsum, SVOL_STREAM(stream));
+}
+int svol_colsum_bf16(const svol_bf16* in, int32_t ld_in, int32_t rows, int32_t cols, float* colsum, void* stream) {
+  SVOL_REQUIRE(in); SVOL_REQUIRE(colsum);
+  return launch_colsum_bf16(in, ld_in, rows, cols, colsum, SVOL_STREAM(stream));
+}
+int svol_attention_backward_bf16(const svol_attn_bwd_args* a, void* stream) {
+  SVOL_REQUIRE(a); SVOL_REQUIRE(a->q); SVOL_REQUIRE(a->k); SVOL_REQUIRE(a->v); SVOL_REQUIRE(a->kt); SVOL_REQUIRE(a->qt);
+  SVOL_REQUIRE(a->o); SVOL_REQUIRE(a->d_o); SVOL_REQUIRE(a->d_ot); SVOL_REQUIRE(a->lse); SVOL_REQUIRE(a->delta);
+  SVOL_REQUIRE(a->dq); SVOL_REQUIRE(a->dk); SVOL_REQUIRE(a->dv);
+  return launch_attention_backward_tc(*a, SVOL_STREAM(stream));
+}
+int svol_heads_backward(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const float* wb, const float* boxes,
+                        const float* dlogits, const float* dboxes, svol_bf16* dhs_cls, svol_bf16* dh2, float* dwc, float* dbc,
+                        float* dwb, float* dbb, int32_t rows, int32_t d, void* stream) {
+  SVOL_REQUIRE(hs); SVOL_REQUIRE(h2); SVOL_REQUIRE(wc); SVOL_REQUIRE(wb); SVOL_REQUIRE(boxes); SVOL_REQUIRE(dlogits);
+  SVOL_REQUIRE(dboxes); SVOL_REQUIRE(dhs_cls); SVOL_REQUIRE(dh2); SVOL_REQUIRE(dwc); SVOL_REQUIRE(dbc); SVOL_REQUIRE(dwb);
+  SVOL_REQUIRE(dbb);
+  return launch_heads_backward(hs, h2, wc, wb, boxes, dlogits, dboxes, dhs_cls, dh2, dwc, dbc, dwb, dbb, rows, d,
+                               SVOL_STREAM(stream));
+}
+int svol_gate_backward(const svol_bf16* xpos, const float* u, const float* scores, const float* datt, const svol_bf16* dx_in,
+                       svol_bf16* dx_out, float* dscores, float* du, int32_t B, int32_t L, int32_t d, int32_t H, void* stream) {
+  SVOL_REQUIRE(xpos); SVOL_REQUIRE(u); SVOL_REQUIRE(scores); SVOL_REQUIRE(datt); SVOL_REQUIRE(dx_in); SVOL_REQUIRE(dx_out);
+  SVOL_REQUIRE(dscores); SVOL_REQUIRE(du);
+  return launch_gate_backward(xpos, u, scores, datt, dx_in, dx_out, dscores, du, B, L, d, H, SVOL_STREAM(stream));
+}
+int svol_gate_vectors_backward(const float* sketch, const float* w, const float* b, const float* du, float* dw, float* db,
+                               float* dsketch, int32_t B, int32_t d, int32_t H, void* stream) {
+  SVOL_REQUIRE(sketch); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(du); SVOL_REQUIRE(dw); SVOL_REQUIRE(db);
+  SVOL_REQUIRE(dsketch);
+  return launch_gate_vectors_backward(sketch, w, b, du, dw, db, dsketch, B, d, H, SVOL_STREAM(stream));
+}
+int svol_ln_linear_f32_backward(const float* x, const float* lw, const float* lb, const float* w, const float* y,
+                                const float* dy, int32_t relu, float* dx, float* dlw, float* dlb, float* dw, float* db,
+                                int32_t rows, int32_t in_dim, int32_t out_dim, float eps, void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(w); SVOL_REQUIRE(y); SVOL_REQUIRE(dy); SVOL_REQUIRE(dlw);
+  SVOL_REQUIRE(dlb); SVOL_REQUIRE(dw); SVOL_REQUIRE(db);
+  return launch_ln_linear_f32_backward(x, lw, lb, w, y, dy, relu, dx, dlw, dlb, dw, db, rows, in_dim, out_dim, eps,
+                                       SVOL_STREAM(stream));
+}
+int svol_batch_sum(const svol_bf16* g, float* acc, int32_t rows, int32_t cols, int32_t mod, void* stream) {
+  SVOL_REQUIRE(g); SVOL_REQUIRE(acc);
+  return launch_batch_sum(g, acc, rows, cols, mod, SVOL_STREAM(stream));
+}
+int svol_accum_bf16(const svol_bf16* src, float* dst, int64_t n, float scale, int32_t accumulate, void* stream) {
+  SVOL_REQUIRE(src); SVOL_REQUIRE(dst);
+  return launch_accum_bf16(src, dst, n, scale, accumulate, SVOL_STREAM(stream));
+}
+int svol_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, int32_t step, float grad_scale, void* stream) {
+  SVOL_REQUIRE(p); SVOL_REQUIRE(g); SVOL_REQUIRE(m); SVOL_REQUIRE(v);
+  return launch_adamw(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, SVOL_STREAM(stream));
 }
 
 }  // extern "C"

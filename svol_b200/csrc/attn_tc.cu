@@ -187,7 +187,7 @@ __device__ __forceinline__ float half_row_max(uint32_t (&s)[attn::HALF], const u
 __global__ void __launch_bounds__(attn::THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, const float* __restrict__ key_mask,
-                    __nv_bfloat16* __restrict__ out, int H, int Lq, int Lk, int ldo) {
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int lse_pitch, int H, int Lq, int Lk, int ldo) {
   using namespace attn;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -455,9 +455,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const float m = fmaxf(m_ref, m_hi);
         const float m_safe = m == -INFINITY ? 0.f : m;
         const float a_lo = ex2_approx(m_ref - m_safe), a_hi = ex2_approx(m_hi - m_safe);
-        const float inv = 1.0f / (a_lo * l_mine + a_hi * l_hi);
+        const float l_tot = a_lo * l_mine + a_hi * l_hi;
+        const float inv = 1.0f / l_tot;
         const int q = q0 + t * BQ + r;
         if (q < Lq) {
+          // training forward: base-2 log-sum-exp of the (pre-scaled) scores, so that the backward recomputes
+          // P = 2^(S - lse) without a second softmax pass
+          if (lse != nullptr) lse[(static_cast<size_t>(b) * H + h) * lse_pitch + q] = m_safe + __log2f(l_tot);
           const float w_lo = a_lo * inv, w_hi = a_hi * inv;
           uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * Lq + q) * ldo + h * DH);
 #pragma unroll
@@ -504,8 +508,10 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
+  if (a.lse != nullptr && a.lse_pitch < a.Lq) return svol_fail(SVOL_ERR_SHAPE, "attention: lse_pitch < Lq");
   attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask,
-                                                            reinterpret_cast<__nv_bfloat16*>(a.out), a.H, a.Lq, a.Lk, a.ldo);
+                                                            reinterpret_cast<__nv_bfloat16*>(a.out), a.lse, a.lse_pitch, a.H, a.Lq,
+                                                            a.Lk, a.ldo);
   return svol_check_launch("attention_tc");
 }
 

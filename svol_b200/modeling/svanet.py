@@ -5,6 +5,7 @@ import torch
 from torch import nn
 
 from ..engine import HeadEngine
+from ..train_engine import TrainEngine
 from .cross_modal_transformer import build_cross_modal_transformer
 from .position_encoding import build_position_encoding
 
@@ -30,6 +31,29 @@ class LinearLayer(nn.Module):
         self.layer_norm = layer_norm
         self.LayerNorm = nn.LayerNorm(in_hsz)
         self.net = nn.Sequential(nn.Dropout(dropout), nn.Linear(in_hsz, out_hsz))
+
+
+class _HeadTrainFn(torch.autograd.Function):
+    """Training-mode forward / backward of the head as ONE autograd node, so that the reference's
+    ``loss.backward()`` (train.py:229) drives the CUDA backward plan.  Inputs after the four data tensors are the
+    module's parameters (their gradients are the node's outputs); the frame features get no gradient (the
+    backbone hand-off is outside this path)."""
+
+    @staticmethod
+    def forward(ctx, module, src_sketch, src_sketch_mask, src_video, src_video_mask, *params):
+        eng = module.train_engine
+        logits, boxes = eng.forward(src_sketch, src_sketch_mask, src_video, src_video_mask)
+        ctx.module, ctx.n_params = module, len(params)
+        return logits.clone(), boxes.clone()
+
+    @staticmethod
+    def backward(ctx, g_logits, g_boxes):
+        module = ctx.module
+        eng = module.train_engine
+        eng.backward(g_logits.contiguous().float(), g_boxes.contiguous().float())
+        unused = {id(p) for p in module.class_head.parameters()}          # never reached by forward (svanet.py:125)
+        grads = [eng.grad_of(p) if (p.requires_grad and id(p) not in unused) else None for p in module.parameters()]
+        return (None, None, None, None, None, *grads)
 
 
 class SVANet(nn.Module):
@@ -65,23 +89,33 @@ class SVANet(nn.Module):
         self.aux_loss = aux_loss
         self.input_dropout = input_dropout
         self._engine = HeadEngine(self, use_graph=use_graph)
+        self._train_engine = None
 
     @property
     def engine(self) -> HeadEngine:
         return self._engine
 
+    @property
+    def train_engine(self) -> TrainEngine:
+        if self._train_engine is None:
+            self._train_engine = TrainEngine(self)
+        return self._train_engine
+
     def forward(self, src_sketch, src_sketch_mask, src_video, src_video_mask):
         """src_sketch (B,1,D_s), src_sketch_mask (B,1), src_video (B,L,D_v), src_video_mask (B,L) float {0,1}.
         Returns {'pred_logits' (B,Q,2), 'pred_boxes' (B,Q,4) cxcywh, 'aux_outputs': [...]} (svanet.py:128-141)."""
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "svol_b200: the CUDA head implements the forward (inference / forward+match) path; "
-                "call it under torch.no_grad() or model.eval() -- there is no silent PyTorch fallback")
-        logits, boxes = self._engine.forward(src_sketch, src_sketch_mask, src_video, src_video_mask)
+            # train.py:216-232: the forward keeps what the backward needs; loss.backward() runs the CUDA backward plan
+            logits, boxes = _HeadTrainFn.apply(self, src_sketch, src_sketch_mask, src_video, src_video_mask,
+                                               *self.parameters())
+        else:
+            logits, boxes = self._engine.forward(src_sketch, src_sketch_mask, src_video, src_video_mask)
         out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1]}
         if self.aux_loss:
             out["aux_outputs"] = [{"pred_logits": a, "pred_boxes": b} for a, b in zip(logits[:-1], boxes[:-1])]
         if self.vis_mode is not None:
+            if logits.requires_grad:
+                raise NotImplementedError("vis_mode returns detached decoder states; use it under torch.no_grad()")
             hs = self._engine._plans[tuple(src_video.shape)].buf["hs"]
             return out, hs.float().view(hs.shape[0], src_video.shape[0], self.num_queries, -1)
         return out

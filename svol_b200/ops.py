@@ -168,3 +168,87 @@ def heads(hs: torch.Tensor, h2: torch.Tensor, wc, bc, wb, bb):
     _lib.check(_lib.get_lib().svol_heads(_P(hs), _P(h2), _P(wc), _P(bc), _P(wb), _P(bb), _P(logits), _P(boxes), rows, d,
                                          _lib.stream_ptr()), "heads")
     return logits, boxes
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training-step entry points (functional form, for tests and one-off use; the training plan is train_engine.py)
+# ---------------------------------------------------------------------------------------------------------------
+def attention_train(q, k, vt, B, H, Lq, Lk, key_mask=None):
+    """Like :func:`attention`, also returns the base-2 log-sum-exp [B, H, round_up(Lq, 64)] (+inf padded)."""
+    _lib.require_device()
+    out = torch.empty((B * Lq, H * 32), device=q.device, dtype=torch.bfloat16)
+    pitch = (Lq + 63) // 64 * 64
+    lse = torch.full((B, H, pitch), float("inf"), device=q.device, dtype=torch.float32)
+    a = _lib.AttnArgs()
+    a.q, a.k, a.vt, a.key_mask, a.out = _P(q), _P(k), _P(vt), _P(key_mask), _P(out)
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.ldq, a.ldk, a.ldo, a.vt_pitch = q.stride(0), k.stride(0), out.stride(0), vt.stride(0)
+    a.lse, a.lse_pitch = _P(lse), pitch
+    _lib.check(_lib.get_lib().svol_attention_bf16(C.byref(a), _lib.stream_ptr()), "attention")
+    return out, lse
+
+
+def attention_backward(q, k, v, kt, qt, o, d_o, d_ot, lse, B, H, Lq, Lk, key_mask=None):
+    """Returns (dq [B*Lq,256] w.r.t. the UNSCALED query projection, dk, dv [B*Lk,256]) bf16."""
+    _lib.require_device()
+    dq = torch.empty((B * Lq, H * 32), device=q.device, dtype=torch.bfloat16)
+    dk = torch.empty((B * Lk, H * 32), device=q.device, dtype=torch.bfloat16)
+    dv = torch.empty_like(dk)
+    delta = torch.zeros_like(lse)
+    a = _lib.AttnBwdArgs()
+    a.q, a.k, a.v, a.kt, a.qt, a.o, a.d_o, a.d_ot = _P(q), _P(k), _P(v), _P(kt), _P(qt), _P(o), _P(d_o), _P(d_ot)
+    a.lse, a.delta, a.key_mask, a.dq, a.dk, a.dv = _P(lse), _P(delta), _P(key_mask), _P(dq), _P(dk), _P(dv)
+    a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk
+    a.ldq, a.ldk, a.ldv, a.ld_o, a.ld_do = q.stride(0), k.stride(0), v.stride(0), o.stride(0), d_o.stride(0)
+    a.ld_dq, a.ld_dk, a.ld_dv = dq.stride(0), dk.stride(0), dv.stride(0)
+    a.kt_pitch, a.qt_pitch, a.stat_pitch = kt.stride(0), qt.stride(0), lse.shape[-1]
+    _lib.check(_lib.get_lib().svol_attention_backward_bf16(C.byref(a), _lib.stream_ptr()), "attention_backward")
+    return dq, dk, dv
+
+
+def layernorm_bf16(z, w, b, pos=None, pos_mod=0, theta=None, eps: float = 1e-5):
+    _lib.require_device()
+    y = torch.empty_like(z)
+    y_pos = torch.empty_like(z) if (pos is not None or theta is not None) else None
+    _lib.check(_lib.get_lib().svol_layernorm_bf16(_P(z), _P(w), _P(b), _P(y), _P(y_pos), _P(pos), pos_mod, _P(theta), z.shape[0],
+                                                  z.shape[1], eps, _lib.stream_ptr()), "layernorm_bf16")
+    return y, y_pos
+
+
+def layernorm_backward(z, dys, gamma, att=None, want_dx: bool = True, eps: float = 1e-5):
+    """Returns (dx bf16 | None, datt | None, dgamma, dbeta)."""
+    _lib.require_device()
+    rows, cols = z.shape
+    dys = list(dys) + [None] * (3 - len(dys))
+    dx = torch.empty((rows, cols), device=z.device, dtype=torch.bfloat16) if want_dx else None
+    datt = torch.empty(rows, device=z.device, dtype=torch.float32) if att is not None else None
+    dg, db = torch.zeros(cols, device=z.device), torch.zeros(cols, device=z.device)
+    _lib.check(_lib.get_lib().svol_layernorm_backward(_P(z), int(z.dtype == torch.float32), _P(att), _P(dys[0]), _P(dys[1]), _P(dys[2]),
+                                                      _P(gamma), _P(dx), _P(datt), _P(dg), _P(db), rows, cols, eps,
+                                                      _lib.stream_ptr()), "layernorm_backward")
+    return dx, datt, dg, db
+
+
+def gelu_bf16(x):
+    _lib.require_device()
+    y = torch.empty_like(x)
+    _lib.check(_lib.get_lib().svol_gelu_bf16(_P(x), _P(y), x.numel(), _lib.stream_ptr()), "gelu")
+    return y
+
+
+def act_backward(dy, saved, mode):
+    _lib.require_device()
+    out = torch.empty_like(dy)
+    _lib.check(_lib.get_lib().svol_act_backward(_P(dy), _P(saved), _P(out), dy.numel(), mode, _lib.stream_ptr()), "act_backward")
+    return out
+
+
+def transpose_bf16(x, want_colsum: bool = False):
+    """x [rows, cols] bf16 -> (x^T [cols, round_up(rows, 64)] zero padded, colsum fp32 | None)."""
+    _lib.require_device()
+    rows, cols = x.shape
+    rp = (rows + 63) // 64 * 64
+    out = torch.zeros((cols, rp), device=x.device, dtype=torch.bfloat16)
+    cs = torch.zeros(cols, device=x.device, dtype=torch.float32) if want_colsum else None
+    _lib.check(_lib.get_lib().svol_transpose_bf16(_P(x), x.stride(0), rows, cols, _P(out), rp, _P(cs), _lib.stream_ptr()), "transpose")
+    return out, cs

@@ -230,6 +230,15 @@ def make_predictions(cfg: HeadConfig, batch: int, seed: int = 0, layers: int | N
     return logits, boxes
 
 
+def make_upstream_grads(cfg: HeadConfig, batch: int, seed: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Synthetic gradients w.r.t. the stacked head outputs (logits (layers,B,Q,2), boxes (layers,B,Q,4)) for the
+    backward parity tests that bypass the matcher: N(0, 1e-2), the scale of d(mean loss)/d(output) times ~1e2."""
+    rng = np.random.RandomState(5000 + seed)
+    gl = (1e-2 * rng.standard_normal((cfg.num_layers, batch, cfg.num_queries, 2))).astype(np.float32)
+    gb = (1e-2 * rng.standard_normal((cfg.num_layers, batch, cfg.num_queries, 4))).astype(np.float32)
+    return gl, gb
+
+
 def targets_to_torch(targets: List[dict]) -> List[dict]:
     """Deep-copies ``targets`` with every ``'bbox'`` leaf as a CPU float32 torch tensor,
     which is what the reference's matcher stacks (matcher.py:64-70)."""

@@ -182,3 +182,30 @@ def test_torch_port_criterion_matches_reference(golden_dir, case, cfg, mpf):
     for k in [k[5:] for k in g.files if k.startswith("loss/")]:
         ref = float(g["loss/" + k])
         assert abs(float(losses[k]) - ref) <= 2e-5 * max(1.0, abs(ref)), k
+
+
+# ------------------------------------------------------------------------------------------ training step (autograd)
+def test_oracle_head_gradients_match_reference_autograd(golden_dir):
+    """oracle/torch_port.head_gradients (autograd over the ATen restatement) against the gradients recorded from the
+    reference's own SVANet in train mode (tests/golden/make_golden_grads.py), config C1a, batch 2."""
+    from dataclasses import replace
+    import torch
+    from oracle import torch_port as tp
+    cfg = replace(synth.CONFIGS["C1a"], input_dropout=0.0)
+    gold = np.load(os.path.join(golden_dir, "grads_C1a_b2.npz"))
+    batch, seed = int(gold["batch"]), int(gold["seed"])
+    sd = synth.random_state_dict(cfg, seed)
+    inp = synth.make_inputs(cfg, batch, seed, padded=bool(gold["padded"]))
+    gl, gb = synth.make_upstream_grads(cfg, batch, seed)
+    grads, _, _ = tp.head_gradients(tp.state_dict_to_torch(sd), inp["src_sketch"], inp["src_sketch_mask"], inp["src_video"],
+                                    inp["src_video_mask"], gl, gb, nheads=cfg.nheads)
+    names = [k[len("head_f32/norm/"):] for k in gold.files if k.startswith("head_f32/norm/")]
+    assert set(names) == set(grads), "same set of parameters receives a gradient"
+    scale = max(float(gold["head_f64/norm/" + k]) for k in names)
+    stride = int(gold["stride"])
+    for k in names:
+        norm = float(gold["head_f32/norm/" + k])
+        got = grads[k].double()
+        assert abs(float(got.norm()) - norm) <= 1e-3 * max(norm, 1e-4 * scale), k
+        sample = gold["head_f32/sample/" + k].astype(np.float64)
+        assert np.abs(got.reshape(-1)[::stride].numpy() - sample).max() <= 1e-3 * max(np.abs(sample).max(), 1e-5 * scale), k
