@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=2, help="pairs per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-kernel time table to this file")
+    ap.add_argument("--mode", default="fwd_match", choices=["fwd_match", "train"],
+                    help="fwd_match: the headline metric (BASELINE configs[1]); train: the training step of BASELINE "
+                         "configs[2] (forward + matching + losses + backward + gradient all-reduce + AdamW)")
     return ap.parse_args()
 
 
@@ -199,6 +202,8 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------ our arm
 def main():
     args = parse()
+    if args.mode == "train":
+        return run_train(args)
     if args.impl == "reference":
         return run_reference(args)
     # stdout carries exactly one JSON line: library banners (NCCL prints its version to stdout) go to stderr
@@ -354,6 +359,183 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps), "host_numa_bound": bool(numa_bound),
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "tflops_algorithmic": synth.algorithmic_flops_per_pair(cfg) * pairs / (ms_step * 1e-3) / 1e12}
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ training step (config 3)
+TRAIN_METRIC = "sketch-video pairs/s training step"
+
+
+def run_train(args):
+    """BASELINE configs[2]: SVOL training step, data-parallel (per-GPU batch fixed, weak scaling): forward in train mode,
+    PerFrameMatcher + SetCriterion on every decoder layer, backward, ONE NCCL all-reduce of the flat fp32 gradient
+    buffer, fused AdamW (lr 1e-4, wd 1e-4: lib/configs.py:71-78).  The model is the deterministic network
+    (input_dropout = 0, see svol_b200/train_engine.py).  `--impl reference` times the same step through the oracle's
+    autograd (oracle/torch_port.py: the reference's ATen / scipy calls + torch.autograd + torch.optim.AdamW) on the
+    host cores, rank 0 only."""
+    from dataclasses import replace
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    from svol_b200 import synth
+    cfg = replace(synth.CONFIGS[args.config], num_layers=args.layers, input_dropout=0.0)
+    workload = {"workload": f"C3 on {args.config}: SVOL training step (train-mode forward + PerFrameMatcher + SetCriterion on all "
+                            f"decoder layers + backward + gradient all-reduce + AdamW), B={args.batch} pairs/GPU, T={cfg.num_frames}, "
+                            f"L={cfg.video_len}, D_in={cfg.input_vid_dim}, Q={cfg.num_queries}, layers={cfg.num_layers}, input_dropout=0",
+                "pairs_per_gpu_per_step": args.batch, "layers": cfg.num_layers,
+                "l2": ">4 GB of saved activations per step: nothing survives in the 126 MB L2 between steps",
+                "parallelism": f"dp{args.gpus}: one NCCL all-reduce of the flat fp32 gradient buffer per step"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from oracle import torch_port as tp
+        torch.set_num_threads(os.cpu_count())
+        b = args.ref_batch
+        sd = {k: v.clone().requires_grad_(True) for k, v in tp.state_dict_to_torch(synth.random_state_dict(cfg, 0)).items()}
+        opt = torch.optim.AdamW(list(sd.values()), lr=1e-4, weight_decay=1e-4)
+        inp = synth.make_inputs(cfg, b, 0, padded=True)
+        targets = synth.targets_to_torch(synth.make_targets(cfg, b, 0, frame_mask=inp["frame_mask"]))
+        wd = {k: w for k, w in (("loss_bbox", cfg.set_cost_bbox), ("loss_giou", cfg.set_cost_giou), ("loss_label", cfg.set_cost_class))}
+        wd.update({f"{k}_{i}": v for i in range(cfg.num_layers - 1) for k, v in list(wd.items())[:3]})
+
+        def step():
+            grads, _, _ = tp.training_step_gradients(sd, inp["src_sketch"], inp["src_sketch_mask"], inp["src_video"],
+                                                     inp["src_video_mask"], targets, cfg, wd)
+            for k, v in sd.items():
+                v.grad = grads.get(k)
+            opt.step()
+        sec = time_cpu(step, max(1, min(args.steps, 3)), 1)
+        value = b / sec
+        print(json.dumps({"impl": "reference", "metric": TRAIN_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": dict(workload, pairs_per_step_cpu=b),
+                          "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                           "sample": f"{b} pairs per step: oracle/torch_port.py forward + criterion under "
+                                                     "torch.autograd + torch.optim.AdamW, all host threads"},
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    import torch.distributed as dist
+    from svol_b200 import _lib, comm
+    from svol_b200.modeling import build_loss, build_svanet
+    from svol_b200.optim import FusedAdamW
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    numa_bound = comm.bind_to_gpu_numa_node(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    ns = cfg.to_namespace()
+    model = build_svanet(ns)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.random_state_dict(cfg, 0).items()}, strict=True)
+    model = model.to(dev).train()
+    criterion = build_loss(ns).to(dev).train()
+    opt = FusedAdamW(model, lr=1e-4, weight_decay=1e-4)
+    wd = criterion.weight_dict
+    sets = []
+    for s_ in range(2):
+        inp = synth.make_inputs(cfg, B, seed=100 * rank + s_, padded=True)
+        tg = synth.targets_to_torch(synth.make_targets(cfg, B, seed=100 * rank + s_, frame_mask=inp["frame_mask"]))
+        host = {k: torch.from_numpy(inp[k]).pin_memory() for k in ("src_sketch", "src_sketch_mask", "src_video", "src_video_mask")}
+        sets.append({"host": host, "dev": {k: v.to(dev) for k, v in host.items()}, "targets": tg})
+    stage = {k: torch.empty_like(v, device=dev) for k, v in sets[0]["host"].items()}
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def train_step(d, targets):
+        out = model(d["src_sketch"], d["src_sketch_mask"], d["src_video"], d["src_video_mask"])
+        loss_dict = criterion(out, targets)
+        total = sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)           # train.py:227-228
+        total.backward()
+        scale, _ = comm.allreduce_gradients(model.train_engine.grad_flat)        # one collective (no-op on 1 GPU)
+        opt.step(from_engine=True, grad_scale=scale)
+        return total.detach()
+
+    def step_resident(i):
+        return train_step(sets[i & 1]["dev"], sets[i & 1]["targets"])
+
+    def step_e2e(i):
+        for k, v in sets[i & 1]["host"].items():
+            stage[k].copy_(v, non_blocking=True)                                  # H2D of the step's inputs
+        criterion.matcher._cache._key = None                                      # targets walked + uploaded every step
+        total = train_step(stage, sets[i & 1]["targets"])
+        loss_host.copy_(total.reshape(1), non_blocking=True)                      # D2H of the step's loss
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        if sampler is not None:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            last = fn(i)
+        e1.record()
+        barrier()
+        return comm.max_over_ranks(e0.elapsed_time(e1), device=dev) / steps, last
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step, last = timed(step_resident, args.steps, max(args.warmup, 3), sampler=sampler)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, 3)
+    criterion.check_status()
+    plan = model.train_engine._last
+    launches = len(plan["fwd"].calls) + len(plan["bwd"].calls) + 2 * 3 + 4       # + attention-backward pairs, matcher, criterion fwd/bwd, AdamW
+    roofline = None
+    if rank == 0:
+        # dominant kernel family of the step: the video self-attention backward (delta + dQ + dK/dV kernels), timed live
+        st = torch.cuda.current_stream().cuda_stream
+        names = [c[0] for c in plan["bwd"].calls]
+        idx = [i for i, n in enumerate(names) if n.endswith("sa_attn_bwd")]
+        times = []
+        for i in idx:
+            name, fn, a = plan["bwd"].calls[i]
+            for _ in range(2):
+                _lib.check(fn(*a, st), name)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                _lib.check(fn(*a, st), name)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / 5)
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        peak = float(peaks.get("bf16_tflops_sustained", 1374.6))
+        flops = 10.0 * cfg.video_len * cfg.video_len * cfg.hidden_dim * B            # 5 GEMMs of 2 L^2 d per sample
+        ms_k = float(np.mean(times))
+        roofline = {"kernel": "attention backward (video self): delta + dQ + dK/dV", "bound": "tensor",
+                    "achieved": flops / (ms_k * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "frac": flops / (ms_k * 1e-3) / 1e12 / peak, "traffic": None, "ms_per_launch": ms_k,
+                    "share_of_step": len(idx) * ms_k / ms_step,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1374.6",
+                    "algorithmic_flops_per_launch": flops}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    pairs = B * world
+    h2d = sum(v.numel() * v.element_size() for v in sets[0]["host"].values())
+    line = {"metric": TRAIN_METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": workload, "clocks": clocks,
+            "e2e": {"value": pairs / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches * args.steps), "host_numa_bound": bool(numa_bound), "roofline": roofline,
+            "cpu_baseline": None, "final_loss": float(last),
+            "tflops_algorithmic": 3.0 * synth.algorithmic_flops_per_pair(cfg) * pairs / (ms_step * 1e-3) / 1e12}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 4
+#define SVOL_ABI_VERSION 5
 
 enum {
   SVOL_OK = 0,
@@ -90,7 +90,10 @@ typedef struct svol_gemm_args {
   svol_gemm_epilogue ep;
   const svol_bf16* A2; /* [M, lda2] or NULL */
   int32_t lda2;
-  int32_t reserved;
+  int32_t ld_f32;
+  float* out_f32;      /* or NULL.  Weight-gradient mode: out_f32[M, ld_f32] += A x W^T in fp32 (atomic accumulation, the
+                          contraction is split over the SMs); excludes every epilogue option.  dW = dY^T X of an
+                          nn.Linear with A = dY^T [N_out, rows], W = X^T [K_in, rows] (svol_transpose_bf16). */
 } svol_gemm_args;
 
 int svol_gemm_bf16(const svol_gemm_args* args, void* stream);
@@ -366,7 +369,8 @@ int svol_gate_backward(const svol_bf16* xpos, const float* u, const float* score
 int svol_gate_vectors_backward(const float* sketch, const float* in_proj_weight, const float* in_proj_bias,
                                const float* du, float* d_in_proj_weight, float* d_in_proj_bias, float* dsketch,
                                int32_t B, int32_t d, int32_t H, void* stream);
-/* Backward of svol_ln_linear_f32 (y = forward output).  dx [rows,in] (or NULL) written; parameter gradients accumulated. */
+/* Backward of svol_ln_linear_f32 (y = forward output).  dx [rows,in] is written (required: it doubles as the
+ * kernel pair's workspace); parameter gradients are accumulated. */
 int svol_ln_linear_f32_backward(const float* x, const float* ln_weight, const float* ln_bias, const float* w,
                                 const float* y, const float* dy, int32_t relu, float* dx, float* d_ln_weight,
                                 float* d_ln_bias, float* dw, float* db, int32_t rows, int32_t in_dim, int32_t out_dim,

@@ -250,7 +250,7 @@ def training_step_gradients(sd: Dict[str, torch.Tensor], src_sketch, src_sketch_
         losses, idx = set_criterion(out32, targets, cfg)
         total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)
         grads = torch.autograd.grad(total, [leaf[k] for k in names], allow_unused=True)
-    return ({k: g for k, g in zip(names, grads) if g is not None}, {k: float(v) for k, v in losses.items()}, idx)
+    return ({k: g for k, g in zip(names, grads) if g is not None}, {k: float(v.detach()) for k, v in losses.items()}, idx)
 
 
 def state_dict_to_torch(sd: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:

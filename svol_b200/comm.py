@@ -3,7 +3,8 @@ launch scripts (train_quickdraw.sh:34-37: one process per GPU; svol_dataloader.p
 
 Sketch-video pairs are independent through forward, matching and per-pair loss terms, so the hot path needs NO
 data-path collective: every rank processes its own shard.  The only collectives are the ones the reference has
-(loss averaging for logging, comm.py:21-25) and the max-over-ranks of device timings in bench.py.  Works on any
+(loss averaging for logging, comm.py:21-25; the gradient all-reduce of a training step, train.py:124) and the
+max-over-ranks of device timings in bench.py.  Works on any
 torch.distributed backend (NCCL on the B200 box, gloo in the CPU tests)."""
 from __future__ import annotations
 
@@ -64,6 +65,19 @@ def reduce_loss_dict(loss_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tens
     dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     flat /= get_world_size()
     return {k: flat[i] for i, k in enumerate(keys)}
+
+
+def allreduce_gradients(flat_grad: torch.Tensor, async_op: bool = False):
+    """Sums the flat fp32 gradient buffer of the head (``TrainEngine.grad_flat``, 27.7 MB at two layers) over the
+    ranks in ONE collective -- the data-parallel exchange of a training step (apex DDP in the reference, train.py:124;
+    SURVEY.md section 8e).  Returns ``(grad_scale, work)``: the optimizer multiplies the summed gradient by
+    ``grad_scale = 1 / world_size`` inside its fused update (the reference averages), ``work`` is the async handle
+    (or None).  The per-rank loss means are over the rank's own pairs (loss.py:55,94,102), so sum / world_size is
+    exactly the gradient of the mean of the rank losses."""
+    if not is_distributed():
+        return 1.0, None
+    work = dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, async_op=async_op)
+    return 1.0 / get_world_size(), (work if async_op else None)
 
 
 def all_gather_indices(local: torch.Tensor) -> torch.Tensor:

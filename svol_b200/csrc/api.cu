@@ -319,8 +319,8 @@ int svol_gate_vectors_backward(const float* sketch, const float* w, const float*
 int svol_ln_linear_f32_backward(const float* x, const float* lw, const float* lb, const float* w, const float* y,
                                 const float* dy, int32_t relu, float* dx, float* dlw, float* dlb, float* dw, float* db,
                                 int32_t rows, int32_t in_dim, int32_t out_dim, float eps, void* stream) {
-  SVOL_REQUIRE(x); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(w); SVOL_REQUIRE(y); SVOL_REQUIRE(dy); SVOL_REQUIRE(dlw);
-  SVOL_REQUIRE(dlb); SVOL_REQUIRE(dw); SVOL_REQUIRE(db);
+  SVOL_REQUIRE(x); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(w); SVOL_REQUIRE(y); SVOL_REQUIRE(dy); SVOL_REQUIRE(dx);
+  SVOL_REQUIRE(dlw); SVOL_REQUIRE(dlb); SVOL_REQUIRE(dw); SVOL_REQUIRE(db);
   return launch_ln_linear_f32_backward(x, lw, lb, w, y, dy, relu, dx, dlw, dlb, dw, db, rows, in_dim, out_dim, eps,
                                        SVOL_STREAM(stream));
 }

@@ -139,7 +139,8 @@ template <bool kResidentW>
 __global__ void __launch_bounds__(gemm::THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutPos,
-                    const __grid_constant__ CUtensorMap tmA2, const GemmEpilogue ep, int M, int N, int K, int split_block) {
+                    const __grid_constant__ CUtensorMap tmA2, const GemmEpilogue ep, int M, int N, int K, int split_block,
+                    int k_splits, float* __restrict__ out_f32, int ld_f32) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
   extern __shared__ uint8_t smem_raw[];
@@ -163,7 +164,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int my_n = kResidentW ? static_cast<int>(blockIdx.x) % n_blocks : 0;
   const int m_first = kResidentW ? static_cast<int>(blockIdx.x) / n_blocks : 0;
   const int m_stride = kResidentW ? static_cast<int>(gridDim.x) / n_blocks : 0;
-  const int num_tiles = m_blocks * n_blocks;
+  // split-K (streaming variant, weight gradients: few output tiles, a contraction over all token rows): a work item
+  // is (tile, k slice); slices accumulate into out_f32 with fp32 atomics.  k_splits == 1 otherwise.
+  const int kb_per_split = (num_kb + k_splits - 1) / k_splits;
+  const int num_tiles = m_blocks * n_blocks * k_splits;
   const int my_tiles = kResidentW ? (m_blocks > m_first ? (m_blocks - m_first + m_stride - 1) / m_stride : 0)
                                   : (num_tiles > static_cast<int>(blockIdx.x)
                                          ? (num_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
@@ -175,7 +179,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int vt_col_shift = second_part ? split_block * BN : 0;
   auto tile_coords = [&](int it, int& m_blk, int& n_blk) {
     if (kResidentW) { m_blk = m_first + it * m_stride; n_blk = my_n; }
-    else { const int tile = blockIdx.x + it * gridDim.x; m_blk = tile / n_blocks; n_blk = tile % n_blocks; }
+    else { const int tile = (blockIdx.x + it * gridDim.x) / k_splits; m_blk = tile / n_blocks; n_blk = tile % n_blocks; }
+  };
+  auto k_range = [&](int it, int& kb0, int& kb1) {      // k-blocks [kb0, kb1) of work item `it`
+    if (kResidentW || k_splits == 1) { kb0 = 0; kb1 = num_kb; return; }
+    const int split = (blockIdx.x + it * gridDim.x) % k_splits;
+    kb0 = split * kb_per_split;
+    kb1 = min(num_kb, kb0 + kb_per_split);
   };
 
   if (warp == 0 && lane == 0) {
@@ -217,9 +227,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        int m_blk, n_blk;
+        int m_blk, n_blk, kb0, kb1;
         tile_coords(it, m_blk, n_blk);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        k_range(it, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&tail->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&tail->full[stage], C::STAGE_BYTES);
           uint8_t* sa = stages + stage * C::STAGE_BYTES;
@@ -243,7 +254,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         SVOL_GTR(1, it, 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0, kb1;
+        k_range(it, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&tail->full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
@@ -251,7 +264,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t b_desc = make_kmajor_desc<128>(kResidentW ? smem_u32(smem + kb * B_BYTES) : sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb0) | k) != 0);
           umma_commit(&tail->empty[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -298,6 +311,23 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
       SVOL_GTR(0, it, 2);
+
+      if (out_f32 != nullptr) {
+        // weight-gradient mode: out_f32[row, col] += partial sum of this k slice (no bias / activation / bf16 output).
+        // An empty slice (kb0 >= kb1) issued no MMA: its accumulator is stale, nothing may be added.
+        int kb0, kb1;
+        k_range(it, kb0, kb1);
+        if (row_ok && kb0 < kb1) {
+          float* orow = out_f32 + static_cast<size_t>(row) * ld_f32 + col0;
+#pragma unroll
+          for (int i = 0; i < COLS_PER_THREAD; i += 4)      // 16-byte vector reductions: 4x fewer L2 atomic operations
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(orow + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]),
+                         "f"(v[i + 3])
+                         : "memory");
+        }
+        __syncwarp();
+        continue;
+      }
 
       if (ep.bias) {
         if (kResidentW) {
@@ -459,7 +489,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 template <bool kResidentW>
 static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
-                          const CUtensorMap& tmOutPos, const CUtensorMap& tmA2, cudaStream_t stream) {
+                          const CUtensorMap& tmOutPos, const CUtensorMap& tmA2, int k_splits, cudaStream_t stream) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
   static bool configured = false;
@@ -469,11 +499,11 @@ static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUten
     configured = true;
   }
   const int m_blocks = (a.M + BM - 1) / BM, n_blocks = a.N / BN;
-  const int tiles = m_blocks * n_blocks;
+  const int tiles = m_blocks * n_blocks * k_splits;
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (kResidentW) grid = grid / n_blocks * n_blocks;       // every CTA owns one n block
   gemm_bf16_tc_kernel<kResidentW><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, tmA2, a.ep, a.M, a.N, a.K,
-                                                                            a.split_block);
+                                                                            a.split_block, k_splits, a.out_f32, a.ld_f32);
   return svol_check_launch("gemm_bf16_tc");
 }
 
@@ -508,10 +538,25 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
     rc = make_tensor_map_2d(&tmA2, a.A2, a.K, a.M, a.lda2, BK, BM, 128);
     if (rc) return rc;
   }
-  const bool resident = a.K == RES_K && a.N / BN <= sm_count();
+  const bool resident = a.K == RES_K && a.N / BN <= sm_count() && a.out_f32 == nullptr;
   if (split > 0 && !resident) return svol_fail(SVOL_ERR_SHAPE, "gemm: split launch needs the resident-weight variant");
-  return resident ? launch_variant<true>(a, tmA, tmB, tmOut, tmOutPos, tmA2, stream)
-                  : launch_variant<false>(a, tmA, tmB, tmOut, tmOutPos, tmA2, stream);
+  int k_splits = 1;
+  if (a.out_f32 != nullptr) {
+    // accumulate-into-fp32 mode (weight gradients): split the contraction so that ~all SMs get a work item, at
+    // least 4 k-blocks per slice
+    if (a.ep.bias || a.ep.act != SVOL_ACT_NONE || a.ep.residual || a.ep.ln_weight || a.ep.out || a.ep.out_pos || a.ep.out_vt || split)
+      return svol_fail(SVOL_ERR_SHAPE, "gemm: out_f32 (accumulating fp32 output) excludes every other epilogue option");
+    if (a.ld_f32 < a.N || a.ld_f32 % 4 != 0 || (reinterpret_cast<uintptr_t>(a.out_f32) & 15))
+      return svol_fail(SVOL_ERR_SHAPE, "gemm: out_f32 must be 16-byte aligned with ld_f32 >= N, ld_f32 % 4 == 0");
+    const int tiles = ((a.M + BM - 1) / BM) * (a.N / BN), num_kb = a.K / BK;
+    k_splits = sm_count() / tiles;
+    if (k_splits > num_kb / 4) k_splits = num_kb / 4;
+    if (k_splits < 1) k_splits = 1;
+    const int per = (num_kb + k_splits - 1) / k_splits;
+    k_splits = (num_kb + per - 1) / per;                     // no empty slices
+  }
+  return resident ? launch_variant<true>(a, tmA, tmB, tmOut, tmOutPos, tmA2, k_splits, stream)
+                  : launch_variant<false>(a, tmA, tmB, tmOut, tmOutPos, tmA2, k_splits, stream);
 }
 
 }  // namespace svol

@@ -583,86 +583,103 @@ int launch_gate_vectors_backward(const float* sketch, const float* w, const floa
 
 // ---------------------------------------------------------------------------------------------
 // Backward of svol_ln_linear_f32 (one LinearLayer of the sketch branch, svanet.py:56-60,159-181), fp32:
-//   y = [ReLU](W xn + b), xn = LayerNorm(x) * gamma + beta.   One CTA per row.
+//   y = [ReLU](W xn + b), xn = LayerNorm(x) * gamma + beta.
+// Two kernels: (rows x out_dim/32) CTAs accumulate dW / db and their share of dxn = dy W into the dx buffer (zeroed
+// first), then one CTA per row turns dxn into dx (LayerNorm backward) and dgamma / dbeta.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ln_linear_f32_bwd_kernel(const float* __restrict__ x, const float* __restrict__ lw,
-                                                                const float* __restrict__ lb, const float* __restrict__ w,
-                                                                const float* __restrict__ y, const float* __restrict__ dy, int relu,
-                                                                float* __restrict__ dx, float* __restrict__ dlw, float* __restrict__ dlb,
-                                                                float* __restrict__ dw, float* __restrict__ db, int in_dim,
-                                                                int out_dim, float eps) {
-  extern __shared__ float sm[];     // xhat[in], xn[in], dxn[in], dyr[out], red[16]
-  float* xh = sm;
-  float* xn = xh + in_dim;
-  float* dxn = xn + in_dim;
-  float* dyr = dxn + in_dim;
-  float* red = dyr + out_dim;
-  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* xr = x + static_cast<size_t>(row) * in_dim;
-  auto block_sum = [&](float v) {
-    v = warp_sum(v);
-    __syncthreads();
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[i];
-    return t;
-  };
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < 8; ++i) t += red[i];
+  return t;
+}
+// xh[i] = (x - mean) * rstd of one row (in shared memory); returns rstd
+__device__ __forceinline__ float row_normalise(const float* __restrict__ xr, float* xh, float* red, int in_dim, float eps) {
   float s = 0.f;
-  for (int i = tid; i < in_dim; i += 256) { xh[i] = xr[i]; s += xr[i]; }
-  const float mean = block_sum(s) / in_dim;
+  for (int i = threadIdx.x; i < in_dim; i += 256) { xh[i] = xr[i]; s += xr[i]; }
+  const float mean = block_sum_256(s, red) / in_dim;
   float ss = 0.f;
-  for (int i = tid; i < in_dim; i += 256) { const float c = xh[i] - mean; ss += c * c; }
-  const float rstd = rsqrtf(block_sum(ss) / in_dim + eps);
-  for (int i = tid; i < in_dim; i += 256) {
-    const float v = (xh[i] - mean) * rstd;
-    xh[i] = v;
-    xn[i] = v * lw[i] + lb[i];
-    dxn[i] = 0.f;
-  }
-  for (int o = tid; o < out_dim; o += 256) {
-    float g = dy[static_cast<size_t>(row) * out_dim + o];
-    if (relu && !(y[static_cast<size_t>(row) * out_dim + o] > 0.f)) g = 0.f;
-    dyr[o] = g;
-    atomicAdd(db + o, g);
-  }
+  for (int i = threadIdx.x; i < in_dim; i += 256) { const float c = xh[i] - mean; ss += c * c; }
+  const float rstd = rsqrtf(block_sum_256(ss, red) / in_dim + eps);
+  for (int i = threadIdx.x; i < in_dim; i += 256) xh[i] = (xh[i] - mean) * rstd;
   __syncthreads();
-  // dW[o,i] += dyr[o] * xn[i];  dxn[i] = sum_o dyr[o] W[o,i]
-  for (int i = tid; i < in_dim; i += 256) {
-    float acc = 0.f;
-    const float xi = xn[i];
-    for (int o = 0; o < out_dim; ++o) {
-      const float g = dyr[o];
-      acc = fmaf(g, __ldg(w + static_cast<size_t>(o) * in_dim + i), acc);
-      if (g != 0.f) atomicAdd(dw + static_cast<size_t>(o) * in_dim + i, g * xi);
+  return rstd;
+}
+
+__global__ void __launch_bounds__(256) ln_linear_f32_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ lw,
+                                                                  const float* __restrict__ lb, const float* __restrict__ w,
+                                                                  const float* __restrict__ y, const float* __restrict__ dy, int relu,
+                                                                  float* __restrict__ dxn, float* __restrict__ dw, float* __restrict__ db,
+                                                                  int in_dim, int out_dim, float eps) {
+  extern __shared__ float sm[];     // xhat[in], dyr[32], red[8]
+  float* xh = sm;
+  float* dyr = xh + in_dim;
+  float* red = dyr + 32;
+  const int row = blockIdx.x, o0 = blockIdx.y * 32, tid = threadIdx.x;
+  row_normalise(x + static_cast<size_t>(row) * in_dim, xh, red, in_dim, eps);
+  if (tid < 32) {
+    const int o = o0 + tid;
+    float g = 0.f;
+    if (o < out_dim) {
+      g = dy[static_cast<size_t>(row) * out_dim + o];
+      if (relu && !(y[static_cast<size_t>(row) * out_dim + o] > 0.f)) g = 0.f;
+      atomicAdd(db + o, g);
     }
-    dxn[i] = acc;
+    dyr[tid] = g;
   }
   __syncthreads();
+  for (int i = tid; i < in_dim; i += 256) {
+    const float xn = xh[i] * lw[i] + lb[i];
+    float acc = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+      const int o = o0 + j;
+      if (o >= out_dim) break;
+      const float g = dyr[j];
+      acc = fmaf(g, __ldg(w + static_cast<size_t>(o) * in_dim + i), acc);
+      if (g != 0.f) atomicAdd(dw + static_cast<size_t>(o) * in_dim + i, g * xn);
+    }
+    atomicAdd(dxn + static_cast<size_t>(row) * in_dim + i, acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_linear_f32_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ lw,
+                                                                  float* __restrict__ dx /* in: dxn, out: dx */,
+                                                                  float* __restrict__ dlw, float* __restrict__ dlb, int in_dim, float eps) {
+  extern __shared__ float sm[];     // xhat[in], red[8]
+  float* xh = sm;
+  float* red = xh + in_dim;
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float rstd = row_normalise(x + static_cast<size_t>(row) * in_dim, xh, red, in_dim, eps);
+  float* dr = dx + static_cast<size_t>(row) * in_dim;
   float s1 = 0.f, s2 = 0.f;
   for (int i = tid; i < in_dim; i += 256) {
-    const float gd = lw[i] * dxn[i];
+    const float d = dr[i], gd = lw[i] * d;
     s1 += gd; s2 += gd * xh[i];
-    atomicAdd(dlw + i, dxn[i] * xh[i]);
-    atomicAdd(dlb + i, dxn[i]);
+    atomicAdd(dlw + i, d * xh[i]);
+    atomicAdd(dlb + i, d);
   }
-  s1 = block_sum(s1) / in_dim;
-  s2 = block_sum(s2) / in_dim;
-  if (dx)
-    for (int i = tid; i < in_dim; i += 256)
-      dx[static_cast<size_t>(row) * in_dim + i] = rstd * (lw[i] * dxn[i] - s1 - xh[i] * s2);
+  s1 = block_sum_256(s1, red) / in_dim;
+  s2 = block_sum_256(s2, red) / in_dim;
+  for (int i = tid; i < in_dim; i += 256) dr[i] = rstd * (lw[i] * dr[i] - s1 - xh[i] * s2);
 }
+
 int launch_ln_linear_f32_backward(const float* x, const float* lw, const float* lb, const float* w, const float* y, const float* dy,
                                   int relu, float* dx, float* dlw, float* dlb, float* dw, float* db, int rows, int in_dim,
                                   int out_dim, float eps, cudaStream_t stream) {
-  if (rows <= 0 || in_dim <= 0 || out_dim <= 0 || in_dim > 4096 || out_dim > 4096) return svol_fail(SVOL_ERR_SHAPE, "ln_linear_backward: bad sizes");
-  const size_t smem = (3 * in_dim + out_dim + 16) * sizeof(float);
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ln_linear_f32_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return svol_fail_cuda(e, "ln_linear_backward: cudaFuncSetAttribute");
-  }
-  ln_linear_f32_bwd_kernel<<<rows, 256, smem, stream>>>(x, lw, lb, w, y, dy, relu, dx, dlw, dlb, dw, db, in_dim, out_dim, eps);
-  return svol_check_launch("ln_linear_f32_backward");
+  if (rows <= 0 || in_dim <= 0 || out_dim <= 0 || in_dim > 8192) return svol_fail(SVOL_ERR_SHAPE, "ln_linear_backward: bad sizes");
+  cudaError_t e = cudaMemsetAsync(dx, 0, static_cast<size_t>(rows) * in_dim * sizeof(float), stream);
+  if (e != cudaSuccess) return svol_fail_cuda(e, "ln_linear_backward: memset");
+  ln_linear_f32_bwd_w_kernel<<<dim3(rows, (out_dim + 31) / 32), 256, (in_dim + 48) * sizeof(float), stream>>>(
+      x, lw, lb, w, y, dy, relu, dx, dw, db, in_dim, out_dim, eps);
+  int rc = svol_check_launch("ln_linear_f32_backward (weights)");
+  if (rc) return rc;
+  ln_linear_f32_bwd_x_kernel<<<rows, 256, (in_dim + 16) * sizeof(float), stream>>>(x, lw, dx, dlw, dlb, in_dim, eps);
+  return svol_check_launch("ln_linear_f32_backward (input)");
 }
 
 // ---------------------------------------------------------------------------------------------

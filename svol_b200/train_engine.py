@@ -11,8 +11,8 @@ Differences from the inference plan (``engine.py``):
     attention backward's MMAs take as K-major operands; the attention forward stores each row's log-sum-exp.
 
 Backward, per ``nn.Linear``: ``dX = dY W`` is the tcgen05 GEMM with the transposed weight as its W operand,
-``dW = dY^T X`` the same GEMM over transposed copies of dY and X (contraction over the token rows), ``db`` falls
-out of the transposition pass.  LayerNorm / GELU / ReLU / gate / heads backward are the kernels of ``train.cu``,
+``dW = dY^T X`` the same GEMM over transposed copies of dY and X (contraction over the token rows, split over the
+SMs and accumulated into the fp32 gradient with atomics), ``db`` falls out of the transposition pass.  LayerNorm / GELU / ReLU / gate / heads backward are the kernels of ``train.cu``,
 the attention backward is ``attn_bwd_tc.cu``.  Activation gradients are bf16, parameter gradients fp32 views of one
 flat buffer (``grad_of(param)``), zeroed at the start of every backward.
 
@@ -138,7 +138,7 @@ class TrainEngine:
 
         # ---------------------------------------------------------------- call recorders
         def gemm(plan, name, A, W, bias=None, out=None, act=ACT_NONE, residual=None, out_pos=None, pos_t=None, pos_mod=0,
-                 theta_t=None, out_vt=None, vt_len=0, vt_pitch=0):
+                 theta_t=None, out_vt=None, vt_len=0, vt_pitch=0, out_f32=None):
             a = GemmArgs()
             a.A, a.W = P(A), P(W)
             a.M, a.K = A.shape
@@ -156,6 +156,9 @@ class TrainEngine:
                 e.pos, e.ld_pos, e.pos_row_mod = P(pos_t), pos_t.stride(0), pos_mod
             if out_vt is not None:
                 e.out_vt, e.vt_len, e.vt_pitch = P(out_vt), vt_len, vt_pitch
+            if out_f32 is not None:                      # weight-gradient mode: fp32 accumulation, split contraction
+                assert out_f32.is_contiguous() and out_f32.shape == (a.M, a.N), name
+                a.out_f32, a.ld_f32 = P(out_f32), out_f32.stride(0)
             plan.keep.append(a)
             plan.calls.append((name, lib.svol_gemm_bf16, (C.byref(a),)))
 
@@ -199,7 +202,6 @@ class TrainEngine:
             if rows not in scratch or scratch[rows][2] < cols:
                 rp = _round_up(rows, 64)
                 scratch[rows] = (torch.zeros(cols * rp, device=dev, dtype=bf), torch.zeros(cols * rp, device=dev, dtype=bf), cols)
-        wtmp = buf("wtmp", (wide * wide,), bf)
 
         def linear_bwd(name, dY, X, weight_grad, bias_grad, wT=None, dX=None, residual=None, out_vt=None, vt_len=0, vt_pitch=0):
             """dY [R, N_out], X [R, K_in] (bf16).  weight_grad [N_out, K_in] / bias_grad [N_out] fp32 views (accumulated).
@@ -212,9 +214,7 @@ class TrainEngine:
             tA, tB = ta[:n_out * rp].view(n_out, rp), tb[:k_in * rp].view(k_in, rp)
             call(bwd, name + ".dYT", lib.svol_transpose_bf16, P(dY), dY.stride(0), rows, n_out, P(tA), rp, P(bias_grad))
             call(bwd, name + ".XT", lib.svol_transpose_bf16, P(X), X.stride(0), rows, k_in, P(tB), rp, None)
-            wt_out = wtmp[:n_out * k_in].view(n_out, k_in)
-            gemm(bwd, name + ".wgrad", tA, tB, out=wt_out)
-            call(bwd, name + ".acc", lib.svol_accum_bf16, P(wt_out), P(weight_grad), n_out * k_in, 1.0, 1)
+            gemm(bwd, name + ".wgrad", tA, tB, out_f32=weight_grad)
             if dX is not None or out_vt is not None:
                 gemm(bwd, name + ".dgrad", dY, wT, out=dX, residual=residual, out_vt=out_vt, vt_len=vt_len, vt_pitch=vt_pitch)
 
@@ -348,6 +348,7 @@ class TrainEngine:
         dscores = buf("dscores", (B, H, L), f32)
         du = buf("du", (B, H, d), f32)
         dsk1, dsk0 = buf("dsk1", (B, d), f32), buf("dsk0", (B, d), f32)
+        dsk_in = buf("dsk_in", (B, d_sk), f32)
         dhs_next = [buf(f"dhs_next{i}", (MQ, d), bf) for i in range(2)]    # d(out_in), d(outp_in) handed to the previous layer
         dX_next = buf("dX_next", (M, d), bf)                               # d(layer input X), handed to the previous layer
 
@@ -467,7 +468,7 @@ class TrainEngine:
               P(w["in_sketch.1.w"]), P(sk1), P(dsk1), 0, P(dsk0), P(G(sp[1].LayerNorm.weight)), P(G(sp[1].LayerNorm.bias)),
               P(G(sp[1].net[1].weight)), P(G(sp[1].net[1].bias)), B, d, d, LN_EPS)
         bcall("sk_proj0_bwd", lib.svol_ln_linear_f32_backward, P(s_in), P(w["in_sketch.0.ln_w"]), P(w["in_sketch.0.ln_b"]),
-              P(w["in_sketch.0.w"]), P(sk0), P(dsk0), 1, None, P(G(sp[0].LayerNorm.weight)), P(G(sp[0].LayerNorm.bias)),
+              P(w["in_sketch.0.w"]), P(sk0), P(dsk0), 1, P(dsk_in), P(G(sp[0].LayerNorm.weight)), P(G(sp[0].LayerNorm.bias)),
               P(G(sp[0].net[1].weight)), P(G(sp[0].net[1].bias)), B, d_sk, d, LN_EPS)
         bufs["_scratch"] = scratch
         return {"fwd": fwd, "bwd": bwd, "buf": bufs}

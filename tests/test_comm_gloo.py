@@ -46,6 +46,10 @@ def _worker(rank, world, port, q):
         out["max"] = comm.max_over_ranks(10.0 * (rank + 1))
         red = comm.reduce_loss_dict({"loss_bbox": torch.tensor(float(rank)), "loss_giou": torch.tensor(2.0 * rank)})
         out["loss"] = {k: float(v) for k, v in red.items()}
+        # 3. training step: one all-reduce over the flat gradient buffer, averaged inside the optimizer update
+        g = torch.full((1000,), float(rank + 1))
+        scale, _ = comm.allreduce_gradients(g)
+        out["grad"] = (float(g[0]), float(g[-1]), scale)
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -87,3 +91,4 @@ def test_two_rank_gloo_sharded_matching_equals_single_process():
     for r in range(world):
         assert res[r]["mean"] == 1.5 and res[r]["max"] == 20.0
         assert res[r]["loss"] == {"loss_bbox": 0.5, "loss_giou": 1.0}
+        assert res[r]["grad"] == (3.0, 3.0, 0.5)          # summed over the two ranks; the optimizer applies 1 / world

@@ -417,3 +417,21 @@ def test_training_step_end_to_end():
         opt.step()
     total, _ = step_loss()
     assert float(total) < first, f"loss did not decrease: {first} -> {float(total)}"
+
+
+def test_wgrad_split_k_fp32():
+    """svol_gemm_bf16 in weight-gradient mode: fp32 atomic accumulation with the contraction split over the SMs."""
+    from svol_b200 import _lib, ops
+    g = torch.Generator().manual_seed(11)
+    for rows, n_out, k_in in ((50176, 256, 256), (10240, 2048, 256), (10240, 256, 2048), (640, 512, 256), (64, 256, 768)):
+        dY = _bf(torch.randn(rows, n_out, generator=g) * 0.05).to(DEV)
+        X = _bf(torch.randn(rows, k_in, generator=g)).to(DEV)
+        dYt, _ = ops.transpose_bf16(dY)
+        Xt, _ = ops.transpose_bf16(X)
+        out = torch.full((n_out, k_in), 1.0, device=DEV)
+        a = _lib.GemmArgs()
+        a.A, a.W, a.M, a.N, a.K, a.lda, a.ldw = dYt.data_ptr(), Xt.data_ptr(), n_out, k_in, dYt.shape[1], dYt.stride(0), Xt.stride(0)
+        a.out_f32, a.ld_f32 = out.data_ptr(), k_in
+        _lib.check(_lib.get_lib().svol_gemm_bf16(C.byref(a), _lib.stream_ptr()), "wgrad")
+        ref = 1.0 + dY.float().t() @ X.float()
+        assert _rel(out, ref) < 1e-4, (rows, n_out, k_in)
