@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 5
+#define SVOL_ABI_VERSION 7
 
 enum {
   SVOL_OK = 0,
@@ -54,7 +54,7 @@ int svol_sizeof_args(int which);
  *   attention in/out proj    lib/modeling/cross_modal_transformer.py:88-97,137-141,145-156
  *   FFN fc1/GELU/fc2 + norm  lib/modeling/cross_modal_transformer.py:142-143,157-158,163-179
  *   box-head hidden layers   lib/modeling/svanet.py:144-156
- * Epilogue order: +bias -> act -> +residual -> LayerNorm(ln_weight, ln_bias, ln_eps) -> stores.
+ * Epilogue order: +bias (-> out_pre) -> act -> * f'(dact_src) -> +residual -> LayerNorm(ln_weight, ln_bias, ln_eps) -> stores.
  * Requirements: N % 256 == 0, K % 64 == 0; LayerNorm and the transposed store need N == 256;
  * A, W, out*, residual 16-byte aligned with row pitches (in elements) multiple of 8.
  * ------------------------------------------------------------------------------------------ */
@@ -77,6 +77,14 @@ typedef struct svol_gemm_epilogue {
   int32_t vt_pitch;           /* row pitch of out_vt in elements (multiple of 8, >= vt_len) */
   const float* pos_theta;     /* alternative to pos for out_pos: fp32 [M] angles from svol_posenc_theta; the sine
                                  encoding is evaluated in the epilogue (needs N == 256), no table is read */
+  /* training step */
+  svol_bf16* out_pre;         /* [M, ld_out] or NULL: the value BEFORE the activation (after bias), stored next to
+                                 out = act(...): the FFN's fc1 keeps its pre-activation for the backward.  Excludes out_pos. */
+  const svol_bf16* dact_src;  /* [M, ld_dact] or NULL: multiply the accumulator by f'(dact_src) before the residual add --
+                                 the activation backward fused into the dgrad GEMM.  dact_mode SVOL_ACT_GELU: dact_src is
+                                 the saved pre-activation; SVOL_ACT_RELU: the saved activation output (mask = src > 0). */
+  int32_t ld_dact;
+  int32_t dact_mode;
 } svol_gemm_epilogue;
 
 typedef struct svol_gemm_args {
@@ -379,6 +387,19 @@ int svol_ln_linear_f32_backward(const float* x, const float* ln_weight, const fl
 int svol_batch_sum(const svol_bf16* g, float* acc, int32_t rows, int32_t cols, int32_t mod, void* stream);
 /* dst[i] (+)= scale * src[i]: bf16 weight-gradient GEMM output -> fp32 parameter gradient. */
 int svol_accum_bf16(const svol_bf16* src, float* dst, int64_t n, float scale, int32_t accumulate, void* stream);
+/* Refreshes the packed operand copies of the launch plans from the fp32 parameters in one launch.  Job k copies
+ * src [rows, cols] fp32 (contiguous) to dst, multiplying rows [0, scaled_rows) by scale (the attention query rows carry
+ * log2(e)/sqrt(dh)), as bf16 (SVOL_PACK_BF16) or fp32, optionally transposed (dst [cols, rows]).  jobs is a DEVICE array. */
+enum { SVOL_PACK_BF16 = 1, SVOL_PACK_TRANSPOSE = 2 };
+typedef struct svol_pack_job {
+  const float* src;
+  void* dst;
+  int32_t rows, cols, scaled_rows, flags;
+  float scale;
+  int32_t reserved;
+} svol_pack_job;
+int svol_pack_weights(const svol_pack_job* jobs, int32_t n_jobs, void* stream);
+
 /* Fused AdamW (torch.optim.AdamW, train.py:71-78) over one flat fp32 buffer; g is multiplied by grad_scale first. */
 int svol_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                float weight_decay, int32_t step, float grad_scale, void* stream);

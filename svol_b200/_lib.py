@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsvol_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 7
 
 # every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -26,6 +26,7 @@ SYMBOLS = [
     "svol_layernorm_bf16", "svol_layernorm_backward", "svol_gelu_bf16", "svol_act_backward", "svol_transpose_bf16",
     "svol_colsum_bf16", "svol_attention_backward_bf16", "svol_heads_backward", "svol_gate_backward",
     "svol_gate_vectors_backward", "svol_ln_linear_f32_backward", "svol_batch_sum", "svol_accum_bf16", "svol_adamw",
+    "svol_pack_weights",
 ]
 
 
@@ -36,6 +37,7 @@ class GemmEpilogue(C.Structure):
         ("out", C.c_void_p), ("out_pos", C.c_void_p), ("pos", C.c_void_p), ("ld_pos", C.c_int32),
         ("pos_row_mod", C.c_int32), ("out_vt", C.c_void_p), ("vt_len", C.c_int32), ("vt_pitch", C.c_int32),
         ("pos_theta", C.c_void_p),
+        ("out_pre", C.c_void_p), ("dact_src", C.c_void_p), ("ld_dact", C.c_int32), ("dact_mode", C.c_int32),
     ]
 
 
@@ -77,6 +79,14 @@ class AttnBwdArgs(C.Structure):
         ("ld_dk", C.c_int32), ("ld_dv", C.c_int32), ("kt_pitch", C.c_int32), ("qt_pitch", C.c_int32),
         ("stat_pitch", C.c_int32), ("reserved", C.c_int32),
     ]
+
+
+class PackJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("scaled_rows", C.c_int32), ("flags", C.c_int32), ("scale", C.c_float), ("reserved", C.c_int32)]
+
+
+PACK_BF16, PACK_TRANSPOSE = 1, 2
 
 
 class MatchArgs(C.Structure):
@@ -142,6 +152,7 @@ def _declare(lib: C.CDLL) -> None:
         "svol_batch_sum": [_vp, _vp, _i32, _i32, _i32, _vp],
         "svol_accum_bf16": [_vp, _vp, _i64, _f32, _i32, _vp],
         "svol_adamw": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
+        "svol_pack_weights": [_vp, _i32, _vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -161,7 +172,7 @@ def get_lib() -> C.CDLL:
         _declare(lib)
         if lib.svol_abi_version() != ABI_VERSION:
             raise ImportError("libsvol_b200.so ABI version mismatch; rebuild it")
-        for which, struct in enumerate((GemmArgs, AttnArgs, MatchArgs, CriterionArgs, GemmEpilogue, FfnArgs, AttnBwdArgs)):
+        for which, struct in enumerate((GemmArgs, AttnArgs, MatchArgs, CriterionArgs, GemmEpilogue, FfnArgs, AttnBwdArgs, PackJob)):
             if lib.svol_sizeof_args(which) != C.sizeof(struct):
                 raise ImportError(f"ctypes layout of {struct.__name__} does not match libsvol_b200.so")
         _lib = lib

@@ -116,6 +116,7 @@ int launch_ln_linear_f32_backward(const float*, const float*, const float*, cons
 int launch_batch_sum(const svol_bf16*, float*, int, int, int, cudaStream_t);
 int launch_accum_bf16(const svol_bf16*, float*, long long, float, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
+int launch_pack_weights(const svol_pack_job*, int, cudaStream_t);
 
 }  // namespace svol
 
@@ -141,6 +142,7 @@ int svol_sizeof_args(int which) {
     case 4: return static_cast<int>(sizeof(svol_gemm_epilogue));
     case 5: return static_cast<int>(sizeof(svol_ffn_args));
     case 6: return static_cast<int>(sizeof(svol_attn_bwd_args));
+    case 7: return static_cast<int>(sizeof(svol_pack_job));
     default: return -1;
   }
 }
@@ -331,6 +333,10 @@ int svol_batch_sum(const svol_bf16* g, float* acc, int32_t rows, int32_t cols, i
 int svol_accum_bf16(const svol_bf16* src, float* dst, int64_t n, float scale, int32_t accumulate, void* stream) {
   SVOL_REQUIRE(src); SVOL_REQUIRE(dst);
   return launch_accum_bf16(src, dst, n, scale, accumulate, SVOL_STREAM(stream));
+}
+int svol_pack_weights(const svol_pack_job* jobs, int32_t n_jobs, void* stream) {
+  SVOL_REQUIRE(jobs);
+  return launch_pack_weights(jobs, n_jobs, SVOL_STREAM(stream));
 }
 int svol_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                float weight_decay, int32_t step, float grad_scale, void* stream) {

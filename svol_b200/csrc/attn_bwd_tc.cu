@@ -20,7 +20,9 @@
 // (gemm_tc.cu: out_vt).  Each CTA uses 256 TMEM columns and ~80 KB of shared memory, so TWO CTAs share an SM: while
 // one CTA's 128 softmax threads turn scores into gradients, the other CTA's MMAs run -- the overlap the forward
 // builds by hand with four staggered warpgroups comes from occupancy here.
-//   warps 0..3  compute (thread = one row of the tile = one TMEM lane)      warp 4  TMA producer      warp 5  MMA issuer
+//   warps 0..7  compute: warp w works on TMEM lane quarter w % 4 (thread = one row of the tile) and on columns
+//               [32 (w / 4), +32) of every 64-column block, so 16 compute warps per SM keep the MUFU pipe fed
+//   warp 8      TMA producer          warp 9  MMA issuer
 #include "common.cuh"
 #include "svol_internal.h"
 
@@ -28,7 +30,8 @@ namespace svol {
 
 namespace abwd {
 constexpr int BM = 128, BN = 64, DH = 32;
-constexpr int THREADS = 192;
+constexpr int COMPUTE_WARPS = 8;                 // two warps per TMEM lane quarter, 32 of the 64 block columns each
+constexpr int THREADS = (COMPUTE_WARPS + 2) * 32;
 constexpr int ROW_TILE_BYTES = BM * DH * 2;      // 8192: [128 x 32] bf16, 64B swizzle
 constexpr int COL_TILE_BYTES = BN * DH * 2;      // 4096: [64 x 32] bf16 (64B swizzle) or its transpose [32 x 64] (128B swizzle)
 constexpr uint32_t TMEM_COLS = 256;
@@ -71,6 +74,15 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait_() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -108,22 +120,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int n_blk = (Lk + BN - 1) / BN;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == COMPUTE_WARPS && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmKt);
     mbar_init(&bars->once_full, 1);
     for (int s = 0; s < DQ_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     mbar_init(&bars->sdp_full, 1);
-    mbar_init(&bars->ds_ready, 4);
+    mbar_init(&bars->ds_ready, COMPUTE_WARPS);
     mbar_init(&bars->acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == COMPUTE_WARPS + 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 4) {
+  if (warp == COMPUTE_WARPS) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       mbar_arrive_expect_tx(&bars->once_full, 2 * ROW_TILE_BYTES);
@@ -139,7 +151,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_2d(st + 2 * COL_TILE_BYTES, &tmKt, &bars->full[s], j * BN, (b * H + h) * DH);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == COMPUTE_WARPS + 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
@@ -176,9 +188,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ------------------------------------------------------------------ compute: thread = query row
-    const int r = warp * 32 + lane;
+    const int quarter = warp & 3, c = warp >> 2;      // TMEM lane quarter, column half of each 64-key block
+    const int r = quarter * 32 + lane;
     const int q = q0 + r;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const size_t stat = (static_cast<size_t>(b) * H + h) * stat_pitch;
     const float lse_r = q < Lq ? __ldg(lse + stat + q) : INFINITY;
     const float delta_r = q < Lq ? __ldg(delta + stat + q) : 0.f;
@@ -188,8 +201,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (mrow != nullptr || (j + 1) * BN > Lk) key_words(mrow, j * BN, Lk, lane, words);
       mbar_wait(&bars->sdp_full, j & 1);
       tcgen05_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
         uint32_t s[32], dp[32], packed[16];
         tmem_ld_32x32b_x32(t_lane + DQ_T_S + c * 32, s);
         tmem_ld_32x32b_x32(t_lane + DQ_T_DP + c * 32, dp);
@@ -210,14 +222,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     mbar_wait(&bars->acc_full, 0);
     tcgen05_fence_after();
-    uint32_t acc[32];
-    tmem_ld_32x32b_x32(t_lane + DQ_T_ACC, acc);
+    uint32_t acc[16];                               // this warp's half of the 32 accumulator columns
+    tmem_ld_32x32b_x16(t_lane + DQ_T_ACC + c * 16, acc);
     tmem_ld_wait();
     if (q < Lq) {
       const float sc = 0.17677669529663687f;       // 1 / sqrt(32)
-      uint4* op = reinterpret_cast<uint4*>(dq + (static_cast<size_t>(b) * Lq + q) * ld_dq + h * DH);
+      uint4* op = reinterpret_cast<uint4*>(dq + (static_cast<size_t>(b) * Lq + q) * ld_dq + h * DH + c * 16);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         uint4 w;
         w.x = pack_bf16x2(__uint_as_float(acc[8 * i + 0]) * sc, __uint_as_float(acc[8 * i + 1]) * sc);
         w.y = pack_bf16x2(__uint_as_float(acc[8 * i + 2]) * sc, __uint_as_float(acc[8 * i + 3]) * sc);
@@ -230,7 +242,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == abwd::COMPUTE_WARPS + 1) {
     tcgen05_fence_after();
     tmem_dealloc<abwd::TMEM_COLS>(tmem_base);
   }
@@ -255,23 +267,23 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
   const int k0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
   const int n_blk = (Lq + BN - 1) / BN;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == COMPUTE_WARPS && lane == 0) {
     tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO);
     tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmdOt);
     mbar_init(&bars->once_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     mbar_init(&bars->sdp_full, 1);
-    mbar_init(&bars->ds_ready, 4);
+    mbar_init(&bars->ds_ready, COMPUTE_WARPS);
     mbar_init(&bars->acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == COMPUTE_WARPS + 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 4) {
+  if (warp == COMPUTE_WARPS) {
     if (elect_one()) {
       mbar_arrive_expect_tx(&bars->once_full, 2 * ROW_TILE_BYTES);
       tma_load_2d(smem, &tmK, &bars->once_full, h * DH, b * Lk + k0);
@@ -287,7 +299,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
         tma_load_2d(st + 3 * COL_TILE_BYTES, &tmdOt, &bars->full[s], j * BN, (b * H + h) * DH);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == COMPUTE_WARPS + 1) {
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_acc = make_idesc_bf16(BM, DH);
@@ -328,37 +340,43 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     }
   } else {
     // ------------------------------------------------------------------ compute: thread = key row
-    const int r = warp * 32 + lane;
+    const int quarter = warp & 3, c = warp >> 2;      // TMEM lane quarter, column half of each 64-query block
+    const int r = quarter * 32 + lane;
     const int key = k0 + r;
     const bool key_ok = key < Lk && (key_mask == nullptr || __ldg(key_mask + static_cast<size_t>(b) * Lk + key) != 0.f);
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const float* stat_g = (r < BN ? lse : delta) + (static_cast<size_t>(b) * H + h) * stat_pitch + (r & (BN - 1));
-    float nxt = __ldg(stat_g);                      // stat_pitch is a multiple of 64: every block read is in bounds
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int tid = threadIdx.x;                      // 0..255; the first 128 threads stage the block's lse | delta
+    const float* stat_g = (tid < BN ? lse : delta) + (static_cast<size_t>(b) * H + h) * stat_pitch + (tid & (BN - 1));
+    float nxt = tid < 2 * BN ? __ldg(stat_g) : 0.f;   // stat_pitch is a multiple of 64: every block read is in bounds
     for (int j = 0; j < n_blk; ++j) {
       float* st = stat_s + (j & 1) * 2 * BN;
-      st[r] = nxt;                                  // threads 0..63: lse of query j*64 + r;  64..127: delta
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (j + 1 < n_blk) nxt = __ldg(stat_g + (j + 1) * BN);
+      if (tid < 2 * BN) st[tid] = nxt;              // threads 0..63: lse of query j*64 + tid;  64..127: delta
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < 2 * BN && j + 1 < n_blk) nxt = __ldg(stat_g + (j + 1) * BN);
       mbar_wait(&bars->sdp_full, j & 1);
       tcgen05_fence_after();
       const uint32_t st_addr = smem_u32(st);
+      {
+        uint32_t pp[16], dsp[16];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t s[32], dp[32], pp[16], dsp[16];
-        tmem_ld_32x32b_x32(t_lane + KV_T_S + c * 32, s);
-        tmem_ld_32x32b_x32(t_lane + KV_T_DP + c * 32, dp);
-        tmem_ld_wait();
+        for (int sub = 0; sub < 2; ++sub) {           // 16 columns at a time: keeps the live registers under the 2-CTA budget
+          uint32_t s[16], dp[16];
+          tmem_ld_32x32b_x16(t_lane + KV_T_S + c * 32 + sub * 16, s);
+          tmem_ld_32x32b_x16(t_lane + KV_T_DP + c * 32 + sub * 16, dp);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 l4 = lds_f4(st_addr + (c * 32 + i) * 4);
-          const float4 d4 = lds_f4(st_addr + (BN + c * 32 + i) * 4);
-          float p0 = ex2f(__uint_as_float(s[i + 0]) - l4.x), p1 = ex2f(__uint_as_float(s[i + 1]) - l4.y);
-          float p2 = ex2f(__uint_as_float(s[i + 2]) - l4.z), p3 = ex2f(__uint_as_float(s[i + 3]) - l4.w);
-          if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
-          pp[i >> 1] = pack_bf16x2(p0, p1);
-          pp[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-          dsp[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[i + 0]) - d4.x), p1 * (__uint_as_float(dp[i + 1]) - d4.y));
-          dsp[(i >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[i + 2]) - d4.z), p3 * (__uint_as_float(dp[i + 3]) - d4.w));
+          for (int i = 0; i < 16; i += 4) {
+            const float4 l4 = lds_f4(st_addr + (c * 32 + sub * 16 + i) * 4);
+            const float4 d4 = lds_f4(st_addr + (BN + c * 32 + sub * 16 + i) * 4);
+            float p0 = ex2f(__uint_as_float(s[i + 0]) - l4.x), p1 = ex2f(__uint_as_float(s[i + 1]) - l4.y);
+            float p2 = ex2f(__uint_as_float(s[i + 2]) - l4.z), p3 = ex2f(__uint_as_float(s[i + 3]) - l4.w);
+            if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+            const int o = sub * 8 + (i >> 1);
+            pp[o] = pack_bf16x2(p0, p1);
+            pp[o + 1] = pack_bf16x2(p2, p3);
+            dsp[o] = pack_bf16x2(p0 * (__uint_as_float(dp[i + 0]) - d4.x), p1 * (__uint_as_float(dp[i + 1]) - d4.y));
+            dsp[o + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[i + 2]) - d4.z), p3 * (__uint_as_float(dp[i + 3]) - d4.w));
+          }
         }
         tmem_st_x16(t_lane + KV_T_P + c * 16, pp);
         tmem_st_x16(t_lane + KV_T_DS + c * 16, dsp);
@@ -370,16 +388,16 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     }
     mbar_wait(&bars->acc_full, 0);
     tcgen05_fence_after();
-    uint32_t av[32], ak[32];
-    tmem_ld_32x32b_x32(t_lane + KV_T_DV, av);
-    tmem_ld_32x32b_x32(t_lane + KV_T_DK, ak);
+    uint32_t av[16], ak[16];                        // this warp's half of the 32 + 32 accumulator columns
+    tmem_ld_32x32b_x16(t_lane + KV_T_DV + c * 16, av);
+    tmem_ld_32x32b_x16(t_lane + KV_T_DK + c * 16, ak);
     tmem_ld_wait();
     if (key < Lk) {
       const float ln2 = 0.6931471805599453f;
-      uint4* ov = reinterpret_cast<uint4*>(dv + (static_cast<size_t>(b) * Lk + key) * ld_dv + h * DH);
-      uint4* ok = reinterpret_cast<uint4*>(dk + (static_cast<size_t>(b) * Lk + key) * ld_dk + h * DH);
+      uint4* ov = reinterpret_cast<uint4*>(dv + (static_cast<size_t>(b) * Lk + key) * ld_dv + h * DH + c * 16);
+      uint4* ok = reinterpret_cast<uint4*>(dk + (static_cast<size_t>(b) * Lk + key) * ld_dk + h * DH + c * 16);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < 2; ++i) {
         uint4 w;
         w.x = pack_bf16x2(__uint_as_float(av[8 * i + 0]), __uint_as_float(av[8 * i + 1]));
         w.y = pack_bf16x2(__uint_as_float(av[8 * i + 2]), __uint_as_float(av[8 * i + 3]));
@@ -397,7 +415,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == abwd::COMPUTE_WARPS + 1) {
     tcgen05_fence_after();
     tmem_dealloc<abwd::TMEM_COLS>(tmem_base);
   }

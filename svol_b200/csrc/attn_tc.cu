@@ -184,6 +184,9 @@ __device__ __forceinline__ float half_row_max(uint32_t (&s)[attn::HALF], const u
   return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
 }
 
+// kLse: the training forward also stores each row's base-2 log-sum-exp (a separate instantiation so that the inference
+// kernel keeps the register allocation it was tuned with).
+template <bool kLse>
 __global__ void __launch_bounds__(attn::THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, const float* __restrict__ key_mask,
@@ -461,7 +464,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (q < Lq) {
           // training forward: base-2 log-sum-exp of the (pre-scaled) scores, so that the backward recomputes
           // P = 2^(S - lse) without a second softmax pass
-          if (lse != nullptr) lse[(static_cast<size_t>(b) * H + h) * lse_pitch + q] = m_safe + __log2f(l_tot);
+          if (kLse) lse[(static_cast<size_t>(b) * H + h) * lse_pitch + q] = m_safe + __log2f(l_tot);
           const float w_lo = a_lo * inv, w_hi = a_hi * inv;
           uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * Lq + q) * ldo + h * DH);
 #pragma unroll
@@ -503,15 +506,19 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return svol_fail_cuda(e, "attention: cudaFuncSetAttribute");
     configured = true;
   }
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
   if (a.lse != nullptr && a.lse_pitch < a.Lq) return svol_fail(SVOL_ERR_SHAPE, "attention: lse_pitch < Lq");
-  attention_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask,
-                                                            reinterpret_cast<__nv_bfloat16*>(a.out), a.lse, a.lse_pitch, a.H, a.Lq,
-                                                            a.Lk, a.ldo);
+  if (a.lse != nullptr)
+    attention_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
+                                                                    a.lse, a.lse_pitch, a.H, a.Lq, a.Lk, a.ldo);
+  else
+    attention_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
+                                                                     nullptr, 0, a.H, a.Lq, a.Lk, a.ldo);
   return svol_check_launch("attention_tc");
 }
 

@@ -230,4 +230,20 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(hx, erfv, hx);
 }
 
+// d/dx of the erf-form GELU: Phi(x) + x phi(x), with the same erfc construction as gelu_erf_fast (two MUFU ex2).
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float g = -0.00014204370381776243f;
+  g = fmaf(g, z, 0.003664282150566578f);
+  g = fmaf(g, z, -0.03089619241654873f);
+  g = fmaf(g, z, 0.14969943463802338f);
+  g = fmaf(g, z, 0.9181654453277588f);
+  g = fmaf(g, z, 1.6279250383377075f);
+  float e, pdf;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * g));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pdf) : "f"(-0.72134752044448170368f * x * x));
+  const float cdf = fmaf(0.5f, copysignf(1.0f - e, x), 0.5f);
+  return fmaf(x * 0.3989422804014327f, pdf, cdf);
+}
+
 }  // namespace svol

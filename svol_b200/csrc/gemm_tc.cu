@@ -135,7 +135,9 @@ __device__ __forceinline__ void block_store_tma(uint8_t* stg, const uint4 (&q)[8
   }
 }
 
-template <bool kResidentW>
+// kTrain compiles in the training-step options (split-K fp32 accumulation, out_pre, fused activation backward); the
+// inference instantiations are exactly the kernels the forward plan was tuned with.
+template <bool kResidentW, bool kTrain>
 __global__ void __launch_bounds__(gemm::THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutPos,
@@ -166,6 +168,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int m_stride = kResidentW ? static_cast<int>(gridDim.x) / n_blocks : 0;
   // split-K (streaming variant, weight gradients: few output tiles, a contraction over all token rows): a work item
   // is (tile, k slice); slices accumulate into out_f32 with fp32 atomics.  k_splits == 1 otherwise.
+  if (!kTrain) k_splits = 1;
   const int kb_per_split = (num_kb + k_splits - 1) / k_splits;
   const int num_tiles = m_blocks * n_blocks * k_splits;
   const int my_tiles = kResidentW ? (m_blocks > m_first ? (m_blocks - m_first + m_stride - 1) / m_stride : 0)
@@ -182,7 +185,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     else { const int tile = (blockIdx.x + it * gridDim.x) / k_splits; m_blk = tile / n_blocks; n_blk = tile % n_blocks; }
   };
   auto k_range = [&](int it, int& kb0, int& kb1) {      // k-blocks [kb0, kb1) of work item `it`
-    if (kResidentW || k_splits == 1) { kb0 = 0; kb1 = num_kb; return; }
+    if (!kTrain || kResidentW || k_splits == 1) { kb0 = 0; kb1 = num_kb; return; }
     const int split = (blockIdx.x + it * gridDim.x) % k_splits;
     kb0 = split * kb_per_split;
     kb1 = min(num_kb, kb0 + kb_per_split);
@@ -312,7 +315,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) mbar_arrive(&tail->tmem_empty[acc]);
       SVOL_GTR(0, it, 2);
 
-      if (out_f32 != nullptr) {
+      if (kTrain && out_f32 != nullptr) {
         // weight-gradient mode: out_f32[row, col] += partial sum of this k slice (no bias / activation / bf16 output).
         // An empty slice (kb0 >= kb1) issued no MMA: its accumulator is stale, nothing may be added.
         int kb0, kb1;
@@ -346,12 +349,47 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (kTrain && ep.out_pre && do_out) {
+        // training forward: keep the pre-activation (second bf16 output through the out_pos tensor map)
+#pragma unroll
+        for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
+          uint4 q[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float* vv = &v[blk * 64 + j * 8];
+            q[j] = make_uint4(pack_bf16x2(vv[0], vv[1]), pack_bf16x2(vv[2], vv[3]), pack_bf16x2(vv[4], vv[5]), pack_bf16x2(vv[6], vv[7]));
+          }
+          block_store_tma(stg, q, &tmOutPos, col0 + blk * 64, slab_row0, lane);
+        }
+      }
       if (ep.act == SVOL_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < COLS_PER_THREAD; ++i) v[i] = fmaxf(v[i], 0.f);
       } else if (ep.act == SVOL_ACT_GELU) {
 #pragma unroll
         for (int i = 0; i < COLS_PER_THREAD; ++i) v[i] = gelu_erf_fast(v[i]);
+      }
+      if (kTrain && ep.dact_src) {
+        // training backward: dX = (dY W) * f'(saved), the activation backward fused into the dgrad GEMM
+        const uint8_t* dbase = reinterpret_cast<const uint8_t*>(ep.dact_src + static_cast<size_t>(slab_row0) * ep.ld_dact + col0);
+#pragma unroll
+        for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
+          uint4 q[8];
+          block_load(stg, q, dbase + blk * 128, static_cast<size_t>(ep.ld_dact) * 2, rows_valid, lane);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float* vv = &v[blk * 64 + j * 8];
+            const float sv[8] = {bf16_lo(q[j].x), bf16_hi(q[j].x), bf16_lo(q[j].y), bf16_hi(q[j].y),
+                                 bf16_lo(q[j].z), bf16_hi(q[j].z), bf16_lo(q[j].w), bf16_hi(q[j].w)};
+            if (ep.dact_mode == SVOL_ACT_GELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) vv[e] *= gelu_grad_fast(sv[e]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) vv[e] = sv[e] > 0.f ? vv[e] : 0.f;
+            }
+          }
+        }
       }
       SVOL_GTR(0, it, 3);
       if (ep.residual) {
@@ -487,14 +525,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <bool kResidentW>
+template <bool kResidentW, bool kTrain>
 static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                           const CUtensorMap& tmOutPos, const CUtensorMap& tmA2, int k_splits, cudaStream_t stream) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<kResidentW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<kResidentW, kTrain>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return svol_fail_cuda(e, "gemm: cudaFuncSetAttribute");
     configured = true;
   }
@@ -502,7 +540,7 @@ static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUten
   const int tiles = m_blocks * n_blocks * k_splits;
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (kResidentW) grid = grid / n_blocks * n_blocks;       // every CTA owns one n block
-  gemm_bf16_tc_kernel<kResidentW><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, tmA2, a.ep, a.M, a.N, a.K,
+  gemm_bf16_tc_kernel<kResidentW, kTrain><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, tmA2, a.ep, a.M, a.N, a.K,
                                                                             a.split_block, k_splits, a.out_f32, a.ld_f32);
   return svol_check_launch("gemm_bf16_tc");
 }
@@ -517,6 +555,9 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   if (a.ep.out_vt && (a.N - split * BN) != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: transposed-V store needs 256 columns");
   if (a.ep.pos_theta && a.N != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: in-epilogue sine positions need N == 256");
   if (a.ep.out_pos && !a.ep.pos && !a.ep.pos_theta) return svol_fail(SVOL_ERR_NULL, "gemm: out_pos needs pos or pos_theta");
+  if (a.ep.out_pre && a.ep.out_pos) return svol_fail(SVOL_ERR_SHAPE, "gemm: out_pre and out_pos are mutually exclusive");
+  if (a.ep.dact_src && (a.ep.ld_dact % 8 != 0 || (a.ep.dact_mode != SVOL_ACT_GELU && a.ep.dact_mode != SVOL_ACT_RELU)))
+    return svol_fail(SVOL_ERR_SHAPE, "gemm: dact_src needs ld_dact % 8 == 0 and dact_mode RELU | GELU");
   CUtensorMap tmA, tmB;
   int rc = make_tensor_map_2d(&tmA, a.A, a.K, a.M, a.lda, BK, BM, 128);
   if (rc) return rc;
@@ -533,6 +574,9 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   if (a.ep.out_pos) {
     rc = make_tensor_map_2d(&tmOutPos, a.ep.out_pos, n_out, a.M, a.ep.ld_out, 64, 32, 128);
     if (rc) return rc;
+  } else if (a.ep.out_pre) {
+    rc = make_tensor_map_2d(&tmOutPos, a.ep.out_pre, n_out, a.M, a.ep.ld_out, 64, 32, 128);
+    if (rc) return rc;
   }
   if (split > 0) {
     rc = make_tensor_map_2d(&tmA2, a.A2, a.K, a.M, a.lda2, BK, BM, 128);
@@ -544,7 +588,8 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   if (a.out_f32 != nullptr) {
     // accumulate-into-fp32 mode (weight gradients): split the contraction so that ~all SMs get a work item, at
     // least 4 k-blocks per slice
-    if (a.ep.bias || a.ep.act != SVOL_ACT_NONE || a.ep.residual || a.ep.ln_weight || a.ep.out || a.ep.out_pos || a.ep.out_vt || split)
+    if (a.ep.bias || a.ep.act != SVOL_ACT_NONE || a.ep.residual || a.ep.ln_weight || a.ep.out || a.ep.out_pos || a.ep.out_vt || split ||
+        a.ep.out_pre || a.ep.dact_src)
       return svol_fail(SVOL_ERR_SHAPE, "gemm: out_f32 (accumulating fp32 output) excludes every other epilogue option");
     if (a.ld_f32 < a.N || a.ld_f32 % 4 != 0 || (reinterpret_cast<uintptr_t>(a.out_f32) & 15))
       return svol_fail(SVOL_ERR_SHAPE, "gemm: out_f32 must be 16-byte aligned with ld_f32 >= N, ld_f32 % 4 == 0");
@@ -555,8 +600,12 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
     const int per = (num_kb + k_splits - 1) / k_splits;
     k_splits = (num_kb + per - 1) / per;                     // no empty slices
   }
-  return resident ? launch_variant<true>(a, tmA, tmB, tmOut, tmOutPos, tmA2, k_splits, stream)
-                  : launch_variant<false>(a, tmA, tmB, tmOut, tmOutPos, tmA2, k_splits, stream);
+  const bool train = a.out_f32 != nullptr || a.ep.out_pre != nullptr || a.ep.dact_src != nullptr;
+  if (train)
+    return resident ? launch_variant<true, true>(a, tmA, tmB, tmOut, tmOutPos, tmA2, k_splits, stream)
+                    : launch_variant<false, true>(a, tmA, tmB, tmOut, tmOutPos, tmA2, k_splits, stream);
+  return resident ? launch_variant<true, false>(a, tmA, tmB, tmOut, tmOutPos, tmA2, k_splits, stream)
+                  : launch_variant<false, false>(a, tmA, tmB, tmOut, tmOutPos, tmA2, k_splits, stream);
 }
 
 }  // namespace svol

@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) gemm_plain_kernel(const __nv_bfloat16* __
 int launch_gemm_bf16_plain(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0 || a.K % 8 != 0 || a.ldw % 8 != 0)
     return svol_fail(SVOL_ERR_SHAPE, "gemm_plain: K and ldw must be multiples of 8");
+  if (a.out_f32 || a.ep.out_pre || a.ep.dact_src)
+    return svol_fail(SVOL_ERR_SHAPE, "gemm_plain: the training-step options (out_f32, out_pre, dact_src) exist on the tcgen05 kernel only");
   const size_t smem = 8 * static_cast<size_t>(a.K + a.N) * sizeof(float);
   if (smem > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "gemm_plain: K + N too large");
   static size_t configured = 0;

@@ -713,6 +713,31 @@ int launch_accum_bf16(const svol_bf16* src, float* dst, long long n, float scale
 }
 
 // ---------------------------------------------------------------------------------------------
+// Weight packing: every bf16 / fp32 operand copy the launch plans read (projection weights with the query rows
+// pre-scaled by log2(e)/sqrt(dh), transposed weights for the dgrad GEMMs, biases) is refreshed from the fp32
+// parameters in ONE launch driven by a job table -- after an optimizer step the per-parameter torch casts /
+// concatenations this replaces cost more GPU time than the AdamW update itself.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_weights_kernel(const svol_pack_job* __restrict__ jobs) {
+  const svol_pack_job j = jobs[blockIdx.y];
+  const long long n = static_cast<long long>(j.rows) * j.cols;
+  const bool to_bf16 = j.flags & SVOL_PACK_BF16, transpose = j.flags & SVOL_PACK_TRANSPOSE;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    const int r = static_cast<int>(i / j.cols), c = static_cast<int>(i - static_cast<long long>(r) * j.cols);
+    float v = j.src[i];
+    if (r < j.scaled_rows) v *= j.scale;
+    const long long o = transpose ? static_cast<long long>(c) * j.rows + r : i;
+    if (to_bf16) reinterpret_cast<__nv_bfloat16*>(j.dst)[o] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(j.dst)[o] = v;
+  }
+}
+int launch_pack_weights(const svol_pack_job* jobs, int n_jobs, cudaStream_t stream) {
+  if (n_jobs <= 0) return svol_fail(SVOL_ERR_SHAPE, "pack_weights: n_jobs > 0");
+  pack_weights_kernel<<<dim3(64, n_jobs), 256, 0, stream>>>(jobs);
+  return svol_check_launch("pack_weights");
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fused AdamW over one flat fp32 parameter buffer (torch.optim.AdamW semantics, train.py:71-78):
 //   p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 // grad_scale multiplies g first (1 / world_size after a sum all-reduce).

@@ -91,6 +91,58 @@ class _Plan:
             main.wait_stream(st)                                   # join
 
 
+class WeightPacker:
+    """Keeps the packed operand copies of a module's parameters (bf16 GEMM operands, scaled / sliced / transposed
+    views, fp32 biases) in persistent buffers and refreshes ALL of them with one ``svol_pack_weights`` launch.
+
+    ``put(name, param, dtype, row0, rows, scaled_rows, scale, transpose)`` declares ``dst = param[row0:row0+rows]``
+    (rows of a [out, in] weight, or elements of a bias) with the first ``scaled_rows`` rows multiplied by ``scale``,
+    cast to ``dtype`` and optionally transposed.  Buffers keep their addresses across refreshes (plans and CUDA graphs
+    stay valid); the job table is re-uploaded only when a parameter's storage moved."""
+
+    def __init__(self):
+        self.tensors: Dict[str, torch.Tensor] = {}
+        self._jobs: List[tuple] = []
+        self._table = None
+        self._table_key = None
+        self._moved = False
+        self._dev = None
+
+    def begin(self, device):
+        self._jobs, self._moved, self._dev = [], False, device
+
+    def put(self, name, param, dtype, row0=0, rows=None, scaled_rows=0, scale=1.0, transpose=False):
+        t = param.detach()
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise NotImplementedError("svol_b200 packs contiguous fp32 parameters")
+        cols = t.shape[1] if t.dim() == 2 else 1
+        total = t.shape[0]
+        rows = total - row0 if rows is None else rows
+        shape = ((cols, rows) if transpose else (rows, cols)) if t.dim() == 2 else (rows,)
+        old = self.tensors.get(name)
+        if old is None or tuple(old.shape) != shape or old.dtype != dtype or old.device != t.device:
+            self.tensors[name] = torch.empty(shape, device=t.device, dtype=dtype)
+            self._moved = True
+        flags = (_lib.PACK_BF16 if dtype == torch.bfloat16 else 0) | (_lib.PACK_TRANSPOSE if transpose else 0)
+        self._jobs.append((t.data_ptr() + row0 * cols * 4, self.tensors[name].data_ptr(), rows, cols, scaled_rows, flags, float(scale)))
+
+    def end(self) -> bool:
+        """Uploads the job table if it changed and runs the packing launch.  Returns True if any buffer moved."""
+        key = tuple(self._jobs)
+        if key != self._table_key:
+            arr = (_lib.PackJob * len(self._jobs))()
+            for i, (src, dst, rows, cols, sr, flags, scale) in enumerate(self._jobs):
+                arr[i].src, arr[i].dst, arr[i].rows, arr[i].cols = src, dst, rows, cols
+                arr[i].scaled_rows, arr[i].flags, arr[i].scale = sr, flags, scale
+            host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+            self._table = host.to(self._dev)
+            self._table_key = key
+        if self._dev.type != "cuda":
+            raise RuntimeError("svol_b200 packs weights on a CUDA device; there is no CPU fallback")
+        _lib.check(_lib.get_lib().svol_pack_weights(self._table.data_ptr(), len(self._jobs), _lib.stream_ptr()), "pack_weights")
+        return self._moved
+
+
 class HeadEngine:
     def __init__(self, module, use_graph: bool = True):
         self.module = module
@@ -98,6 +150,7 @@ class HeadEngine:
         self.plain = os.environ.get("SVOL_B200_PLAIN", "0") == "1"   # debug: SIMT kernels instead of tcgen05
         self._w: Dict[str, torch.Tensor] = {}
         self._wstate = None
+        self._packer = WeightPacker()
         self._plans: Dict[Tuple[int, int, int], _Plan] = {}
         self._side = None                  # (query, input) capture streams: the forked branches of the forward graph
         self.launches_per_forward = 0
@@ -109,23 +162,13 @@ class HeadEngine:
     @torch.no_grad()
     def _pack_weights(self) -> None:
         m = self.module
-        dev = next(m.parameters()).device
         d = m.transformer.d_model
         if d != 256 or m.transformer.nhead != 8:
             raise NotImplementedError("svol_b200 kernels are built for hidden_dim 256 / 8 heads (head_dim 32)")
         qscale = math.log2(math.e) / math.sqrt(HEAD_DIM)
-        new: Dict[str, torch.Tensor] = {}
-
-        def put(name, t, dtype):
-            t = t.detach().to(device=dev, dtype=dtype).contiguous()
-            old = self._w.get(name)
-            if old is not None and old.shape == t.shape and old.dtype == t.dtype and old.device == t.device:
-                old.copy_(t)            # keep the address: plans and graphs stay valid
-                new[name] = old
-            else:
-                new[name] = t.clone()
-                self._plans.clear()
-
+        pk = self._packer
+        pk.begin(next(m.parameters()).device)
+        put = pk.put
         bf, f32 = torch.bfloat16, torch.float32
         for which in ("video", "sketch"):
             seq = getattr(m, f"input_{which}_proj")
@@ -142,27 +185,28 @@ class HeadEngine:
             put(p + "gate.b", g.in_proj_bias, f32)
             for tag, att in (("sa", layer.content_self_attn), ("ta", layer.token_self_attn)):
                 W, b = att.in_proj_weight, att.in_proj_bias
-                put(p + tag + ".wqk", torch.cat([W[:d] * qscale, W[d:2 * d]]), bf)
-                put(p + tag + ".bqk", torch.cat([b[:d] * qscale, b[d:2 * d]]), f32)
-                put(p + tag + ".wv", W[2 * d:], bf)
-                put(p + tag + ".bv", b[2 * d:], f32)
+                # rows [0, d) = q (pre-scaled by log2(e)/sqrt(d_head): the attention softmax is a bare ex2), [d, 2d) = k
+                put(p + tag + ".wqk", W, bf, rows=2 * d, scaled_rows=d, scale=qscale)
+                put(p + tag + ".bqk", b, f32, rows=2 * d, scaled_rows=d, scale=qscale)
+                put(p + tag + ".wv", W, bf, row0=2 * d)
+                put(p + tag + ".bv", b, f32, row0=2 * d)
                 put(p + tag + ".wo", att.out_proj.weight, bf)
                 put(p + tag + ".bo", att.out_proj.bias, f32)
                 # one launch computes q | k from x + pos and v from x (split GEMM): [q * scale ; k ; v]
-                put(p + tag + ".wqkv", torch.cat([W[:d] * qscale, W[d:]]), bf)
-                put(p + tag + ".bqkv", torch.cat([b[:d] * qscale, b[d:]]), f32)
+                put(p + tag + ".wqkv", W, bf, scaled_rows=d, scale=qscale)
+                put(p + tag + ".bqkv", b, f32, scaled_rows=d, scale=qscale)
             ca = layer.content_token_cross_attn
             W, b = ca.in_proj_weight, ca.in_proj_bias
-            put(p + "ca.wq", W[:d] * qscale, bf)
-            put(p + "ca.bq", b[:d] * qscale, f32)
-            put(p + "ca.wk", W[d:2 * d], bf)
-            put(p + "ca.bk", b[d:2 * d], f32)
-            put(p + "ca.wv", W[2 * d:], bf)
-            put(p + "ca.bv", b[2 * d:], f32)
+            put(p + "ca.wq", W, bf, rows=d, scaled_rows=d, scale=qscale)
+            put(p + "ca.bq", b, f32, rows=d, scaled_rows=d, scale=qscale)
+            put(p + "ca.wk", W, bf, row0=d, rows=d)
+            put(p + "ca.bk", b, f32, row0=d, rows=d)
+            put(p + "ca.wv", W, bf, row0=2 * d)
+            put(p + "ca.bv", b, f32, row0=2 * d)
             put(p + "ca.wo", ca.out_proj.weight, bf)
             put(p + "ca.bo", ca.out_proj.bias, f32)
-            put(p + "ca.wkv", W[d:], bf)                 # k from mem + pos, v from mem: one split launch
-            put(p + "ca.bkv", b[d:], f32)
+            put(p + "ca.wkv", W, bf, row0=d)             # k from mem + pos, v from mem: one split launch
+            put(p + "ca.bkv", b, f32, row0=d)
             for n in range(1, 7):
                 norm = getattr(layer, f"norm{n}")
                 put(p + f"n{n}.w", norm.weight, f32)
@@ -179,7 +223,9 @@ class HeadEngine:
         put("box.2.b", m.bbox_embed.layers[2].bias, f32)
         put("cls.w", m.class_embed.weight, f32)
         put("cls.b", m.class_embed.bias, f32)
-        self._w = new
+        if pk.end():
+            self._plans.clear()                 # a packed buffer moved: recorded plans hold stale addresses
+        self._w = pk.tensors
 
     def _weights(self) -> Dict[str, torch.Tensor]:
         st = self._param_state()

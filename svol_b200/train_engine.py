@@ -5,8 +5,8 @@ Differences from the inference plan (``engine.py``):
 
   * every LayerNorm input ``z`` (the residual sum in front of norm1..norm6) is stored, so the projections run
     without the fused LayerNorm epilogue and ``svol_layernorm_bf16`` follows them;
-  * the FFN runs unfused (fc1 -> stored pre-activation -> GELU -> fc2): the fused kernel of ``ffn_tc.cu`` keeps the
-    2048-wide hidden activation on the SM, the backward needs it (``gelu'``, ``dW2``);
+  * the FFN runs as two GEMMs (fc1 stores its pre-activation AND GELU(pre) from one epilogue, then fc2): the fused
+    kernel of ``ffn_tc.cu`` keeps the 2048-wide hidden activation on the SM, the backward needs it (``gelu'``, ``dW2``);
   * q, k, v projections are three launches that also write the per-head transposed copies (Q^T, K^T, V^T) the
     attention backward's MMAs take as K-major operands; the attention forward stores each row's log-sum-exp.
 
@@ -24,13 +24,14 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List
 
 import torch
 
 from . import _lib
 from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, AttnArgs, AttnBwdArgs, GemmArgs
-from .engine import HEAD_DIM, LN_EPS, _Plan, _round_up
+from .engine import HEAD_DIM, LN_EPS, WeightPacker, _Plan, _round_up
 
 P = _lib.ptr
 
@@ -44,6 +45,9 @@ class TrainEngine:
         self.head = module.engine
         self._wt: Dict[str, torch.Tensor] = {}
         self._wt_state = None
+        self._packer = WeightPacker()
+        # both plans replay as CUDA graphs after one eager warm-up run per shape (SVOL_B200_TRAIN_GRAPH=0: eager launches)
+        self.use_graph = os.environ.get("SVOL_B200_TRAIN_GRAPH", "1") != "0"
         self._plans: Dict[tuple, dict] = {}
         self._params: List[torch.nn.Parameter] = []
         self.grad_flat: torch.Tensor = None
@@ -77,17 +81,11 @@ class TrainEngine:
         m = self.module
         d = m.transformer.d_model
         bf = torch.bfloat16
-        new: Dict[str, torch.Tensor] = {}
+        pk = self._packer
+        pk.begin(next(m.parameters()).device)
 
-        def put(name, t):
-            t = t.detach().to(dtype=bf).t().contiguous()
-            old = self._wt.get(name)
-            if old is not None and old.shape == t.shape and old.device == t.device:
-                old.copy_(t)
-                new[name] = old
-            else:
-                new[name] = t
-                self._plans.clear()
+        def put(name, param, row0=0, rows=None):
+            pk.put(name, param, bf, row0=row0, rows=rows, transpose=True)
 
         for i, lin in enumerate(m.input_video_proj):
             put(f"in_video.{i}.wT", lin.net[1].weight)
@@ -95,17 +93,19 @@ class TrainEngine:
             p = f"l{li}."
             for tag, att in (("sa", layer.content_self_attn), ("ta", layer.token_self_attn), ("ca", layer.content_token_cross_attn)):
                 W = att.in_proj_weight
-                put(p + tag + ".wqkT", W[:2 * d])          # [d, 2d]: d(x+pos) = [dq | dk] [Wq ; Wk]
-                put(p + tag + ".wqT", W[:d])
-                put(p + tag + ".wkT", W[d:2 * d])
-                put(p + tag + ".wvT", W[2 * d:])
+                put(p + tag + ".wqkT", W, rows=2 * d)      # [d, 2d]: d(x+pos) = [dq | dk] [Wq ; Wk]
+                put(p + tag + ".wqT", W, rows=d)
+                put(p + tag + ".wkT", W, row0=d, rows=d)
+                put(p + tag + ".wvT", W, row0=2 * d)
                 put(p + tag + ".woT", att.out_proj.weight)
             for tag, mlp in (("mlp1", layer.mlp1), ("mlp2", layer.mlp2)):
                 put(p + tag + ".w1T", mlp.fc1.weight)      # [d, ff]
                 put(p + tag + ".w2T", mlp.fc2.weight)      # [ff, d]
         for i in range(2):
             put(f"box.{i}.wT", m.bbox_embed.layers[i].weight)
-        self._wt = new
+        if pk.end():
+            self._plans.clear()
+        self._wt = pk.tensors
         self._wt_state = st
         return w
 
@@ -138,7 +138,7 @@ class TrainEngine:
 
         # ---------------------------------------------------------------- call recorders
         def gemm(plan, name, A, W, bias=None, out=None, act=ACT_NONE, residual=None, out_pos=None, pos_t=None, pos_mod=0,
-                 theta_t=None, out_vt=None, vt_len=0, vt_pitch=0, out_f32=None):
+                 theta_t=None, out_vt=None, vt_len=0, vt_pitch=0, out_f32=None, out_pre=None, dact=None, dact_mode=0):
             a = GemmArgs()
             a.A, a.W = P(A), P(W)
             a.M, a.K = A.shape
@@ -156,6 +156,10 @@ class TrainEngine:
                 e.pos, e.ld_pos, e.pos_row_mod = P(pos_t), pos_t.stride(0), pos_mod
             if out_vt is not None:
                 e.out_vt, e.vt_len, e.vt_pitch = P(out_vt), vt_len, vt_pitch
+            if out_pre is not None:                      # fc1 keeps its pre-activation next to GELU(pre)
+                e.out_pre = P(out_pre)
+            if dact is not None:                         # activation backward fused into the dgrad epilogue
+                e.dact_src, e.ld_dact, e.dact_mode = P(dact), dact.stride(0), dact_mode
             if out_f32 is not None:                      # weight-gradient mode: fp32 accumulation, split contraction
                 assert out_f32.is_contiguous() and out_f32.shape == (a.M, a.N), name
                 a.out_f32, a.ld_f32 = P(out_f32), out_f32.stride(0)
@@ -203,7 +207,8 @@ class TrainEngine:
                 rp = _round_up(rows, 64)
                 scratch[rows] = (torch.zeros(cols * rp, device=dev, dtype=bf), torch.zeros(cols * rp, device=dev, dtype=bf), cols)
 
-        def linear_bwd(name, dY, X, weight_grad, bias_grad, wT=None, dX=None, residual=None, out_vt=None, vt_len=0, vt_pitch=0):
+        def linear_bwd(name, dY, X, weight_grad, bias_grad, wT=None, dX=None, residual=None, out_vt=None, vt_len=0, vt_pitch=0,
+                       dact=None, dact_mode=0):
             """dY [R, N_out], X [R, K_in] (bf16).  weight_grad [N_out, K_in] / bias_grad [N_out] fp32 views (accumulated).
             Optional dgrad dX = dY W (+ residual), optionally also stored per-head transposed."""
             rows, n_out = dY.shape
@@ -216,7 +221,8 @@ class TrainEngine:
             call(bwd, name + ".XT", lib.svol_transpose_bf16, P(X), X.stride(0), rows, k_in, P(tB), rp, None)
             gemm(bwd, name + ".wgrad", tA, tB, out_f32=weight_grad)
             if dX is not None or out_vt is not None:
-                gemm(bwd, name + ".dgrad", dY, wT, out=dX, residual=residual, out_vt=out_vt, vt_len=vt_len, vt_pitch=vt_pitch)
+                gemm(bwd, name + ".dgrad", dY, wT, out=dX, residual=residual, out_vt=out_vt, vt_len=vt_len, vt_pitch=vt_pitch,
+                     dact=dact, dact_mode=dact_mode)
 
         def bcall(name, fn, *args):
             call(bwd, name, fn, *args)
@@ -283,8 +289,7 @@ class TrainEngine:
             gemm(fwd, p + "sa_out", s["ao"], w[p + "sa.wo"], w[p + "sa.bo"], out=s["z2"], residual=s["mem"])
             ln(p + "n2", s["z2"], w[p + "n2.w"], w[p + "n2.b"], s["mem2"])
             sb("pre1", (M, ff)); sb("hid1", (M, ff))
-            gemm(fwd, p + "ffn1_up", s["mem2"], w[p + "mlp1.w1"], w[p + "mlp1.b1"], out=s["pre1"])
-            call(fwd, p + "ffn1_gelu", lib.svol_gelu_bf16, P(s["pre1"]), P(s["hid1"]), M * ff)
+            gemm(fwd, p + "ffn1_up", s["mem2"], w[p + "mlp1.w1"], w[p + "mlp1.b1"], out=s["hid1"], act=ACT_GELU, out_pre=s["pre1"])
             gemm(fwd, p + "ffn1_down", s["hid1"], w[p + "mlp1.w2"], w[p + "mlp1.b2"], out=s["z3"], residual=s["mem2"])
             Xn, Xpn = buf(f"X{li + 1}", (M, d), bf), buf(f"Xp{li + 1}", (M, d), bf)
             layers_in_X.append(Xn); layers_in_Xp.append(Xpn)
@@ -315,8 +320,7 @@ class TrainEngine:
             gemm(fwd, p + "ca_out", s["ac"], w[p + "ca.wo"], w[p + "ca.bo"], out=s["z5"], residual=s["o1"])
             ln(p + "n5", s["z5"], w[p + "n5.w"], w[p + "n5.b"], s["o2"])
             sb("pre2", (MQ, ff)); sb("hid2", (MQ, ff))
-            gemm(fwd, p + "ffn2_up", s["o2"], w[p + "mlp2.w1"], w[p + "mlp2.b1"], out=s["pre2"])
-            call(fwd, p + "ffn2_gelu", lib.svol_gelu_bf16, P(s["pre2"]), P(s["hid2"]), MQ * ff)
+            gemm(fwd, p + "ffn2_up", s["o2"], w[p + "mlp2.w1"], w[p + "mlp2.b1"], out=s["hid2"], act=ACT_GELU, out_pre=s["pre2"])
             gemm(fwd, p + "ffn2_down", s["hid2"], w[p + "mlp2.w2"], w[p + "mlp2.b2"], out=s["z6"], residual=s["o2"])
             ln(p + "n6", s["z6"], w[p + "n6.w"], w[p + "n6.b"], hs[li], y_pos=s["outp"], pos_t=w["query_embed"], mod=Q)
             out_cur, outp_cur = hs[li], s["outp"]
@@ -357,8 +361,7 @@ class TrainEngine:
         bcall("heads_bwd", lib.svol_heads_backward, P(hs_all), P(h2), P(w["cls.w"]), P(w["box.2.w"]), P(boxes), P(dlogits), P(dboxes),
               P(dhs_cls), P(dh2), P(G(ce.weight)), P(G(ce.bias)), P(G(be[2].weight)), P(G(be[2].bias)), R, d)
         # dh2 already carries relu'(h2); box1: h2 = relu(h1 W1^T + b1)
-        linear_bwd("box1", dh2, h1, G(be[1].weight), G(be[1].bias), wT=wt["box.1.wT"], dX=dh1)
-        bcall("box0_relu", lib.svol_act_backward, P(dh1), P(h1), P(dh1), R * d, ACT_RELU)
+        linear_bwd("box1", dh2, h1, G(be[1].weight), G(be[1].bias), wT=wt["box.1.wT"], dX=dh1, dact=h1, dact_mode=ACT_RELU)
         # dhs (from the box MLP) + dhs_cls  ->  gR[1] reused as the heads' total gradient w.r.t. hs_all
         dhs_heads = gR[1]
         linear_bwd("box0", dh1, hs_all, G(be[0].weight), G(be[0].bias), wT=wt["box.0.wT"], dX=dhs_heads, residual=dhs_cls)
@@ -376,8 +379,8 @@ class TrainEngine:
             ln_bwd(p + "n6_bwd", s["z6"], dhs_h, w[p + "n6.w"], layer.norm6, dz6, dy2=None if last else dhs_next[0], dy3=None if last else dhs_next[1])
             if not last:       # outp = hs + query_embed is the q/k operand of the next layer's query self-attention
                 bcall(p + "dqe_outp", lib.svol_batch_sum, P(dhs_next[1]), P(dqe), MQ, d, Q)
-            linear_bwd(p + "ffn2_down", dz6, s["hid2"], G(layer.mlp2.fc2.weight), G(layer.mlp2.fc2.bias), wT=wt[p + "mlp2.w2T"], dX=dhid)
-            bcall(p + "ffn2_gelu_bwd", lib.svol_act_backward, P(dhid), P(s["pre2"]), P(dhid), MQ * ff, ACT_GELU)
+            linear_bwd(p + "ffn2_down", dz6, s["hid2"], G(layer.mlp2.fc2.weight), G(layer.mlp2.fc2.bias), wT=wt[p + "mlp2.w2T"], dX=dhid,
+                       dact=s["pre2"], dact_mode=ACT_GELU)          # dhid = (dz6 W2) * gelu'(pre2)
             linear_bwd(p + "ffn2_up", dhid, s["o2"], G(layer.mlp2.fc1.weight), G(layer.mlp2.fc1.bias), wT=wt[p + "mlp2.w1T"], dX=do2,
                        residual=dz6)
             ln_bwd(p + "n5_bwd", s["z5"], do2, w[p + "n5.w"], layer.norm5, dz5)
@@ -424,8 +427,8 @@ class TrainEngine:
             dz3 = gv[0]
             ln_bwd(p + "n3_bwd", s["z3"], dXn, w[p + "n3.w"], layer.norm3, dz3, dy2=None if last else dX_next)
             dmem2 = gv[1]
-            linear_bwd(p + "ffn1_down", dz3, s["hid1"], G(layer.mlp1.fc2.weight), G(layer.mlp1.fc2.bias), wT=wt[p + "mlp1.w2T"], dX=gv_ff)
-            bcall(p + "ffn1_gelu_bwd", lib.svol_act_backward, P(gv_ff), P(s["pre1"]), P(gv_ff), M * ff, ACT_GELU)
+            linear_bwd(p + "ffn1_down", dz3, s["hid1"], G(layer.mlp1.fc2.weight), G(layer.mlp1.fc2.bias), wT=wt[p + "mlp1.w2T"], dX=gv_ff,
+                       dact=s["pre1"], dact_mode=ACT_GELU)
             linear_bwd(p + "ffn1_up", gv_ff, s["mem2"], G(layer.mlp1.fc1.weight), G(layer.mlp1.fc1.bias), wT=wt[p + "mlp1.w1T"], dX=dmem2,
                        residual=dz3)
             dz2, dao = gv[2], gv[3]
@@ -500,9 +503,32 @@ class TrainEngine:
             raise NotImplementedError("svol_b200 supports one sketch token per pair (L_sketch == 1)")
         b["src_sketch"].copy_(src_sketch.reshape(B, -1), non_blocking=True)
         b["src_video_mask"].copy_(src_video_mask, non_blocking=True)
-        plan["fwd"].run(torch.cuda.current_stream().cuda_stream)
+        self._run(plan, "fwd")
         self._last = plan
         return b["logits"], b["boxes"]
+
+    def _run(self, plan: dict, which: str) -> None:
+        """Eager on the first call of a shape (module loading, function attributes), captured on the second,
+        replayed afterwards.  The backward graph includes the zeroing of the gradient buffers."""
+        def body():
+            if which == "bwd":
+                self.grad_flat.zero_()
+                plan["buf"]["dsk1"].zero_()
+            plan[which].run(torch.cuda.current_stream().cuda_stream)
+
+        if not self.use_graph:
+            return body()
+        state = plan.setdefault("graphs", {})
+        if which not in state:
+            state[which] = None                      # warm-up run
+            return body()
+        if state[which] is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                body()
+            state[which] = g
+        state[which].replay()
 
     @torch.no_grad()
     def backward(self, grad_logits: torch.Tensor, grad_boxes: torch.Tensor) -> None:
@@ -511,6 +537,4 @@ class TrainEngine:
         b = plan["buf"]
         b["dlogits"].copy_(grad_logits.reshape(b["dlogits"].shape))
         b["dboxes"].copy_(grad_boxes.reshape(b["dboxes"].shape))
-        self.grad_flat.zero_()
-        b["dsk1"].zero_()
-        plan["bwd"].run(torch.cuda.current_stream().cuda_stream)
+        self._run(plan, "bwd")

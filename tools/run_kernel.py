@@ -19,7 +19,22 @@ if os.environ.get("SVOL_CONFIG") == "C4":      # long clip: T=128 -> L=6272, Q=1
 g = torch.Generator(device="cpu").manual_seed(0)
 rnd = lambda *s: torch.randn(*s, generator=g)
 
-if which.startswith("attn"):
+if which.startswith("attn_bwd"):
+    # attention backward (delta + dQ + dK/dV kernels) at the video self-attention / cross-attention shapes
+    Lq, Lk = (L, L) if which == "attn_bwd_self" else (Q, L)
+    Lqp, Lkp = (Lq + 7) // 8 * 8, (Lk + 7) // 8 * 8
+
+    def head_t(x, n, npad):
+        out = torch.zeros(B * d, npad, dtype=torch.bfloat16, device=dev)
+        out.view(B, d, npad)[:, :, :n] = x.view(B, n, d).transpose(1, 2)
+        return out
+    q = (rnd(B * Lq, d) * math.log2(math.e) / math.sqrt(32)).to(torch.bfloat16).to(dev)
+    k, v = rnd(B * Lk, d).to(torch.bfloat16).to(dev), rnd(B * Lk, d).to(torch.bfloat16).to(dev)
+    d_o = (rnd(B * Lq, d) * 0.1).to(torch.bfloat16).to(dev)
+    o, lse = ops.attention_train(q, k, head_t(v, Lk, Lkp), B, H, Lq, Lk)
+    kt, qt, dot = head_t(k, Lk, Lkp), head_t(q, Lq, Lqp), head_t(d_o, Lq, Lqp)
+    fn = lambda: ops.attention_backward(q, k, v, kt, qt, o, d_o, dot, lse, B, H, Lq, Lk)
+elif which.startswith("attn"):
     Lq, Lk = (L, L) if which == "attn_self" else ((Q, L) if which == "attn_cross" else (Q, Q))
     q = (rnd(B * Lq, d) * math.log2(math.e) / math.sqrt(32)).to(torch.bfloat16).to(dev)
     k = rnd(B * Lk, d).to(torch.bfloat16).to(dev)
