@@ -371,8 +371,8 @@ TRAIN_METRIC = "sketch-video pairs/s training step"
 def run_train(args):
     """BASELINE configs[2]: SVOL training step, data-parallel (per-GPU batch fixed, weak scaling): forward in train mode,
     PerFrameMatcher + SetCriterion on every decoder layer, backward, ONE NCCL all-reduce of the flat fp32 gradient
-    buffer, fused AdamW (lr 1e-4, wd 1e-4: lib/configs.py:71-78).  The model is the deterministic network
-    (input_dropout = 0, see svol_b200/train_engine.py).  `--impl reference` times the same step through the oracle's
+    buffer, fused AdamW (lr 1e-4, wd 1e-4: lib/configs.py:71-78), input dropout 0.4 as in lib/configs.py:127 (this library's
+    counter-based mask, see svol_b200/train_engine.py).  `--impl reference` times the same step through the oracle's
     autograd (oracle/torch_port.py: the reference's ATen / scipy calls + torch.autograd + torch.optim.AdamW) on the
     host cores, rank 0 only."""
     from dataclasses import replace
@@ -381,10 +381,11 @@ def run_train(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     import torch
     from svol_b200 import synth
-    cfg = replace(synth.CONFIGS[args.config], num_layers=args.layers, input_dropout=0.0)
+    cfg = replace(synth.CONFIGS[args.config], num_layers=args.layers)        # input_dropout = 0.4 (lib/configs.py:127)
     workload = {"workload": f"C3 on {args.config}: SVOL training step (train-mode forward + PerFrameMatcher + SetCriterion on all "
                             f"decoder layers + backward + gradient all-reduce + AdamW), B={args.batch} pairs/GPU, T={cfg.num_frames}, "
-                            f"L={cfg.video_len}, D_in={cfg.input_vid_dim}, Q={cfg.num_queries}, layers={cfg.num_layers}, input_dropout=0",
+                            f"L={cfg.video_len}, D_in={cfg.input_vid_dim}, Q={cfg.num_queries}, layers={cfg.num_layers}, "
+                            f"input_dropout={cfg.input_dropout}",
                 "pairs_per_gpu_per_step": args.batch, "layers": cfg.num_layers,
                 "l2": ">4 GB of saved activations per step: nothing survives in the 126 MB L2 between steps",
                 "parallelism": f"dp{args.gpus}: one NCCL all-reduce of the flat fp32 gradient buffer per step"}
@@ -403,7 +404,7 @@ def run_train(args):
 
         def step():
             grads, _, _ = tp.training_step_gradients(sd, inp["src_sketch"], inp["src_sketch_mask"], inp["src_video"],
-                                                     inp["src_video_mask"], targets, cfg, wd)
+                                                     inp["src_video_mask"], targets, cfg, wd, dropout=(cfg.input_dropout, 1))
             for k, v in sd.items():
                 v.grad = grads.get(k)
             opt.step()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 7
+#define SVOL_ABI_VERSION 8
 
 enum {
   SVOL_OK = 0,
@@ -314,14 +314,27 @@ int svol_postprocess(const float* logits, const float* boxes, float* out, int32_
  * LayerNorm (cross_modal_transformer.py:127,141,143,149,156,158; svanet.py:174-176) when z must be kept. */
 int svol_layernorm_bf16(const svol_bf16* z, const float* weight, const float* bias, svol_bf16* y, svol_bf16* y_pos,
                         const float* pos, int32_t pos_mod, const float* theta, int32_t rows, int32_t cols, float eps,
-                        void* stream);
+                        float drop_p, const int64_t* seed, int32_t site, void* stream);
+
+/* Train-mode Dropout of the input projections (svanet.py:168-170: LayerNorm -> Dropout -> Linear).  The mask is
+ * counter based and stateless: element idx (row * cols + col) of dropout site `site` is kept iff the top 32 bits of
+ * splitmix64(idx + (8 * *seed + site) * 0x9E3779B97F4A7C15) are >= drop_p * 2^32; kept values are scaled by
+ * 1 / (1 - drop_p).  `seed` is a DEVICE scalar (the host bumps it every step; the plans replay as CUDA graphs).  The
+ * backward entry points recompute the mask from the same (seed, site) instead of storing it.  drop_p == 0 disables it.
+ * Dropout variants of the two inference-path LayerNorm entry points: */
+int svol_layernorm_f32_to_bf16_dropout(const float* x, const float* weight, const float* bias, svol_bf16* y, int32_t rows,
+                                       int32_t cols, float eps, float drop_p, const int64_t* seed, int32_t site, void* stream);
+int svol_ln_linear_f32_dropout(const float* x, const float* ln_weight, const float* ln_bias, const float* w, const float* b,
+                               int32_t relu, float* y, int32_t rows, int32_t in_dim, int32_t out_dim, float eps, float drop_p,
+                               const int64_t* seed, int32_t site, void* stream);
 
 /* LayerNorm backward, cols = 256, 512, 768 or 1024.  z = forward input (bf16, or fp32 when z_is_f32), optionally times
  * (1 + att[row]) (the sketch gate, cross_modal_transformer.py:124-126: then dx = dz * (1 + att) and
  * datt[row] = sum_c dz * z_in).  dy = dy1 + dy2 + dy3 (dy2, dy3 optional).  dgamma / dbeta [cols] are accumulated. */
 int svol_layernorm_backward(const void* z, int32_t z_is_f32, const float* att, const svol_bf16* dy1,
                             const svol_bf16* dy2, const svol_bf16* dy3, const float* gamma, svol_bf16* dx, float* datt,
-                            float* dgamma, float* dbeta, int32_t rows, int32_t cols, float eps, void* stream);
+                            float* dgamma, float* dbeta, int32_t rows, int32_t cols, float eps, float drop_p, const int64_t* seed,
+                            int32_t site, void* stream);
 
 /* y = GELU_erf(x) elementwise (F.gelu, cross_modal_transformer.py:163-179), n % 8 == 0. */
 int svol_gelu_bf16(const svol_bf16* x, svol_bf16* y, int64_t n, void* stream);
@@ -382,7 +395,7 @@ int svol_gate_vectors_backward(const float* sketch, const float* in_proj_weight,
 int svol_ln_linear_f32_backward(const float* x, const float* ln_weight, const float* ln_bias, const float* w,
                                 const float* y, const float* dy, int32_t relu, float* dx, float* d_ln_weight,
                                 float* d_ln_bias, float* dw, float* db, int32_t rows, int32_t in_dim, int32_t out_dim,
-                                float eps, void* stream);
+                                float eps, float drop_p, const int64_t* seed, int32_t site, void* stream);
 /* acc[r % mod, :] += g[r, :] summed over rows (bf16 -> fp32, 256 columns): query-embedding gradient. */
 int svol_batch_sum(const svol_bf16* g, float* acc, int32_t rows, int32_t cols, int32_t mod, void* stream);
 /* dst[i] (+)= scale * src[i]: bf16 weight-gradient GEMM output -> fp32 parameter gradient. */

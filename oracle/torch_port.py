@@ -34,11 +34,34 @@ def _lsap(cost: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------------ head forward
-def _input_proj(x, sd, prefix, n):
+def dropout_mask(rows: int, cols: int, p: float, seed: int, site: int) -> np.ndarray:
+    """Host restatement of the CUDA path's counter-based dropout mask (include/svol_b200.h, common.cuh: dropout_keep):
+    element idx = row * cols + col of site `site` is kept iff the top 32 bits of
+    splitmix64(idx + (8 * seed + site) * 0x9E3779B97F4A7C15) are >= p * 2^32.  Returns the fp32 multiplier
+    keep / (1 - p), shape (rows, cols).  (nn.Dropout's own Philox stream cannot be reproduced by another
+    implementation; parity under dropout is checked with THIS mask on both sides.)"""
+    m64 = (1 << 64) - 1
+    key = np.uint64((((8 * seed + site) & m64) * 0x9E3779B97F4A7C15) & m64)
+    with np.errstate(over="ignore"):
+        z = np.arange(rows * cols, dtype=np.uint64) + key
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    thr = np.uint64(min(int(np.float32(p) * np.float32(4294967296.0)), 4294967040))
+    keep = (z >> np.uint64(32)) >= thr
+    scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+    return (keep.astype(np.float32) * scale).reshape(rows, cols)
+
+
+def _input_proj(x, sd, prefix, n, dropout=None, first_site=0):
     """LinearLayer x n: LayerNorm -> Dropout (eval: identity) -> Linear -> ReLU except after the last
-    (svanet.py:49-60,159-181)."""
+    (svanet.py:49-60,159-181).  ``dropout`` = (p, seed): train mode with the CUDA path's mask at sites first_site + i."""
     for i in range(n):
         x = F.layer_norm(x, x.shape[-1:], sd[f"{prefix}.{i}.LayerNorm.weight"], sd[f"{prefix}.{i}.LayerNorm.bias"])
+        if dropout is not None and dropout[0] > 0:
+            rows = x.numel() // x.shape[-1]
+            mask = torch.from_numpy(dropout_mask(rows, x.shape[-1], dropout[0], dropout[1], first_site + i)).to(x.dtype)
+            x = x * mask.reshape(x.shape)
         x = F.linear(x, sd[f"{prefix}.{i}.net.1.weight"], sd[f"{prefix}.{i}.net.1.bias"])
         if i != n - 1:
             x = F.relu(x)
@@ -71,11 +94,12 @@ def _ffn(x, sd, prefix):
 
 @torch.no_grad()
 def svanet_forward(sd: Dict[str, torch.Tensor], src_sketch, src_sketch_mask, src_video, src_video_mask, nheads=8,
-                   n_input_proj=2):
+                   n_input_proj=2, dropout=None):
     """SVANet.forward (svanet.py:65-141) + CrossModalTransformer.forward (cross_modal_transformer.py:27-81,105-160),
-    eval mode, fp32, sequence-major (S,B,d) inside the transformer like the reference."""
-    vid = _input_proj(src_video, sd, "input_video_proj", n_input_proj)
-    skch = _input_proj(src_sketch, sd, "input_sketch_proj", n_input_proj)
+    eval mode, fp32, sequence-major (S,B,d) inside the transformer like the reference.  ``dropout`` = (p, seed): the
+    train-mode input dropout with the CUDA path's mask (sites 0,1 frame tokens; 2,3 sketch)."""
+    vid = _input_proj(src_video, sd, "input_video_proj", n_input_proj, dropout, 0)
+    skch = _input_proj(src_sketch, sd, "input_sketch_proj", n_input_proj, dropout, 2)
     mask_vid = src_video_mask != 0
     pos = _pos_sine(mask_vid, vid.shape[-1]).permute(1, 0, 2)
     pad = ~mask_vid
@@ -219,7 +243,7 @@ def _stack_outputs(out):
 
 
 def head_gradients(sd: Dict[str, torch.Tensor], src_sketch, src_sketch_mask, src_video, src_video_mask, grad_logits,
-                   grad_boxes, nheads=8, n_input_proj=2, dtype=torch.float32):
+                   grad_boxes, nheads=8, n_input_proj=2, dtype=torch.float32, dropout=None):
     """Parameter gradients of the head for given upstream gradients w.r.t. the stacked (logits [NL,B,Q,2], boxes
     [NL,B,Q,4]) of all decoder layers: what ``loss.backward()`` (train.py:229) propagates through
     ``SVANet.forward`` in train mode with the input dropout at 0.  Returns ({name: grad}, logits, boxes)."""
@@ -228,7 +252,7 @@ def head_gradients(sd: Dict[str, torch.Tensor], src_sketch, src_sketch_mask, src
     c = lambda t: torch.as_tensor(t).to(dtype)
     with torch.enable_grad():
         out = svanet_forward.__wrapped__(leaf, c(src_sketch), c(src_sketch_mask), c(src_video), c(src_video_mask), nheads,
-                                         n_input_proj)
+                                         n_input_proj, dropout)
         logits, boxes = _stack_outputs(out)
         grads = torch.autograd.grad([logits, boxes], [leaf[k] for k in names], [c(grad_logits), c(grad_boxes)],
                                     allow_unused=True)
@@ -236,7 +260,7 @@ def head_gradients(sd: Dict[str, torch.Tensor], src_sketch, src_sketch_mask, src
 
 
 def training_step_gradients(sd: Dict[str, torch.Tensor], src_sketch, src_sketch_mask, src_video, src_video_mask, targets,
-                            cfg, weight_dict: Dict[str, float], dtype=torch.float32):
+                            cfg, weight_dict: Dict[str, float], dtype=torch.float32, dropout=None):
     """train.py:222-229: outputs = model(...); loss_dict = criterion(outputs, targets); losses = sum(loss_dict[k] *
     weight_dict[k]); losses.backward().  Returns ({name: grad}, {loss name: value}, matching indices)."""
     names = [k for k, v in sd.items() if v.is_floating_point()]
@@ -244,7 +268,7 @@ def training_step_gradients(sd: Dict[str, torch.Tensor], src_sketch, src_sketch_
     c = lambda t: torch.as_tensor(t).to(dtype)
     with torch.enable_grad():
         out = svanet_forward.__wrapped__(leaf, c(src_sketch), c(src_sketch_mask), c(src_video), c(src_video_mask), cfg.nheads,
-                                         cfg.n_input_proj)
+                                         cfg.n_input_proj, dropout)
         out32 = {"pred_logits": out["pred_logits"].float(), "pred_boxes": out["pred_boxes"].float(),
                  "aux_outputs": [{k: v.float() for k, v in a.items()} for a in out["aux_outputs"]]}
         losses, idx = set_criterion(out32, targets, cfg)

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsvol_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -26,7 +26,7 @@ SYMBOLS = [
     "svol_layernorm_bf16", "svol_layernorm_backward", "svol_gelu_bf16", "svol_act_backward", "svol_transpose_bf16",
     "svol_colsum_bf16", "svol_attention_backward_bf16", "svol_heads_backward", "svol_gate_backward",
     "svol_gate_vectors_backward", "svol_ln_linear_f32_backward", "svol_batch_sum", "svol_accum_bf16", "svol_adamw",
-    "svol_pack_weights",
+    "svol_pack_weights", "svol_layernorm_f32_to_bf16_dropout", "svol_ln_linear_f32_dropout",
 ]
 
 
@@ -138,8 +138,10 @@ def _declare(lib: C.CDLL) -> None:
         "svol_criterion": [C.POINTER(CriterionArgs), _vp],
         "svol_criterion_backward": [C.POINTER(CriterionArgs), _vp, _vp, _vp, _vp],
         "svol_postprocess": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
-        "svol_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _f32, _vp],
-        "svol_layernorm_backward": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
+        "svol_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _f32, _f32, _vp, _i32, _vp],
+        "svol_layernorm_backward": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp, _i32, _vp],
+        "svol_layernorm_f32_to_bf16_dropout": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp, _i32, _vp],
+        "svol_ln_linear_f32_dropout": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _i32, _vp],
         "svol_gelu_bf16": [_vp, _vp, _i64, _vp],
         "svol_act_backward": [_vp, _vp, _vp, _i64, _i32, _vp],
         "svol_transpose_bf16": [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp],
@@ -148,7 +150,7 @@ def _declare(lib: C.CDLL) -> None:
         "svol_heads_backward": [_vp] * 13 + [_i32, _i32, _vp],
         "svol_gate_backward": [_vp] * 8 + [_i32, _i32, _i32, _i32, _vp],
         "svol_gate_vectors_backward": [_vp] * 7 + [_i32, _i32, _i32, _vp],
-        "svol_ln_linear_f32_backward": [_vp] * 6 + [_i32] + [_vp] * 5 + [_i32, _i32, _i32, _f32, _vp],
+        "svol_ln_linear_f32_backward": [_vp] * 6 + [_i32] + [_vp] * 5 + [_i32, _i32, _i32, _f32, _f32, _vp, _i32, _vp],
         "svol_batch_sum": [_vp, _vp, _i32, _i32, _i32, _vp],
         "svol_accum_bf16": [_vp, _vp, _i64, _f32, _i32, _vp],
         "svol_adamw": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp],

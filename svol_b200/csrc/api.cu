@@ -82,9 +82,10 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, int64_t inner, int64_
 }
 
 // rowwise.cu
-int launch_layernorm_f32_to_bf16(const float*, const float*, const float*, svol_bf16*, int, int, float, cudaStream_t);
+int launch_layernorm_f32_to_bf16(const float*, const float*, const float*, svol_bf16*, int, int, float, float, const long long*, int,
+                                 cudaStream_t);
 int launch_ln_linear_f32(const float*, const float*, const float*, const float*, const float*, int, float*, int, int, int,
-                         float, cudaStream_t);
+                         float, float, const long long*, int, cudaStream_t);
 int launch_posenc_sine(const float*, float*, int, int, int, cudaStream_t);
 int launch_posenc_theta(const float*, float*, int, int, cudaStream_t);
 int launch_add_pos_bf16(const float*, const float*, svol_bf16*, int, int, int, cudaStream_t);
@@ -97,9 +98,9 @@ int launch_heads(const svol_bf16*, const svol_bf16*, const float*, const float*,
 int launch_postprocess(const float*, const float*, float*, int32_t*, int, int, int, cudaStream_t);
 // train.cu / attn_bwd_tc.cu
 int launch_layernorm_bf16(const svol_bf16*, const float*, const float*, svol_bf16*, svol_bf16*, const float*, int, const float*,
-                          int, int, float, cudaStream_t);
+                          int, int, float, float, const long long*, int, cudaStream_t);
 int launch_layernorm_backward(const void*, int, const float*, const svol_bf16*, const svol_bf16*, const svol_bf16*, const float*,
-                              svol_bf16*, float*, float*, float*, int, int, float, cudaStream_t);
+                              svol_bf16*, float*, float*, float*, int, int, float, float, const long long*, int, cudaStream_t);
 int launch_gelu_bf16(const svol_bf16*, svol_bf16*, long long, cudaStream_t);
 int launch_act_backward(const svol_bf16*, const svol_bf16*, svol_bf16*, long long, int, cudaStream_t);
 int launch_transpose_bf16(const svol_bf16*, int, int, int, svol_bf16*, int, float*, cudaStream_t);
@@ -112,7 +113,7 @@ int launch_gate_backward(const svol_bf16*, const float*, const float*, const flo
 int launch_gate_vectors_backward(const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int,
                                  cudaStream_t);
 int launch_ln_linear_f32_backward(const float*, const float*, const float*, const float*, const float*, const float*, int, float*,
-                                  float*, float*, float*, float*, int, int, int, float, cudaStream_t);
+                                  float*, float*, float*, float*, int, int, int, float, float, const long long*, int, cudaStream_t);
 int launch_batch_sum(const svol_bf16*, float*, int, int, int, cudaStream_t);
 int launch_accum_bf16(const svol_bf16*, float*, long long, float, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
@@ -181,12 +182,25 @@ int svol_attention_bf16_plain(const svol_attn_args* a, void* stream) {
 int svol_layernorm_f32_to_bf16(const float* x, const float* w, const float* b, svol_bf16* y, int32_t rows,
                                int32_t cols, float eps, void* stream) {
   SVOL_REQUIRE(x); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
-  return launch_layernorm_f32_to_bf16(x, w, b, y, rows, cols, eps, SVOL_STREAM(stream));
+  return launch_layernorm_f32_to_bf16(x, w, b, y, rows, cols, eps, 0.f, nullptr, 0, SVOL_STREAM(stream));
+}
+int svol_layernorm_f32_to_bf16_dropout(const float* x, const float* w, const float* b, svol_bf16* y, int32_t rows, int32_t cols,
+                                       float eps, float drop_p, const int64_t* seed, int32_t site, void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
+  return launch_layernorm_f32_to_bf16(x, w, b, y, rows, cols, eps, drop_p, reinterpret_cast<const long long*>(seed), site,
+                                      SVOL_STREAM(stream));
 }
 int svol_ln_linear_f32(const float* x, const float* lw, const float* lb, const float* w, const float* b, int32_t relu,
                        float* y, int32_t rows, int32_t in_dim, int32_t out_dim, float eps, void* stream) {
   SVOL_REQUIRE(x); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
-  return launch_ln_linear_f32(x, lw, lb, w, b, relu, y, rows, in_dim, out_dim, eps, SVOL_STREAM(stream));
+  return launch_ln_linear_f32(x, lw, lb, w, b, relu, y, rows, in_dim, out_dim, eps, 0.f, nullptr, 0, SVOL_STREAM(stream));
+}
+int svol_ln_linear_f32_dropout(const float* x, const float* lw, const float* lb, const float* w, const float* b, int32_t relu,
+                               float* y, int32_t rows, int32_t in_dim, int32_t out_dim, float eps, float drop_p,
+                               const int64_t* seed, int32_t site, void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
+  return launch_ln_linear_f32(x, lw, lb, w, b, relu, y, rows, in_dim, out_dim, eps, drop_p, reinterpret_cast<const long long*>(seed),
+                              site, SVOL_STREAM(stream));
 }
 int svol_posenc_sine(const float* mask, float* pos, int32_t B, int32_t L, int32_t d, void* stream) {
   SVOL_REQUIRE(mask); SVOL_REQUIRE(pos);
@@ -262,17 +276,19 @@ int svol_postprocess(const float* logits, const float* boxes, float* out, int32_
 
 // ---- training step
 int svol_layernorm_bf16(const svol_bf16* z, const float* w, const float* b, svol_bf16* y, svol_bf16* y_pos, const float* pos,
-                        int32_t pos_mod, const float* theta, int32_t rows, int32_t cols, float eps, void* stream) {
+                        int32_t pos_mod, const float* theta, int32_t rows, int32_t cols, float eps, float drop_p,
+                        const int64_t* seed, int32_t site, void* stream) {
   SVOL_REQUIRE(z); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
-  return launch_layernorm_bf16(z, w, b, y, y_pos, pos, pos_mod, theta, rows, cols, eps, SVOL_STREAM(stream));
+  return launch_layernorm_bf16(z, w, b, y, y_pos, pos, pos_mod, theta, rows, cols, eps, drop_p,
+                               reinterpret_cast<const long long*>(seed), site, SVOL_STREAM(stream));
 }
 int svol_layernorm_backward(const void* z, int32_t z_is_f32, const float* att, const svol_bf16* dy1, const svol_bf16* dy2,
                             const svol_bf16* dy3, const float* gamma, svol_bf16* dx, float* datt, float* dgamma, float* dbeta,
-                            int32_t rows, int32_t cols, float eps, void* stream) {
+                            int32_t rows, int32_t cols, float eps, float drop_p, const int64_t* seed, int32_t site, void* stream) {
   SVOL_REQUIRE(z); SVOL_REQUIRE(dy1); SVOL_REQUIRE(gamma); SVOL_REQUIRE(dgamma); SVOL_REQUIRE(dbeta);
   if (att && !datt) return svol_fail(SVOL_ERR_NULL, "layernorm_backward: att needs datt");
-  return launch_layernorm_backward(z, z_is_f32, att, dy1, dy2, dy3, gamma, dx, datt, dgamma, dbeta, rows, cols, eps,
-                                   SVOL_STREAM(stream));
+  return launch_layernorm_backward(z, z_is_f32, att, dy1, dy2, dy3, gamma, dx, datt, dgamma, dbeta, rows, cols, eps, drop_p,
+                                   reinterpret_cast<const long long*>(seed), site, SVOL_STREAM(stream));
 }
 int svol_gelu_bf16(const svol_bf16* x, svol_bf16* y, int64_t n, void* stream) {
   SVOL_REQUIRE(x); SVOL_REQUIRE(y);
@@ -320,11 +336,12 @@ int svol_gate_vectors_backward(const float* sketch, const float* w, const float*
 }
 int svol_ln_linear_f32_backward(const float* x, const float* lw, const float* lb, const float* w, const float* y,
                                 const float* dy, int32_t relu, float* dx, float* dlw, float* dlb, float* dw, float* db,
-                                int32_t rows, int32_t in_dim, int32_t out_dim, float eps, void* stream) {
+                                int32_t rows, int32_t in_dim, int32_t out_dim, float eps, float drop_p, const int64_t* seed,
+                                int32_t site, void* stream) {
   SVOL_REQUIRE(x); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(w); SVOL_REQUIRE(y); SVOL_REQUIRE(dy); SVOL_REQUIRE(dx);
   SVOL_REQUIRE(dlw); SVOL_REQUIRE(dlb); SVOL_REQUIRE(dw); SVOL_REQUIRE(db);
-  return launch_ln_linear_f32_backward(x, lw, lb, w, y, dy, relu, dx, dlw, dlb, dw, db, rows, in_dim, out_dim, eps,
-                                       SVOL_STREAM(stream));
+  return launch_ln_linear_f32_backward(x, lw, lb, w, y, dy, relu, dx, dlw, dlb, dw, db, rows, in_dim, out_dim, eps, drop_p,
+                                       reinterpret_cast<const long long*>(seed), site, SVOL_STREAM(stream));
 }
 int svol_batch_sum(const svol_bf16* g, float* acc, int32_t rows, int32_t cols, int32_t mod, void* stream) {
   SVOL_REQUIRE(g); SVOL_REQUIRE(acc);

@@ -230,6 +230,29 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(hx, erfv, hx);
 }
 
+// Counter-based dropout mask (train-mode nn.Dropout of the input projections, svanet.py:168-170): element `idx` of
+// dropout site `site` at step seed `seed` is kept iff the top 32 bits of splitmix64(idx + (8 seed + site) * golden)
+// are >= p * 2^32.  Stateless, so the backward recomputes the mask instead of storing it, and a host-side numpy
+// restatement (tests) reproduces it bit for bit.
+struct DropoutCfg {
+  float p;                 // 0: disabled
+  const long long* seed;   // device scalar (changes every step under CUDA-graph replay)
+  int site;
+};
+__device__ __forceinline__ bool dropout_keep(unsigned long long idx, unsigned long long key, uint32_t threshold) {
+  unsigned long long z = idx + key;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return static_cast<uint32_t>(z >> 32) >= threshold;
+}
+__device__ __forceinline__ unsigned long long dropout_key(const DropoutCfg& c) {
+  return (static_cast<unsigned long long>(*c.seed) * 8ull + static_cast<unsigned long long>(c.site)) * 0x9E3779B97F4A7C15ull;
+}
+__device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  return static_cast<uint32_t>(fminf(p * 4294967296.0f, 4294967040.0f));
+}
+
 // d/dx of the erf-form GELU: Phi(x) + x phi(x), with the same erfc construction as gelu_erf_fast (two MUFU ex2).
 __device__ __forceinline__ float gelu_grad_fast(float x) {
   const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);

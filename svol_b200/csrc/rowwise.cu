@@ -12,11 +12,12 @@ namespace svol {
 // ---------------------------------------------------------------------------------------------
 constexpr int LN_MAXV = 8;   // float4 per lane -> cols <= 1024
 
+template <bool kDrop>
 __global__ void __launch_bounds__(256) layernorm_f32_to_bf16_kernel(const float* __restrict__ x,
                                                                      const float* __restrict__ w,
                                                                      const float* __restrict__ b,
                                                                      __nv_bfloat16* __restrict__ y, int rows,
-                                                                     int cols, float eps) {
+                                                                     int cols, float eps, DropoutCfg drop) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -51,20 +52,35 @@ __global__ void __launch_bounds__(256) layernorm_f32_to_bf16_kernel(const float*
     const int idx = i * 32 + lane;
     if (idx < nv) {
       const float4 g = __ldg(w4 + idx), o = __ldg(b4 + idx);
+      float v0 = (buf[i].x - mean) * rstd * g.x + o.x, v1 = (buf[i].y - mean) * rstd * g.y + o.y;
+      float v2 = (buf[i].z - mean) * rstd * g.z + o.z, v3 = (buf[i].w - mean) * rstd * g.w + o.w;
+      if (kDrop) {       // train-mode Dropout after the LayerNorm (svanet.py:168-170)
+        const unsigned long long key = dropout_key(drop), e0 = static_cast<unsigned long long>(row) * cols + idx * 4;
+        const uint32_t thr = dropout_threshold(drop.p);
+        const float sc = 1.0f / (1.0f - drop.p);
+        v0 = dropout_keep(e0, key, thr) ? v0 * sc : 0.f; v1 = dropout_keep(e0 + 1, key, thr) ? v1 * sc : 0.f;
+        v2 = dropout_keep(e0 + 2, key, thr) ? v2 * sc : 0.f; v3 = dropout_keep(e0 + 3, key, thr) ? v3 * sc : 0.f;
+      }
       uint2 q;
-      q.x = pack_bf16x2((buf[i].x - mean) * rstd * g.x + o.x, (buf[i].y - mean) * rstd * g.y + o.y);
-      q.y = pack_bf16x2((buf[i].z - mean) * rstd * g.z + o.z, (buf[i].w - mean) * rstd * g.w + o.w);
+      q.x = pack_bf16x2(v0, v1);
+      q.y = pack_bf16x2(v2, v3);
       yr[idx] = q;
     }
   }
 }
 
 int launch_layernorm_f32_to_bf16(const float* x, const float* w, const float* b, svol_bf16* y, int rows, int cols,
-                                 float eps, cudaStream_t stream) {
+                                 float eps, float drop_p, const long long* seed, int site, cudaStream_t stream) {
   if (cols % 4 != 0 || cols > LN_MAXV * 128 || rows <= 0) return svol_fail(SVOL_ERR_SHAPE, "layernorm: cols % 4 == 0, cols <= 1024");
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !seed)) return svol_fail(SVOL_ERR_SHAPE, "layernorm: 0 <= drop_p < 1, seed required");
   const int wpb = 8;
-  layernorm_f32_to_bf16_kernel<<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
-      x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps);
+  const DropoutCfg drop{drop_p, seed, site};
+  if (drop_p > 0.f)
+    layernorm_f32_to_bf16_kernel<true><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
+        x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, drop);
+  else
+    layernorm_f32_to_bf16_kernel<false><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
+        x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, drop);
   return svol_check_launch("layernorm_f32_to_bf16");
 }
 
@@ -74,7 +90,8 @@ int launch_layernorm_f32_to_bf16(const float* x, const float* w, const float* b,
 __global__ void __launch_bounds__(256) ln_linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ lw,
                                                             const float* __restrict__ lb, const float* __restrict__ w,
                                                             const float* __restrict__ bias, int relu,
-                                                            float* __restrict__ y, int in_dim, int out_dim, float eps) {
+                                                            float* __restrict__ y, int in_dim, int out_dim, float eps,
+                                                            DropoutCfg drop) {
   extern __shared__ float xs[];   // in_dim normalised inputs + 16 scratch
   float* red = xs + in_dim;
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,6 +114,13 @@ __global__ void __launch_bounds__(256) ln_linear_f32_kernel(const float* __restr
   for (int i = 0; i < 8; ++i) tot += red[i];
   const float rstd = rsqrtf(tot / in_dim + eps);
   for (int i = tid; i < in_dim; i += blockDim.x) xs[i] = (xs[i] - mean) * rstd * lw[i] + lb[i];
+  if (drop.p > 0.f) {   // train-mode Dropout between the LayerNorm and the Linear (svanet.py:168-170)
+    const unsigned long long key = dropout_key(drop);
+    const uint32_t thr = dropout_threshold(drop.p);
+    const float sc = 1.0f / (1.0f - drop.p);
+    for (int i = tid; i < in_dim; i += blockDim.x)
+      xs[i] = dropout_keep(static_cast<unsigned long long>(row) * in_dim + i, key, thr) ? xs[i] * sc : 0.f;
+  }
   __syncthreads();
   const int o_end = min(out_dim, static_cast<int>(blockIdx.y + 1) * 32);
   for (int o = blockIdx.y * 32 + warp; o < o_end; o += 8) {
@@ -112,9 +136,12 @@ __global__ void __launch_bounds__(256) ln_linear_f32_kernel(const float* __restr
 }
 
 int launch_ln_linear_f32(const float* x, const float* lw, const float* lb, const float* w, const float* b, int relu,
-                         float* y, int rows, int in_dim, int out_dim, float eps, cudaStream_t stream) {
+                         float* y, int rows, int in_dim, int out_dim, float eps, float drop_p, const long long* seed, int site,
+                         cudaStream_t stream) {
   if (rows <= 0 || in_dim <= 0 || in_dim > 8192) return svol_fail(SVOL_ERR_SHAPE, "ln_linear: bad sizes");
-  ln_linear_f32_kernel<<<dim3(rows, (out_dim + 31) / 32), 256, (in_dim + 16) * sizeof(float), stream>>>(x, lw, lb, w, b, relu, y, in_dim, out_dim, eps);
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !seed)) return svol_fail(SVOL_ERR_SHAPE, "ln_linear: 0 <= drop_p < 1, seed required");
+  const DropoutCfg drop{drop_p, seed, site};
+  ln_linear_f32_kernel<<<dim3(rows, (out_dim + 31) / 32), 256, (in_dim + 16) * sizeof(float), stream>>>(x, lw, lb, w, b, relu, y, in_dim, out_dim, eps, drop);
   return svol_check_launch("ln_linear_f32");
 }
 

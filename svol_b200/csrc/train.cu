@@ -40,7 +40,8 @@ __device__ __forceinline__ void load8_f32(const float* p, float (&v)[8]) {
 __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ w,
                                                              const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
                                                              __nv_bfloat16* __restrict__ y_pos, const float* __restrict__ pos,
-                                                             int pos_mod, const float* __restrict__ theta, int rows, float eps) {
+                                                             int pos_mod, const float* __restrict__ theta, int rows, float eps,
+                                                             DropoutCfg drop) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -59,6 +60,13 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16
   float yv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) yv[i] = (v[i] - mean) * rstd * g[i] + o[i];
+  if (drop.p > 0.f) {     // train-mode Dropout after the LayerNorm (svanet.py:168-170); y_pos is not combined with it
+    const unsigned long long key = dropout_key(drop), e0 = static_cast<unsigned long long>(row) * TD + lane * 8;
+    const uint32_t thr = dropout_threshold(drop.p);
+    const float sc = 1.0f / (1.0f - drop.p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yv[i] = dropout_keep(e0 + i, key, thr) ? yv[i] * sc : 0.f;
+  }
   reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * TD)[lane] = pack8(yv);
   if (y_pos) {
     float pp[8];
@@ -82,13 +90,15 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const __nv_bfloat16
 }
 
 int launch_layernorm_bf16(const svol_bf16* z, const float* w, const float* b, svol_bf16* y, svol_bf16* y_pos,
-                          const float* pos, int pos_mod, const float* theta, int rows, int cols, float eps,
-                          cudaStream_t stream) {
+                          const float* pos, int pos_mod, const float* theta, int rows, int cols, float eps, float drop_p,
+                          const long long* seed, int site, cudaStream_t stream) {
   if (cols != TD || rows <= 0) return svol_fail(SVOL_ERR_SHAPE, "layernorm_bf16: 256 columns only");
   if (y_pos && !pos && !theta) return svol_fail(SVOL_ERR_NULL, "layernorm_bf16: y_pos needs pos or theta");
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && (!seed || y_pos)))
+    return svol_fail(SVOL_ERR_SHAPE, "layernorm_bf16: 0 <= drop_p < 1; dropout needs seed and excludes y_pos");
   layernorm_bf16_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(z), w, b, reinterpret_cast<__nv_bfloat16*>(y),
-      reinterpret_cast<__nv_bfloat16*>(y_pos), pos, pos_mod, theta, rows, eps);
+      reinterpret_cast<__nv_bfloat16*>(y_pos), pos, pos_mod, theta, rows, eps, DropoutCfg{drop_p, seed, site});
   return svol_check_launch("layernorm_bf16");
 }
 
@@ -108,7 +118,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
                                                             const __nv_bfloat16* __restrict__ dy3,
                                                             const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
                                                             float* __restrict__ datt, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int rows, float eps) {
+                                                            float* __restrict__ dbeta, int rows, float eps, DropoutCfg drop) {
   constexpr int COLS = 256 * kV;
   __shared__ float red[8][32 * 8 * kV + 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -139,6 +149,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
         unpack8(__ldg(reinterpret_cast<const uint4*>(dy3 + static_cast<size_t>(row) * COLS) + k * 32 + lane), t);
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[k][i] += t[i];
+      }
+      if (drop.p > 0.f) {      // the forward dropped this LayerNorm's output: dy <- mask * dy / (1 - p), mask recomputed
+        const unsigned long long key = dropout_key(drop), e0 = static_cast<unsigned long long>(row) * COLS + (k * 32 + lane) * 8;
+        const uint32_t thr = dropout_threshold(drop.p);
+        const float dsc = 1.0f / (1.0f - drop.p);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[k][i] = dropout_keep(e0 + i, key, thr) ? d[k][i] * dsc : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += x[k][i];
@@ -202,15 +219,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const void* __restri
 
 int launch_layernorm_backward(const void* z, int z_is_f32, const float* att, const svol_bf16* dy1, const svol_bf16* dy2,
                               const svol_bf16* dy3, const float* gamma, svol_bf16* dx, float* datt, float* dgamma,
-                              float* dbeta, int rows, int cols, float eps, cudaStream_t stream) {
+                              float* dbeta, int rows, int cols, float eps, float drop_p, const long long* seed, int site,
+                              cudaStream_t stream) {
   if (rows <= 0 || cols % 256 != 0 || cols < 256 || cols > 1024)
     return svol_fail(SVOL_ERR_SHAPE, "layernorm_backward: cols must be 256, 512, 768 or 1024");
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !seed)) return svol_fail(SVOL_ERR_SHAPE, "layernorm_backward: 0 <= drop_p < 1, seed required");
+  const DropoutCfg drop{drop_p, seed, site};
   const int grid = min((rows + 7) / 8, sm_count() * 4);
   auto a1 = reinterpret_cast<const __nv_bfloat16*>(dy1);
   auto a2 = reinterpret_cast<const __nv_bfloat16*>(dy2);
   auto a3 = reinterpret_cast<const __nv_bfloat16*>(dy3);
   auto o = reinterpret_cast<__nv_bfloat16*>(dx);
-#define SVOL_LNB(KV, F32) layernorm_bwd_kernel<KV, F32><<<grid, 256, 0, stream>>>(z, att, a1, a2, a3, gamma, o, datt, dgamma, dbeta, rows, eps)
+#define SVOL_LNB(KV, F32) layernorm_bwd_kernel<KV, F32><<<grid, 256, 0, stream>>>(z, att, a1, a2, a3, gamma, o, datt, dgamma, dbeta, rows, eps, drop)
   switch (cols / 256 * 2 + (z_is_f32 ? 1 : 0)) {
     case 2: SVOL_LNB(1, false); break;
     case 3: SVOL_LNB(1, true); break;
@@ -614,7 +634,7 @@ __global__ void __launch_bounds__(256) ln_linear_f32_bwd_w_kernel(const float* _
                                                                   const float* __restrict__ lb, const float* __restrict__ w,
                                                                   const float* __restrict__ y, const float* __restrict__ dy, int relu,
                                                                   float* __restrict__ dxn, float* __restrict__ dw, float* __restrict__ db,
-                                                                  int in_dim, int out_dim, float eps) {
+                                                                  int in_dim, int out_dim, float eps, DropoutCfg drop) {
   extern __shared__ float sm[];     // xhat[in], dyr[32], red[8]
   float* xh = sm;
   float* dyr = xh + in_dim;
@@ -632,8 +652,14 @@ __global__ void __launch_bounds__(256) ln_linear_f32_bwd_w_kernel(const float* _
     dyr[tid] = g;
   }
   __syncthreads();
+  const unsigned long long dkey = drop.p > 0.f ? dropout_key(drop) : 0ull;
+  const uint32_t dthr = dropout_threshold(drop.p);
+  const float dsc = 1.0f / (1.0f - drop.p);
   for (int i = tid; i < in_dim; i += 256) {
-    const float xn = xh[i] * lw[i] + lb[i];
+    // the Linear saw dropout(xn): keep ? xn / (1 - p) : 0 (mask recomputed); its input gradient passes the same mask
+    const float keep = (drop.p > 0.f && !dropout_keep(static_cast<unsigned long long>(row) * in_dim + i, dkey, dthr)) ? 0.f
+                       : (drop.p > 0.f ? dsc : 1.0f);
+    const float xn = (xh[i] * lw[i] + lb[i]) * keep;
     float acc = 0.f;
 #pragma unroll 4
     for (int j = 0; j < 32; ++j) {
@@ -643,7 +669,7 @@ __global__ void __launch_bounds__(256) ln_linear_f32_bwd_w_kernel(const float* _
       acc = fmaf(g, __ldg(w + static_cast<size_t>(o) * in_dim + i), acc);
       if (g != 0.f) atomicAdd(dw + static_cast<size_t>(o) * in_dim + i, g * xn);
     }
-    atomicAdd(dxn + static_cast<size_t>(row) * in_dim + i, acc);
+    atomicAdd(dxn + static_cast<size_t>(row) * in_dim + i, acc * keep);
   }
 }
 
@@ -670,12 +696,13 @@ __global__ void __launch_bounds__(256) ln_linear_f32_bwd_x_kernel(const float* _
 
 int launch_ln_linear_f32_backward(const float* x, const float* lw, const float* lb, const float* w, const float* y, const float* dy,
                                   int relu, float* dx, float* dlw, float* dlb, float* dw, float* db, int rows, int in_dim,
-                                  int out_dim, float eps, cudaStream_t stream) {
+                                  int out_dim, float eps, float drop_p, const long long* seed, int site, cudaStream_t stream) {
   if (rows <= 0 || in_dim <= 0 || out_dim <= 0 || in_dim > 8192) return svol_fail(SVOL_ERR_SHAPE, "ln_linear_backward: bad sizes");
+  if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !seed)) return svol_fail(SVOL_ERR_SHAPE, "ln_linear_backward: 0 <= drop_p < 1, seed required");
   cudaError_t e = cudaMemsetAsync(dx, 0, static_cast<size_t>(rows) * in_dim * sizeof(float), stream);
   if (e != cudaSuccess) return svol_fail_cuda(e, "ln_linear_backward: memset");
   ln_linear_f32_bwd_w_kernel<<<dim3(rows, (out_dim + 31) / 32), 256, (in_dim + 48) * sizeof(float), stream>>>(
-      x, lw, lb, w, y, dy, relu, dx, dw, db, in_dim, out_dim, eps);
+      x, lw, lb, w, y, dy, relu, dx, dw, db, in_dim, out_dim, eps, DropoutCfg{drop_p, seed, site});
   int rc = svol_check_launch("ln_linear_f32_backward (weights)");
   if (rc) return rc;
   ln_linear_f32_bwd_x_kernel<<<rows, 256, (in_dim + 16) * sizeof(float), stream>>>(x, lw, dx, dlw, dlb, in_dim, eps);

@@ -104,22 +104,31 @@ def posenc_theta(mask: torch.Tensor) -> torch.Tensor:
     return theta
 
 
-def layernorm_to_bf16(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+def layernorm_to_bf16(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-5, drop_p: float = 0.0, seed=None,
+                      site: int = 0) -> torch.Tensor:
     _lib.require_device()
     rows, cols = x.shape
     y = torch.empty((rows, cols), device=x.device, dtype=torch.bfloat16)
-    _lib.check(_lib.get_lib().svol_layernorm_f32_to_bf16(_P(x), _P(w), _P(b), _P(y), rows, cols, eps, _lib.stream_ptr()),
-               "layernorm")
+    if drop_p > 0:
+        _lib.check(_lib.get_lib().svol_layernorm_f32_to_bf16_dropout(_P(x), _P(w), _P(b), _P(y), rows, cols, eps, drop_p, _P(seed), site,
+                                                                     _lib.stream_ptr()), "layernorm_dropout")
+    else:
+        _lib.check(_lib.get_lib().svol_layernorm_f32_to_bf16(_P(x), _P(w), _P(b), _P(y), rows, cols, eps, _lib.stream_ptr()),
+                   "layernorm")
     return y
 
 
-def ln_linear_f32(x, ln_w, ln_b, w, b, relu: bool, eps: float = 1e-5) -> torch.Tensor:
+def ln_linear_f32(x, ln_w, ln_b, w, b, relu: bool, eps: float = 1e-5, drop_p: float = 0.0, seed=None, site: int = 0) -> torch.Tensor:
     _lib.require_device()
     rows, in_dim = x.shape
     out_dim = w.shape[0]
     y = torch.empty((rows, out_dim), device=x.device, dtype=torch.float32)
-    _lib.check(_lib.get_lib().svol_ln_linear_f32(_P(x), _P(ln_w), _P(ln_b), _P(w), _P(b), int(relu), _P(y), rows, in_dim,
-                                                 out_dim, eps, _lib.stream_ptr()), "ln_linear")
+    if drop_p > 0:
+        _lib.check(_lib.get_lib().svol_ln_linear_f32_dropout(_P(x), _P(ln_w), _P(ln_b), _P(w), _P(b), int(relu), _P(y), rows, in_dim,
+                                                             out_dim, eps, drop_p, _P(seed), site, _lib.stream_ptr()), "ln_linear_dropout")
+    else:
+        _lib.check(_lib.get_lib().svol_ln_linear_f32(_P(x), _P(ln_w), _P(ln_b), _P(w), _P(b), int(relu), _P(y), rows, in_dim,
+                                                     out_dim, eps, _lib.stream_ptr()), "ln_linear")
     return y
 
 
@@ -206,16 +215,18 @@ def attention_backward(q, k, v, kt, qt, o, d_o, d_ot, lse, B, H, Lq, Lk, key_mas
     return dq, dk, dv
 
 
-def layernorm_bf16(z, w, b, pos=None, pos_mod=0, theta=None, eps: float = 1e-5):
+def layernorm_bf16(z, w, b, pos=None, pos_mod=0, theta=None, eps: float = 1e-5, drop_p: float = 0.0, seed=None, site: int = 0):
+    """``seed``: int64 device tensor of one element (dropout, see include/svol_b200.h)."""
     _lib.require_device()
     y = torch.empty_like(z)
     y_pos = torch.empty_like(z) if (pos is not None or theta is not None) else None
     _lib.check(_lib.get_lib().svol_layernorm_bf16(_P(z), _P(w), _P(b), _P(y), _P(y_pos), _P(pos), pos_mod, _P(theta), z.shape[0],
-                                                  z.shape[1], eps, _lib.stream_ptr()), "layernorm_bf16")
+                                                  z.shape[1], eps, drop_p, _P(seed), site, _lib.stream_ptr()), "layernorm_bf16")
     return y, y_pos
 
 
-def layernorm_backward(z, dys, gamma, att=None, want_dx: bool = True, eps: float = 1e-5):
+def layernorm_backward(z, dys, gamma, att=None, want_dx: bool = True, eps: float = 1e-5, drop_p: float = 0.0, seed=None,
+                       site: int = 0):
     """Returns (dx bf16 | None, datt | None, dgamma, dbeta)."""
     _lib.require_device()
     rows, cols = z.shape
@@ -224,8 +235,8 @@ def layernorm_backward(z, dys, gamma, att=None, want_dx: bool = True, eps: float
     datt = torch.empty(rows, device=z.device, dtype=torch.float32) if att is not None else None
     dg, db = torch.zeros(cols, device=z.device), torch.zeros(cols, device=z.device)
     _lib.check(_lib.get_lib().svol_layernorm_backward(_P(z), int(z.dtype == torch.float32), _P(att), _P(dys[0]), _P(dys[1]), _P(dys[2]),
-                                                      _P(gamma), _P(dx), _P(datt), _P(dg), _P(db), rows, cols, eps,
-                                                      _lib.stream_ptr()), "layernorm_backward")
+                                                      _P(gamma), _P(dx), _P(datt), _P(dg), _P(db), rows, cols, eps, drop_p,
+                                                      _P(seed), site, _lib.stream_ptr()), "layernorm_backward")
     return dx, datt, dg, db
 
 

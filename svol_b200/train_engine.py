@@ -17,8 +17,11 @@ the attention backward is ``attn_bwd_tc.cu``.  Activation gradients are bf16, pa
 flat buffer (``grad_of(param)``), zeroed at the start of every backward.
 
 Dropout: the reference applies ``Dropout(input_dropout)`` after the LayerNorm of each input-projection stage in
-train mode (svanet.py:168-170).  The CUDA training path implements the deterministic network (dropout 0); a model
-built with ``input_dropout > 0`` refuses to train rather than silently dropping the regulariser.
+train mode (svanet.py:168-170: four sites, frame tokens and sketch, two stages each).  The forward kernels apply a
+counter-based mask (splitmix64 of element index, step seed and site; see include/svol_b200.h), the backward kernels
+recompute it from the same seed -- nothing is stored.  The step seed lives in a device scalar that the host bumps
+before every training forward, so the plans still replay as CUDA graphs.  The random stream is this library's own
+(torch's Philox stream cannot be reproduced); parity tests rebuild the masks on the host from the same hash.
 """
 from __future__ import annotations
 
@@ -48,6 +51,9 @@ class TrainEngine:
         self._packer = WeightPacker()
         # both plans replay as CUDA graphs after one eager warm-up run per shape (SVOL_B200_TRAIN_GRAPH=0: eager launches)
         self.use_graph = os.environ.get("SVOL_B200_TRAIN_GRAPH", "1") != "0"
+        self.seed_base = int(torch.initial_seed()) & 0x3FFFFFFF      # dropout stream; step k uses seed_base + k
+        self.step_index = 0
+        self.last_seed = None
         self._plans: Dict[tuple, dict] = {}
         self._params: List[torch.nn.Parameter] = []
         self.grad_flat: torch.Tensor = None
@@ -169,13 +175,17 @@ class TrainEngine:
         def call(plan, name, fn, *args):
             plan.calls.append((name, fn, args))
 
-        def ln(name, z, g, b_, y, y_pos=None, pos_t=None, mod=0, theta_t=None):
-            call(fwd, name, lib.svol_layernorm_bf16, P(z), P(g), P(b_), P(y), P(y_pos), P(pos_t), mod, P(theta_t), z.shape[0], d,
-                 LN_EPS)
+        drop_p = float(getattr(m, "input_dropout", 0.0))
+        seed = buf("seed", (1,), torch.int64, fill=0)
 
-        def ln_bwd(name, z, dy1, gamma, norm, dx, dy2=None, dy3=None, att=None, datt=None, z_f32=False, cols=256):
+        def ln(name, z, g, b_, y, y_pos=None, pos_t=None, mod=0, theta_t=None, site=None):
+            call(fwd, name, lib.svol_layernorm_bf16, P(z), P(g), P(b_), P(y), P(y_pos), P(pos_t), mod, P(theta_t), z.shape[0], d,
+                 LN_EPS, drop_p if site is not None else 0.0, P(seed), site or 0)
+
+        def ln_bwd(name, z, dy1, gamma, norm, dx, dy2=None, dy3=None, att=None, datt=None, z_f32=False, cols=256, site=None):
             call(bwd, name, lib.svol_layernorm_backward, P(z), int(z_f32), P(att), P(dy1), P(dy2), P(dy3), P(gamma),
-                 P(dx), P(datt), P(G(norm.weight)), P(G(norm.bias)), dy1.shape[0], cols, LN_EPS)
+                 P(dx), P(datt), P(G(norm.weight)), P(G(norm.bias)), dy1.shape[0], cols, LN_EPS,
+                 drop_p if site is not None else 0.0, P(seed), site or 0)
 
         def attention(name, q, k, vt_t, out, lse, Lq, Lk, pitch, stat_pitch, mask=None):
             a = AttnArgs()
@@ -243,17 +253,18 @@ class TrainEngine:
         layers_in_Xp = [buf("Xp0", (M, d), bf)]
         vp, sp = m.input_video_proj, m.input_sketch_proj
         fwd.ln_in_index = 0
-        call(fwd, "ln_in", lib.svol_layernorm_f32_to_bf16, P(x_in), P(w["in_video.0.ln_w"]), P(w["in_video.0.ln_b"]), P(xn0), M, d_in,
-             LN_EPS)
+        # dropout sites: 0 / 1 = frame-token stages, 2 / 3 = sketch stages (svanet.py:49-60,168-170)
+        call(fwd, "ln_in", lib.svol_layernorm_f32_to_bf16_dropout, P(x_in), P(w["in_video.0.ln_w"]), P(w["in_video.0.ln_b"]), P(xn0),
+             M, d_in, LN_EPS, drop_p, P(seed), 0)
         call(fwd, "posenc_theta", lib.svol_posenc_theta, P(vmask), P(theta), B, L)
         gemm(fwd, "in_proj0", xn0, w["in_video.0.w"], w["in_video.0.b"], out=a0, act=ACT_RELU)
-        ln("in_ln1", a0, w["in_video.1.ln_w"], w["in_video.1.ln_b"], xn1)
+        ln("in_ln1", a0, w["in_video.1.ln_w"], w["in_video.1.ln_b"], xn1, site=1)
         gemm(fwd, "in_proj1", xn1, w["in_video.1.w"], w["in_video.1.b"], out=layers_in_X[0], out_pos=layers_in_Xp[0], theta_t=theta)
         sk0, sk1 = buf("sk0", (B, d), f32), buf("sk1", (B, d), f32)
-        call(fwd, "sk_proj0", lib.svol_ln_linear_f32, P(s_in), P(w["in_sketch.0.ln_w"]), P(w["in_sketch.0.ln_b"]), P(w["in_sketch.0.w"]),
-             P(w["in_sketch.0.b"]), 1, P(sk0), B, d_sk, d, LN_EPS)
-        call(fwd, "sk_proj1", lib.svol_ln_linear_f32, P(sk0), P(w["in_sketch.1.ln_w"]), P(w["in_sketch.1.ln_b"]), P(w["in_sketch.1.w"]),
-             P(w["in_sketch.1.b"]), 0, P(sk1), B, d, d, LN_EPS)
+        call(fwd, "sk_proj0", lib.svol_ln_linear_f32_dropout, P(s_in), P(w["in_sketch.0.ln_w"]), P(w["in_sketch.0.ln_b"]),
+             P(w["in_sketch.0.w"]), P(w["in_sketch.0.b"]), 1, P(sk0), B, d_sk, d, LN_EPS, drop_p, P(seed), 2)
+        call(fwd, "sk_proj1", lib.svol_ln_linear_f32_dropout, P(sk0), P(w["in_sketch.1.ln_w"]), P(w["in_sketch.1.ln_b"]),
+             P(w["in_sketch.1.w"]), P(w["in_sketch.1.b"]), 0, P(sk1), B, d, d, LN_EPS, drop_p, P(seed), 3)
         qe_bf = buf("qe_bf", (MQ, d), bf)
         zeros_q = buf("zeros_q", (MQ, d), bf, fill=0)
         call(fwd, "qe_bcast", lib.svol_add_pos_bf16, P(w["query_embed"]), None, P(qe_bf), MQ, d, Q)
@@ -462,17 +473,17 @@ class TrainEngine:
         # ---- input projection of the frame tokens: X0 = xn1 W1^T + b1; xn1 = LN(a0); a0 = relu(xn0 W0^T + b0); xn0 = LN(x_in)
         dxn1, da0 = gv[1], gv[2]
         linear_bwd("in_proj1", dX_next, xn1, G(vp[1].net[1].weight), G(vp[1].net[1].bias), wT=wt["in_video.1.wT"], dX=dxn1)
-        ln_bwd("in_ln1_bwd", a0, dxn1, w["in_video.1.ln_w"], vp[1].LayerNorm, da0)
+        ln_bwd("in_ln1_bwd", a0, dxn1, w["in_video.1.ln_w"], vp[1].LayerNorm, da0, site=1)
         bcall("in_relu_bwd", lib.svol_act_backward, P(da0), P(a0), P(da0), M * d, ACT_RELU)
         linear_bwd("in_proj0", da0, xn0, G(vp[0].net[1].weight), G(vp[0].net[1].bias), wT=wt["in_video.0.wT"], dX=gv_in)
-        ln_bwd("in_ln0_bwd", x_in, gv_in, w["in_video.0.ln_w"], vp[0].LayerNorm, None, z_f32=True, cols=d_in)
+        ln_bwd("in_ln0_bwd", x_in, gv_in, w["in_video.0.ln_w"], vp[0].LayerNorm, None, z_f32=True, cols=d_in, site=0)
         # ---- sketch branch
         bcall("sk_proj1_bwd", lib.svol_ln_linear_f32_backward, P(sk0), P(w["in_sketch.1.ln_w"]), P(w["in_sketch.1.ln_b"]),
               P(w["in_sketch.1.w"]), P(sk1), P(dsk1), 0, P(dsk0), P(G(sp[1].LayerNorm.weight)), P(G(sp[1].LayerNorm.bias)),
-              P(G(sp[1].net[1].weight)), P(G(sp[1].net[1].bias)), B, d, d, LN_EPS)
+              P(G(sp[1].net[1].weight)), P(G(sp[1].net[1].bias)), B, d, d, LN_EPS, drop_p, P(seed), 3)
         bcall("sk_proj0_bwd", lib.svol_ln_linear_f32_backward, P(s_in), P(w["in_sketch.0.ln_w"]), P(w["in_sketch.0.ln_b"]),
               P(w["in_sketch.0.w"]), P(sk0), P(dsk0), 1, P(dsk_in), P(G(sp[0].LayerNorm.weight)), P(G(sp[0].LayerNorm.bias)),
-              P(G(sp[0].net[1].weight)), P(G(sp[0].net[1].bias)), B, d_sk, d, LN_EPS)
+              P(G(sp[0].net[1].weight)), P(G(sp[0].net[1].bias)), B, d_sk, d, LN_EPS, drop_p, P(seed), 2)
         bufs["_scratch"] = scratch
         return {"fwd": fwd, "bwd": bwd, "buf": bufs}
 
@@ -491,10 +502,6 @@ class TrainEngine:
     def forward(self, src_sketch, src_sketch_mask, src_video, src_video_mask):
         """Training forward.  Returns (logits [NL,B,Q,2], boxes [NL,B,Q,4]) fp32 views of the plan's buffers."""
         _lib.require_device()
-        if float(getattr(self.module, "input_dropout", 0.0)) > 0.0:
-            raise NotImplementedError(
-                "svol_b200 training path implements the deterministic network: build the model with input_dropout=0 "
-                "(the reference's Dropout(0.4) after the input LayerNorms is not applied by these kernels)")
         B, L, d_in = src_video.shape
         plan = self.plan_for(B, L, d_in)
         b = plan["buf"]
@@ -503,6 +510,9 @@ class TrainEngine:
             raise NotImplementedError("svol_b200 supports one sketch token per pair (L_sketch == 1)")
         b["src_sketch"].copy_(src_sketch.reshape(B, -1), non_blocking=True)
         b["src_video_mask"].copy_(src_video_mask, non_blocking=True)
+        self.last_seed = self.seed_base + self.step_index      # this step's dropout stream; the backward reuses it
+        self.step_index += 1
+        b["seed"].fill_(self.last_seed)
         self._run(plan, "fwd")
         self._last = plan
         return b["logits"], b["boxes"]

@@ -256,7 +256,7 @@ def test_ln_linear_f32_backward():
         outs = [torch.zeros_like(t) for t in (lw, lb, w, b)]
         P = _lib.ptr
         _lib.check(_lib.get_lib().svol_ln_linear_f32_backward(P(x), P(lw), P(lb), P(w), P(y), P(dy), relu, P(dx), P(outs[0]), P(outs[1]),
-                                                              P(outs[2]), P(outs[3]), rows, din, dout, 1e-5, _lib.stream_ptr()), "bwd")
+                                                              P(outs[2]), P(outs[3]), rows, din, dout, 1e-5, 0.0, None, 0, _lib.stream_ptr()), "bwd")
         assert _rel(dx, leaves[0].grad) < 1e-4
         for got, leaf in zip(outs, leaves[1:]):
             assert _rel(got, leaf.grad) < 1e-4
@@ -435,3 +435,77 @@ def test_wgrad_split_k_fp32():
         _lib.check(_lib.get_lib().svol_gemm_bf16(C.byref(a), _lib.stream_ptr()), "wgrad")
         ref = 1.0 + dY.float().t() @ X.float()
         assert _rel(out, ref) < 1e-4, (rows, n_out, k_in)
+
+
+# ------------------------------------------------------------------------------------------ dropout
+def test_dropout_kernels_match_host_mask():
+    """Train-mode Dropout after the input LayerNorms (svanet.py:168-170): the kernels' counter-based mask equals its
+    host restatement (oracle/torch_port.dropout_mask) element for element; kept values are LN(x) / (1 - p); the
+    LayerNorm backward replays the same mask."""
+    from oracle import torch_port as tp
+    from svol_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    p, seed_v = 0.4, 123457
+    seed = torch.tensor([seed_v], dtype=torch.int64, device=DEV)
+    for rows, cols, site, f32 in ((3136, 512, 0, True), (3136, 256, 1, False), (64, 768, 0, True)):
+        w, b = (1 + 0.1 * torch.randn(cols, generator=g)).to(DEV), (0.1 * torch.randn(cols, generator=g)).to(DEV)
+        x = torch.randn(rows, cols, generator=g) * 1.3 + 0.1
+        x = x.to(DEV) if f32 else _bf(x).to(DEV)
+        if f32:
+            y = ops.layernorm_to_bf16(x, w, b, drop_p=p, seed=seed, site=site)
+        else:
+            y, _ = ops.layernorm_bf16(x, w, b, drop_p=p, seed=seed, site=site)
+        mask = torch.from_numpy(tp.dropout_mask(rows, cols, p, seed_v, site)).to(DEV)
+        ref = torch.nn.functional.layer_norm(x.float(), (cols,), w, b)
+        assert abs(float((mask > 0).float().mean()) - (1 - p)) < 5e-3
+        assert torch.equal(y == 0, (mask == 0) | (_bf(ref * mask) == 0)), "kernel mask != host restatement"
+        assert _rel(y.float(), ref * mask) < 4e-3
+        dy = _bf(torch.randn(rows, cols, generator=g) * 0.01).to(DEV)
+        xr = x.float().requires_grad_(True)
+        wr = w.clone().requires_grad_(True)
+        (torch.nn.functional.layer_norm(xr, (cols,), wr, b) * mask).backward(dy.float())
+        dx, _, dg, db = ops.layernorm_backward(x, [dy], w, drop_p=p, seed=seed, site=site)
+        assert _rel(dx.float(), xr.grad) < 6e-3 and _rel(dg, wr.grad) < 2e-3
+    # sketch branch (fused LayerNorm -> Dropout -> Linear), forward and backward
+    rows, din, dout, site = 8, 512, 256, 2
+    x = torch.randn(rows, din, generator=g).to(DEV)
+    lw, lb = (1 + 0.1 * torch.randn(din, generator=g)).to(DEV), (0.1 * torch.randn(din, generator=g)).to(DEV)
+    w, b = (torch.randn(dout, din, generator=g) * 0.05).to(DEV), (torch.randn(dout, generator=g) * 0.05).to(DEV)
+    dy = torch.randn(rows, dout, generator=g).to(DEV)
+    y = ops.ln_linear_f32(x, lw, lb, w, b, True, drop_p=p, seed=seed, site=site)
+    mask = torch.from_numpy(tp.dropout_mask(rows, din, p, seed_v, site)).to(DEV)
+    leaves = [t.clone().requires_grad_(True) for t in (x, lw, lb, w, b)]
+    yr = torch.relu(torch.nn.functional.linear(torch.nn.functional.layer_norm(leaves[0], (din,), leaves[1], leaves[2]) * mask, leaves[3], leaves[4]))
+    yr.backward(dy)
+    assert _rel(y, yr) < 1e-4
+    from svol_b200 import _lib
+    dx = torch.empty_like(x)
+    outs = [torch.zeros_like(t) for t in (lw, lb, w, b)]
+    P = _lib.ptr
+    _lib.check(_lib.get_lib().svol_ln_linear_f32_backward(P(x), P(lw), P(lb), P(w), P(y), P(dy), 1, P(dx), P(outs[0]), P(outs[1]), P(outs[2]),
+                                                          P(outs[3]), rows, din, dout, 1e-5, p, P(seed), site, _lib.stream_ptr()), "bwd")
+    assert _rel(dx, leaves[0].grad) < 1e-4
+    for got, leaf in zip(outs, leaves[1:]):
+        assert _rel(got, leaf.grad) < 1e-4
+
+
+def test_head_backward_with_dropout_vs_oracle():
+    """The whole head in train mode with the reference's default input_dropout = 0.4 against the oracle's autograd
+    with the same (host-rebuilt) masks."""
+    from oracle import torch_port as tp
+    from svol_b200 import synth
+    cfg = synth.CONFIGS["C1b"]                     # input_dropout = 0.4 (lib/configs.py:127)
+    assert cfg.input_dropout == 0.4
+    model, sd, inp, (gl, gb), grads, logits, boxes = _head_grads(cfg, 2, 3)
+    seed = model.train_engine.last_seed
+    ref, ref_logits, ref_boxes = tp.head_gradients(tp.state_dict_to_torch(sd), inp["src_sketch"], inp["src_sketch_mask"],
+                                                   inp["src_video"], inp["src_video_mask"], gl, gb, nheads=cfg.nheads,
+                                                   dropout=(cfg.input_dropout, seed))
+    assert float((logits - ref_logits).abs().max()) < 5e-2 and float((boxes - ref_boxes).abs().max()) < 5e-3, "training forward"
+    worst = _compare(grads, ref, "dropout 0.4 vs oracle autograd")
+    print(f"dropout: worst per-tensor relative gradient error vs oracle {worst[1]:.4g} ({worst[0]})")
+    # a second forward draws a different mask
+    t = lambda k: torch.from_numpy(inp[k]).to(DEV)
+    out2 = model(t("src_sketch"), t("src_sketch_mask"), t("src_video"), t("src_video_mask"))
+    assert model.train_engine.last_seed == seed + 1
+    assert float((out2["pred_logits"].detach().float().cpu() - logits[-1]).abs().max()) > 1e-4

@@ -16,7 +16,7 @@ ap.add_argument("--config", default="C2")
 ap.add_argument("--breakdown", action="store_true")
 args = ap.parse_args()
 dev = "cuda:0"
-cfg = replace(synth.CONFIGS[args.config], input_dropout=0.0)
+cfg = synth.CONFIGS[args.config]        # input_dropout 0.4, the reference default
 model = build_svanet(cfg.to_namespace())
 sd = synth.random_state_dict(cfg, 0)
 model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
