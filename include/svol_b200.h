@@ -174,6 +174,13 @@ int svol_attention_bf16_plain(const svol_attn_args* args, void* stream);   /* SI
 int svol_layernorm_f32_to_bf16(const float* x, const float* weight, const float* bias, svol_bf16* y,
                                int32_t rows, int32_t cols, float eps, void* stream);
 
+/* Backbone hand-off (backbone.py:72-89, model.py:18-22): x [frames, channels, spatial] fp32 is the ResNet
+ * trunk's (N*T, C, h, w) feature map as cuDNN leaves it; y [frames*spatial, channels] bf16 = LayerNorm over the channels
+ * of token (frame, position), i.e. the first LayerNorm of the head applied to the (N, T*h*w, C) token layout without
+ * materialising the reshaped / transposed fp32 copy the reference builds.  channels <= 1024, channels*spatial*4 <= 200 KB. */
+int svol_layernorm_nchw_to_bf16(const float* x, const float* weight, const float* bias, svol_bf16* y, int32_t frames,
+                                int32_t channels, int32_t spatial, float eps, void* stream);
+
 /* y = [ReLU](Linear(LayerNorm(x))) in fp32 for a handful of rows: the sketch branch of the input
  * projection (svanet.py:56-60,87), one call per LinearLayer.  x [rows,in], w [out,in], y [rows,out]. */
 int svol_ln_linear_f32(const float* x, const float* ln_weight, const float* ln_bias, const float* w,

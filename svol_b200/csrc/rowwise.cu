@@ -85,6 +85,70 @@ int launch_layernorm_f32_to_bf16(const float* x, const float* w, const float* b,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Backbone hand-off (backbone.py:72-89, model.py:18-22): the ResNet trunk emits (N*T, C, h, w); the reference
+// reshapes / transposes it twice into (N, T*h*w, C) tokens (a strided copy of the whole 100 MB tensor) before the
+// head's first LayerNorm reads it again.  This kernel reads the channel-major feature map of one frame per CTA
+// (one fully coalesced pass into shared memory) and writes the LayerNorm-ed bf16 TOKEN rows directly: the permuted
+// fp32 copy never exists.  x [F, C, S] fp32 (S = h*w), y [F*S, C] bf16; token row = f*S + s, as the reference's
+// flatten(2).transpose(1,2).reshape(N, -1, C) orders them.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_nchw_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                     const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
+                                                                     int C, int S, float eps) {
+  extern __shared__ float tile[];                  // [C][S] of this frame
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t n = static_cast<size_t>(C) * S;
+  const float* xf = x + static_cast<size_t>(f) * n;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(xf) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(xf);
+    for (size_t i = tid; i < n / 4; i += 256) reinterpret_cast<float4*>(tile)[i] = __ldcs(x4 + i);
+  } else {
+    for (size_t i = tid; i < n; i += 256) tile[i] = __ldcs(xf + i);
+  }
+  __syncthreads();
+  const int per_lane = (C + 31) / 32;               // <= 32 (C <= 1024)
+  for (int s = warp; s < S; s += 8) {
+    float v[32];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = (k < per_lane && c < C) ? tile[static_cast<size_t>(c) * S + s] : 0.f;     // stride S floats: S odd -> conflict-free
+      sum += v[k];
+    }
+    const float mean = warp_sum(sum) / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int c = lane + 32 * k;
+      if (k < per_lane && c < C) { const float d = v[k] - mean; ss += d * d; }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+    __nv_bfloat16* yr = y + (static_cast<size_t>(f) * S + s) * C;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int c = lane + 32 * k;
+      if (k < per_lane && c < C) yr[c] = __float2bfloat16_rn((v[k] - mean) * rstd * __ldg(w + c) + __ldg(b + c));
+    }
+  }
+}
+
+int launch_layernorm_nchw_to_bf16(const float* x, const float* w, const float* b, svol_bf16* y, int frames, int C, int S, float eps,
+                                  cudaStream_t stream) {
+  if (frames <= 0 || C <= 0 || C > 1024 || S <= 0) return svol_fail(SVOL_ERR_SHAPE, "layernorm_nchw: C <= 1024");
+  const size_t smem = static_cast<size_t>(C) * S * sizeof(float);
+  if (smem > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "layernorm_nchw: C * h * w * 4 bytes must fit in shared memory (200 KB)");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(layernorm_nchw_to_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return svol_fail_cuda(e, "layernorm_nchw: cudaFuncSetAttribute");
+    configured = smem;
+  }
+  layernorm_nchw_to_bf16_kernel<<<frames, 256, smem, stream>>>(x, w, b, reinterpret_cast<__nv_bfloat16*>(y), C, S, eps);
+  return svol_check_launch("layernorm_nchw_to_bf16");
+}
+
+// ---------------------------------------------------------------------------------------------
 // y = [ReLU](Linear(LayerNorm(x))) in fp32, one CTA per row (sketch branch, B rows only)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) ln_linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ lw,

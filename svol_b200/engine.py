@@ -479,14 +479,24 @@ class HeadEngine:
         """Returns (logits [NL,B,Q,2], boxes [NL,B,Q,4]) fp32, views of the plan's static output buffers
         (overwritten by the next forward of the same shape)."""
         _lib.require_device()
-        B, L, d_in = src_video.shape
+        fmap = src_video.dim() == 5
+        if fmap:
+            # backbone hand-off (SURVEY 8f-2): (B, T, C, h, w) trunk output, tokens = (frame, position) in the
+            # reference's flatten(2).transpose(1, 2).reshape(N, -1, C) order (backbone.py:72-89)
+            B, T, d_in, fh, fw = src_video.shape
+            L = T * fh * fw
+        else:
+            B, L, d_in = src_video.shape
         plan = self.plan_for(B, L, d_in)
         b = plan.buf
         # The first kernel (LayerNorm of the frame tokens, the only reader of the 100 MB fp32 input) always runs
         # eagerly and reads the caller's tensor in place; everything after it works on plan-owned buffers and can
         # be replayed as one CUDA graph.
         src = src_video
-        if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and src.data_ptr() % 16 == 0):
+        if fmap:
+            if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
+                src = src.to(device=b["src_video"].device, dtype=torch.float32).contiguous()
+        elif not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and src.data_ptr() % 16 == 0):
             b["src_video"].copy_(src_video, non_blocking=True)
             src = b["src_video"]
         if src_sketch.data_ptr() != b["src_sketch"].data_ptr():
@@ -497,7 +507,11 @@ class HeadEngine:
             b["src_video_mask"].copy_(src_video_mask, non_blocking=True)
         assert plan.ln_in_index == 0
         name, fn, args = plan.calls[0]
-        rc = fn(src.data_ptr(), *args[1:], torch.cuda.current_stream().cuda_stream)
+        if fmap:   # LayerNorm straight from the channel-major feature map: no permuted fp32 copy
+            rc = _lib.get_lib().svol_layernorm_nchw_to_bf16(src.data_ptr(), args[1], args[2], args[3], B * T, d_in, fh * fw, LN_EPS,
+                                                            torch.cuda.current_stream().cuda_stream)
+        else:
+            rc = fn(src.data_ptr(), *args[1:], torch.cuda.current_stream().cuda_stream)
         if rc != 0:
             _lib.check(rc, name)
         self.run_plan(plan)

@@ -25,11 +25,20 @@ class ResNetBackbone(nn.Module):
         self.sketch_trunk = nn.Sequential(*list(s.children())[:-1])      # pooled (C, 1, 1)
         self.out_dim = v.fc.in_features
 
-    def forward(self, src_sketch, src_video):
+    def feature_map(self, src_sketch, src_video):
+        """Sketch feature (N, 1, C) and the video trunk's output AS cuDNN LEAVES IT, (N, T, C, h, w): the CUDA head's
+        first LayerNorm reads this layout directly (svol_layernorm_nchw_to_bf16), so the reference's reshape /
+        transpose copy of the whole feature tensor (backbone.py:72-89) never happens.  (Reshaping with explicit N
+        also avoids the reference's batch-1 ``.squeeze()`` collapse, backbone.py:78.)"""
         N, T = src_video.shape[:2]
         f = self.video_trunk(src_video.flatten(0, 1))                   # (N*T, C, h, w)
-        f = f.flatten(2).transpose(1, 2).reshape(N, -1, f.shape[1])     # (N, T*h*w, C)
-        s = self.sketch_trunk(src_sketch.flatten(0, 1)).flatten(1).reshape(N, -1, f.shape[-1])
+        s = self.sketch_trunk(src_sketch.flatten(0, 1)).flatten(1).reshape(N, -1, f.shape[1])
+        return s, f.reshape(N, T, *f.shape[1:])
+
+    def forward(self, src_sketch, src_video):
+        s, f = self.feature_map(src_sketch, src_video)
+        N = f.shape[0]
+        f = f.flatten(3).permute(0, 1, 3, 2).reshape(N, -1, f.shape[2])  # (N, T*h*w, C)
         return s, f
 
 
@@ -41,10 +50,17 @@ class SketchLocalizationModel(nn.Module):
 
     def forward(self, src_sketch, src_video, src_sketch_mask=None, src_video_mask=None):
         N, T = src_video.shape[:2]
-        src_sketch, src_video = self.backbone(src_sketch, src_video)
+        training = self.training and torch.is_grad_enabled()
+        if hasattr(self.backbone, "feature_map") and not training:
+            # fused hand-off: the head normalises the trunk's channel-major output in place
+            src_sketch, src_video = self.backbone.feature_map(src_sketch, src_video)          # (N,1,C), (N,T,C,h,w)
+            tokens_per_frame = src_video.shape[-1] * src_video.shape[-2]
+        else:
+            src_sketch, src_video = self.backbone(src_sketch, src_video)
+            tokens_per_frame = src_video.shape[1] // T
         # model.py:21-22: per-frame masks repeated over each frame's tokens
         src_sketch_mask = src_sketch_mask.repeat_interleave(src_sketch.shape[1], dim=1)
-        src_video_mask = src_video_mask.repeat_interleave(src_video.shape[1] // T, dim=1)
+        src_video_mask = src_video_mask.repeat_interleave(tokens_per_frame, dim=1)
         return self.head(src_sketch, src_sketch_mask, src_video, src_video_mask)
 
 

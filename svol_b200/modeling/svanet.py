@@ -103,9 +103,13 @@ class SVANet(nn.Module):
 
     def forward(self, src_sketch, src_sketch_mask, src_video, src_video_mask):
         """src_sketch (B,1,D_s), src_sketch_mask (B,1), src_video (B,L,D_v), src_video_mask (B,L) float {0,1}.
+        Inference also accepts src_video as the backbone's (B,T,D_v,h,w) feature map (L = T*h*w tokens in (frame,
+        position) order): the first LayerNorm then reads the channel-major layout directly.
         Returns {'pred_logits' (B,Q,2), 'pred_boxes' (B,Q,4) cxcywh, 'aux_outputs': [...]} (svanet.py:128-141)."""
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # train.py:216-232: the forward keeps what the backward needs; loss.backward() runs the CUDA backward plan
+            if src_video.dim() == 5:        # training plan takes token rows: (B,T,C,h,w) -> (B, T*h*w, C)
+                src_video = src_video.flatten(3).permute(0, 1, 3, 2).reshape(src_video.shape[0], -1, src_video.shape[2])
             logits, boxes = _HeadTrainFn.apply(self, src_sketch, src_sketch_mask, src_video, src_video_mask,
                                                *self.parameters())
         else:
@@ -116,7 +120,9 @@ class SVANet(nn.Module):
         if self.vis_mode is not None:
             if logits.requires_grad:
                 raise NotImplementedError("vis_mode returns detached decoder states; use it under torch.no_grad()")
-            hs = self._engine._plans[tuple(src_video.shape)].buf["hs"]
+            key = tuple(src_video.shape) if src_video.dim() == 3 else \
+                (src_video.shape[0], src_video.shape[1] * src_video.shape[3] * src_video.shape[4], src_video.shape[2])
+            hs = self._engine._plans[key].buf["hs"]
             return out, hs.float().view(hs.shape[0], src_video.shape[0], self.num_queries, -1)
         return out
 

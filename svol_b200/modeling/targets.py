@@ -55,8 +55,20 @@ def _walk(targets: Sequence[dict]):
     return np.ascontiguousarray(boxes.reshape(-1, 4)), per_video, [int(n) for n in per_frame_counts]
 
 
-def flatten_targets(targets: Sequence[dict], device, per_frame: bool, num_frames: int, num_queries: int,
-                    q_per_frame: int) -> FlatTargets:
+class PackedTargets(list):
+    """The reference's ``batched_targets`` list (svol_dataset.py:310-312) plus its flat packing, built where the list
+    is built -- in the DataLoader worker's ``collate_fn`` -- so that the training / evaluation process
+    only issues one H2D copy per batch and never walks the nested dicts.  Behaves as the plain list for every other
+    consumer (``test.py`` reads ``targets[i]['bboxes']`` etc.)."""
+
+    def __init__(self, targets, host: torch.Tensor, meta: dict):
+        super().__init__(targets)
+        self.host, self.meta = host, meta
+
+
+def _pack_host(targets: Sequence[dict], per_frame: bool, num_frames: int, num_queries: int, q_per_frame: int):
+    """Nested targets -> (packed uint8 numpy buffer, meta).  Layout: [cost_off i64 | boxes f32 | tgt_off, match_off,
+    video_tgt_off, video_match_off, match_video i32], sections 16-byte aligned."""
     boxes, per_video, per_frame_counts = _walk(targets)
     B = len(targets)
     if per_frame:
@@ -78,22 +90,60 @@ def flatten_targets(targets: Sequence[dict], device, per_frame: bool, num_frames
     video_match_off = match_off[::ppv].copy()
     K = int(match_off[-1])
     match_video = np.repeat(np.arange(B, dtype=np.int32), np.diff(video_match_off))
-
-    # one packed host buffer -> one H2D copy: [cost_off i64 | boxes f32 | tgt_off, match_off, video_tgt_off,
-    # video_match_off, match_video i32]; the pinned staging buffers are recycled (ring + event) because
-    # cudaHostAlloc per batch costs more than the copy itself
     ints = np.concatenate([tgt_off, match_off, video_tgt_off, video_match_off, match_video]).astype(np.int32)
     S = int(boxes.shape[0])
     n_cost, n_box, n_int = ((P + 1) * 8 + 15) // 16 * 16, S * 16, ints.shape[0] * 4     # sections stay 16-byte aligned
     total = n_cost + n_box + n_int
-    if device.type == "cuda":
-        host, done = _staging(total)
-    else:
-        host, done = torch.empty(total, dtype=torch.uint8), None
-    hb = host.numpy()
+    hb = np.zeros(total, np.uint8)
     hb[:(P + 1) * 8].view(np.int64)[:] = cost_off
     hb[n_cost:n_cost + n_box].view(np.float32)[:] = boxes.reshape(-1)
     hb[n_cost + n_box:total].view(np.int32)[:] = ints
+    meta = dict(B=B, S=S, K=K, P=P, ppv=ppv, rows=rows, max_cols=int(cols.max()), cost_total=int(cost_off[-1]),
+                n_cost=n_cost, n_box=n_box, total=total, video_match_off=video_match_off, per_frame=per_frame,
+                key=(per_frame, num_frames, num_queries, q_per_frame))
+    return hb, meta
+
+
+def pack_targets(targets: Sequence[dict], per_frame: bool, num_frames: int, num_queries: int, q_per_frame: int,
+                 pin: bool = False) -> PackedTargets:
+    """Collate-time packing.  ``pin=True`` page-locks the buffer (only in a process that owns a CUDA context; a
+    DataLoader with ``pin_memory=True`` does not look inside list subclasses, so the main process pins on upload)."""
+    hb, meta = _pack_host(targets, per_frame, num_frames, num_queries, q_per_frame)
+    host = torch.from_numpy(hb)
+    return PackedTargets(targets, host.pin_memory() if pin else host, meta)
+
+
+def make_collate_fn(base_collate, matcher, num_queries: int):
+    """Wraps the reference's ``collate_fn`` (svol_dataset.py:310-319): the returned ``batched_targets`` is a
+    ``PackedTargets`` for the configuration of ``matcher`` (= ``build_matcher(args)``) and ``args.num_queries``."""
+    if hasattr(matcher, "num_queries_per_frame"):          # PerFrameMatcher
+        args = (True, matcher.num_frames, num_queries, matcher.num_queries_per_frame)
+    else:                                                   # HungarianMatcher (one problem per video)
+        args = (False, 0, num_queries, 0)
+
+    def collate(batch):
+        inputs, targets = base_collate(batch)
+        return inputs, pack_targets(targets, *args)
+    return collate
+
+
+def flatten_targets(targets: Sequence[dict], device, per_frame: bool, num_frames: int, num_queries: int,
+                    q_per_frame: int) -> FlatTargets:
+    if isinstance(targets, PackedTargets) and targets.meta["key"] == (per_frame, num_frames, num_queries, q_per_frame):
+        hb, meta = targets.host.numpy(), targets.meta              # packed at collate time: no walk here
+    else:
+        hb, meta = _pack_host(targets, per_frame, num_frames, num_queries, q_per_frame)
+    B, S, K, P, total = meta["B"], meta["S"], meta["K"], meta["P"], meta["total"]
+    n_cost, n_box = meta["n_cost"], meta["n_box"]
+    # one packed host buffer -> one H2D copy; the pinned staging buffers are recycled (ring + event) because
+    # cudaHostAlloc per batch costs more than the copy itself
+    if isinstance(targets, PackedTargets) and targets.host.is_pinned():
+        host, done = targets.host, None
+    elif device.type == "cuda":
+        host, done = _staging(total)
+        host.numpy()[:total] = hb
+    else:
+        host, done = torch.from_numpy(hb), None
     dbuf = host[:total].to(device, non_blocking=True)
     if done is not None:
         done.record()
@@ -102,11 +152,11 @@ def flatten_targets(targets: Sequence[dict], device, per_frame: bool, num_frames
     d_int = dbuf[n_cost + n_box:].view(torch.int32)
     n1, n2, n3, n4 = P + 1, 2 * (P + 1), 2 * (P + 1) + B + 1, 2 * (P + 1) + 2 * (B + 1)
     return FlatTargets(
-        B=B, S=S, K=K, P=P, problems_per_video=ppv, rows_per_problem=rows,
-        max_cols=int(cols.max()), cost_total=int(cost_off[-1]),
+        B=B, S=S, K=K, P=P, problems_per_video=meta["ppv"], rows_per_problem=meta["rows"],
+        max_cols=meta["max_cols"], cost_total=meta["cost_total"],
         tgt_boxes=d_box, tgt_off=d_int[:n1], match_off=d_int[n1:n2],
         cost_off=d_cost, video_tgt_off=d_int[n2:n3], video_match_off=d_int[n3:n4],
-        match_video=d_int[n4:], h_video_match_off=video_match_off, per_frame=per_frame)
+        match_video=d_int[n4:], h_video_match_off=meta["video_match_off"], per_frame=meta["per_frame"])
 
 
 _STAGING = {"bufs": [], "next": 0}

@@ -151,3 +151,41 @@ def test_long_clip_config_properties():
     m.engine._plans.clear()
     _, lg_pl, bx_pl = _run(m, one)
     assert np.abs(lg1 - lg_pl).max() < 3e-2 and np.abs(bx1 - bx_pl).max() < 8e-3
+
+
+def test_backbone_handoff_feature_map():
+    """the head fed with the trunk's (B,T,C,h,w) feature map equals the head fed with the reference's
+    reshaped / transposed (B, T*h*w, C) tokens (backbone.py:72-89), and the hand-off LayerNorm kernel equals the
+    oracle's LayerNorm of the permuted tensor."""
+    import numpy as np
+    import torch
+    from oracle import svol_oracle as orc
+    from svol_b200 import _lib, synth
+    from svol_b200.modeling import build_svanet
+    cfg = synth.CONFIGS["C1b"]
+    B, T, C, hw = 3, cfg.num_frames, cfg.input_vid_dim, 7
+    model = build_svanet(cfg.to_namespace())
+    sd = synth.random_state_dict(cfg, 5)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    model = model.to("cuda:0").eval()
+    inp = synth.make_inputs(cfg, B, 5, padded=True)
+    rng = np.random.RandomState(11)
+    fmap = np.maximum(rng.standard_normal((B, T, C, hw, hw)).astype(np.float32), 0.0)
+    tokens = np.ascontiguousarray(fmap.reshape(B, T, C, hw * hw).transpose(0, 1, 3, 2).reshape(B, T * hw * hw, C))
+    t = lambda a: torch.from_numpy(a).to("cuda:0")
+    with torch.no_grad():
+        out_f = {k: v.clone() for k, v in model(t(inp["src_sketch"]), t(inp["src_sketch_mask"]), t(fmap), t(inp["src_video_mask"])).items()
+                 if k != "aux_outputs"}
+        out_t = model(t(inp["src_sketch"]), t(inp["src_sketch_mask"]), t(tokens), t(inp["src_video_mask"]))
+    assert float((out_f["pred_logits"] - out_t["pred_logits"]).abs().max()) < 2e-2
+    assert float((out_f["pred_boxes"] - out_t["pred_boxes"]).abs().max()) < 2e-3
+    # kernel alone against the oracle
+    w, b = sd["input_video_proj.0.LayerNorm.weight"], sd["input_video_proj.0.LayerNorm.bias"]
+    y = torch.empty((B * T * hw * hw, C), device="cuda:0", dtype=torch.bfloat16)
+    ft, wt, bt = t(fmap), t(w), t(b)
+    _lib.check(_lib.get_lib().svol_layernorm_nchw_to_bf16(ft.data_ptr(), wt.data_ptr(), bt.data_ptr(), y.data_ptr(), B * T, C,
+                                                          hw * hw, 1e-5, _lib.stream_ptr()), "nchw")
+    torch.cuda.synchronize()
+    ref = orc.layer_norm(tokens.reshape(-1, C), w, b)
+    err = np.abs(y.float().cpu().numpy() - ref)
+    assert (err <= 2.0 ** -8 * np.abs(ref) + 1e-3).all(), float(err.max())
