@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 8
+#define SVOL_ABI_VERSION 9
 
 enum {
   SVOL_OK = 0,
@@ -306,6 +306,23 @@ int svol_criterion_backward(const svol_criterion_args* args, const float* grad_w
 int svol_postprocess(const float* logits, const float* boxes, float* out, int32_t* order, int32_t B,
                      int32_t Q, int32_t q_per_frame, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluation metrics (lib/evaluate/eval.py:20-117, lib/evaluate/utils.py:36-202) on the device arrays the
+ * forward produced.  pred = svol_postprocess output viewed as [B*T, q_per_frame, 5] (per-frame score-sorted x0,y0,x1,y1,
+ * score); evaluated frame f reads pred[frame_index[f]]; gt [n_gt, 4] fp32 xyxy, frame f owns gt[gt_off[f] : gt_off[f+1]];
+ * evaluation unit (video + sketch) u owns frames [frame_off[u], frame_off[u+1]).  Predictions are rounded to 4 decimals
+ * (test.py:161) and all comparisons are float64 in the reference's operation order.
+ *   svol_eval_max_iou            max1 / max5 [n_gt] fp64: column maxima of the reference's (k, n_f) IoU array for k = 1, 5
+ *                                (eval.py:75-90, including compute_iou_batch_cross's tile / repeat / reshape pairing)
+ *   svol_eval_average_precision  ap [units, 10] fp64: interpolated AP at IoU 0.50:0.05:0.95 after the greedy, score-ordered
+ *                                matching of utils.py:118-202
+ * ------------------------------------------------------------------------------------------ */
+int svol_eval_max_iou(const float* pred, const int32_t* frame_index, const float* gt, const int32_t* gt_off, int32_t frames,
+                      int32_t n_gt, int32_t q_per_frame, double* max1, double* max5, void* stream);
+int svol_eval_average_precision(const float* pred, const int32_t* frame_index, const float* gt, const int32_t* gt_off,
+                                const int32_t* frame_off, int32_t units, int32_t q_per_frame, int32_t max_frames, int32_t max_gt,
+                                double* ap, void* stream);
 
 /* ==========================================================================================
  * TRAINING STEP (train.py:216-232: forward in train mode, criterion, loss.backward(), AdamW).

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsvol_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -27,6 +27,7 @@ SYMBOLS = [
     "svol_colsum_bf16", "svol_attention_backward_bf16", "svol_heads_backward", "svol_gate_backward",
     "svol_gate_vectors_backward", "svol_ln_linear_f32_backward", "svol_batch_sum", "svol_accum_bf16", "svol_adamw",
     "svol_pack_weights", "svol_layernorm_f32_to_bf16_dropout", "svol_ln_linear_f32_dropout", "svol_layernorm_nchw_to_bf16",
+    "svol_eval_max_iou", "svol_eval_average_precision",
 ]
 
 
@@ -156,6 +157,8 @@ def _declare(lib: C.CDLL) -> None:
         "svol_accum_bf16": [_vp, _vp, _i64, _f32, _i32, _vp],
         "svol_adamw": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
         "svol_pack_weights": [_vp, _i32, _vp],
+        "svol_eval_max_iou": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
+        "svol_eval_average_precision": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)

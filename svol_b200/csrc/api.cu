@@ -119,6 +119,10 @@ int launch_batch_sum(const svol_bf16*, float*, int, int, int, cudaStream_t);
 int launch_accum_bf16(const svol_bf16*, float*, long long, float, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
 int launch_pack_weights(const svol_pack_job*, int, cudaStream_t);
+// evaluate.cu
+int launch_eval_max_iou(const float*, const int*, const float*, const int*, int, int, int, double*, double*, cudaStream_t);
+int launch_eval_average_precision(const float*, const int*, const float*, const int*, const int*, int, int, int, int, double*,
+                                  cudaStream_t);
 
 }  // namespace svol
 
@@ -356,6 +360,18 @@ int svol_batch_sum(const svol_bf16* g, float* acc, int32_t rows, int32_t cols, i
 int svol_accum_bf16(const svol_bf16* src, float* dst, int64_t n, float scale, int32_t accumulate, void* stream) {
   SVOL_REQUIRE(src); SVOL_REQUIRE(dst);
   return launch_accum_bf16(src, dst, n, scale, accumulate, SVOL_STREAM(stream));
+}
+int svol_eval_max_iou(const float* pred, const int32_t* frame_index, const float* gt, const int32_t* gt_off, int32_t frames,
+                      int32_t n_gt, int32_t q_per_frame, double* max1, double* max5, void* stream) {
+  SVOL_REQUIRE(pred); SVOL_REQUIRE(frame_index); SVOL_REQUIRE(gt); SVOL_REQUIRE(gt_off); SVOL_REQUIRE(max1); SVOL_REQUIRE(max5);
+  return launch_eval_max_iou(pred, frame_index, gt, gt_off, frames, n_gt, q_per_frame, max1, max5, SVOL_STREAM(stream));
+}
+int svol_eval_average_precision(const float* pred, const int32_t* frame_index, const float* gt, const int32_t* gt_off,
+                                const int32_t* frame_off, int32_t units, int32_t q_per_frame, int32_t max_frames, int32_t max_gt,
+                                double* ap, void* stream) {
+  SVOL_REQUIRE(pred); SVOL_REQUIRE(frame_index); SVOL_REQUIRE(gt); SVOL_REQUIRE(gt_off); SVOL_REQUIRE(frame_off); SVOL_REQUIRE(ap);
+  return launch_eval_average_precision(pred, frame_index, gt, gt_off, frame_off, units, q_per_frame, max_frames, max_gt, ap,
+                                       SVOL_STREAM(stream));
 }
 int svol_pack_weights(const svol_pack_job* jobs, int32_t n_jobs, void* stream) {
   SVOL_REQUIRE(jobs);

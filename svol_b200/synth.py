@@ -230,6 +230,28 @@ def make_predictions(cfg: HeadConfig, batch: int, seed: int = 0, layers: int | N
     return logits, boxes
 
 
+def make_eval_predictions(cfg: HeadConfig, batch: int, seed: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """Last-layer predictions for the evaluation-metric tests: logits (B,Q,2) ~ N(0,1) and cxcywh boxes (B,Q,4) of which
+    roughly a third are jittered copies of the frame's ground-truth boxes (same seed as :func:`make_targets` with the
+    padded frame mask), so that recall / mAP take non-trivial values; the rest are random boxes."""
+    rng = np.random.RandomState(6000 + seed)
+    inp = make_inputs(cfg, batch, seed, padded=True)
+    targets = make_targets(cfg, batch, seed, frame_mask=inp["frame_mask"])
+    logits = rng.standard_normal((batch, cfg.num_queries, 2)).astype(np.float32)
+    cxcy = rng.uniform(0.15, 0.85, size=(batch, cfg.num_queries, 2))
+    wh = rng.uniform(0.03, 0.4, size=(batch, cfg.num_queries, 2))
+    boxes = np.concatenate([cxcy, wh], axis=-1).astype(np.float32)
+    qf = cfg.num_queries_per_frame
+    for b, t in enumerate(targets):
+        for fi, frame in enumerate(t["bboxes"].values()):
+            for o in frame:
+                for _ in range(3):
+                    q = fi * qf + int(rng.randint(0, qf))
+                    boxes[b, q] = (np.asarray(o["bbox"]) * (1.0 + 0.07 * rng.standard_normal(4))).clip(0.02, 0.98).astype(np.float32)
+                    logits[b, q, 0] += 2.0
+    return logits, boxes
+
+
 def make_upstream_grads(cfg: HeadConfig, batch: int, seed: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     """Synthetic gradients w.r.t. the stacked head outputs (logits (layers,B,Q,2), boxes (layers,B,Q,4)) for the
     backward parity tests that bypass the matcher: N(0, 1e-2), the scale of d(mean loss)/d(output) times ~1e2."""

@@ -209,3 +209,29 @@ def test_oracle_head_gradients_match_reference_autograd(golden_dir):
         assert abs(float(got.norm()) - norm) <= 1e-3 * max(norm, 1e-4 * scale), k
         sample = gold["head_f32/sample/" + k].astype(np.float64)
         assert np.abs(got.reshape(-1)[::stride].numpy() - sample).max() <= 1e-3 * max(np.abs(sample).max(), 1e-5 * scale), k
+
+
+# ------------------------------------------------------------------------------------------ evaluation metrics
+def _eval_arrays(cfg, batch, seed):
+    """Flat evaluation inputs from the synthetic predictions, through the oracle's post-processing."""
+    from svol_b200.evaluate import flatten_eval_targets
+    logits, boxes = synth.make_eval_predictions(cfg, batch, seed)
+    inp = synth.make_inputs(cfg, batch, seed, padded=True)
+    targets = synth.make_targets(cfg, batch, seed, frame_mask=inp["frame_mask"])
+    sorted_rows, _ = orc.postprocess(logits, boxes, cfg.num_frames)
+    post = np.asarray(sorted_rows, np.float32).reshape(batch * cfg.num_frames, cfg.num_queries_per_frame, 5)
+    gt, gt_off, frame_off, frame_index = flatten_eval_targets(targets, cfg.num_frames)
+    return post, gt, gt_off, frame_off, frame_index
+
+
+@pytest.mark.parametrize("name", ["C2_b4", "C2_b3"])
+def test_eval_oracle_matches_reference_eval_svol(name, golden_dir):
+    """oracle/eval_oracle.py against the metric dictionary the reference's own eval_svol produced."""
+    import json
+    from oracle import eval_oracle as ev
+    gold = np.load(os.path.join(golden_dir, f"eval_{name}.npz"))
+    cfg = synth.CONFIGS["C2"]
+    post, gt, gt_off, frame_off, frame_index = _eval_arrays(cfg, int(gold["batch"]), int(gold["seed"]))
+    got = ev.eval_svol(post[frame_index], gt, gt_off, frame_off)
+    ref = json.loads(str(gold["metrics"]))
+    assert got == ref
