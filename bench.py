@@ -437,6 +437,7 @@ def run_train(args):
     model = model.to(dev).train()
     criterion = build_loss(ns).to(dev).train()
     opt = FusedAdamW(model, lr=1e-4, weight_decay=1e-4)
+    model.train_engine.publish_grads = False        # the fused optimizer reads the flat gradient buffer directly
     wd = criterion.weight_dict
     sets = []
     for s_ in range(2):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 9
+#define SVOL_ABI_VERSION 10
 
 enum {
   SVOL_OK = 0,
@@ -102,6 +102,10 @@ typedef struct svol_gemm_args {
   float* out_f32;      /* or NULL.  Weight-gradient mode: out_f32[M, ld_f32] += A x W^T in fp32 (atomic accumulation, the
                           contraction is split over the SMs); excludes every epilogue option.  dW = dY^T X of an
                           nn.Linear with A = dY^T [N_out, rows], W = X^T [K_in, rows] (svol_transpose_bf16). */
+  int32_t mn_major;    /* with out_f32 only: the operands are given UNtransposed, A = dY [K, lda] (K rows, M columns) and
+                          W = X [K, ldw] (K rows, N columns), the contraction index is the row; tiles are consumed through
+                          MN-major shared-memory descriptors, no transposed copies are needed.  M % 8 == 0, any K. */
+  int32_t reserved;
 } svol_gemm_args;
 
 int svol_gemm_bf16(const svol_gemm_args* args, void* stream);

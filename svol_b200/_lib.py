@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsvol_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -47,6 +47,7 @@ class GemmArgs(C.Structure):
         ("A", C.c_void_p), ("W", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
         ("lda", C.c_int32), ("ldw", C.c_int32), ("split_block", C.c_int32), ("ep", GemmEpilogue),
         ("A2", C.c_void_p), ("lda2", C.c_int32), ("ld_f32", C.c_int32), ("out_f32", C.c_void_p),
+        ("mn_major", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

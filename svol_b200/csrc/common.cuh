@@ -100,6 +100,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 1-D bulk copy global -> shared (size and both addresses multiples of 16 bytes), completion on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
@@ -142,6 +148,21 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Shared-memory matrix descriptor for an MN-major operand (the M / N index is the contiguous one in memory) stored by
+// TMA as [64 MN elements = 128 B] x [K rows] boxes with 128B swizzle: canonical layout
+//   Swizzle<3,4,3> o ((T,8,m),(8,k)) : ((1,T,LBO),(8T,SBO))      (T = one 16-byte unit)
+// i.e. K rows of 128 bytes, groups of 8 K rows SBO bytes apart (1024 when contiguous), 64-element MN chunks LBO
+// bytes apart (the distance between consecutive TMA boxes).
+__device__ __forceinline__ uint64_t make_mnmajor_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16, BF16 x BF16 -> FP32, both operands K-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4)                 // D format: F32
@@ -150,6 +171,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
          | (0u << 15) | (0u << 16) // A, B K-major
          | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
+// Same with both operands MN-major (bits 15 / 16).
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int m, int n) { return make_idesc_bf16(m, n) | (1u << 15) | (1u << 16); }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,

@@ -142,9 +142,13 @@ __global__ void __launch_bounds__(gemm::THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutPos,
                     const __grid_constant__ CUtensorMap tmA2, const GemmEpilogue ep, int M, int N, int K, int split_block,
-                    int k_splits, float* __restrict__ out_f32, int ld_f32) {
+                    int k_splits, float* __restrict__ out_f32, int ld_f32, int mn_major) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
+  // mn_major (training, streaming variant): the operands are given untransposed, A = dY [K rows, M columns] and
+  // W = X [K rows, N columns] (row-major, the contraction index is the ROW): tiles are loaded as 64-column x 64-row TMA
+  // boxes and consumed through MN-major shared-memory descriptors -- dW = dY^T X without a transposition pass.
+  const bool mn = kTrain && !kResidentW && mn_major != 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem + C::OFF_STAGES;
@@ -160,7 +164,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #endif
   const int m_blocks = (M + BM - 1) / BM;
   const int n_blocks = N / BN;
-  const int num_kb = K / BK;
+  const int num_kb = (K + BK - 1) / BK;        // K % 64 != 0 only with mn_major operands (rows beyond K read as zero)
   // tile schedule.  streaming: tile = blockIdx.x + i*grid, n fastest.  resident: this CTA's n block is
   // fixed (grid is a multiple of n_blocks) and it walks m blocks with stride grid / n_blocks.
   const int my_n = kResidentW ? static_cast<int>(blockIdx.x) % n_blocks : 0;
@@ -237,8 +241,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&tail->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&tail->full[stage], C::STAGE_BYTES);
           uint8_t* sa = stages + stage * C::STAGE_BYTES;
-          tma_load_2d(sa, second_part ? &tmA2 : &tmA, &tail->full[stage], kb * BK, m_blk * BM);
-          if (!kResidentW) tma_load_2d(sa + A_BYTES, &tmB, &tail->full[stage], kb * BK, n_blk * BN);
+          if (mn) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, &tail->full[stage], m_blk * BM + c * 64, kb * BK);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sa + A_BYTES + c * 8192, &tmB, &tail->full[stage], n_blk * BN + c * 64, kb * BK);
+          } else {
+            tma_load_2d(sa, second_part ? &tmA2 : &tmA, &tail->full[stage], kb * BK, m_blk * BM);
+            if (!kResidentW) tma_load_2d(sa + A_BYTES, &tmB, &tail->full[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -263,11 +274,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&tail->full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);
-          const uint64_t a_desc = make_kmajor_desc<128>(sa);
-          const uint64_t b_desc = make_kmajor_desc<128>(kResidentW ? smem_u32(smem + kb * B_BYTES) : sa + A_BYTES);
+          if (mn) {
+            // [64 MN x 64 K] boxes of 8 KB; a K16 step advances 16 rows of 128 bytes
+            constexpr uint32_t idesc_mn = make_idesc_bf16_mn(BM, BN);
+            const uint64_t a_desc = make_mnmajor_desc_sw128(sa, 8192, 1024);
+            const uint64_t b_desc = make_mnmajor_desc_sw128(sa + A_BYTES, 8192, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss(d_tmem, a_desc + 128 * k, b_desc + 128 * k, idesc_mn, ((kb - kb0) | k) != 0);
+          } else {
+            const uint64_t a_desc = make_kmajor_desc<128>(sa);
+            const uint64_t b_desc = make_kmajor_desc<128>(kResidentW ? smem_u32(smem + kb * B_BYTES) : sa + A_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, ((kb - kb0) | k) != 0);
+          }
           umma_commit(&tail->empty[stage]);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -541,13 +562,16 @@ static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUten
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (kResidentW) grid = grid / n_blocks * n_blocks;       // every CTA owns one n block
   gemm_bf16_tc_kernel<kResidentW, kTrain><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, tmA2, a.ep, a.M, a.N, a.K,
-                                                                            a.split_block, k_splits, a.out_f32, a.ld_f32);
+                                                                            a.split_block, k_splits, a.out_f32, a.ld_f32, a.mn_major);
   return svol_check_launch("gemm_bf16_tc");
 }
 
 int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   using namespace gemm;
-  if (a.N % BN != 0 || a.K % BK != 0 || a.M <= 0) return svol_fail(SVOL_ERR_SHAPE, "gemm: need N % 256 == 0, K % 64 == 0, M > 0");
+  if (a.mn_major) {
+    if (!a.out_f32) return svol_fail(SVOL_ERR_SHAPE, "gemm: mn_major operands are the weight-gradient mode (out_f32)");
+    if (a.N % BN != 0 || a.M <= 0 || a.K <= 0 || a.M % 8 != 0) return svol_fail(SVOL_ERR_SHAPE, "gemm (mn_major): need N % 256 == 0, M % 8 == 0");
+  } else if (a.N % BN != 0 || a.K % BK != 0 || a.M <= 0) return svol_fail(SVOL_ERR_SHAPE, "gemm: need N % 256 == 0, K % 64 == 0, M > 0");
   if (a.ep.ln_weight && a.N != BN) return svol_fail(SVOL_ERR_SHAPE, "gemm: fused LayerNorm needs N == 256");
   const int split = a.split_block;
   if (split != 0 && (split < 0 || split >= a.N / BN || a.K != RES_K || !a.A2 || !a.ep.out_vt || a.ep.ln_weight))
@@ -559,9 +583,16 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
   if (a.ep.dact_src && (a.ep.ld_dact % 8 != 0 || (a.ep.dact_mode != SVOL_ACT_GELU && a.ep.dact_mode != SVOL_ACT_RELU)))
     return svol_fail(SVOL_ERR_SHAPE, "gemm: dact_src needs ld_dact % 8 == 0 and dact_mode RELU | GELU");
   CUtensorMap tmA, tmB;
-  int rc = make_tensor_map_2d(&tmA, a.A, a.K, a.M, a.lda, BK, BM, 128);
-  if (rc) return rc;
-  rc = make_tensor_map_2d(&tmB, a.W, a.K, a.N, a.ldw, BK, BN, 128);
+  int rc;
+  if (a.mn_major) {      // A [K rows, M cols], W [K rows, N cols]: boxes of 64 columns x 64 rows (rows beyond K read as zero)
+    rc = make_tensor_map_2d(&tmA, a.A, a.M, a.K, a.lda, 64, BK, 128);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&tmB, a.W, a.N, a.K, a.ldw, 64, BK, 128);
+  } else {
+    rc = make_tensor_map_2d(&tmA, a.A, a.K, a.M, a.lda, BK, BM, 128);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&tmB, a.W, a.K, a.N, a.ldw, BK, BN, 128);
+  }
   if (rc) return rc;
   // outputs are written by TMA stores of [32 rows x 64 columns] boxes (rows beyond M clipped by the map)
   CUtensorMap tmOut = tmA, tmOutPos = tmA;
@@ -593,7 +624,7 @@ int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream) {
       return svol_fail(SVOL_ERR_SHAPE, "gemm: out_f32 (accumulating fp32 output) excludes every other epilogue option");
     if (a.ld_f32 < a.N || a.ld_f32 % 4 != 0 || (reinterpret_cast<uintptr_t>(a.out_f32) & 15))
       return svol_fail(SVOL_ERR_SHAPE, "gemm: out_f32 must be 16-byte aligned with ld_f32 >= N, ld_f32 % 4 == 0");
-    const int tiles = ((a.M + BM - 1) / BM) * (a.N / BN), num_kb = a.K / BK;
+    const int tiles = ((a.M + BM - 1) / BM) * (a.N / BN), num_kb = (a.K + BK - 1) / BK;
     k_splits = sm_count() / tiles;
     if (k_splits > num_kb / 4) k_splits = num_kb / 4;
     if (k_splits < 1) k_splits = 1;

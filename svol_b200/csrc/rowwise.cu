@@ -95,17 +95,27 @@ int launch_layernorm_f32_to_bf16(const float* x, const float* w, const float* b,
 __global__ void __launch_bounds__(256) layernorm_nchw_to_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                      const float* __restrict__ b, __nv_bfloat16* __restrict__ y,
                                                                      int C, int S, float eps) {
-  extern __shared__ float tile[];                  // [C][S] of this frame
+  extern __shared__ __align__(16) float tile[];    // [C][S] of this frame
+  __shared__ uint64_t bar;
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t n = static_cast<size_t>(C) * S;
   const float* xf = x + static_cast<size_t>(f) * n;
   if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(xf) & 15) == 0) {
-    const float4* x4 = reinterpret_cast<const float4*>(xf);
-    for (size_t i = tid; i < n / 4; i += 256) reinterpret_cast<float4*>(tile)[i] = __ldcs(x4 + i);
+    // the frame's C*S floats are contiguous: bulk-async copies (no register staging, completion on an mbarrier); the
+    // second resident CTA of the SM computes while this one's copy is in flight
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(n * 4);
+      mbar_arrive_expect_tx(&bar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768)
+        bulk_load_1d(reinterpret_cast<uint8_t*>(tile) + off, reinterpret_cast<const uint8_t*>(xf) + off, min(32768u, bytes - off), &bar);
+    }
+    mbar_wait(&bar, 0);
   } else {
     for (size_t i = tid; i < n; i += 256) tile[i] = __ldcs(xf + i);
+    __syncthreads();
   }
-  __syncthreads();
   const int per_lane = (C + 31) / 32;               // <= 32 (C <= 1024)
   for (int s = warp; s < S; s += 8) {
     float v[32];

@@ -330,21 +330,56 @@ int launch_transpose_bf16(const svol_bf16* in, int ld_in, int rows, int cols, sv
   return svol_check_launch("transpose_bf16");
 }
 
-// colsum[c] += sum_r in[r, c] alone (bias gradients whose transposed copy is not needed)
+// colsum[c] += sum_r in[r, c] (bias gradient of an nn.Linear from its output gradient).  A CTA covers 256 columns:
+// warp w reads rows w, w + 8, ... 16 bytes per lane (512 contiguous bytes per warp and row), partial sums are combined
+// through shared memory and added with one atomic per column.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, int ld_in, int rows, int cols,
                                                           float* __restrict__ colsum) {
+  __shared__ float red[8][256 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * 256 + lane * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < cols) {
+    uint4 q[4];
+    int r = blockIdx.x * 8 + warp;
+    const int step = gridDim.x * 8;
+    for (; r + 3 * step < rows; r += 4 * step) {           // four independent 16-byte loads in flight per lane
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(in + static_cast<size_t>(r + u * step) * ld_in + c0));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v[8];
+        unpack8(q[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+    }
+    for (; r < rows; r += step) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(in + static_cast<size_t>(r) * ld_in + c0)), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
   const int c = blockIdx.y * 256 + threadIdx.x;
-  if (c >= cols) return;
-  const int per = (rows + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
-  float acc = 0.f;
-  for (int r = r0; r < r1; ++r) acc += __bfloat162float(in[static_cast<size_t>(r) * ld_in + c]);
-  atomicAdd(colsum + c, acc);
+  if (c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(colsum + c, t);
+  }
 }
 int launch_colsum_bf16(const svol_bf16* in, int ld_in, int rows, int cols, float* colsum, cudaStream_t stream) {
-  if (rows <= 0 || cols <= 0) return svol_fail(SVOL_ERR_SHAPE, "colsum_bf16: bad sizes");
-  const int gx = min(512, (rows + 63) / 64);
-  colsum_bf16_kernel<<<dim3(gx, (cols + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, rows, cols, colsum);
+  if (rows <= 0 || cols <= 0 || cols % 8 != 0 || ld_in % 8 != 0 || (reinterpret_cast<uintptr_t>(in) & 15))
+    return svol_fail(SVOL_ERR_SHAPE, "colsum_bf16: cols and ld_in must be multiples of 8, in 16-byte aligned");
+  const int cblocks = (cols + 255) / 256;
+  int gx = (rows + 31) / 32;
+  const int cap = max(1, 4 * sm_count() / cblocks);
+  if (gx > cap) gx = cap;
+  colsum_bf16_kernel<<<dim3(gx, cblocks), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld_in, rows, cols, colsum);
   return svol_check_launch("colsum_bf16");
 }
 

@@ -51,6 +51,8 @@ class _HeadTrainFn(torch.autograd.Function):
         module = ctx.module
         eng = module.train_engine
         eng.backward(g_logits.contiguous().float(), g_boxes.contiguous().float())
+        if not eng.publish_grads:        # fused-optimizer loop: gradients stay in eng.grad_flat (FusedAdamW.step(from_engine=True))
+            return (None,) * (5 + ctx.n_params)
         unused = {id(p) for p in module.class_head.parameters()}          # never reached by forward (svanet.py:125)
         grads = [eng.grad_of(p) if (p.requires_grad and id(p) not in unused) else None for p in module.parameters()]
         return (None, None, None, None, None, *grads)

@@ -11,8 +11,8 @@ Differences from the inference plan (``engine.py``):
     attention backward's MMAs take as K-major operands; the attention forward stores each row's log-sum-exp.
 
 Backward, per ``nn.Linear``: ``dX = dY W`` is the tcgen05 GEMM with the transposed weight as its W operand,
-``dW = dY^T X`` the same GEMM over transposed copies of dY and X (contraction over the token rows, split over the
-SMs and accumulated into the fp32 gradient with atomics), ``db`` falls out of the transposition pass.  LayerNorm / GELU / ReLU / gate / heads backward are the kernels of ``train.cu``,
+``dW = dY^T X`` the same GEMM on the untransposed operands (MN-major shared-memory descriptors; the contraction over
+the token rows is split over the SMs and accumulated into the fp32 gradient with vector atomics), ``db`` a column sum.  LayerNorm / GELU / ReLU / gate / heads backward are the kernels of ``train.cu``,
 the attention backward is ``attn_bwd_tc.cu``.  Activation gradients are bf16, parameter gradients fp32 views of one
 flat buffer (``grad_of(param)``), zeroed at the start of every backward.
 
@@ -51,6 +51,9 @@ class TrainEngine:
         self._packer = WeightPacker()
         # both plans replay as CUDA graphs after one eager warm-up run per shape (SVOL_B200_TRAIN_GRAPH=0: eager launches)
         self.use_graph = os.environ.get("SVOL_B200_TRAIN_GRAPH", "1") != "0"
+        # True: loss.backward() fills param.grad like the reference (one copy per parameter and step).  A loop that
+        # feeds FusedAdamW.step(from_engine=True) from grad_flat can switch it off.
+        self.publish_grads = True
         self.seed_base = int(torch.initial_seed()) & 0x3FFFFFFF      # dropout stream; step k uses seed_base + k
         self.step_index = 0
         self.last_seed = None
@@ -208,28 +211,22 @@ class TrainEngine:
             bwd.keep.append(a)
             bwd.calls.append((name, lib.svol_attention_backward_bf16, (C.byref(a),)))
 
-        # transposition scratch per row count (pad columns [rows, round_up(rows, 64)) stay zero for ever)
         R = NL * MQ
-        wide = max(ff, 2 * d, d_in)
-        scratch: Dict[int, tuple] = {}
-        for rows, cols in ((M, wide), (MQ, wide), (R, d)):
-            if rows not in scratch or scratch[rows][2] < cols:
-                rp = _round_up(rows, 64)
-                scratch[rows] = (torch.zeros(cols * rp, device=dev, dtype=bf), torch.zeros(cols * rp, device=dev, dtype=bf), cols)
 
         def linear_bwd(name, dY, X, weight_grad, bias_grad, wT=None, dX=None, residual=None, out_vt=None, vt_len=0, vt_pitch=0,
                        dact=None, dact_mode=0):
-            """dY [R, N_out], X [R, K_in] (bf16).  weight_grad [N_out, K_in] / bias_grad [N_out] fp32 views (accumulated).
-            Optional dgrad dX = dY W (+ residual), optionally also stored per-head transposed."""
+            """dY [rows, N_out], X [rows, K_in] (bf16).  weight_grad [N_out, K_in] / bias_grad [N_out] fp32 views (accumulated).
+            dW += dY^T X runs on the UNtransposed operands (MN-major descriptors, contraction split over the SMs);
+            optional dgrad dX = dY W (+ residual, * f'(dact)), optionally also stored per-head transposed."""
             rows, n_out = dY.shape
             k_in = X.shape[1]
-            rp = _round_up(rows, 64)
-            ta, tb, cap = scratch[rows]
-            assert n_out <= cap and k_in <= cap and X.shape[0] == rows, name
-            tA, tB = ta[:n_out * rp].view(n_out, rp), tb[:k_in * rp].view(k_in, rp)
-            call(bwd, name + ".dYT", lib.svol_transpose_bf16, P(dY), dY.stride(0), rows, n_out, P(tA), rp, P(bias_grad))
-            call(bwd, name + ".XT", lib.svol_transpose_bf16, P(X), X.stride(0), rows, k_in, P(tB), rp, None)
-            gemm(bwd, name + ".wgrad", tA, tB, out_f32=weight_grad)
+            assert X.shape[0] == rows and weight_grad.is_contiguous() and tuple(weight_grad.shape) == (n_out, k_in), name
+            call(bwd, name + ".db", lib.svol_colsum_bf16, P(dY), dY.stride(0), rows, n_out, P(bias_grad))
+            a = GemmArgs()
+            a.A, a.W, a.M, a.N, a.K, a.lda, a.ldw = P(dY), P(X), n_out, k_in, rows, dY.stride(0), X.stride(0)
+            a.out_f32, a.ld_f32, a.mn_major = P(weight_grad), k_in, 1
+            bwd.keep.append(a)
+            bwd.calls.append((name + ".wgrad", lib.svol_gemm_bf16, (C.byref(a),)))
             if dX is not None or out_vt is not None:
                 gemm(bwd, name + ".dgrad", dY, wT, out=dX, residual=residual, out_vt=out_vt, vt_len=vt_len, vt_pitch=vt_pitch,
                      dact=dact, dact_mode=dact_mode)
@@ -484,7 +481,6 @@ class TrainEngine:
         bcall("sk_proj0_bwd", lib.svol_ln_linear_f32_backward, P(s_in), P(w["in_sketch.0.ln_w"]), P(w["in_sketch.0.ln_b"]),
               P(w["in_sketch.0.w"]), P(sk0), P(dsk0), 1, P(dsk_in), P(G(sp[0].LayerNorm.weight)), P(G(sp[0].LayerNorm.bias)),
               P(G(sp[0].net[1].weight)), P(G(sp[0].net[1].bias)), B, d_sk, d, LN_EPS, drop_p, P(seed), 2)
-        bufs["_scratch"] = scratch
         return {"fwd": fwd, "bwd": bwd, "buf": bufs}
 
     def plan_for(self, B: int, L: int, d_in: int) -> dict:

@@ -99,6 +99,16 @@ def test_transpose_colsum():
     assert torch.equal(xt2[:, :640], wide[:, 256:].t())
 
 
+def test_colsum():
+    from svol_b200 import _lib
+    g = torch.Generator().manual_seed(14)
+    for rows, cols, ld in ((50176, 256, 256), (10240, 2048, 2048), (1000, 256, 512), (7, 512, 512)):
+        x = _bf(torch.randn(rows, ld, generator=g)).to(DEV)
+        out = torch.ones(cols, device=DEV)
+        _lib.check(_lib.get_lib().svol_colsum_bf16(x.data_ptr(), ld, rows, cols, out.data_ptr(), _lib.stream_ptr()), "colsum")
+        assert _rel(out, 1 + x[:, :cols].float().sum(0)) < 1e-5, (rows, cols)
+
+
 def test_wgrad_through_gemm():
     """dW = dY^T X as svol_gemm_bf16 over the transposed operands (contraction over 10240 token rows)."""
     from svol_b200 import ops
@@ -509,3 +519,29 @@ def test_head_backward_with_dropout_vs_oracle():
     out2 = model(t("src_sketch"), t("src_sketch_mask"), t("src_video"), t("src_video_mask"))
     assert model.train_engine.last_seed == seed + 1
     assert float((out2["pred_logits"].detach().float().cpu() - logits[-1]).abs().max()) > 1e-4
+
+
+def test_wgrad_mn_major_operands():
+    """Weight-gradient GEMM on UNtransposed operands (MN-major shared-memory descriptors): dW += dY^T X with dY [rows, N_out],
+    X [rows, K_in] row-major, any number of rows (the tail k-block is zero-filled by TMA)."""
+    from svol_b200 import _lib
+    g = torch.Generator().manual_seed(13)
+    for rows, n_out, k_in in ((10240, 256, 256), (50176, 512, 256), (10240, 2048, 256), (10240, 256, 2048), (1000, 256, 512), (64, 256, 768)):
+        dY = _bf(torch.randn(rows, n_out, generator=g) * 0.05).to(DEV)
+        X = _bf(torch.randn(rows, k_in, generator=g)).to(DEV)
+        out = torch.full((n_out, k_in), 1.0, device=DEV)
+        a = _lib.GemmArgs()
+        a.A, a.W, a.M, a.N, a.K, a.lda, a.ldw = dY.data_ptr(), X.data_ptr(), n_out, k_in, rows, dY.stride(0), X.stride(0)
+        a.out_f32, a.ld_f32, a.mn_major = out.data_ptr(), k_in, 1
+        _lib.check(_lib.get_lib().svol_gemm_bf16(C.byref(a), _lib.stream_ptr()), "wgrad mn")
+        ref = 1.0 + dY.float().t() @ X.float()
+        assert _rel(out, ref) < 1e-4, (rows, n_out, k_in, _rel(out, ref))
+    # column slices of wider matrices (dq | dk gradients share one buffer)
+    wide = _bf(torch.randn(4096, 512, generator=g) * 0.05).to(DEV)
+    X = _bf(torch.randn(4096, 256, generator=g)).to(DEV)
+    out = torch.zeros((256, 256), device=DEV)
+    a = _lib.GemmArgs()
+    a.A, a.W, a.M, a.N, a.K, a.lda, a.ldw = wide[:, 256:].data_ptr(), X.data_ptr(), 256, 256, 4096, 512, 256
+    a.out_f32, a.ld_f32, a.mn_major = out.data_ptr(), 256, 1
+    _lib.check(_lib.get_lib().svol_gemm_bf16(C.byref(a), _lib.stream_ptr()), "wgrad mn slice")
+    assert _rel(out, wide[:, 256:].float().t() @ X.float()) < 1e-4

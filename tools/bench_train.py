@@ -23,6 +23,7 @@ model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=Tr
 model = model.to(dev).train()
 criterion = build_loss(cfg.to_namespace()).to(dev).train()
 opt = FusedAdamW(model, lr=1e-4, weight_decay=1e-4)
+model.train_engine.publish_grads = False
 B = args.batch
 inp = synth.make_inputs(cfg, B, 0, padded=True)
 targets = synth.targets_to_torch(synth.make_targets(cfg, B, 0, frame_mask=inp["frame_mask"]))

@@ -8,8 +8,9 @@ run() {  # name, timeout, pytest args...
   timeout "$t" python -m pytest -q --tb=short -p no:cacheprovider -x "$@" > "gpurun_out/$name.log" 2>&1
   echo "$name: exit $? :: $(tail -1 gpurun_out/$name.log)"
 }
-run tr_rowwise 300 tests/test_train_gpu.py -m gpu -k "layernorm or gelu or transpose or wgrad_through or heads or ln_linear or batch_sum"
+run tr_rowwise 300 tests/test_train_gpu.py -m gpu -k "layernorm or gelu or transpose or colsum or wgrad_through or heads or ln_linear or batch_sum"
 run tr_splitk  300 tests/test_train_gpu.py -m gpu -k "split_k"
+run tr_mnmajor 300 tests/test_train_gpu.py -m gpu -k "mn_major"
 run tr_gate    200 tests/test_train_gpu.py -m gpu -k "gate"
 run tr_attn_a  200 tests/test_train_gpu.py -m gpu -k "attention_backward and 128"
 run tr_attn_b  300 tests/test_train_gpu.py -m gpu -k "attention_backward and not 128"
