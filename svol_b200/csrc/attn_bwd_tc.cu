@@ -206,12 +206,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_32x32b_x32(t_lane + DQ_T_S + c * 32, s);
         tmem_ld_32x32b_x32(t_lane + DQ_T_DP + c * 32, dp);
         tmem_ld_wait();
+        // per pair of scores: one packed subtract (S - lse), two MUFU ex2, one packed subtract (dP - delta), one packed
+        // multiply, one pack -- 3 issue slots per element; blocks without invalid keys skip the mask selects
+        const float2 nl = make_float2(-lse_r, -lse_r), nd = make_float2(-delta_r, -delta_r);
+        if (words[c] == 0xffffffffu) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2f(__uint_as_float(s[i]) - lse_r), p1 = ex2f(__uint_as_float(s[i + 1]) - lse_r);
-          if (!((words[c] >> i) & 1u)) p0 = 0.f;
-          if (!((words[c] >> (i + 1)) & 1u)) p1 = 0.f;
-          packed[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[i]) - delta_r), p1 * (__uint_as_float(dp[i + 1]) - delta_r));
+          for (int i = 0; i < 32; i += 2) {
+            const float2 x = __fadd2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), nl);
+            const float2 pr = make_float2(ex2f(x.x), ex2f(x.y));
+            const float2 g = __fmul2_rn(pr, __fadd2_rn(make_float2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), nd));
+            packed[i >> 1] = pack_bf16x2(g.x, g.y);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 x = __fadd2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), nl);
+            float2 pr = make_float2(ex2f(x.x), ex2f(x.y));
+            if (!((words[c] >> i) & 1u)) pr.x = 0.f;
+            if (!((words[c] >> (i + 1)) & 1u)) pr.y = 0.f;
+            const float2 g = __fmul2_rn(pr, __fadd2_rn(make_float2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), nd));
+            packed[i >> 1] = pack_bf16x2(g.x, g.y);
+          }
         }
         tmem_st_x16(t_lane + DQ_T_DS + c * 16, packed);
       }
@@ -345,6 +360,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     const int key = k0 + r;
     const bool key_ok = key < Lk && (key_mask == nullptr || __ldg(key_mask + static_cast<size_t>(b) * Lk + key) != 0.f);
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const float2 kb2 = key_ok ? make_float2(0.f, 0.f) : make_float2(-INFINITY, -INFINITY);
     const int tid = threadIdx.x;                      // 0..255; the first 128 threads stage the block's lse | delta
     const float* stat_g = (tid < BN ? lse : delta) + (static_cast<size_t>(b) * H + h) * stat_pitch + (tid & (BN - 1));
     float nxt = tid < 2 * BN ? __ldg(stat_g) : 0.f;   // stat_pitch is a multiple of 64: every block read is in bounds
@@ -368,14 +384,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
           for (int i = 0; i < 16; i += 4) {
             const float4 l4 = lds_f4(st_addr + (c * 32 + sub * 16 + i) * 4);
             const float4 d4 = lds_f4(st_addr + (BN + c * 32 + sub * 16 + i) * 4);
-            float p0 = ex2f(__uint_as_float(s[i + 0]) - l4.x), p1 = ex2f(__uint_as_float(s[i + 1]) - l4.y);
-            float p2 = ex2f(__uint_as_float(s[i + 2]) - l4.z), p3 = ex2f(__uint_as_float(s[i + 3]) - l4.w);
-            if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+            // packed subtracts / multiplies (3 issue slots per element besides the two shared-memory loads); an invalid
+            // key row adds -inf to every exponent (key_bias), so its probabilities are exactly 0 without per-element selects
+            const float2 x0 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(s[i + 0]), __uint_as_float(s[i + 1])), make_float2(-l4.x, -l4.y)), kb2);
+            const float2 x1 = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(s[i + 2]), __uint_as_float(s[i + 3])), make_float2(-l4.z, -l4.w)), kb2);
+            const float2 p01 = make_float2(ex2f(x0.x), ex2f(x0.y)), p23 = make_float2(ex2f(x1.x), ex2f(x1.y));
+            const float2 g01 = __fmul2_rn(p01, __fadd2_rn(make_float2(__uint_as_float(dp[i + 0]), __uint_as_float(dp[i + 1])), make_float2(-d4.x, -d4.y)));
+            const float2 g23 = __fmul2_rn(p23, __fadd2_rn(make_float2(__uint_as_float(dp[i + 2]), __uint_as_float(dp[i + 3])), make_float2(-d4.z, -d4.w)));
             const int o = sub * 8 + (i >> 1);
-            pp[o] = pack_bf16x2(p0, p1);
-            pp[o + 1] = pack_bf16x2(p2, p3);
-            dsp[o] = pack_bf16x2(p0 * (__uint_as_float(dp[i + 0]) - d4.x), p1 * (__uint_as_float(dp[i + 1]) - d4.y));
-            dsp[o + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[i + 2]) - d4.z), p3 * (__uint_as_float(dp[i + 3]) - d4.w));
+            pp[o] = pack_bf16x2(p01.x, p01.y);
+            pp[o + 1] = pack_bf16x2(p23.x, p23.y);
+            dsp[o] = pack_bf16x2(g01.x, g01.y);
+            dsp[o + 1] = pack_bf16x2(g23.x, g23.y);
           }
         }
         tmem_st_x16(t_lane + KV_T_P + c * 16, pp);

