@@ -57,6 +57,7 @@ class TrainEngine:
         self.seed_base = int(torch.initial_seed()) & 0x3FFFFFFF      # dropout stream; step k uses seed_base + k
         self.step_index = 0
         self.last_seed = None
+        self._side = None
         self._plans: Dict[tuple, dict] = {}
         self._params: List[torch.nn.Parameter] = []
         self.grad_flat: torch.Tensor = None
@@ -265,6 +266,7 @@ class TrainEngine:
         qe_bf = buf("qe_bf", (MQ, d), bf)
         zeros_q = buf("zeros_q", (MQ, d), bf, fill=0)
         call(fwd, "qe_bcast", lib.svol_add_pos_bf16, P(w["query_embed"]), None, P(qe_bf), MQ, d, Q)
+        fwd.branch["qe_bcast"] = "q"
         hs = buf("hs", (NL, MQ, d), bf)
         S: List[dict] = []
         out_cur, outp_cur = zeros_q, qe_bf
@@ -316,6 +318,7 @@ class TrainEngine:
                 sb(nm, (B * d, Qp), fill=0)
             sb("lse_q", (B, H, Qs), f32, fill=float("inf")); sb("lse_c", (B, H, Qs), f32, fill=float("inf"))
             s["out_in"], s["outp_in"] = out_cur, outp_cur
+            q_first = len(fwd.calls)     # object-query branch: overlaps the frame-token chain of the next layer (engine.py:_Plan)
             gemm(fwd, p + "ta_q", outp_cur, w[p + "ta.wqk"][:d], w[p + "ta.bqk"][:d], out=s["qq"], out_vt=s["qqT"], vt_len=Q, vt_pitch=Qp)
             gemm(fwd, p + "ta_k", outp_cur, w[p + "ta.wqk"][d:], w[p + "ta.bqk"][d:], out=s["kq"], out_vt=s["kqT"], vt_len=Q, vt_pitch=Qp)
             gemm(fwd, p + "ta_v", out_cur, w[p + "ta.wv"], w[p + "ta.bv"], out=s["vq"], out_vt=s["vqT"], vt_len=Q, vt_pitch=Qp)
@@ -331,6 +334,9 @@ class TrainEngine:
             gemm(fwd, p + "ffn2_up", s["o2"], w[p + "mlp2.w1"], w[p + "mlp2.b1"], out=s["hid2"], act=ACT_GELU, out_pre=s["pre2"])
             gemm(fwd, p + "ffn2_down", s["hid2"], w[p + "mlp2.w2"], w[p + "mlp2.b2"], out=s["z6"], residual=s["o2"])
             ln(p + "n6", s["z6"], w[p + "n6.w"], w[p + "n6.b"], hs[li], y_pos=s["outp"], pos_t=w["query_embed"], mod=Q)
+            for name, _, _ in fwd.calls[q_first:]:
+                fwd.branch[name] = "q"
+            fwd.after[p + "ca_attn"] = [p + "ca_v"]
             out_cur, outp_cur = hs[li], s["outp"]
             S.append(s)
         hs_all = hs.view(R, d)
@@ -340,6 +346,8 @@ class TrainEngine:
         gemm(fwd, "box1", h1, w["box.1.w"], w["box.1.b"], out=h2, act=ACT_RELU)
         call(fwd, "heads", lib.svol_heads, P(hs_all), P(h2), P(w["cls.w"]), P(w["cls.b"]), P(w["box.2.w"]), P(w["box.2.b"]), P(logits),
              P(boxes), R, d)
+        for name in ("box0", "box1", "heads"):
+            fwd.branch[name] = "q"
 
         # ================================================================= BACKWARD
         dlogits, dboxes = buf("dlogits", (NL, B, Q, 2), f32), buf("dboxes", (NL, B, Q, 4), f32)
@@ -363,6 +371,10 @@ class TrainEngine:
         dsk_in = buf("dsk_in", (B, d_sk), f32)
         dhs_next = [buf(f"dhs_next{i}", (MQ, d), bf) for i in range(2)]    # d(out_in), d(outp_in) handed to the previous layer
         dX_next = buf("dX_next", (M, d), bf)                               # d(layer input X), handed to the previous layer
+        # cross-attention dK / dV are produced by the query branch of layer i and consumed by its frame-token branch, which
+        # runs concurrently with the query branch of layer i - 1: two alternating pairs
+        dkc_b = [buf(f"dkc{i}", (M, d), bf) for i in range(2)]
+        dvc_b = [buf(f"dvc{i}", (M, d), bf) for i in range(2)]
 
         be, ce = m.bbox_embed.layers, m.class_embed
         dhs_cls, dh2, dh1 = gR[0], gR[1], gR[2]
@@ -382,6 +394,7 @@ class TrainEngine:
             last = li == NL - 1
             ta, ca, sa = layer.token_self_attn, layer.content_token_cross_attn, layer.content_self_attn
             # ------------------------------------------------------------ query side
+            bq_first = len(bwd.calls) if not last else 0     # (the last layer's range also covers the heads' backward)
             dhs_h = dhs_heads[li * MQ:(li + 1) * MQ]
             dz6, dhid, do2, dz5, dac = gq[0], gq_ff, gq[1], gq[2], gq[3]
             ln_bwd(p + "n6_bwd", s["z6"], dhs_h, w[p + "n6.w"], layer.norm6, dz6, dy2=None if last else dhs_next[0], dy3=None if last else dhs_next[1])
@@ -395,7 +408,7 @@ class TrainEngine:
             d_ = d
             linear_bwd(p + "ca_out", dz5, s["ac"], G(ca.out_proj.weight), G(ca.out_proj.bias), wT=wt[p + "ca.woT"], dX=dac,
                        out_vt=dOT_q, vt_len=Q, vt_pitch=Qp)
-            dqc, dkc, dvc = gq[4], gv[0], gv[1]
+            dqc, dkc, dvc = gq[4], dkc_b[li & 1], dvc_b[li & 1]
             a = AttnBwdArgs()
             a.q, a.k, a.v, a.kt, a.qt, a.o, a.d_o, a.d_ot = P(s["qc"]), P(s["kc"]), P(s["vc"]), P(s["kcT"]), P(s["qcT"]), P(s["ac"]), P(dac), P(dOT_q)
             a.lse, a.delta, a.key_mask, a.dq, a.dk, a.dv = P(s["lse_c"]), P(delta_q), P(vmask), P(dqc), P(dkc), P(dvc)
@@ -427,11 +440,17 @@ class TrainEngine:
             linear_bwd(p + "ta_v", dvq, s["out_in"], gw[2 * d_:], gb[2 * d_:], wT=wt[p + "ta.wvT"], dX=dhs_next[0], residual=dz4)
             if li == 0:        # out_in = 0 (no parameters behind it); outp_in = query_embed broadcast
                 bcall(p + "dqe_qe", lib.svol_batch_sum, P(dhs_next[1]), P(dqe), MQ, d, Q)
+            # Branches of the backward graph: the query side of layer i - 1 only needs the query side of layer i, so it runs
+            # concurrently with the frame-token side of layer i (which waits for layer i's cross-attention backward).
+            for name, _, _ in bwd.calls[bq_first:]:
+                bwd.branch[name] = "q"
+            bv_first = len(bwd.calls)
             # ------------------------------------------------------------ frame-token side
             gw, gb = G(ca.in_proj_weight), G(ca.in_proj_bias)
             dXpn, dXn = gv[2], gv[3]
             linear_bwd(p + "ca_k", dkc, Xpn, gw[d_:2 * d_], gb[d_:2 * d_], wT=wt[p + "ca.wkT"], dX=dXpn)
             linear_bwd(p + "ca_v", dvc, Xn, gw[2 * d_:], gb[2 * d_:], wT=wt[p + "ca.wvT"], dX=dXn, residual=dXpn)
+            bwd.after[bwd.calls[bv_first][0]] = [p + "ca_attn_bwd"]
             dz3 = gv[0]
             ln_bwd(p + "n3_bwd", s["z3"], dXn, w[p + "n3.w"], layer.norm3, dz3, dy2=None if last else dX_next)
             dmem2 = gv[1]
@@ -516,11 +535,11 @@ class TrainEngine:
     def _run(self, plan: dict, which: str) -> None:
         """Eager on the first call of a shape (module loading, function attributes), captured on the second,
         replayed afterwards.  The backward graph includes the zeroing of the gradient buffers."""
-        def body():
+        def body(side=None):
             if which == "bwd":
                 self.grad_flat.zero_()
                 plan["buf"]["dsk1"].zero_()
-            plan[which].run(torch.cuda.current_stream().cuda_stream)
+            plan[which].run(torch.cuda.current_stream().cuda_stream, side=side)
 
         if not self.use_graph:
             return body()
@@ -530,9 +549,11 @@ class TrainEngine:
             return body()
         if state[which] is None:
             torch.cuda.synchronize()
+            if self._side is None:
+                self._side = (torch.cuda.Stream(), torch.cuda.Stream())
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                body()
+                body(side=self._side)            # the query / frame-token branches become concurrent graph branches
             state[which] = g
         state[which].replay()
 
