@@ -445,8 +445,15 @@ def run_train(args):
         tg = synth.targets_to_torch(synth.make_targets(cfg, B, seed=100 * rank + s_, frame_mask=inp["frame_mask"]))
         host = {k: torch.from_numpy(inp[k]).pin_memory() for k in ("src_sketch", "src_sketch_mask", "src_video", "src_video_mask")}
         sets.append({"host": host, "dev": {k: v.to(dev) for k, v in host.items()}, "targets": tg})
-    stage = {k: torch.empty_like(v, device=dev) for k, v in sets[0]["host"].items()}
-    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    # end-to-end: host (pinned) inputs in, loss out, every step.  Two device staging sets: the H2D copy of step i + 1 runs
+    # on a copy stream while step i computes (the reference's DataLoader(pin_memory) + .to(non_blocking) pipeline,
+    # train.py:213-221); the host reads step i's loss (pinned, async D2H) while step i + 1 runs.
+    stages = [{k: torch.empty_like(v, device=dev) for k, v in sets[0]["host"].items()} for _ in range(2)]
+    loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_copied = [torch.cuda.Event() for _ in range(2)]
+    ev_done = [torch.cuda.Event() for _ in range(2)]
+    e2e_sink = []
 
     def train_step(d, targets):
         out = model(d["src_sketch"], d["src_sketch_mask"], d["src_video"], d["src_video_mask"])
@@ -460,30 +467,55 @@ def run_train(args):
     def step_resident(i):
         return train_step(sets[i & 1]["dev"], sets[i & 1]["targets"])
 
-    def step_e2e(i):
-        for k, v in sets[i & 1]["host"].items():
-            stage[k].copy_(v, non_blocking=True)                                  # H2D of the step's inputs
-        criterion.matcher._cache._key = None                                      # targets walked + uploaded every step
-        total = train_step(stage, sets[i & 1]["targets"])
-        loss_host.copy_(total.reshape(1), non_blocking=True)                      # D2H of the step's loss
-        torch.cuda.current_stream().synchronize()
-        return float(loss_host[0])
+    def h2d(i):
+        slot = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_done[slot])
+            for k, v in sets[i & 1]["host"].items():
+                stages[slot][k].copy_(v, non_blocking=True)                       # H2D of step i's inputs
+            ev_copied[slot].record(copy_stream)
+
+    def run_e2e(steps):
+        main = torch.cuda.current_stream()
+        h2d(0)
+        last = None
+        for i in range(steps):
+            slot = i & 1
+            if i + 1 < steps:
+                h2d(i + 1)
+            main.wait_event(ev_copied[slot])
+            criterion.matcher._cache._key = None                                  # targets walked + uploaded every step
+            total = train_step(stages[slot], sets[i & 1]["targets"])
+            loss_host[slot].copy_(total.reshape(1), non_blocking=True)            # D2H of the step's loss
+            ev_done[slot].record(main)
+            if i > 0:
+                ev_done[slot ^ 1].synchronize()
+                e2e_sink.append(float(loss_host[slot ^ 1][0]))
+        ev_done[(steps - 1) & 1].synchronize()
+        e2e_sink.append(float(loss_host[(steps - 1) & 1][0]))
+        return e2e_sink[-1]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sampler=None):
-        for i in range(warmup):
-            fn(i)
+    def timed(fn, steps, warmup, sampler=None, whole_loop=False):
+        if whole_loop:
+            fn(warmup)
+        else:
+            for i in range(warmup):
+                fn(i)
         barrier()
         if sampler is not None:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
-            last = fn(i)
+        if whole_loop:
+            last = fn(steps)
+        else:
+            for i in range(steps):
+                last = fn(i)
         e1.record()
         barrier()
         return comm.max_over_ranks(e0.elapsed_time(e1), device=dev) / steps, last
@@ -491,7 +523,7 @@ def run_train(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ms_step, last = timed(step_resident, args.steps, max(args.warmup, 3), sampler=sampler)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, args.steps, 3)
+    ms_e2e, _ = timed(run_e2e, args.steps, 3, whole_loop=True)
     criterion.check_status()
     plan = model.train_engine._last
     launches = len(plan["fwd"].calls) + len(plan["bwd"].calls) + 2 * 3 + 4       # + attention-backward pairs, matcher, criterion fwd/bwd, AdamW

@@ -410,7 +410,7 @@ int svol_heads_backward(const svol_bf16* hs, const svol_bf16* h2, const float* w
 
 /* Backward of the sketch gate from datt [B*L] (produced by svol_layernorm_backward with att):
  *   dscores [B,H,L] workspace;  dx_out = dx_in + sum_h dscores u  (gradient w.r.t. the layer input x, through
- *   both x * (1 + att) and the scores of x + pos);  du [B,H,d] accumulated. */
+ *   both x * (1 + att) and the scores of x + pos);  du [B,H,d] is overwritten. */
 int svol_gate_backward(const svol_bf16* xpos, const float* u, const float* scores, const float* datt,
                        const svol_bf16* dx_in, svol_bf16* dx_out, float* dscores, float* du, int32_t B, int32_t L,
                        int32_t d, int32_t H, void* stream);

@@ -55,7 +55,7 @@ constexpr int MAX_STAGES = 5;
 struct AttnBwdBars {
   uint64_t once_full;                       // the CTA's own row tiles
   uint64_t full[abwd::MAX_STAGES], empty[abwd::MAX_STAGES];
-  uint64_t sdp_full, ds_ready, acc_full;
+  uint64_t sdp_full[2], ds_ready[2], acc_full;   // per 32-column half of the block: two independent MMA <-> compute chains
   uint32_t tmem_base, pad;
 };
 static_assert(sizeof(AttnBwdBars) <= 256, "barrier block");
@@ -124,8 +124,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmKt);
     mbar_init(&bars->once_full, 1);
     for (int s = 0; s < DQ_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    mbar_init(&bars->sdp_full, 1);
-    mbar_init(&bars->ds_ready, COMPUTE_WARPS);
+    for (int hf = 0; hf < 2; ++hf) { mbar_init(&bars->sdp_full[hf], 1); mbar_init(&bars->ds_ready[hf], COMPUTE_WARPS / 2); }
     mbar_init(&bars->acc_full, 1);
     fence_barrier_init();
   }
@@ -154,36 +153,44 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == COMPUTE_WARPS + 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_acc = make_idesc_bf16(BM, DH);
       const uint64_t dQd = make_kmajor_desc<64>(smem_u32(smem));
       const uint64_t dOd = make_kmajor_desc<64>(smem_u32(smem + ROW_TILE_BYTES));
-      auto issue_acc = [&](int j) {                 // dQ += dS(j) K_j
+      // Each 64-key block is processed as two 32-key halves with their own barriers: while the compute warps of one half
+      // turn scores into dS, the MMAs of the other half run -- two MMA <-> compute chains per CTA, four per SM.
+      auto issue_acc = [&](int j, int hf) {         // dQ += dS_hf(j) K_j[32 hf : 32 hf + 32]
         const int s = j % DQ_STAGES;
-        mbar_wait(&bars->ds_ready, j & 1);
+        mbar_wait(&bars->ds_ready[hf], j & 1);
         tcgen05_fence_after();
         const uint64_t dKt = make_kmajor_desc<128>(smem_u32(smem + DQ_OFF_STAGES + s * DQ_STAGE_BYTES + 2 * COL_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k)
-          umma_ts(tmem_base + DQ_T_ACC, tmem_base + DQ_T_DS + k * 8, dKt + 2 * k, idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&bars->empty[s]);
+        for (int k = 0; k < 2; ++k) {
+          const int kk = hf * 2 + k;
+          umma_ts(tmem_base + DQ_T_ACC, tmem_base + DQ_T_DS + kk * 8, dKt + 2 * kk, idesc_acc, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        if (hf == 1) umma_commit(&bars->empty[s]);
       };
       mbar_wait(&bars->once_full, 0);
       for (int j = 0; j < n_blk; ++j) {
         const int s = j % DQ_STAGES;
         mbar_wait(&bars->full[s], (j / DQ_STAGES) & 1);
-        if (j > 0) issue_acc(j - 1);
-        tcgen05_fence_after();
         const uint8_t* st = smem + DQ_OFF_STAGES + s * DQ_STAGE_BYTES;
-        const uint64_t dK = make_kmajor_desc<64>(smem_u32(st));
-        const uint64_t dV = make_kmajor_desc<64>(smem_u32(st + COL_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + DQ_T_S, dQd + 2 * k, dK + 2 * k, idesc_s, k != 0);
+        for (int hf = 0; hf < 2; ++hf) {
+          if (j > 0) issue_acc(j - 1, hf);
+          tcgen05_fence_after();
+          // rows [32 hf, +32) of the 64B-swizzled [64 x 32] K / V tiles start 2048 bytes in
+          const uint64_t dK = make_kmajor_desc<64>(smem_u32(st) + hf * 2048);
+          const uint64_t dV = make_kmajor_desc<64>(smem_u32(st + COL_TILE_BYTES) + hf * 2048);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + DQ_T_DP, dOd + 2 * k, dV + 2 * k, idesc_s, k != 0);
-        umma_commit(&bars->sdp_full);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + DQ_T_S + hf * 32, dQd + 2 * k, dK + 2 * k, idesc_acc, k != 0);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + DQ_T_DP + hf * 32, dOd + 2 * k, dV + 2 * k, idesc_acc, k != 0);
+          umma_commit(&bars->sdp_full[hf]);
+        }
       }
-      issue_acc(n_blk - 1);
+      issue_acc(n_blk - 1, 0);
+      issue_acc(n_blk - 1, 1);
       umma_commit(&bars->acc_full);
     }
   } else {
@@ -199,7 +206,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int j = 0; j < n_blk; ++j) {
       uint32_t words[2] = {0xffffffffu, 0xffffffffu};
       if (mrow != nullptr || (j + 1) * BN > Lk) key_words(mrow, j * BN, Lk, lane, words);
-      mbar_wait(&bars->sdp_full, j & 1);
+      mbar_wait(&bars->sdp_full[c], j & 1);
       tcgen05_fence_after();
       {
         uint32_t s[32], dp[32], packed[16];
@@ -233,7 +240,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_st_wait_();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->ds_ready);
+      if (lane == 0) mbar_arrive(&bars->ds_ready[c]);
     }
     mbar_wait(&bars->acc_full, 0);
     tcgen05_fence_after();
@@ -287,8 +294,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     tma_prefetch_desc(&tmQt); tma_prefetch_desc(&tmdOt);
     mbar_init(&bars->once_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    mbar_init(&bars->sdp_full, 1);
-    mbar_init(&bars->ds_ready, COMPUTE_WARPS);
+    for (int hf = 0; hf < 2; ++hf) { mbar_init(&bars->sdp_full[hf], 1); mbar_init(&bars->ds_ready[hf], COMPUTE_WARPS / 2); }
     mbar_init(&bars->acc_full, 1);
     fence_barrier_init();
   }
@@ -316,41 +322,48 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     }
   } else if (warp == COMPUTE_WARPS + 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_acc = make_idesc_bf16(BM, DH);
       const uint64_t dKd = make_kmajor_desc<64>(smem_u32(smem));
       const uint64_t dVd = make_kmajor_desc<64>(smem_u32(smem + ROW_TILE_BYTES));
-      auto issue_acc = [&](int j) {                 // dV += P^T(j) dO_j ;  dK += dS^T(j) Q_j
+      auto issue_acc = [&](int j, int hf) {         // dV += P^T_hf(j) dO_j[32 hf : +32] ;  dK += dS^T_hf(j) Q_j[32 hf : +32]
         const int s = j % KV_STAGES;
-        mbar_wait(&bars->ds_ready, j & 1);
+        mbar_wait(&bars->ds_ready[hf], j & 1);
         tcgen05_fence_after();
         const uint8_t* st = smem + KV_OFF_STAGES + s * KV_STAGE_BYTES;
         const uint64_t dQt = make_kmajor_desc<128>(smem_u32(st + 2 * COL_TILE_BYTES));
         const uint64_t dOt = make_kmajor_desc<128>(smem_u32(st + 3 * COL_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k)
-          umma_ts(tmem_base + KV_T_DV, tmem_base + KV_T_P + k * 8, dOt + 2 * k, idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 2; ++k) {
+          const int kk = hf * 2 + k;
+          umma_ts(tmem_base + KV_T_DV, tmem_base + KV_T_P + kk * 8, dOt + 2 * kk, idesc_acc, (j > 0 || kk > 0) ? 1u : 0u);
+        }
 #pragma unroll
-        for (int k = 0; k < BN / 16; ++k)
-          umma_ts(tmem_base + KV_T_DK, tmem_base + KV_T_DS + k * 8, dQt + 2 * k, idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&bars->empty[s]);
+        for (int k = 0; k < 2; ++k) {
+          const int kk = hf * 2 + k;
+          umma_ts(tmem_base + KV_T_DK, tmem_base + KV_T_DS + kk * 8, dQt + 2 * kk, idesc_acc, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        if (hf == 1) umma_commit(&bars->empty[s]);
       };
       mbar_wait(&bars->once_full, 0);
       for (int j = 0; j < n_blk; ++j) {
         const int s = j % KV_STAGES;
         mbar_wait(&bars->full[s], (j / KV_STAGES) & 1);
-        if (j > 0) issue_acc(j - 1);
-        tcgen05_fence_after();
         const uint8_t* st = smem + KV_OFF_STAGES + s * KV_STAGE_BYTES;
-        const uint64_t dQ = make_kmajor_desc<64>(smem_u32(st));
-        const uint64_t dO = make_kmajor_desc<64>(smem_u32(st + COL_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + KV_T_S, dKd + 2 * k, dQ + 2 * k, idesc_s, k != 0);
+        for (int hf = 0; hf < 2; ++hf) {
+          if (j > 0) issue_acc(j - 1, hf);
+          tcgen05_fence_after();
+          const uint64_t dQ = make_kmajor_desc<64>(smem_u32(st) + hf * 2048);
+          const uint64_t dO = make_kmajor_desc<64>(smem_u32(st + COL_TILE_BYTES) + hf * 2048);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + KV_T_DP, dVd + 2 * k, dO + 2 * k, idesc_s, k != 0);
-        umma_commit(&bars->sdp_full);
+          for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + KV_T_S + hf * 32, dKd + 2 * k, dQ + 2 * k, idesc_acc, k != 0);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + KV_T_DP + hf * 32, dVd + 2 * k, dO + 2 * k, idesc_acc, k != 0);
+          umma_commit(&bars->sdp_full[hf]);
+        }
       }
-      issue_acc(n_blk - 1);
+      issue_acc(n_blk - 1, 0);
+      issue_acc(n_blk - 1, 1);
       umma_commit(&bars->acc_full);
     }
   } else {
@@ -369,7 +382,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       if (tid < 2 * BN) st[tid] = nxt;              // threads 0..63: lse of query j*64 + tid;  64..127: delta
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid < 2 * BN && j + 1 < n_blk) nxt = __ldg(stat_g + (j + 1) * BN);
-      mbar_wait(&bars->sdp_full, j & 1);
+      mbar_wait(&bars->sdp_full[c], j & 1);
       tcgen05_fence_after();
       const uint32_t st_addr = smem_u32(st);
       {
@@ -404,7 +417,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
       tmem_st_wait_();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->ds_ready);
+      if (lane == 0) mbar_arrive(&bars->ds_ready[c]);
     }
     mbar_wait(&bars->acc_full, 0);
     tcgen05_fence_after();

@@ -577,6 +577,8 @@ __global__ void __launch_bounds__(256) gate_scores_bwd_kernel(const __nv_bfloat1
 int launch_gate_backward(const svol_bf16* xpos, const float* u, const float* scores, const float* datt, const svol_bf16* dx_in,
                          svol_bf16* dx_out, float* dscores, float* du, int B, int L, int d, int H, cudaStream_t stream) {
   if (d != TD || H != TH || B <= 0 || L <= 0) return svol_fail(SVOL_ERR_SHAPE, "gate_backward: hidden_dim 256 / 8 heads only");
+  cudaError_t e = cudaMemsetAsync(du, 0, static_cast<size_t>(B) * TH * TD * sizeof(float), stream);     // du is written, not accumulated
+  if (e != cudaSuccess) return svol_fail_cuda(e, "gate_backward: memset");
   gate_softmax_bwd_kernel<<<dim3(TH, B), 256, 0, stream>>>(scores, datt, dscores, L);
   int rc = svol_check_launch("gate_softmax_bwd");
   if (rc) return rc;

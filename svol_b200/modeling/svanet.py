@@ -43,14 +43,14 @@ class _HeadTrainFn(torch.autograd.Function):
     def forward(ctx, module, src_sketch, src_sketch_mask, src_video, src_video_mask, *params):
         eng = module.train_engine
         logits, boxes = eng.forward(src_sketch, src_sketch_mask, src_video, src_video_mask)
-        ctx.module, ctx.n_params = module, len(params)
+        ctx.module, ctx.n_params, ctx.token = module, len(params), eng.forward_token
         return logits.clone(), boxes.clone()
 
     @staticmethod
     def backward(ctx, g_logits, g_boxes):
         module = ctx.module
         eng = module.train_engine
-        eng.backward(g_logits.contiguous().float(), g_boxes.contiguous().float())
+        eng.backward(g_logits.contiguous().float(), g_boxes.contiguous().float(), token=ctx.token)
         if not eng.publish_grads:        # fused-optimizer loop: gradients stay in eng.grad_flat (FusedAdamW.step(from_engine=True))
             return (None,) * (5 + ctx.n_params)
         unused = {id(p) for p in module.class_head.parameters()}          # never reached by forward (svanet.py:125)

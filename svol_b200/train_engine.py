@@ -58,6 +58,7 @@ class TrainEngine:
         self.step_index = 0
         self.last_seed = None
         self._side = None
+        self.forward_token = 0
         self._plans: Dict[tuple, dict] = {}
         self._params: List[torch.nn.Parameter] = []
         self.grad_flat: torch.Tensor = None
@@ -479,7 +480,6 @@ class TrainEngine:
             # norm1 over x * (1 + att): dx = dz (1 + att), datt; mem feeds the residual (dz2), memp/mem (dmem)
             dxg = gv[0]
             ln_bwd(p + "n1_bwd", X, dmem, w[p + "n1.w"], layer.norm1, dxg, dy2=dz2, att=s["att"], datt=datt)
-            bcall(p + "du_zero", lib.svol_accum_bf16, P(zeros_q), P(du), B * H * d, 0.0, 0)
             bcall(p + "gate_bwd", lib.svol_gate_backward, P(Xp), P(s["u"]), P(s["scores"]), P(datt), P(dxg), P(dX_next), P(dscores), P(du),
                   B, L, d, H)
             g_ = layer.sketch_video_cross_attn
@@ -530,6 +530,7 @@ class TrainEngine:
         b["seed"].fill_(self.last_seed)
         self._run(plan, "fwd")
         self._last = plan
+        self.forward_token += 1          # identifies whose activations the plan buffers hold (see backward)
         return b["logits"], b["boxes"]
 
     def _run(self, plan: dict, which: str) -> None:
@@ -558,8 +559,13 @@ class TrainEngine:
         state[which].replay()
 
     @torch.no_grad()
-    def backward(self, grad_logits: torch.Tensor, grad_boxes: torch.Tensor) -> None:
-        """Runs the backward of the most recent training forward; parameter gradients land in ``grad_of(p)``."""
+    def backward(self, grad_logits: torch.Tensor, grad_boxes: torch.Tensor, token: int = None) -> None:
+        """Runs the backward of the most recent training forward; parameter gradients land in ``grad_of(p)``.
+        ``token`` (the value of ``forward_token`` right after the forward being differentiated) guards against a second
+        forward having overwritten the saved activations (they live in static plan buffers, one set per shape)."""
+        if token is not None and token != self.forward_token:
+            raise RuntimeError("svol_b200: backward() of a training forward whose saved activations were overwritten by a later "
+                               "forward; call loss.backward() before the next model(...) call (one forward in flight)")
         plan = self._last
         b = plan["buf"]
         b["dlogits"].copy_(grad_logits.reshape(b["dlogits"].shape))

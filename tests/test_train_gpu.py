@@ -546,3 +546,20 @@ def test_wgrad_mn_major_operands():
     a.out_f32, a.ld_f32, a.mn_major = out.data_ptr(), 256, 1
     _lib.check(_lib.get_lib().svol_gemm_bf16(C.byref(a), _lib.stream_ptr()), "wgrad mn slice")
     assert _rel(out, wide[:, 256:].float().t() @ X.float()) < 1e-4
+
+
+def test_backward_of_overwritten_forward_is_refused():
+    """The saved activations live in static plan buffers: differentiating an older forward after a newer one must fail
+    loudly, not return gradients of the wrong batch."""
+    from svol_b200 import synth
+    cfg = replace(synth.CONFIGS["C1a"], input_dropout=0.0)
+    model, _ = _build(cfg, 0)
+    model.train()
+    inp = synth.make_inputs(cfg, 2, 0)
+    t = lambda k: torch.from_numpy(inp[k]).to(DEV)
+    out1 = model(t("src_sketch"), t("src_sketch_mask"), t("src_video"), t("src_video_mask"))
+    out2 = model(t("src_sketch"), t("src_sketch_mask"), t("src_video"), t("src_video_mask"))
+    with pytest.raises(RuntimeError, match="overwritten"):
+        out1["pred_logits"].sum().backward()
+    out2["pred_logits"].sum().backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)

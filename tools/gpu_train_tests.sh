@@ -16,5 +16,5 @@ run tr_attn_a  200 tests/test_train_gpu.py -m gpu -k "attention_backward and 128
 run tr_attn_b  300 tests/test_train_gpu.py -m gpu -k "attention_backward and not 128"
 run tr_dropout 300 tests/test_train_gpu.py -m gpu -s -k "dropout"
 run tr_head    600 tests/test_train_gpu.py -m gpu -s -k "head_backward_vs"
-run tr_step    600 tests/test_train_gpu.py -m gpu -s -k "training_step"
+run tr_step    600 tests/test_train_gpu.py -m gpu -s -k "training_step or overwritten"
 grep -h "worst per-tensor" gpurun_out/tr_head.log
