@@ -74,6 +74,11 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* r) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -92,14 +97,10 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// validity of the 64 keys [kv0, kv0 + 64) of sample b as two ballot words (ragged tail and key_padding_mask)
-__device__ __forceinline__ void key_words(const float* mrow, int kv0, int Lk, int lane, uint32_t (&words)[2]) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    const int kv = kv0 + c * 32 + lane;
-    const bool ok = kv < Lk && (mrow == nullptr || __ldg(mrow + kv) != 0.f);
-    words[c] = __ballot_sync(0xffffffffu, ok);
-  }
+// validity of the 32 keys [kv0, kv0 + 32) of sample b as a ballot word (ragged tail and key_padding_mask)
+__device__ __forceinline__ uint32_t key_word(const float* mrow, int kv0, int Lk, int lane) {
+  const int kv = kv0 + lane;
+  return __ballot_sync(0xffffffffu, kv < Lk && (mrow == nullptr || __ldg(mrow + kv) != 0.f));
 }
 }  // namespace
 
@@ -204,8 +205,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float delta_r = q < Lq ? __ldg(delta + stat + q) : 0.f;
     const float* mrow = key_mask ? key_mask + static_cast<size_t>(b) * Lk : nullptr;
     for (int j = 0; j < n_blk; ++j) {
-      uint32_t words[2] = {0xffffffffu, 0xffffffffu};
-      if (mrow != nullptr || (j + 1) * BN > Lk) key_words(mrow, j * BN, Lk, lane, words);
+      uint32_t word = 0xffffffffu;                  // validity of this warp's 32 keys of the block
+      if (mrow != nullptr || (j + 1) * BN > Lk) word = key_word(mrow, j * BN + c * 32, Lk, lane);
       mbar_wait(&bars->sdp_full[c], j & 1);
       tcgen05_fence_after();
       {
@@ -216,7 +217,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // per pair of scores: one packed subtract (S - lse), two MUFU ex2, one packed subtract (dP - delta), one packed
         // multiply, one pack -- 3 issue slots per element; blocks without invalid keys skip the mask selects
         const float2 nl = make_float2(-lse_r, -lse_r), nd = make_float2(-delta_r, -delta_r);
-        if (words[c] == 0xffffffffu) {
+        if (word == 0xffffffffu) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float2 x = __fadd2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), nl);
@@ -229,8 +230,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int i = 0; i < 32; i += 2) {
             const float2 x = __fadd2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), nl);
             float2 pr = make_float2(ex2f(x.x), ex2f(x.y));
-            if (!((words[c] >> i) & 1u)) pr.x = 0.f;
-            if (!((words[c] >> (i + 1)) & 1u)) pr.y = 0.f;
+            if (!((word >> i) & 1u)) pr.x = 0.f;
+            if (!((word >> (i + 1)) & 1u)) pr.y = 0.f;
             const float2 g = __fmul2_rn(pr, __fadd2_rn(make_float2(__uint_as_float(dp[i]), __uint_as_float(dp[i + 1])), nd));
             packed[i >> 1] = pack_bf16x2(g.x, g.y);
           }
@@ -374,22 +375,24 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
     const bool key_ok = key < Lk && (key_mask == nullptr || __ldg(key_mask + static_cast<size_t>(b) * Lk + key) != 0.f);
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const float2 kb2 = key_ok ? make_float2(0.f, 0.f) : make_float2(-INFINITY, -INFINITY);
-    const int tid = threadIdx.x;                      // 0..255; the first 128 threads stage the block's lse | delta
-    const float* stat_g = (tid < BN ? lse : delta) + (static_cast<size_t>(b) * H + h) * stat_pitch + (tid & (BN - 1));
-    float nxt = tid < 2 * BN ? __ldg(stat_g) : 0.f;   // stat_pitch is a multiple of 64: every block read is in bounds
+    // Each half (4 warps) stages the lse | delta of ITS 32 queries of the block and synchronises on its own named
+    // barrier, so the two halves never wait for each other.  hid = thread index inside the half: 0..31 load lse,
+    // 32..63 load delta.  Layout of a buffer: [lse 64 | delta 64] floats, half c owns entries [32 c, 32 c + 32) of each.
+    const int hid = quarter * 32 + lane;
+    const float* stat_g = (hid < 32 ? lse : delta) + (static_cast<size_t>(b) * H + h) * stat_pitch + c * 32 + (hid & 31);
+    float nxt = hid < 64 ? __ldg(stat_g) : 0.f;       // stat_pitch is a multiple of 64: every block read is in bounds
     for (int j = 0; j < n_blk; ++j) {
       float* st = stat_s + (j & 1) * 2 * BN;
-      if (tid < 2 * BN) st[tid] = nxt;              // threads 0..63: lse of query j*64 + tid;  64..127: delta
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (tid < 2 * BN && j + 1 < n_blk) nxt = __ldg(stat_g + (j + 1) * BN);
+      if (hid < 64) st[(hid < 32 ? 0 : BN) + c * 32 + (hid & 31)] = nxt;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + c) : "memory");
+      if (hid < 64 && j + 1 < n_blk) nxt = __ldg(stat_g + (j + 1) * BN);
       mbar_wait(&bars->sdp_full[c], j & 1);
       tcgen05_fence_after();
       const uint32_t st_addr = smem_u32(st);
       {
-        uint32_t pp[16], dsp[16];
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {           // 16 columns at a time: keeps the live registers under the 2-CTA budget
-          uint32_t s[16], dp[16];
+          uint32_t s[16], dp[16], pp[8], dsp[8];
           tmem_ld_32x32b_x16(t_lane + KV_T_S + c * 32 + sub * 16, s);
           tmem_ld_32x32b_x16(t_lane + KV_T_DP + c * 32 + sub * 16, dp);
           tmem_ld_wait();
@@ -404,15 +407,15 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_const
             const float2 p01 = make_float2(ex2f(x0.x), ex2f(x0.y)), p23 = make_float2(ex2f(x1.x), ex2f(x1.y));
             const float2 g01 = __fmul2_rn(p01, __fadd2_rn(make_float2(__uint_as_float(dp[i + 0]), __uint_as_float(dp[i + 1])), make_float2(-d4.x, -d4.y)));
             const float2 g23 = __fmul2_rn(p23, __fadd2_rn(make_float2(__uint_as_float(dp[i + 2]), __uint_as_float(dp[i + 3])), make_float2(-d4.z, -d4.w)));
-            const int o = sub * 8 + (i >> 1);
+            const int o = i >> 1;
             pp[o] = pack_bf16x2(p01.x, p01.y);
             pp[o + 1] = pack_bf16x2(p23.x, p23.y);
             dsp[o] = pack_bf16x2(g01.x, g01.y);
             dsp[o + 1] = pack_bf16x2(g23.x, g23.y);
           }
+          tmem_st_x8(t_lane + KV_T_P + c * 16 + sub * 8, pp);
+          tmem_st_x8(t_lane + KV_T_DS + c * 16 + sub * 8, dsp);
         }
-        tmem_st_x16(t_lane + KV_T_P + c * 16, pp);
-        tmem_st_x16(t_lane + KV_T_DS + c * 16, dsp);
       }
       tmem_st_wait_();
       tcgen05_fence_before();
