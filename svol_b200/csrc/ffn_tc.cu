@@ -26,6 +26,9 @@
 // GELU is the exact-erf form evaluated branch-free as  relu(t) -+ 0.5 t * 2^(|t| q(|t|))  with q a degree-4 minimax
 // polynomial of log2(erfc(|t|/sqrt 2))/|t| (max |error| 1.2e-6, far below the bf16 rounding of the hidden units):
 // 8 FMA-pipe, 3.5 ALU-pipe and 1 MUFU instruction per element.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "svol_internal.h"
 
@@ -115,6 +118,12 @@ __device__ __forceinline__ float2 gelu_erf_q4_x2(float2 t) {
   return __ffma2_rn(hx, se, make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f)));
 }
 
+// kMC: the kernel runs as clusters of two CTAs that work on different token tiles but consume the SAME weight stream.
+// Each CTA loads half of every [256 x 32] weight block (128 rows) and multicasts it into both CTAs' rings, so the L2 ->
+// SM weight traffic per SM halves (the non-multicast kernel is bound by exactly that feed: ~43 B/clk/SM delivered against
+// the 64 B/clk/SM the tensor pipe could consume).  A ring slot is refilled only after BOTH CTAs' MMAs released it
+// (tcgen05.commit multicast onto both w_empty barriers).
+template <bool kMC>
 __global__ void __launch_bounds__(ffn::THREADS, 1)
 ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
@@ -134,14 +143,20 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #endif
   const int m_blocks = (p.M + BM - 1) / BM;
   const int n_chunks = p.FF / CH;
-  const int my_tiles = m_blocks > static_cast<int>(blockIdx.x)
-                           ? (m_blocks - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x)
-                           : 0;
+  // tile schedule: group g (a cluster, or a single CTA) takes tile groups g, g + n_groups, ...; inside a group the CTA
+  // of rank r takes tile 2 * group + r.  Both CTAs of a cluster run the same number of tiles (the weight stream is shared);
+  // a tile index >= m_blocks is a phantom tile: its loads read zeros, its stores are clipped by the tensor maps.
+  constexpr int kStride = kMC ? 2 : 1;
+  const int rank = kMC ? static_cast<int>(cluster_ctarank()) : 0;
+  const int group = static_cast<int>(blockIdx.x) / kStride, n_groups = static_cast<int>(gridDim.x) / kStride;
+  const int tile_groups = (m_blocks + kStride - 1) / kStride;
+  const int my_tiles = tile_groups > group ? (tile_groups - group + n_groups - 1) / n_groups : 0;
+  auto tile_of = [&](int it) { return (group + it * n_groups) * kStride + rank; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmW1); tma_prefetch_desc(&tmW2); tma_prefetch_desc(&tmOut);
     if (p.has_out_pos) tma_prefetch_desc(&tmOutPos);
-    for (int s = 0; s < W_STAGES; ++s) { mbar_init(&bars->w_full[s], 1); mbar_init(&bars->w_empty[s], 1); }
+    for (int s = 0; s < W_STAGES; ++s) { mbar_init(&bars->w_full[s], 1); mbar_init(&bars->w_empty[s], kMC ? 2 : 1); }
     mbar_init(&bars->x_full, 1);    mbar_init(&bars->x_free, 1);
     mbar_init(&bars->hacc_full, 1); mbar_init(&bars->hacc_free, EPI_WARPS);
     mbar_init(&bars->h_ready, EPI_WARPS); mbar_init(&bars->h_free, 1);
@@ -162,6 +177,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  if (kMC) cluster_sync_all();       // the peer's barriers are initialised before any multicast traffic targets them
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp < FIRST_EPI_WARP) {
@@ -174,7 +190,11 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           for (int kb = 0; kb < STAGES_PER_GEMM; ++kb) {
             mbar_wait(&bars->w_empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&bars->w_full[stage], W_STAGE_BYTES);
-            tma_load_2d(smem + OFF_W + stage * W_STAGE_BYTES, tm, &bars->w_full[stage], k0 + kb * BKW, n0);
+            if (kMC)      // this CTA's 128 rows of the block, delivered to both CTAs (the peer sends the other 128)
+              tma_load_2d_multicast(smem + OFF_W + stage * W_STAGE_BYTES + rank * (W_STAGE_BYTES / 2), tm, &bars->w_full[stage],
+                                    k0 + kb * BKW, n0 + rank * 128, 0x3);
+            else
+              tma_load_2d(smem + OFF_W + stage * W_STAGE_BYTES, tm, &bars->w_full[stage], k0 + kb * BKW, n0);
             if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
           }
         };
@@ -190,7 +210,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       // ------------------------------------------------------------------ x-tile producer
       if (elect_one()) {
         for (int it = 0; it < my_tiles; ++it) {
-          const int m_blk = blockIdx.x + it * gridDim.x;
+          const int m_blk = tile_of(it);
           mbar_wait(&bars->x_free, (it & 1) ^ 1);
           mbar_arrive_expect_tx(&bars->x_full, X_BYTES);
           for (int kb = 0; kb < D / BKX; ++kb)
@@ -214,7 +234,8 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             const uint64_t b = dW + static_cast<uint64_t>(stage * (W_STAGE_BYTES >> 4));
 #pragma unroll
             for (int k = 0; k < BKW / 16; ++k) umma_bf16_ss(d_tmem, a + 2 * k, b + 2 * k, idesc, (fresh && s == 0 && k == 0) ? 0u : 1u);
-            umma_commit(&bars->w_empty[stage]);
+            if (kMC) umma_commit_multicast(&bars->w_empty[stage], 0x3);      // the slot is shared: release it in both CTAs
+            else umma_commit(&bars->w_empty[stage]);
             if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
           }
         };
@@ -282,7 +303,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     };
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int m_blk = blockIdx.x + it * gridDim.x;
+      const int m_blk = tile_of(it);
       const int row = m_blk * BM + r;
       for (int c = 0; c < n_chunks; ++c) {
         // ---- chunk epilogue: H_c = GELU(acc + b1_c) -> bf16 -> shared memory operand of MMA 2
@@ -424,6 +445,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
   tcgen05_fence_before();
   __syncthreads();
+  if (kMC) cluster_sync_all();       // no CTA exits while its peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -440,9 +462,15 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
   CUtensorMap tmX, tmW1, tmW2, tmOut, tmOutPos;
   int rc = make_tensor_map_2d(&tmX, a.x, D, a.M, a.ldx, BKX, BM, 128);
   if (rc) return rc;
-  rc = make_tensor_map_2d(&tmW1, a.w1, D, a.ff, a.ldw1, BKW, 256, 64);
+  const int m_blocks = (a.M + BM - 1) / BM;
+  static const bool mc_enabled = [] { const char* e = getenv("SVOL_FFN_MULTICAST"); return !(e && e[0] == '0'); }();
+  // measured (B200, C2): 50176 tokens (392 tiles, persistent, 3 waves) 129.7 -> 122.1 us with multicast; 10240 tokens (80 tiles,
+  // one wave) 53.5 -> 55.4 us: the pairing only pays when every SM streams the weights several times
+  const bool multicast = mc_enabled && m_blocks > sm_count() && sm_count() >= 2;
+  const int w_box_rows = multicast ? 128 : 256;        // multicast: each CTA of the pair loads half of a weight block
+  rc = make_tensor_map_2d(&tmW1, a.w1, D, a.ff, a.ldw1, BKW, w_box_rows, 64);
   if (rc) return rc;
-  rc = make_tensor_map_2d(&tmW2, a.w2, a.ff, D, a.ldw2, BKW, 256, 64);
+  rc = make_tensor_map_2d(&tmW2, a.w2, a.ff, D, a.ldw2, BKW, w_box_rows, 64);
   if (rc) return rc;
   rc = make_tensor_map_2d(&tmOut, a.out, D, a.M, a.ld_out, BKX, BM, 128);
   if (rc) return rc;
@@ -450,7 +478,8 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ffn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return svol_fail_cuda(e, "ffn: cudaFuncSetAttribute");
     configured = true;
   }
@@ -458,9 +487,24 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
   p.b1 = a.b1; p.b2 = a.b2; p.ln_w = a.ln_weight; p.ln_b = a.ln_bias; p.pos = a.pos; p.pos_theta = a.pos_theta;
   p.ld_pos = a.ld_pos; p.pos_row_mod = a.pos_row_mod; p.ln_eps = a.ln_eps; p.M = a.M; p.FF = a.ff;
   p.has_out_pos = a.out_pos != nullptr;
-  const int m_blocks = (a.M + BM - 1) / BM;
+  if (multicast) {
+    const int pairs = std::min((m_blocks + 1) / 2, sm_count() / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ffn_tc_kernel<true>, tmX, tmW1, tmW2, tmOut, tmOutPos, p);
+    if (e != cudaSuccess) return svol_fail_cuda(e, "ffn: cluster launch");
+    return svol_check_launch("ffn_tc (2-CTA multicast)");
+  }
   const int grid = m_blocks < sm_count() ? m_blocks : sm_count();
-  ffn_tc_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, tmOutPos, p);
+  ffn_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, tmOutPos, p);
   return svol_check_launch("ffn_tc");
 }
 
