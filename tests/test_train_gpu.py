@@ -133,7 +133,8 @@ def _head_t(x, B, L, Lp):
 
 
 @pytest.mark.parametrize("B,Lq,Lk,masked", [(2, 128, 128, False), (2, 320, 320, False), (3, 320, 1568, True),
-                                            (2, 1568, 1568, False), (1, 100, 200, True)])
+                                            (2, 1568, 1568, False), (1, 100, 200, True),
+                                            (1, 1280, 6272, True), (1, 6272, 6272, False)])      # long clip (config C4)
 def test_attention_backward(B, Lq, Lk, masked):
     from svol_b200 import ops
     H, dh = 8, 32
