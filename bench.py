@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=2, help="pairs per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default="", help="write the per-kernel time table to this file")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2, 3, 4],
+                    help="fwd_match mode: batches in flight (n: consecutive steps rotate over n streams / forward workspaces)")
     ap.add_argument("--mode", default="fwd_match", choices=["fwd_match", "train"],
                     help="fwd_match: the headline metric (BASELINE configs[1]); train: the training step of BASELINE "
                          "configs[2] (forward + matching + losses + backward + gradient all-reduce + AdamW)")
@@ -61,7 +63,8 @@ def workload_config(args, cfg):
             "pairs_per_gpu_per_step": args.batch, "layers": cfg.num_layers,
             "l2": "two alternating input sets (2 x %.0f MB frame features) and a >1 GB per-step activation stream: "
                   "no step finds its inputs in the 126 MB L2" % (args.batch * cfg.video_len * cfg.input_vid_dim * 4 / 1e6),
-            "parallelism": f"dp{args.gpus} (independent pairs, no collective)"}
+            "parallelism": f"dp{args.gpus} (independent pairs, no collective)",
+            "batches_in_flight": getattr(args, "streams", 1)}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -243,11 +246,30 @@ def main():
         devt = {k: v.to(dev) for k, v in host.items()}
         sets.append({"host": host, "dev": devt, "targets": tg})
 
+    # Two batches in flight: step i runs on stream i & 1 (its own forward workspace and graph, HeadEngine.plan_for), so
+    # the low-occupancy tail of one step (object-query chain, heads, matcher, criterion) overlaps the head of the next.
+    # Pairs are independent; every step's work completes inside the timed region (both streams are joined before e1).
+    step_streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)] if args.streams > 1 else None
+
     def step_resident(i):
         s = sets[i & 1]
         d = s["dev"]
-        out = model(d["src_sketch"], d["src_sketch_mask"], d["src_video"], d["src_video_mask"])
-        return criterion(out, s["targets"])
+        if step_streams is None:
+            out = model(d["src_sketch"], d["src_sketch_mask"], d["src_video"], d["src_video_mask"])
+            return criterion(out, s["targets"])
+        with torch.cuda.stream(step_streams[i % len(step_streams)]):
+            out = model(d["src_sketch"], d["src_sketch_mask"], d["src_video"], d["src_video_mask"])
+            return criterion(out, s["targets"])
+
+    def fork_streams():
+        if step_streams is not None:
+            for st in step_streams:
+                st.wait_stream(torch.cuda.current_stream())
+
+    def join_streams():
+        if step_streams is not None:
+            for st in step_streams:
+                torch.cuda.current_stream().wait_stream(st)
 
     # ---- end-to-end path: host buffers in, losses out, through the public API (model(...), criterion(...)).
     # Two device staging sets; the H2D copy of step i+1 runs on a copy stream while step i computes, and the
@@ -309,8 +331,10 @@ def main():
             if whole_loop:
                 fn(steps)
             else:
+                fork_streams()                      # the step streams start after e0 ...
                 for i in range(steps):
                     fn(i)
+                join_streams()                      # ... and e1 is recorded after both have drained
             e1.record()
             barrier()
         return comm.max_over_ranks(e0.elapsed_time(e1), device=dev) / steps      # slowest rank
@@ -321,6 +345,7 @@ def main():
     ms_e2e = timed(run_e2e, args.steps, 3, whole_loop=True)
     with torch.no_grad():
         step_resident(0)
+    torch.cuda.synchronize()
     criterion.check_status()
 
     flat = criterion.last_indices[2]
@@ -586,6 +611,9 @@ def kernel_breakdown(model, inset, cfg, B, dev):
         peaks.update(json.load(open(pk)))
         peaks["_src"] = "measured"
     eng = model.engine
+    d = inset["dev"]
+    with torch.no_grad():           # fills the current stream's workspace (plans are per stream) with this input set
+        model(d["src_sketch"], d["src_sketch_mask"], d["src_video"], d["src_video_mask"])
     plan = eng.plan_for(B, cfg.video_len, cfg.input_vid_dim)
     stream = torch.cuda.current_stream().cuda_stream
     reps = 5

@@ -151,7 +151,7 @@ class HeadEngine:
         self._w: Dict[str, torch.Tensor] = {}
         self._wstate = None
         self._packer = WeightPacker()
-        self._plans: Dict[Tuple[int, int, int], _Plan] = {}
+        self._plans: Dict[Tuple[int, int, int, int], _Plan] = {}
         self._side = None                  # (query, input) capture streams: the forked branches of the forward graph
         self.launches_per_forward = 0
 
@@ -465,8 +465,11 @@ class HeadEngine:
 
     # ------------------------------------------------------------------ run
     def plan_for(self, B: int, L: int, d_in: int) -> _Plan:
+        """The plan (workspace + recorded launches + CUDA graph) of this input shape ON THE CURRENT STREAM: a caller that
+        keeps two batches in flight on two streams gets two independent workspaces, so the low-occupancy tail of one
+        forward (the object-query chain, the heads) overlaps the large frame-token kernels of the next."""
         self._weights()
-        key = (B, L, d_in)
+        key = (B, L, d_in, torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0)
         plan = self._plans.get(key)
         if plan is None:
             plan = self._build_plan(B, L, d_in)

@@ -124,7 +124,7 @@ class SVANet(nn.Module):
                 raise NotImplementedError("vis_mode returns detached decoder states; use it under torch.no_grad()")
             key = tuple(src_video.shape) if src_video.dim() == 3 else \
                 (src_video.shape[0], src_video.shape[1] * src_video.shape[3] * src_video.shape[4], src_video.shape[2])
-            hs = self._engine._plans[key].buf["hs"]
+            hs = self._engine.plan_for(*key).buf["hs"]
             return out, hs.float().view(hs.shape[0], src_video.shape[0], self.num_queries, -1)
         return out
 
