@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 10
+#define SVOL_ABI_VERSION 11
 
 enum {
   SVOL_OK = 0,
@@ -177,6 +177,11 @@ int svol_attention_bf16_plain(const svol_attn_args* args, void* stream);   /* SI
 /* y = LayerNorm(x) rows of `cols` fp32 -> bf16.  First op of LinearLayer (svanet.py:174-176). */
 int svol_layernorm_f32_to_bf16(const float* x, const float* weight, const float* bias, svol_bf16* y,
                                int32_t rows, int32_t cols, float eps, void* stream);
+
+/* The same first LayerNorm for frame features kept in bf16 by the caller (a precomputed feature cache; the reference
+ * stores its sketch features precomputed, preprocess/sketch_vit_feature_extractor.py): x [rows, cols] bf16. */
+int svol_layernorm_bf16_to_bf16(const svol_bf16* x, const float* weight, const float* bias, svol_bf16* y, int32_t rows,
+                                int32_t cols, float eps, void* stream);
 
 /* Backbone hand-off (backbone.py:72-89, model.py:18-22): x [frames, channels, spatial] fp32 is the ResNet
  * trunk's (N*T, C, h, w) feature map as cuDNN leaves it; y [frames*spatial, channels] bf16 = LayerNorm over the channels

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsvol_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -26,7 +26,7 @@ SYMBOLS = [
     "svol_layernorm_bf16", "svol_layernorm_backward", "svol_gelu_bf16", "svol_act_backward", "svol_transpose_bf16",
     "svol_colsum_bf16", "svol_attention_backward_bf16", "svol_heads_backward", "svol_gate_backward",
     "svol_gate_vectors_backward", "svol_ln_linear_f32_backward", "svol_batch_sum", "svol_accum_bf16", "svol_adamw",
-    "svol_pack_weights", "svol_layernorm_f32_to_bf16_dropout", "svol_ln_linear_f32_dropout", "svol_layernorm_nchw_to_bf16",
+    "svol_pack_weights", "svol_layernorm_f32_to_bf16_dropout", "svol_ln_linear_f32_dropout", "svol_layernorm_nchw_to_bf16", "svol_layernorm_bf16_to_bf16",
     "svol_eval_max_iou", "svol_eval_average_precision",
 ]
 
@@ -128,6 +128,7 @@ def _declare(lib: C.CDLL) -> None:
         "svol_layernorm_f32_to_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
         "svol_ln_linear_f32": [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _f32, _vp],
         "svol_layernorm_nchw_to_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp],
+        "svol_layernorm_bf16_to_bf16": [_vp, _vp, _vp, _vp, _i32, _i32, _f32, _vp],
         "svol_posenc_sine": [_vp, _vp, _i32, _i32, _i32, _vp],
         "svol_posenc_theta": [_vp, _vp, _i32, _i32, _vp],
         "svol_add_pos_bf16": [_vp, _vp, _vp, _i32, _i32, _i32, _vp],

@@ -86,6 +86,7 @@ int launch_layernorm_f32_to_bf16(const float*, const float*, const float*, svol_
                                  cudaStream_t);
 int launch_ln_linear_f32(const float*, const float*, const float*, const float*, const float*, int, float*, int, int, int,
                          float, float, const long long*, int, cudaStream_t);
+int launch_layernorm_bf16_to_bf16(const svol_bf16*, const float*, const float*, svol_bf16*, int, int, float, cudaStream_t);
 int launch_layernorm_nchw_to_bf16(const float*, const float*, const float*, svol_bf16*, int, int, int, float, cudaStream_t);
 int launch_posenc_sine(const float*, float*, int, int, int, cudaStream_t);
 int launch_posenc_theta(const float*, float*, int, int, cudaStream_t);
@@ -206,6 +207,11 @@ int svol_ln_linear_f32_dropout(const float* x, const float* lw, const float* lb,
   SVOL_REQUIRE(x); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
   return launch_ln_linear_f32(x, lw, lb, w, b, relu, y, rows, in_dim, out_dim, eps, drop_p, reinterpret_cast<const long long*>(seed),
                               site, SVOL_STREAM(stream));
+}
+int svol_layernorm_bf16_to_bf16(const svol_bf16* x, const float* w, const float* b, svol_bf16* y, int32_t rows, int32_t cols,
+                                float eps, void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(w); SVOL_REQUIRE(b); SVOL_REQUIRE(y);
+  return launch_layernorm_bf16_to_bf16(x, w, b, y, rows, cols, eps, SVOL_STREAM(stream));
 }
 int svol_layernorm_nchw_to_bf16(const float* x, const float* w, const float* b, svol_bf16* y, int32_t frames, int32_t channels,
                                 int32_t spatial, float eps, void* stream) {

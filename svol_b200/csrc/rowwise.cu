@@ -12,8 +12,15 @@ namespace svol {
 // ---------------------------------------------------------------------------------------------
 constexpr int LN_MAXV = 8;   // float4 per lane -> cols <= 1024
 
-template <bool kDrop>
-__global__ void __launch_bounds__(256) layernorm_f32_to_bf16_kernel(const float* __restrict__ x,
+// 16-byte load of four consecutive inputs (fp32) / eight consecutive inputs (bf16 feature caches) as floats
+__device__ __forceinline__ float4 ln_load4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ln_load4(const __nv_bfloat16* p) {
+  const uint2 q = __ldcs(reinterpret_cast<const uint2*>(p));
+  return make_float4(bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y));
+}
+
+template <bool kDrop, typename TIn>
+__global__ void __launch_bounds__(256) layernorm_f32_to_bf16_kernel(const TIn* __restrict__ x,
                                                                      const float* __restrict__ w,
                                                                      const float* __restrict__ b,
                                                                      __nv_bfloat16* __restrict__ y, int rows,
@@ -21,7 +28,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_to_bf16_kernel(const float*
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * cols);
+  const TIn* xr = x + static_cast<size_t>(row) * cols;
   const int nv = cols >> 2;
   float4 buf[LN_MAXV];
   float s = 0.f;
@@ -29,7 +36,7 @@ __global__ void __launch_bounds__(256) layernorm_f32_to_bf16_kernel(const float*
   for (int i = 0; i < LN_MAXV; ++i) {
     const int idx = i * 32 + lane;
     if (idx < nv) {
-      buf[i] = __ldcs(xr + idx);       // streamed once
+      buf[i] = ln_load4(xr + idx * 4);       // streamed once
       s += (buf[i].x + buf[i].y) + (buf[i].z + buf[i].w);
     }
   }
@@ -76,12 +83,23 @@ int launch_layernorm_f32_to_bf16(const float* x, const float* w, const float* b,
   const int wpb = 8;
   const DropoutCfg drop{drop_p, seed, site};
   if (drop_p > 0.f)
-    layernorm_f32_to_bf16_kernel<true><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
+    layernorm_f32_to_bf16_kernel<true, float><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
         x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, drop);
   else
-    layernorm_f32_to_bf16_kernel<false><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
+    layernorm_f32_to_bf16_kernel<false, float><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
         x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, drop);
   return svol_check_launch("layernorm_f32_to_bf16");
+}
+
+// Same LayerNorm for frame features the caller keeps in bf16 (a precomputed feature cache): half the bytes to read and,
+// when they come from the host, half the PCIe traffic of the step.
+int launch_layernorm_bf16_to_bf16(const svol_bf16* x, const float* w, const float* b, svol_bf16* y, int rows, int cols,
+                                  float eps, cudaStream_t stream) {
+  if (cols % 4 != 0 || cols > LN_MAXV * 128 || rows <= 0) return svol_fail(SVOL_ERR_SHAPE, "layernorm: cols % 4 == 0, cols <= 1024");
+  const int wpb = 8;
+  layernorm_f32_to_bf16_kernel<false, __nv_bfloat16><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, DropoutCfg{0.f, nullptr, 0});
+  return svol_check_launch("layernorm_bf16_to_bf16");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -496,9 +496,13 @@ class HeadEngine:
         # eagerly and reads the caller's tensor in place; everything after it works on plan-owned buffers and can
         # be replayed as one CUDA graph.
         src = src_video
+        bf16_in = (not fmap) and src.dtype == torch.bfloat16      # frame features kept in bf16 by the caller (feature cache)
         if fmap:
             if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
                 src = src.to(device=b["src_video"].device, dtype=torch.float32).contiguous()
+        elif bf16_in:
+            if not (src.is_cuda and src.is_contiguous() and src.data_ptr() % 16 == 0):
+                src = src.to(device=b["src_video"].device).contiguous()
         elif not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous() and src.data_ptr() % 16 == 0):
             b["src_video"].copy_(src_video, non_blocking=True)
             src = b["src_video"]
@@ -512,6 +516,9 @@ class HeadEngine:
         name, fn, args = plan.calls[0]
         if fmap:   # LayerNorm straight from the channel-major feature map: no permuted fp32 copy
             rc = _lib.get_lib().svol_layernorm_nchw_to_bf16(src.data_ptr(), args[1], args[2], args[3], B * T, d_in, fh * fw, LN_EPS,
+                                                            torch.cuda.current_stream().cuda_stream)
+        elif bf16_in:
+            rc = _lib.get_lib().svol_layernorm_bf16_to_bf16(src.data_ptr(), args[1], args[2], args[3], B * L, d_in, LN_EPS,
                                                             torch.cuda.current_stream().cuda_stream)
         else:
             rc = fn(src.data_ptr(), *args[1:], torch.cuda.current_stream().cuda_stream)

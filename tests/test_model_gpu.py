@@ -189,3 +189,22 @@ def test_backbone_handoff_feature_map():
     ref = orc.layer_norm(tokens.reshape(-1, C), w, b)
     err = np.abs(y.float().cpu().numpy() - ref)
     assert (err <= 2.0 ** -8 * np.abs(ref) + 1e-3).all(), float(err.max())
+
+
+def test_bf16_frame_features_input():
+    """Frame features handed over in bf16 (a feature cache): identical to the fp32 path fed with the same bf16-rounded
+    values (the first LayerNorm converts on load)."""
+    import torch
+    from svol_b200 import synth
+    from svol_b200.modeling import build_svanet
+    cfg = synth.CONFIGS["C1b"]
+    model = build_svanet(cfg.to_namespace())
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.random_state_dict(cfg, 6).items()}, strict=True)
+    model = model.to("cuda:0").eval()
+    inp = synth.make_inputs(cfg, 2, 6, padded=True)
+    t = lambda k: torch.from_numpy(inp[k]).to("cuda:0")
+    xb = t("src_video").to(torch.bfloat16)
+    with torch.no_grad():
+        a = {k: v.clone() for k, v in model(t("src_sketch"), t("src_sketch_mask"), xb, t("src_video_mask")).items() if k != "aux_outputs"}
+        b = model(t("src_sketch"), t("src_sketch_mask"), xb.float(), t("src_video_mask"))
+    assert torch.equal(a["pred_logits"], b["pred_logits"]) and torch.equal(a["pred_boxes"], b["pred_boxes"])
