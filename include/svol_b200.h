@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 11
+#define SVOL_ABI_VERSION 12
 
 enum {
   SVOL_OK = 0,
@@ -227,6 +227,16 @@ int svol_gate_apply(const svol_bf16* x, const float* scores, const float* ln_wei
 int svol_gate_apply_theta(const svol_bf16* x, const float* scores, const float* ln_weight, const float* ln_bias,
                           const float* theta, svol_bf16* mem, svol_bf16* mem_pos, float* att_out, int32_t B, int32_t L,
                           int32_t d, int32_t H, float eps, void* stream);
+
+/* svol_gate_scores + the softmax + svol_gate_apply_theta in ONE launch (cross_modal_transformer.py:122-127): a cluster of
+ * 8 CTAs per sample keeps the sample's token rows in shared memory (read from HBM once), forms the scores from x + pos
+ * in fp32 (positions evaluated from theta) and closes the softmax over the L tokens through distributed shared memory.
+ * Available when a sample's rows fit one cluster (svol_gate_fused_supported(L) == 1, L <= 3384); att_out [B,L] and
+ * scores_out [B,H,L] are optional (NULL). */
+int svol_gate_fused_supported(int32_t L);
+int svol_gate_fused(const svol_bf16* x, const float* u, const float* ln_weight, const float* ln_bias, const float* theta,
+                    svol_bf16* mem, svol_bf16* mem_pos, float* att_out, float* scores_out, int32_t B, int32_t L,
+                    int32_t d, int32_t H, float eps, void* stream);
 
 /* Output heads (svanet.py:125-127): logits = class_embed(hs); boxes = sigmoid(bbox_embed.layers.2(h2))
  * where h2 is the output of the two hidden box-MLP layers (svol_gemm_bf16 with ReLU).

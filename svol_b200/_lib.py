@@ -13,14 +13,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsvol_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "svol_abi_version", "svol_last_error", "svol_device_check", "svol_sizeof_args",
     "svol_gemm_bf16", "svol_gemm_bf16_plain", "svol_ffn_bf16", "svol_attention_bf16", "svol_attention_bf16_plain",
     "svol_layernorm_f32_to_bf16", "svol_ln_linear_f32", "svol_posenc_sine", "svol_posenc_theta", "svol_add_pos_bf16",
-    "svol_gate_vectors", "svol_gate_scores", "svol_gate_apply", "svol_gate_apply_theta", "svol_heads",
+    "svol_gate_vectors", "svol_gate_scores", "svol_gate_apply", "svol_gate_apply_theta", "svol_gate_fused",
+    "svol_gate_fused_supported", "svol_heads",
     "svol_match", "svol_match_localize", "svol_criterion", "svol_criterion_backward", "svol_postprocess",
     # training step
     "svol_layernorm_bf16", "svol_layernorm_backward", "svol_gelu_bf16", "svol_act_backward", "svol_transpose_bf16",
@@ -136,6 +137,8 @@ def _declare(lib: C.CDLL) -> None:
         "svol_gate_scores": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp],
         "svol_gate_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
         "svol_gate_apply_theta": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
+        "svol_gate_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _vp],
+        "svol_gate_fused_supported": [_i32],
         "svol_heads": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp],
         "svol_match": [C.POINTER(MatchArgs), _vp],
         "svol_match_localize": [_vp, _vp, _i32, _i32, _i32, _vp],

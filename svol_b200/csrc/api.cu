@@ -110,6 +110,9 @@ int launch_colsum_bf16(const svol_bf16*, int, int, int, float*, cudaStream_t);
 int launch_attention_backward_tc(const svol_attn_bwd_args&, cudaStream_t);
 int launch_heads_backward(const svol_bf16*, const svol_bf16*, const float*, const float*, const float*, const float*, const float*,
                           svol_bf16*, svol_bf16*, float*, float*, float*, float*, int, int, cudaStream_t);
+int launch_gate_fused(const svol_bf16*, const float*, const float*, const float*, const float*, svol_bf16*, svol_bf16*, float*,
+                      float*, int, int, int, int, float, cudaStream_t);
+int gate_fused_supported(int);
 int launch_gate_backward(const svol_bf16*, const float*, const float*, const float*, const svol_bf16*, svol_bf16*, float*, float*,
                          int, int, int, int, cudaStream_t);
 int launch_gate_vectors_backward(const float*, const float*, const float*, const float*, float*, float*, float*, int, int, int,
@@ -254,6 +257,14 @@ int svol_gate_apply_theta(const svol_bf16* x, const float* scores, const float* 
   SVOL_REQUIRE(x); SVOL_REQUIRE(scores); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(theta); SVOL_REQUIRE(mem);
   SVOL_REQUIRE(mem_pos);
   return launch_gate_apply(x, scores, lw, lb, theta, mem, mem_pos, att_out, B, L, d, H, eps, true, SVOL_STREAM(stream));
+}
+int svol_gate_fused_supported(int32_t L) { return gate_fused_supported(L); }
+int svol_gate_fused(const svol_bf16* x, const float* u, const float* lw, const float* lb, const float* theta, svol_bf16* mem,
+                    svol_bf16* mem_pos, float* att_out, float* scores_out, int32_t B, int32_t L, int32_t d, int32_t H, float eps,
+                    void* stream) {
+  SVOL_REQUIRE(x); SVOL_REQUIRE(u); SVOL_REQUIRE(lw); SVOL_REQUIRE(lb); SVOL_REQUIRE(theta); SVOL_REQUIRE(mem);
+  SVOL_REQUIRE(mem_pos);
+  return launch_gate_fused(x, u, lw, lb, theta, mem, mem_pos, att_out, scores_out, B, L, d, H, eps, SVOL_STREAM(stream));
 }
 int svol_heads(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const float* bc, const float* wb,
                const float* bb, float* logits, float* boxes, int32_t rows, int32_t d, void* stream) {

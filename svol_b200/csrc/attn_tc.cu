@@ -200,6 +200,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int q0 = blockIdx.x * (2 * BQ), h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (Lk + BKV - 1) / BKV;
   const int n_q = (q0 + BQ < Lq) ? 2 : 1;          // is the second query tile of this CTA populated?
+  // key tiles whose upper 64 keys hold at least one in-range key: when Lk % 128 is in (0, 64] the upper half of the last
+  // tile is empty and its QK^T / softmax / PV are skipped altogether (1568 keys: 1 of 26 half tiles; 320 keys: 1 of 6)
+  const int n_hi = Lk > HALF ? (Lk - HALF + BKV - 1) / BKV : 0;
 #ifdef SVOL_ATTN_TRACE
   const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && ((warp & 3) == 0 || warp >= 16);
 #endif
@@ -277,13 +280,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_bf16_ts(tmem_base + TMEM_O + g * DH, tmem_base + TMEM_P + g * 32 + k * 8, dVs + 2 * k, idesc_o,
                          (j > 0 || k > 0) ? 1u : 0u);
           umma_commit(&bars->o_full[g]);
-          if (half == 1) umma_commit(&bars->kv_empty[s]);   // last reader of stage s (covers every earlier MMA)
+          // last reader of stage s (covers every earlier MMA); a last tile without an upper half is never reloaded
+          if (half == 1) umma_commit(&bars->kv_empty[s]);
         };
         mbar_wait(&bars->q_full, 0);
         for (int i = 0; i <= n_tiles + 1; ++i) {
           if (i < n_tiles) issue_qk(i, 0);
-          if (i >= 2) issue_pv(i - 2, 1);
-          if (i < n_tiles) issue_qk(i, 1);
+          if (i >= 2 && i - 2 < n_hi) issue_pv(i - 2, 1);
+          if (i < n_hi) issue_qk(i, 1);
           if (i >= 1 && i <= n_tiles) issue_pv(i - 1, 0);
         }
       }
@@ -329,7 +333,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t s_ready = 0;
       const uint32_t a_sfull = smem_u32(&bars->s_full[g]), a_ofull = smem_u32(&bars->o_full[g]);
 
-      for (int j = 0; j < n_tiles; ++j) {
+      const int n_mine = half ? n_hi : n_tiles;           // key tiles this warpgroup has keys in
+      for (int j = 0; j < n_mine; ++j) {
         const int kv0 = j * BKV + half * HALF;
         SVOL_TR(g, j, 0);
         if (!s_ready) mbar_wait(&bars->s_full[g], j & 1);
@@ -424,7 +429,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (!ok) mbar_wait(&bars->o_full[g], (j - 1) & 1);
           tcgen05_fence_after();
         }
-        if (j + 1 < n_tiles)   // probe the next score tile (its QK^T was issued when this tile's scores were read out)
+        if (j + 1 < n_mine)   // probe the next score tile (its QK^T was issued when this tile's scores were read out)
           asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_sf, [%0], %1;" ::"r"(a_sfull), "r"((j + 1) & 1) : "memory");
         SVOL_TR(g, j, 6);
         // P half tile -> tensor memory: lane = query row, 32 columns of packed bf16 pairs (the A operand of P V)
@@ -434,16 +439,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_ready[g]);
         s_ready = 0;
-        if (j + 1 < n_tiles) asm volatile("selp.u32 %0, 1, 0, p_sf;" : "=r"(s_ready));
+        if (j + 1 < n_mine) asm volatile("selp.u32 %0, 1, 0, p_sf;" : "=r"(s_ready));
         SVOL_TR(g, j, 7);
       }
 
       // ---- epilogue: O_g is complete once the last P V has landed; merge the two key halves of each row
-      mbar_wait(&bars->o_full[g], (n_tiles - 1) & 1);
-      tcgen05_fence_after();
       uint32_t o[DH];
-      tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
-      tmem_ld_wait();
+      if (n_mine > 0) {
+        mbar_wait(&bars->o_full[g], (n_mine - 1) & 1);
+        tcgen05_fence_after();
+        tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+        tmem_ld_wait();
+      } else {                                            // Lk <= 64: the upper-half warpgroups never ran (m = -inf, l = 0)
+#pragma unroll
+        for (int i = 0; i < DH; ++i) o[i] = 0u;
+      }
       const float l_mine = l2.x + l2.y;
       float* cmb = reinterpret_cast<float*>(smem + OFF_CMB) + (t * BQ + r) * CMB_STRIDE;
       if (half == 1) {

@@ -562,6 +562,287 @@ int launch_gate_apply(const svol_bf16* x, const float* scores, const float* lw, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// The whole gate in ONE launch (inference path): scores -> per-sample softmax statistics -> att -> LN1 -> mem, mem + pos.
+// A cluster of GF_CL CTAs owns one sample; each CTA bulk-copies its contiguous slice of token rows into shared memory
+// ONCE (cp.async.bulk, one mbarrier per 32-row chunk, everything in flight from the first cycle), computes the 8 head
+// scores per row from x + pos (positions evaluated from the angle, fp32, never rounded to bf16), and the softmax over the
+// sample's L tokens is closed with one exchange of (max, sum) pairs through distributed shared memory.  Against
+// gate_scores + gate_apply this drops the second read of the token rows, the (x + pos) operand, the score round trip
+// through HBM and one launch: compulsory traffic = B*L*d*2 read + 2*B*L*d*2 written.
+// ---------------------------------------------------------------------------------------------
+constexpr int GF_CHUNK = 32, GF_MAX_CHUNKS = 16, GF_ILP = 2;
+constexpr int GF_ROW_BYTES = GATE_D * 2;
+constexpr int GF_MAX_ROWS = GF_CHUNK * GF_MAX_CHUNKS;                 // token rows per CTA
+constexpr int GF_HDR_BYTES = 256;                                      // chunk barriers [16], local stats [8] float2, global [8] float2
+
+__host__ __device__ inline int gf_pad4(int n) { return (n + 3) & ~3; }
+__host__ __device__ inline size_t gf_smem_bytes(int rpc) {
+  return GF_HDR_BYTES + static_cast<size_t>(gf_pad4(rpc)) * (1 + GATE_H) * 4 + static_cast<size_t>(rpc) * GF_ROW_BYTES;
+}
+
+// columns (2k, 2k+1) = (sin, cos)(theta / 10000^(2k/d)) for this lane's four k (position_encoding.py:62-70)
+__device__ __forceinline__ void gate_sincos(float theta, const float (&idt)[4], float (&pp)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float a = theta * idt[i];
+    a = a > 3.14159265358979f ? a - 6.28318530717959f : a;     // theta in [0, 2 pi] -> [-pi, pi] for MUFU sin / cos
+    pp[2 * i] = __sinf(a);
+    pp[2 * i + 1] = __cosf(a);
+  }
+}
+
+// kCL CTAs per sample (cluster), kThreads threads per CTA: <8, 256> runs two CTAs per SM (<= 113 KB of rows each),
+// <4, 512> one CTA per SM; both keep 16 warps and the same number of token rows per SM.
+template <int kCL, int kThreads>
+__global__ void __launch_bounds__(kThreads, 512 / kThreads)
+gate_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ u, const float* __restrict__ lw,
+                  const float* __restrict__ lb, const float* __restrict__ theta, __nv_bfloat16* __restrict__ mem,
+                  __nv_bfloat16* __restrict__ mem_pos, float* __restrict__ att_out, float* __restrict__ scores_out,
+                  int L, int rpc, float eps) {
+  constexpr int NW = kThreads / 32;
+  extern __shared__ __align__(128) uint8_t gf_smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gf_smem);                    // [GF_MAX_CHUNKS]
+  float2* stat_local = reinterpret_cast<float2*>(gf_smem + 128);            // [GATE_H] (max, sum exp) over this CTA's rows
+  float2* stat_all = reinterpret_cast<float2*>(gf_smem + 192);              // [GATE_H] (max, 1 / sum exp) over the sample
+  const int rpc_pad = gf_pad4(rpc);
+  float* th_s = reinterpret_cast<float*>(gf_smem + GF_HDR_BYTES);           // [rpc_pad]
+  float* sc_s = th_s + rpc_pad;                                             // [GATE_H][rpc_pad]
+  uint4* rows_s = reinterpret_cast<uint4*>(sc_s + GATE_H * rpc_pad);        // [rpc][32]
+
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rank = static_cast<int>(cluster_ctarank());
+  const int l_begin = rank * rpc;
+  const int n_rows = max(0, min(L - l_begin, rpc));
+  const size_t row0 = static_cast<size_t>(b) * L + l_begin;
+  const int n_chunks = (n_rows + GF_CHUNK - 1) / GF_CHUNK;
+
+  if (tid == 0) {
+    for (int c = 0; c < n_chunks; ++c) mbar_init(&bars[c], 1);
+    fence_barrier_init();
+    for (int c = 0; c < n_chunks; ++c) {
+      const int nr = min(GF_CHUNK, n_rows - c * GF_CHUNK);
+      mbar_arrive_expect_tx(&bars[c], nr * GF_ROW_BYTES);
+      bulk_load_1d(rows_s + c * GF_CHUNK * 32, x + (row0 + c * GF_CHUNK) * GATE_D, nr * GF_ROW_BYTES, &bars[c]);
+    }
+  }
+  for (int i = tid; i < n_rows; i += kThreads) th_s[i] = __ldg(theta + row0 + i);
+  // this lane's 8 columns of every head's gate vector stay in registers
+  float ur[GATE_H][8];
+#pragma unroll
+  for (int h = 0; h < GATE_H; ++h) {
+    const float4* up = reinterpret_cast<const float4*>(u + (static_cast<size_t>(b) * GATE_H + h) * GATE_D) + lane * 2;
+    const float4 a = __ldg(up), c = __ldg(up + 1);
+    ur[h][0] = a.x; ur[h][1] = a.y; ur[h][2] = a.z; ur[h][3] = a.w;
+    ur[h][4] = c.x; ur[h][5] = c.y; ur[h][6] = c.z; ur[h][7] = c.w;
+  }
+  float idt[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)     // 10000^(-2k/d) = 2^(-k * log2(10000) * 2 / d), k = 4 lane + i
+    idt[i] = exp2f(-static_cast<float>(lane * 4 + i) * (13.287712379549449f * 2.0f / GATE_D));
+  __syncthreads();          // barrier inits and th_s visible
+
+  // ---- phase 1: scores of this CTA's rows (warp per row, GF_ILP independent rows in flight per warp)
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+  const int head = (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0);
+  uint32_t chunks_seen = 0;
+  for (int lr0 = warp; lr0 < n_rows; lr0 += GF_ILP * NW) {
+    uint4 q[GF_ILP];
+    float th[GF_ILP];
+#pragma unroll
+    for (int r = 0; r < GF_ILP; ++r) {
+      const int lr = lr0 + r * NW;
+      q[r] = make_uint4(0u, 0u, 0u, 0u); th[r] = 0.f;
+      if (lr < n_rows) {
+        const int c = lr / GF_CHUNK;
+        if (!((chunks_seen >> c) & 1u)) { mbar_wait(&bars[c], 0); chunks_seen |= 1u << c; }
+        q[r] = rows_s[lr * 32 + lane];
+        th[r] = th_s[lr];
+      }
+    }
+    float a1[GF_ILP];
+#pragma unroll
+    for (int r = 0; r < GF_ILP; ++r) {
+      float pp[8];
+      gate_sincos(th[r], idt, pp);
+      const float xv[8] = {bf16_lo(q[r].x) + pp[0], bf16_hi(q[r].x) + pp[1], bf16_lo(q[r].y) + pp[2], bf16_hi(q[r].y) + pp[3],
+                           bf16_lo(q[r].z) + pp[4], bf16_hi(q[r].z) + pp[5], bf16_lo(q[r].w) + pp[6], bf16_hi(q[r].w) + pp[7]};
+      float acc[GATE_H];
+#pragma unroll
+      for (int h = 0; h < GATE_H; ++h) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a = fmaf(xv[i], ur[h][i], a);
+        acc[h] = a;
+      }
+      // reduce-scatter butterfly (see gate_scores_kernel): every group of 4 lanes ends up with one head's score
+      float a4[4], a2[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = b16 ? acc[i] : acc[i + 4], keep = b16 ? acc[i + 4] : acc[i];
+        a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = b8 ? a4[i] : a4[i + 2], keep = b8 ? a4[i + 2] : a4[i];
+        a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      const float send = b4 ? a2[0] : a2[1], keep = b4 ? a2[1] : a2[0];
+      float t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      a1[r] = t;
+    }
+#pragma unroll
+    for (int r = 0; r < GF_ILP; ++r) {
+      const int lr = lr0 + r * NW;
+      if (lr < n_rows && (lane & 3) == 0) {
+        sc_s[head * rpc_pad + lr] = a1[r];
+        if (scores_out) scores_out[(static_cast<size_t>(b) * GATE_H + head) * L + l_begin + lr] = a1[r];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax statistics: warp h reduces head h over this CTA's rows, then the cluster exchanges (max, sum) pairs
+  if (warp < GATE_H) {
+    const float* sr = sc_s + warp * rpc_pad;
+    float m = -INFINITY;
+    for (int i = lane; i < n_rows; i += 32) m = fmaxf(m, sr[i]);
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int i = lane; i < n_rows; i += 32) sum += expf(sr[i] - m);
+    sum = warp_sum(sum);
+    if (lane == 0) stat_local[warp] = make_float2(m, n_rows > 0 ? sum : 0.f);
+  }
+  cluster_sync_all();
+  if (tid < GATE_H * kCL) {
+    const int h = tid / kCL, c = tid % kCL;
+    uint32_t remote;
+    float m_c, s_c;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(&stat_local[h])), "r"(c));
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(m_c), "=f"(s_c) : "r"(remote) : "memory");
+    float m = m_c;
+#pragma unroll
+    for (int o = kCL / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = m_c == -INFINITY ? 0.f : s_c * expf(m_c - m);
+#pragma unroll
+    for (int o = kCL / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (c == 0) stat_all[h] = make_float2(m, 1.f / sum);
+  }
+  // second cluster phase: arrive now (the remote reads above are done), wait before exit, so that no CTA's shared
+  // memory disappears while a peer may still be reading its statistics
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  __syncthreads();
+
+  // ---- phase 2: att, LN1(x (1 + att)), + pos
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(lw) + lane * 2), g1 = __ldg(reinterpret_cast<const float4*>(lw) + lane * 2 + 1);
+  const float4 o0 = __ldg(reinterpret_cast<const float4*>(lb) + lane * 2), o1 = __ldg(reinterpret_cast<const float4*>(lb) + lane * 2 + 1);
+  const float gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float gb[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+  const float2 st = lane < GATE_H ? stat_all[lane] : make_float2(0.f, 0.f);
+  for (int lr0 = warp; lr0 < n_rows; lr0 += GF_ILP * NW) {
+#pragma unroll
+    for (int r = 0; r < GF_ILP; ++r) {
+      const int lr = min(lr0 + r * NW, n_rows - 1);        // a tail slot recomputes (and rewrites) the last row
+      const size_t row = row0 + lr;
+      const uint4 q = rows_s[lr * 32 + lane];
+      float a = 0.f;
+      if (lane < GATE_H) a = expf(sc_s[lane * rpc_pad + lr] - st.x) * st.y;
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      const float att = __shfl_sync(0xffffffffu, a, 0) * (1.0f / GATE_H);
+      if (att_out && lane == 0) att_out[row] = att;
+      float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { v[i] = v[i] + att * v[i]; s += v[i]; }
+      const float mean = warp_sum(s) * (1.0f / GATE_D);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float dlt = v[i] - mean; ss += dlt * dlt; }
+      const float rstd = rsqrtf(warp_sum(ss) * (1.0f / GATE_D) + eps);
+      float pp[8];
+      gate_sincos(th_s[lr], idt, pp);
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = (v[i] - mean) * rstd * gw[i] + gb[i];
+      uint4 o, op;
+      o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]); o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+      op.x = pack_bf16x2(y[0] + pp[0], y[1] + pp[1]); op.y = pack_bf16x2(y[2] + pp[2], y[3] + pp[3]);
+      op.z = pack_bf16x2(y[4] + pp[4], y[5] + pp[5]); op.w = pack_bf16x2(y[6] + pp[6], y[7] + pp[7]);
+      reinterpret_cast<uint4*>(mem + row * GATE_D)[lane] = o;
+      reinterpret_cast<uint4*>(mem_pos + row * GATE_D)[lane] = op;
+    }
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// cluster size for a launch: 4 CTAs of 512 threads (one per SM) when a quarter of a sample fits one CTA's shared memory
+// and the batch still fills the GPU, else 8 CTAs of 256 threads (two per SM); 0 = the rows do not fit (L > 3384)
+static int gate_fused_cluster(int B, int L) {
+  if (L <= 0) return 0;
+  static const int forced = [] { const char* e = getenv("SVOL_GATE_CL"); return e ? atoi(e) : 0; }();
+  for (int cl : {4, 8}) {
+    const int rpc = (L + cl - 1) / cl;
+    const bool fits = rpc <= GF_MAX_ROWS && gf_smem_bytes(rpc) <= (cl == 4 ? 227u : 113u) * 1024u;
+    if (forced == cl && rpc <= GF_MAX_ROWS && gf_smem_bytes(rpc) <= 227u * 1024u) return cl;
+    if (forced == 0 && fits && (cl == 8 || B * 4 >= 96)) return cl;
+  }
+  const int rpc = (L + 7) / 8;       // 8 CTAs, one per SM
+  return (rpc <= GF_MAX_ROWS && gf_smem_bytes(rpc) <= 227u * 1024u) ? 8 : 0;
+}
+
+// 1 when the fused kernel can keep a sample's token rows in the shared memory of one cluster (L <= 3384)
+int gate_fused_supported(int L) { return gate_fused_cluster(1, L) != 0; }
+
+template <int kCL, int kThreads>
+static int launch_gate_fused_t(const svol_bf16* x, const float* u, const float* lw, const float* lb, const float* theta,
+                               svol_bf16* mem, svol_bf16* mem_pos, float* att_out, float* scores_out, int B, int L, float eps,
+                               cudaStream_t stream) {
+  const int rpc = (L + kCL - 1) / kCL;
+  const size_t smem = gf_smem_bytes(rpc);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(gate_fused_kernel<kCL, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return svol_fail_cuda(e, "gate_fused: cudaFuncSetAttribute");
+    configured = smem;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCL, B);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (getenv("SVOL_DEBUG_OCC")) {
+    int n = -1;
+    cudaOccupancyMaxActiveClusters(&n, gate_fused_kernel<kCL, kThreads>, &cfg);
+    fprintf(stderr, "gate_fused<%d,%d>: %d clusters requested, %d co-resident, %zu B smem\n", kCL, kThreads, B, n, smem);
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gate_fused_kernel<kCL, kThreads>, reinterpret_cast<const __nv_bfloat16*>(x), u, lw, lb,
+                                     theta, reinterpret_cast<__nv_bfloat16*>(mem), reinterpret_cast<__nv_bfloat16*>(mem_pos),
+                                     att_out, scores_out, L, rpc, eps);
+  if (e != cudaSuccess) return svol_fail_cuda(e, "gate_fused: cluster launch");
+  return svol_check_launch("gate_fused");
+}
+
+int launch_gate_fused(const svol_bf16* x, const float* u, const float* lw, const float* lb, const float* theta, svol_bf16* mem,
+                      svol_bf16* mem_pos, float* att_out, float* scores_out, int B, int L, int d, int H, float eps,
+                      cudaStream_t stream) {
+  if (d != GATE_D || H != GATE_H || B <= 0 || L <= 0) return svol_fail(SVOL_ERR_SHAPE, "gate_fused: hidden_dim 256 / 8 heads only");
+  const int cl = gate_fused_cluster(B, L);
+  if (cl == 0) return svol_fail(SVOL_ERR_SHAPE, "gate_fused: a sample's tokens do not fit one cluster's shared memory (use gate_scores + gate_apply)");
+  if (reinterpret_cast<uintptr_t>(x) % 16 != 0) return svol_fail(SVOL_ERR_SHAPE, "gate_fused: x must be 16-byte aligned");
+  if (cl == 4) return launch_gate_fused_t<4, 512>(x, u, lw, lb, theta, mem, mem_pos, att_out, scores_out, B, L, eps, stream);
+  return launch_gate_fused_t<8, 256>(x, u, lw, lb, theta, mem, mem_pos, att_out, scores_out, B, L, eps, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Output heads (svanet.py:125-127): class logits and sigmoid of the last box-MLP layer
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ hs,

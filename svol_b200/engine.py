@@ -353,6 +353,10 @@ class HeadEngine:
             if after:
                 plan.after[name] = list(after)
 
+        # the gate runs as one cluster kernel when a sample's token rows fit one cluster's shared memory (L <= 3384);
+        # longer clips (config C4) and the SIMT debug path keep gate_scores + gate_apply (SVOL_B200_GATE=split forces them)
+        fused_gate = (not self.plain and os.environ.get("SVOL_B200_GATE", "fused") != "split"
+                      and bool(lib.svol_gate_fused_supported(L)))
         # ---- input projection of the frame tokens (svanet.py:49-55,83): LN -> Linear -> ReLU -> LN -> Linear
         plan.ln_in_index = len(plan.calls)
         call("ln_in", lib.svol_layernorm_f32_to_bf16, P(x_in), P(w["in_video.0.ln_w"]), P(w["in_video.0.ln_b"]), P(xn),
@@ -367,7 +371,7 @@ class HeadEngine:
             gemm(f"in_proj{i}", cur, w[f"in_video.{i}.w"], w[f"in_video.{i}.b"], out=dst,
                  act=ACT_NONE if last else ACT_RELU,
                  ln=None if last else (w[f"in_video.{i + 1}.ln_w"], w[f"in_video.{i + 1}.ln_b"]),
-                 out_pos=Xp if last else None, pos_t=pos if last else None,
+                 out_pos=Xp if (last and not fused_gate) else None, pos_t=pos if last else None,   # x + pos only feeds gate_scores
                  theta_t=theta if (last and not self.plain) else None)
             cur = dst
         # ---- sketch branch (svanet.py:56-60,87), fp32, B rows
@@ -390,14 +394,20 @@ class HeadEngine:
             # (a) sketch-conditioned gate + norm1                                        :122-127
             call(p + "gate_vec", lib.svol_gate_vectors, P(s_cur), P(w[p + "gate.w"]), P(w[p + "gate.b"]), P(u[li]), B, d, H)
             tag("in")
-            call(p + "gate_scores", lib.svol_gate_scores, P(xp_cur), P(u[li]), P(scores), B, L, d, H)
-            tag("v", after=[p + "gate_vec"])
-            if self.plain:
-                call(p + "gate_apply", lib.svol_gate_apply, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]), P(pos),
-                     P(mem), P(memp), None, B, L, d, H, LN_EPS)
+            if fused_gate:
+                # one launch: scores from x + pos (fp32), softmax over the sample closed inside a cluster, norm1
+                call(p + "gate_fused", lib.svol_gate_fused, P(x_cur), P(u[li]), P(w[p + "n1.w"]), P(w[p + "n1.b"]), P(theta),
+                     P(mem), P(memp), None, None, B, L, d, H, LN_EPS)
+                tag("v", after=[p + "gate_vec"])
             else:
-                call(p + "gate_apply", lib.svol_gate_apply_theta, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]),
-                     P(theta), P(mem), P(memp), None, B, L, d, H, LN_EPS)
+                call(p + "gate_scores", lib.svol_gate_scores, P(xp_cur), P(u[li]), P(scores), B, L, d, H)
+                tag("v", after=[p + "gate_vec"])
+                if self.plain:
+                    call(p + "gate_apply", lib.svol_gate_apply, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]), P(pos),
+                         P(mem), P(memp), None, B, L, d, H, LN_EPS)
+                else:
+                    call(p + "gate_apply", lib.svol_gate_apply_theta, P(x_cur), P(scores), P(w[p + "n1.w"]), P(w[p + "n1.b"]),
+                         P(theta), P(mem), P(memp), None, B, L, d, H, LN_EPS)
             # (b) video self-attention + norm2, FFN + norm3                               :137-143
             if self.plain:
                 gemm(p + "sa_qk", memp, w[p + "sa.wqk"], w[p + "sa.bqk"], out=qk)

@@ -169,6 +169,25 @@ def gate(x: torch.Tensor, xpos: torch.Tensor, sketch: torch.Tensor, in_w: torch.
     return mem, mem_pos, att, scores
 
 
+def gate_fused(x: torch.Tensor, sketch: torch.Tensor, in_w: torch.Tensor, in_b: torch.Tensor, ln_w: torch.Tensor,
+               ln_b: torch.Tensor, theta: torch.Tensor, B: int, L: int, H: int = 8, eps: float = 1e-5):
+    """svol_gate_vectors + the one-launch gate (svol_gate_fused).  Returns (mem, mem_pos, att [B,L], scores [B,H,L])."""
+    _lib.require_device()
+    lib = _lib.get_lib()
+    d = x.shape[-1]
+    s = _lib.stream_ptr()
+    if not lib.svol_gate_fused_supported(L):
+        raise ValueError(f"svol_gate_fused: L = {L} tokens per sample do not fit one cluster's shared memory")
+    u = torch.empty((B, H, d), device=x.device, dtype=torch.float32)
+    scores = torch.empty((B, H, L), device=x.device, dtype=torch.float32)
+    att = torch.empty((B, L), device=x.device, dtype=torch.float32)
+    mem, mem_pos = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(lib.svol_gate_vectors(_P(sketch), _P(in_w), _P(in_b), _P(u), B, d, H, s), "gate_vectors")
+    _lib.check(lib.svol_gate_fused(_P(x), _P(u), _P(ln_w), _P(ln_b), _P(theta), _P(mem), _P(mem_pos), _P(att), _P(scores),
+                                   B, L, d, H, eps, s), "gate_fused")
+    return mem, mem_pos, att, scores
+
+
 def heads(hs: torch.Tensor, h2: torch.Tensor, wc, bc, wb, bb):
     _lib.require_device()
     rows, d = hs.shape

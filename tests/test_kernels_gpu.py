@@ -137,6 +137,9 @@ ATTN_CASES = [
     (2, 200, 392, False),       # ragged tails on both sides
     (2, 320, 1568, True),       # cross-attention with padded keys
     (1, 1568, 1568, False),     # video self-attention shape
+    (2, 96, 40, False),         # fewer than 64 keys: the upper-half softmax warpgroups never run
+    (2, 130, 192, False),       # Lk % 128 == 64: upper half of the last key tile empty (skipped)
+    (2, 130, 193, False),       # Lk % 128 == 65: one key in the upper half of the last tile
 ]
 
 
@@ -257,6 +260,55 @@ def test_gate(B, L, theta):
     mem_ref = orc.layer_norm(xf + att_ref[..., None] * xf, lw, lb)
     _assert_close(_f(mem).reshape(B, L, d_model), mem_ref, atol=1e-3, what="mem")
     _assert_close(_f(mem_pos).reshape(B, L, d_model), mem_ref + pos, atol=2e-3, what="mem_pos")
+
+
+@pytest.mark.parametrize("B,L", [(2, 1568), (3, 70), (2, 5), (1, 3384), (33, 257)])
+def test_gate_fused(B, L):
+    """One-launch gate (cluster per sample, rows kept in shared memory, softmax statistics exchanged through
+    distributed shared memory) vs the oracle's multi-head attention weights; scores are formed from x + pos in fp32
+    (the split kernels read a bf16-rounded x + pos), so the oracle gets the unrounded sum."""
+    from svol_b200 import ops
+    rng = np.random.RandomState(L + 1)
+    d_model, H = 256, 8
+    x = _bf16(rng.standard_normal((B, L, d_model)).astype(np.float32))
+    mask = np.ones((B, L), bool)
+    mask[-1, L - L // 5:] = False
+    pos = orc.position_embedding_sine(mask, d_model)
+    skch = rng.standard_normal((B, d_model)).astype(np.float32)
+    in_w = (rng.standard_normal((3 * d_model, d_model)) * 0.08).astype(np.float32)
+    in_b = (rng.standard_normal(3 * d_model) * 0.05).astype(np.float32)
+    lw, lb = (1 + 0.1 * rng.standard_normal(d_model)).astype(np.float32), (0.1 * rng.standard_normal(d_model)).astype(np.float32)
+    dv = _dev()
+    t = lambda a: torch.from_numpy(a).to(dv)
+    theta = ops.posenc_theta(t(mask.astype(np.float32))).reshape(-1)
+    mem, mem_pos, att, scores = ops.gate_fused(x.reshape(B * L, d_model).to(dv), t(skch), t(in_w), t(in_b), t(lw), t(lb), theta,
+                                               B, L, H)
+    torch.cuda.synchronize()
+    xf = x.float().numpy()
+    xpf = (xf + pos).astype(np.float32)
+    _, att_ref = orc.multihead_attention(skch[:, None, :], xpf, xpf, in_w, in_b, np.eye(d_model, dtype=np.float32),
+                                         np.zeros(d_model, np.float32), H)
+    att_ref = att_ref[:, 0, :]
+    assert np.abs(_f(att) - att_ref).max() < 1e-3 * att_ref.max() + 1e-7
+    assert np.allclose(_f(att).sum(1), 1.0, atol=1e-4)
+    # the exported scores reproduce att through a plain softmax (what the training backward consumes)
+    sc = _f(scores).astype(np.float64)
+    p = np.exp(sc - sc.max(-1, keepdims=True))
+    assert np.abs((p / p.sum(-1, keepdims=True)).mean(1) - _f(att)).max() < 1e-5
+    mem_ref = orc.layer_norm(xf + att_ref[..., None] * xf, lw, lb)
+    _assert_close(_f(mem).reshape(B, L, d_model), mem_ref, atol=1e-3, what="mem")
+    _assert_close(_f(mem_pos).reshape(B, L, d_model), mem_ref + pos, atol=2e-3, what="mem_pos")
+
+
+def test_gate_fused_rejects_long_clips():
+    from svol_b200 import ops, _lib
+    assert _lib.get_lib().svol_gate_fused_supported(3384) == 1
+    assert _lib.get_lib().svol_gate_fused_supported(3385) == 0
+    dv = _dev()
+    with pytest.raises(ValueError):
+        ops.gate_fused(torch.zeros(6272, 256, dtype=torch.bfloat16, device=dv), torch.zeros(1, 256, device=dv),
+                       torch.zeros(768, 256, device=dv), torch.zeros(768, device=dv), torch.ones(256, device=dv),
+                       torch.zeros(256, device=dv), torch.zeros(6272, device=dv), 1, 6272)
 
 
 def test_heads():

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs one kernel of the hot path at the headline (C2) shapes a few times -- the target command for
-`ncu --set full` captures:   python tools/run_kernel.py attn_self | attn_cross | attn_q | ffn_video | ffn_query | gemm_ffn_up | gemm_ffn_down | gemm_qk"""
+`ncu --set full` captures:   python tools/run_kernel.py attn_self | attn_cross | attn_q | ffn_video | ffn_query | gemm_ffn_up | gemm_ffn_down | gemm_qk | gate_fused | gate_split"""
 import math
 import os
 import sys
@@ -44,6 +44,30 @@ elif which.startswith("attn"):
     vt = vt.to(dev)
     mask = torch.ones(B, Lk, device=dev) if which == "attn_cross" else None
     fn = lambda: ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask)
+elif which.startswith("gate"):
+    # gate_fused (one cluster launch) | gate_split (gate_scores + gate_apply_theta); gate_vectors runs in both
+    M = B * L
+    x = rnd(M, d).to(torch.bfloat16).to(dev)
+    theta = ops.posenc_theta(torch.ones(B, L, device=dev)).reshape(-1)
+    pos = torch.from_numpy(__import__("numpy").zeros((1,), "float32"))
+    sk, in_w, in_b = rnd(B, d).to(dev), (rnd(3 * d, d) * 0.08).to(dev), (rnd(3 * d) * 0.05).to(dev)
+    lw, lb = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    from svol_b200 import _lib
+    lib, P_, st = _lib.get_lib(), _lib.ptr, _lib.stream_ptr()
+    u = torch.empty(B, H, d, device=dev)
+    _lib.check(lib.svol_gate_vectors(P_(sk), P_(in_w), P_(in_b), P_(u), B, d, H, st), "gate_vectors")
+    scores = torch.empty(B, H, L, device=dev)
+    mem, memp = torch.empty_like(x), torch.empty_like(x)
+    if which == "gate_fused":       # the kernel alone (gate_vectors ran once above)
+        fn = lambda: _lib.check(lib.svol_gate_fused(P_(x), P_(u), P_(lw), P_(lb), P_(theta), P_(mem), P_(memp), None, None,
+                                                    B, L, d, H, 1e-5, st), "gate_fused")
+    else:
+        xpos = (x.float() + rnd(M, d).to(dev)).to(torch.bfloat16)
+
+        def fn():
+            _lib.check(lib.svol_gate_scores(P_(xpos), P_(u), P_(scores), B, L, d, H, st), "gate_scores")
+            _lib.check(lib.svol_gate_apply_theta(P_(x), P_(scores), P_(lw), P_(lb), P_(theta), P_(mem), P_(memp), None,
+                                                 B, L, d, H, 1e-5, st), "gate_apply")
 elif which.startswith("ffn"):
     M = B * L if which == "ffn_video" else B * Q
     x = rnd(M, d).to(torch.bfloat16).to(dev)
