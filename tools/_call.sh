@@ -1,5 +1,6 @@
 cd /root/repo; mkdir -p gpurun_out; O=gpurun_out
-SVOL_GATE_CL=4 timeout 120 python tools/run_kernel.py gate_fused 50 2>&1 | tail -1
-SVOL_GATE_CL=8 timeout 120 python tools/run_kernel.py gate_fused 50 2>&1 | tail -1
-timeout 120 python tools/run_kernel.py gate_split 50 2>&1 | tail -1
-SVOL_GATE_CL=8 timeout 300 ncu --set full --clock-control none --import-source on -k regex:gate_fused -c 1 -o $O/gate_fused python tools/run_kernel.py gate_fused 1 > $O/ncu_gate.log 2>&1; echo "ncu $?"
+run() { local name=$1 t=$2; shift 2; timeout "$t" python -m pytest -q --tb=short -p no:cacheprovider "$@" > "$O/$name.log" 2>&1; echo "$name: exit $? :: $(tail -1 $O/$name.log)"; }
+run attn_tc 300 tests/test_kernels_gpu.py -m gpu -k "attention and tcgen05"
+run model 600 tests/test_model_gpu.py -m gpu
+for k in attn_self attn_cross attn_q; do timeout 120 python tools/run_kernel.py $k 20 2>&1 | tail -1; done
+timeout 600 python bench.py --steps 100 --warmup 5 --no-cpu-baseline > $O/bench.json 2> $O/bench.err; echo "bench exit $?"; cut -c1-220 $O/bench.json
