@@ -570,7 +570,7 @@ int launch_gate_apply(const svol_bf16* x, const float* scores, const float* lw, 
 // gate_scores + gate_apply this drops the second read of the token rows, the (x + pos) operand, the score round trip
 // through HBM and one launch: compulsory traffic = B*L*d*2 read + 2*B*L*d*2 written.
 // ---------------------------------------------------------------------------------------------
-constexpr int GF_CHUNK = 32, GF_MAX_CHUNKS = 16, GF_ILP = 2;
+constexpr int GF_CHUNK = 32, GF_MAX_CHUNKS = 16, GF_ILP = 2, GF_ILP2 = 4;   // rows in flight per warp: score pass / LayerNorm pass
 constexpr int GF_ROW_BYTES = GATE_D * 2;
 constexpr int GF_MAX_ROWS = GF_CHUNK * GF_MAX_CHUNKS;                 // token rows per CTA
 constexpr int GF_HDR_BYTES = 256;                                      // chunk barriers [16], local stats [8] float2, global [8] float2
@@ -645,9 +645,8 @@ gate_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
   const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
   const int head = (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0);
   uint32_t chunks_seen = 0;
-  for (int lr0 = warp; lr0 < n_rows; lr0 += GF_ILP * NW) {
-    uint4 q[GF_ILP];
-    float th[GF_ILP];
+  // rows of iteration i + 1 are fetched from shared memory before iteration i is computed
+  auto fetch = [&](int lr0, uint4 (&q)[GF_ILP], float (&th)[GF_ILP]) {
 #pragma unroll
     for (int r = 0; r < GF_ILP; ++r) {
       const int lr = lr0 + r * NW;
@@ -659,6 +658,16 @@ gate_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
         th[r] = th_s[lr];
       }
     }
+  };
+  uint4 q_next[GF_ILP];
+  float th_next[GF_ILP];
+  fetch(warp, q_next, th_next);
+  for (int lr0 = warp; lr0 < n_rows; lr0 += GF_ILP * NW) {
+    uint4 q[GF_ILP];
+    float th[GF_ILP];
+#pragma unroll
+    for (int r = 0; r < GF_ILP; ++r) { q[r] = q_next[r]; th[r] = th_next[r]; }
+    fetch(lr0 + GF_ILP * NW, q_next, th_next);
     float a1[GF_ILP];
 #pragma unroll
     for (int r = 0; r < GF_ILP; ++r) {
@@ -740,39 +749,68 @@ gate_fused_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__
   const float gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
   const float gb[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
   const float2 st = lane < GATE_H ? stat_all[lane] : make_float2(0.f, 0.f);
-  for (int lr0 = warp; lr0 < n_rows; lr0 += GF_ILP * NW) {
+  // GF_ILP2 rows per warp in flight, every stage (att, mean, variance) written across the rows so that the shuffle
+  // chains of different rows overlap; a tail slot recomputes the last row and skips the stores
+  for (int lr0 = warp; lr0 < n_rows; lr0 += GF_ILP2 * NW) {
+    uint4 q[GF_ILP2];
+    float a[GF_ILP2], thv[GF_ILP2];
 #pragma unroll
-    for (int r = 0; r < GF_ILP; ++r) {
-      const int lr = min(lr0 + r * NW, n_rows - 1);        // a tail slot recomputes (and rewrites) the last row
-      const size_t row = row0 + lr;
-      const uint4 q = rows_s[lr * 32 + lane];
-      float a = 0.f;
-      if (lane < GATE_H) a = expf(sc_s[lane * rpc_pad + lr] - st.x) * st.y;
-      a += __shfl_xor_sync(0xffffffffu, a, 4);
-      a += __shfl_xor_sync(0xffffffffu, a, 2);
-      a += __shfl_xor_sync(0xffffffffu, a, 1);
-      const float att = __shfl_sync(0xffffffffu, a, 0) * (1.0f / GATE_H);
-      if (att_out && lane == 0) att_out[row] = att;
-      float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+    for (int r = 0; r < GF_ILP2; ++r) {
+      const int lr = min(lr0 + r * NW, n_rows - 1);
+      q[r] = rows_s[lr * 32 + lane];
+      thv[r] = th_s[lr];
+      a[r] = lane < GATE_H ? expf(sc_s[lane * rpc_pad + lr] - st.x) * st.y : 0.f;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < GF_ILP2; ++r) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+    float v[GF_ILP2][8], red[GF_ILP2];
+#pragma unroll
+    for (int r = 0; r < GF_ILP2; ++r) {
+      const float att = __shfl_sync(0xffffffffu, a[r], 0) * (1.0f / GATE_H);
+      if (att_out && lane == 0 && lr0 + r * NW < n_rows) att_out[row0 + lr0 + r * NW] = att;
+      const float x8[8] = {bf16_lo(q[r].x), bf16_hi(q[r].x), bf16_lo(q[r].y), bf16_hi(q[r].y),
+                           bf16_lo(q[r].z), bf16_hi(q[r].z), bf16_lo(q[r].w), bf16_hi(q[r].w)};
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { v[i] = v[i] + att * v[i]; s += v[i]; }
-      const float mean = warp_sum(s) * (1.0f / GATE_D);
+      for (int i = 0; i < 8; ++i) { v[r][i] = x8[i] + att * x8[i]; s += v[r][i]; }
+      red[r] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < GF_ILP2; ++r) red[r] += __shfl_xor_sync(0xffffffffu, red[r], o);
+    float mean[GF_ILP2];
+#pragma unroll
+    for (int r = 0; r < GF_ILP2; ++r) {
+      mean[r] = red[r] * (1.0f / GATE_D);
       float ss = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float dlt = v[i] - mean; ss += dlt * dlt; }
-      const float rstd = rsqrtf(warp_sum(ss) * (1.0f / GATE_D) + eps);
+      for (int i = 0; i < 8; ++i) { const float dlt = v[r][i] - mean[r]; ss += dlt * dlt; }
+      red[r] = ss;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < GF_ILP2; ++r) red[r] += __shfl_xor_sync(0xffffffffu, red[r], o);
+#pragma unroll
+    for (int r = 0; r < GF_ILP2; ++r) {
+      const float rstd = rsqrtf(red[r] * (1.0f / GATE_D) + eps);
       float pp[8];
-      gate_sincos(th_s[lr], idt, pp);
+      gate_sincos(thv[r], idt, pp);
       float y[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = (v[i] - mean) * rstd * gw[i] + gb[i];
+      for (int i = 0; i < 8; ++i) y[i] = (v[r][i] - mean[r]) * rstd * gw[i] + gb[i];
       uint4 o, op;
       o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]); o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
       op.x = pack_bf16x2(y[0] + pp[0], y[1] + pp[1]); op.y = pack_bf16x2(y[2] + pp[2], y[3] + pp[3]);
       op.z = pack_bf16x2(y[4] + pp[4], y[5] + pp[5]); op.w = pack_bf16x2(y[6] + pp[6], y[7] + pp[7]);
-      reinterpret_cast<uint4*>(mem + row * GATE_D)[lane] = o;
-      reinterpret_cast<uint4*>(mem_pos + row * GATE_D)[lane] = op;
+      if (lr0 + r * NW < n_rows) {
+        const size_t row = row0 + lr0 + r * NW;
+        reinterpret_cast<uint4*>(mem + row * GATE_D)[lane] = o;
+        reinterpret_cast<uint4*>(mem_pos + row * GATE_D)[lane] = op;
+      }
     }
   }
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
