@@ -1,8 +1,4 @@
 cd /root/repo; mkdir -p gpurun_out; O=gpurun_out
-b() { timeout 600 python bench.py --steps 200 --warmup 10 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['value']), d['ms_per_step'], d['host_enqueue_ms_per_step'])"; }
-b new; b new
-cp svol_b200/csrc/libsvol_b200.so /tmp/new.so; cp svol_b200/csrc/libsvol_b200_prev.so svol_b200/csrc/libsvol_b200.so
-b prev; b prev
-cp /tmp/new.so svol_b200/csrc/libsvol_b200.so
-b new
-timeout 600 python bench.py --steps 50 --warmup 5 --breakdown $O/breakdown.txt --no-cpu-baseline > /dev/null 2>&1; head -12 $O/breakdown.txt
+SVOL_FFN_2SM=0 timeout 120 python tools/ffn_trace.py > $O/ftrace_1sm_noload.txt 2>&1; echo "1sm $?"
+SVOL_FFN_2SM=1 timeout 120 python tools/ffn_trace.py > $O/ftrace_2sm_noload.txt 2>&1; echo "2sm $?"
+for m in 0 1; do for k in ffn_video; do echo -n "NOLOAD 2SM=$m "; SVOL_FFN_2SM=$m timeout 60 python tools/run_kernel.py $k 20 2>&1 | tail -1; done; done

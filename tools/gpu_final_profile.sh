@@ -16,5 +16,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 python tools/summarize_launches.py $O/launches.csv > $O/launches_summary.txt
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/train_launches.csv python bench.py --mode train --steps 2 --warmup 3 > $O/ncu_train.log 2>&1; echo "ncu train $?"
 python tools/summarize_launches.py $O/train_launches.csv > $O/train_launches_summary.txt
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_bwd -c 2 -o $O/attn_bwd python tools/run_kernel.py attn_bwd_self 1 > $O/ncu_attn_bwd.log 2>&1; echo "ncu attn_bwd $?"
-python tools/ncu_summary.py $O/attn_bwd.ncu-rep > $O/attn_bwd_summary.txt
+for k in attn_self attn_cross attn_q ffn_video ffn_query gate_fused gate_split; do timeout 120 python tools/run_kernel.py $k 20 2>&1 | tail -1; done > $O/kernels_alone.txt; cat $O/kernels_alone.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_tc -c 1 -o $O/attn_self python tools/run_kernel.py attn_self 1 > $O/ncu_attn.log 2>&1; echo "ncu attn_self $?"
+python tools/ncu_summary.py $O/attn_self.ncu-rep > $O/attn_self_summary.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ffn_tc -c 1 -o $O/ffn_video python tools/run_kernel.py ffn_video 1 > $O/ncu_ffn.log 2>&1; echo "ncu ffn_video $?"
+python tools/ncu_summary.py $O/ffn_video.ncu-rep > $O/ffn_video_summary.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gate_fused -c 1 -o $O/gate_fused python tools/run_kernel.py gate_fused 1 > $O/ncu_gate.log 2>&1; echo "ncu gate_fused $?"
+python tools/ncu_summary.py $O/gate_fused.ncu-rep > $O/gate_fused_summary.txt
