@@ -56,6 +56,7 @@ class _Plan:
         self.keep: List[object] = []        # ctypes structs must outlive the plan
         self.buf: Dict[str, torch.Tensor] = {}
         self.graph = None
+        self.graph_full = None              # same, including the input LayerNorm (inputs written into the plan's own buffers)
 
     def run(self, stream: int, start: int = 0, side=None) -> None:
         """Launches calls[start:].  ``side`` = None: sequentially on ``stream``.  ``side`` = (query stream, input
@@ -506,6 +507,13 @@ class HeadEngine:
         # eagerly and reads the caller's tensor in place; everything after it works on plan-owned buffers and can
         # be replayed as one CUDA graph.
         src = src_video
+        if (not fmap and self.use_graph and src.data_ptr() == b["src_video"].data_ptr()
+                and src_sketch.data_ptr() == b["src_sketch"].data_ptr()
+                and src_video_mask.data_ptr() == b["src_video_mask"].data_ptr()):
+            # the caller filled the plan's own input buffers (input_buffers()): nothing to copy, and the input LayerNorm is
+            # replayed as part of the graph -- one graph launch per forward
+            self.run_plan(plan, full=True)
+            return b["logits"], b["boxes"]
         bf16_in = (not fmap) and src.dtype == torch.bfloat16      # frame features kept in bf16 by the caller (feature cache)
         if fmap:
             if not (src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()):
@@ -537,19 +545,29 @@ class HeadEngine:
         self.run_plan(plan)
         return b["logits"], b["boxes"]
 
-    def run_plan(self, plan: _Plan) -> None:
-        """Runs calls[1:] of the plan (everything after the input LayerNorm), eagerly or as a graph replay."""
+    def input_buffers(self, B: int, L: int, d_in: int) -> Dict[str, torch.Tensor]:
+        """The static input tensors of this shape's plan ON THE CURRENT STREAM: ``src_video`` (B,L,d_in) fp32,
+        ``src_sketch`` (B,d_sk) fp32 (pass it to forward as ``.view(B, 1, -1)`` or as is), ``src_video_mask`` (B,L) fp32.
+        A caller that produces its inputs on the device (a backbone, a feature cache) writes them here and passes these
+        very tensors to ``forward``: the forward is then a single CUDA-graph launch (input LayerNorm included)."""
+        b = self.plan_for(B, L, d_in).buf
+        return {k: b[k] for k in ("src_video", "src_sketch", "src_video_mask")}
+
+    def run_plan(self, plan: _Plan, full: bool = False) -> None:
+        """Runs calls[1:] of the plan (everything after the input LayerNorm; ``full``: calls[0:], the LayerNorm reading the
+        plan's own input buffer), eagerly or as a graph replay."""
         if self.use_graph:
-            if plan.graph is None:
+            attr, start = ("graph_full", 0) if full else ("graph", 1)
+            if getattr(plan, attr) is None:
                 # warm-up run outside capture (sets function attributes, loads modules)
-                plan.run(torch.cuda.current_stream().cuda_stream, start=1)
+                plan.run(torch.cuda.current_stream().cuda_stream, start=start)
                 torch.cuda.synchronize()
                 if self._side is None:
                     self._side = (torch.cuda.Stream(), torch.cuda.Stream())
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    plan.run(torch.cuda.current_stream().cuda_stream, start=1, side=self._side)
-                plan.graph = g
-            plan.graph.replay()
+                    plan.run(torch.cuda.current_stream().cuda_stream, start=start, side=self._side)
+                setattr(plan, attr, g)
+            getattr(plan, attr).replay()
         else:
             plan.run(torch.cuda.current_stream().cuda_stream, start=1)

@@ -208,3 +208,31 @@ def test_bf16_frame_features_input():
         a = {k: v.clone() for k, v in model(t("src_sketch"), t("src_sketch_mask"), xb, t("src_video_mask")).items() if k != "aux_outputs"}
         b = model(t("src_sketch"), t("src_sketch_mask"), xb.float(), t("src_video_mask"))
     assert torch.equal(a["pred_logits"], b["pred_logits"]) and torch.equal(a["pred_boxes"], b["pred_boxes"])
+
+
+def test_inputs_written_into_the_plan_buffers():
+    """A producer that already runs on the device writes its features into HeadEngine.input_buffers() and passes those very
+    tensors to forward: nothing is copied, the input LayerNorm is part of the replayed graph, results are bit-identical to
+    the forward that reads caller-owned tensors; new contents of the buffers are picked up by the next replay."""
+    import torch
+    from svol_b200 import synth
+    from svol_b200.modeling import build_svanet
+    cfg = synth.CONFIGS["C1b"]
+    model = build_svanet(cfg.to_namespace())
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.random_state_dict(cfg, 7).items()}, strict=True)
+    model = model.to("cuda:0").eval()
+    B = 2
+    for seed in (7, 8):
+        inp = synth.make_inputs(cfg, B, seed, padded=True)
+        t = lambda k: torch.from_numpy(inp[k]).to("cuda:0")
+        with torch.no_grad():
+            ref = model(t("src_sketch"), t("src_sketch_mask"), t("src_video"), t("src_video_mask"))
+            ref = {k: ref[k].clone() for k in ("pred_logits", "pred_boxes")}
+            bufs = model.engine.input_buffers(B, inp["src_video"].shape[1], inp["src_video"].shape[2])
+            bufs["src_video"].copy_(t("src_video"))
+            bufs["src_sketch"].copy_(t("src_sketch").reshape(B, -1))
+            bufs["src_video_mask"].copy_(t("src_video_mask"))
+            for _ in range(2):      # capture, then replay
+                out = model(bufs["src_sketch"].view(B, 1, -1), t("src_sketch_mask"), bufs["src_video"], bufs["src_video_mask"])
+        assert torch.equal(out["pred_logits"], ref["pred_logits"]) and torch.equal(out["pred_boxes"], ref["pred_boxes"])
+    assert model.engine.plan_for(B, inp["src_video"].shape[1], inp["src_video"].shape[2]).graph_full is not None
