@@ -36,25 +36,36 @@
 // a quarter of a key-tile period apart (g0, g2, g1, g3) so that on every sub-partition the ex2 sections of the
 // four resident warps interleave instead of colliding; equal periods keep the offsets.
 // TMEM map (512 columns): S_g [64g, +64) P_g [256+32g, +32) O_g [384+32g, +32).
+// A CTA whose second query tile is empty (the tail of Lq: the last CTA of every (sample, head) when Lq % 256 is in
+// (0, 128]) would leave warpgroups 2, 3 and one MMA issuer idle while the other two walk all key tiles at the latency-bound
+// pace of a single chain (2043 clk per key tile, measured).  Such a CTA instead runs its ONE query tile on all four
+// warpgroups: "tile slot" t = 0 / 1 takes the even / odd key tiles, each slot with its own issuer, S / P / O columns and
+// running maxima, and the four partial results per row are merged at the end.
 // Q is pre-scaled by log2(e)/sqrt(dh) when it is produced, so the softmax is a bare ex2.
+#include <type_traits>
+
 #include "common.cuh"
 #include "svol_internal.h"
 
 namespace svol {
 
 namespace attn {
-constexpr int BQ = 128, BKV = 128, HALF = 64, DH = 32, STAGES = 5;
+// K / V^T ring depth.  A stage is released by the P V of its tile's upper half, which an issuer reaches two of ITS OWN
+// key tiles later; in a single-tile CTA consecutive key tiles alternate between the two issuers, so a stage stays
+// occupied for four tiles and a 5-deep ring left no room to prefetch (measured: 2-3 k clk of load latency exposed on
+// every key tile).  8 stages = 4 tiles of lag + 4 of prefetch.
+constexpr int BQ = 128, BKV = 128, HALF = 64, DH = 32, STAGES = 8;
 constexpr int Q_BYTES = BQ * DH * 2;            // 8192 per query tile
 constexpr int K_BYTES = BKV * DH * 2;           // 8192
 constexpr int VT_KB_BYTES = DH * 128;           // one 64-key block of V^T: 32 rows x 128 B
 constexpr int VT_BYTES = 2 * VT_KB_BYTES;       // 8192
 constexpr int CMB_STRIDE = 35;                  // floats per row of the merge buffer: m, l, O[32] (+1: odd stride, no bank conflicts)
-constexpr int CMB_BYTES = 2 * BQ * CMB_STRIDE * 4;
+constexpr int CMB_BYTES = 3 * BQ * CMB_STRIDE * 4;           // up to three partial results per row (single-tile CTAs)
 constexpr int OFF_K = 2 * Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES, OFF_CMB = OFF_VT + STAGES * VT_BYTES;
 constexpr int KMASK_WORDS = 256;                // key-padding bitmask of one sample: up to 8192 keys
 constexpr int OFF_KMASK = OFF_CMB + CMB_BYTES;
 constexpr int OFF_BAR = OFF_KMASK + KMASK_WORDS * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 constexpr int THREADS = 640;   // 5 warpgroups: 4 x softmax, {TMA, MMA 0, MMA 1, idle}
 constexpr uint32_t TMEM_COLS = 512, TMEM_P = 256, TMEM_O = 384;
 constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
@@ -203,8 +214,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // key tiles whose upper 64 keys hold at least one in-range key: when Lk % 128 is in (0, 64] the upper half of the last
   // tile is empty and its QK^T / softmax / PV are skipped altogether (1568 keys: 1 of 26 half tiles; 320 keys: 1 of 6)
   const int n_hi = Lk > HALF ? (Lk - HALF + BKV - 1) / BKV : 0;
+  // single-tile CTA: both tile slots work on query tile 0, slot t on key tiles t, t + 2, ... (see the header)
+  // Both variants of the role code below are separate instantiations (generic lambdas on a compile-time flag): the
+  // two-tile path keeps exactly the code it was tuned with (key tile == iteration, no extra live values).
+  // (with fewer than four key tiles the extra merge costs more than the shorter walk saves: query self-attention, 3 tiles)
+  const bool split = n_q == 1 && n_tiles >= 4;
 #ifdef SVOL_ATTN_TRACE
+#ifdef SVOL_ATTN_TRACE_LAST      // trace the LAST query-tile pair of (sample 0, head 0): the single-tile CTA when Lq % 256 is in (0, 128]
+  const bool trace_on = blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && ((warp & 3) == 0 || warp >= 16);
+#else
   const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && ((warp & 3) == 0 || warp >= 16);
+#endif
 #endif
 
   if (warp == 16 && lane == 0) {
@@ -248,49 +268,66 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tma_load_2d(smem + OFF_VT + s * VT_BYTES + VT_KB_BYTES, &tmVt, &bars->kv_full[s], j * BKV + HALF, vrow);
         }
       }
-    } else if (warp - 17 < n_q) {
-      // ------------------------------------------------------------------ MMA issuer of query tile t
+    } else if (warp == 17 || warp == 18) {
+      // ------------------------------------------------------------------ MMA issuer of tile slot t
       const int t = warp - 17;
+      auto run_issuer = [&](auto split_tag) {
+      constexpr bool kSplit = decltype(split_tag)::value;
+      constexpr int j_step = kSplit ? 2 : 1;
+      if (!kSplit && t >= n_q) return;                    // second query tile empty and not worth splitting: this issuer idles
+      const int j0 = kSplit ? t : 0;
+      // key tiles of this slot: all / those with a populated upper half
+      const int cnt_lo = n_tiles > j0 ? (n_tiles - j0 + j_step - 1) / j_step : 0;
+      const int cnt_hi = n_hi > j0 ? (n_hi - j0 + j_step - 1) / j_step : 0;
       if (elect_one()) {
         constexpr uint32_t idesc_s = make_idesc_bf16(BQ, HALF);
         constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH);
         // descriptors differ only in their 14-bit start-address field (bytes >> 4): plain integer adds below
-        const uint64_t dQ = make_kmajor_desc<64>(smem_u32(smem + t * Q_BYTES));
+        const uint64_t dQ = make_kmajor_desc<64>(smem_u32(smem + (kSplit ? 0 : t) * Q_BYTES));
         const uint64_t dK = make_kmajor_desc<64>(smem_u32(smem + OFF_K));
         const uint64_t dV = make_kmajor_desc<128>(smem_u32(smem + OFF_VT));
-        auto issue_qk = [&](int j, int half) {          // S_g(j) = Q_t K_half(j)^T
+        auto issue_qk = [&](int i, int half) {          // i-th key tile of this slot: S_g = Q K_half(j)^T
+          const int j = j0 + j_step * i;
           const int g = 2 * t + half, s = j % STAGES;
-          if (half == 0) mbar_wait(&bars->kv_full[s], (j / STAGES) & 1);
-          if (j > 0) mbar_wait(&bars->s_free[g], (j - 1) & 1);
-          SVOL_TR(4 + t, j, half);
+          if (half == 0) {
+            // single-tile CTA: this issuer consumes every other key tile only, but it still observes EVERY fill of the ring
+            // in order (the skipped tile's barrier first), so that a parity wait can never alias a fill two phases back
+            if (kSplit && j > 0) mbar_wait(&bars->kv_full[(j - 1) % STAGES], ((j - 1) / STAGES) & 1);
+            mbar_wait(&bars->kv_full[s], (j / STAGES) & 1);
+          }
+          if (i > 0) mbar_wait(&bars->s_free[g], (i - 1) & 1);
+          SVOL_TR(4 + t, i, half);
           tcgen05_fence_after();
           const uint64_t dKs = dK + static_cast<uint64_t>(s * (K_BYTES >> 4) + half * (HALF * DH * 2 >> 4));
 #pragma unroll
           for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + g * HALF, dQ + 2 * k, dKs + 2 * k, idesc_s, k != 0);
           umma_commit(&bars->s_full[g]);
         };
-        auto issue_pv = [&](int j, int half) {          // O_g += P_g(j) V_half(j)
+        auto issue_pv = [&](int i, int half) {          // O_g += P_g V_half(j)
+          const int j = j0 + j_step * i;
           const int g = 2 * t + half, s = j % STAGES;
-          mbar_wait(&bars->p_ready[g], j & 1);
-          SVOL_TR(4 + t, j, 2 + half);
+          mbar_wait(&bars->p_ready[g], i & 1);
+          SVOL_TR(4 + t, i, 2 + half);
           tcgen05_fence_after();
           const uint64_t dVs = dV + static_cast<uint64_t>(s * (VT_BYTES >> 4) + half * (VT_KB_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < HALF / 16; ++k)
             umma_bf16_ts(tmem_base + TMEM_O + g * DH, tmem_base + TMEM_P + g * 32 + k * 8, dVs + 2 * k, idesc_o,
-                         (j > 0 || k > 0) ? 1u : 0u);
+                         (i > 0 || k > 0) ? 1u : 0u);
           umma_commit(&bars->o_full[g]);
           // last reader of stage s (covers every earlier MMA); a last tile without an upper half is never reloaded
           if (half == 1) umma_commit(&bars->kv_empty[s]);
         };
         mbar_wait(&bars->q_full, 0);
-        for (int i = 0; i <= n_tiles + 1; ++i) {
-          if (i < n_tiles) issue_qk(i, 0);
-          if (i >= 2 && i - 2 < n_hi) issue_pv(i - 2, 1);
-          if (i < n_hi) issue_qk(i, 1);
-          if (i >= 1 && i <= n_tiles) issue_pv(i - 1, 0);
+        for (int i = 0; i <= cnt_lo + 1; ++i) {
+          if (i < cnt_lo) issue_qk(i, 0);
+          if (i >= 2 && i - 2 < cnt_hi) issue_pv(i - 2, 1);
+          if (i < cnt_hi) issue_qk(i, 1);
+          if (i >= 1 && i <= cnt_lo) issue_pv(i - 1, 0);
         }
       }
+      };
+      if (split) run_issuer(std::true_type{}); else run_issuer(std::false_type{});
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
@@ -309,8 +346,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       asm volatile("bar.sync 3, 512;" ::: "memory");     // all 16 softmax warps
     }
-    if (t < n_q) {
-      // ------------------------------------------------------------------ softmax warpgroups
+    {
+      // ------------------------------------------------------------------ softmax warpgroups: two query tiles x two key
+      // halves, or -- single-tile CTA with at least four key tiles -- one query tile x two key halves x even / odd key tiles
       const int quarter = warp & 3;                       // TMEM lane quarter == warp % 4
       const int r = quarter * 32 + lane;                  // row inside the tile == TMEM lane
       const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -330,26 +368,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // Barrier probes are software-pipelined: a (non-blocking) mbarrier.test_wait is issued well before its result
       // is needed and consumed after independent work; the blocking wait is only the fallback.
       asm volatile(".reg .pred p_of, p_sf;");
-      uint32_t s_ready = 0;
       const uint32_t a_sfull = smem_u32(&bars->s_full[g]), a_ofull = smem_u32(&bars->o_full[g]);
 
-      const int n_mine = half ? n_hi : n_tiles;           // key tiles this warpgroup has keys in
-      for (int j = 0; j < n_mine; ++j) {
+      auto run_softmax = [&](auto split_tag) {
+      constexpr bool kSplit = decltype(split_tag)::value;
+      constexpr int j_step = kSplit ? 2 : 1;
+      if (!kSplit && t >= n_q) return;                    // (see the issuer)
+      uint32_t s_ready = 0;
+      const int j0 = kSplit ? t : 0;
+      const int n_half = half ? n_hi : n_tiles;           // key tiles that have keys in this warpgroup's half ...
+      const int n_mine = n_half > j0 ? (n_half - j0 + j_step - 1) / j_step : 0;    // ... of which this tile slot takes these
+      for (int i = 0; i < n_mine; ++i) {
+        const int j = j0 + j_step * i;                    // key tile; barrier phases count i, this warpgroup's own iterations
         const int kv0 = j * BKV + half * HALF;
-        SVOL_TR(g, j, 0);
-        if (!s_ready) mbar_wait(&bars->s_full[g], j & 1);
-        SVOL_TR(g, j, 1);
+        SVOL_TR(g, i, 0);
+        if (!s_ready) mbar_wait(&bars->s_full[g], i & 1);
+        SVOL_TR(g, i, 1);
         tcgen05_fence_after();
         uint32_t s[HALF];
         tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
         tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
         tmem_ld_wait();
-        SVOL_TR(g, j, 2);
+        SVOL_TR(g, i, 2);
         // scores are in registers: hand the TMEM buffer back so the next QK^T can start now
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->s_free[g]);
-        SVOL_TR(g, j, 4);
+        SVOL_TR(g, i, 4);
 
         // validity of this half tile's 64 keys as two 32-bit words (ragged tail and key_padding_mask); the
         // masked variant of the row-max code is a separate instantiation so full tiles pay nothing for it
@@ -374,16 +419,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         if (masked) mx = half_row_max<true>(s, words);
         else mx = half_row_max<false>(s, words);
-        SVOL_TR_AFTER(g, j, 3, mx);
+        SVOL_TR_AFTER(g, i, 3, mx);
 
-        if (j == 0) {
+        if (i == 0) {
           m_ref = mx;
         } else {
           // lazy rescaling: only when some row's maximum outgrew the reference by more than 2^8
           const bool need = mx > m_ref + RESCALE_THRESHOLD;
           if (__any_sync(0xffffffffu, need)) {
             const float alpha = need ? ex2_approx(m_ref - mx) : 1.0f;   // (m_ref = -inf, finite mx) -> 0
-            mbar_wait(&bars->o_full[g], (j - 1) & 1);                  // every earlier P V has landed in O_g
+            mbar_wait(&bars->o_full[g], (i - 1) & 1);                  // every earlier P V has landed in O_g
             tcgen05_fence_after();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -400,8 +445,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
         float m_use = m_ref == -INFINITY ? 0.f : m_ref;
-        if (j > 0)   // probe: has the previous P V landed (P columns reusable)?  consumed after the exponentials
-          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_of, [%0], %1;" ::"r"(a_ofull), "r"((j - 1) & 1) : "memory");
+        if (i > 0)   // probe: has the previous P V landed (P columns reusable)?  consumed after the exponentials
+          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_of, [%0], %1;" ::"r"(a_ofull), "r"((i - 1) & 1) : "memory");
 
         // one MUFU ex2 per probability (ex2.approx.ftz.bf16x2 was tried: on sm_100 it is issued as two
         // MUFU.EX2.BF16 ops plus a PRMT, so it saves nothing and only costs precision); the subtraction
@@ -420,18 +465,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           s[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
         }
         l2 = __fadd2_rn(l2, __fadd2_rn(la, lb));
-        SVOL_TR(g, j, 5);
+        SVOL_TR(g, i, 5);
 
         // the previous P V must be done reading the P columns before they are overwritten
-        if (j > 0) {
+        if (i > 0) {
           uint32_t ok;
           asm volatile("selp.u32 %0, 1, 0, p_of;" : "=r"(ok));
-          if (!ok) mbar_wait(&bars->o_full[g], (j - 1) & 1);
+          if (!ok) mbar_wait(&bars->o_full[g], (i - 1) & 1);
           tcgen05_fence_after();
         }
-        if (j + 1 < n_mine)   // probe the next score tile (its QK^T was issued when this tile's scores were read out)
-          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_sf, [%0], %1;" ::"r"(a_sfull), "r"((j + 1) & 1) : "memory");
-        SVOL_TR(g, j, 6);
+        if (i + 1 < n_mine)   // probe the next score tile (its QK^T was issued when this tile's scores were read out)
+          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_sf, [%0], %1;" ::"r"(a_sfull), "r"((i + 1) & 1) : "memory");
+        SVOL_TR(g, i, 6);
         // P half tile -> tensor memory: lane = query row, 32 columns of packed bf16 pairs (the A operand of P V)
         tmem_st_32x32b_x32(t_p, &s[0]);
         tmem_st_wait();
@@ -439,58 +484,75 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars->p_ready[g]);
         s_ready = 0;
-        if (j + 1 < n_mine) asm volatile("selp.u32 %0, 1, 0, p_sf;" : "=r"(s_ready));
-        SVOL_TR(g, j, 7);
+        if (i + 1 < n_mine) asm volatile("selp.u32 %0, 1, 0, p_sf;" : "=r"(s_ready));
+        SVOL_TR(g, i, 7);
       }
 
-      // ---- epilogue: O_g is complete once the last P V has landed; merge the two key halves of each row
+      // ---- epilogue: O_g is complete once the last P V has landed; merge the partial results of each row
       uint32_t o[DH];
       if (n_mine > 0) {
         mbar_wait(&bars->o_full[g], (n_mine - 1) & 1);
         tcgen05_fence_after();
         tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
         tmem_ld_wait();
-      } else {                                            // Lk <= 64: the upper-half warpgroups never ran (m = -inf, l = 0)
+      } else {                                            // this warpgroup had no key tile (m = -inf, l = 0)
 #pragma unroll
         for (int i = 0; i < DH; ++i) o[i] = 0u;
       }
       const float l_mine = l2.x + l2.y;
-      float* cmb = reinterpret_cast<float*>(smem + OFF_CMB) + (t * BQ + r) * CMB_STRIDE;
-      if (half == 1) {
+      // two query tiles: warpgroup (t, hi) hands its partial to (t, lo) through slot t.  Single-tile CTA: warpgroups 1, 2, 3
+      // hand theirs to warpgroup 0 through slots 0, 1, 2.
+      float* cmb_base = reinterpret_cast<float*>(smem + OFF_CMB);
+      const bool writer = kSplit ? (g != 0) : (half == 1);
+      if (writer) {
+        float* cmb = cmb_base + ((kSplit ? g - 1 : t) * BQ + r) * CMB_STRIDE;
         cmb[0] = m_ref;
         cmb[1] = l_mine;
 #pragma unroll
         for (int i = 0; i < DH; ++i) cmb[2 + i] = __uint_as_float(o[i]);
       }
-      asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");   // the two warpgroups of query tile t
-      if (half == 0) {
-        const float m_hi = cmb[0], l_hi = cmb[1];
-        const float m = fmaxf(m_ref, m_hi);
+      if (kSplit) asm volatile("bar.sync 4, 512;" ::: "memory");      // all four warpgroups
+      else asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");   // the two warpgroups of query tile t
+      if (!writer) {
+        constexpr int n_parts = kSplit ? 3 : 1;
+        const int first = kSplit ? 0 : t;
+        float m = m_ref;
+#pragma unroll
+        for (int pi = 0; pi < n_parts; ++pi) m = fmaxf(m, cmb_base[((first + pi) * BQ + r) * CMB_STRIDE]);
         const float m_safe = m == -INFINITY ? 0.f : m;
-        const float a_lo = ex2_approx(m_ref - m_safe), a_hi = ex2_approx(m_hi - m_safe);
-        const float l_tot = a_lo * l_mine + a_hi * l_hi;
+        const float a_own = ex2_approx(m_ref - m_safe);
+        float l_tot = a_own * l_mine;
+        float acc[DH];
+#pragma unroll
+        for (int i = 0; i < DH; ++i) acc[i] = __uint_as_float(o[i]) * a_own;
+#pragma unroll
+        for (int pi = 0; pi < n_parts; ++pi) {
+          const float* cmb = cmb_base + ((first + pi) * BQ + r) * CMB_STRIDE;
+          const float a_p = ex2_approx(cmb[0] - m_safe);
+          l_tot = fmaf(a_p, cmb[1], l_tot);
+#pragma unroll
+          for (int i = 0; i < DH; ++i) acc[i] = fmaf(a_p, cmb[2 + i], acc[i]);
+        }
         const float inv = 1.0f / l_tot;
-        const int q = q0 + t * BQ + r;
+        const int q = q0 + (kSplit ? 0 : t) * BQ + r;
         if (q < Lq) {
           // training forward: base-2 log-sum-exp of the (pre-scaled) scores, so that the backward recomputes
           // P = 2^(S - lse) without a second softmax pass
           if (kLse) lse[(static_cast<size_t>(b) * H + h) * lse_pitch + q] = m_safe + __log2f(l_tot);
-          const float w_lo = a_lo * inv, w_hi = a_hi * inv;
           uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * Lq + q) * ldo + h * DH);
 #pragma unroll
           for (int i = 0; i < DH / 8; ++i) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(o[8 * i + e]) * w_lo + cmb[2 + 8 * i + e] * w_hi;
             uint4 w;
-            w.x = pack_bf16x2(v[0], v[1]);
-            w.y = pack_bf16x2(v[2], v[3]);
-            w.z = pack_bf16x2(v[4], v[5]);
-            w.w = pack_bf16x2(v[6], v[7]);
+            w.x = pack_bf16x2(acc[8 * i + 0] * inv, acc[8 * i + 1] * inv);
+            w.y = pack_bf16x2(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
+            w.z = pack_bf16x2(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
+            w.w = pack_bf16x2(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
             op[i] = w;
           }
         }
       }
+      };
+      if (split) run_softmax(std::true_type{}); else run_softmax(std::false_type{});
     }
   }
 

@@ -140,6 +140,10 @@ ATTN_CASES = [
     (2, 96, 40, False),         # fewer than 64 keys: the upper-half softmax warpgroups never run
     (2, 130, 192, False),       # Lk % 128 == 64: upper half of the last key tile empty (skipped)
     (2, 130, 193, False),       # Lk % 128 == 65: one key in the upper half of the last tile
+    (2, 64, 1000, False),       # single-tile CTA only (even / odd key tiles on the two tile slots), 8 key tiles
+    (2, 100, 1408, True),       # single-tile CTA, 11 key tiles (odd count, ring wraps twice), padded keys
+    (1, 384, 128, False),       # one key tile: the odd tile slot of the single-tile CTA has no work
+    (1, 900, 700, False),       # three full CTAs + a single-tile CTA, ragged keys
 ]
 
 
