@@ -102,3 +102,13 @@ def test_flatten_targets_offsets():
     assert np.array_equal(flat.tgt_boxes.numpy(), boxes)
     flat_v = flatten_targets(synth.targets_to_torch(targets), torch.device("cpu"), False, 0, cfg.num_queries, 0)
     assert flat_v.P == 3 and flat_v.rows_per_problem == cfg.num_queries
+
+
+def test_gate_fused_shape_limit_is_a_host_query():
+    """svol_gate_fused_supported is plain host code (no CUDA call): the one-launch gate takes clips whose token rows fit one
+    cluster's shared memory (the headline L = 1568 does, the long clip L = 6272 falls back to gate_scores + gate_apply)."""
+    from svol_b200 import _lib
+    lib = _lib.get_lib()
+    assert lib.svol_gate_fused_supported(1568) == 1 and lib.svol_gate_fused_supported(1) == 1
+    assert lib.svol_gate_fused_supported(3384) == 1 and lib.svol_gate_fused_supported(3385) == 0
+    assert lib.svol_gate_fused_supported(6272) == 0 and lib.svol_gate_fused_supported(0) == 0
