@@ -143,6 +143,9 @@ ATTN_CASES = [
     (2, 64, 1000, False),       # single-tile CTA only (even / odd key tiles on the two tile slots), 8 key tiles
     (2, 100, 1408, True),       # single-tile CTA, 11 key tiles (odd count, ring wraps twice), padded keys
     (1, 384, 128, False),       # one key tile: the odd tile slot of the single-tile CTA has no work
+    (2, 64, 936, False),        # single-tile CTA, 8 key tiles, the last one (odd slot) without an upper half
+    (2, 320, 936, True),        # same key layout behind a full CTA + a single-tile CTA, padded keys
+    (1, 40, 520, False),        # single-tile CTA, 5 key tiles: last tile on the even slot, 8 keys in it
     (1, 900, 700, False),       # three full CTAs + a single-tile CTA, ragged keys
 ]
 
