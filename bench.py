@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"],
+                    help="reference: the reference's CPU path (what the driver's reference arm runs); reference-gpu: the same "
+                         "eager PyTorch path on this GPU (fp32 and autocast bf16) -- the 'beat it on the same box' number")
     ap.add_argument("--batch", type=int, default=32, help="pairs per GPU per step")
     ap.add_argument("--layers", type=int, default=2)
     ap.add_argument("--config", default="C2", help="svol_b200.synth.CONFIGS key (C2 = BASELINE configs[1])")
@@ -204,6 +206,74 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_reference_gpu(args):
+    """The reference's eager PyTorch path ON THE B200: oracle/torch_port.py --
+    the reference's own ATen / scipy call sequence (cross_modal_transformer.py:105-160 with nn.MultiheadAttention's
+    need_weights=True score materialisation, matcher.py:38-119 with its full cross-batch cost matrix, the D2H copy and one
+    scipy call per frame, loss.py:126-157) -- with every tensor on cuda:0, in fp32 (TF32 off, PyTorch's default: what the
+    reference's scripts run) and under torch.autocast(bfloat16).  Same workload, batch and step definition as our arm;
+    CUDA events around K steps; targets resident as the nested dict the reference consumes."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from dataclasses import replace
+    from oracle import torch_port as tp
+    from svol_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    cfg = replace(synth.CONFIGS[args.config], num_layers=args.layers)
+    B = args.batch
+    sd = {k: v.to(dev) for k, v in tp.state_dict_to_torch(synth.random_state_dict(cfg, 0)).items()}
+    sets = []
+    for s_ in range(2):
+        inp = synth.make_inputs(cfg, B, seed=s_, padded=True)
+        tg = synth.targets_to_torch(synth.make_targets(cfg, B, seed=s_, frame_mask=inp["frame_mask"]))
+        sets.append(({k: torch.from_numpy(inp[k]).to(dev) for k in ("src_sketch", "src_sketch_mask", "src_video", "src_video_mask")}, tg))
+
+    def step(i):
+        t, tg = sets[i & 1]
+        out = tp.svanet_forward(sd, t["src_sketch"], t["src_sketch_mask"], t["src_video"], t["src_video_mask"], nheads=cfg.nheads)
+        out = {"pred_logits": out["pred_logits"].float(), "pred_boxes": out["pred_boxes"].float(),
+               "aux_outputs": [{k: v.float() for k, v in a.items()} for a in out["aux_outputs"]]}
+        return tp.set_criterion(out, tg, cfg)
+
+    def timed(steps, warmup):
+        for i in range(warmup):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    sampler = ClockSampler(dev.index or 0)
+    steps, warmup = args.steps, max(args.warmup, 3)
+    with torch.no_grad():
+        sampler.start()
+        ms_f32 = timed(steps, warmup)
+        clocks = sampler.stop()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ms_bf16 = timed(steps, warmup)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
+        ms_tf32 = timed(steps, warmup)
+    line = {"impl": "reference-gpu", "metric": METRIC, "value": B / (ms_f32 * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_f32, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, cfg), "clocks": clocks,
+            "variants": {"fp32": {"value": B / (ms_f32 * 1e-3), "ms_per_step": ms_f32},
+                         "fp32_tf32_matmul": {"value": B / (ms_tf32 * 1e-3), "ms_per_step": ms_tf32},
+                         "autocast_bf16": {"value": B / (ms_bf16 * 1e-3), "ms_per_step": ms_bf16}},
+            "what": "oracle/torch_port.py on cuda: the reference's eager ATen / scipy call sequence (pinned to the reference's "
+                    "golden outputs on CPU), torch " + torch.__version__,
+            "gpu": torch.cuda.get_device_name(dev)}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def main():
     args = parse()
@@ -211,6 +281,8 @@ def main():
         return run_train(args)
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "reference-gpu":
+        return run_reference_gpu(args)
     # stdout carries exactly one JSON line: library banners (NCCL prints its version to stdout) go to stderr
     real_stdout = os.dup(1)
     os.dup2(2, 1)
@@ -385,7 +457,20 @@ def main():
         (flat.tgt_off.numel() + flat.match_off.numel() + flat.video_tgt_off.numel() + flat.video_match_off.numel()
          + flat.match_video.numel()) * 4 + flat.cost_off.numel() * 8
     d2h = cfg.num_layers * 4 * 4
-    launches_per_step = model.engine.launches_per_forward + (3 if flat.per_frame else 2)
+    launches_per_step = model.engine.launches_per_forward + 3        # + match, match_finalize, criterion
+
+    # end-to-end index agreement with the reference on the headline batch (north_star; svol_b200/parity.py): reference
+    # forward -> reference matcher (committed fixture tests/golden/head_C2_b32.npz) vs this GPU's forward -> matcher
+    agreement = None
+    gpath = os.path.join(ROOT, "tests", "golden", "head_C2_b32.npz")
+    if rank == 0 and args.config == "C2" and args.layers == 2 and os.path.exists(gpath):
+        from svol_b200.parity import index_agreement
+        golden = dict(np.load(gpath))
+        with torch.no_grad():           # the fixture's weights (same architecture; the timed runs above used seed 0)
+            model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.random_state_dict(cfg, int(golden["seed"])).items()})
+        agreement = index_agreement(model, criterion.matcher, cfg, golden, dev)
+        with torch.no_grad():
+            model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.random_state_dict(cfg, 0).items()})
 
     roofline, breakdown = None, None
     cpu_baseline = None
@@ -419,7 +504,7 @@ def main():
                                   "h2d_bytes_per_step": int(h2d - sets[0]["host"]["src_video"].numel() * 2)},
             "gpu_launches": int(launches_per_step * args.steps), "host_numa_bound": bool(numa_bound),
             "host_enqueue_ms_per_step": host_ms[0],
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "index_agreement_vs_reference": agreement,
             "tflops_algorithmic": synth.algorithmic_flops_per_pair(cfg) * pairs / (ms_step * 1e-3) / 1e12}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SVOL_ABI_VERSION 12
+#define SVOL_ABI_VERSION 13
 
 enum {
   SVOL_OK = 0,
@@ -261,11 +261,26 @@ int svol_heads(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const 
  *   logits [NL,B,Q,2], boxes [NL,B,Q,4] fp32 (cxcywh); tgt_boxes [S,4] fp32 (cxcywh)
  *   tgt_off   [P+1] int32, P = B*problems_per_video : target range of problem p
  *   match_off [P+1] int32 : output range of problem p (min(rows, cols) entries)
- *   cost_ws   fp32 workspace, cost_off[p] (int64, [P+1]) = offset of problem p's block inside one
- *             layer's slab of cost_off[P] floats; total NL*cost_off[P] floats
- *   pred_idx, tgt_idx [NL, K] int64, K = match_off[P]: query index inside the video, GLOBAL target
- *             index (localised by svol_match_localize)
- *   status    [1] int32, set nonzero on NaN / -inf costs or infeasible problems
+ *   cost_ws   fp32 workspace or NULL.  When given, every problem's cost block (rows x cols, row-major) is also
+ *             written to it: cost_off[p] (int64, [P+1]) = offset of problem p's block inside one layer's slab of
+ *             cost_off[P] floats; total NL*cost_off[P] floats.  Required when rows_per_problem * max_cols * 4 bytes
+ *             exceed 96 KB (the block is then read back from the workspace instead of shared memory) and for
+ *             mode 1 / 2.
+ *   pred_idx, tgt_idx [NL, K] int64, K = match_off[P]: query index inside the video, target index (global, or
+ *             local to the video after `localize`)
+ *   status    [2] int32, ZERO-INITIALISED ONCE by the caller and then owned by the library: status[0] = result of
+ *             the most recent svol_match on this buffer (bit 0: NaN / -inf cost entries -- scipy's "matrix contains
+ *             invalid numeric entries"; bit 1: infeasible problem), status[1] = accumulator of the call in flight
+ *             (published and cleared by the call's own finalize kernel: no host-side memset per call, the call can
+ *             be captured in a CUDA graph).  A problem without a solution still gets valid indices (row r <->
+ *             column min(r, cols-1)) so that svol_criterion never dereferences garbage; check status[0].
+ *   mode      0: cost blocks + assignment (default); 1: cost blocks only (into cost_ws); 2: assignment from the
+ *             blocks already in cost_ws.  1 and 2 exist to time / profile the two halves separately.
+ *   solver    0: per-column solver state in registers (problems up to 320 working columns; wider ones fall back);
+ *             1: force the shared-memory-state solver (any size; test / triangulation aid)
+ *   localize  0: tgt_idx stays global; 1: PerFrameMatcher (matcher.py:114-115): per (layer, video) subtract the
+ *             minimum matched global index; 2: HungarianMatcher (matcher.py:158): subtract the video's first target
+ *             (video_tgt_off).  video_match_off [B+1] int32 = output range of each video.
  * ------------------------------------------------------------------------------------------ */
 typedef struct svol_match_args {
   const float* logits;
@@ -280,21 +295,37 @@ typedef struct svol_match_args {
   int32_t* status;
   int32_t NL, B, Q, problems_per_video, rows_per_problem, max_cols;
   float w_class, w_bbox, w_giou;
-  int32_t reserved;
+  int32_t K;                        /* match_off[P] as known to the host: row pitch of pred_idx / tgt_idx */
+  const int32_t* video_match_off;   /* [B+1] or NULL (localize == 0) */
+  const int32_t* video_tgt_off;     /* [B+1] or NULL (localize != 2) */
+  int32_t mode, solver, localize, reserved;
 } svol_match_args;
 
 int svol_match(const svol_match_args* args, void* stream);
 
-/* PerFrameMatcher's localisation quirk (matcher.py:114-115): per (layer, video) subtract the minimum
- * matched global target index.  video_match_off [B+1] int32 = output range of each video. */
+/* PerFrameMatcher's localisation quirk (matcher.py:114-115) as a stand-alone call for callers that ran svol_match with
+ * localize == 0: per (layer, video) subtract the minimum matched global target index. */
 int svol_match_localize(int64_t* tgt_idx, const int32_t* video_match_off, int32_t NL, int32_t B,
                         int32_t K, void* stream);
+
+/* Batched scipy.optimize.linear_sum_assignment (matcher.py:93,158) on caller-supplied fp32 cost matrices, one warp
+ * per problem, the solver of svol_match.  Problem p: shape[2p] x shape[2p+1] row-major at cost + cost_off[p];
+ * min(rows, cols) assignments written to rows_out / cols_out + out_off[p] (rows ascending, as scipy returns them);
+ * status[p] = 0 ok, 1 invalid entries (NaN / -inf), 2 infeasible.  max_rows * max_cols * 4 bytes must fit in shared
+ * memory (<= ~190 KB).  solver as in svol_match_args. */
+int svol_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int32_t n_problems,
+                  int32_t max_rows, int32_t max_cols, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off,
+                  int32_t* status, int32_t solver, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * SetCriterion losses (lib/modeling/loss.py:39-60,76-103) for ALL decoder layers in one launch.
  *   losses [NL,4] fp32 = (loss_label, class_error, loss_bbox, loss_giou) per layer
  *   pred_idx / tgt_idx [NL,K] int64 as produced above (tgt_idx video-local),
- *   match_video [K] int32 = video of each matched pair, video_tgt_off [B+1] int32.
+ *   match_video [K] int32 = video of each matched pair (or NULL: derived from video_match_off [B+1] int32, the
+ *   output range of each video), video_tgt_off [B+1] int32.
+ *   meta: NULL, or a device int32 array whose first element is K -- the launch then does not depend on the batch's
+ *   number of matched pairs (one captured CUDA graph serves every batch); idx_pitch = fixed row pitch (>= K) of
+ *   pred_idx / tgt_idx in that case (0: pitch = K).  Out-of-range indices are clamped, never dereferenced.
  * svol_criterion_backward writes d(sum_i w_i * loss_i)/d(logits, boxes) with per-layer weights
  * grad_w [NL,3] = (w_label, w_bbox, w_giou) (train.py:227-228).
  * ------------------------------------------------------------------------------------------ */
@@ -309,7 +340,9 @@ typedef struct svol_criterion_args {
   float* losses;
   int32_t NL, B, Q, K;
   float eos_coef;
-  int32_t reserved;
+  int32_t idx_pitch;
+  const int32_t* video_match_off;
+  const int32_t* meta;
 } svol_criterion_args;
 
 int svol_criterion(const svol_criterion_args* args, void* stream);
@@ -459,6 +492,21 @@ int svol_pack_weights(const svol_pack_job* jobs, int32_t n_jobs, void* stream);
 /* Fused AdamW (torch.optim.AdamW, train.py:71-78) over one flat fp32 buffer; g is multiplied by grad_scale first. */
 int svol_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* The same update over a flat buffer made of parameter SEGMENTS with per-group hyper-parameters (torch.optim
+ * param_groups: train.py:72-96 builds them, the lr schedulers of train.py:129-137 rewrite group['lr']).
+ *   seg_end   [n_seg] int64 (device): exclusive end offset of every segment, ascending, multiples of 4; the last = n
+ *   seg_group [n_seg] int32 (device): group index of the segment, or -1 = skip it entirely (torch.optim.AdamW does
+ *             not touch a parameter whose .grad is None: no weight decay, no moment update)
+ *   groups    HOST array of n_groups <= SVOL_ADAMW_MAX_GROUPS entries, read during the call */
+#define SVOL_ADAMW_MAX_GROUPS 8
+typedef struct svol_adamw_group {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;        /* 1-based step count of the group's active parameters (bias correction) */
+} svol_adamw_group;
+int svol_adamw_segments(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end,
+                        const int32_t* seg_group, int32_t n_seg, const svol_adamw_group* groups, int32_t n_groups,
+                        float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,7 @@ def _pos_sine(mask, d, temperature=10000.0):
     """PositionEmbeddingSine(normalize=True) (position_encoding.py:51-71); mask (B,L) bool, True = valid."""
     x = mask.cumsum(1, dtype=torch.float32)
     x = x / (x[:, -1:] + 1e-6) * (2 * math.pi)
-    i = torch.arange(d, dtype=torch.float32)
+    i = torch.arange(d, dtype=torch.float32, device=mask.device)
     dim_t = temperature ** (2 * torch.div(i, 2, rounding_mode="trunc") / d)
     p = x[:, :, None] / dim_t
     return torch.stack((p[:, :, 0::2].sin(), p[:, :, 1::2].cos()), dim=3).flatten(2)
@@ -166,10 +166,10 @@ def per_frame_matcher(logits, boxes, targets, num_frames, q_per_frame, w_class=2
     B, Q = logits.shape[:2]
     prob = logits.flatten(0, 1).softmax(-1)
     obox = boxes.flatten(0, 1)
-    tgt = _target_boxes(targets)
+    tgt = _target_boxes(targets).to(obox.device)                                                  # matcher.py:70
     num_boxes = [int(n) for t in targets for n in t["num_boxes_per_frame"]]
     cost = w_bbox * torch.cdist(obox, tgt, p=1) - w_giou * _giou(_xyxy(obox), _xyxy(tgt)) - w_class * prob[:, :1]
-    cost = cost.view(B * num_frames, q_per_frame, -1)
+    cost = cost.view(B * num_frames, q_per_frame, -1).cpu()                                       # matcher.py:86
     res, off = [], 0
     for b in range(B):
         pv, tv = [], []
@@ -192,10 +192,10 @@ def video_matcher(logits, boxes, targets, w_class=2.0, w_bbox=5.0, w_giou=1.0):
     B, Q = logits.shape[:2]
     prob = logits.flatten(0, 1).softmax(-1)
     obox = boxes.flatten(0, 1)
-    tgt = _target_boxes(targets)
+    tgt = _target_boxes(targets).to(obox.device)
     sizes = [sum(len(fr) for fr in t["bboxes"].values()) for t in targets]
     cost = w_bbox * torch.cdist(obox, tgt, p=1) - w_giou * _giou(_xyxy(obox), _xyxy(tgt)) - w_class * prob[:, :1]
-    cost = cost.view(B, Q, -1)
+    cost = cost.view(B, Q, -1).cpu()                                                              # matcher.py:152
     res = []
     for b, c in enumerate(cost.split(sizes, -1)):
         r, cc = _lsap(c[b])
@@ -211,18 +211,19 @@ def set_criterion(outputs, targets, cfg):
                                      cfg.set_cost_bbox, cfg.set_cost_giou)
         return video_matcher(lg, bx, targets, cfg.set_cost_class, cfg.set_cost_bbox, cfg.set_cost_giou)
 
-    weight = torch.tensor([1.0, cfg.eos_coef])
+    dev = outputs["pred_logits"].device
+    weight = torch.tensor([1.0, cfg.eos_coef], device=dev)
     per_video = [torch.stack([torch.as_tensor(np.asarray(o["bbox"]), dtype=torch.float32)
-                              for fr in t["bboxes"].values() for o in fr]) for t in targets]
+                              for fr in t["bboxes"].values() for o in fr]).to(dev) for t in targets]
     losses, all_idx = {}, []
     layers = [(outputs["pred_logits"], outputs["pred_boxes"], "")]
     layers += [(a["pred_logits"], a["pred_boxes"], f"_{i}") for i, a in enumerate(outputs.get("aux_outputs", []))]
     for lg, bx, suffix in layers:
         idx = match(lg, bx)
         all_idx.append(idx)
-        bidx = torch.cat([torch.full_like(s, i) for i, (s, _) in enumerate(idx)])
+        bidx = torch.cat([torch.full_like(s, i) for i, (s, _) in enumerate(idx)])         # CPU int64, like the reference
         sidx = torch.cat([s for s, _ in idx])
-        tc = torch.full(lg.shape[:2], 1, dtype=torch.int64)
+        tc = torch.full(lg.shape[:2], 1, dtype=torch.int64, device=dev)
         tc[bidx, sidx] = 0
         losses["loss_label" + suffix] = F.cross_entropy(lg.transpose(1, 2), tc, weight, reduction="none").mean()
         matched = lg[bidx, sidx]

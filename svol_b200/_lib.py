@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libsvol_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # every symbol include/svol_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -22,11 +22,11 @@ SYMBOLS = [
     "svol_layernorm_f32_to_bf16", "svol_ln_linear_f32", "svol_posenc_sine", "svol_posenc_theta", "svol_add_pos_bf16",
     "svol_gate_vectors", "svol_gate_scores", "svol_gate_apply", "svol_gate_apply_theta", "svol_gate_fused",
     "svol_gate_fused_supported", "svol_heads",
-    "svol_match", "svol_match_localize", "svol_criterion", "svol_criterion_backward", "svol_postprocess",
+    "svol_match", "svol_match_localize", "svol_lsap_f32", "svol_criterion", "svol_criterion_backward", "svol_postprocess",
     # training step
     "svol_layernorm_bf16", "svol_layernorm_backward", "svol_gelu_bf16", "svol_act_backward", "svol_transpose_bf16",
     "svol_colsum_bf16", "svol_attention_backward_bf16", "svol_heads_backward", "svol_gate_backward",
-    "svol_gate_vectors_backward", "svol_ln_linear_f32_backward", "svol_batch_sum", "svol_accum_bf16", "svol_adamw",
+    "svol_gate_vectors_backward", "svol_ln_linear_f32_backward", "svol_batch_sum", "svol_accum_bf16", "svol_adamw", "svol_adamw_segments",
     "svol_pack_weights", "svol_layernorm_f32_to_bf16_dropout", "svol_ln_linear_f32_dropout", "svol_layernorm_nchw_to_bf16", "svol_layernorm_bf16_to_bf16",
     "svol_eval_max_iou", "svol_eval_average_precision",
 ]
@@ -92,6 +92,11 @@ class PackJob(C.Structure):
 PACK_BF16, PACK_TRANSPOSE = 1, 2
 
 
+class AdamwGroup(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("step", C.c_int32)]
+
+
 class MatchArgs(C.Structure):
     _fields_ = [
         ("logits", C.c_void_p), ("boxes", C.c_void_p), ("tgt_boxes", C.c_void_p), ("tgt_off", C.c_void_p),
@@ -99,7 +104,9 @@ class MatchArgs(C.Structure):
         ("tgt_idx", C.c_void_p), ("status", C.c_void_p),
         ("NL", C.c_int32), ("B", C.c_int32), ("Q", C.c_int32), ("problems_per_video", C.c_int32),
         ("rows_per_problem", C.c_int32), ("max_cols", C.c_int32),
-        ("w_class", C.c_float), ("w_bbox", C.c_float), ("w_giou", C.c_float), ("reserved", C.c_int32),
+        ("w_class", C.c_float), ("w_bbox", C.c_float), ("w_giou", C.c_float), ("K", C.c_int32),
+        ("video_match_off", C.c_void_p), ("video_tgt_off", C.c_void_p),
+        ("mode", C.c_int32), ("solver", C.c_int32), ("localize", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -108,7 +115,7 @@ class CriterionArgs(C.Structure):
         ("logits", C.c_void_p), ("boxes", C.c_void_p), ("tgt_boxes", C.c_void_p), ("pred_idx", C.c_void_p),
         ("tgt_idx", C.c_void_p), ("match_video", C.c_void_p), ("video_tgt_off", C.c_void_p), ("losses", C.c_void_p),
         ("NL", C.c_int32), ("B", C.c_int32), ("Q", C.c_int32), ("K", C.c_int32),
-        ("eos_coef", C.c_float), ("reserved", C.c_int32),
+        ("eos_coef", C.c_float), ("idx_pitch", C.c_int32), ("video_match_off", C.c_void_p), ("meta", C.c_void_p),
     ]
 
 
@@ -142,6 +149,7 @@ def _declare(lib: C.CDLL) -> None:
         "svol_heads": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp],
         "svol_match": [C.POINTER(MatchArgs), _vp],
         "svol_match_localize": [_vp, _vp, _i32, _i32, _i32, _vp],
+        "svol_lsap_f32": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
         "svol_criterion": [C.POINTER(CriterionArgs), _vp],
         "svol_criterion_backward": [C.POINTER(CriterionArgs), _vp, _vp, _vp, _vp],
         "svol_postprocess": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
@@ -161,6 +169,7 @@ def _declare(lib: C.CDLL) -> None:
         "svol_batch_sum": [_vp, _vp, _i32, _i32, _i32, _vp],
         "svol_accum_bf16": [_vp, _vp, _i64, _f32, _i32, _vp],
         "svol_adamw": [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp],
+        "svol_adamw_segments": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _i32, _f32, _vp],
         "svol_pack_weights": [_vp, _i32, _vp],
         "svol_eval_max_iou": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp],
         "svol_eval_average_precision": [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp],

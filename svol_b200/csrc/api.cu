@@ -122,6 +122,8 @@ int launch_ln_linear_f32_backward(const float*, const float*, const float*, cons
 int launch_batch_sum(const svol_bf16*, float*, int, int, int, cudaStream_t);
 int launch_accum_bf16(const svol_bf16*, float*, long long, float, int, cudaStream_t);
 int launch_adamw(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
+int launch_adamw_segments(float*, const float*, float*, float*, long long, const long long*, const int*, int,
+                          const svol_adamw_group*, int, float, cudaStream_t);
 int launch_pack_weights(const svol_pack_job*, int, cudaStream_t);
 // evaluate.cu
 int launch_eval_max_iou(const float*, const int*, const float*, const int*, int, int, int, double*, double*, cudaStream_t);
@@ -275,9 +277,17 @@ int svol_heads(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const 
 
 int svol_match(const svol_match_args* a, void* stream) {
   SVOL_REQUIRE(a); SVOL_REQUIRE(a->logits); SVOL_REQUIRE(a->boxes); SVOL_REQUIRE(a->tgt_boxes); SVOL_REQUIRE(a->tgt_off);
-  SVOL_REQUIRE(a->match_off); SVOL_REQUIRE(a->cost_off); SVOL_REQUIRE(a->cost_ws); SVOL_REQUIRE(a->pred_idx);
+  SVOL_REQUIRE(a->match_off); SVOL_REQUIRE(a->cost_off); SVOL_REQUIRE(a->pred_idx);
   SVOL_REQUIRE(a->tgt_idx); SVOL_REQUIRE(a->status);
   return launch_match(*a, SVOL_STREAM(stream));
+}
+int svol_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int32_t n_problems, int32_t max_rows,
+                  int32_t max_cols, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off, int32_t* status,
+                  int32_t solver, void* stream) {
+  SVOL_REQUIRE(cost); SVOL_REQUIRE(cost_off); SVOL_REQUIRE(shape); SVOL_REQUIRE(rows_out); SVOL_REQUIRE(cols_out);
+  SVOL_REQUIRE(out_off); SVOL_REQUIRE(status);
+  return launch_lsap_f32(cost, cost_off, shape, n_problems, max_rows, max_cols, rows_out, cols_out, out_off, status, solver,
+                         SVOL_STREAM(stream));
 }
 int svol_match_localize(int64_t* tgt_idx, const int32_t* video_match_off, int32_t NL, int32_t B, int32_t K,
                         void* stream) {
@@ -286,7 +296,7 @@ int svol_match_localize(int64_t* tgt_idx, const int32_t* video_match_off, int32_
 }
 int svol_criterion(const svol_criterion_args* a, void* stream) {
   SVOL_REQUIRE(a); SVOL_REQUIRE(a->logits); SVOL_REQUIRE(a->boxes); SVOL_REQUIRE(a->tgt_boxes); SVOL_REQUIRE(a->pred_idx);
-  SVOL_REQUIRE(a->tgt_idx); SVOL_REQUIRE(a->match_video); SVOL_REQUIRE(a->video_tgt_off); SVOL_REQUIRE(a->losses);
+  SVOL_REQUIRE(a->tgt_idx); SVOL_REQUIRE(a->video_tgt_off); SVOL_REQUIRE(a->losses);
   return launch_criterion(*a, SVOL_STREAM(stream));
 }
 int svol_criterion_backward(const svol_criterion_args* a, const float* grad_w, float* grad_logits, float* grad_boxes,
@@ -398,6 +408,14 @@ int svol_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr
                float weight_decay, int32_t step, float grad_scale, void* stream) {
   SVOL_REQUIRE(p); SVOL_REQUIRE(g); SVOL_REQUIRE(m); SVOL_REQUIRE(v);
   return launch_adamw(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, SVOL_STREAM(stream));
+}
+int svol_adamw_segments(float* p, const float* g, float* m, float* v, int64_t n, const int64_t* seg_end,
+                        const int32_t* seg_group, int32_t n_seg, const svol_adamw_group* groups, int32_t n_groups,
+                        float grad_scale, void* stream) {
+  SVOL_REQUIRE(p); SVOL_REQUIRE(g); SVOL_REQUIRE(m); SVOL_REQUIRE(v); SVOL_REQUIRE(seg_end); SVOL_REQUIRE(seg_group);
+  SVOL_REQUIRE(groups);
+  return launch_adamw_segments(p, g, m, v, n, reinterpret_cast<const long long*>(seg_end), seg_group, n_seg, groups, n_groups,
+                               grad_scale, SVOL_STREAM(stream));
 }
 
 }  // extern "C"

@@ -51,13 +51,43 @@ __device__ __forceinline__ PairGeom pair_geom(const float4& s, const float4& t) 
   return g;
 }
 
-__device__ __forceinline__ void mark_matched(uint32_t* bitmap, const CriterionArgs& a, int layer) {
+// Sizes that may live on the device (meta[0] = K of the batch in the static target buffer) so that one captured launch
+// serves every batch; the index arrays then have a fixed row pitch.
+struct CritDims { int K, pitch, S; };
+__device__ __forceinline__ CritDims crit_dims(const CriterionArgs& a) {
+  CritDims d;
+  d.K = a.meta ? a.meta[0] : a.K;
+  d.pitch = a.idx_pitch > 0 ? a.idx_pitch : d.K;
+  d.S = a.video_tgt_off[a.B];
+  return d;
+}
+// video of matched pair k: the caller's table, or a binary search in the per-video output ranges
+__device__ __forceinline__ int pair_video(const CriterionArgs& a, int k) {
+  if (a.match_video) return a.match_video[k];
+  int lo = 0, hi = a.B;               // video_match_off[lo] <= k < video_match_off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (a.video_match_off[mid] <= k) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// Indices are clamped into range: a problem without a solution (NaN costs; reported through the matcher's status word,
+// matcher.cu) must not turn into out-of-bounds shared / global accesses here.
+__device__ __forceinline__ int pred_entry(const CriterionArgs& a, int b, int64_t q) {
+  return b * a.Q + static_cast<int>(q < 0 ? 0 : (q >= a.Q ? a.Q - 1 : q));
+}
+__device__ __forceinline__ int tgt_entry(const CriterionArgs& a, const CritDims& d, int b, int64_t t) {
+  const long long g = static_cast<long long>(a.video_tgt_off[b]) + t;
+  return static_cast<int>(g < 0 ? 0 : (g >= d.S ? d.S - 1 : g));
+}
+
+__device__ __forceinline__ void mark_matched(uint32_t* bitmap, const CriterionArgs& a, const CritDims& d, int layer) {
   const int words = (a.B * a.Q + 31) >> 5;
   for (int i = threadIdx.x; i < words; i += blockDim.x) bitmap[i] = 0u;
   __syncthreads();
-  const int64_t* pi = a.pred_idx + static_cast<size_t>(layer) * a.K;
-  for (int k = threadIdx.x; k < a.K; k += blockDim.x) {
-    const int e = a.match_video[k] * a.Q + static_cast<int>(pi[k]);
+  const int64_t* pi = a.pred_idx + static_cast<size_t>(layer) * d.pitch;
+  for (int k = threadIdx.x; k < d.K; k += blockDim.x) {
+    const int e = pred_entry(a, pair_video(a, k), pi[k]);
     atomicOr(&bitmap[e >> 5], 1u << (e & 31));
   }
   __syncthreads();
@@ -68,7 +98,8 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_kernel(const Criterion
   __shared__ double red[32];
   const int layer = blockIdx.x, tid = threadIdx.x;
   const int n = a.B * a.Q;
-  mark_matched(bitmap, a, layer);
+  const CritDims d = crit_dims(a);
+  mark_matched(bitmap, a, d, layer);
 
   // weighted cross-entropy over every query (loss.py:50-55): sum(w * nll) / (B*Q)
   const float2* lg = reinterpret_cast<const float2*>(a.logits) + static_cast<size_t>(layer) * n;
@@ -82,17 +113,17 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_kernel(const Criterion
     ce += static_cast<double>((fg ? 1.0f : a.eos_coef) * nll);
   }
   // matched pairs: class_error (loss.py:57-59), L1 and GIoU (loss.py:92-102)
-  const int64_t* pi = a.pred_idx + static_cast<size_t>(layer) * a.K;
-  const int64_t* ti = a.tgt_idx + static_cast<size_t>(layer) * a.K;
+  const int64_t* pi = a.pred_idx + static_cast<size_t>(layer) * d.pitch;
+  const int64_t* ti = a.tgt_idx + static_cast<size_t>(layer) * d.pitch;
   const float4* bx = reinterpret_cast<const float4*>(a.boxes) + static_cast<size_t>(layer) * n;
   double correct = 0.0, l1 = 0.0, gl = 0.0;
-  for (int k = tid; k < a.K; k += blockDim.x) {
-    const int b = a.match_video[k];
-    const int e = b * a.Q + static_cast<int>(pi[k]);
+  for (int k = tid; k < d.K; k += blockDim.x) {
+    const int b = pair_video(a, k);
+    const int e = pred_entry(a, b, pi[k]);
     const float2 l = __ldg(lg + e);
     correct += (l.x >= l.y) ? 1.0 : 0.0;        // top-1 == foreground (index 0 wins ties)
     const float4 s = __ldg(bx + e);
-    const float4 t = __ldg(reinterpret_cast<const float4*>(a.tgt_boxes) + a.video_tgt_off[b] + static_cast<int>(ti[k]));
+    const float4 t = __ldg(reinterpret_cast<const float4*>(a.tgt_boxes) + tgt_entry(a, d, b, ti[k]));
     l1 += static_cast<double>(fabsf(s.x - t.x) + fabsf(s.y - t.y) + fabsf(s.z - t.z) + fabsf(s.w - t.w));
     gl += static_cast<double>(1.0f - pair_geom(s, t).giou);
   }
@@ -103,9 +134,9 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_kernel(const Criterion
   if (tid == 0) {
     float* o = a.losses + layer * 4;
     o[0] = static_cast<float>(ce / n);
-    o[1] = static_cast<float>(100.0 - correct * (100.0 / a.K));
-    o[2] = static_cast<float>(l1 / (4.0 * a.K));
-    o[3] = static_cast<float>(gl / a.K);
+    o[1] = static_cast<float>(100.0 - correct * (100.0 / d.K));
+    o[2] = static_cast<float>(l1 / (4.0 * d.K));
+    o[3] = static_cast<float>(gl / d.K);
   }
 }
 
@@ -117,7 +148,8 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_backward_kernel(const 
   extern __shared__ uint32_t bitmap[];
   const int layer = blockIdx.x, tid = threadIdx.x;
   const int n = a.B * a.Q;
-  mark_matched(bitmap, a, layer);
+  const CritDims d = crit_dims(a);
+  mark_matched(bitmap, a, d, layer);
   const float w_label = grad_w[layer * 3 + 0], w_bbox = grad_w[layer * 3 + 1], w_giou = grad_w[layer * 3 + 2];
   const float2* lg = reinterpret_cast<const float2*>(a.logits) + static_cast<size_t>(layer) * n;
   float2* glg = reinterpret_cast<float2*>(grad_logits) + static_cast<size_t>(layer) * n;
@@ -133,15 +165,15 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_backward_kernel(const 
     glg[e] = make_float2(w * (p0 - (fg ? 1.f : 0.f)), w * (p1 - (fg ? 0.f : 1.f)));
     if (!fg) gbx[e] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  const int64_t* pi = a.pred_idx + static_cast<size_t>(layer) * a.K;
-  const int64_t* ti = a.tgt_idx + static_cast<size_t>(layer) * a.K;
+  const int64_t* pi = a.pred_idx + static_cast<size_t>(layer) * d.pitch;
+  const int64_t* ti = a.tgt_idx + static_cast<size_t>(layer) * d.pitch;
   const float4* bx = reinterpret_cast<const float4*>(a.boxes) + static_cast<size_t>(layer) * n;
-  const float s_l1 = w_bbox / (4.0f * a.K), s_g = -w_giou / a.K;       // loss_giou = mean(1 - giou)
-  for (int k = tid; k < a.K; k += blockDim.x) {
-    const int b = a.match_video[k];
-    const int e = b * a.Q + static_cast<int>(pi[k]);
+  const float s_l1 = w_bbox / (4.0f * d.K), s_g = -w_giou / d.K;       // loss_giou = mean(1 - giou)
+  for (int k = tid; k < d.K; k += blockDim.x) {
+    const int b = pair_video(a, k);
+    const int e = pred_entry(a, b, pi[k]);
     const float4 s = __ldg(bx + e);
-    const float4 t = __ldg(reinterpret_cast<const float4*>(a.tgt_boxes) + a.video_tgt_off[b] + static_cast<int>(ti[k]));
+    const float4 t = __ldg(reinterpret_cast<const float4*>(a.tgt_boxes) + tgt_entry(a, d, b, ti[k]));
     const PairGeom g = pair_geom(s, t);
     // d inter, d hull, d area w.r.t. the four corners of the prediction
     const float di_x1 = (g.iw > 0.f && g.x1 < g.tx1) ? g.ih : 0.f, di_x0 = (g.iw > 0.f && g.x0 > g.tx0) ? -g.ih : 0.f;
@@ -167,7 +199,11 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_backward_kernel(const 
 }
 
 static int check_criterion(const CriterionArgs& a, size_t* smem) {
-  if (a.NL <= 0 || a.B <= 0 || a.Q <= 0 || a.K <= 0) return svol_fail(SVOL_ERR_SHAPE, "criterion: bad sizes (K must be > 0)");
+  if (a.NL <= 0 || a.B <= 0 || a.Q <= 0 || (a.meta == nullptr && a.K <= 0))
+    return svol_fail(SVOL_ERR_SHAPE, "criterion: bad sizes (K must be > 0)");
+  if (a.match_video == nullptr && a.video_match_off == nullptr)
+    return svol_fail(SVOL_ERR_NULL, "criterion: match_video or video_match_off is required");
+  if (a.meta != nullptr && a.idx_pitch <= 0) return svol_fail(SVOL_ERR_SHAPE, "criterion: a device-side K needs idx_pitch");
   *smem = static_cast<size_t>((a.B * a.Q + 31) / 32) * 4;
   if (*smem > 160 * 1024) return svol_fail(SVOL_ERR_SHAPE, "criterion: B*Q too large for the shared-memory bitmap");
   return SVOL_OK;

@@ -4,15 +4,28 @@
 // 131-159): the reference builds the full cross-batch (B*Q) x sum(n) cost matrix on the device,
 // copies it to the host and calls scipy.optimize.linear_sum_assignment once per frame.  Here one
 // warp owns one assignment problem: it forms only that problem's cost block (the block-diagonal
-// entries the reference reads, matcher.py:92-93) and solves it in place.
+// entries the reference reads, matcher.py:92-93) in shared memory and solves it in place.
 //
 // Bit-exactness: the cost is evaluated in fp32 with the reference's operation order and with
 // explicit round-to-nearest intrinsics so the compiler cannot contract a*b+c into an FMA
 // (matcher.py:59-85; box_utils.py:9-13,24-37,55-61).  The solver is the shortest-augmenting-path
 // algorithm scipy uses (Crouse 2016) on costs promoted to fp64, including its candidate order
-// (columns scanned last-to-first), its preference for unassigned columns among equal minima, the
-// transpose for tall problems and rows returned in ascending order.
+// (the `remaining` list: columns last-to-first, the last entry moved into a removed slot), its
+// preference for unassigned columns among equal minima, the transpose for tall problems and rows
+// returned in ascending order.
+//
+// Solver layout (round 2): the per-column state of a problem (dual v, shortest-path cost, position
+// in scipy's `remaining` list, scanned / free flags) lives in REGISTERS, column j on lane j % 32 --
+// up to 10 columns per lane (320 columns); only what is addressed by row (u, col4row) or walked
+// sequentially (path, row4col) stays in shared memory.  One path step is then: one conflict-free
+// shared-memory load of the cost row per owned column, three fp64 adds, and THREE `redux.sync`
+// warp reductions -- the fp64 minimum as two 32-bit halves of an order-preserving key, then one
+// packed (free?, position) key that encodes scipy's tie rule -- instead of 25 shuffles and seven
+// dependent shared-memory round trips.  Problems wider than 320 columns keep the shared-memory
+// state solver (`lsap_warp_smem`), which is also selectable for tests.
 #include <math_constants.h>
+
+#include <climits>
 
 #include "common.cuh"
 #include "svol_internal.h"
@@ -61,79 +74,150 @@ __device__ __forceinline__ double warp_min_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ int warp_min_i(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+__device__ __forceinline__ int warp_min_i(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Shared-memory workspace of one warp's problem.  `ms` / `mb` = even upper bounds of min / max(rows, cols).
+struct LsapSmem {
+  double* u;        // [ms]   row duals
+  double* v;        // [mb]   (shared-memory-state solver only)
+  double* spc;      // [mb]   (shared-memory-state solver only)
+  int* col4row;     // [ms]
+  int* row4col;     // [mb]
+  int* path;        // [mb]
+  int* remaining;   // [mb]   (shared-memory-state solver only)
+  uint8_t* SR;      // [ms]   (shared-memory-state solver only)
+  uint8_t* SC;      // [mb]   (shared-memory-state solver only)
+};
+__host__ __device__ inline size_t lsap_smem_bytes(int ms, int mb) {
+  return (sizeof(double) * (ms + 2 * mb) + sizeof(int) * (3 * mb + ms) + (ms + mb) + 15) & ~static_cast<size_t>(15);
 }
-__device__ __forceinline__ int warp_max_i(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+__device__ __forceinline__ LsapSmem lsap_carve(uint8_t* raw, int ms, int mb) {
+  LsapSmem s;
+  s.u = reinterpret_cast<double*>(raw);
+  s.v = s.u + ms;
+  s.spc = s.v + mb;
+  s.col4row = reinterpret_cast<int*>(s.spc + mb);
+  s.row4col = s.col4row + ms;
+  s.path = s.row4col + mb;
+  s.remaining = s.path + mb;
+  s.SR = reinterpret_cast<uint8_t*>(s.remaining + mb);
+  s.SC = s.SR + ms;
+  return s;
 }
 
-// One warp per problem.  Dynamic shared memory per warp (n_small = min(rows, cols), n_big = max):
-//   double u[n_small], v[n_big], spc[n_big]; int path[n_big], col4row[n_small], row4col[n_big],
-//   remaining[n_big]; uint8 SR[n_small], SC[n_big]
-// When a problem's cost block fits (cost_smem_floats > 0) it is also kept in shared memory: the solver re-reads
-// costs once per scanned column per path step, and from the global workspace every such read was an exposed L2
-// round trip (C5 stress: 482 us -> see profiles; the default 10 x n_f problems are launch-latency bound either way).
-__global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_small, int max_big, int cost_smem_floats) {
-  extern __shared__ __align__(16) uint8_t sm_raw[];
-  const int lane = threadIdx.x;
-  const int P = a.B * a.problems_per_video;
-  const int layer = blockIdx.x / P, p = blockIdx.x - layer * P;
-  const int video = p / a.problems_per_video, local = p - video * a.problems_per_video;
-  const int nrows = a.rows_per_problem;
-  const int t0 = a.tgt_off[p], ncols = a.tgt_off[p + 1] - t0;
-  if (ncols <= 0 || nrows <= 0) return;
+// Order-preserving 64-bit key of a double (no NaN; -0 folded into +0 first).
+__device__ __forceinline__ unsigned long long ordered_key(double x) {
+  const long long b = __double_as_longlong(x + 0.0);
+  return static_cast<unsigned long long>(b) ^ (static_cast<unsigned long long>(b >> 63) | 0x8000000000000000ull);
+}
 
-  double* u = reinterpret_cast<double*>(sm_raw);
-  double* v = u + max_small;
-  double* spc = v + max_big;
-  int* path = reinterpret_cast<int*>(spc + max_big);
-  int* col4row = path + max_big;
-  int* row4col = col4row + max_small;
-  int* remaining = row4col + max_big;
-  uint8_t* SR = reinterpret_cast<uint8_t*>(remaining + max_big);
-  uint8_t* SC = SR + max_small;
-  float* Cs = reinterpret_cast<float*>(sm_raw + ((sizeof(double) * (max_small + 2 * max_big) + sizeof(int) * (3 * max_big + max_small) +
-                                                   (max_small + max_big) + 15) & ~static_cast<size_t>(15)));
-  const bool cost_in_smem = nrows * ncols <= cost_smem_floats;
-
-  // ---- cost block, row-major nrows x ncols, in this layer's slab of the workspace
-  const size_t q0 = (static_cast<size_t>(layer) * a.B + video) * a.Q + static_cast<size_t>(local) * nrows;
-  float* C = a.cost_ws + static_cast<size_t>(layer) * a.cost_off[P] + a.cost_off[p];
-  bool bad = false;
-  for (int e = lane; e < nrows * ncols; e += 32) {
-    const int r = e / ncols, c = e - r * ncols;
-    const float2 lg = reinterpret_cast<const float2*>(a.logits)[q0 + r];
-    const float4 pb = reinterpret_cast<const float4*>(a.boxes)[q0 + r];
-    const float4 tb = reinterpret_cast<const float4*>(a.tgt_boxes)[t0 + c];
-    const Box pa{pb.x, pb.y, pb.z, pb.w}, ta{tb.x, tb.y, tb.z, tb.w};
-    const float cost = pair_cost(fg_prob(lg.x, lg.y), pa, ta, a.w_class, a.w_bbox, a.w_giou);
-    bad |= (cost != cost) || (cost == -CUDART_INF_F);
-    C[e] = cost;
-    if (cost_in_smem) Cs[e] = cost;
+// Register-state solver.  C: cost block of the WORKING problem (nr <= nc <= 32 * CPL), entry (i, j) at C[i * si + j * sj]
+// (shared memory: si = nc, sj = 1; a tall block read in place from the global workspace: si = 1, sj = its row pitch).
+// Returns 0, or 2 when the problem is infeasible (every remaining entry +inf).  On return col4row / row4col hold the
+// assignment of the working problem.
+template <int CPL>
+__device__ __forceinline__ int lsap_warp_regs(const float* __restrict__ C, int si, int sj, int nr, int nc, const LsapSmem& s,
+                                              int lane) {
+  double v[CPL], spc[CPL];
+  int pos[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) v[k] = 0.0;
+  unsigned valid = 0, freem = 0;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+    const int j = lane + 32 * k;
+    if (j < nc) { valid |= 1u << k; s.row4col[j] = -1; s.path[j] = -1; }
   }
-  if (__any_sync(0xffffffffu, bad)) {      // scipy: "matrix contains invalid numeric entries"
-    if (lane == 0) atomicOr(a.status, 1);
-    return;
-  }
+  freem = valid;
+  for (int i = lane; i < nr; i += 32) { s.u[i] = 0.0; s.col4row[i] = -1; }
   __syncwarp();
 
-  // ---- rectangular LSAP on the short side (scipy transposes tall problems)
-  const bool transposed = ncols < nrows;
-  const int nr = transposed ? ncols : nrows;      // rows of the working problem
-  const int nc = transposed ? nrows : ncols;
-  const float* Cr = cost_in_smem ? Cs : C;
-  auto cost_at = [&](int i, int j) -> double {
-    return static_cast<double>(transposed ? Cr[j * ncols + i] : Cr[i * ncols + j]);
-  };
+  for (int cur = 0; cur < nr; ++cur) {
+    unsigned scm = 0;                                   // scanned columns (SC) among mine
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) { spc[k] = CUDART_INF; pos[k] = nc - 1 - (lane + 32 * k); }   // remaining[t] = nc - t - 1
+    int n_rem = nc, i = cur, sink = -1;
+    double best = 0.0;
+    while (sink == -1) {
+      const double ui = s.u[i];
+      const float* crow = C + static_cast<size_t>(i) * si;
+      double lw = CUDART_INF;
+      unsigned kw = 0;
+      int jw = -1;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        if (((valid & ~scm) >> k) & 1u) {
+          const int j = lane + 32 * k;
+          const double r = ((best + static_cast<double>(crow[static_cast<size_t>(j) * sj])) - ui) - v[k];
+          if (r < spc[k]) { s.path[j] = i; spc[k] = r; }
+          const double sv = spc[k];
+          // scipy: a strictly lower value wins; among equal values a free column found later in `remaining` order wins.
+          // As a set function: max over the minima of (free ? 2^31 + position : 2^31 - 1 - position).
+          const unsigned key = ((freem >> k) & 1u) ? (0x80000000u | static_cast<unsigned>(pos[k]))
+                                                   : (0x7fffffffu - static_cast<unsigned>(pos[k]));
+          if (sv < lw || (sv == lw && key > kw)) { lw = sv; kw = key; jw = j; }
+        }
+      }
+      const unsigned long long ok = ordered_key(lw);
+      const unsigned hi = static_cast<unsigned>(ok >> 32), lo = static_cast<unsigned>(ok);
+      const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+      const bool mine = hi == mh && lo == ml && jw >= 0;
+      const unsigned kmax = __reduce_max_sync(0xffffffffu, mine ? kw : 0u);
+      if (mh == 0xfff00000u && ml == 0u) return 2;      // minimum is +inf: infeasible
+      const unsigned who = __ballot_sync(0xffffffffu, mine && kw == kmax);
+      const int src = __ffs(who) - 1;
+      const int j = __shfl_sync(0xffffffffu, jw, src);
+      best = __shfl_sync(0xffffffffu, lw, src);
+      const int pick = (kmax & 0x80000000u) ? static_cast<int>(kmax & 0x7fffffffu) : static_cast<int>(0x7fffffffu - kmax);
+      const int owner = s.row4col[j];
+      if (lane == (j & 31)) scm |= 1u << (j >> 5);
+      --n_rem;                                          // remaining[pick] = remaining[--n_rem]
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) pos[k] = pos[k] == n_rem ? pick : pos[k];
+      if (owner == -1) sink = j; else i = owner;
+    }
+    // dual update: rows reached through a scanned column (their col4row is that column), then the scanned columns
+    if (lane == 0) s.u[cur] += best;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      if ((scm >> k) & 1u) {
+        const int j = lane + 32 * k;
+        const double dlt = best - spc[k];
+        if (j != sink) s.u[s.row4col[j]] += dlt;
+        v[k] -= dlt;
+      }
+    }
+    __syncwarp();
+    // augment along the path (sequential)
+    if (lane == 0) {
+      int j = sink;
+      while (true) {
+        const int r = s.path[j];
+        s.row4col[j] = r;
+        const int prev = s.col4row[r];
+        s.col4row[r] = j;
+        j = prev;
+        if (r == cur) break;
+      }
+    }
+    if (lane == (sink & 31)) freem &= ~(1u << (sink >> 5));
+    __syncwarp();
+  }
+  return 0;
+}
+
+// Shared-memory-state solver (any width).  Same algorithm, all state in shared memory.
+__device__ __noinline__ int lsap_warp_smem(const float* __restrict__ C, int si, int sj, int nr, int nc, const LsapSmem& s,
+                                           int lane) {
+  double* u = s.u; double* v = s.v; double* spc = s.spc;
+  int* path = s.path; int* col4row = s.col4row; int* row4col = s.row4col; int* remaining = s.remaining;
+  uint8_t* SR = s.SR; uint8_t* SC = s.SC;
   for (int i = lane; i < nr; i += 32) { u[i] = 0.0; col4row[i] = -1; }
   for (int j = lane; j < nc; j += 32) { v[j] = 0.0; row4col[j] = -1; path[j] = -1; }
   __syncwarp();
-
   for (int cur = 0; cur < nr; ++cur) {
     for (int j = lane; j < nc; j += 32) { remaining[j] = nc - j - 1; SC[j] = 0; spc[j] = CUDART_INF; }
     for (int i = lane; i < nr; i += 32) SR[i] = 0;
@@ -147,21 +231,18 @@ __global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_sm
       int first_pos = INT_MAX, last_free = -1;
       for (int t = lane; t < n_rem; t += 32) {
         const int j = remaining[t];
-        const double r = ((best + cost_at(i, j)) - ui) - v[j];
-        double s = spc[j];
-        if (r < s) { path[j] = i; spc[j] = r; s = r; }
+        const double r = ((best + static_cast<double>(C[static_cast<size_t>(i) * si + static_cast<size_t>(j) * sj])) - ui) - v[j];
+        double sv = spc[j];
+        if (r < sv) { path[j] = i; spc[j] = r; sv = r; }
         const bool free_col = row4col[j] == -1;
-        if (s < lowest) { lowest = s; first_pos = t; last_free = free_col ? t : -1; }
-        else if (s == lowest && free_col) last_free = t;
+        if (sv < lowest) { lowest = sv; first_pos = t; last_free = free_col ? t : -1; }
+        else if (sv == lowest && free_col) last_free = t;
       }
       const double gl = warp_min_d(lowest);
       const bool mine = lowest == gl && first_pos != INT_MAX;
       const int fp = warp_min_i(mine ? first_pos : INT_MAX);
       const int lf = warp_max_i(mine ? last_free : -1);
-      if (!(gl < CUDART_INF)) {             // infeasible (cannot happen with finite costs)
-        if (lane == 0) atomicOr(a.status, 2);
-        return;
-      }
+      if (!(gl < CUDART_INF)) return 2;
       // sequential rule: the first minimum wins unless a later (or the same) equal minimum is free
       const int pick = lf >= 0 ? lf : fp;
       best = gl;
@@ -174,7 +255,6 @@ __global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_sm
       --n_rem;
       __syncwarp();
     }
-    // dual update
     for (int r = lane; r < nr; r += 32) {
       if (r == cur) u[r] += best;
       else if (SR[r]) u[r] += best - spc[col4row[r]];
@@ -182,7 +262,6 @@ __global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_sm
     for (int j = lane; j < nc; j += 32)
       if (SC[j]) v[j] -= best - spc[j];
     __syncwarp();
-    // augment along the path (sequential)
     if (lane == 0) {
       int j = sink;
       while (true) {
@@ -196,43 +275,171 @@ __global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int max_sm
     }
     __syncwarp();
   }
+  return 0;
+}
 
-  // ---- emit (query index within the video, global target index), query ascending
-  const int m0 = a.match_off[p];
-  int64_t* po = a.pred_idx + static_cast<size_t>(layer) * a.match_off[P] + m0;
-  int64_t* to = a.tgt_idx + static_cast<size_t>(layer) * a.match_off[P] + m0;
+__device__ __forceinline__ int lsap_dispatch(const float* C, int si, int sj, int nr, int nc, const LsapSmem& s, int lane,
+                                             bool force_smem_state) {
+  if (force_smem_state || nc > 320) return lsap_warp_smem(C, si, sj, nr, nc, s, lane);
+  if (nc <= 32) return lsap_warp_regs<1>(C, si, sj, nr, nc, s, lane);
+  if (nc <= 64) return lsap_warp_regs<2>(C, si, sj, nr, nc, s, lane);
+  if (nc <= 128) return lsap_warp_regs<4>(C, si, sj, nr, nc, s, lane);
+  return lsap_warp_regs<10>(C, si, sj, nr, nc, s, lane);
+}
+
+// Emits the assignment of the ORIGINAL problem (rows ascending, like scipy) through `put(k, row, col)`.
+template <typename Put>
+__device__ __forceinline__ void lsap_emit(bool transposed, int nr, int nc, const LsapSmem& s, int lane, Put put) {
   if (!transposed) {
-    for (int r = lane; r < nr; r += 32) { po[r] = static_cast<int64_t>(local) * nrows + r; to[r] = t0 + col4row[r]; }
+    for (int r = lane; r < nr; r += 32) put(r, r, s.col4row[r]);
   } else {
-    // working columns are the original rows (queries); compact the assigned ones in order
+    // working columns are the original rows; compact the assigned ones in order
     int written = 0;
     for (int base = 0; base < nc; base += 32) {
       const int j = base + lane;
-      const bool has = j < nc && row4col[j] != -1;
+      const bool has = j < nc && s.row4col[j] != -1;
       const unsigned m = __ballot_sync(0xffffffffu, has);
-      if (has) {
-        const int k = written + __popc(m & ((1u << lane) - 1));
-        po[k] = static_cast<int64_t>(local) * nrows + j;
-        to[k] = t0 + row4col[j];
-      }
+      if (has) put(written + __popc(m & ((1u << lane) - 1)), j, s.row4col[j]);
       written += __popc(m);
     }
   }
+}
+
+// One warp per (layer, problem).  mode 0: cost block + solve; 1: cost blocks only (into cost_ws); 2: solve from cost_ws.
+// Dynamic shared memory: solver state (lsap_smem_bytes) followed by the cost block in working orientation when it fits
+// (cost_smem_floats > 0); larger problems read the block from the global workspace.
+__global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int ms, int mb, int cost_smem_floats) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  const int lane = threadIdx.x;
+  const int P = a.B * a.problems_per_video;
+  const int layer = blockIdx.x / P, p = blockIdx.x - layer * P;
+  const int video = p / a.problems_per_video, local = p - video * a.problems_per_video;
+  const int nrows = a.rows_per_problem;
+  const int t0 = a.tgt_off[p], ncols = a.tgt_off[p + 1] - t0;
+  if (ncols <= 0 || nrows <= 0) return;
+  int32_t* status_acc = a.status + 1;
+
+  const LsapSmem s = lsap_carve(sm_raw, ms, mb);
+  float* Cs = reinterpret_cast<float*>(sm_raw + lsap_smem_bytes(ms, mb));
+  const bool cost_in_smem = nrows * ncols <= cost_smem_floats;
+  const bool transposed = ncols < nrows;          // scipy transposes tall problems
+  const int nr = transposed ? ncols : nrows;      // rows of the working problem
+  const int nc = transposed ? nrows : ncols;
+
+  const int m0 = a.match_off[p];
+  int64_t* po = a.pred_idx + static_cast<size_t>(layer) * a.K + m0;       // a.K: row pitch of the index arrays (>= match_off[P])
+  int64_t* to = a.tgt_idx + static_cast<size_t>(layer) * a.K + m0;
+  // indices that downstream kernels can always dereference (row r <-> column min(r, ncols - 1)): written whenever the
+  // problem has no solution, next to the status bit -- the criterion must never see uninitialised indices
+  auto safe_indices = [&]() {
+    for (int r = lane; r < nr; r += 32) {
+      po[r] = static_cast<int64_t>(local) * nrows + r;
+      to[r] = t0 + (r < ncols ? r : ncols - 1);
+    }
+  };
+
+  // ---- cost block
+  const size_t q0 = (static_cast<size_t>(layer) * a.B + video) * a.Q + static_cast<size_t>(local) * nrows;
+  float* Cg = a.cost_ws ? a.cost_ws + static_cast<size_t>(layer) * a.cost_off[P] + a.cost_off[p] : nullptr;   // nrows x ncols
+  bool bad = false;
+  if (a.mode != 2) {
+    // entries visited in working order (conflict-free shared-memory stores)
+    for (int e = lane; e < nr * nc; e += 32) {
+      const int i = e / nc, j = e - i * nc;
+      const int r = transposed ? j : i, c = transposed ? i : j;
+      const float2 lg = reinterpret_cast<const float2*>(a.logits)[q0 + r];
+      const float4 pb = reinterpret_cast<const float4*>(a.boxes)[q0 + r];
+      const float4 tb = reinterpret_cast<const float4*>(a.tgt_boxes)[t0 + c];
+      const Box pa{pb.x, pb.y, pb.z, pb.w}, ta{tb.x, tb.y, tb.z, tb.w};
+      const float cost = pair_cost(fg_prob(lg.x, lg.y), pa, ta, a.w_class, a.w_bbox, a.w_giou);
+      bad |= (cost != cost) || (cost == -CUDART_INF_F);
+      if (Cg) Cg[r * ncols + c] = cost;
+      if (cost_in_smem) Cs[e] = cost;
+    }
+    if (a.mode == 1) return;
+  } else {
+    for (int e = lane; e < nr * nc; e += 32) {
+      const int i = e / nc, j = e - i * nc;
+      const float cost = Cg[transposed ? j * ncols + i : e];
+      bad |= (cost != cost) || (cost == -CUDART_INF_F);
+      if (cost_in_smem) Cs[e] = cost;
+    }
+  }
+  if (__any_sync(0xffffffffu, bad)) {      // scipy: "matrix contains invalid numeric entries"
+    if (lane == 0) atomicOr(status_acc, 1);
+    safe_indices();
+    return;
+  }
+  __syncwarp();
+
+  // a block that does not fit in shared memory is read in place from the workspace (original orientation: a tall
+  // problem's working entry (i, j) is the block's entry (j, i))
+  const int rc = cost_in_smem ? lsap_dispatch(Cs, nc, 1, nr, nc, s, lane, a.solver == 1)
+                              : lsap_dispatch(Cg, transposed ? 1 : ncols, transposed ? ncols : 1, nr, nc, s, lane, a.solver == 1);
+  if (rc != 0) {                           // infeasible: every candidate +inf
+    if (lane == 0) atomicOr(status_acc, 2);
+    safe_indices();
+    return;
+  }
+  // ---- emit (query index within the video, global target index), query ascending
+  lsap_emit(transposed, nr, nc, s, lane,
+            [&](int k, int r, int c) { po[k] = static_cast<int64_t>(local) * nrows + r; to[k] = t0 + c; });
+}
+
+// After match_kernel on the same stream: (1) global -> video-local target indices.  localize 1 = PerFrameMatcher's quirk
+// (matcher.py:114-115): subtract the minimum matched global index of the video; 2 = HungarianMatcher (:158): columns are
+// local to the video's split, i.e. global minus the video's first target.  (2) publish the status word of this call and
+// clear the accumulator for the next one (status[0] = status[1]; status[1] = 0), so no host-side memset is needed and the
+// whole matcher can sit inside a captured CUDA graph.
+__global__ void __launch_bounds__(32) match_finalize_kernel(int64_t* tgt_idx, const int32_t* video_match_off,
+                                                            const int32_t* video_tgt_off, int32_t* status, int B, int K,
+                                                            int localize) {
+  const int layer = blockIdx.x / B, b = blockIdx.x - layer * B, lane = threadIdx.x;
+  if (blockIdx.x == 0 && lane == 0 && status) { status[0] = status[1]; status[1] = 0; }
+  if (!localize) return;
+  const int k0 = video_match_off[b], k1 = video_match_off[b + 1];
+  int64_t* t = tgt_idx + static_cast<size_t>(layer) * K;
+  long long mn = LLONG_MAX;
+  if (localize == 1) {
+    for (int k = k0 + lane; k < k1; k += 32) mn = min(mn, static_cast<long long>(t[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  } else {
+    mn = video_tgt_off[b];
+  }
+  for (int k = k0 + lane; k < k1; k += 32) t[k] -= mn;
+}
+
+static int match_smem(const MatchArgs& a, int* ms_out, int* mb_out, int* cost_floats_out, size_t* smem_out) {
+  const int max_small = a.rows_per_problem < a.max_cols ? a.rows_per_problem : a.max_cols;
+  const int max_big = a.rows_per_problem > a.max_cols ? a.rows_per_problem : a.max_cols;
+  const int ms = (max_small + 1) & ~1, mb = (max_big + 1) & ~1;     // keep the int arrays 8-byte aligned
+  const size_t smem_solver = lsap_smem_bytes(ms, mb);
+  if (smem_solver > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "match: problem too large for one warp's shared memory");
+  // cost block in shared memory when it fits next to the solver state (<= 96 KB keeps >= 2 problems resident per SM)
+  const size_t cost_bytes = static_cast<size_t>(a.rows_per_problem) * static_cast<size_t>(a.max_cols) * sizeof(float);
+  const bool fits = cost_bytes <= 96 * 1024 && smem_solver + cost_bytes <= 200 * 1024;
+  if (!fits && a.cost_ws == nullptr)
+    return svol_fail(SVOL_ERR_NULL, "match: problems this large need the global cost workspace (cost_ws)");
+  *ms_out = ms; *mb_out = mb;
+  *cost_floats_out = fits ? a.rows_per_problem * a.max_cols : 0;
+  *smem_out = smem_solver + (fits ? cost_bytes : 0);
+  return SVOL_OK;
 }
 
 int launch_match(const MatchArgs& a, cudaStream_t stream) {
   if (a.NL <= 0 || a.B <= 0 || a.Q <= 0 || a.problems_per_video <= 0 || a.rows_per_problem <= 0 ||
       a.problems_per_video * a.rows_per_problem != a.Q)      // matcher.py:56
     return svol_fail(SVOL_ERR_SHAPE, "match: Q must equal problems_per_video * rows_per_problem");
-  const int max_small = a.rows_per_problem < a.max_cols ? a.rows_per_problem : a.max_cols;
-  const int max_big = a.rows_per_problem > a.max_cols ? a.rows_per_problem : a.max_cols;
-  const int ms = (max_small + 1) & ~1, mb = (max_big + 1) & ~1;     // keep the int arrays 8-byte aligned
-  const size_t smem_solver = (sizeof(double) * (ms + 2 * mb) + sizeof(int) * (3 * mb + ms) + (ms + mb) + 15) & ~static_cast<size_t>(15);
-  if (smem_solver > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "match: problem too large for one warp's shared memory");
-  // cost block in shared memory when it fits in ~64 KB per warp (keeps >= 3 problems resident per SM)
-  const size_t cost_bytes = static_cast<size_t>(a.rows_per_problem) * static_cast<size_t>(a.max_cols) * sizeof(float);
-  const int cost_smem_floats = cost_bytes <= 64 * 1024 ? a.rows_per_problem * a.max_cols : 0;
-  const size_t smem = smem_solver + static_cast<size_t>(cost_smem_floats) * sizeof(float);
+  if (a.mode < 0 || a.mode > 2 || a.solver < 0 || a.solver > 1 || a.localize < 0 || a.localize > 2)
+    return svol_fail(SVOL_ERR_SHAPE, "match: mode in 0..2, solver in 0..1, localize in 0..2");
+  if (a.K <= 0) return svol_fail(SVOL_ERR_SHAPE, "match: K (row pitch of pred_idx / tgt_idx, >= match_off[P]) must be > 0");
+  if (a.mode != 0 && a.cost_ws == nullptr) return svol_fail(SVOL_ERR_NULL, "match: modes 1 and 2 need cost_ws");
+  if (a.localize && (a.video_match_off == nullptr || (a.localize == 2 && a.video_tgt_off == nullptr)))
+    return svol_fail(SVOL_ERR_NULL, "match: localize needs video_match_off (and video_tgt_off for mode 2)");
+  int ms, mb, cost_floats;
+  size_t smem;
+  if (int rc = match_smem(a, &ms, &mb, &cost_floats, &smem)) return rc;
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -240,26 +447,81 @@ int launch_match(const MatchArgs& a, cudaStream_t stream) {
     configured = smem;
   }
   const int P = a.B * a.problems_per_video;
-  match_kernel<<<a.NL * P, 32, smem, stream>>>(a, ms, mb, cost_smem_floats);
-  return svol_check_launch("match");
+  match_kernel<<<a.NL * P, 32, smem, stream>>>(a, ms, mb, cost_floats);
+  if (int rc = svol_check_launch("match")) return rc;
+  if (a.mode == 1) return SVOL_OK;
+  match_finalize_kernel<<<a.NL * a.B, 32, 0, stream>>>(a.tgt_idx, a.video_match_off, a.video_tgt_off, a.status, a.B,
+                                                        a.K, a.localize);
+  return svol_check_launch("match_finalize");
 }
 
-// matcher.py:114-115: tgt_idx -= min(tgt_idx) per video (and per layer)
-__global__ void __launch_bounds__(32) match_localize_kernel(int64_t* tgt_idx, const int32_t* video_match_off, int B, int K) {
-  const int layer = blockIdx.x / B, b = blockIdx.x - layer * B, lane = threadIdx.x;
-  const int k0 = video_match_off[b], k1 = video_match_off[b + 1];
-  int64_t* t = tgt_idx + static_cast<size_t>(layer) * K;
-  long long mn = LLONG_MAX;
-  for (int k = k0 + lane; k < k1; k += 32) mn = min(mn, static_cast<long long>(t[k]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-  for (int k = k0 + lane; k < k1; k += 32) t[k] -= mn;
-}
-
+// matcher.py:114-115 as a stand-alone call (kept for callers that ran svol_match with localize = 0)
 int launch_match_localize(int64_t* tgt_idx, const int32_t* video_match_off, int NL, int B, int K, cudaStream_t stream) {
   if (NL <= 0 || B <= 0) return svol_fail(SVOL_ERR_SHAPE, "match_localize: bad sizes");
-  match_localize_kernel<<<NL * B, 32, 0, stream>>>(tgt_idx, video_match_off, B, K);
+  match_finalize_kernel<<<NL * B, 32, 0, stream>>>(tgt_idx, video_match_off, nullptr, nullptr, B, K, 1);
   return svol_check_launch("match_localize");
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stand-alone batched LSAP on caller-supplied fp32 cost matrices: scipy.optimize.linear_sum_assignment semantics
+// (matcher.py:93,158), one warp per problem, the same solver code as match_kernel.
+__global__ void __launch_bounds__(32) lsap_kernel(const float* __restrict__ cost, const int64_t* __restrict__ cost_off,
+                                                  const int32_t* __restrict__ shape, int64_t* __restrict__ rows_out,
+                                                  int64_t* __restrict__ cols_out, const int64_t* __restrict__ out_off,
+                                                  int32_t* __restrict__ status, int ms, int mb, int cost_smem_floats,
+                                                  int solver) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  const int lane = threadIdx.x, p = blockIdx.x;
+  const int nrows = shape[2 * p], ncols = shape[2 * p + 1];
+  if (lane == 0) status[p] = 0;
+  if (nrows <= 0 || ncols <= 0) return;
+  const LsapSmem s = lsap_carve(sm_raw, ms, mb);
+  float* Cs = reinterpret_cast<float*>(sm_raw + lsap_smem_bytes(ms, mb));
+  const bool transposed = ncols < nrows;
+  const int nr = transposed ? ncols : nrows, nc = transposed ? nrows : ncols;
+  const float* Cg = cost + cost_off[p];
+  bool bad = false;
+  for (int e = lane; e < nr * nc; e += 32) {
+    const int i = e / nc, j = e - i * nc;
+    const float c = Cg[transposed ? j * ncols + i : e];
+    bad |= (c != c) || (c == -CUDART_INF_F);
+    Cs[e] = c;
+  }
+  int64_t* ro = rows_out + out_off[p];
+  int64_t* co = cols_out + out_off[p];
+  if (__any_sync(0xffffffffu, bad)) {
+    if (lane == 0) status[p] = 1;
+    return;
+  }
+  __syncwarp();
+  (void)cost_smem_floats;
+  const int rc = lsap_dispatch(Cs, nc, 1, nr, nc, s, lane, solver == 1);
+  if (rc != 0) {
+    if (lane == 0) status[p] = 2;
+    return;
+  }
+  lsap_emit(transposed, nr, nc, s, lane, [&](int k, int r, int c) { ro[k] = r; co[k] = c; });
+}
+
+int launch_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int n_problems, int max_rows,
+                    int max_cols, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off, int32_t* status, int solver,
+                    cudaStream_t stream) {
+  if (n_problems <= 0 || max_rows <= 0 || max_cols <= 0 || solver < 0 || solver > 1)
+    return svol_fail(SVOL_ERR_SHAPE, "lsap: n_problems, max_rows, max_cols > 0; solver in 0..1");
+  const int small = max_rows < max_cols ? max_rows : max_cols, big = max_rows > max_cols ? max_rows : max_cols;
+  const int ms = (small + 1) & ~1, mb = (big + 1) & ~1;
+  const size_t cost_bytes = static_cast<size_t>(max_rows) * max_cols * sizeof(float);
+  const size_t smem = lsap_smem_bytes(ms, mb) + cost_bytes;
+  if (smem > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "lsap: max_rows * max_cols * 4 bytes must fit in shared memory");
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return svol_fail_cuda(e, "lsap: cudaFuncSetAttribute");
+    configured = smem;
+  }
+  lsap_kernel<<<n_problems, 32, smem, stream>>>(cost, cost_off, shape, rows_out, cols_out, out_off, status, ms, mb,
+                                                max_rows * max_cols, solver);
+  return svol_check_launch("lsap");
 }
 
 }  // namespace svol

@@ -828,4 +828,57 @@ int launch_adamw(float* p, const float* g, float* m, float* v, long long n, floa
   return svol_check_launch("adamw");
 }
 
+// Same update over a flat buffer that is a concatenation of parameter SEGMENTS (4-element aligned): segment s covers
+// [seg_end[s-1], seg_end[s]) and belongs to hyper-parameter group seg_group[s], or is skipped when seg_group[s] < 0 --
+// torch.optim.AdamW leaves a parameter whose .grad is None untouched (no weight decay, no moment update).
+struct AdamwGroups { svol_adamw_group g[SVOL_ADAMW_MAX_GROUPS]; float bc1[SVOL_ADAMW_MAX_GROUPS]; float bc2_sqrt[SVOL_ADAMW_MAX_GROUPS]; };
+
+__global__ void __launch_bounds__(256) adamw_segments_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                             float* __restrict__ m, float* __restrict__ v, long long n4,
+                                                             const long long* __restrict__ seg_end,
+                                                             const int* __restrict__ seg_group, int n_seg, AdamwGroups G,
+                                                             float grad_scale) {
+  const long long i4 = blockIdx.x * 256LL + threadIdx.x;
+  if (i4 >= n4) return;
+  const long long i = i4 * 4;
+  int lo = 0, hi = n_seg - 1;                       // first segment with seg_end > i
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(seg_end + mid) > i) hi = mid; else lo = mid + 1;
+  }
+  const int gi = __ldg(seg_group + lo);
+  if (gi < 0) return;
+  const svol_adamw_group h = G.g[gi];
+  const float bc1 = G.bc1[gi], bc2s = G.bc2_sqrt[gi];
+  float4 pv = reinterpret_cast<float4*>(p)[i4], mv = reinterpret_cast<float4*>(m)[i4], vv = reinterpret_cast<float4*>(v)[i4];
+  const float4 gv = reinterpret_cast<const float4*>(g)[i4];
+  auto upd = [&](float& pi, float& mi, float& vi, float gr) {
+    gr *= grad_scale;
+    pi *= 1.0f - h.lr * h.weight_decay;
+    mi = h.beta1 * mi + (1.0f - h.beta1) * gr;
+    vi = h.beta2 * vi + (1.0f - h.beta2) * gr * gr;
+    pi -= (h.lr / bc1) * mi / (sqrtf(vi) / bc2s + h.eps);
+  };
+  upd(pv.x, mv.x, vv.x, gv.x); upd(pv.y, mv.y, vv.y, gv.y); upd(pv.z, mv.z, vv.z, gv.z); upd(pv.w, mv.w, vv.w, gv.w);
+  reinterpret_cast<float4*>(p)[i4] = pv; reinterpret_cast<float4*>(m)[i4] = mv; reinterpret_cast<float4*>(v)[i4] = vv;
+}
+
+int launch_adamw_segments(float* p, const float* g, float* m, float* v, long long n, const long long* seg_end,
+                          const int* seg_group, int n_seg, const svol_adamw_group* groups, int n_groups, float grad_scale,
+                          cudaStream_t stream) {
+  if (n <= 0 || (n & 3) || n_seg <= 0 || n_groups <= 0 || n_groups > SVOL_ADAMW_MAX_GROUPS)
+    return svol_fail(SVOL_ERR_SHAPE, "adamw_segments: n > 0 and a multiple of 4, 1..8 groups, >= 1 segment");
+  AdamwGroups G;
+  for (int i = 0; i < n_groups; ++i) {
+    if (groups[i].step <= 0) return svol_fail(SVOL_ERR_SHAPE, "adamw_segments: group step >= 1");
+    G.g[i] = groups[i];
+    G.bc1[i] = 1.0f - powf(groups[i].beta1, static_cast<float>(groups[i].step));
+    G.bc2_sqrt[i] = sqrtf(1.0f - powf(groups[i].beta2, static_cast<float>(groups[i].step)));
+  }
+  const long long n4 = n / 4;
+  adamw_segments_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, stream>>>(p, g, m, v, n4, seg_end, seg_group, n_seg, G,
+                                                                                      grad_scale);
+  return svol_check_launch("adamw_segments");
+}
+
 }  // namespace svol

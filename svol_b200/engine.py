@@ -151,6 +151,7 @@ class HeadEngine:
         self.plain = os.environ.get("SVOL_B200_PLAIN", "0") == "1"   # debug: SIMT kernels instead of tcgen05
         self._w: Dict[str, torch.Tensor] = {}
         self._wstate = None
+        self.weights_generation = 0        # bumped by every repack: consumers of derived copies (TrainEngine's W^T) compare it
         self._packer = WeightPacker()
         self._plans: Dict[Tuple[int, int, int, int], _Plan] = {}
         self._side = None                  # (query, input) capture streams: the forked branches of the forward graph
@@ -227,6 +228,7 @@ class HeadEngine:
         if pk.end():
             self._plans.clear()                 # a packed buffer moved: recorded plans hold stale addresses
         self._w = pk.tensors
+        self.weights_generation += 1
 
     def _weights(self) -> Dict[str, torch.Tensor]:
         st = self._param_state()
@@ -292,6 +294,7 @@ class HeadEngine:
         h1, h2 = buf("h1", (NL * MQ, d), bf), buf("h2", (NL * MQ, d), bf)
         logits = buf("logits", (NL, B, Q, 2), f32)
         boxes = buf("boxes", (NL, B, Q, 4), f32)
+        logits._svol_static = boxes._svol_static = True       # plan-owned outputs: stable addresses (criterion graph replay)
 
         P = _lib.ptr
         gemm_fn = lib.svol_gemm_bf16_plain if self.plain else lib.svol_gemm_bf16

@@ -17,36 +17,48 @@ from .. import _lib
 from .targets import FlatTargets, TargetsCache
 
 
+def fill_match_args(a, logits, boxes, src, NL, B, Q, K_pitch, ppv, rows, max_cols, per_frame, w_class, w_bbox, w_giou,
+                    cost_ws, pred_idx, tgt_idx, status, mode=0, solver=0):
+    """``src``: anything with tgt_boxes / tgt_off / match_off / cost_off / video_match_off / video_tgt_off tensors
+    (a FlatTargets, or the static views of a criterion workspace)."""
+    g = (lambda k: src[k]) if isinstance(src, dict) else (lambda k: getattr(src, k))
+    a.logits, a.boxes, a.tgt_boxes = logits.data_ptr(), boxes.data_ptr(), g("tgt_boxes").data_ptr()
+    a.tgt_off, a.match_off, a.cost_off = g("tgt_off").data_ptr(), g("match_off").data_ptr(), g("cost_off").data_ptr()
+    a.cost_ws = cost_ws.data_ptr() if cost_ws is not None else None
+    a.pred_idx, a.tgt_idx, a.status = pred_idx.data_ptr(), tgt_idx.data_ptr(), status.data_ptr()
+    a.NL, a.B, a.Q = NL, B, Q
+    a.problems_per_video, a.rows_per_problem, a.max_cols = ppv, rows, max_cols
+    a.w_class, a.w_bbox, a.w_giou = float(w_class), float(w_bbox), float(w_giou)
+    a.K = K_pitch
+    a.video_match_off, a.video_tgt_off = g("video_match_off").data_ptr(), g("video_tgt_off").data_ptr()
+    # global -> video-local target indices inside the call's finalize kernel.  PerFrameMatcher subtracts the minimum
+    # matched global index (matcher.py:114-115); HungarianMatcher's columns are local to the video's split (:158).
+    a.mode, a.solver, a.localize = mode, solver, (1 if per_frame else 2)
+    return a
+
+
+COST_SMEM_LIMIT = 96 * 1024          # matcher.cu: larger cost blocks are solved from the global workspace
+
+
 def run_match(logits: torch.Tensor, boxes: torch.Tensor, flat: FlatTargets, w_class: float, w_bbox: float,
-              w_giou: float):
+              w_giou: float, export_cost: bool = False, solver: int = 0, mode: int = 0, cost_ws: torch.Tensor = None):
     """logits [NL,B,Q,2], boxes [NL,B,Q,4] fp32 contiguous on the GPU.  Returns device tensors
-    (pred_idx [NL,K] i64, tgt_idx [NL,K] i64 video-local, status [1] i32, cost_ws)."""
+    (pred_idx [NL,K] i64, tgt_idx [NL,K] i64 video-local, status [2] i32 (status[0] = this call's), cost_ws or None).
+    Allocating convenience path (stand-alone matcher calls, tests); the criterion keeps a static workspace (loss.py)."""
     _lib.require_device()
     lib = _lib.get_lib()
     NL, B, Q = logits.shape[:3]
     dev = logits.device
-    cost_ws = torch.empty((NL, max(flat.cost_total, 1)), device=dev, dtype=torch.float32)
+    need_ws = export_cost or mode != 0 or flat.rows_per_problem * flat.max_cols * 4 > COST_SMEM_LIMIT
+    if cost_ws is None and need_ws:
+        cost_ws = torch.empty((NL, max(flat.cost_total, 1)), device=dev, dtype=torch.float32)
     pred_idx = torch.empty((NL, flat.K), device=dev, dtype=torch.int64)
     tgt_idx = torch.empty((NL, flat.K), device=dev, dtype=torch.int64)
-    status = torch.zeros(1, device=dev, dtype=torch.int32)
-    a = _lib.MatchArgs()
-    a.logits, a.boxes, a.tgt_boxes = logits.data_ptr(), boxes.data_ptr(), flat.tgt_boxes.data_ptr()
-    a.tgt_off, a.match_off, a.cost_off = flat.tgt_off.data_ptr(), flat.match_off.data_ptr(), flat.cost_off.data_ptr()
-    a.cost_ws, a.pred_idx, a.tgt_idx, a.status = cost_ws.data_ptr(), pred_idx.data_ptr(), tgt_idx.data_ptr(), status.data_ptr()
-    a.NL, a.B, a.Q = NL, B, Q
-    a.problems_per_video, a.rows_per_problem, a.max_cols = flat.problems_per_video, flat.rows_per_problem, flat.max_cols
-    a.w_class, a.w_bbox, a.w_giou = float(w_class), float(w_bbox), float(w_giou)
-    stream = _lib.stream_ptr()
-    _lib.check(lib.svol_match(C.byref(a), stream), "match")
-    # global -> video-local target indices.  PerFrameMatcher subtracts the minimum matched global index
-    # (matcher.py:114-115); HungarianMatcher's columns are already local to the video's split (:158),
-    # which is the same subtraction because every column of a Q x n_v problem with n_v <= Q is matched --
-    # and when n_v > Q the reference returns split-local columns, i.e. global minus the video offset.
-    if flat.per_frame:
-        _lib.check(lib.svol_match_localize(tgt_idx.data_ptr(), flat.video_match_off.data_ptr(), NL, B, flat.K, stream),
-                   "match_localize")
-    else:
-        tgt_idx -= flat.video_tgt_off.to(torch.int64)[flat.match_video.long()][None]
+    status = torch.zeros(2, device=dev, dtype=torch.int32)
+    a = fill_match_args(_lib.MatchArgs(), logits, boxes, flat, NL, B, Q, flat.K, flat.problems_per_video,
+                        flat.rows_per_problem, flat.max_cols, flat.per_frame, w_class, w_bbox, w_giou, cost_ws, pred_idx,
+                        tgt_idx, status, mode, solver)
+    _lib.check(lib.svol_match(C.byref(a), _lib.stream_ptr()), "match")
     return pred_idx, tgt_idx, status, cost_ws
 
 
@@ -57,7 +69,7 @@ def _to_index_list(pred_idx: torch.Tensor, tgt_idx: torch.Tensor, flat: FlatTarg
 
 
 def _check_status(status: torch.Tensor) -> None:
-    s = int(status.item())
+    s = int(status[0].item())
     if s & 1:
         raise ValueError("matrix contains invalid numeric entries")      # scipy's message for NaN / -inf costs
     if s & 2:

@@ -41,6 +41,11 @@ class _HeadTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, src_sketch, src_sketch_mask, src_video, src_video_mask, *params):
+        if src_video.requires_grad or src_sketch.requires_grad:
+            # train.py:72 optimises backbone + head; this node returns no gradient for the features, so a backbone behind
+            # them would silently stop training.  Fail loudly instead (detach the features to train the head alone).
+            raise NotImplementedError("svol_b200's head backward does not produce d/d(src_video), d/d(src_sketch): pass "
+                                      "detached features (frozen backbone / precomputed features)")
         eng = module.train_engine
         logits, boxes = eng.forward(src_sketch, src_sketch_mask, src_video, src_video_mask)
         ctx.module, ctx.n_params, ctx.token = module, len(params), eng.forward_token
@@ -53,7 +58,7 @@ class _HeadTrainFn(torch.autograd.Function):
         eng.backward(g_logits.contiguous().float(), g_boxes.contiguous().float(), token=ctx.token)
         if not eng.publish_grads:        # fused-optimizer loop: gradients stay in eng.grad_flat (FusedAdamW.step(from_engine=True))
             return (None,) * (5 + ctx.n_params)
-        unused = {id(p) for p in module.class_head.parameters()}          # never reached by forward (svanet.py:125)
+        unused = {id(p) for p in module.params_without_grad()}            # None in the reference's autograd too
         grads = [eng.grad_of(p) if (p.requires_grad and id(p) not in unused) else None for p in module.parameters()]
         return (None, None, None, None, None, *grads)
 
@@ -92,6 +97,15 @@ class SVANet(nn.Module):
         self.input_dropout = input_dropout
         self._engine = HeadEngine(self, use_graph=use_graph)
         self._train_engine = None
+
+    def params_without_grad(self):
+        """Parameters the forward never reaches -- ``.grad`` stays None in the reference's autograd as well:
+        ``class_head`` (svanet.py:125 uses class_embed) and the output projection of the sketch->video attention, whose
+        attended values are discarded (cross_modal_transformer.py:124: only the attention weights are used)."""
+        out = list(self.class_head.parameters())
+        for layer in self.transformer.layers:
+            out += list(layer.sketch_video_cross_attn.out_proj.parameters())
+        return out
 
     @property
     def engine(self) -> HeadEngine:

@@ -33,6 +33,10 @@ class FlatTargets:
     match_video: torch.Tensor    # [K] i32
     h_video_match_off: np.ndarray
     per_frame: bool
+    meta: torch.Tensor = None    # [4] i32 on the device: K, S, max_cols, P
+    packed: torch.Tensor = None  # the whole packed buffer (uint8, device); [0, n_static) = everything but match_video
+    n_fixed: int = 0             # bytes in front of the boxes: a function of (P, B) only
+    n_static: int = 0            # n_fixed + 16 * S
 
 
 def _walk(targets: Sequence[dict]):
@@ -67,8 +71,10 @@ class PackedTargets(list):
 
 
 def _pack_host(targets: Sequence[dict], per_frame: bool, num_frames: int, num_queries: int, q_per_frame: int):
-    """Nested targets -> (packed uint8 numpy buffer, meta).  Layout: [cost_off i64 | boxes f32 | tgt_off, match_off,
-    video_tgt_off, video_match_off, match_video i32], sections 16-byte aligned."""
+    """Nested targets -> (packed uint8 numpy buffer, meta).  Layout: [cost_off i64 | tgt_off, match_off, video_tgt_off,
+    video_match_off, (K, S, max_cols, P) i32 | boxes f32 | match_video i32], sections 16-byte aligned.  Everything in
+    front of the boxes has a size that depends on (P, B) only, so a consumer with a static device copy of this buffer
+    (the criterion's captured launch sequence, loss.py) finds every array at a fixed address for every batch."""
     boxes, per_video, per_frame_counts = _walk(targets)
     B = len(targets)
     if per_frame:
@@ -90,16 +96,20 @@ def _pack_host(targets: Sequence[dict], per_frame: bool, num_frames: int, num_qu
     video_match_off = match_off[::ppv].copy()
     K = int(match_off[-1])
     match_video = np.repeat(np.arange(B, dtype=np.int32), np.diff(video_match_off))
-    ints = np.concatenate([tgt_off, match_off, video_tgt_off, video_match_off, match_video]).astype(np.int32)
     S = int(boxes.shape[0])
-    n_cost, n_box, n_int = ((P + 1) * 8 + 15) // 16 * 16, S * 16, ints.shape[0] * 4     # sections stay 16-byte aligned
-    total = n_cost + n_box + n_int
+    max_cols = int(cols.max())
+    ints = np.concatenate([tgt_off, match_off, video_tgt_off, video_match_off, [K, S, max_cols, P]]).astype(np.int32)
+    n_cost = ((P + 1) * 8 + 15) // 16 * 16                                           # sections stay 16-byte aligned
+    n_fixed = n_cost + (ints.shape[0] * 4 + 15) // 16 * 16
+    n_box = S * 16
+    total = n_fixed + n_box + K * 4
     hb = np.zeros(total, np.uint8)
     hb[:(P + 1) * 8].view(np.int64)[:] = cost_off
-    hb[n_cost:n_cost + n_box].view(np.float32)[:] = boxes.reshape(-1)
-    hb[n_cost + n_box:total].view(np.int32)[:] = ints
-    meta = dict(B=B, S=S, K=K, P=P, ppv=ppv, rows=rows, max_cols=int(cols.max()), cost_total=int(cost_off[-1]),
-                n_cost=n_cost, n_box=n_box, total=total, video_match_off=video_match_off, per_frame=per_frame,
+    hb[n_cost:n_cost + ints.shape[0] * 4].view(np.int32)[:] = ints
+    hb[n_fixed:n_fixed + n_box].view(np.float32)[:] = boxes.reshape(-1)
+    hb[n_fixed + n_box:total].view(np.int32)[:] = match_video
+    meta = dict(B=B, S=S, K=K, P=P, ppv=ppv, rows=rows, max_cols=max_cols, cost_total=int(cost_off[-1]),
+                n_cost=n_cost, n_fixed=n_fixed, n_box=n_box, total=total, video_match_off=video_match_off, per_frame=per_frame,
                 key=(per_frame, num_frames, num_queries, q_per_frame))
     return hb, meta
 
@@ -134,7 +144,7 @@ def flatten_targets(targets: Sequence[dict], device, per_frame: bool, num_frames
     else:
         hb, meta = _pack_host(targets, per_frame, num_frames, num_queries, q_per_frame)
     B, S, K, P, total = meta["B"], meta["S"], meta["K"], meta["P"], meta["total"]
-    n_cost, n_box = meta["n_cost"], meta["n_box"]
+    n_cost, n_fixed, n_box = meta["n_cost"], meta["n_fixed"], meta["n_box"]
     # one packed host buffer -> one H2D copy; the pinned staging buffers are recycled (ring + event) because
     # cudaHostAlloc per batch costs more than the copy itself
     if isinstance(targets, PackedTargets) and targets.host.is_pinned():
@@ -148,15 +158,29 @@ def flatten_targets(targets: Sequence[dict], device, per_frame: bool, num_frames
     if done is not None:
         done.record()
     d_cost = dbuf[:(P + 1) * 8].view(torch.int64)
-    d_box = dbuf[n_cost:n_cost + n_box].view(torch.float32).view(S, 4)
-    d_int = dbuf[n_cost + n_box:].view(torch.int32)
+    d_int = dbuf[n_cost:n_fixed].view(torch.int32)
+    d_box = dbuf[n_fixed:n_fixed + n_box].view(torch.float32).view(S, 4)
     n1, n2, n3, n4 = P + 1, 2 * (P + 1), 2 * (P + 1) + B + 1, 2 * (P + 1) + 2 * (B + 1)
     return FlatTargets(
         B=B, S=S, K=K, P=P, problems_per_video=meta["ppv"], rows_per_problem=meta["rows"],
         max_cols=meta["max_cols"], cost_total=meta["cost_total"],
         tgt_boxes=d_box, tgt_off=d_int[:n1], match_off=d_int[n1:n2],
         cost_off=d_cost, video_tgt_off=d_int[n2:n3], video_match_off=d_int[n3:n4],
-        match_video=d_int[n4:], h_video_match_off=meta["video_match_off"], per_frame=meta["per_frame"])
+        match_video=dbuf[n_fixed + n_box:].view(torch.int32), h_video_match_off=meta["video_match_off"],
+        per_frame=meta["per_frame"], meta=d_int[n4:n4 + 4], packed=dbuf, n_fixed=n_fixed, n_static=n_fixed + n_box)
+
+
+def static_views(buf: torch.Tensor, P: int, B: int):
+    """The arrays of a packed target buffer that sit at addresses fixed by (P, B): a static device copy ``buf`` (uint8,
+    at least FlatTargets.n_static bytes) keeps them valid for every batch copied into it."""
+    n_cost = ((P + 1) * 8 + 15) // 16 * 16
+    n_int = 2 * (P + 1) + 2 * (B + 1) + 4
+    n_fixed = n_cost + (n_int * 4 + 15) // 16 * 16
+    ints = buf[n_cost:n_fixed].view(torch.int32)
+    n1, n2, n3, n4 = P + 1, 2 * (P + 1), 2 * (P + 1) + B + 1, 2 * (P + 1) + 2 * (B + 1)
+    return dict(cost_off=buf[:(P + 1) * 8].view(torch.int64), tgt_off=ints[:n1], match_off=ints[n1:n2],
+                video_tgt_off=ints[n2:n3], video_match_off=ints[n3:n4], meta=ints[n4:n4 + 4],
+                tgt_boxes=buf[n_fixed:], n_fixed=n_fixed)
 
 
 _STAGING = {"bufs": [], "next": 0}

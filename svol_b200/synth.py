@@ -94,14 +94,17 @@ def _linear_default(rng, out_f, in_f):
     return _uniform(rng, (out_f, in_f), b), _uniform(rng, (out_f,), b)
 
 
-def random_state_dict(cfg: HeadConfig, seed: int = 0, perturb: bool = True) -> Dict[str, np.ndarray]:
+def random_state_dict(cfg: HeadConfig, seed: int = 0, perturb: bool = True, box_spread: float = 0.0
+                      ) -> Dict[str, np.ndarray]:
     """Random weights under the reference's state_dict key names and shapes.
 
     Distributions mirror the reference's initialisers (xavier_uniform on the transformer
     matrices, cross_modal_transformer.py:22-25; torch defaults elsewhere).  With
     ``perturb`` the LayerNorm affine parameters and the attention biases, which the
     reference initialises to exactly 1/0, are jittered so that a kernel that drops one
-    of them fails parity instead of passing by accident.
+    of them fails parity instead of passing by accident.  ``box_spread`` > 0 scales the box head (every layer of
+    ``bbox_embed``, after all random draws, so the other tensors of a seed are unchanged) until the sigmoid boxes
+    cover most of (0, 1): at the default initialisation every box lies within 0.03 of 0.5.
     """
     rng = np.random.RandomState(1000 + seed)
     d, ff = cfg.hidden_dim, cfg.dim_feedforward
@@ -147,6 +150,9 @@ def random_state_dict(cfg: HeadConfig, seed: int = 0, perturb: bool = True) -> D
             sd[f"{p}.{m}.fc1.bias"] = _uniform(rng, (ff,), 1.0 / math.sqrt(d))
             sd[f"{p}.{m}.fc2.weight"] = _xavier(rng, (d, ff))
             sd[f"{p}.{m}.fc2.bias"] = _uniform(rng, (d,), 1.0 / math.sqrt(ff))
+    if box_spread > 0:
+        for i in range(3):
+            sd[f"bbox_embed.layers.{i}.weight"] = sd[f"bbox_embed.layers.{i}.weight"] * np.float32(1.0 + 1.6 * box_spread)
     return sd
 
 

@@ -86,7 +86,10 @@ class TrainEngine:
     def _pack_transposed(self):
         """bf16 W^T operands of the dgrad GEMMs (unscaled q rows), refreshed with the forward's packed weights."""
         w = self.head._weights()
-        st = self.head._wstate
+        # An explicit generation counter, not the (data_ptr, _version) tuple: FusedAdamW updates the flat parameter buffer
+        # through a raw pointer, which changes neither, and only resets the head engine's state -- the forward weights
+        # were then repacked while these transposed copies silently kept the initial values (round-1 ADVICE, high).
+        st = self.head.weights_generation
         if st == self._wt_state and self._wt:
             return w
         m = self.module

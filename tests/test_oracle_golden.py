@@ -163,6 +163,41 @@ def test_torch_port_head_matches_reference(golden_dir, case, cfgname, padded):
     assert np.abs(boxes - g["boxes_f32"]).max() < 2e-5
 
 
+@pytest.mark.parametrize("case,cfgname,spread", [("C2n4_b4", "C2n4", 0.0), ("C2_b4_spread", "C2", 1.0), ("C1b_spread", "C1b", 1.0),
+                                                 ("C4_b1", "C4", 0.0)])
+def test_torch_port_head_matches_reference_full_size(golden_dir, case, cfgname, spread):
+    """Round-2 goldens (tests/golden/make_golden_r2.py: four layers, the spread box head, the long clip with a masked
+    tail): the ATen restatement against the reference's fp64 outputs, and -- where the golden carries a matching record
+    -- its PerFrameMatcher against the reference's indices on those outputs."""
+    import torch
+    from oracle import torch_port as tp
+    g = _load(golden_dir, "head_" + case)
+    cfg = C[cfgname]
+    batch, seed = int(g["batch"]), int(g["seed"])
+    sd = tp.state_dict_to_torch(synth.random_state_dict(cfg, seed, box_spread=spread))
+    inp = synth.make_inputs(cfg, batch, seed, padded=bool(g["padded"]))
+    tail = int(g["mask_tail_frames"])
+    if tail:
+        inp["src_video_mask"][-1, -tail * cfg.tokens_per_frame:] = 0
+        inp["frame_mask"][-1, -tail:] = 0
+    t = lambda k: torch.from_numpy(inp[k])
+    out = tp.svanet_forward(sd, t("src_sketch"), t("src_sketch_mask"), t("src_video"), t("src_video_mask"), nheads=cfg.nheads)
+    logits = torch.stack([a["pred_logits"] for a in out["aux_outputs"]] + [out["pred_logits"]])
+    boxes = torch.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]])
+    assert np.abs(logits.numpy() - g["logits_f64"]).max() < 5e-5
+    assert np.abs(boxes.numpy() - g["boxes_f64"]).max() < 5e-5
+    if "frame_gap" in g.files:
+        targets = synth.make_targets(cfg, batch, seed, frame_mask=inp["frame_mask"])
+        ref_l, ref_b = torch.from_numpy(g["logits_f32"]), torch.from_numpy(g["boxes_f32"])
+        for li in range(cfg.num_layers):
+            idx = tp.per_frame_matcher(ref_l[li], ref_b[li], targets, cfg.num_frames, cfg.num_queries_per_frame,
+                                       cfg.set_cost_class, cfg.set_cost_bbox, cfg.set_cost_giou)
+            assert np.array_equal(torch.cat([p for p, _ in idx]).numpy(), g[f"pred_idx_{li}"])
+            assert np.array_equal(torch.cat([t for _, t in idx]).numpy(), g[f"tgt_idx_{li}"])
+        gaps = g["frame_gap"]
+        assert np.isfinite(gaps).sum() > 0 and (gaps[np.isfinite(gaps)] >= 0).all()
+
+
 @pytest.mark.parametrize("case,cfg,mpf", [("tiny", C["tiny"], 2), ("C2_b4", C["C2"], 2),
                                           ("C2_video", replace(C["C2"], matcher="video_matcher"), 2)])
 def test_torch_port_criterion_matches_reference(golden_dir, case, cfg, mpf):

@@ -431,6 +431,114 @@ def test_training_step_end_to_end():
     assert float(total) < first, f"loss did not decrease: {first} -> {float(total)}"
 
 
+def test_gradients_after_fused_adamw_steps_use_the_updated_weights():
+    """Round-1 ADVICE (high): FusedAdamW updates the flat parameter buffer through a raw pointer, so neither data_ptr nor
+    _version of a parameter changes -- the transposed bf16 weight copies of the dgrad GEMMs must still be refreshed.
+    After N large-lr steps the gradients are compared with the oracle's autograd on the UPDATED state_dict; with stale
+    W^T operands every activation gradient (and so every weight gradient upstream of the heads) would be wrong."""
+    from oracle import torch_port as tp
+    from svol_b200 import synth
+    from svol_b200.optim import FusedAdamW
+    cfg = replace(synth.CONFIGS["C1b"], input_dropout=0.0)
+    batch, seed = 2, 4
+    model, _ = _build(cfg, seed)
+    model.train()
+    inp = synth.make_inputs(cfg, batch, seed, padded=True)
+    t = lambda k: torch.from_numpy(inp[k]).to(DEV)
+    gl, gb = synth.make_upstream_grads(cfg, batch, seed)
+    tgl, tgb = torch.from_numpy(gl).to(DEV), torch.from_numpy(gb).to(DEV)
+    opt = FusedAdamW(model, lr=3e-3, weight_decay=1e-2)           # large steps: W moves by ~1e-2 per element in 4 steps
+    model.train_engine.publish_grads = False
+
+    def backward_once():
+        out = model(t("src_sketch"), t("src_sketch_mask"), t("src_video"), t("src_video_mask"))
+        logits = torch.stack([a["pred_logits"] for a in out["aux_outputs"]] + [out["pred_logits"]])
+        boxes = torch.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]])
+        torch.autograd.backward([logits, boxes], [tgl, tgb])
+
+    w0 = model.transformer.layers[0].mlp1.fc1.weight.detach().clone()
+    for _ in range(4):
+        backward_once()
+        opt.step(from_engine=True)
+    assert float((model.transformer.layers[0].mlp1.fc1.weight - w0).abs().mean()) > 3e-3
+    model.train_engine.publish_grads = True
+    for p in model.parameters():
+        p.grad = None
+    backward_once()
+    torch.cuda.synchronize()
+    sd_now = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    ref, _, _ = tp.head_gradients(sd_now, inp["src_sketch"], inp["src_sketch_mask"], inp["src_video"], inp["src_video_mask"],
+                                  gl, gb, nheads=cfg.nheads)
+    grads = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    _compare(grads, ref, "gradients after 4 FusedAdamW steps vs oracle autograd on the updated weights")
+
+
+def test_fused_adamw_is_a_torch_optimizer():
+    """Round-1 ADVICE (medium): param_groups drive the step (lr schedulers, train.py:129-137), state_dict / load_state_dict
+    in torch.optim.AdamW's format (train.py:149,270), parameters without a gradient are left untouched.  Checked against
+    torch.optim.AdamW itself on a small module: two groups with different lr / weight decay, one parameter that never gets a
+    gradient, StepLR, a checkpoint round trip in both directions."""
+    from svol_b200.optim import FusedAdamW
+
+    def make():
+        torch.manual_seed(0)
+        m = torch.nn.Sequential(torch.nn.Linear(13, 7), torch.nn.Linear(7, 5), torch.nn.Linear(5, 3)).to(DEV)
+        return m
+
+    def groups(m):
+        return [{"params": list(m[0].parameters()), "lr": 3e-3}, {"params": list(m[1].parameters()) + list(m[2].parameters()),
+                                                                    "weight_decay": 0.05}]
+
+    ma, mb = make(), make()
+    oa = torch.optim.AdamW(groups(ma), lr=1e-2, weight_decay=1e-2)
+    ob = FusedAdamW(groups(mb), lr=1e-2, weight_decay=1e-2)
+    assert isinstance(ob, torch.optim.Optimizer) and len(ob.param_groups) == 2 and ob.param_groups[0]["lr"] == 3e-3
+    sa = torch.optim.lr_scheduler.StepLR(oa, step_size=2, gamma=0.5)
+    sb = torch.optim.lr_scheduler.StepLR(ob, step_size=2, gamma=0.5)
+    x = torch.randn(11, 13, device=DEV)
+
+    def run(m, o, s, steps):
+        for _ in range(steps):
+            o.zero_grad()
+            (m[1](m[0](x)) ** 2).mean().backward()        # m[2] never receives a gradient
+            o.step()
+            s.step()
+
+    run(ma, oa, sa, 5)
+    run(mb, ob, sb, 5)
+    for pa, pb in zip(ma.parameters(), mb.parameters()):
+        assert torch.allclose(pa, pb, rtol=2e-5, atol=2e-6), float((pa - pb).abs().max())
+    assert torch.equal(mb[2].weight, make()[2].weight)                      # no gradient -> no weight decay either
+    assert ob.param_groups[0]["lr"] == oa.param_groups[0]["lr"] != 3e-3     # the scheduler reached the fused optimizer
+    # checkpoint round trips: fused -> torch and torch -> fused continue identically
+    sd_a, sd_b = oa.state_dict(), ob.state_dict()
+    assert sorted(sd_b["state"].keys()) == sorted(sd_a["state"].keys()) and set(sd_b["state"][0]) >= {"step", "exp_avg", "exp_avg_sq"}
+    mc, md = make(), make()
+    mc.load_state_dict(ma.state_dict()); md.load_state_dict(mb.state_dict())
+    oc = torch.optim.AdamW(groups(mc), lr=1e-2, weight_decay=1e-2)
+    od = FusedAdamW(groups(md), lr=1e-2, weight_decay=1e-2)
+    oc.load_state_dict(sd_b)                   # torch loads the fused optimizer's checkpoint
+    od.load_state_dict(sd_a)                   # and the other way round
+    sc = torch.optim.lr_scheduler.StepLR(oc, step_size=2, gamma=0.5); sc.load_state_dict(sa.state_dict())
+    sd_ = torch.optim.lr_scheduler.StepLR(od, step_size=2, gamma=0.5); sd_.load_state_dict(sb.state_dict())
+    run(ma, oa, sa, 3); run(mc, oc, sc, 3); run(md, od, sd_, 3)
+    for pa, pc, pd in zip(ma.parameters(), mc.parameters(), md.parameters()):
+        assert torch.allclose(pa, pc, rtol=2e-5, atol=2e-6) and torch.allclose(pa, pd, rtol=2e-5, atol=2e-6)
+
+
+def test_head_input_requires_grad_raises():
+    """train.py:72 optimises backbone + head.  The head's backward returns no gradient for its input features, so it must
+    refuse features that require one instead of silently freezing the backbone."""
+    from svol_b200 import synth
+    cfg = replace(synth.CONFIGS["tiny"], input_dropout=0.0)
+    model, _ = _build(cfg, 0)
+    model.train()
+    inp = synth.make_inputs(cfg, 2, 0)
+    t = lambda k: torch.from_numpy(inp[k]).to(DEV)
+    with pytest.raises(NotImplementedError, match="detached features"):
+        model(t("src_sketch"), t("src_sketch_mask"), t("src_video").requires_grad_(True), t("src_video_mask"))
+
+
 def test_wgrad_split_k_fp32():
     """svol_gemm_bf16 in weight-gradient mode: fp32 atomic accumulation with the contraction split over the SMs."""
     from svol_b200 import _lib, ops
