@@ -264,8 +264,9 @@ int svol_heads(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const 
  *   cost_ws   fp32 workspace or NULL.  When given, every problem's cost block (rows x cols, row-major) is also
  *             written to it: cost_off[p] (int64, [P+1]) = offset of problem p's block inside one layer's slab of
  *             cost_off[P] floats; total NL*cost_off[P] floats.  Required when rows_per_problem * max_cols * 4 bytes
- *             exceed 96 KB (the block is then read back from the workspace instead of shared memory) and for
- *             mode 1 / 2.
+ *             exceed 96 KB (the blocks are then read back from the workspace instead of shared memory, and are
+ *             stored in the solver's working orientation: TRANSPOSED, cols x rows, for problems with rows > cols)
+ *             and for mode 1 / 2.
  *   pred_idx, tgt_idx [NL, K] int64, K = match_off[P]: query index inside the video, target index (global, or
  *             local to the video after `localize`)
  *   status    [2] int32, ZERO-INITIALISED ONCE by the caller and then owned by the library: status[0] = result of
@@ -299,6 +300,8 @@ typedef struct svol_match_args {
   const int32_t* video_match_off;   /* [B+1] or NULL (localize == 0) */
   const int32_t* video_tgt_off;     /* [B+1] or NULL (localize != 2) */
   int32_t mode, solver, localize, reserved;
+  const int32_t* order;             /* [P] permutation of the problems or NULL: launch order, e.g. most columns first
+                                       (longest-processing-time-first: the launch does not end on its largest problem) */
 } svol_match_args;
 
 int svol_match(const svol_match_args* args, void* stream);
@@ -311,10 +314,11 @@ int svol_match_localize(int64_t* tgt_idx, const int32_t* video_match_off, int32_
 /* Batched scipy.optimize.linear_sum_assignment (matcher.py:93,158) on caller-supplied fp32 cost matrices, one warp
  * per problem, the solver of svol_match.  Problem p: shape[2p] x shape[2p+1] row-major at cost + cost_off[p];
  * min(rows, cols) assignments written to rows_out / cols_out + out_off[p] (rows ascending, as scipy returns them);
- * status[p] = 0 ok, 1 invalid entries (NaN / -inf), 2 infeasible.  max_rows * max_cols * 4 bytes must fit in shared
- * memory (<= ~190 KB).  solver as in svol_match_args. */
+ * status[p] = 0 ok, 1 invalid entries (NaN / -inf), 2 infeasible.  max_small / max_big = upper bounds of min / max(rows,
+ * cols) over the batch, max_entries of rows * cols; max_entries * 4 bytes must fit in shared memory (<= ~190 KB).
+ * solver as in svol_match_args. */
 int svol_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int32_t n_problems,
-                  int32_t max_rows, int32_t max_cols, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off,
+                  int32_t max_small, int32_t max_big, int32_t max_entries, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off,
                   int32_t* status, int32_t solver, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -343,7 +347,12 @@ typedef struct svol_criterion_args {
   int32_t idx_pitch;
   const int32_t* video_match_off;
   const int32_t* meta;
+  void* scratch;     /* NULL: one CTA per layer.  Else >= svol_criterion_scratch_bytes(NL, B) bytes, ZERO-INITIALISED ONCE by
+                        the caller (needs video_match_off): one CTA per (video, layer), fp64 partial sums combined in video
+                        order by the last CTA to arrive, which also resets the arrival counters */
 } svol_criterion_args;
+/* NL * B * 4 doubles + NL int32 counters, rounded up to 16 bytes */
+int64_t svol_criterion_scratch_bytes(int32_t NL, int32_t B);
 
 int svol_criterion(const svol_criterion_args* args, void* stream);
 int svol_criterion_backward(const svol_criterion_args* args, const float* grad_w, float* grad_logits,

@@ -22,7 +22,7 @@ SYMBOLS = [
     "svol_layernorm_f32_to_bf16", "svol_ln_linear_f32", "svol_posenc_sine", "svol_posenc_theta", "svol_add_pos_bf16",
     "svol_gate_vectors", "svol_gate_scores", "svol_gate_apply", "svol_gate_apply_theta", "svol_gate_fused",
     "svol_gate_fused_supported", "svol_heads",
-    "svol_match", "svol_match_localize", "svol_lsap_f32", "svol_criterion", "svol_criterion_backward", "svol_postprocess",
+    "svol_match", "svol_match_localize", "svol_lsap_f32", "svol_criterion", "svol_criterion_backward", "svol_criterion_scratch_bytes", "svol_postprocess",
     # training step
     "svol_layernorm_bf16", "svol_layernorm_backward", "svol_gelu_bf16", "svol_act_backward", "svol_transpose_bf16",
     "svol_colsum_bf16", "svol_attention_backward_bf16", "svol_heads_backward", "svol_gate_backward",
@@ -107,6 +107,7 @@ class MatchArgs(C.Structure):
         ("w_class", C.c_float), ("w_bbox", C.c_float), ("w_giou", C.c_float), ("K", C.c_int32),
         ("video_match_off", C.c_void_p), ("video_tgt_off", C.c_void_p),
         ("mode", C.c_int32), ("solver", C.c_int32), ("localize", C.c_int32), ("reserved", C.c_int32),
+        ("order", C.c_void_p),
     ]
 
 
@@ -116,6 +117,7 @@ class CriterionArgs(C.Structure):
         ("tgt_idx", C.c_void_p), ("match_video", C.c_void_p), ("video_tgt_off", C.c_void_p), ("losses", C.c_void_p),
         ("NL", C.c_int32), ("B", C.c_int32), ("Q", C.c_int32), ("K", C.c_int32),
         ("eos_coef", C.c_float), ("idx_pitch", C.c_int32), ("video_match_off", C.c_void_p), ("meta", C.c_void_p),
+        ("scratch", C.c_void_p),
     ]
 
 
@@ -149,9 +151,10 @@ def _declare(lib: C.CDLL) -> None:
         "svol_heads": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp],
         "svol_match": [C.POINTER(MatchArgs), _vp],
         "svol_match_localize": [_vp, _vp, _i32, _i32, _i32, _vp],
-        "svol_lsap_f32": [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
+        "svol_lsap_f32": [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp],
         "svol_criterion": [C.POINTER(CriterionArgs), _vp],
         "svol_criterion_backward": [C.POINTER(CriterionArgs), _vp, _vp, _vp, _vp],
+        "svol_criterion_scratch_bytes": [_i32, _i32],
         "svol_postprocess": [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp],
         "svol_layernorm_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _i32, _f32, _f32, _vp, _i32, _vp],
         "svol_layernorm_backward": [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _f32, _f32, _vp, _i32, _vp],
@@ -178,6 +181,7 @@ def _declare(lib: C.CDLL) -> None:
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.svol_criterion_scratch_bytes.restype = C.c_int64
 
 
 def get_lib() -> C.CDLL:

@@ -281,18 +281,21 @@ int svol_match(const svol_match_args* a, void* stream) {
   SVOL_REQUIRE(a->tgt_idx); SVOL_REQUIRE(a->status);
   return launch_match(*a, SVOL_STREAM(stream));
 }
-int svol_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int32_t n_problems, int32_t max_rows,
-                  int32_t max_cols, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off, int32_t* status,
+int svol_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int32_t n_problems, int32_t max_small,
+                  int32_t max_big, int32_t max_entries, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off, int32_t* status,
                   int32_t solver, void* stream) {
   SVOL_REQUIRE(cost); SVOL_REQUIRE(cost_off); SVOL_REQUIRE(shape); SVOL_REQUIRE(rows_out); SVOL_REQUIRE(cols_out);
   SVOL_REQUIRE(out_off); SVOL_REQUIRE(status);
-  return launch_lsap_f32(cost, cost_off, shape, n_problems, max_rows, max_cols, rows_out, cols_out, out_off, status, solver,
+  return launch_lsap_f32(cost, cost_off, shape, n_problems, max_small, max_big, max_entries, rows_out, cols_out, out_off, status, solver,
                          SVOL_STREAM(stream));
 }
 int svol_match_localize(int64_t* tgt_idx, const int32_t* video_match_off, int32_t NL, int32_t B, int32_t K,
                         void* stream) {
   SVOL_REQUIRE(tgt_idx); SVOL_REQUIRE(video_match_off);
   return launch_match_localize(tgt_idx, video_match_off, NL, B, K, SVOL_STREAM(stream));
+}
+int64_t svol_criterion_scratch_bytes(int32_t NL, int32_t B) {
+  return (static_cast<int64_t>(NL) * B * 4 * 8 + static_cast<int64_t>(NL) * 4 + 15) / 16 * 16;
 }
 int svol_criterion(const svol_criterion_args* a, void* stream) {
   SVOL_REQUIRE(a); SVOL_REQUIRE(a->logits); SVOL_REQUIRE(a->boxes); SVOL_REQUIRE(a->tgt_boxes); SVOL_REQUIRE(a->pred_idx);

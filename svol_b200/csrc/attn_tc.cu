@@ -207,7 +207,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem + OFF_BAR);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // `lane` and the tensor-memory base are re-derived inside each role (opaque to common-subexpression elimination): as
+  // values of the common prologue they would have to live in the 32-register budget of the producer / issuer warpgroup
+  // and were spilled to local memory there
+  const int warp = threadIdx.x >> 5;
+  auto lane_id = []() { int l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; };
+  auto tmem_base_of = [](const AttnBars* b) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&b->tmem_base)) : "memory"); return v; };
   const int q0 = blockIdx.x * (2 * BQ), h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (Lk + BKV - 1) / BKV;
   const int n_q = (q0 + BQ < Lq) ? 2 : 1;          // is the second query tile of this CTA populated?
@@ -221,13 +226,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const bool split = n_q == 1 && n_tiles >= 4;
 #ifdef SVOL_ATTN_TRACE
 #ifdef SVOL_ATTN_TRACE_LAST      // trace the LAST query-tile pair of (sample 0, head 0): the single-tile CTA when Lq % 256 is in (0, 128]
-  const bool trace_on = blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && ((warp & 3) == 0 || warp >= 16);
+  const bool trace_on = blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane_id() == 0 && ((warp & 3) == 0 || warp >= 16);
 #else
-  const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && ((warp & 3) == 0 || warp >= 16);
+  const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane_id() == 0 && ((warp & 3) == 0 || warp >= 16);
 #endif
 #endif
 
-  if (warp == 16 && lane == 0) {
+  if (warp == 16 && lane_id() == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
     mbar_init(&bars->q_full, 1);
     for (int g = 0; g < 4; ++g) {
@@ -246,12 +251,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
 
   // register re-split (each role branch starts with its own setmaxnreg so that it dominates the role's code).
-  // The CTA is launched with 640 x 96 registers and setmaxnreg only redistributes them: 4 x 112 + 24 <= 5 x 96.
+  // The CTA is launched with 640 x 96 registers and setmaxnreg only redistributes them: 4 x 112 + 32 = 5 x 96.  (With 24
+  // for the fifth warpgroup the issuers' descriptors and counters were spilled INSIDE their issue loops.)
   if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 16) {
       // ------------------------------------------------------------------ TMA producer
       if (elect_one()) {
@@ -271,6 +276,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     } else if (warp == 17 || warp == 18) {
       // ------------------------------------------------------------------ MMA issuer of tile slot t
       const int t = warp - 17;
+      const uint32_t tmem_base = tmem_base_of(bars);
       auto run_issuer = [&](auto split_tag) {
       constexpr bool kSplit = decltype(split_tag)::value;
       constexpr int j_step = kSplit ? 2 : 1;
@@ -333,6 +339,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int g = warp >> 2;                            // softmax warpgroup
     const int t = g >> 1, half = g & 1;                 // query tile, key half
+    const int lane = lane_id();
+    const uint32_t tmem_base = tmem_base_of(bars);
     // key_padding_mask of this sample as a bitmask in shared memory (built once, under the TMA / first-QK^T latency):
     // reading the float mask inside the key loop put an L2 round trip on every tile's critical path
     uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + OFF_KMASK);
@@ -562,7 +570,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   if (warp == 17) {
     tcgen05_fence_after();
-    tmem_dealloc<attn::TMEM_COLS>(tmem_base);
+    tmem_dealloc<attn::TMEM_COLS>(tmem_base_of(bars));
   }
 }
 

@@ -81,32 +81,55 @@ __device__ __forceinline__ int tgt_entry(const CriterionArgs& a, const CritDims&
   return static_cast<int>(g < 0 ? 0 : (g >= d.S ? d.S - 1 : g));
 }
 
-__device__ __forceinline__ void mark_matched(uint32_t* bitmap, const CriterionArgs& a, const CritDims& d, int layer) {
-  const int words = (a.B * a.Q + 31) >> 5;
+// A CTA works on the videos [b0, b1) of one decoder layer: queries [b0*Q, b1*Q), matched pairs
+// [video_match_off[b0], video_match_off[b1]) (the whole batch when launched with one CTA per layer).
+struct CritRange { int b0, b1, q0, q1, k0, k1; };
+__device__ __forceinline__ CritRange crit_range(const CriterionArgs& a, const CritDims& d, bool chunked) {
+  CritRange r;
+  if (chunked) {
+    r.b0 = blockIdx.x; r.b1 = r.b0 + 1;
+    r.k0 = a.video_match_off[r.b0]; r.k1 = a.video_match_off[r.b1];
+  } else {
+    r.b0 = 0; r.b1 = a.B; r.k0 = 0; r.k1 = d.K;
+  }
+  r.q0 = r.b0 * a.Q; r.q1 = r.b1 * a.Q;
+  return r;
+}
+
+__device__ __forceinline__ void mark_matched(uint32_t* bitmap, const CriterionArgs& a, const CritDims& d, const CritRange& r,
+                                             bool chunked, int layer) {
+  const int words = (r.q1 - r.q0 + 31) >> 5;
   for (int i = threadIdx.x; i < words; i += blockDim.x) bitmap[i] = 0u;
   __syncthreads();
   const int64_t* pi = a.pred_idx + static_cast<size_t>(layer) * d.pitch;
-  for (int k = threadIdx.x; k < d.K; k += blockDim.x) {
-    const int e = pred_entry(a, pair_video(a, k), pi[k]);
+  for (int k = r.k0 + threadIdx.x; k < r.k1; k += blockDim.x) {
+    const int e = pred_entry(a, chunked ? r.b0 : pair_video(a, k), pi[k]) - r.q0;
     atomicOr(&bitmap[e >> 5], 1u << (e & 31));
   }
   __syncthreads();
 }
 
+// Launched as (1, NL) x 1024 threads (one CTA per layer), or -- with a scratch buffer -- as (B, NL) x 256: one CTA per
+// (video, layer) writes four fp64 partial sums, the last CTA of a layer to arrive adds them up in video order
+// (deterministic) and resets the arrival counter for the next launch.
 __global__ void __launch_bounds__(CRIT_THREADS) criterion_kernel(const CriterionArgs a) {
   extern __shared__ uint32_t bitmap[];
   __shared__ double red[32];
-  const int layer = blockIdx.x, tid = threadIdx.x;
+  __shared__ int is_last;
+  const bool chunked = gridDim.x > 1;
+  const int layer = blockIdx.y, tid = threadIdx.x;
   const int n = a.B * a.Q;
   const CritDims d = crit_dims(a);
-  mark_matched(bitmap, a, d, layer);
+  const CritRange r = crit_range(a, d, chunked);
+  mark_matched(bitmap, a, d, r, chunked, layer);
 
   // weighted cross-entropy over every query (loss.py:50-55): sum(w * nll) / (B*Q)
   const float2* lg = reinterpret_cast<const float2*>(a.logits) + static_cast<size_t>(layer) * n;
   double ce = 0.0;
-  for (int e = tid; e < n; e += blockDim.x) {
+  for (int e = r.q0 + tid; e < r.q1; e += blockDim.x) {
     const float2 l = __ldg(lg + e);
-    const bool fg = (bitmap[e >> 5] >> (e & 31)) & 1u;
+    const int w = e - r.q0;
+    const bool fg = (bitmap[w >> 5] >> (w & 31)) & 1u;
     const float m = fmaxf(l.x, l.y);
     const float lse = m + logf(expf(l.x - m) + expf(l.y - m));
     const float nll = lse - (fg ? l.x : l.y);
@@ -117,8 +140,8 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_kernel(const Criterion
   const int64_t* ti = a.tgt_idx + static_cast<size_t>(layer) * d.pitch;
   const float4* bx = reinterpret_cast<const float4*>(a.boxes) + static_cast<size_t>(layer) * n;
   double correct = 0.0, l1 = 0.0, gl = 0.0;
-  for (int k = tid; k < d.K; k += blockDim.x) {
-    const int b = pair_video(a, k);
+  for (int k = r.k0 + tid; k < r.k1; k += blockDim.x) {
+    const int b = chunked ? r.b0 : pair_video(a, k);
     const int e = pred_entry(a, b, pi[k]);
     const float2 l = __ldg(lg + e);
     correct += (l.x >= l.y) ? 1.0 : 0.0;        // top-1 == foreground (index 0 wins ties)
@@ -131,33 +154,62 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_kernel(const Criterion
   correct = block_sum(correct, red);
   l1 = block_sum(l1, red);
   gl = block_sum(gl, red);
-  if (tid == 0) {
+  auto publish = [&](double ce_, double correct_, double l1_, double gl_) {
     float* o = a.losses + layer * 4;
-    o[0] = static_cast<float>(ce / n);
-    o[1] = static_cast<float>(100.0 - correct * (100.0 / d.K));
-    o[2] = static_cast<float>(l1 / (4.0 * d.K));
-    o[3] = static_cast<float>(gl / d.K);
+    o[0] = static_cast<float>(ce_ / n);
+    o[1] = static_cast<float>(100.0 - correct_ * (100.0 / d.K));
+    o[2] = static_cast<float>(l1_ / (4.0 * d.K));
+    o[3] = static_cast<float>(gl_ / d.K);
+  };
+  if (!chunked) {
+    if (tid == 0) publish(ce, correct, l1, gl);
+    return;
+  }
+  double* partial = reinterpret_cast<double*>(a.scratch) + (static_cast<size_t>(layer) * a.B) * 4;
+  int* counter = reinterpret_cast<int*>(reinterpret_cast<double*>(a.scratch) + static_cast<size_t>(gridDim.y) * a.B * 4) + layer;
+  if (tid == 0) {
+    double* p = partial + blockIdx.x * 4;
+    p[0] = ce; p[1] = correct; p[2] = l1; p[3] = gl;
+    __threadfence();
+    is_last = atomicAdd(counter, 1) == a.B - 1;
+  }
+  __syncthreads();
+  if (is_last && tid < 32) {
+    __threadfence();
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (tid < 4) {
+      for (int b = 0; b < a.B; ++b) acc[0] += __ldcg(partial + b * 4 + tid);       // lane c sums component c, in video order
+    }
+    const double c0 = __shfl_sync(0xffffffffu, acc[0], 0), c1 = __shfl_sync(0xffffffffu, acc[0], 1);
+    const double c2 = __shfl_sync(0xffffffffu, acc[0], 2), c3 = __shfl_sync(0xffffffffu, acc[0], 3);
+    if (tid == 0) {
+      publish(c0, c1, c2, c3);
+      *counter = 0;
+    }
   }
 }
 
-// d(sum_layer w_label*loss_label + w_bbox*loss_bbox + w_giou*loss_giou) / d(logits, boxes)
+// d(sum_layer w_label*loss_label + w_bbox*loss_bbox + w_giou*loss_giou) / d(logits, boxes); same two launch shapes.
 __global__ void __launch_bounds__(CRIT_THREADS) criterion_backward_kernel(const CriterionArgs a,
                                                                           const float* __restrict__ grad_w,
                                                                           float* __restrict__ grad_logits,
                                                                           float* __restrict__ grad_boxes) {
   extern __shared__ uint32_t bitmap[];
-  const int layer = blockIdx.x, tid = threadIdx.x;
+  const bool chunked = gridDim.x > 1;
+  const int layer = blockIdx.y, tid = threadIdx.x;
   const int n = a.B * a.Q;
   const CritDims d = crit_dims(a);
-  mark_matched(bitmap, a, d, layer);
+  const CritRange r = crit_range(a, d, chunked);
+  mark_matched(bitmap, a, d, r, chunked, layer);
   const float w_label = grad_w[layer * 3 + 0], w_bbox = grad_w[layer * 3 + 1], w_giou = grad_w[layer * 3 + 2];
   const float2* lg = reinterpret_cast<const float2*>(a.logits) + static_cast<size_t>(layer) * n;
   float2* glg = reinterpret_cast<float2*>(grad_logits) + static_cast<size_t>(layer) * n;
   float4* gbx = reinterpret_cast<float4*>(grad_boxes) + static_cast<size_t>(layer) * n;
   const float ce_scale = w_label / n;
-  for (int e = tid; e < n; e += blockDim.x) {
+  for (int e = r.q0 + tid; e < r.q1; e += blockDim.x) {
     const float2 l = __ldg(lg + e);
-    const bool fg = (bitmap[e >> 5] >> (e & 31)) & 1u;
+    const int w_ = e - r.q0;
+    const bool fg = (bitmap[w_ >> 5] >> (w_ & 31)) & 1u;
     const float m = fmaxf(l.x, l.y);
     const float e0 = expf(l.x - m), e1 = expf(l.y - m);
     const float p0 = e0 / (e0 + e1), p1 = e1 / (e0 + e1);
@@ -169,8 +221,8 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_backward_kernel(const 
   const int64_t* ti = a.tgt_idx + static_cast<size_t>(layer) * d.pitch;
   const float4* bx = reinterpret_cast<const float4*>(a.boxes) + static_cast<size_t>(layer) * n;
   const float s_l1 = w_bbox / (4.0f * d.K), s_g = -w_giou / d.K;       // loss_giou = mean(1 - giou)
-  for (int k = tid; k < d.K; k += blockDim.x) {
-    const int b = pair_video(a, k);
+  for (int k = r.k0 + tid; k < r.k1; k += blockDim.x) {
+    const int b = chunked ? r.b0 : pair_video(a, k);
     const int e = pred_entry(a, b, pi[k]);
     const float4 s = __ldg(bx + e);
     const float4 t = __ldg(reinterpret_cast<const float4*>(a.tgt_boxes) + tgt_entry(a, d, b, ti[k]));
@@ -198,41 +250,44 @@ __global__ void __launch_bounds__(CRIT_THREADS) criterion_backward_kernel(const 
   }
 }
 
-static int check_criterion(const CriterionArgs& a, size_t* smem) {
+static int check_criterion(const CriterionArgs& a, size_t* smem, dim3* grid, int* threads) {
   if (a.NL <= 0 || a.B <= 0 || a.Q <= 0 || (a.meta == nullptr && a.K <= 0))
     return svol_fail(SVOL_ERR_SHAPE, "criterion: bad sizes (K must be > 0)");
   if (a.match_video == nullptr && a.video_match_off == nullptr)
     return svol_fail(SVOL_ERR_NULL, "criterion: match_video or video_match_off is required");
   if (a.meta != nullptr && a.idx_pitch <= 0) return svol_fail(SVOL_ERR_SHAPE, "criterion: a device-side K needs idx_pitch");
-  *smem = static_cast<size_t>((a.B * a.Q + 31) / 32) * 4;
+  const bool chunked = a.scratch != nullptr && a.video_match_off != nullptr && a.B > 1;
+  *grid = dim3(chunked ? a.B : 1, a.NL);
+  *threads = chunked ? 256 : CRIT_THREADS;
+  *smem = static_cast<size_t>(((chunked ? 1 : a.B) * a.Q + 31) / 32) * 4;
   if (*smem > 160 * 1024) return svol_fail(SVOL_ERR_SHAPE, "criterion: B*Q too large for the shared-memory bitmap");
   return SVOL_OK;
 }
 
 int launch_criterion(const CriterionArgs& a, cudaStream_t stream) {
-  size_t smem;
-  if (int rc = check_criterion(a, &smem)) return rc;
+  size_t smem; dim3 grid; int threads;
+  if (int rc = check_criterion(a, &smem, &grid, &threads)) return rc;
   static size_t configured = 0;
   if (smem > 40 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(criterion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return svol_fail_cuda(e, "criterion: cudaFuncSetAttribute");
     configured = smem;
   }
-  criterion_kernel<<<a.NL, CRIT_THREADS, smem, stream>>>(a);
+  criterion_kernel<<<grid, threads, smem, stream>>>(a);
   return svol_check_launch("criterion");
 }
 
 int launch_criterion_backward(const CriterionArgs& a, const float* grad_w, float* grad_logits, float* grad_boxes,
                               cudaStream_t stream) {
-  size_t smem;
-  if (int rc = check_criterion(a, &smem)) return rc;
+  size_t smem; dim3 grid; int threads;
+  if (int rc = check_criterion(a, &smem, &grid, &threads)) return rc;
   static size_t configured = 0;
   if (smem > 40 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(criterion_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return svol_fail_cuda(e, "criterion_backward: cudaFuncSetAttribute");
     configured = smem;
   }
-  criterion_backward_kernel<<<a.NL, CRIT_THREADS, smem, stream>>>(a, grad_w, grad_logits, grad_boxes);
+  criterion_backward_kernel<<<grid, threads, smem, stream>>>(a, grad_w, grad_logits, grad_boxes);
   return svol_check_launch("criterion_backward");
 }
 

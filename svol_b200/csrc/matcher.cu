@@ -120,17 +120,16 @@ __device__ __forceinline__ unsigned long long ordered_key(double x) {
 template <int CPL>
 __device__ __forceinline__ int lsap_warp_regs(const float* __restrict__ C, int si, int sj, int nr, int nc, const LsapSmem& s,
                                               int lane) {
-  double v[CPL], spc[CPL];
-  int pos[CPL];
+  double v[CPL], spc[CPL], uo[CPL];   // per owned column: dual, shortest-path cost, u of the row it is assigned to
+  int pos[CPL], own[CPL];             // position in scipy's `remaining` list; row4col (constant during one search)
 #pragma unroll
-  for (int k = 0; k < CPL; ++k) v[k] = 0.0;
-  unsigned valid = 0, freem = 0;
+  for (int k = 0; k < CPL; ++k) { v[k] = 0.0; uo[k] = 0.0; own[k] = -1; }
+  unsigned valid = 0;
 #pragma unroll
   for (int k = 0; k < CPL; ++k) {
     const int j = lane + 32 * k;
     if (j < nc) { valid |= 1u << k; s.row4col[j] = -1; s.path[j] = -1; }
   }
-  freem = valid;
   for (int i = lane; i < nr; i += 32) { s.u[i] = 0.0; s.col4row[i] = -1; }
   __syncwarp();
 
@@ -139,41 +138,55 @@ __device__ __forceinline__ int lsap_warp_regs(const float* __restrict__ C, int s
 #pragma unroll
     for (int k = 0; k < CPL; ++k) { spc[k] = CUDART_INF; pos[k] = nc - 1 - (lane + 32 * k); }   // remaining[t] = nc - t - 1
     int n_rem = nc, i = cur, sink = -1;
-    double best = 0.0;
+    double best = 0.0, ui = s.u[cur];
     while (sink == -1) {
-      const double ui = s.u[i];
       const float* crow = C + static_cast<size_t>(i) * si;
+      // branch-free over the owned columns, so that their load -> three fp64 adds -> compare chains overlap
+      float c[CPL];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) c[k] = crow[static_cast<size_t>(min(lane + 32 * k, nc - 1)) * sj];
       double lw = CUDART_INF;
       unsigned kw = 0;
-      int jw = -1;
+      const unsigned live = valid & ~scm;
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
-        if (((valid & ~scm) >> k) & 1u) {
-          const int j = lane + 32 * k;
-          const double r = ((best + static_cast<double>(crow[static_cast<size_t>(j) * sj])) - ui) - v[k];
-          if (r < spc[k]) { s.path[j] = i; spc[k] = r; }
-          const double sv = spc[k];
-          // scipy: a strictly lower value wins; among equal values a free column found later in `remaining` order wins.
-          // As a set function: max over the minima of (free ? 2^31 + position : 2^31 - 1 - position).
-          const unsigned key = ((freem >> k) & 1u) ? (0x80000000u | static_cast<unsigned>(pos[k]))
-                                                   : (0x7fffffffu - static_cast<unsigned>(pos[k]));
-          if (sv < lw || (sv == lw && key > kw)) { lw = sv; kw = key; jw = j; }
-        }
+        const int j = lane + 32 * k;
+        const bool on = (live >> k) & 1u;
+        const double r = ((best + static_cast<double>(c[k])) - ui) - v[k];
+        const bool upd = on && r < spc[k];
+        if (upd) s.path[j] = i;
+        spc[k] = upd ? r : spc[k];
+        const double sv = on ? spc[k] : CUDART_INF;
+        // scipy: a strictly lower value wins; among equal values a free column found later in `remaining` order wins.
+        // As a set function: the maximum over the minima of (free, free ? position : -position); the column index rides
+        // in the low 10 bits (positions are unique, so it never decides).
+        const unsigned p = static_cast<unsigned>(pos[k]);
+        const unsigned key = on ? ((own[k] < 0 ? (0x80000000u | (p << 10)) : ((0x1fffffu - p) << 10)) | static_cast<unsigned>(j)) : 0u;
+        const bool take = sv < lw || (sv == lw && key > kw);
+        lw = take ? sv : lw;
+        kw = take ? key : kw;
       }
+      // fp64 minimum as two 32-bit reductions of an order-preserving key, then the tie rule as a third
       const unsigned long long ok = ordered_key(lw);
       const unsigned hi = static_cast<unsigned>(ok >> 32), lo = static_cast<unsigned>(ok);
       const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
       const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
-      const bool mine = hi == mh && lo == ml && jw >= 0;
-      const unsigned kmax = __reduce_max_sync(0xffffffffu, mine ? kw : 0u);
+      const unsigned kmax = __reduce_max_sync(0xffffffffu, (hi == mh && lo == ml) ? kw : 0u);
       if (mh == 0xfff00000u && ml == 0u) return 2;      // minimum is +inf: infeasible
-      const unsigned who = __ballot_sync(0xffffffffu, mine && kw == kmax);
-      const int src = __ffs(who) - 1;
-      const int j = __shfl_sync(0xffffffffu, jw, src);
-      best = __shfl_sync(0xffffffffu, lw, src);
-      const int pick = (kmax & 0x80000000u) ? static_cast<int>(kmax & 0x7fffffffu) : static_cast<int>(0x7fffffffu - kmax);
-      const int owner = s.row4col[j];
-      if (lane == (j & 31)) scm |= 1u << (j >> 5);
+      const unsigned long long okm = (static_cast<unsigned long long>(mh) << 32) | ml;
+      best = __longlong_as_double(static_cast<long long>((okm >> 63) ? (okm ^ 0x8000000000000000ull) : ~okm));
+      const int j = static_cast<int>(kmax & 0x3ffu);
+      const unsigned pf = (kmax >> 10) & 0x1fffffu;
+      const int pick = (kmax & 0x80000000u) ? static_cast<int>(pf) : static_cast<int>(0x1fffffu - pf);
+      // owner row of column j and its dual, from the registers of the lane that holds the column
+      const int slot = j >> 5;
+      int own_s = own[0];
+      double uo_s = uo[0];
+#pragma unroll
+      for (int k = 1; k < CPL; ++k) { own_s = slot == k ? own[k] : own_s; uo_s = slot == k ? uo[k] : uo_s; }
+      const int owner = __shfl_sync(0xffffffffu, own_s, j & 31);
+      ui = __shfl_sync(0xffffffffu, uo_s, j & 31);
+      if (lane == (j & 31)) scm |= 1u << slot;
       --n_rem;                                          // remaining[pick] = remaining[--n_rem]
 #pragma unroll
       for (int k = 0; k < CPL; ++k) pos[k] = pos[k] == n_rem ? pick : pos[k];
@@ -186,7 +199,7 @@ __device__ __forceinline__ int lsap_warp_regs(const float* __restrict__ C, int s
       if ((scm >> k) & 1u) {
         const int j = lane + 32 * k;
         const double dlt = best - spc[k];
-        if (j != sink) s.u[s.row4col[j]] += dlt;
+        if (j != sink) s.u[own[k]] += dlt;
         v[k] -= dlt;
       }
     }
@@ -203,8 +216,15 @@ __device__ __forceinline__ int lsap_warp_regs(const float* __restrict__ C, int s
         if (r == cur) break;
       }
     }
-    if (lane == (sink & 31)) freem &= ~(1u << (sink >> 5));
     __syncwarp();
+    // refresh the per-column copies of row4col / u[row4col] for the next search
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      if ((valid >> k) & 1u) {
+        own[k] = s.row4col[lane + 32 * k];
+        uo[k] = own[k] >= 0 ? s.u[own[k]] : 0.0;
+      }
+    }
   }
   return 0;
 }
@@ -305,14 +325,54 @@ __device__ __forceinline__ void lsap_emit(bool transposed, int nr, int nc, const
   }
 }
 
-// One warp per (layer, problem).  mode 0: cost block + solve; 1: cost blocks only (into cost_ws); 2: solve from cost_ws.
-// Dynamic shared memory: solver state (lsap_smem_bytes) followed by the cost block in working orientation when it fits
-// (cost_smem_floats > 0); larger problems read the block from the global workspace.
-__global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int ms, int mb, int cost_smem_floats) {
+// Per-box quantities of the cost formula that do not depend on the partner box, staged once per problem in shared
+// memory (structure of arrays: consecutive lanes read consecutive boxes).  Computed with the same fp32 operations as
+// pair_cost(), so a cost assembled from them is bit-identical.
+constexpr int QF = 10, TF = 9;     // floats per query (p_fg, cx, cy, w, h, x0, y0, x1, y1, area) / per target (no p_fg)
+__device__ __forceinline__ void box_derive(const float4& b, float* dst, int pitch) {
+  dst[0 * pitch] = b.x; dst[1 * pitch] = b.y; dst[2 * pitch] = b.z; dst[3 * pitch] = b.w;
+  const float x0 = __fsub_rn(b.x, __fmul_rn(0.5f, b.z)), y0 = __fsub_rn(b.y, __fmul_rn(0.5f, b.w));
+  const float x1 = __fadd_rn(b.x, __fmul_rn(0.5f, b.z)), y1 = __fadd_rn(b.y, __fmul_rn(0.5f, b.w));
+  dst[4 * pitch] = x0; dst[5 * pitch] = y0; dst[6 * pitch] = x1; dst[7 * pitch] = y1;
+  dst[8 * pitch] = __fmul_rn(__fsub_rn(x1, x0), __fsub_rn(y1, y0));
+}
+__device__ __forceinline__ float staged_cost(const float* q, int qp, int r, const float* t, int tp, int c, float w_class,
+                                             float w_bbox, float w_giou) {
+  const float p_fg = q[r];
+  const float* qb = q + qp + r;      // box fields of query r start after the p_fg plane
+  const float* tb = t + c;
+  float l1 = fabsf(__fsub_rn(qb[0], tb[0]));
+  l1 = __fadd_rn(l1, fabsf(__fsub_rn(qb[qp], tb[tp])));
+  l1 = __fadd_rn(l1, fabsf(__fsub_rn(qb[2 * qp], tb[2 * tp])));
+  l1 = __fadd_rn(l1, fabsf(__fsub_rn(qb[3 * qp], tb[3 * tp])));
+  const float ax0 = qb[4 * qp], ay0 = qb[5 * qp], ax1 = qb[6 * qp], ay1 = qb[7 * qp], area_a = qb[8 * qp];
+  const float tx0 = tb[4 * tp], ty0 = tb[5 * tp], tx1 = tb[6 * tp], ty1 = tb[7 * tp], area_t = tb[8 * tp];
+  const float iw = fmaxf(__fsub_rn(fminf(ax1, tx1), fmaxf(ax0, tx0)), 0.f);
+  const float ih = fmaxf(__fsub_rn(fminf(ay1, ty1), fmaxf(ay0, ty0)), 0.f);
+  const float inter = __fmul_rn(iw, ih);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_t), inter);
+  const float iou = __fdiv_rn(inter, uni);
+  const float cw = fmaxf(__fsub_rn(fmaxf(ax1, tx1), fminf(ax0, tx0)), 0.f);
+  const float ch = fmaxf(__fsub_rn(fmaxf(ay1, ty1), fminf(ay0, ty0)), 0.f);
+  const float hull = __fmul_rn(cw, ch);
+  const float giou = __fsub_rn(iou, __fdiv_rn(__fsub_rn(hull, uni), hull));
+  return __fadd_rn(__fadd_rn(__fmul_rn(w_bbox, l1), __fmul_rn(w_giou, -giou)), __fmul_rn(w_class, -p_fg));
+}
+
+// One CTA of 1, 2 or 4 warps per (layer, problem): all of them stage the problem's boxes and fill its cost block, warp 0
+// solves (registers are allocated per thread, so extra fill warps cost solver occupancy: launch_match picks the width).
+// Problems are taken in the caller's `order` (largest first: the launch ends with the short ones) when one is given.
+// mode 0: cost block + solve; 1: cost blocks only (into cost_ws); 2: solve from cost_ws.
+// Dynamic shared memory: solver state (lsap_smem_bytes) | staged boxes (QF * rows + TF * max_cols floats) | the cost
+// block in the solver's working orientation when it fits (cost_smem_floats > 0); larger blocks live in the global
+// workspace, also in working orientation (transposed when the problem is tall) so that the solver's row reads coalesce.
+template <int MATCH_THREADS>
+__global__ void __launch_bounds__(MATCH_THREADS) match_kernel(const MatchArgs a, int ms, int mb, int cost_smem_floats) {
   extern __shared__ __align__(16) uint8_t sm_raw[];
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = a.B * a.problems_per_video;
-  const int layer = blockIdx.x / P, p = blockIdx.x - layer * P;
+  const int slot_p = blockIdx.x / a.NL, layer = blockIdx.x - slot_p * a.NL;     // layers of one problem run side by side
+  const int p = a.order ? a.order[slot_p] : slot_p;
   const int video = p / a.problems_per_video, local = p - video * a.problems_per_video;
   const int nrows = a.rows_per_problem;
   const int t0 = a.tgt_off[p], ncols = a.tgt_off[p + 1] - t0;
@@ -320,7 +380,10 @@ __global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int ms, in
   int32_t* status_acc = a.status + 1;
 
   const LsapSmem s = lsap_carve(sm_raw, ms, mb);
-  float* Cs = reinterpret_cast<float*>(sm_raw + lsap_smem_bytes(ms, mb));
+  const int qp = (nrows + 3) & ~3, tp = (a.max_cols + 3) & ~3;           // plane pitches of the staged boxes
+  float* qs = reinterpret_cast<float*>(sm_raw + lsap_smem_bytes(ms, mb));
+  float* ts = qs + QF * qp;
+  float* Cs = ts + TF * tp;
   const bool cost_in_smem = nrows * ncols <= cost_smem_floats;
   const bool transposed = ncols < nrows;          // scipy transposes tall problems
   const int nr = transposed ? ncols : nrows;      // rows of the working problem
@@ -340,42 +403,51 @@ __global__ void __launch_bounds__(32) match_kernel(const MatchArgs a, int ms, in
 
   // ---- cost block
   const size_t q0 = (static_cast<size_t>(layer) * a.B + video) * a.Q + static_cast<size_t>(local) * nrows;
-  float* Cg = a.cost_ws ? a.cost_ws + static_cast<size_t>(layer) * a.cost_off[P] + a.cost_off[p] : nullptr;   // nrows x ncols
+  float* Cg = a.cost_ws ? a.cost_ws + static_cast<size_t>(layer) * a.cost_off[P] + a.cost_off[p] : nullptr;
+  const bool ws_working = cost_smem_floats == 0;  // workspace blocks in working orientation (see above)
   bool bad = false;
   if (a.mode != 2) {
-    // entries visited in working order (conflict-free shared-memory stores)
-    for (int e = lane; e < nr * nc; e += 32) {
+    for (int r = tid; r < nrows; r += MATCH_THREADS) {
+      const float2 lg = reinterpret_cast<const float2*>(a.logits)[q0 + r];
+      qs[r] = fg_prob(lg.x, lg.y);
+      box_derive(reinterpret_cast<const float4*>(a.boxes)[q0 + r], qs + qp + r, qp);
+    }
+    for (int c = tid; c < ncols; c += MATCH_THREADS)
+      box_derive(reinterpret_cast<const float4*>(a.tgt_boxes)[t0 + c], ts + c, tp);
+    if (MATCH_THREADS > 32) __syncthreads(); else __syncwarp();
+    // entries visited in working order (conflict-free shared-memory stores, coalesced workspace stores)
+    for (int e = tid; e < nr * nc; e += MATCH_THREADS) {
       const int i = e / nc, j = e - i * nc;
       const int r = transposed ? j : i, c = transposed ? i : j;
-      const float2 lg = reinterpret_cast<const float2*>(a.logits)[q0 + r];
-      const float4 pb = reinterpret_cast<const float4*>(a.boxes)[q0 + r];
-      const float4 tb = reinterpret_cast<const float4*>(a.tgt_boxes)[t0 + c];
-      const Box pa{pb.x, pb.y, pb.z, pb.w}, ta{tb.x, tb.y, tb.z, tb.w};
-      const float cost = pair_cost(fg_prob(lg.x, lg.y), pa, ta, a.w_class, a.w_bbox, a.w_giou);
+      const float cost = staged_cost(qs, qp, r, ts, tp, c, a.w_class, a.w_bbox, a.w_giou);
       bad |= (cost != cost) || (cost == -CUDART_INF_F);
-      if (Cg) Cg[r * ncols + c] = cost;
+      if (Cg) Cg[ws_working ? e : r * ncols + c] = cost;
       if (cost_in_smem) Cs[e] = cost;
     }
     if (a.mode == 1) return;
   } else {
-    for (int e = lane; e < nr * nc; e += 32) {
+    for (int e = tid; e < nr * nc; e += MATCH_THREADS) {
       const int i = e / nc, j = e - i * nc;
-      const float cost = Cg[transposed ? j * ncols + i : e];
+      const float cost = Cg[(ws_working || !transposed) ? e : j * ncols + i];
       bad |= (cost != cost) || (cost == -CUDART_INF_F);
       if (cost_in_smem) Cs[e] = cost;
     }
   }
-  if (__any_sync(0xffffffffu, bad)) {      // scipy: "matrix contains invalid numeric entries"
+  bool any_bad;
+  if (MATCH_THREADS > 32) {
+    any_bad = __syncthreads_or(bad);
+    if (warp != 0) return;                 // the assignment itself is one warp's sequential work
+  } else {
+    any_bad = __any_sync(0xffffffffu, bad);
+    __syncwarp();
+  }
+  if (any_bad) {                           // scipy: "matrix contains invalid numeric entries"
     if (lane == 0) atomicOr(status_acc, 1);
     safe_indices();
     return;
   }
-  __syncwarp();
 
-  // a block that does not fit in shared memory is read in place from the workspace (original orientation: a tall
-  // problem's working entry (i, j) is the block's entry (j, i))
-  const int rc = cost_in_smem ? lsap_dispatch(Cs, nc, 1, nr, nc, s, lane, a.solver == 1)
-                              : lsap_dispatch(Cg, transposed ? 1 : ncols, transposed ? ncols : 1, nr, nc, s, lane, a.solver == 1);
+  const int rc = lsap_dispatch(cost_in_smem ? Cs : Cg, nc, 1, nr, nc, s, lane, a.solver == 1);
   if (rc != 0) {                           // infeasible: every candidate +inf
     if (lane == 0) atomicOr(status_acc, 2);
     safe_indices();
@@ -414,8 +486,9 @@ static int match_smem(const MatchArgs& a, int* ms_out, int* mb_out, int* cost_fl
   const int max_small = a.rows_per_problem < a.max_cols ? a.rows_per_problem : a.max_cols;
   const int max_big = a.rows_per_problem > a.max_cols ? a.rows_per_problem : a.max_cols;
   const int ms = (max_small + 1) & ~1, mb = (max_big + 1) & ~1;     // keep the int arrays 8-byte aligned
-  const size_t smem_solver = lsap_smem_bytes(ms, mb);
-  if (smem_solver > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "match: problem too large for one warp's shared memory");
+  const size_t smem_solver = lsap_smem_bytes(ms, mb) +
+      sizeof(float) * (QF * ((a.rows_per_problem + 3) & ~3) + TF * ((a.max_cols + 3) & ~3));     // + staged boxes
+  if (smem_solver > 120 * 1024) return svol_fail(SVOL_ERR_SHAPE, "match: problem too large for one CTA's shared memory");
   // cost block in shared memory when it fits next to the solver state (<= 96 KB keeps >= 2 problems resident per SM)
   const size_t cost_bytes = static_cast<size_t>(a.rows_per_problem) * static_cast<size_t>(a.max_cols) * sizeof(float);
   const bool fits = cost_bytes <= 96 * 1024 && smem_solver + cost_bytes <= 200 * 1024;
@@ -440,14 +513,26 @@ int launch_match(const MatchArgs& a, cudaStream_t stream) {
   int ms, mb, cost_floats;
   size_t smem;
   if (int rc = match_smem(a, &ms, &mb, &cost_floats, &smem)) return rc;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return svol_fail_cuda(e, "match: cudaFuncSetAttribute");
-    configured = smem;
-  }
   const int P = a.B * a.problems_per_video;
-  match_kernel<<<a.NL * P, 32, smem, stream>>>(a, ms, mb, cost_floats);
+  // width of a CTA: one warp for tiny blocks; two when there are many problems (the solver's ~128 registers per thread are
+  // allocated for every thread of the CTA, so more fill warps would cut the number of resident solvers); four otherwise
+  const long long entries = static_cast<long long>(a.rows_per_problem) * a.max_cols;
+  const int threads = entries <= 512 ? 32 : (static_cast<long long>(a.NL) * P >= 4LL * sm_count() ? 64 : 128);
+  auto launch = [&](auto kernel, size_t* configured) -> int {
+    if (smem > 48 * 1024 && smem > *configured) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return svol_fail_cuda(e, "match: cudaFuncSetAttribute");
+      *configured = smem;
+    }
+    kernel<<<a.NL * P, threads, smem, stream>>>(a, ms, mb, cost_floats);
+    return SVOL_OK;
+  };
+  static size_t conf32 = 0, conf64 = 0, conf128 = 0;
+  int lrc;
+  if (threads == 32) lrc = launch(match_kernel<32>, &conf32);
+  else if (threads == 64) lrc = launch(match_kernel<64>, &conf64);
+  else lrc = launch(match_kernel<128>, &conf128);
+  if (lrc) return lrc;
   if (int rc = svol_check_launch("match")) return rc;
   if (a.mode == 1) return SVOL_OK;
   match_finalize_kernel<<<a.NL * a.B, 32, 0, stream>>>(a.tgt_idx, a.video_match_off, a.video_tgt_off, a.status, a.B,
@@ -503,16 +588,15 @@ __global__ void __launch_bounds__(32) lsap_kernel(const float* __restrict__ cost
   lsap_emit(transposed, nr, nc, s, lane, [&](int k, int r, int c) { ro[k] = r; co[k] = c; });
 }
 
-int launch_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int n_problems, int max_rows,
-                    int max_cols, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off, int32_t* status, int solver,
-                    cudaStream_t stream) {
-  if (n_problems <= 0 || max_rows <= 0 || max_cols <= 0 || solver < 0 || solver > 1)
-    return svol_fail(SVOL_ERR_SHAPE, "lsap: n_problems, max_rows, max_cols > 0; solver in 0..1");
-  const int small = max_rows < max_cols ? max_rows : max_cols, big = max_rows > max_cols ? max_rows : max_cols;
-  const int ms = (small + 1) & ~1, mb = (big + 1) & ~1;
-  const size_t cost_bytes = static_cast<size_t>(max_rows) * max_cols * sizeof(float);
+int launch_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int n_problems, int max_small,
+                    int max_big, int max_entries, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off, int32_t* status,
+                    int solver, cudaStream_t stream) {
+  if (n_problems <= 0 || max_small <= 0 || max_big < max_small || max_entries <= 0 || solver < 0 || solver > 1)
+    return svol_fail(SVOL_ERR_SHAPE, "lsap: n_problems, max_small <= max_big, max_entries > 0; solver in 0..1");
+  const int ms = (max_small + 1) & ~1, mb = (max_big + 1) & ~1;
+  const size_t cost_bytes = static_cast<size_t>(max_entries) * sizeof(float);
   const size_t smem = lsap_smem_bytes(ms, mb) + cost_bytes;
-  if (smem > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "lsap: max_rows * max_cols * 4 bytes must fit in shared memory");
+  if (smem > 200 * 1024) return svol_fail(SVOL_ERR_SHAPE, "lsap: max_entries * 4 bytes must fit in shared memory");
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -520,7 +604,7 @@ int launch_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* s
     configured = smem;
   }
   lsap_kernel<<<n_problems, 32, smem, stream>>>(cost, cost_off, shape, rows_out, cols_out, out_off, status, ms, mb,
-                                                max_rows * max_cols, solver);
+                                                max_entries, solver);
   return svol_check_launch("lsap");
 }
 

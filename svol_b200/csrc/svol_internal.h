@@ -34,8 +34,8 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream);
 int launch_attention_plain(const AttnArgs& a, cudaStream_t stream);
 int launch_match(const MatchArgs& a, cudaStream_t stream);
 int launch_match_localize(int64_t* tgt_idx, const int32_t* video_match_off, int NL, int B, int K, cudaStream_t stream);
-int launch_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int n_problems, int max_rows,
-                    int max_cols, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off, int32_t* status, int solver,
+int launch_lsap_f32(const float* cost, const int64_t* cost_off, const int32_t* shape, int n_problems, int max_small,
+                    int max_big, int max_entries, int64_t* rows_out, int64_t* cols_out, const int64_t* out_off, int32_t* status, int solver,
                     cudaStream_t stream);
 int launch_criterion(const CriterionArgs& a, cudaStream_t stream);
 int launch_criterion_backward(const CriterionArgs& a, const float* grad_w, float* grad_logits, float* grad_boxes,

@@ -38,6 +38,8 @@ class _Workspace:
         self.tgt_idx = torch.zeros((NL, s_cap), device=dev, dtype=torch.int64)
         self.status = torch.zeros(2, device=dev, dtype=torch.int32)                   # zeroed ONCE; then owned by the kernels
         self.losses = torch.zeros((NL, 4), device=dev, dtype=torch.float32)
+        # criterion partial sums + arrival counters (zeroed once; the kernels reset the counters themselves)
+        self.scratch = torch.zeros(int(_lib.get_lib().svol_criterion_scratch_bytes(NL, B)), device=dev, dtype=torch.uint8)
         self.cost_ws = None
         if self.rows * cols_cap * 4 > COST_SMEM_LIMIT:        # blocks too large for shared memory: solved from HBM
             self.cost_ws = torch.empty((NL, self.rows * s_cap), device=dev, dtype=torch.float32)
@@ -72,6 +74,7 @@ class _Workspace:
         a.losses = self.losses.data_ptr()
         a.NL, a.B, a.Q, a.K, a.idx_pitch = self.NL, self.B, self.Q, 0, self.s_cap
         a.eos_coef = self.eos_coef
+        a.scratch = self.scratch.data_ptr()
         self.bound = key
 
     def launch(self, stream: int) -> None:

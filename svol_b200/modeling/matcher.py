@@ -34,6 +34,7 @@ def fill_match_args(a, logits, boxes, src, NL, B, Q, K_pitch, ppv, rows, max_col
     # global -> video-local target indices inside the call's finalize kernel.  PerFrameMatcher subtracts the minimum
     # matched global index (matcher.py:114-115); HungarianMatcher's columns are local to the video's split (:158).
     a.mode, a.solver, a.localize = mode, solver, (1 if per_frame else 2)
+    a.order = g("order").data_ptr()            # problems with the most targets first
     return a
 
 

@@ -34,6 +34,7 @@ class FlatTargets:
     h_video_match_off: np.ndarray
     per_frame: bool
     meta: torch.Tensor = None    # [4] i32 on the device: K, S, max_cols, P
+    order: torch.Tensor = None   # [P] i32: problems sorted by number of targets, descending (launch order of svol_match)
     packed: torch.Tensor = None  # the whole packed buffer (uint8, device); [0, n_static) = everything but match_video
     n_fixed: int = 0             # bytes in front of the boxes: a function of (P, B) only
     n_static: int = 0            # n_fixed + 16 * S
@@ -72,7 +73,7 @@ class PackedTargets(list):
 
 def _pack_host(targets: Sequence[dict], per_frame: bool, num_frames: int, num_queries: int, q_per_frame: int):
     """Nested targets -> (packed uint8 numpy buffer, meta).  Layout: [cost_off i64 | tgt_off, match_off, video_tgt_off,
-    video_match_off, (K, S, max_cols, P) i32 | boxes f32 | match_video i32], sections 16-byte aligned.  Everything in
+    video_match_off, (K, S, max_cols, P), order i32 | boxes f32 | match_video i32], sections 16-byte aligned.  Everything in
     front of the boxes has a size that depends on (P, B) only, so a consumer with a static device copy of this buffer
     (the criterion's captured launch sequence, loss.py) finds every array at a fixed address for every batch."""
     boxes, per_video, per_frame_counts = _walk(targets)
@@ -98,7 +99,8 @@ def _pack_host(targets: Sequence[dict], per_frame: bool, num_frames: int, num_qu
     match_video = np.repeat(np.arange(B, dtype=np.int32), np.diff(video_match_off))
     S = int(boxes.shape[0])
     max_cols = int(cols.max())
-    ints = np.concatenate([tgt_off, match_off, video_tgt_off, video_match_off, [K, S, max_cols, P]]).astype(np.int32)
+    order = np.argsort(-cols, kind="stable")                 # largest problems first (svol_match's launch order)
+    ints = np.concatenate([tgt_off, match_off, video_tgt_off, video_match_off, [K, S, max_cols, P], order]).astype(np.int32)
     n_cost = ((P + 1) * 8 + 15) // 16 * 16                                           # sections stay 16-byte aligned
     n_fixed = n_cost + (ints.shape[0] * 4 + 15) // 16 * 16
     n_box = S * 16
@@ -167,19 +169,20 @@ def flatten_targets(targets: Sequence[dict], device, per_frame: bool, num_frames
         tgt_boxes=d_box, tgt_off=d_int[:n1], match_off=d_int[n1:n2],
         cost_off=d_cost, video_tgt_off=d_int[n2:n3], video_match_off=d_int[n3:n4],
         match_video=dbuf[n_fixed + n_box:].view(torch.int32), h_video_match_off=meta["video_match_off"],
-        per_frame=meta["per_frame"], meta=d_int[n4:n4 + 4], packed=dbuf, n_fixed=n_fixed, n_static=n_fixed + n_box)
+        per_frame=meta["per_frame"], meta=d_int[n4:n4 + 4], order=d_int[n4 + 4:n4 + 4 + P], packed=dbuf, n_fixed=n_fixed,
+        n_static=n_fixed + n_box)
 
 
 def static_views(buf: torch.Tensor, P: int, B: int):
     """The arrays of a packed target buffer that sit at addresses fixed by (P, B): a static device copy ``buf`` (uint8,
     at least FlatTargets.n_static bytes) keeps them valid for every batch copied into it."""
     n_cost = ((P + 1) * 8 + 15) // 16 * 16
-    n_int = 2 * (P + 1) + 2 * (B + 1) + 4
+    n_int = 2 * (P + 1) + 2 * (B + 1) + 4 + P
     n_fixed = n_cost + (n_int * 4 + 15) // 16 * 16
     ints = buf[n_cost:n_fixed].view(torch.int32)
     n1, n2, n3, n4 = P + 1, 2 * (P + 1), 2 * (P + 1) + B + 1, 2 * (P + 1) + 2 * (B + 1)
     return dict(cost_off=buf[:(P + 1) * 8].view(torch.int64), tgt_off=ints[:n1], match_off=ints[n1:n2],
-                video_tgt_off=ints[n2:n3], video_match_off=ints[n3:n4], meta=ints[n4:n4 + 4],
+                video_tgt_off=ints[n2:n3], video_match_off=ints[n3:n4], meta=ints[n4:n4 + 4], order=ints[n4 + 4:n4 + 4 + P],
                 tgt_boxes=buf[n_fixed:], n_fixed=n_fixed)
 
 

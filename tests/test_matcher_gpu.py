@@ -131,7 +131,8 @@ def _lsap_gpu(costs, solver):
     cols = torch.full_like(rows, -7)
     status = torch.full((len(costs),), -1, device=DEV, dtype=torch.int32)
     _lib.check(_lib.get_lib().svol_lsap_f32(d_cost.data_ptr(), d_off.data_ptr(), d_shape.data_ptr(), len(costs),
-                                            int(shapes[:, 0].max()), int(shapes[:, 1].max()), rows.data_ptr(), cols.data_ptr(),
+                                            int(shapes.min(axis=1).max()), int(shapes.max(axis=1).max()),
+                                            int((shapes[:, 0] * shapes[:, 1]).max()), rows.data_ptr(), cols.data_ptr(),
                                             d_out_off.data_ptr(), status.data_ptr(), solver, _lib.stream_ptr()), "lsap")
     torch.cuda.synchronize()
     return rows.cpu().numpy(), cols.cpu().numpy(), status.cpu().numpy(), out_off
