@@ -389,25 +389,35 @@ def main():
             ev_copied[slot].record(copy_stream)
 
     def run_e2e(steps):
+        # step i runs on step stream i & 1 (its own forward workspace / criterion workspace, like the resident loop): the
+        # low-occupancy tail of one step overlaps the head of the next, and with bf16 features the loop is no longer bound by
+        # one stream's device time
         main = torch.cuda.current_stream()
+        lanes = step_streams if step_streams is not None and len(step_streams) == 2 else [main, main]
+        for st_ in set(lanes):
+            st_.wait_stream(main)
         h2d(0)
         for i in range(steps):
             slot = i & 1
             if i + 1 < steps:
                 h2d(i + 1)
-            main.wait_event(ev_copied[slot])
-            st = e2e_cfg["stages"][slot]
-            criterion.matcher._cache._key = None                       # new targets every step: host walk + H2D
-            out = model(st["src_sketch"], st["src_sketch_mask"], st["src_video"], st["src_video_mask"])
-            losses = criterion(out, sets[i & 1]["targets"])
-            vals = torch.stack([losses[k] for k in losses])
-            loss_host[slot].view(-1)[: vals.numel()].copy_(vals, non_blocking=True)    # D2H of the step's result
-            ev_done[slot].record(main)
+            lane = lanes[slot]
+            with torch.cuda.stream(lane):
+                lane.wait_event(ev_copied[slot])
+                st = e2e_cfg["stages"][slot]
+                criterion.matcher._cache._key = None                   # new targets every step: host walk + H2D
+                out = model(st["src_sketch"], st["src_sketch_mask"], st["src_video"], st["src_video_mask"])
+                losses = criterion(out, sets[i & 1]["targets"])
+                vals = torch.stack([losses[k] for k in losses])
+                loss_host[slot].view(-1)[: vals.numel()].copy_(vals, non_blocking=True)    # D2H of the step's result
+                ev_done[slot].record(lane)
             if i > 0:
                 ev_done[slot ^ 1].synchronize()                        # host consumes the previous step's losses
                 e2e_sink.append(float(loss_host[slot ^ 1][0, 0]))
         ev_done[(steps - 1) & 1].synchronize()
         e2e_sink.append(float(loss_host[(steps - 1) & 1][0, 0]))
+        for st_ in set(lanes):
+            main.wait_stream(st_)
 
     def barrier():
         if world > 1:

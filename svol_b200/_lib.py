@@ -209,12 +209,18 @@ def check(rc: int, what: str = "") -> None:
         raise RuntimeError(f"svol_b200 {what} failed (code {rc}): {msg}")
 
 
+_device_ok = set()
+
+
 def require_device() -> None:
-    """Fails loudly unless the current CUDA device can run the sm_100a kernels."""
+    """Fails loudly unless the current CUDA device can run the sm_100a kernels (checked once per device)."""
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("svol_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    check(get_lib().svol_device_check(), "device check")
+    dev = torch._C._cuda_getDevice()
+    if dev not in _device_ok:
+        check(get_lib().svol_device_check(), "device check")
+        _device_ok.add(dev)
 
 
 def ptr(t) -> Optional[int]:
@@ -222,5 +228,7 @@ def ptr(t) -> Optional[int]:
 
 
 def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw C call: torch.cuda.current_stream() builds
+    a Python Stream object and resolves the device index through several layers, ~8 us per call)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())

@@ -124,6 +124,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #ifndef SVOL_ATTN_POLY_PER4
 #define SVOL_ATTN_POLY_PER4 0
 #endif
+#ifndef SVOL_ATTN_POLY_PAIRS
+#define SVOL_ATTN_POLY_PAIRS 0      // of every four pairs of probabilities, this many use the packed polynomial (ex2_poly2).
+// EXPERIMENT, off by default.  Measured on B200 (video self / cross / query self-attention, us per launch, kernels alone):
+// 0: 262.7 / 72.3 / 30.0;  1: 265.7 / 76.8 / 29.7;  2: 293.3 / 82.6 / 31.9 -- a quarter fewer MUFU operations at 4 packed issue
+// slots per probability buys nothing: the key-tile period is set by the four warps' serial chains queueing on the shared
+// pipes, not by MUFU or issue throughput.
+#endif
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -126.f);                                   // also maps masked scores (-inf) to 2^-126 ~ 0
   const float t = __fadd_rn(x, 12582912.f);               // 1.5 * 2^23: round(x) lands in the low mantissa bits
@@ -176,6 +183,33 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// Two probabilities 2^(s - m) on the FMA pipe with PACKED f32x2 instructions (add.f32x2 / fma.rn.f32x2): Cody-Waite split
+// n = round(x), r = x - n in [-0.5, 0.5], degree-3 minimax polynomial for 2^r (max relative error 1.5e-4, an order of magnitude
+// below the bf16 rounding of P), 2^n added into the exponent field.  3 packed adds + 3 packed FMAs + 2 integer ops for two
+// values: 4 issue slots per probability instead of 9 for the scalar form above -- what makes moving a quarter of the
+// exponentials off the MUFU pipe pay (the kernel is MUFU-bound at 8 clk per warp instruction but uses ~60 % of its issue
+// slots).  Requires finite s - m > -126 (not used on tiles with masked keys).
+//   magic_m = 1.5 * 2^23 - m (both lanes), neg_m = -m.
+__device__ __forceinline__ float2 ex2_poly2(float2 sc, float2 magic_m, float2 neg_m) {
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = __fadd2_rn(sc, magic_m);                         // x + magic: round(x) lands in the low mantissa bits
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 x = __fadd2_rn(sc, neg_m);
+  const float2 r = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  (void)magic;
+  float2 p = __ffma2_rn(make_float2(0.055170271545648575f, 0.055170271545648575f), r, make_float2(0.2426079511642456f, 0.2426079511642456f));
+  p = __ffma2_rn(p, r, make_float2(0.693260908126831f, 0.693260908126831f));
+  p = __ffma2_rn(p, r, make_float2(0.9999282956123352f, 0.9999282956123352f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
 // Row maximum of the 64 scores a thread holds; kMasked additionally overwrites invalid keys with -inf.
 template <bool kMasked>
 __device__ __forceinline__ float half_row_max(uint32_t (&s)[attn::HALF], const uint32_t (&words)[2]) {
@@ -186,13 +220,16 @@ __device__ __forceinline__ float half_row_max(uint32_t (&s)[attn::HALF], const u
       for (int i = 0; i < 32; ++i)
         if (!((words[c] >> i) & 1u)) s[c * 32 + i] = 0xff800000u;   // -inf
   }
+  // three-input maxima (FMNMX3 on sm_100): 32 instructions for 64 scores instead of 64
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < attn::HALF; i += 4) {
-    m0 = fmaxf(m0, __uint_as_float(s[i + 0])); m1 = fmaxf(m1, __uint_as_float(s[i + 1]));
-    m2 = fmaxf(m2, __uint_as_float(s[i + 2])); m3 = fmaxf(m3, __uint_as_float(s[i + 3]));
+  for (int i = 0; i < attn::HALF; i += 8) {
+    m0 = fmax3(m0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+    m1 = fmax3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+    m2 = fmax3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+    m3 = fmax3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
   }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  return fmax3(fmaxf(m0, m1), m2, m3);
 }
 
 // kLse: the training forward also stores each row's base-2 log-sum-exp (a separate instantiation so that the inference
@@ -463,6 +500,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // of the reference maximum and the row sum are packed FADD2s
         const float2 neg_m = make_float2(-m_use, -m_use);
         float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+        if (SVOL_ATTN_POLY_PAIRS > 0 && !masked) {
+          // unmasked tile: SVOL_ATTN_POLY_PAIRS of every four pairs go through the packed FMA-pipe polynomial
+          const float2 magic_m = make_float2(12582912.f - m_use, 12582912.f - m_use);
+#pragma unroll
+          for (int i = 0; i < HALF; i += 8) {
+            float2 p[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 sc = make_float2(__uint_as_float(s[i + 2 * k]), __uint_as_float(s[i + 2 * k + 1]));
+              if (k >= 4 - SVOL_ATTN_POLY_PAIRS) {
+                p[k] = ex2_poly2(sc, magic_m, neg_m);
+              } else {
+                const float2 x = __fadd2_rn(sc, neg_m);
+                p[k] = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+              }
+            }
+            la = __fadd2_rn(la, __fadd2_rn(p[0], p[1]));
+            lb = __fadd2_rn(lb, __fadd2_rn(p[2], p[3]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[(i >> 1) + k] = pack_bf16x2(p[k].x, p[k].y);
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < HALF; i += 4) {
           const float2 x0 = __fadd2_rn(make_float2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), neg_m);
@@ -473,6 +532,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           lb = __fadd2_rn(lb, p1);
           s[i >> 1] = pack_bf16x2(p0.x, p0.y);
           s[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+        }
         }
         l2 = __fadd2_rn(l2, __fadd2_rn(la, lb));
         SVOL_TR(g, i, 5);

@@ -57,7 +57,7 @@ struct GemmSmemTail {
   uint64_t empty[gemm::MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t w_full;
+  uint64_t w_full[gemm::RES_KB];     // resident weights: one barrier per 64-wide k block, so the first MMAs start after 32 KB, not 128
   uint32_t tmem_base;
   uint32_t pad;
 };
@@ -200,7 +200,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tail->tmem_full[s], 1); mbar_init(&tail->tmem_empty[s], EPI_WARPS); }
-    mbar_init(&tail->w_full, 1);
+    for (int kb = 0; kb < RES_KB; ++kb) mbar_init(&tail->w_full[kb], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&tail->tmem_base);
@@ -228,16 +228,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
    if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      if (kResidentW && my_tiles > 0) {
-        mbar_arrive_expect_tx(&tail->w_full, C::W_BYTES);
-        for (int kb = 0; kb < RES_KB; ++kb) tma_load_2d(smem + kb * B_BYTES, &tmB, &tail->w_full, kb * BK, my_n * BN);
-      }
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         int m_blk, n_blk, kb0, kb1;
         tile_coords(it, m_blk, n_blk);
         k_range(it, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (kResidentW && it == 0) {      // this CTA's weight block, k block by k block, interleaved with the first A tiles
+            mbar_arrive_expect_tx(&tail->w_full[kb], B_BYTES);
+            tma_load_2d(smem + kb * B_BYTES, &tmB, &tail->w_full[kb], kb * BK, my_n * BN);
+          }
           mbar_wait(&tail->empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&tail->full[stage], C::STAGE_BYTES);
           uint8_t* sa = stages + stage * C::STAGE_BYTES;
@@ -259,7 +259,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       int stage = 0; uint32_t phase = 0;
-      if (kResidentW && my_tiles > 0) mbar_wait(&tail->w_full, 0);
       for (int it = 0; it < my_tiles; ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -271,6 +270,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int kb0, kb1;
         k_range(it, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (kResidentW && it == 0) mbar_wait(&tail->w_full[kb], 0);
           mbar_wait(&tail->full[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(stages + stage * C::STAGE_BYTES);

@@ -151,6 +151,7 @@ class HeadEngine:
         self.plain = os.environ.get("SVOL_B200_PLAIN", "0") == "1"   # debug: SIMT kernels instead of tcgen05
         self._w: Dict[str, torch.Tensor] = {}
         self._wstate = None
+        self._plist = None
         self.weights_generation = 0        # bumped by every repack: consumers of derived copies (TrainEngine's W^T) compare it
         self._packer = WeightPacker()
         self._plans: Dict[Tuple[int, int, int, int], _Plan] = {}
@@ -159,7 +160,15 @@ class HeadEngine:
 
     # ------------------------------------------------------------------ weights
     def _param_state(self):
-        return tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+        """Cheap change signature of the module's parameters (this runs on every forward: walking module.parameters() and
+        calling data_ptr() on each of the ~100 tensors cost 0.17 ms per step, most of the host's enqueue time).  In-place
+        updates (optimizers, load_state_dict) bump ``_version``; ``.to()`` / ``.cuda()`` move every storage, the first and the
+        last included; FusedAdamW, which updates through a raw pointer, resets ``_wstate`` explicitly.  The Parameter list
+        itself is re-read whenever the state was reset."""
+        if self._wstate is None or self._plist is None:
+            self._plist = list(self.module.parameters())
+        ps = self._plist
+        return (ps[0].data_ptr(), ps[-1].data_ptr(), tuple([p._version for p in ps]))
 
     @torch.no_grad()
     def _pack_weights(self) -> None:
@@ -483,7 +492,7 @@ class HeadEngine:
         keeps two batches in flight on two streams gets two independent workspaces, so the low-occupancy tail of one
         forward (the object-query chain, the heads) overlaps the large frame-token kernels of the next."""
         self._weights()
-        key = (B, L, d_in, torch.cuda.current_stream().cuda_stream if torch.cuda.is_available() else 0)
+        key = (B, L, d_in, _lib.stream_ptr())
         plan = self._plans.get(key)
         if plan is None:
             plan = self._build_plan(B, L, d_in)
@@ -537,12 +546,12 @@ class HeadEngine:
         name, fn, args = plan.calls[0]
         if fmap:   # LayerNorm straight from the channel-major feature map: no permuted fp32 copy
             rc = _lib.get_lib().svol_layernorm_nchw_to_bf16(src.data_ptr(), args[1], args[2], args[3], B * T, d_in, fh * fw, LN_EPS,
-                                                            torch.cuda.current_stream().cuda_stream)
+                                                            _lib.stream_ptr())
         elif bf16_in:
             rc = _lib.get_lib().svol_layernorm_bf16_to_bf16(src.data_ptr(), args[1], args[2], args[3], B * L, d_in, LN_EPS,
-                                                            torch.cuda.current_stream().cuda_stream)
+                                                            _lib.stream_ptr())
         else:
-            rc = fn(src.data_ptr(), *args[1:], torch.cuda.current_stream().cuda_stream)
+            rc = fn(src.data_ptr(), *args[1:], _lib.stream_ptr())
         if rc != 0:
             _lib.check(rc, name)
         self.run_plan(plan)
@@ -563,14 +572,14 @@ class HeadEngine:
             attr, start = ("graph_full", 0) if full else ("graph", 1)
             if getattr(plan, attr) is None:
                 # warm-up run outside capture (sets function attributes, loads modules)
-                plan.run(torch.cuda.current_stream().cuda_stream, start=start)
+                plan.run(_lib.stream_ptr(), start=start)
                 torch.cuda.synchronize()
                 if self._side is None:
                     self._side = (torch.cuda.Stream(), torch.cuda.Stream())
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    plan.run(torch.cuda.current_stream().cuda_stream, start=start, side=self._side)
+                    plan.run(_lib.stream_ptr(), start=start, side=self._side)
                 setattr(plan, attr, g)
             getattr(plan, attr).replay()
         else:
-            plan.run(torch.cuda.current_stream().cuda_stream, start=1)
+            plan.run(_lib.stream_ptr(), start=1)

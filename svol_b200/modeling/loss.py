@@ -94,7 +94,7 @@ class _Workspace:
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.launch(torch.cuda.current_stream().cuda_stream)
+                self.launch(_lib.stream_ptr())
             self.graph, self.graph_key = g, self.bound
         self.graph.replay()
 
@@ -180,7 +180,7 @@ class SetCriterion(nn.Module):
 
     def _workspace(self, logits, flat) -> _Workspace:
         NL, B, Q = logits.shape[:3]
-        key = (logits.device, torch.cuda.current_stream().cuda_stream, NL, B, Q)
+        key = (logits.device, _lib.stream_ptr(), NL, B, Q)
         ws = self._ws.get(key)
         if ws is None or not ws.fits(flat) or ws.eos_coef != float(self.eos_coef) or \
                 ws.weights != (self.matcher.cost_class, self.matcher.cost_bbox, self.matcher.cost_giou):

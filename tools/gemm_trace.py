@@ -23,6 +23,8 @@ if which == "gemm_ffn_up":
     K, N, kw = d, ff, dict(act=ops.ACT_GELU)
 elif which == "gemm_ffn_down":
     K, N, kw = ff, d, dict(residual=True, ln=True, pos=True)
+elif which == "gemm_sa_out":            # attention output projection + residual + LayerNorm (cross_modal_transformer.py:140-141)
+    K, N, kw = d, d, dict(residual=True, ln=True)
 else:
     K, N, kw = d, 2 * d, dict()
 A = rnd(M, K).to(torch.bfloat16).to(dev)
@@ -31,9 +33,16 @@ bias = rnd(N).to(dev)
 res = rnd(M, N).to(torch.bfloat16).to(dev) if kw.pop("residual", False) else None
 ln = (torch.ones(N, device=dev), torch.zeros(N, device=dev)) if kw.pop("ln", False) else None
 pos = rnd(M, N).to(dev) if kw.pop("pos", False) else None
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 for _ in range(3):
+    if os.environ.get("SVOL_TRACE_COLD", "1") == "1":
+        flush.zero_()                     # operands come from HBM, as they do inside the step
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     ops.gemm(A, W, bias, residual=res, ln=ln, pos=pos, **kw)
+    e1.record()
 torch.cuda.synchronize()
+print(f"{which}: M={M} N={N} K={K}: {e0.elapsed_time(e1) * 1e3:.1f} us (last launch, events)")
 buf = np.zeros((2, 32, 8), dtype=np.int64)
 rc = _lib.get_lib().svol_debug_gemm_trace(C.c_void_p(buf.ctypes.data))
 assert rc == 0
