@@ -36,18 +36,15 @@ class LinearLayer(nn.Module):
 class _HeadTrainFn(torch.autograd.Function):
     """Training-mode forward / backward of the head as ONE autograd node, so that the reference's
     ``loss.backward()`` (train.py:229) drives the CUDA backward plan.  Inputs after the four data tensors are the
-    module's parameters (their gradients are the node's outputs); the frame features get no gradient (the
-    backbone hand-off is outside this path)."""
+    module's parameters (their gradients are the node's outputs).  Features that require a gradient -- a backbone trained
+    through the head, as train.py:72 does -- get d(loss)/d(src_video), d(loss)/d(src_sketch) as well."""
 
     @staticmethod
     def forward(ctx, module, src_sketch, src_sketch_mask, src_video, src_video_mask, *params):
-        if src_video.requires_grad or src_sketch.requires_grad:
-            # train.py:72 optimises backbone + head; this node returns no gradient for the features, so a backbone behind
-            # them would silently stop training.  Fail loudly instead (detach the features to train the head alone).
-            raise NotImplementedError("svol_b200's head backward does not produce d/d(src_video), d/d(src_sketch): pass "
-                                      "detached features (frozen backbone / precomputed features)")
         eng = module.train_engine
-        logits, boxes = eng.forward(src_sketch, src_sketch_mask, src_video, src_video_mask)
+        ctx.want_sketch, ctx.want_video = bool(ctx.needs_input_grad[1]), bool(ctx.needs_input_grad[3])
+        ctx.sketch_shape = tuple(src_sketch.shape)
+        logits, boxes = eng.forward(src_sketch, src_sketch_mask, src_video, src_video_mask, want_input_grads=ctx.want_video)
         ctx.module, ctx.n_params, ctx.token = module, len(params), eng.forward_token
         return logits.clone(), boxes.clone()
 
@@ -56,11 +53,16 @@ class _HeadTrainFn(torch.autograd.Function):
         module = ctx.module
         eng = module.train_engine
         eng.backward(g_logits.contiguous().float(), g_boxes.contiguous().float(), token=ctx.token)
+        g_sketch = g_video = None
+        if ctx.want_video or ctx.want_sketch:
+            g_sketch, g_video = eng.input_grads()
+            g_sketch = g_sketch.view(ctx.sketch_shape) if ctx.want_sketch else None
+            g_video = g_video if ctx.want_video else None
         if not eng.publish_grads:        # fused-optimizer loop: gradients stay in eng.grad_flat (FusedAdamW.step(from_engine=True))
-            return (None,) * (5 + ctx.n_params)
+            return (None, g_sketch, None, g_video, None) + (None,) * ctx.n_params
         unused = {id(p) for p in module.params_without_grad()}            # None in the reference's autograd too
         grads = [eng.grad_of(p) if (p.requires_grad and id(p) not in unused) else None for p in module.parameters()]
-        return (None, None, None, None, None, *grads)
+        return (None, g_sketch, None, g_video, None, *grads)
 
 
 class SVANet(nn.Module):

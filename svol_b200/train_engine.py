@@ -124,7 +124,7 @@ class TrainEngine:
         return w
 
     # ------------------------------------------------------------------ plans
-    def _build(self, B: int, L: int, d_in: int) -> dict:
+    def _build(self, B: int, L: int, d_in: int, want_dx: bool = False) -> dict:
         m, w, wt = self.module, self.head._w, self._wt
         lib = _lib.get_lib()
         dev = w["cls.w"].device
@@ -364,6 +364,9 @@ class TrainEngine:
         gv_ff = buf("gv_ff", (M, ff), bf)
         gv_qk = buf("gv_qk", (M, 2 * d), bf)
         gv_in = buf("gv_in", (M, d_in), bf)
+        # d(loss)/d(src_video): only when the caller's frame features require a gradient (a backbone trained through the
+        # head, train.py:72): the input LayerNorm's backward then also writes dx (51 MB of bf16 at the headline shape)
+        dx_in = buf("dx_in", (M, d_in), bf) if want_dx else None
         dOT_v = buf("dOT_v", (B * d, Lp), bf, fill=0)
         dOT_q = buf("dOT_q", (B * d, Qp), bf, fill=0)
         delta_v = buf("delta_v", (B, H, Ls), f32, fill=0)
@@ -495,7 +498,7 @@ class TrainEngine:
         ln_bwd("in_ln1_bwd", a0, dxn1, w["in_video.1.ln_w"], vp[1].LayerNorm, da0, site=1)
         bcall("in_relu_bwd", lib.svol_act_backward, P(da0), P(a0), P(da0), M * d, ACT_RELU)
         linear_bwd("in_proj0", da0, xn0, G(vp[0].net[1].weight), G(vp[0].net[1].bias), wT=wt["in_video.0.wT"], dX=gv_in)
-        ln_bwd("in_ln0_bwd", x_in, gv_in, w["in_video.0.ln_w"], vp[0].LayerNorm, None, z_f32=True, cols=d_in, site=0)
+        ln_bwd("in_ln0_bwd", x_in, gv_in, w["in_video.0.ln_w"], vp[0].LayerNorm, dx_in, z_f32=True, cols=d_in, site=0)
         # ---- sketch branch
         bcall("sk_proj1_bwd", lib.svol_ln_linear_f32_backward, P(sk0), P(w["in_sketch.1.ln_w"]), P(w["in_sketch.1.ln_b"]),
               P(w["in_sketch.1.w"]), P(sk1), P(dsk1), 0, P(dsk0), P(G(sp[1].LayerNorm.weight)), P(G(sp[1].LayerNorm.bias)),
@@ -505,23 +508,24 @@ class TrainEngine:
               P(G(sp[0].net[1].weight)), P(G(sp[0].net[1].bias)), B, d_sk, d, LN_EPS, drop_p, P(seed), 2)
         return {"fwd": fwd, "bwd": bwd, "buf": bufs}
 
-    def plan_for(self, B: int, L: int, d_in: int) -> dict:
+    def plan_for(self, B: int, L: int, d_in: int, want_dx: bool = False) -> dict:
         self._setup_grads()
         self._pack_transposed()
-        key = (B, L, d_in)
+        key = (B, L, d_in, bool(want_dx))
         plan = self._plans.get(key)
         if plan is None:
-            plan = self._build(B, L, d_in)
+            plan = self._build(B, L, d_in, bool(want_dx))
             self._plans[key] = plan
         return plan
 
     # ------------------------------------------------------------------ run
     @torch.no_grad()
-    def forward(self, src_sketch, src_sketch_mask, src_video, src_video_mask):
-        """Training forward.  Returns (logits [NL,B,Q,2], boxes [NL,B,Q,4]) fp32 views of the plan's buffers."""
+    def forward(self, src_sketch, src_sketch_mask, src_video, src_video_mask, want_input_grads: bool = False):
+        """Training forward.  Returns (logits [NL,B,Q,2], boxes [NL,B,Q,4]) fp32 views of the plan's buffers.
+        ``want_input_grads``: the backward also produces d/d(src_video) (``input_grads()``)."""
         _lib.require_device()
         B, L, d_in = src_video.shape
-        plan = self.plan_for(B, L, d_in)
+        plan = self.plan_for(B, L, d_in, want_input_grads)
         b = plan["buf"]
         b["src_video"].copy_(src_video, non_blocking=True)
         if src_sketch.dim() == 3 and src_sketch.shape[1] != 1:
@@ -535,6 +539,16 @@ class TrainEngine:
         self._last = plan
         self.forward_token += 1          # identifies whose activations the plan buffers hold (see backward)
         return b["logits"], b["boxes"]
+
+    def input_grads(self):
+        """(d/d src_sketch [B, 1, D_s] fp32, d/d src_video [B, L, D_v] fp32 or None) of the most recent backward, as new
+        tensors.  The frame-feature gradient exists when the forward was run with ``want_input_grads``; like every
+        activation gradient of this backward it is computed in bf16."""
+        b = self._last["buf"]
+        B = b["src_sketch"].shape[0]
+        g_sk = b["dsk_in"].view(B, 1, -1).clone()
+        g_v = b["dx_in"].view(b["src_video"].shape).float() if "dx_in" in b else None
+        return g_sk, g_v
 
     def _run(self, plan: dict, which: str) -> None:
         """Eager on the first call of a shape (module loading, function attributes), captured on the second,
