@@ -180,8 +180,12 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (kMC) cluster_sync_all();       // the peer's barriers are initialised before any multicast traffic targets them
   const uint32_t tmem_base = bars->tmem_base;
 
+  // Register split of the 384 x 168 launch allocation: 88 for the producer / MMA-issuer warpgroup, 208 for the epilogue
+  // warps (128 x 88 + 256 x 208 = 384 x 168).  With 40 / 232 the MMA issuer's descriptors, phases and chunk counters did
+  // not fit: ptxas spilled 400 bytes, 130 local-memory instructions INSIDE the issue loop (ncu: 171 k local loads per
+  // launch) -- latency on the one thread that feeds the tensor pipe.  88 / 208: 0 bytes.
   if (warp < FIRST_EPI_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == 0) {
       // ------------------------------------------------------------------ weight producer
       if (elect_one()) {
@@ -270,7 +274,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int quarter = warp & 3;                             // TMEM lane quarter this warp may read
     const int half = (warp - FIRST_EPI_WARP) >> 2;            // which 128 of the 256 columns
     const int r = quarter * 32 + lane;                        // row inside the tile
