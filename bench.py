@@ -251,12 +251,31 @@ def run_reference_gpu(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
+    def timed_parts(steps):
+        """fp32: head forward alone and matcher + criterion alone (wall clock around a synchronised region: the
+        reference's matcher is host code -- a D2H copy of the cost matrix and one scipy call per frame)."""
+        t, tg = sets[0]
+        fwd = lambda: tp.svanet_forward(sd, t["src_sketch"], t["src_sketch_mask"], t["src_video"], t["src_video_mask"], nheads=cfg.nheads)
+        out = fwd()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fwd()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(steps):
+            tp.set_criterion(out, tg, cfg)
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        return (t1 - t0) / steps * 1e3, (t2 - t1) / steps * 1e3
+
     sampler = ClockSampler(dev.index or 0)
     steps, warmup = args.steps, max(args.warmup, 3)
     with torch.no_grad():
         sampler.start()
         ms_f32 = timed(steps, warmup)
         clocks = sampler.stop()
+        ms_fwd, ms_crit = timed_parts(steps)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             ms_bf16 = timed(steps, warmup)
         torch.backends.cuda.matmul.allow_tf32 = True
@@ -268,6 +287,7 @@ def run_reference_gpu(args):
             "variants": {"fp32": {"value": B / (ms_f32 * 1e-3), "ms_per_step": ms_f32},
                          "fp32_tf32_matmul": {"value": B / (ms_tf32 * 1e-3), "ms_per_step": ms_tf32},
                          "autocast_bf16": {"value": B / (ms_bf16 * 1e-3), "ms_per_step": ms_bf16}},
+            "parts_fp32_ms": {"head_forward": ms_fwd, "matcher_and_criterion": ms_crit},
             "what": "oracle/torch_port.py on cuda: the reference's eager ATen / scipy call sequence (pinned to the reference's "
                     "golden outputs on CPU), torch " + torch.__version__,
             "gpu": torch.cuda.get_device_name(dev)}
