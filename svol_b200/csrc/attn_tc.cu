@@ -124,6 +124,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 #ifndef SVOL_ATTN_POLY_PER4
 #define SVOL_ATTN_POLY_PER4 0
 #endif
+#ifndef SVOL_ATTN_SPEC_MAX
+#define SVOL_ATTN_SPEC_MAX 0        // fold the row maximum of tiles 1.. into the exponential loop (see the softmax loop).
+// EXPERIMENT, off by default: measured 303.8 / 82.4 / 33.7 us against 261.7 / 72.7 / 29.9 (video self / cross / query self): with
+// all 64 scores, the running maxima and the packed results live at once the loop no longer fits the 112 registers of a
+// softmax thread (140 B of spills INSIDE the key loop), which costs far more than the ~360 clk the max phase took.
+#endif
 #ifndef SVOL_ATTN_POLY_PAIRS
 #define SVOL_ATTN_POLY_PAIRS 0      // of every four pairs of probabilities, this many use the packed polynomial (ex2_poly2).
 // EXPERIMENT, off by default.  Measured on B200 (video self / cross / query self-attention, us per launch, kernels alone):
@@ -401,6 +407,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t t_p = t_lane + TMEM_P + g * 32, t_o = t_lane + TMEM_O + g * DH;
       const float* mrow = key_mask ? key_mask + static_cast<size_t>(b) * Lk : nullptr;
       float m_ref = -INFINITY;      // reference maximum the stored probabilities / O / l are relative to
+      float mx_seen = -INFINITY;    // largest row maximum seen so far (drives the lazy rescaling)
+      bool refs_finite = false;     // warp-uniform: every row of this warp has a finite reference maximum
       float2 l2 = make_float2(0.f, 0.f);
 
       // start offsets: g0, g2, g1, g3 a quarter period apart (lo before hi inside a tile, as the MMA issue order assumes)
@@ -464,17 +472,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             masked |= words[c] != 0xffffffffu;
           }
         }
-        if (masked) mx = half_row_max<true>(s, words);
-        else mx = half_row_max<false>(s, words);
-        SVOL_TR_AFTER(g, i, 3, mx);
+        // Speculative tiles (every unmasked tile after the first, once all rows have a finite reference): the exponentials
+        // below run against the CURRENT reference maximum and this tile's row maximum is folded into their loop (FMNMX3 on
+        // the ALU pipe between the MUFU instructions) instead of preceding it -- ~360 clk off each warp's serial chain per
+        // key tile.  The lazy-rescaling test then looks at the maximum seen up to the PREVIOUS tile; a tile whose scores
+        // outgrow the reference only produces probabilities above 2^8 for that one tile (fp32 / bf16 exponent range is not
+        // at risk below 2^127), and the reference is raised before the next one.
+        const bool spec = SVOL_ATTN_SPEC_MAX && i > 0 && !masked && refs_finite;
+        if (!spec) {
+          if (masked) mx = half_row_max<true>(s, words);
+          else mx = half_row_max<false>(s, words);
+          mx_seen = fmaxf(mx_seen, mx);
+        }
+        SVOL_TR_AFTER(g, i, 3, mx_seen);
 
         if (i == 0) {
           m_ref = mx;
+          refs_finite = !__any_sync(0xffffffffu, m_ref == -INFINITY);
         } else {
           // lazy rescaling: only when some row's maximum outgrew the reference by more than 2^8
-          const bool need = mx > m_ref + RESCALE_THRESHOLD;
+          const bool need = mx_seen > m_ref + RESCALE_THRESHOLD;
           if (__any_sync(0xffffffffu, need)) {
-            const float alpha = need ? ex2_approx(m_ref - mx) : 1.0f;   // (m_ref = -inf, finite mx) -> 0
+            const float alpha = need ? ex2_approx(m_ref - mx_seen) : 1.0f;   // (m_ref = -inf, finite maximum) -> 0
             mbar_wait(&bars->o_full[g], (i - 1) & 1);                  // every earlier P V has landed in O_g
             tcgen05_fence_after();
 #pragma unroll
@@ -488,7 +507,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             tmem_st_wait();
             l2.x *= alpha; l2.y *= alpha;
-            if (need) m_ref = mx;
+            if (need) m_ref = mx_seen;
+            refs_finite = !__any_sync(0xffffffffu, m_ref == -INFINITY);
           }
         }
         float m_use = m_ref == -INFINITY ? 0.f : m_ref;
@@ -500,7 +520,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // of the reference maximum and the row sum are packed FADD2s
         const float2 neg_m = make_float2(-m_use, -m_use);
         float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
-        if (SVOL_ATTN_POLY_PAIRS > 0 && !masked) {
+        if (spec) {
+          // scores -> probabilities with the row maximum of THIS tile accumulated on the side (see above)
+          float m0 = mx_seen, m1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < HALF; i += 4) {
+            const float s0 = __uint_as_float(s[i]), s1 = __uint_as_float(s[i + 1]), s2 = __uint_as_float(s[i + 2]), s3 = __uint_as_float(s[i + 3]);
+            m0 = fmax3(m0, s0, s1);
+            m1 = fmax3(m1, s2, s3);
+            const float2 x0 = __fadd2_rn(make_float2(s0, s1), neg_m);
+            const float2 x1 = __fadd2_rn(make_float2(s2, s3), neg_m);
+            const float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+            const float2 p1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+            la = __fadd2_rn(la, p0);
+            lb = __fadd2_rn(lb, p1);
+            s[i >> 1] = pack_bf16x2(p0.x, p0.y);
+            s[(i >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+          }
+          mx_seen = fmaxf(m0, m1);
+        } else if (SVOL_ATTN_POLY_PAIRS > 0 && !masked) {
           // unmasked tile: SVOL_ATTN_POLY_PAIRS of every four pairs go through the packed FMA-pipe polynomial
           const float2 magic_m = make_float2(12582912.f - m_use, 12582912.f - m_use);
 #pragma unroll
