@@ -414,11 +414,34 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       SVOL_GTR(0, it, 3);
       if (ep.residual) {
+        // both 64-column blocks of the residual are requested before either is consumed: one DRAM round trip per tile
+        // instead of two dependent ones (phase trace: 6.5 k of the 11.8 k-clock tile period of the attention output projection)
         const uint8_t* rbase = reinterpret_cast<const uint8_t*>(ep.residual + static_cast<size_t>(slab_row0) * ep.ld_res + col0);
+        uint4 raw[COLS_PER_THREAD / 64][8];
+#pragma unroll
+        for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rr = k * 4 + (lane >> 3), ch = lane & 7;
+            raw[blk][k] = make_uint4(0u, 0u, 0u, 0u);
+            if (rr < rows_valid)
+              raw[blk][k] = __ldg(reinterpret_cast<const uint4*>(rbase + blk * 128 + static_cast<size_t>(rr) * ep.ld_res * 2 + ch * 16));
+          }
+        }
 #pragma unroll
         for (int blk = 0; blk < COLS_PER_THREAD / 64; ++blk) {
           uint4 q[8];
-          block_load(stg, q, rbase + blk * 128, static_cast<size_t>(ep.ld_res) * 2, rows_valid, lane);
+          if (lane == 0) tma_store_wait_read<0>();      // a TMA store may still be reading this warp's staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int rr = k * 4 + (lane >> 3), ch = lane & 7;
+            *reinterpret_cast<uint4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4)) = raw[blk][k];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) q[j] = *reinterpret_cast<const uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4));
+          __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float* vv = &v[blk * 64 + j * 8];
