@@ -50,3 +50,28 @@ def test_collate_time_packing_equals_in_process_flattening():
         if matcher_name == "per_frame_matcher":
             c = matcher._flat(other, torch.device("cpu"), cfg.num_queries)
             assert np.array_equal(_fields(c)["match_off"], fa["match_off"])
+
+
+def test_static_views_match_the_flat_packing():
+    """The criterion's static device workspace (modeling/loss.py) addresses a COPY of the packed target buffer through
+    ``static_views``: every array in front of the boxes must sit where ``flatten_targets`` put it, for any batch with the
+    same (P, B) -- and ``order`` lists the problems by number of targets, largest first (svol_match's launch order)."""
+    cfg = synth.CONFIGS["C2"]
+    for seed, mpf in ((0, 2), (1, 5), (2, 9)):
+        tn = synth.make_targets(cfg, 3, seed, max_per_frame=mpf)
+        targets = synth.targets_to_torch(tn)
+        flat = T.flatten_targets(targets, torch.device("cpu"), True, cfg.num_frames, cfg.num_queries, cfg.num_queries_per_frame)
+        cap = flat.n_fixed + 16 * (flat.S + 7)
+        buf = torch.zeros(cap, dtype=torch.uint8)
+        buf[:flat.n_static].copy_(flat.packed[:flat.n_static])
+        v = T.static_views(buf, flat.P, flat.B)
+        assert v["n_fixed"] == flat.n_fixed and flat.n_static == flat.n_fixed + 16 * flat.S
+        for k in ("cost_off", "tgt_off", "match_off", "video_tgt_off", "video_match_off", "meta", "order"):
+            assert torch.equal(v[k], getattr(flat, k)), k
+        assert v["meta"].tolist() == [flat.K, flat.S, flat.max_cols, flat.P]
+        assert torch.equal(v["tgt_boxes"][:16 * flat.S].view(torch.float32).view(-1, 4), flat.tgt_boxes)
+        cols = (flat.tgt_off[1:] - flat.tgt_off[:-1]).numpy()
+        order = flat.order.numpy()
+        assert sorted(order.tolist()) == list(range(flat.P)) and (np.diff(cols[order]) <= 0).all()
+        # same (P, B) -> same fixed layout, whatever the number of boxes
+        assert v["n_fixed"] == T.static_views(torch.zeros(0, dtype=torch.uint8), flat.P, flat.B)["n_fixed"]
