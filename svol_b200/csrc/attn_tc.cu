@@ -672,6 +672,486 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// =====================================================================================================================
+// Persistent variant (round 2).  Same tiles, roles and inner loops as attention_tc_kernel, but ONE CTA per SM walks a list
+// of work items (query-tile pair, head, sample) instead of exiting after one: tensor memory, barriers and descriptors are set
+// up once, the TMA producer runs ahead across item boundaries (Q is double-buffered, the K / V^T ring simply keeps
+// filling), and an issuer starts the next item's first Q K^T as soon as its score columns are free -- so the next item's
+// pipeline fills while the current item's last tiles and epilogue drain.  At the headline shape a CTA lives for only 13 key
+// tiles; the same kernel on the long clip (49 key tiles per CTA) reaches 416 TFLOP/s against 302 here, i.e. ~27 % of the
+// one-item-per-CTA kernel's time was prologue, drain and wave quantisation (1792 CTAs on 148 SMs).
+// Items are numbered query-pair-major, so the cheaper single-tile items (the last pair of every (sample, head)) come last
+// and level the tail.  Every mbarrier phase is a toggling parity bit instead of the per-item iteration count.
+//
+// MEASURED (B200, kernels alone, us per launch; bit-identical outputs over 1000 launches, tools/attn_p_check.py), and the
+// reason this kernel is NOT the default:
+//                                 one item per CTA    persistent
+//   video self (1792 items x 13 key tiles)   261.8         280.6
+//   cross      ( 512 items x 13 key tiles)    72.1          95.6
+//   long clip  ( 800 items x 49 key tiles)   410.7         479.3
+//   112 items x 13 tiles, ONE item per CTA in both kernels:  27.9 vs 31.1  (tools/attn_p_time.py)
+// The last line isolates the cause: with identical scheduling the persistent kernel's per-key-tile code is ~11 % slower --
+// the cross-item state (phase bits, ring position, item decode) does not fit the 32 registers that the 4 x 112 softmax
+// allocation leaves the issuer warpgroup (23 local-memory instructions in the issue loop) nor the softmax threads' 112
+// (3 per key tile) -- and that costs more than the overlapped prologue / drain wins (~4 %); static round-robin assignment
+// adds a 7 % imbalance (12.2 vs 11.4 two-tile units per CTA) that a work counter would remove.  Net: not better than the
+// hardware's own CTA scheduler refilling an SM every ~20 us.
+// Per-stage / per-Q-buffer release barriers always expect TWO arrivals, one per issuer: in a split single-tile item an
+// issuer also passes and releases the key tiles it does not consume (the issuers drift apart at item boundaries, and a
+// stage released by its consumer alone could be refilled twice before the other issuer looked at it: parity aliasing,
+// found as a deadlock after ~40 launches); in an item with a single active issuer that issuer arrives twice.
+// =====================================================================================================================
+namespace attn_p {
+using namespace attn;
+constexpr int KMW = 128;                         // key-validity words per warp (keys up to 8192 -> else the in-loop fallback)
+constexpr int OFF_Q2 = 0;                        // two Q buffers of two tiles each
+constexpr int OFF_K = 2 * 2 * Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES, OFF_CMB = OFF_VT + STAGES * VT_BYTES;
+constexpr int OFF_KMASK = OFF_CMB + CMB_BYTES;
+constexpr int OFF_BAR = OFF_KMASK + 16 * KMW * 4;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+static_assert(SMEM_BYTES <= 232448, "attention (persistent): shared memory budget");
+}  // namespace attn_p
+
+struct AttnPBars {
+  uint64_t q_full[2], q_free[2];
+  uint64_t s_full[4], s_free[4];
+  uint64_t p_ready[4], o_full[4], o_free[4];
+  uint64_t kv_full[attn::STAGES], kv_empty[attn::STAGES];
+  uint32_t tmem_base, pad;
+};
+static_assert(sizeof(AttnPBars) <= 512, "barrier block");
+
+template <bool kLse>
+__global__ void __launch_bounds__(attn::THREADS, 1)
+attention_p_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmVt, const float* __restrict__ key_mask,
+                   __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int lse_pitch, int B, int H, int Lq, int Lk, int ldo) {
+  using namespace attn;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  AttnPBars* bars = reinterpret_cast<AttnPBars*>(smem + attn_p::OFF_BAR);
+
+  const int warp = threadIdx.x >> 5;
+  auto lane_id = []() { int l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; };
+  auto tmem_base_of = [](const AttnPBars* b) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&b->tmem_base)) : "memory"); return v; };
+  const int n_tiles = (Lk + BKV - 1) / BKV;
+  const int n_hi = Lk > HALF ? (Lk - HALF + BKV - 1) / BKV : 0;
+  const int nx = (Lq + 2 * BQ - 1) / (2 * BQ);          // query-tile pairs per (sample, head)
+  const int BH = B * H;
+  const int n_items = nx * BH;
+  const int my_items = n_items > static_cast<int>(blockIdx.x) ? (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+  // Items are numbered query-pair-major: every item but those of the last pair has two populated tiles, and whether a
+  // single-tile item is split over both tile slots only depends on the key length -- so the item kind follows from the
+  // pair index alone.
+  const bool last_single = (nx - 1) * (2 * BQ) + BQ >= Lq;          // the last pair of every (sample, head) holds one tile
+  const bool split_single = n_tiles >= 4;
+  auto pair_of = [&](int n) { return (static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x)) / BH; };
+
+  if (warp == 16 && lane_id() == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->q_full[i], 1); mbar_init(&bars->q_free[i], 2); }
+    for (int g = 0; g < 4; ++g) {
+      mbar_init(&bars->s_full[g], 1);
+      mbar_init(&bars->s_free[g], 4);
+      mbar_init(&bars->p_ready[g], 4);
+      mbar_init(&bars->o_full[g], 1);
+      mbar_init(&bars->o_free[g], 4);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->kv_full[s], 1);
+      mbar_init(&bars->kv_empty[s], 2);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 17) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == 16) {
+      // ------------------------------------------------------------------ TMA producer (runs ahead across items)
+      if (elect_one()) {
+        int jt = 0;                                             // ring fills so far
+        for (int n = 0; n < my_items; ++n) {
+          const int idx = blockIdx.x + n * gridDim.x;
+          const int qp = idx / BH, bh = idx - qp * BH;
+          const int b = bh / H, h = bh - b * H;
+          const int q0 = qp * (2 * BQ);
+          const int n_q = (q0 + BQ < Lq) ? 2 : 1;
+          const int qb = n & 1;
+          mbar_wait(&bars->q_free[qb], ((n >> 1) & 1) ^ 1);      // both issuers are done with this Q buffer (passes on a fresh barrier)
+          mbar_arrive_expect_tx(&bars->q_full[qb], n_q * Q_BYTES);
+          for (int t = 0; t < n_q; ++t)
+            tma_load_2d(smem + attn_p::OFF_Q2 + (qb * 2 + t) * Q_BYTES, &tmQ, &bars->q_full[qb], h * DH, b * Lq + q0 + t * BQ);
+          for (int j = 0; j < n_tiles; ++j, ++jt) {
+            const int s = jt % STAGES;
+            mbar_wait(&bars->kv_empty[s], ((jt / STAGES) & 1) ^ 1);
+            mbar_arrive_expect_tx(&bars->kv_full[s], K_BYTES + VT_BYTES);
+            tma_load_2d(smem + attn_p::OFF_K + s * K_BYTES, &tmK, &bars->kv_full[s], h * DH, b * Lk + j * BKV);
+            tma_load_2d(smem + attn_p::OFF_VT + s * VT_BYTES, &tmVt, &bars->kv_full[s], j * BKV, bh * DH);
+            tma_load_2d(smem + attn_p::OFF_VT + s * VT_BYTES + VT_KB_BYTES, &tmVt, &bars->kv_full[s], j * BKV + HALF, bh * DH);
+          }
+        }
+      }
+    } else if (warp == 17 || warp == 18) {
+      // ------------------------------------------------------------------ MMA issuer of tile slot t
+      const int t = warp - 17;
+      const uint32_t tmem_base = tmem_base_of(bars);
+      if (elect_one()) {
+        constexpr uint32_t idesc_s = make_idesc_bf16(BQ, HALF);
+        constexpr uint32_t idesc_o = make_idesc_bf16(BQ, DH);
+        const uint64_t dK = make_kmajor_desc<64>(smem_u32(smem + attn_p::OFF_K));
+        const uint64_t dV = make_kmajor_desc<128>(smem_u32(smem + attn_p::OFF_VT));
+        // Phase bits of this issuer's barriers (bit k toggles at every use): 0 / 1 s_free (the parity of the NEXT Q K^T use
+        // of key half 0 / 1: the release it needs is the previous phase, and a fresh barrier passes), 2 / 3 p_ready,
+        // 4 / 5 o_free (items completed by half 0 / 1).
+        uint32_t ph = 0;
+        int jj0 = 0;                                            // ring fill number of this item's key tile 0
+        auto item = [&](auto split_tag, int qb, bool alone) {
+          constexpr bool kSplit = decltype(split_tag)::value;
+          constexpr int j_step = kSplit ? 2 : 1;
+          const int j0 = kSplit ? t : 0;
+          const int cnt_lo = n_tiles > j0 ? (n_tiles - j0 + j_step - 1) / j_step : 0;
+          const int cnt_hi = n_hi > j0 ? (n_hi - j0 + j_step - 1) / j_step : 0;
+          const uint64_t dQ = make_kmajor_desc<64>(smem_u32(smem + attn_p::OFF_Q2 + (qb * 2 + (kSplit ? 0 : t)) * Q_BYTES));
+          auto issue_qk = [&](int i, int half) {
+            const int jj = jj0 + j0 + j_step * i;               // ring fill number of this key tile
+            const int g = 2 * t + half, s = jj % STAGES;
+            if (half == 0) {
+              // A split issuer consumes every other key tile, but it passes EVERY fill of the ring in order and releases the
+              // tiles it skips as well (one arrival per issuer and stage, like in a two-tile item).  With the consumer
+              // releasing a stage alone, an issuer that enters the item late (the two issuers drift apart at item
+              // boundaries) found its first stage refilled twice and waited on an aliased parity forever.
+              if (kSplit && j0 + j_step * i > 0) {
+                mbar_wait(&bars->kv_full[(jj - 1) % STAGES], ((jj - 1) / STAGES) & 1);
+                umma_commit(&bars->kv_empty[(jj - 1) % STAGES]);
+              }
+              mbar_wait(&bars->kv_full[s], (jj / STAGES) & 1);
+            }
+            mbar_wait(&bars->s_free[g], ((ph >> half) & 1u) ^ 1u);
+            ph ^= 1u << half;
+            tcgen05_fence_after();
+            const uint64_t dKs = dK + static_cast<uint64_t>(s * (K_BYTES >> 4) + half * (HALF * DH * 2 >> 4));
+#pragma unroll
+            for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + g * HALF, dQ + 2 * k, dKs + 2 * k, idesc_s, k != 0);
+            umma_commit(&bars->s_full[g]);
+          };
+          auto issue_pv = [&](int i, int half) {
+            const int jj = jj0 + j0 + j_step * i;
+            const int g = 2 * t + half, s = jj % STAGES;
+            mbar_wait(&bars->p_ready[g], (ph >> (2 + half)) & 1u);
+            ph ^= 4u << half;
+            // the first P V of an item overwrites O_g: the previous item's accumulator must have been read out
+            if (i == 0) mbar_wait(&bars->o_free[g], ((ph >> (4 + half)) & 1u) ^ 1u);
+            tcgen05_fence_after();
+            const uint64_t dVs = dV + static_cast<uint64_t>(s * (VT_BYTES >> 4) + half * (VT_KB_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < HALF / 16; ++k)
+              umma_bf16_ts(tmem_base + TMEM_O + g * DH, tmem_base + TMEM_P + g * 32 + k * 8, dVs + 2 * k, idesc_o,
+                           (i > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&bars->o_full[g]);
+            // last reader of the stage among this issuer's MMAs: the upper half's P V, or the lower half's when the
+            // tile has no upper half (the last tile of a ragged key length); covers every earlier MMA of this thread
+            if (half == 1 || i >= cnt_hi) {
+              umma_commit(&bars->kv_empty[s]);
+              if (alone) umma_commit(&bars->kv_empty[s]);
+            }
+          };
+          for (int i = 0; i <= cnt_lo + 1; ++i) {
+            if (i < cnt_lo) issue_qk(i, 0);
+            if (i >= 2 && i - 2 < cnt_hi) issue_pv(i - 2, 1);
+            if (i < cnt_hi) issue_qk(i, 1);
+            if (i >= 1 && i <= cnt_lo) issue_pv(i - 1, 0);
+          }
+          if (kSplit && ((n_tiles - 1 - j0) & 1)) {
+            // the item's last key tile belongs to the other issuer: pass and release it too
+            const int jl = jj0 + n_tiles - 1;
+            mbar_wait(&bars->kv_full[jl % STAGES], (jl / STAGES) & 1);
+            umma_commit(&bars->kv_empty[jl % STAGES]);
+          }
+          // this item's Q tile(s) are no longer read (covers every Q K^T above)
+          umma_commit(&bars->q_free[qb]);
+          if (alone) umma_commit(&bars->q_free[qb]);
+          if (cnt_lo > 0) ph ^= 16u;
+          if (cnt_hi > 0) ph ^= 32u;
+        };
+        for (int n = 0; n < my_items; ++n, jj0 += n_tiles) {
+          const bool single = last_single && pair_of(n) == nx - 1;
+          const bool split = single && split_single;
+          if (single && !split && t == 1) continue;             // (the active issuer releases stages / Q for both)
+          mbar_wait(&bars->q_full[n & 1], (n >> 1) & 1);
+          if (split) item(std::true_type{}, n & 1, false);
+          else item(std::false_type{}, n & 1, single);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int g = warp >> 2;                            // softmax warpgroup
+    const int t = g >> 1, half = g & 1;                 // tile slot, key half
+    const int lane = lane_id();
+    const uint32_t tmem_base = tmem_base_of(bars);
+    uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + attn_p::OFF_KMASK) + warp * attn_p::KMW;   // this warp's own words
+    const bool mask_words = key_mask != nullptr && (Lk + 31) / 32 <= attn_p::KMW;
+    const int quarter = warp & 3;                       // TMEM lane quarter == warp % 4
+    const int r = quarter * 32 + lane;                  // row inside the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_s = t_lane + g * HALF;
+    const uint32_t t_p = t_lane + TMEM_P + g * 32, t_o = t_lane + TMEM_O + g * DH;
+    asm volatile(".reg .pred pp_of, pp_sf;");
+    const uint32_t a_sfull = smem_u32(&bars->s_full[g]), a_ofull = smem_u32(&bars->o_full[g]);
+    uint32_t u = 0;                                     // parity of this warpgroup's next key-tile iteration (all items)
+    int b_mask = -1;
+
+    // one item: the key loop of the one-item kernel, phases taken from `u`
+    bool guard_armed = false;                           // a reader's arrival on the merge-buffer guard is pending for this writer
+    auto item = [&](auto split_tag, int n, bool more_of_kind) {
+      constexpr bool kSplit = decltype(split_tag)::value;
+      constexpr int j_step = kSplit ? 2 : 1;
+      const int j0 = kSplit ? t : 0;
+      const int n_half = half ? n_hi : n_tiles;
+      const int n_mine = n_half > j0 ? (n_half - j0 + j_step - 1) / j_step : 0;
+      const float* mrow = nullptr;
+      if (key_mask != nullptr) {
+        const int idx = blockIdx.x + n * gridDim.x;
+        const int b = (idx % BH) / H;
+        mrow = key_mask + static_cast<size_t>(b) * Lk;
+        if (mask_words && b != b_mask) {
+          // key_padding_mask of this sample as a bitmask, one private copy per warp (no cross-warp synchronisation at
+          // item boundaries); eight independent loads in flight per lane
+          const int n_words = (Lk + 31) / 32;
+          for (int w0 = 0; w0 < n_words; w0 += 8) {
+            float mv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int kv = (w0 + e) * 32 + lane;
+              mv[e] = (w0 + e < n_words && kv < Lk) ? __ldg(mrow + kv) : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const uint32_t m = __ballot_sync(0xffffffffu, mv[e] != 0.f);
+              if (lane == 0 && w0 + e < n_words) kmask[w0 + e] = m;
+            }
+          }
+          __syncwarp();
+          b_mask = b;
+        }
+      }
+      float m_ref = -INFINITY;
+      float2 l2 = make_float2(0.f, 0.f);
+      uint32_t s_ready = 0;
+      for (int i = 0; i < n_mine; ++i, u ^= 1u) {
+        const int kv0 = (j0 + j_step * i) * BKV + half * HALF;
+        if (!s_ready) mbar_wait(&bars->s_full[g], u);
+        tcgen05_fence_after();
+        uint32_t s[HALF];
+        tmem_ld_32x32b_x32(t_s, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+        tmem_ld_32x32b_x32(t_s + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->s_free[g]);
+
+        float mx;
+        bool masked = false;
+        uint32_t words[2];
+        if (mask_words) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int w = (kv0 >> 5) + c;
+            words[c] = w * 32 < Lk ? kmask[w] : 0u;
+            masked |= words[c] != 0xffffffffu;
+          }
+        } else if (mrow != nullptr || kv0 + HALF > Lk) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int kv = kv0 + c * 32 + lane;
+            const bool ok = kv < Lk && (mrow == nullptr || __ldg(mrow + kv) != 0.f);
+            words[c] = __ballot_sync(0xffffffffu, ok);
+            masked |= words[c] != 0xffffffffu;
+          }
+        }
+        if (masked) mx = half_row_max<true>(s, words);
+        else mx = half_row_max<false>(s, words);
+
+        if (i == 0) {
+          m_ref = mx;
+        } else {
+          const bool need = mx > m_ref + RESCALE_THRESHOLD;
+          if (__any_sync(0xffffffffu, need)) {
+            const float alpha = need ? ex2_approx(m_ref - mx) : 1.0f;
+            mbar_wait(&bars->o_full[g], u ^ 1u);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(t_o + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st_32x32b_x16(t_o + c * 16, o);
+            }
+            tmem_st_wait();
+            l2.x *= alpha; l2.y *= alpha;
+            if (need) m_ref = mx;
+          }
+        }
+        const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
+        if (i > 0)
+          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 pp_of, [%0], %1;" ::"r"(a_ofull), "r"(u ^ 1u) : "memory");
+
+        const float2 neg_m = make_float2(-m_use, -m_use);
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < HALF; e += 4) {
+          const float2 x0 = __fadd2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), neg_m);
+          const float2 x1 = __fadd2_rn(make_float2(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])), neg_m);
+          const float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+          const float2 p1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+          la = __fadd2_rn(la, p0);
+          lb = __fadd2_rn(lb, p1);
+          s[e >> 1] = pack_bf16x2(p0.x, p0.y);
+          s[(e >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+        }
+        l2 = __fadd2_rn(l2, __fadd2_rn(la, lb));
+
+        if (i > 0) {
+          uint32_t ok;
+          asm volatile("selp.u32 %0, 1, 0, pp_of;" : "=r"(ok));
+          if (!ok) mbar_wait(&bars->o_full[g], u ^ 1u);
+          tcgen05_fence_after();
+        }
+        if (i + 1 < n_mine)
+          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 pp_sf, [%0], %1;" ::"r"(a_sfull), "r"(u ^ 1u) : "memory");
+        tmem_st_32x32b_x32(t_p, &s[0]);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_ready[g]);
+        s_ready = 0;
+        if (i + 1 < n_mine) asm volatile("selp.u32 %0, 1, 0, pp_sf;" : "=r"(s_ready));
+      }
+
+      // ---- item epilogue: O_g is complete once the last P V has landed; the accumulator is handed back to the issuer
+      // (the next item's first P V overwrites it) as soon as it is in registers
+      uint32_t o[DH];
+      if (n_mine > 0) {
+        mbar_wait(&bars->o_full[g], u ^ 1u);
+        tcgen05_fence_after();
+        tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->o_free[g]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < DH; ++e) o[e] = 0u;
+      }
+      const float l_mine = l2.x + l2.y;
+      float* cmb_base = reinterpret_cast<float*>(smem + attn_p::OFF_CMB);
+      const bool writer = kSplit ? (g != 0) : (half == 1);
+      if (writer) {
+        // the slot's previous contents (the previous item of the same kind) have been read: the reader ARRIVED on the
+        // guard barrier when it was through, long ago by now -- the writer never waits for the reader's epilogue, so the two
+        // warpgroups of a tile do not fall into lockstep at item boundaries (lockstep halves the MUFU overlap)
+        if (guard_armed) {
+          if (kSplit) asm volatile("bar.sync 7, 512;" ::: "memory");
+          else asm volatile("bar.sync %0, 256;" ::"r"(5 + t) : "memory");
+        }
+        float* cmb = cmb_base + ((kSplit ? g - 1 : t) * BQ + r) * CMB_STRIDE;
+        cmb[0] = m_ref;
+        cmb[1] = l_mine;
+#pragma unroll
+        for (int e = 0; e < DH; ++e) cmb[2 + e] = __uint_as_float(o[e]);
+      }
+      // partial results ready: the writers only ARRIVE (PTX's producer / consumer form of the named barrier) and move on
+      // to the next item; the reader waits
+      if (writer) {
+        if (kSplit) asm volatile("bar.arrive 4, 512;" ::: "memory");
+        else asm volatile("bar.arrive %0, 256;" ::"r"(1 + t) : "memory");
+      } else {
+        if (kSplit) asm volatile("bar.sync 4, 512;" ::: "memory");
+        else asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");
+      }
+      if (!writer) {
+        constexpr int n_parts = kSplit ? 3 : 1;
+        const int first = kSplit ? 0 : t;
+        float m = m_ref;
+#pragma unroll
+        for (int pi = 0; pi < n_parts; ++pi) m = fmaxf(m, cmb_base[((first + pi) * BQ + r) * CMB_STRIDE]);
+        const float m_safe = m == -INFINITY ? 0.f : m;
+        const float a_own = ex2_approx(m_ref - m_safe);
+        float l_tot = a_own * l_mine;
+        float acc[DH];
+#pragma unroll
+        for (int e = 0; e < DH; ++e) acc[e] = __uint_as_float(o[e]) * a_own;
+#pragma unroll
+        for (int pi = 0; pi < n_parts; ++pi) {
+          const float* cmb = cmb_base + ((first + pi) * BQ + r) * CMB_STRIDE;
+          const float a_p = ex2_approx(cmb[0] - m_safe);
+          l_tot = fmaf(a_p, cmb[1], l_tot);
+#pragma unroll
+          for (int e = 0; e < DH; ++e) acc[e] = fmaf(a_p, cmb[2 + e], acc[e]);
+        }
+        const float inv = 1.0f / l_tot;
+        // item coordinates are only needed here: recomputed instead of being kept live through the key loop
+        const int idx = blockIdx.x + n * gridDim.x;
+        const int qp = idx / BH, bh = idx - qp * BH;
+        const int q = qp * (2 * BQ) + (kSplit ? 0 : t) * BQ + r;
+        if (q < Lq) {
+          const int b = bh / H, h = bh - b * H;
+          if (kLse) lse[static_cast<size_t>(bh) * lse_pitch + q] = m_safe + __log2f(l_tot);
+          uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * Lq + q) * ldo + h * DH);
+#pragma unroll
+          for (int e = 0; e < DH / 8; ++e) {
+            uint4 w;
+            w.x = pack_bf16x2(acc[8 * e + 0] * inv, acc[8 * e + 1] * inv);
+            w.y = pack_bf16x2(acc[8 * e + 2] * inv, acc[8 * e + 3] * inv);
+            w.z = pack_bf16x2(acc[8 * e + 4] * inv, acc[8 * e + 5] * inv);
+            w.w = pack_bf16x2(acc[8 * e + 6] * inv, acc[8 * e + 7] * inv);
+            op[e] = w;
+          }
+        }
+      }
+      // the merge buffer is rewritten by the next item's writers only after its readers are through (see above)
+      if (!writer && more_of_kind) {
+        if (kSplit) asm volatile("bar.arrive 7, 512;" ::: "memory");
+        else asm volatile("bar.arrive %0, 256;" ::"r"(5 + t) : "memory");
+      }
+      guard_armed = more_of_kind;
+    };
+
+    {
+      // start offsets of the first item: g0, g2, g1, g3 a quarter period apart (see the one-item kernel)
+      const int slot = n_tiles >= 6 ? half * 2 + t : 0;
+      const long long t_start = clock64();
+      while (clock64() - t_start < static_cast<long long>(slot) * STAGGER_CLK) {}
+    }
+    bool was_split = false;
+    for (int n = 0; n < my_items; ++n) {
+      const bool single = last_single && pair_of(n) == nx - 1;
+      const bool split = single && split_single;
+      // the NEXT item of this CTA has the same writer / reader roles (items are pair-major: kinds change at most once)
+      const bool next_single = n + 1 < my_items && last_single && pair_of(n + 1) == nx - 1;
+      const bool more = n + 1 < my_items && (next_single == single);
+      if (split && !was_split && n > 0) asm volatile("bar.sync 8, 512;" ::: "memory");   // roles change: everyone is through with the two-tile items
+      was_split = split;
+      if (single && !split && t == 1) continue;
+      if (split) item(std::true_type{}, n, more);
+      else item(std::false_type{}, n, more);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tcgen05_fence_after();
+    tmem_dealloc<attn::TMEM_COLS>(tmem_base_of(bars));
+  }
+}
+
 int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   using namespace attn;
   if (a.B <= 0 || a.H <= 0 || a.Lq <= 0 || a.Lk <= 0) return svol_fail(SVOL_ERR_SHAPE, "attention: bad sizes");
@@ -691,8 +1171,30 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
     if (e != cudaSuccess) return svol_fail_cuda(e, "attention: cudaFuncSetAttribute");
     configured = true;
   }
-  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
   if (a.lse != nullptr && a.lse_pitch < a.Lq) return svol_fail(SVOL_ERR_SHAPE, "attention: lse_pitch < Lq");
+  // Persistent CTAs (one per SM walking a work list): OFF by default -- measured slower, see the kernel's header.
+  // SVOL_ATTN_PERSISTENT=1 enables it when there is more than one wave of work, =2 always (tests, experiments).
+  const char* env_p = getenv("SVOL_ATTN_PERSISTENT");          // read per launch: tests flip it between calls
+  const int persistent = env_p ? atoi(env_p) : 0;
+  const int n_items = ((a.Lq + 2 * BQ - 1) / (2 * BQ)) * a.H * a.B;
+  if (persistent == 2 || (persistent && n_items > sm_count())) {      // 2: force (experiments)
+    static bool configured_p = false;
+    if (!configured_p) {
+      cudaError_t e = cudaFuncSetAttribute(attention_p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_p::SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_p::SMEM_BYTES);
+      if (e != cudaSuccess) return svol_fail_cuda(e, "attention (persistent): cudaFuncSetAttribute");
+      configured_p = true;
+    }
+    const int grid_p = n_items < sm_count() ? n_items : sm_count();
+    if (a.lse != nullptr)
+      attention_p_kernel<true><<<grid_p, THREADS, attn_p::SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
+                                                                              a.lse, a.lse_pitch, a.B, a.H, a.Lq, a.Lk, a.ldo);
+    else
+      attention_p_kernel<false><<<grid_p, THREADS, attn_p::SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
+                                                                               nullptr, 0, a.B, a.H, a.Lq, a.Lk, a.ldo);
+    return svol_check_launch("attention_tc (persistent)");
+  }
+  dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
   if (a.lse != nullptr)
     attention_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
                                                                     a.lse, a.lse_pitch, a.H, a.Lq, a.Lk, a.ldo);

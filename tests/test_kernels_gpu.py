@@ -2,6 +2,7 @@
 the CPU oracle's functions on the same seeded inputs.  bf16 tolerances are stated per test: operands
 are rounded to bf16 on both sides, so what remains is fp32 accumulation order plus the bf16 rounding
 of the stored result (relative 2^-8) -- and, for attention, of the probabilities."""
+import os
 import math
 
 import numpy as np
@@ -382,3 +383,40 @@ def test_ffn_fused(M, ff, posmode):
     if pos is not None:
         prow = np.arange(M) % pos_mod if pos_mod else np.arange(M)
         _assert_close(_f(out["out_pos"]), ref + pos.numpy()[prow], what="out_pos")
+
+
+@pytest.mark.parametrize("Lq,Lk,masked", [(1568, 1568, False), (320, 1568, True), (700, 320, False)])
+def test_persistent_attention_kernel_matches_one_item_kernel(Lq, Lk, masked):
+    """The persistent variant of the attention kernel (SVOL_ATTN_PERSISTENT, off by default: measured slower, see
+    attn_tc.cu) walks several work items per CTA with cross-item barrier phases; its output must be bit-identical to the
+    one-item-per-CTA kernel's (same tiles, same operation order), also when launched back to back."""
+    import math
+    from svol_b200 import ops
+    B, H, d = 6, 8, 256
+    DEV = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    q = (torch.randn(B * Lq, d, generator=g) * 2.0 * math.log2(math.e) / math.sqrt(32)).to(torch.bfloat16).to(DEV)
+    k = torch.randn(B * Lk, d, generator=g).to(torch.bfloat16).to(DEV)
+    pitch = (Lk + 7) // 8 * 8
+    vt = torch.zeros(B * d, pitch, dtype=torch.bfloat16)
+    vt[:, :Lk] = torch.randn(B * d, Lk, generator=g).to(torch.bfloat16)
+    vt = vt.to(DEV)
+    mask = None
+    if masked:
+        mask = torch.ones(B, Lk)
+        for b in range(0, B, 2):
+            mask[b, Lk - 49 * (1 + b):] = 0
+        mask = mask.to(DEV)
+    old = os.environ.get("SVOL_ATTN_PERSISTENT")
+    try:
+        os.environ["SVOL_ATTN_PERSISTENT"] = "0"
+        ref = ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask).clone()
+        os.environ["SVOL_ATTN_PERSISTENT"] = "2"
+        outs = [ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask) for _ in range(8)]
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("SVOL_ATTN_PERSISTENT", None)
+        else:
+            os.environ["SVOL_ATTN_PERSISTENT"] = old
+    assert all(torch.equal(o, ref) for o in outs)
