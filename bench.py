@@ -398,7 +398,7 @@ def main():
     ev_done = [torch.cuda.Event() for _ in range(2)]
     e2e_sink = []
 
-    e2e_cfg = {"host": "host", "stages": stages}
+    e2e_cfg = {"host": "host", "stages": stages, "two_lanes": False}
 
     def h2d(i):
         slot = i & 1
@@ -413,7 +413,9 @@ def main():
         # low-occupancy tail of one step overlaps the head of the next, and with bf16 features the loop is no longer bound by
         # one stream's device time
         main = torch.cuda.current_stream()
-        lanes = step_streams if step_streams is not None and len(step_streams) == 2 else [main, main]
+        # (only when the upload is shorter than a step -- bf16 features: with fp32 features the loop is bound by the PCIe copy,
+        # and two overlapping steps only delay the loss read-back that paces the host's next copy: 2.05 vs 1.95 ms per step)
+        lanes = step_streams if (e2e_cfg["two_lanes"] and step_streams is not None and len(step_streams) == 2) else [main, main]
         for st_ in set(lanes):
             st_.wait_stream(main)
         h2d(0)
@@ -457,6 +459,8 @@ def main():
             if sampler is not None:
                 sampler.start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if sampler is not None:
+                torch.cuda.nvtx.range_push("timed")      # `ncu --nvtx --nvtx-include "timed/"`: the steady-state steps only
             e0.record()
             t_host = time.perf_counter()
             if whole_loop:
@@ -468,6 +472,8 @@ def main():
                 join_streams()                      # ... and e1 is recorded after both have drained
             host_ms.append((time.perf_counter() - t_host) / steps * 1e3)     # host time to ENQUEUE a step (not waiting for it)
             e1.record()
+            if sampler is not None:
+                torch.cuda.nvtx.range_pop()
             barrier()
         return comm.max_over_ranks(e0.elapsed_time(e1), device=dev) / steps      # slowest rank
 
@@ -475,7 +481,7 @@ def main():
     ms_step = timed(step_resident, args.steps, max(args.warmup, 3), sampler=sampler)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(run_e2e, args.steps, 3, whole_loop=True)
-    e2e_cfg.update(host="host_bf16", stages=stages_bf16)
+    e2e_cfg.update(host="host_bf16", stages=stages_bf16, two_lanes=True)
     ms_e2e_bf16 = timed(run_e2e, args.steps, 3, whole_loop=True)
     with torch.no_grad():
         step_resident(0)
