@@ -491,8 +491,13 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
   p.b1 = a.b1; p.b2 = a.b2; p.ln_w = a.ln_weight; p.ln_b = a.ln_bias; p.pos = a.pos; p.pos_theta = a.pos_theta;
   p.ld_pos = a.ld_pos; p.pos_row_mod = a.pos_row_mod; p.ln_eps = a.ln_eps; p.M = a.M; p.FF = a.ff;
   p.has_out_pos = a.out_pos != nullptr;
+  // Launch only as many CTAs as the slowest one needs rounds: 392 token tiles on 148 SMs are three rounds whether 148
+  // CTAs (96 of them with three tiles, 52 with two) or 131 (all with three) run them -- the second form finishes at the same
+  // time and leaves 17 SMs to the kernels of the other graph branches / the other batch in flight.
+  const int rounds = (m_blocks + sm_count() - 1) / sm_count();
+  const int ctas_needed = (m_blocks + rounds - 1) / rounds;
   if (multicast) {
-    const int pairs = std::min((m_blocks + 1) / 2, sm_count() / 2);
+    const int pairs = std::min((ctas_needed + 1) / 2, sm_count() / 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(THREADS);
@@ -507,7 +512,7 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
     if (e != cudaSuccess) return svol_fail_cuda(e, "ffn: cluster launch");
     return svol_check_launch("ffn_tc (2-CTA multicast)");
   }
-  const int grid = m_blocks < sm_count() ? m_blocks : sm_count();
+  const int grid = ctas_needed < sm_count() ? ctas_needed : sm_count();
   ffn_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, tmOutPos, p);
   return svol_check_launch("ffn_tc");
 }

@@ -584,6 +584,16 @@ static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUten
   const int tiles = m_blocks * n_blocks * k_splits;
   int grid = tiles < sm_count() ? tiles : sm_count();
   if (kResidentW) grid = grid / n_blocks * n_blocks;       // every CTA owns one n block
+  if (kResidentW && k_splits == 1 && grid >= n_blocks) {
+    // only as many CTAs as the slowest one needs rounds (392 row tiles on 148 SMs: 131 CTAs x 3 tiles finish when 148 CTAs
+    // with 3 / 2 tiles would, and leave 17 SMs to concurrent graph branches)
+    const int per_n = grid / n_blocks;
+    const int rounds = (m_blocks + per_n - 1) / per_n;
+    grid = ((m_blocks + rounds - 1) / rounds) * n_blocks;
+  } else if (!kResidentW && grid > 0) {
+    const int rounds = (tiles + grid - 1) / grid;
+    grid = (tiles + rounds - 1) / rounds;
+  }
   gemm_bf16_tc_kernel<kResidentW, kTrain><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, tmA2, a.ep, a.M, a.N, a.K,
                                                                             a.split_block, k_splits, a.out_f32, a.ld_f32, a.mn_major);
   return svol_check_launch("gemm_bf16_tc");
