@@ -575,7 +575,10 @@ class HeadEngine:
                 plan.run(_lib.stream_ptr(), start=start)
                 torch.cuda.synchronize()
                 if self._side is None:
-                    self._side = (torch.cuda.Stream(), torch.cuda.Stream())
+                    # the query / input branches are captured on high-priority streams (SVOL_B200_SIDE_PRIORITY, default -1; their kernel
+                    # nodes inherit it), so that the short query-side kernels get SMs ahead of the frame-token kernels
+                    prio = int(os.environ.get("SVOL_B200_SIDE_PRIORITY", "-1"))
+                    self._side = (torch.cuda.Stream(priority=prio), torch.cuda.Stream(priority=prio))
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     plan.run(_lib.stream_ptr(), start=start, side=self._side)
