@@ -349,13 +349,13 @@ def main():
     # what a producer that already runs on the device writes into): nothing is copied per step and the whole forward,
     # input LayerNorm included, is one CUDA-graph launch.  Otherwise the caller-owned tensors are read in place.
     resident = None
-    if step_streams is not None and len(step_streams) == 2 and args.graph and not os.environ.get("SVOL_BENCH_NO_RESIDENT_BUFFERS"):
+    if step_streams is not None and args.graph and not os.environ.get("SVOL_BENCH_NO_RESIDENT_BUFFERS"):
         resident = []
         L_tok, d_in = sets[0]["dev"]["src_video"].shape[1:]
         for si, st in enumerate(step_streams):
             with torch.cuda.stream(st):
                 bufs = model.engine.input_buffers(B, L_tok, d_in)
-                d = sets[si]["dev"]
+                d = sets[si & 1]["dev"]
                 bufs["src_video"].copy_(d["src_video"])
                 bufs["src_sketch"].copy_(d["src_sketch"].reshape(B, -1))
                 bufs["src_video_mask"].copy_(d["src_video_mask"])
@@ -363,9 +363,12 @@ def main():
                                  "src_video": bufs["src_video"], "src_video_mask": bufs["src_video_mask"]})
         torch.cuda.synchronize()
 
+    n_lanes = len(step_streams) if step_streams is not None else 1
+
     def step_resident(i):
-        s = sets[i & 1]
-        d = resident[i & 1] if resident is not None else s["dev"]
+        lane_i = i % n_lanes
+        s = sets[lane_i & 1] if resident is not None else sets[i & 1]      # stream k always works on input set k & 1
+        d = resident[lane_i] if resident is not None else s["dev"]
         if step_streams is None:
             out = model(d["src_sketch"], d["src_sketch_mask"], d["src_video"], d["src_video_mask"])
             return criterion(out, s["targets"])
@@ -415,7 +418,7 @@ def main():
         main = torch.cuda.current_stream()
         # (only when the upload is shorter than a step -- bf16 features: with fp32 features the loop is bound by the PCIe copy,
         # and two overlapping steps only delay the loss read-back that paces the host's next copy: 2.05 vs 1.95 ms per step)
-        lanes = step_streams if (e2e_cfg["two_lanes"] and step_streams is not None and len(step_streams) == 2) else [main, main]
+        lanes = step_streams[:2] if (e2e_cfg["two_lanes"] and step_streams is not None and len(step_streams) >= 2) else [main, main]
         for st_ in set(lanes):
             st_.wait_stream(main)
         h2d(0)

@@ -471,8 +471,11 @@ class HeadEngine:
                 gemm(p + "ffn2_down", hidq, w[p + "mlp2.w2"], w[p + "mlp2.b2"], out=hs[li], residual=o2,
                      ln=(w[p + "n6.w"], w[p + "n6.b"]), out_pos=outp, pos_t=w["query_embed"], pos_mod=Q)
             else:
+                # (out + query_pos feeds the NEXT layer's query self-attention: not produced by the last layer)
+                last_layer = li == NL - 1
                 ffn(p + "ffn2", o2, w[p + "mlp2.w1"], w[p + "mlp2.b1"], w[p + "mlp2.w2"], w[p + "mlp2.b2"],
-                    (w[p + "n6.w"], w[p + "n6.b"]), out=hs[li], out_pos=outp, pos_t=w["query_embed"], pos_mod=Q)
+                    (w[p + "n6.w"], w[p + "n6.b"]), out=hs[li], out_pos=None if last_layer else outp,
+                    pos_t=None if last_layer else w["query_embed"], pos_mod=0 if last_layer else Q)
             for name, _, _ in plan.calls[q_first:]:
                 plan.branch[name] = "q"
             out_cur, outp_cur = hs[li], outp
