@@ -104,6 +104,10 @@ __device__ long long g_attn_trace[6][64][8];
       g_attn_trace[role][j][slot] = c_;                                                    \
     }                                                                                      \
   } while (0)
+// per-CTA timeline: {SM id, first instruction, -, last instruction} in globaltimer ns, indexed by the linear block id
+// (tools/attn_cta_timeline.py)
+__device__ long long g_attn_cta[8192][4];
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory"); return t; }
 #else
 #define SVOL_TR(role, j, slot) do {} while (0)
 #define SVOL_TR_AFTER(role, j, slot, val) do {} while (0)
@@ -257,6 +261,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   auto lane_id = []() { int l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; };
   auto tmem_base_of = [](const AttnBars* b) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&b->tmem_base)) : "memory"); return v; };
   const int q0 = blockIdx.x * (2 * BQ), h = blockIdx.y, b = blockIdx.z;
+#ifdef SVOL_ATTN_TRACE
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (threadIdx.x == 0 && cta_lin < 8192) {
+    uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_attn_cta[cta_lin][0] = smid;
+    g_attn_cta[cta_lin][1] = global_ns();
+  }
+#endif
   const int n_tiles = (Lk + BKV - 1) / BKV;
   const int n_q = (q0 + BQ < Lq) ? 2 : 1;          // is the second query tile of this CTA populated?
   // key tiles whose upper 64 keys hold at least one in-range key: when Lk % 128 is in (0, 64] the upper half of the last
@@ -666,6 +678,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   tcgen05_fence_before();
   __syncthreads();
+#ifdef SVOL_ATTN_TRACE
+  if (threadIdx.x == 0 && cta_lin < 8192) g_attn_cta[cta_lin][3] = global_ns();
+#endif
   if (warp == 17) {
     tcgen05_fence_after();
     tmem_dealloc<attn::TMEM_COLS>(tmem_base_of(bars));
@@ -1207,6 +1222,9 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
 }  // namespace svol
 
 #ifdef SVOL_ATTN_TRACE
+extern "C" int svol_debug_attn_cta_timeline(long long* host_out) {
+  return static_cast<int>(cudaMemcpyFromSymbol(host_out, svol::g_attn_cta, sizeof(svol::g_attn_cta)));
+}
 extern "C" int svol_debug_attn_trace(long long* host_out) {
   return static_cast<int>(cudaMemcpyFromSymbol(host_out, svol::g_attn_trace, sizeof(svol::g_attn_trace)));
 }
