@@ -46,13 +46,14 @@ constexpr int MAX_FF = 2048;
 constexpr int OFF_X = 0, OFF_H = OFF_X + X_BYTES, OFF_W = OFF_H + H_BYTES;
 constexpr int OFF_B1 = OFF_W + W_STAGES * W_STAGE_BYTES;       // fp32 [MAX_FF]
 constexpr int OFF_P2 = OFF_B1 + MAX_FF * 4;                    // fp32 b2, ln_w, ln_b [3][256]
-constexpr int OFF_LN = OFF_P2 + 3 * D * 4;                     // fp32 [2][128] LayerNorm exchange
-constexpr int OFF_IDT = OFF_LN + 2 * BM * 4;                   // fp32 [128] 1 / dim_t of the sine positional encoding
+constexpr int OFF_LN = OFF_P2 + 3 * D * 4;                     // float2 [4][128] LayerNorm exchange: (sum, M2) per column group
+constexpr int OFF_IDT = OFF_LN + 8 * BM * 4;                   // fp32 [128] 1 / dim_t of the sine positional encoding
 constexpr int OFF_BAR = OFF_IDT + (D / 2) * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-constexpr int EPI_WARPS = 8, FIRST_EPI_WARP = 4, THREADS = (FIRST_EPI_WARP + EPI_WARPS) * 32;
-constexpr int COLS = 128;                               // columns per epilogue thread
+// Epilogue warps: 8 (two column groups of 128 per row, 384 threads) or 16 (four groups of 64, 640 threads) -- template
+// parameter kEW of the kernel.  A warp may only read its own 32-lane quarter of tensor memory, so the groups split columns.
+constexpr int FIRST_EPI_WARP = 4;
 constexpr uint32_t TMEM_H = 0, TMEM_O = 256;
 }  // namespace ffn
 
@@ -83,7 +84,7 @@ struct FfnParams {
 // Debug build only (-DSVOL_FFN_TRACE): CTA 0 records clock64() per chunk of its first tiles.
 // role 0: epilogue warp 4 (slots: top, hacc_full, acc->reg, gelu done, h_free, stored); role 1: MMA issuer
 // (slots: mma1 start, mma1 issued, h_ready, mma2 issued)
-__device__ long long g_ffn_trace[2][64][8];
+__device__ long long g_ffn_trace[3][64][8];   // [2]: tile epilogue of the first epilogue warp, per tile
 #define SVOL_FTR(role, idx, slot)                                                          \
   do {                                                                                     \
     if (ftrace_on && (idx) < 64) {                                                         \
@@ -96,26 +97,27 @@ __device__ long long g_ffn_trace[2][64][8];
 #define SVOL_FTR(role, idx, slot) do {} while (0)
 #endif
 
-// exact-erf GELU of two values (t = accumulator + bias), see the header comment.  The FMA-pipe part is written with
-// packed f32x2 instructions: the chunk epilogue is bound by instruction issue (measured: 13.6 scalar instructions
-// per element at 77 % issue utilisation), and packing halves the instruction count of the polynomial.
-__device__ __forceinline__ float2 gelu_erf_q4_x2(float2 t) {
+// erf-form GELU of two values (t = accumulator + bias).  For either sign of t
+//     gelu(t) = relu(t) - |t|/2 * erfc(|t| / sqrt 2)
+// (t > 0: t - t/2 erfc; t < 0: t/2 erfc(-t/sqrt 2) ... = -|t|/2 erfc(|t|/sqrt 2)), so no sign handling is needed.  With
+// n = -min(|t|, 4 sqrt 2) (beyond the clamp the correction is below 5e-8) and erfc(a/sqrt 2)/2 = 2^(n Q(n) - 1), Q a degree-3
+// minimax fit of -log2(erfc(a/sqrt 2))/a weighted by the GELU's sensitivity (max |gelu error| 8.6e-6, far below the bf16
+// rounding of the hidden activation this feeds):  gelu = fma(n, 2^fma(n, Q(n), -1), relu(t)).
+// Per PAIR of values: 6 packed f32x2 FMA-pipe instructions (bias add, 3 Horner steps, exponent, final), 4 FMNMX, 2 MUFU.EX2 --
+// the chunk epilogue is bound by the FP32 / ALU pipes of its sub-partition (phase trace: ~4 k clk per chunk with 8 OR 16
+// epilogue warps, against 4.8 k of MMA), so every instruction removed here shortens the chunk period.  (Round 1 used a
+// degree-4 fit with an explicit sign flip: 8 packed + 6 ALU instructions per pair.)
+__device__ __forceinline__ float2 gelu_erf_q3_x2(float2 t) {
   constexpr float kClamp = 5.65685424949238f;                   // |t| clamped at z = |t| / sqrt 2 = 4
-  const float2 a = make_float2(fminf(fabsf(t.x), kClamp), fminf(fabsf(t.y), kClamp));
-  // q(a) = log2(erfc(a / sqrt 2)) / a, degree-4 minimax fit (max |erf error| 6.8e-7)
-  float2 q = __ffma2_rn(make_float2(-0.00052047055f, -0.00052047055f), a, make_float2(0.007397568f, 0.007397568f));
-  q = __ffma2_rn(q, a, make_float2(-0.052561324f, -0.052561324f));
-  q = __ffma2_rn(q, a, make_float2(-0.45925465f, -0.45925465f));
-  q = __ffma2_rn(q, a, make_float2(-1.1510913f, -1.1510913f));
-  const float2 u = __fmul2_rn(a, q);
+  const float2 n = make_float2(fmaxf(-fabsf(t.x), -kClamp), fmaxf(-fabsf(t.y), -kClamp));
+  float2 q = __ffma2_rn(make_float2(0.004160920158f, 0.004160920158f), n, make_float2(0.04573254287f, 0.04573254287f));
+  q = __ffma2_rn(q, n, make_float2(-0.4649338424f, -0.4649338424f));
+  q = __ffma2_rn(q, n, make_float2(1.149565816f, 1.149565816f));
+  const float2 u = __ffma2_rn(n, q, make_float2(-1.0f, -1.0f));
   float ex, ey;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(u.x));       // erfc(|t| / sqrt 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(u.x));       // erfc(|t| / sqrt 2) / 2
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ey) : "f"(u.y));
-  // -e for t > 0, +e for t < 0:   gelu(t) = relu(t) + 0.5 t * (-+ e)
-  const float2 se = make_float2(__uint_as_float(__float_as_uint(ex) ^ (~__float_as_uint(t.x) & 0x80000000u)),
-                                __uint_as_float(__float_as_uint(ey) ^ (~__float_as_uint(t.y) & 0x80000000u)));
-  const float2 hx = __fmul2_rn(t, make_float2(0.5f, 0.5f));
-  return __ffma2_rn(hx, se, make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f)));
+  return __ffma2_rn(n, make_float2(ex, ey), make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f)));
 }
 
 // kMC: the kernel runs as clusters of two CTAs that work on different token tiles but consume the SAME weight stream.
@@ -123,12 +125,17 @@ __device__ __forceinline__ float2 gelu_erf_q4_x2(float2 t) {
 // SM weight traffic per SM halves (the non-multicast kernel is bound by exactly that feed: ~43 B/clk/SM delivered against
 // the 64 B/clk/SM the tensor pipe could consume).  A ring slot is refilled only after BOTH CTAs' MMAs released it
 // (tcgen05.commit multicast onto both w_empty barriers).
-template <bool kMC>
-__global__ void __launch_bounds__(ffn::THREADS, 1)
+template <bool kMC, int kEW>
+__global__ void __launch_bounds__((ffn::FIRST_EPI_WARP + kEW) * 32, 1)
 ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
               const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut,
               const __grid_constant__ CUtensorMap tmOutPos, const FfnParams p) {
   using namespace ffn;
+  constexpr int EPI_WARPS = kEW, THREADS = (FIRST_EPI_WARP + kEW) * 32;
+  constexpr int NCG = kEW / 4;                 // column groups (threads per token row)
+  constexpr int COLS = D / NCG;                // columns per epilogue thread
+  constexpr int KBT = COLS / BKX;              // 64-wide k-blocks of the operand tile a thread owns
+  static_assert(kEW == 8 || kEW == 16, "8 or 16 epilogue warps");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   FfnBars* bars = reinterpret_cast<FfnBars*>(smem + OFF_BAR);
@@ -178,14 +185,18 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   __syncthreads();
   tcgen05_fence_after();
   if (kMC) cluster_sync_all();       // the peer's barriers are initialised before any multicast traffic targets them
-  const uint32_t tmem_base = bars->tmem_base;
+  // the tensor-memory base is re-read inside each role (opaque to common-subexpression elimination): as a value of the
+  // common prologue it was spilled to local memory and reloaded before every MMA in the issuer's 88-register budget
+  auto tmem_base_of = [](const FfnBars* b) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&b->tmem_base)) : "memory"); return v; };
 
   // Register split of the 384 x 168 launch allocation: 88 for the producer / MMA-issuer warpgroup, 208 for the epilogue
   // warps (128 x 88 + 256 x 208 = 384 x 168).  With 40 / 232 the MMA issuer's descriptors, phases and chunk counters did
   // not fit: ptxas spilled 400 bytes, 130 local-memory instructions INSIDE the issue loop (ncu: 171 k local loads per
   // launch) -- latency on the one thread that feeds the tensor pipe.  88 / 208: 0 bytes.
   if (warp < FIRST_EPI_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // (16 epilogue warps: 640 x 96 at launch = 128 x 64 + 512 x 104)
+    if (kEW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
       // ------------------------------------------------------------------ weight producer
       if (elect_one()) {
@@ -245,6 +256,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         };
         uint32_t n_h = 0;          // chunks whose MMA 1 has been issued (H accumulator uses)
         uint32_t n_o = 0;          // chunks whose MMA 2 has been issued (H operand uses)
+        const uint32_t tmem_base = tmem_base_of(bars);
         for (int it = 0; it < my_tiles; ++it) {
           mbar_wait(&bars->x_full, it & 1);
           auto mma1 = [&]() {
@@ -274,25 +286,26 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    if (kEW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int quarter = warp & 3;                             // TMEM lane quarter this warp may read
-    const int half = (warp - FIRST_EPI_WARP) >> 2;            // which 128 of the 256 columns
+    const int half = (warp - FIRST_EPI_WARP) >> 2;            // column group: which COLS of the 256 columns
     const int r = quarter * 32 + lane;                        // row inside the tile
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_lane = tmem_base_of(bars) + (static_cast<uint32_t>(quarter * 32) << 16);
     // this thread's row inside a [4 k-blocks][128 rows][128 B] operand tile: 16-byte chunk j of k-block kb lives at
-    // kb * 16 KB + r * 128 + ((j ^ (r & 7)) << 4); the thread owns k-blocks 2*half and 2*half + 1
+    // kb * 16 KB + r * 128 + ((j ^ (r & 7)) << 4); the thread owns k-blocks KBT*half .. KBT*half + KBT - 1
     const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
     const uint32_t swz = static_cast<uint32_t>(r & 7);
     uint32_t n_h = 0, n_hs = 0;     // H accumulator read-outs / H operand stores so far
     auto store_tile_half = [&](uint8_t* buf, const float (&v)[COLS]) {
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb)
+      for (int kb = 0; kb < KBT; ++kb)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float* vv = &v[kb * 64 + j * 8];
           const uint4 q = make_uint4(pack_bf16x2(vv[0], vv[1]), pack_bf16x2(vv[2], vv[3]), pack_bf16x2(vv[4], vv[5]),
                                      pack_bf16x2(vv[6], vv[7]));
-          *reinterpret_cast<uint4*>(buf + (2 * half + kb) * XKB_BYTES + row_off + ((static_cast<uint32_t>(j) ^ swz) << 4)) = q;
+          *reinterpret_cast<uint4*>(buf + (KBT * half + kb) * XKB_BYTES + row_off + ((static_cast<uint32_t>(j) ^ swz) << 4)) = q;
         }
     };
     auto load_acc = [&](uint32_t col0, float (&v)[COLS]) {
@@ -326,14 +339,20 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < COLS / 4; ++i) {
           const float4 b = lds_f4(bp + i * 16);
-          const float2 g0 = gelu_erf_q4_x2(__fadd2_rn(make_float2(v[4 * i + 0], v[4 * i + 1]), make_float2(b.x, b.y)));
-          const float2 g1 = gelu_erf_q4_x2(__fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w)));
+          const float2 g0 = gelu_erf_q3_x2(__fadd2_rn(make_float2(v[4 * i + 0], v[4 * i + 1]), make_float2(b.x, b.y)));
+          const float2 g1 = gelu_erf_q3_x2(__fadd2_rn(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(b.z, b.w)));
           v[4 * i + 0] = g0.x; v[4 * i + 1] = g0.y; v[4 * i + 2] = g1.x; v[4 * i + 3] = g1.y;
         }
         // the H buffer is free once MMA 2 of the previous chunk has consumed it; at the start of a tile it also served as
         // the staging buffer of the previous tile's output store (x_free is signalled only after those stores are read)
         SVOL_FTR(0, n_hs, 3);
         if (n_hs > 0) mbar_wait(&bars->h_free, (n_hs - 1) & 1);
+        if (c == 0 && it > 0) {
+          // the previous tile's last output store is still being read out of this buffer by the TMA engine: waited for
+          // HERE, after this chunk's GELU, instead of at the end of the tile epilogue (2 k clk that nothing else covered)
+          if (warp == FIRST_EPI_WARP && lane == 0) tma_store_wait_read<0>();
+          asm volatile("bar.sync 5, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        }
         SVOL_FTR(0, n_hs, 4);
         store_tile_half(smem + OFF_H, v);
         fence_proxy_async_smem();
@@ -346,19 +365,21 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
       // ---- tile epilogue: y = LayerNorm(O + b2 + x)
       mbar_wait(&bars->oacc_full, it & 1);
+      SVOL_FTR(2, it, 0);
       tcgen05_fence_after();
       float v[COLS];
       load_acc(TMEM_O, v);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->oacc_free);
+      SVOL_FTR(2, it, 1);
       {
         const uint32_t bp = smem_u32(s_p2 + half * COLS);
 #pragma unroll
-        for (int kb = 0; kb < 2; ++kb)
+        for (int kb = 0; kb < KBT; ++kb)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint4 xq = *reinterpret_cast<const uint4*>(smem + OFF_X + (2 * half + kb) * XKB_BYTES + row_off +
+            const uint4 xq = *reinterpret_cast<const uint4*>(smem + OFF_X + (KBT * half + kb) * XKB_BYTES + row_off +
                                                              ((static_cast<uint32_t>(j) ^ swz) << 4));
             const float4 b0 = lds_f4(bp + (kb * 16 + j * 2) * 16), b1 = lds_f4(bp + (kb * 16 + j * 2 + 1) * 16);
             float* vv = &v[kb * 64 + j * 8];
@@ -367,22 +388,33 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           }
       }
       // every epilogue warp has read its residual: the x buffer can be refilled with the next tile while this one finishes
-      asm volatile("bar.sync 5, 256;" ::: "memory");
+      asm volatile("bar.sync 5, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       if (warp == FIRST_EPI_WARP && lane == 0) mbar_arrive(&bars->x_free);
-      // LayerNorm over the 256-wide row: the two warps that share a row exchange partial sums (two-pass)
-      float s = 0.f;
+      SVOL_FTR(2, it, 2);
+      // LayerNorm over the 256-wide row.  Each of the NCG threads that share a row reduces its own columns to (sum, M2 about
+      // its own mean) in registers; ONE exchange through shared memory, then the partials are combined exactly
+      // (Chan et al.: M2 = sum_i M2_i + n_i (mean_i - mean)^2) -- two named barriers fewer than a two-pass exchange.
+      // (four independent partial sums each: one 128-long dependent chain of adds is ~500 clk of pure latency)
+      float sp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < COLS; ++i) s += v[i];
-      ln_x[half * BM + r] = s;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      const float mean = (ln_x[r] + ln_x[BM + r]) * (1.0f / D);
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      float ss = 0.f;
+      for (int i = 0; i < COLS; ++i) sp[i & 3] += v[i];
+      const float s = (sp[0] + sp[1]) + (sp[2] + sp[3]);
+      const float mean_own = s * (1.0f / COLS);
+      float mp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < COLS; ++i) { const float d = v[i] - mean; ss += d * d; }
-      ln_x[half * BM + r] = ss;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      const float var = (ln_x[r] + ln_x[BM + r]) * (1.0f / D);
+      for (int i = 0; i < COLS; ++i) { const float d = v[i] - mean_own; mp[i & 3] = fmaf(d, d, mp[i & 3]); }
+      const float m2 = (mp[0] + mp[1]) + (mp[2] + mp[3]);
+      reinterpret_cast<float2*>(ln_x)[half * BM + r] = make_float2(s, m2);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "n"(NCG * 32) : "memory");
+      float2 part[NCG];
+      float tot = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCG; ++c) { part[c] = reinterpret_cast<const float2*>(ln_x)[c * BM + r]; tot += part[c].x; }
+      const float mean = tot * (1.0f / D);
+      float m2_tot = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCG; ++c) { const float dm = part[c].x * (1.0f / COLS) - mean; m2_tot += part[c].y + COLS * dm * dm; }
+      const float var = m2_tot * (1.0f / D);
       const float rstd = rsqrtf(var + p.ln_eps);
       {
         const uint32_t gp = smem_u32(s_p2 + D + half * COLS), bp = smem_u32(s_p2 + 2 * D + half * COLS);
@@ -396,13 +428,15 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
       }
       // y -> H buffer (free: oacc_full implies the last MMA 2 of this tile has completed) -> TMA store
+      SVOL_FTR(2, it, 3);
       store_tile_half(smem + OFF_H, v);
       fence_proxy_async_smem();
-      asm volatile("bar.sync 5, 256;" ::: "memory");
+      asm volatile("bar.sync 5, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       if (warp == FIRST_EPI_WARP && lane == 0) {
         for (int kb = 0; kb < D / BKX; ++kb) tma_store_2d(&tmOut, smem + OFF_H + kb * XKB_BYTES, kb * BKX, m_blk * BM);
         tma_store_commit();
       }
+      SVOL_FTR(2, it, 4);
       if (p.has_out_pos) {
         // second output y + pos, staged in the same buffer once the first store has been read out of it
         if (p.pos_theta != nullptr) {
@@ -432,17 +466,18 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           }
         }
         if (warp == FIRST_EPI_WARP && lane == 0) tma_store_wait_read<0>();
-        asm volatile("bar.sync 5, 256;" ::: "memory");
+        SVOL_FTR(2, it, 5);
+        asm volatile("bar.sync 5, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         store_tile_half(smem + OFF_H, v);
         fence_proxy_async_smem();
-        asm volatile("bar.sync 5, 256;" ::: "memory");
+        asm volatile("bar.sync 5, %0;" ::"n"(EPI_WARPS * 32) : "memory");
         if (warp == FIRST_EPI_WARP && lane == 0) {
           for (int kb = 0; kb < D / BKX; ++kb) tma_store_2d(&tmOutPos, smem + OFF_H + kb * XKB_BYTES, kb * BKX, m_blk * BM);
           tma_store_commit();
         }
+        SVOL_FTR(2, it, 6);
       }
-      if (warp == FIRST_EPI_WARP && lane == 0) tma_store_wait_read<0>();   // staging buffer read out by the TMA engine
-      asm volatile("bar.sync 5, 256;" ::: "memory");                       // ... and may be rewritten by the next tile's chunk 0
+      SVOL_FTR(2, it, 7);
     }
     if (warp == FIRST_EPI_WARP && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -452,7 +487,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (kMC) cluster_sync_all();       // no CTA exits while its peer can still multicast into it / arrive on its barriers
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<512>(tmem_base_of(bars));
   }
 }
 
@@ -482,11 +517,16 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(ffn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(ffn_tc_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ffn_tc_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ffn_tc_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ffn_tc_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return svol_fail_cuda(e, "ffn: cudaFuncSetAttribute");
     configured = true;
   }
+  const char* env_ew = getenv("SVOL_FFN_EPI_WARPS");            // read per launch (A/B measurements)
+  const bool wide = env_ew ? atoi(env_ew) == 16 : false;
+  const int threads = (FIRST_EPI_WARP + (wide ? 16 : 8)) * 32;
   FfnParams p;
   p.b1 = a.b1; p.b2 = a.b2; p.ln_w = a.ln_weight; p.ln_b = a.ln_bias; p.pos = a.pos; p.pos_theta = a.pos_theta;
   p.ld_pos = a.ld_pos; p.pos_row_mod = a.pos_row_mod; p.ln_eps = a.ln_eps; p.M = a.M; p.FF = a.ff;
@@ -500,7 +540,7 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
     const int pairs = std::min((ctas_needed + 1) / 2, sm_count() / 2);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -508,12 +548,14 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, ffn_tc_kernel<true>, tmX, tmW1, tmW2, tmOut, tmOutPos, p);
+    cudaError_t e = wide ? cudaLaunchKernelEx(&cfg, ffn_tc_kernel<true, 16>, tmX, tmW1, tmW2, tmOut, tmOutPos, p)
+                         : cudaLaunchKernelEx(&cfg, ffn_tc_kernel<true, 8>, tmX, tmW1, tmW2, tmOut, tmOutPos, p);
     if (e != cudaSuccess) return svol_fail_cuda(e, "ffn: cluster launch");
     return svol_check_launch("ffn_tc (2-CTA multicast)");
   }
   const int grid = ctas_needed < sm_count() ? ctas_needed : sm_count();
-  ffn_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, tmOutPos, p);
+  if (wide) ffn_tc_kernel<false, 16><<<grid, threads, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, tmOutPos, p);
+  else ffn_tc_kernel<false, 8><<<grid, threads, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, tmOutPos, p);
   return svol_check_launch("ffn_tc");
 }
 
