@@ -92,6 +92,15 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
+// L2 prefetch of a 2-D box (same coordinates as the load that will follow) / of a contiguous byte range: no shared memory,
+// no completion -- puts a later tile's DRAM round trip under the current tile's work.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {      // gptr 16-byte aligned, bytes % 16 == 0
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 // 2-D tiled load: coordinates are (inner, outer) element indices.
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0,
                                             int c1) {

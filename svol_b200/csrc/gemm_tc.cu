@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutPos,
                     const __grid_constant__ CUtensorMap tmA2, const GemmEpilogue ep, int M, int N, int K, int split_block,
-                    int k_splits, float* __restrict__ out_f32, int ld_f32, int mn_major) {
+                    int k_splits, float* __restrict__ out_f32, int ld_f32, int mn_major, int l2_prefetch) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
   // mn_major (training, streaming variant): the operands are given untransposed, A = dY [K rows, M columns] and
@@ -233,6 +233,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         int m_blk, n_blk, kb0, kb1;
         tile_coords(it, m_blk, n_blk);
         k_range(it, kb0, kb1);
+        if (kResidentW && l2_prefetch) {
+          // One CTA per SM and a 3-stage ring (48 KB) keep less than one A tile in flight: the loads were latency-bound
+          // (phase trace: 3.9 k clk per tile in the MMA issuer against 2.3 k of tensor work) and the epilogue's residual read
+          // paid a full DRAM round trip per tile (4.6 k of 11.1 k clk).  The producer therefore pulls the NEXT tile's A
+          // block and THIS tile's residual rows (consumed two tile periods from now) into L2 ahead of time.
+          if (it + 1 < my_tiles) {
+            const int m_next = m_first + (it + 1) * m_stride;
+            for (int kb = kb0; kb < kb1; ++kb) tma_prefetch_2d(second_part ? &tmA2 : &tmA, kb * BK, m_next * BM);
+          }
+          if (ep.residual != nullptr) {
+            const int rows = min(BM, M - m_blk * BM);
+            const svol_bf16* rp = ep.residual + static_cast<size_t>(m_blk) * BM * ep.ld_res + n_blk * BN;
+            if (ep.ld_res == BN) bulk_prefetch_l2(rp, static_cast<uint32_t>(rows) * BN * 2);
+            else for (int r = 0; r < rows; ++r) bulk_prefetch_l2(rp + static_cast<size_t>(r) * ep.ld_res, BN * 2);
+          }
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           if (kResidentW && it == 0) {      // this CTA's weight block, k block by k block, interleaved with the first A tiles
             mbar_arrive_expect_tx(&tail->w_full[kb], B_BYTES);
@@ -594,8 +610,11 @@ static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUten
     const int rounds = (tiles + grid - 1) / grid;
     grid = (tiles + rounds - 1) / rounds;
   }
+  const char* env_pf = getenv("SVOL_GEMM_L2_PREFETCH");       // read per launch (A/B measurements); default on
+  const int l2_prefetch = env_pf ? atoi(env_pf) : 1;
   gemm_bf16_tc_kernel<kResidentW, kTrain><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, tmA2, a.ep, a.M, a.N, a.K,
-                                                                            a.split_block, k_splits, a.out_f32, a.ld_f32, a.mn_major);
+                                                                            a.split_block, k_splits, a.out_f32, a.ld_f32, a.mn_major,
+                                                                            l2_prefetch);
   return svol_check_launch("gemm_bf16_tc");
 }
 
