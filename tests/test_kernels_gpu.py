@@ -106,6 +106,29 @@ def test_gemm_epilogues(M, N, K, flags, plain):
         assert (vt[:, :, vt_len:] == 0).all()
 
 
+def test_gemm_l2_prefetch_changes_nothing_but_timing(monkeypatch):
+    """The resident-weight GEMM's producer prefetches the next A tile and the tile's residual rows into L2 (gemm_tc.cu);
+    a hint only: outputs with SVOL_GEMM_L2_PREFETCH=0 / 1 are bit-identical, also when the last row tile is ragged and a
+    CTA walks several tiles."""
+    from svol_b200 import ops
+    M, N, K = 148 * 128 * 2 + 77, 256, 256
+    rng = np.random.RandomState(11)
+    d = _dev()
+    A = _bf16(rng.standard_normal((M, K)).astype(np.float32)).to(d)
+    W = _bf16((rng.standard_normal((N, K)) / math.sqrt(K)).astype(np.float32)).to(d)
+    bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).to(d)
+    res = _bf16(rng.standard_normal((M, N)).astype(np.float32)).to(d)
+    ln = (torch.ones(N, device=d), torch.zeros(N, device=d))
+    outs = []
+    for pf in ("0", "1"):
+        monkeypatch.setenv("SVOL_GEMM_L2_PREFETCH", pf)
+        outs.append(ops.gemm(A, W, bias, residual=res, ln=ln)["out"].clone())
+        torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    ref = orc.layer_norm((A.float() @ W.float().T + bias + res.float()).cpu().numpy(), np.ones(N, np.float32), np.zeros(N, np.float32))
+    _assert_close(_f(outs[1]), ref, what="out")
+
+
 def test_gemm_split_launch_qk_and_v():
     """One launch: columns [0,512) = (x + pos) Wqk^T written row-major, columns [512,768) = x Wv^T written per-head
     transposed (the q/k and v projections of cross_modal_transformer.py:137-139 share a kernel)."""
@@ -343,6 +366,32 @@ FFN_CASES = [
     (20000, 2048, "full"),        # > 148 tiles: persistent loop, barrier phase wrap across tiles
     (2 * 1568, 2048, "theta"),    # sine positional encoding evaluated inside the kernel (padded second sample)
 ]
+
+
+def test_ffn_gelu_range_and_wide_epilogue(monkeypatch):
+    """The chunk epilogue's GELU is relu(t) - |t|/2 erfc(|t|/sqrt 2) with a degree-3 fit of log2 erfc (ffn_tc.cu): checked
+    against the oracle's erf form over pre-activations spanning +-12 (far tails, the clamp at 4 sqrt 2, values near 0), for the
+    default 8 epilogue warps and for the 16-warp instantiation (SVOL_FFN_EPI_WARPS=16)."""
+    from svol_b200 import ops
+    d, ff, M = 256, 512, 384
+    rng = np.random.RandomState(5)
+    x = _bf16(rng.standard_normal((M, d)).astype(np.float32))
+    w1 = _bf16((3.0 * rng.standard_normal((ff, d)) / math.sqrt(d)).astype(np.float32))      # pre-activations ~ N(0, 3)
+    w2 = _bf16((rng.standard_normal((d, ff)) / math.sqrt(ff)).astype(np.float32))
+    b1 = torch.from_numpy(np.linspace(-6, 6, ff).astype(np.float32))
+    b2 = torch.zeros(d)
+    ln = (torch.ones(d), torch.zeros(d))
+    dv = _dev()
+    xf = x.float().numpy()
+    t = (xf @ w1.float().numpy().T + b1.numpy()).astype(np.float32)
+    assert np.abs(t).max() > 10 and (np.abs(t) < 1e-2).any()
+    h = _bf16(orc.gelu(t)).float().numpy()
+    ref = orc.layer_norm((xf + h @ w2.float().numpy().T).astype(np.float32), ln[0].numpy(), ln[1].numpy())
+    for ew in ("8", "16"):
+        monkeypatch.setenv("SVOL_FFN_EPI_WARPS", ew)
+        out = ops.ffn(x.to(dv), w1.to(dv), b1.to(dv), w2.to(dv), b2.to(dv), (ln[0].to(dv), ln[1].to(dv)))
+        torch.cuda.synchronize()
+        _assert_close(_f(out["out"]), ref, what=f"out ({ew} epilogue warps)")
 
 
 @pytest.mark.parametrize("M,ff,posmode", FFN_CASES)
