@@ -19,75 +19,117 @@ __device__ __forceinline__ float4 ln_load4(const __nv_bfloat16* p) {
   return make_float4(bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y));
 }
 
-template <bool kDrop, typename TIn>
-__global__ void __launch_bounds__(256) layernorm_f32_to_bf16_kernel(const TIn* __restrict__ x,
-                                                                     const float* __restrict__ w,
-                                                                     const float* __restrict__ b,
-                                                                     __nv_bfloat16* __restrict__ y, int rows,
-                                                                     int cols, float eps, DropoutCfg drop) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+// Persistent warps: a warp keeps its 4 * kV columns of gamma / beta in registers and walks rows with a stride of the whole grid,
+// TWO rows per iteration (both rows' 16-byte loads are issued before either is reduced).  The one-row-per-warp form re-read
+// gamma and beta (fp32, 2 x the row's own bytes) through the LSU for every row and was half instruction-bound
+// (ncu: issue slots 56 % busy at 3.8 TB/s); kV is a template parameter so the common widths have no per-element predicates.
+template <bool kDrop, typename TIn, int kV>
+__global__ void __launch_bounds__(256, kV > 6 ? 1 : 2) layernorm_f32_to_bf16_kernel(const TIn* __restrict__ x,
+                                                                        const float* __restrict__ w,
+                                                                        const float* __restrict__ b,
+                                                                        __nv_bfloat16* __restrict__ y, int rows,
+                                                                        int cols, float eps, DropoutCfg drop) {
   const int lane = threadIdx.x & 31;
-  const TIn* xr = x + static_cast<size_t>(row) * cols;
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
   const int nv = cols >> 2;
-  float4 buf[LN_MAXV];
-  float s = 0.f;
+  const bool exact = nv == kV * 32;
+  float4 g[kV], o[kV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < kV; ++i) {
     const int idx = i * 32 + lane;
-    if (idx < nv) {
-      buf[i] = ln_load4(xr + idx * 4);       // streamed once
-      s += (buf[i].x + buf[i].y) + (buf[i].z + buf[i].w);
-    }
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f); o[i] = g[i];
+    if (exact || idx < nv) { g[i] = __ldg(reinterpret_cast<const float4*>(w) + idx); o[i] = __ldg(reinterpret_cast<const float4*>(b) + idx); }
   }
-  const float mean = warp_sum(s) / cols;
-  float ss = 0.f;
+  const float inv_cols = 1.0f / cols;
+  for (int row0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row0 < rows; row0 += 2 * n_warps) {
+    float4 buf[2][kV];
+    float s[2] = {0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = i * 32 + lane;
-    if (idx < nv) {
-      const float a = buf[i].x - mean, c = buf[i].y - mean, d = buf[i].z - mean, e = buf[i].w - mean;
-      ss += (a * a + c * c) + (d * d + e * e);
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / cols + eps);
-  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * cols);
-  const float4* w4 = reinterpret_cast<const float4*>(w);
-  const float4* b4 = reinterpret_cast<const float4*>(b);
+    for (int r = 0; r < 2; ++r) {
+      const int row = row0 + r * n_warps;
+      const TIn* xr = x + static_cast<size_t>(row) * cols;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int idx = i * 32 + lane;
-    if (idx < nv) {
-      const float4 g = __ldg(w4 + idx), o = __ldg(b4 + idx);
-      float v0 = (buf[i].x - mean) * rstd * g.x + o.x, v1 = (buf[i].y - mean) * rstd * g.y + o.y;
-      float v2 = (buf[i].z - mean) * rstd * g.z + o.z, v3 = (buf[i].w - mean) * rstd * g.w + o.w;
-      if (kDrop) {       // train-mode Dropout after the LayerNorm (svanet.py:168-170)
-        const unsigned long long key = dropout_key(drop), e0 = static_cast<unsigned long long>(row) * cols + idx * 4;
-        const uint32_t thr = dropout_threshold(drop.p);
-        const float sc = 1.0f / (1.0f - drop.p);
-        v0 = dropout_keep(e0, key, thr) ? v0 * sc : 0.f; v1 = dropout_keep(e0 + 1, key, thr) ? v1 * sc : 0.f;
-        v2 = dropout_keep(e0 + 2, key, thr) ? v2 * sc : 0.f; v3 = dropout_keep(e0 + 3, key, thr) ? v3 * sc : 0.f;
+      for (int i = 0; i < kV; ++i) {
+        const int idx = i * 32 + lane;
+        buf[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows && (exact || idx < nv)) buf[r][i] = ln_load4(xr + idx * 4);       // streamed once
       }
-      uint2 q;
-      q.x = pack_bf16x2(v0, v1);
-      q.y = pack_bf16x2(v2, v3);
-      yr[idx] = q;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int i = 0; i < kV; ++i) s[r] += (buf[r][i].x + buf[r][i].y) + (buf[r][i].z + buf[r][i].w);
+    float mean[2], ss[2] = {0.f, 0.f};
+#pragma unroll
+    for (int o_ = 16; o_ > 0; o_ >>= 1) {
+      s[0] += __shfl_xor_sync(0xffffffffu, s[0], o_);
+      s[1] += __shfl_xor_sync(0xffffffffu, s[1], o_);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mean[r] = s[r] * inv_cols;
+#pragma unroll
+      for (int i = 0; i < kV; ++i) {
+        if (exact || i * 32 + lane < nv) {
+          const float a = buf[r][i].x - mean[r], c = buf[r][i].y - mean[r], d = buf[r][i].z - mean[r], e = buf[r][i].w - mean[r];
+          ss[r] += (a * a + c * c) + (d * d + e * e);
+        }
+      }
+    }
+#pragma unroll
+    for (int o_ = 16; o_ > 0; o_ >>= 1) {
+      ss[0] += __shfl_xor_sync(0xffffffffu, ss[0], o_);
+      ss[1] += __shfl_xor_sync(0xffffffffu, ss[1], o_);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = row0 + r * n_warps;
+      if (row >= rows) break;
+      const float rstd = rsqrtf(ss[r] * inv_cols + eps);
+      uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * cols);
+#pragma unroll
+      for (int i = 0; i < kV; ++i) {
+        const int idx = i * 32 + lane;
+        if (exact || idx < nv) {
+          float v0 = (buf[r][i].x - mean[r]) * rstd * g[i].x + o[i].x, v1 = (buf[r][i].y - mean[r]) * rstd * g[i].y + o[i].y;
+          float v2 = (buf[r][i].z - mean[r]) * rstd * g[i].z + o[i].z, v3 = (buf[r][i].w - mean[r]) * rstd * g[i].w + o[i].w;
+          if (kDrop) {       // train-mode Dropout after the LayerNorm (svanet.py:168-170)
+            const unsigned long long key = dropout_key(drop), e0 = static_cast<unsigned long long>(row) * cols + idx * 4;
+            const uint32_t thr = dropout_threshold(drop.p);
+            const float sc = 1.0f / (1.0f - drop.p);
+            v0 = dropout_keep(e0, key, thr) ? v0 * sc : 0.f; v1 = dropout_keep(e0 + 1, key, thr) ? v1 * sc : 0.f;
+            v2 = dropout_keep(e0 + 2, key, thr) ? v2 * sc : 0.f; v3 = dropout_keep(e0 + 3, key, thr) ? v3 * sc : 0.f;
+          }
+          uint2 q;
+          q.x = pack_bf16x2(v0, v1);
+          q.y = pack_bf16x2(v2, v3);
+          yr[idx] = q;
+        }
+      }
     }
   }
+}
+
+template <bool kDrop, typename TIn>
+static void launch_ln_rows(const TIn* x, const float* w, const float* b, __nv_bfloat16* y, int rows, int cols, float eps, DropoutCfg drop,
+                           cudaStream_t stream) {
+  const int wpb = 8;
+  const int want = (rows + 2 * wpb - 1) / (2 * wpb);            // one pass of two rows per warp
+  const int grid = std::min(want, 2 * sm_count());              // two resident CTAs per SM (launch bounds)
+  const int kv = (cols + 127) / 128;
+  if (kv <= 2) layernorm_f32_to_bf16_kernel<kDrop, TIn, 2><<<grid, wpb * 32, 0, stream>>>(x, w, b, y, rows, cols, eps, drop);
+  else if (kv <= 4) layernorm_f32_to_bf16_kernel<kDrop, TIn, 4><<<grid, wpb * 32, 0, stream>>>(x, w, b, y, rows, cols, eps, drop);
+  else if (kv <= 6) layernorm_f32_to_bf16_kernel<kDrop, TIn, 6><<<grid, wpb * 32, 0, stream>>>(x, w, b, y, rows, cols, eps, drop);
+  else layernorm_f32_to_bf16_kernel<kDrop, TIn, 8><<<grid, wpb * 32, 0, stream>>>(x, w, b, y, rows, cols, eps, drop);
 }
 
 int launch_layernorm_f32_to_bf16(const float* x, const float* w, const float* b, svol_bf16* y, int rows, int cols,
                                  float eps, float drop_p, const long long* seed, int site, cudaStream_t stream) {
   if (cols % 4 != 0 || cols > LN_MAXV * 128 || rows <= 0) return svol_fail(SVOL_ERR_SHAPE, "layernorm: cols % 4 == 0, cols <= 1024");
   if (drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !seed)) return svol_fail(SVOL_ERR_SHAPE, "layernorm: 0 <= drop_p < 1, seed required");
-  const int wpb = 8;
   const DropoutCfg drop{drop_p, seed, site};
-  if (drop_p > 0.f)
-    layernorm_f32_to_bf16_kernel<true, float><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
-        x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, drop);
-  else
-    layernorm_f32_to_bf16_kernel<false, float><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
-        x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, drop);
+  if (drop_p > 0.f) launch_ln_rows<true, float>(x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, drop, stream);
+  else launch_ln_rows<false, float>(x, w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, drop, stream);
   return svol_check_launch("layernorm_f32_to_bf16");
 }
 
@@ -96,9 +138,8 @@ int launch_layernorm_f32_to_bf16(const float* x, const float* w, const float* b,
 int launch_layernorm_bf16_to_bf16(const svol_bf16* x, const float* w, const float* b, svol_bf16* y, int rows, int cols,
                                   float eps, cudaStream_t stream) {
   if (cols % 4 != 0 || cols > LN_MAXV * 128 || rows <= 0) return svol_fail(SVOL_ERR_SHAPE, "layernorm: cols % 4 == 0, cols <= 1024");
-  const int wpb = 8;
-  layernorm_f32_to_bf16_kernel<false, __nv_bfloat16><<<(rows + wpb - 1) / wpb, wpb * 32, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps, DropoutCfg{0.f, nullptr, 0});
+  launch_ln_rows<false, __nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(x), w, b, reinterpret_cast<__nv_bfloat16*>(y), rows, cols, eps,
+                                       DropoutCfg{0.f, nullptr, 0}, stream);
   return svol_check_launch("layernorm_bf16_to_bf16");
 }
 
