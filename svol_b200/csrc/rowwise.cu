@@ -929,41 +929,81 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
                                                     const float* __restrict__ bc, const float* __restrict__ wb,
                                                     const float* __restrict__ bb, float* __restrict__ logits,
                                                     float* __restrict__ boxes, int rows) {
-  __shared__ float w[6][GATE_D];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 2 * GATE_D; i += 256) w[i / GATE_D][i % GATE_D] = wc[i];
-  for (int i = tid; i < 4 * GATE_D; i += 256) w[2 + i / GATE_D][i % GATE_D] = wb[i];
-  __syncthreads();
-  const int row = blockIdx.x * 8 + warp;
-  if (row >= rows) return;
-  const uint4 qa = __ldg(reinterpret_cast<const uint4*>(hs + static_cast<size_t>(row) * GATE_D) + lane);
-  const uint4 qb = __ldg(reinterpret_cast<const uint4*>(h2 + static_cast<size_t>(row) * GATE_D) + lane);
-  const float a[8] = {bf16_lo(qa.x), bf16_hi(qa.x), bf16_lo(qa.y), bf16_hi(qa.y), bf16_lo(qa.z), bf16_hi(qa.z), bf16_lo(qa.w), bf16_hi(qa.w)};
-  const float c[8] = {bf16_lo(qb.x), bf16_hi(qb.x), bf16_lo(qb.y), bf16_hi(qb.y), bf16_lo(qb.z), bf16_hi(qb.z), bf16_lo(qb.w), bf16_hi(qb.w)};
-  float acc[6];
+  // Persistent warps: a lane keeps its 8 columns of the six weight rows in registers (the one-row-per-warp form staged the
+  // 6 KB of weights through shared memory in every CTA of 8 rows: 15 MB of L2 reads and a block barrier per 8 rows), two
+  // rows in flight per warp, and the six dot products are reduced together (8 values -> reduce-scatter butterfly).
+  const int lane = threadIdx.x & 31;
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
+  float w[6][8];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s = fmaf(j < 2 ? a[i] : c[i], w[j][lane * 8 + i], s);
-    acc[j] = warp_sum(s);
+    const float4* wp = reinterpret_cast<const float4*>((j < 2 ? wc + j * GATE_D : wb + (j - 2) * GATE_D)) + lane * 2;
+    const float4 p = __ldg(wp), q = __ldg(wp + 1);
+    w[j][0] = p.x; w[j][1] = p.y; w[j][2] = p.z; w[j][3] = p.w; w[j][4] = q.x; w[j][5] = q.y; w[j][6] = q.z; w[j][7] = q.w;
   }
-  if (lane == 0) {
-    logits[static_cast<size_t>(row) * 2 + 0] = acc[0] + bc[0];
-    logits[static_cast<size_t>(row) * 2 + 1] = acc[1] + bc[1];
-    float4 o;
-    o.x = 1.f / (1.f + expf(-(acc[2] + bb[0]))); o.y = 1.f / (1.f + expf(-(acc[3] + bb[1])));
-    o.z = 1.f / (1.f + expf(-(acc[4] + bb[2]))); o.w = 1.f / (1.f + expf(-(acc[5] + bb[3])));
-    reinterpret_cast<float4*>(boxes)[row] = o;
+  const float bias_c0 = __ldg(bc), bias_c1 = __ldg(bc + 1);
+  const float4 bias_b = make_float4(__ldg(bb), __ldg(bb + 1), __ldg(bb + 2), __ldg(bb + 3));   // (no alignment assumed)
+  const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+  for (int row0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row0 < rows; row0 += 2 * n_warps) {
+    uint4 qa[2], qb[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = min(row0 + r * n_warps, rows - 1);
+      qa[r] = __ldg(reinterpret_cast<const uint4*>(hs + static_cast<size_t>(row) * GATE_D) + lane);
+      qb[r] = __ldg(reinterpret_cast<const uint4*>(h2 + static_cast<size_t>(row) * GATE_D) + lane);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float a[8] = {bf16_lo(qa[r].x), bf16_hi(qa[r].x), bf16_lo(qa[r].y), bf16_hi(qa[r].y), bf16_lo(qa[r].z), bf16_hi(qa[r].z), bf16_lo(qa[r].w), bf16_hi(qa[r].w)};
+      const float c[8] = {bf16_lo(qb[r].x), bf16_hi(qb[r].x), bf16_lo(qb[r].y), bf16_hi(qb[r].y), bf16_lo(qb[r].z), bf16_hi(qb[r].z), bf16_lo(qb[r].w), bf16_hi(qb[r].w)};
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(j < 2 ? a[i] : c[i], w[j][i], s);
+        acc[j] = s;
+      }
+      acc[6] = 0.f; acc[7] = 0.f;
+      // reduce-scatter: after three exchange steps every group of 4 lanes holds one output's partial sum
+      float a4[4], a2[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = b16 ? acc[i] : acc[i + 4], keep = b16 ? acc[i + 4] : acc[i];
+        a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = b8 ? a4[i] : a4[i + 2], keep = b8 ? a4[i + 2] : a4[i];
+        a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      const float send = b4 ? a2[0] : a2[1], keep = b4 ? a2[1] : a2[0];
+      float t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      // lane group g = lane >> 2 holds output (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0); gather the six on lane 0
+      const float o0 = t, o1 = __shfl_sync(0xffffffffu, t, 4), o2 = __shfl_sync(0xffffffffu, t, 8), o3 = __shfl_sync(0xffffffffu, t, 12),
+                  o4 = __shfl_sync(0xffffffffu, t, 16), o5 = __shfl_sync(0xffffffffu, t, 20);
+      const int row = row0 + r * n_warps;
+      if (lane == 0 && row < rows) {
+        reinterpret_cast<float2*>(logits)[row] = make_float2(o0 + bias_c0, o1 + bias_c1);
+        float4 o;
+        o.x = 1.f / (1.f + expf(-(o2 + bias_b.x))); o.y = 1.f / (1.f + expf(-(o3 + bias_b.y)));
+        o.z = 1.f / (1.f + expf(-(o4 + bias_b.z))); o.w = 1.f / (1.f + expf(-(o5 + bias_b.w)));
+        reinterpret_cast<float4*>(boxes)[row] = o;
+      }
+    }
   }
 }
 
 int launch_heads(const svol_bf16* hs, const svol_bf16* h2, const float* wc, const float* bc, const float* wb,
                  const float* bb, float* logits, float* boxes, int rows, int d, cudaStream_t stream) {
   if (d != GATE_D || rows <= 0) return svol_fail(SVOL_ERR_SHAPE, "heads: hidden_dim 256 only");
-  heads_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hs),
-                                                   reinterpret_cast<const __nv_bfloat16*>(h2), wc, bc, wb, bb, logits,
-                                                   boxes, rows);
+  const int want = (rows + 15) / 16;                         // 8 warps x 2 rows per pass
+  const int grid = std::min(want, 4 * sm_count());
+  heads_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hs),
+                                         reinterpret_cast<const __nv_bfloat16*>(h2), wc, bc, wb, bb, logits,
+                                         boxes, rows);
   return svol_check_launch("heads");
 }
 
