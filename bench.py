@@ -832,6 +832,18 @@ def kernel_breakdown(model, inset, cfg, B, dev):
                 "traffic": traffic, "ms_per_launch": per_launch_ms, "share_of_forward": t_top / total,
                 "peak_source": f"{peaks['_src']} bf16_tflops_sustained (kernel timed inside the step)",
                 "algorithmic_flops_per_launch": flops[top]}
+        if top.startswith("attention"):
+            # informational: at head_dim 32 the softmax's exponentials, not the tensor pipe, bound a flash-style attention tile
+            # (one ex2 per 128 tensor FLOPs; MUFU.EX2 issues 16 results / clk / SM on sm_100a, tools/ubench/mufu.cu ->
+            # profiles/r02_ubench_mufu_packed.txt).  exps = B * H * Lq * Lk of the shape; the clock is the one sampled under load.
+            H = 8
+            exps = {"attention(video self)": float(B) * H * L * L, "attention(query self)": float(B) * H * Q * Q,
+                    "attention(cross)": float(B) * H * Q * L}[top]
+            props = torch.cuda.get_device_properties(dev)
+            mhz = float(peaks.get("sm_mhz_under_load", 0) or 1965.0)
+            floor_ms = exps / (16.0 * props.multi_processor_count * mhz * 1e6) * 1e3
+            roof["limiting_pipe"] = {"pipe": "MUFU.EX2 (16 results/clk/SM measured)", "exps_per_launch": exps, "sm_mhz_assumed": mhz,
+                                     "floor_ms_per_launch": floor_ms, "frac_of_floor": floor_ms / per_launch_ms}
     else:
         roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s", "frac": None,
                 "traffic": traffic, "ms_per_launch": per_launch_ms, "share_of_forward": t_top / total}

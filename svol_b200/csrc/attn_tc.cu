@@ -60,7 +60,10 @@ constexpr int K_BYTES = BKV * DH * 2;           // 8192
 constexpr int VT_KB_BYTES = DH * 128;           // one 64-key block of V^T: 32 rows x 128 B
 constexpr int VT_BYTES = 2 * VT_KB_BYTES;       // 8192
 constexpr int CMB_STRIDE = 35;                  // floats per row of the merge buffer: m, l, O[32] (+1: odd stride, no bank conflicts)
-constexpr int CMB_BYTES = 3 * BQ * CMB_STRIDE * 4;           // up to three partial results per row (single-tile CTAs)
+// merge buffer: up to three partial results per row of a 128-row tile (single-tile CTAs), or seven per row of a 64-row tile
+// (single-tile CTAs with at most 64 query rows: two key parts per half tile, run_softmax_dup)
+constexpr int CMB_BYTES = 7 * 64 * CMB_STRIDE * 4;
+constexpr int CMB_BYTES_3 = 3 * BQ * CMB_STRIDE * 4;           // three partials per 128-row tile only (persistent variant)
 constexpr int OFF_K = 2 * Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES, OFF_CMB = OFF_VT + STAGES * VT_BYTES;
 constexpr int KMASK_WORDS = 256;                // key-padding bitmask of one sample: up to 8192 keys
 constexpr int OFF_KMASK = OFF_CMB + CMB_BYTES;
@@ -242,12 +245,30 @@ __device__ __forceinline__ float half_row_max(uint32_t (&s)[attn::HALF], const u
   return fmax3(fmaxf(m0, m1), m2, m3);
 }
 
+// row maximum of one 32-key part (single-tile CTAs with at most 64 query rows, see run_softmax_dup)
+template <bool kMasked>
+__device__ __forceinline__ float part32_row_max(uint32_t (&s)[32], uint32_t word) {
+  if (kMasked) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (!((word >> i) & 1u)) s[i] = 0xff800000u;   // -inf
+  }
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    m0 = fmax3(m0, __uint_as_float(s[i + 0]), __uint_as_float(s[i + 1]));
+    m1 = fmax3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+  }
+  return fmaxf(m0, m1);
+}
+
 // kLse: the training forward also stores each row's base-2 log-sum-exp (a separate instantiation so that the inference
 // kernel keeps the register allocation it was tuned with).
 template <bool kLse>
 __global__ void __launch_bounds__(attn::THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmVt, const float* __restrict__ key_mask,
+                    const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmQ64,
+                    const float* __restrict__ key_mask,
                     __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int lse_pitch, int H, int Lq, int Lk, int ldo) {
   using namespace attn;
   extern __shared__ uint8_t smem_raw[];
@@ -279,6 +300,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // two-tile path keeps exactly the code it was tuned with (key tile == iteration, no extra live values).
   // (with fewer than four key tiles the extra merge costs more than the shorter walk saves: query self-attention, 3 tiles)
   const bool split = n_q == 1 && n_tiles >= 4;
+  // ... and when that one query tile holds at most 64 rows (cross-attention: 320 = 2 x 128 + 64 queries; video self-attention:
+  // 1568 = 12 x 128 + 32), the rows are loaded TWICE (tile rows 64..127 = rows 0..63 again) and the two copies split every
+  // half tile's 64 keys: copy 0 exponentiates keys [0, 32), copy 1 keys [32, 64), each writing zeros for the other part's
+  // probabilities once.  The MMAs are unchanged; every softmax warp issues half the MUFU / row-max work per key tile
+  // instead of spending it on rows that do not exist, and eight partial results per row are merged at the end.
+  const bool dup = split && Lq - q0 <= 64;
 #ifdef SVOL_ATTN_TRACE
 #ifdef SVOL_ATTN_TRACE_LAST      // trace the LAST query-tile pair of (sample 0, head 0): the single-tile CTA when Lq % 256 is in (0, 128]
   const bool trace_on = blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane_id() == 0 && ((warp & 3) == 0 || warp >= 16);
@@ -316,8 +343,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // ------------------------------------------------------------------ TMA producer
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->q_full, n_q * Q_BYTES);
-        for (int t = 0; t < n_q; ++t)
-          tma_load_2d(smem + t * Q_BYTES, &tmQ, &bars->q_full, h * DH, b * Lq + q0 + t * BQ);
+        if (dup) {          // the same 64 rows into both halves of the tile (64 rows x 64 B = 4 KB: a whole number of swizzle atoms)
+          tma_load_2d(smem, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
+          tma_load_2d(smem + Q_BYTES / 2, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
+        } else {
+          for (int t = 0; t < n_q; ++t)
+            tma_load_2d(smem + t * Q_BYTES, &tmQ, &bars->q_full, h * DH, b * Lq + q0 + t * BQ);
+        }
         const int vrow = (b * H + h) * DH;
         for (int j = 0; j < n_tiles; ++j) {
           const int s = j % STAGES;
@@ -672,7 +704,164 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       };
-      if (split) run_softmax(std::true_type{}); else run_softmax(std::false_type{});
+      // ---- single-tile CTA with at most 64 query rows: the split walk above with the two row copies sharing each half tile
+      auto run_softmax_dup = [&]() {
+      const int copy = quarter >> 1;                      // rows 0..63: keys [0, 32) of the half tile; rows 64..127: keys [32, 64)
+      const int r64 = r & 63;                             // query row of this thread
+      uint32_t s_ready = 0;
+      const int j0 = t;
+      const int n_half = half ? n_hi : n_tiles;
+      const int n_mine = n_half > j0 ? (n_half - j0 + 1) / 2 : 0;
+      {
+        // probabilities of the OTHER copy's keys are zero in this warp's rows for the whole walk: written once (ordered before
+        // the first p_ready arrival by the fence in front of it)
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+        tmem_st_32x32b_x16(t_p + (1 - copy) * 16, z);
+        tmem_st_wait();
+      }
+      for (int i = 0; i < n_mine; ++i) {
+        const int j = j0 + 2 * i;
+        const int kv0 = j * BKV + half * HALF + copy * 32;
+        if (!s_ready) mbar_wait(&bars->s_full[g], i & 1);
+        tcgen05_fence_after();
+        uint32_t s[32];
+        tmem_ld_32x32b_x32(t_s + copy * 32, s);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->s_free[g]);
+
+        uint32_t word = 0xffffffffu;
+        if (mask_in_smem) {
+          const int w = kv0 >> 5;
+          word = w * 32 < Lk ? kmask[w] : 0u;
+        } else if (mrow != nullptr || kv0 + 32 > Lk) {
+          const int kv = kv0 + lane;
+          word = __ballot_sync(0xffffffffu, kv < Lk && (mrow == nullptr || __ldg(mrow + kv) != 0.f));
+        }
+        float mx;
+        if (word != 0xffffffffu) mx = part32_row_max<true>(s, word);
+        else mx = part32_row_max<false>(s, word);
+        mx_seen = fmaxf(mx_seen, mx);
+
+        if (i == 0) {
+          m_ref = mx;
+        } else {
+          const bool need = mx_seen > m_ref + RESCALE_THRESHOLD;
+          if (__any_sync(0xffffffffu, need)) {
+            const float alpha = need ? ex2_approx(m_ref - mx_seen) : 1.0f;
+            mbar_wait(&bars->o_full[g], (i - 1) & 1);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[16];
+              tmem_ld_32x32b_x16(t_o + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st_32x32b_x16(t_o + c * 16, o);
+            }
+            tmem_st_wait();
+            l2.x *= alpha; l2.y *= alpha;
+            if (need) m_ref = mx_seen;
+          }
+        }
+        const float m_use = m_ref == -INFINITY ? 0.f : m_ref;
+        if (i > 0)
+          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_of, [%0], %1;" ::"r"(a_ofull), "r"((i - 1) & 1) : "memory");
+        const float2 neg_m = make_float2(-m_use, -m_use);
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          const float2 x0 = __fadd2_rn(make_float2(__uint_as_float(s[e]), __uint_as_float(s[e + 1])), neg_m);
+          const float2 x1 = __fadd2_rn(make_float2(__uint_as_float(s[e + 2]), __uint_as_float(s[e + 3])), neg_m);
+          const float2 p0 = make_float2(ex2_approx(x0.x), ex2_approx(x0.y));
+          const float2 p1 = make_float2(ex2_approx(x1.x), ex2_approx(x1.y));
+          la = __fadd2_rn(la, p0);
+          lb = __fadd2_rn(lb, p1);
+          s[e >> 1] = pack_bf16x2(p0.x, p0.y);
+          s[(e >> 1) + 1] = pack_bf16x2(p1.x, p1.y);
+        }
+        l2 = __fadd2_rn(l2, __fadd2_rn(la, lb));
+        if (i > 0) {
+          uint32_t ok;
+          asm volatile("selp.u32 %0, 1, 0, p_of;" : "=r"(ok));
+          if (!ok) mbar_wait(&bars->o_full[g], (i - 1) & 1);
+          tcgen05_fence_after();
+        }
+        if (i + 1 < n_mine)
+          asm volatile("mbarrier.test_wait.parity.shared::cta.b64 p_sf, [%0], %1;" ::"r"(a_sfull), "r"((i + 1) & 1) : "memory");
+        tmem_st_32x32b_x16(t_p + copy * 16, *reinterpret_cast<uint32_t(*)[16]>(&s[0]));
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->p_ready[g]);
+        s_ready = 0;
+        if (i + 1 < n_mine) asm volatile("selp.u32 %0, 1, 0, p_sf;" : "=r"(s_ready));
+      }
+
+      // ---- epilogue: eight partial results per query row (4 warpgroups x 2 copies); (warpgroup 0, copy 0) merges
+      uint32_t o[DH];
+      if (n_mine > 0) {
+        mbar_wait(&bars->o_full[g], (n_mine - 1) & 1);
+        tcgen05_fence_after();
+        tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < DH; ++i) o[i] = 0u;
+      }
+      const float l_mine = l2.x + l2.y;
+      float* cmb_base = reinterpret_cast<float*>(smem + OFF_CMB);
+      const int slot = g * 2 + copy;
+      if (slot != 0) {
+        float* cmb = cmb_base + ((slot - 1) * 64 + r64) * CMB_STRIDE;
+        cmb[0] = m_ref;
+        cmb[1] = l_mine;
+#pragma unroll
+        for (int i = 0; i < DH; ++i) cmb[2 + i] = __uint_as_float(o[i]);
+      }
+      asm volatile("bar.sync 4, 512;" ::: "memory");      // all four warpgroups
+      if (slot == 0) {
+        float m = m_ref;
+#pragma unroll
+        for (int pi = 0; pi < 7; ++pi) m = fmaxf(m, cmb_base[(pi * 64 + r64) * CMB_STRIDE]);
+        const float m_safe = m == -INFINITY ? 0.f : m;
+        const float a_own = ex2_approx(m_ref - m_safe);
+        float l_tot = a_own * l_mine;
+        float acc[DH];
+#pragma unroll
+        for (int i = 0; i < DH; ++i) acc[i] = __uint_as_float(o[i]) * a_own;
+#pragma unroll
+        for (int pi = 0; pi < 7; ++pi) {
+          const float* cmb = cmb_base + (pi * 64 + r64) * CMB_STRIDE;
+          const float a_p = ex2_approx(cmb[0] - m_safe);
+          l_tot = fmaf(a_p, cmb[1], l_tot);
+#pragma unroll
+          for (int i = 0; i < DH; ++i) acc[i] = fmaf(a_p, cmb[2 + i], acc[i]);
+        }
+        const float inv = 1.0f / l_tot;
+        const int q = q0 + r64;
+        if (q < Lq) {
+          if (kLse) lse[(static_cast<size_t>(b) * H + h) * lse_pitch + q] = m_safe + __log2f(l_tot);
+          uint4* op = reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * Lq + q) * ldo + h * DH);
+#pragma unroll
+          for (int i = 0; i < DH / 8; ++i) {
+            uint4 w;
+            w.x = pack_bf16x2(acc[8 * i + 0] * inv, acc[8 * i + 1] * inv);
+            w.y = pack_bf16x2(acc[8 * i + 2] * inv, acc[8 * i + 3] * inv);
+            w.z = pack_bf16x2(acc[8 * i + 4] * inv, acc[8 * i + 5] * inv);
+            w.w = pack_bf16x2(acc[8 * i + 6] * inv, acc[8 * i + 7] * inv);
+            op[i] = w;
+          }
+        }
+      }
+      };
+      if (dup) run_softmax_dup();
+      else if (split) run_softmax(std::true_type{});
+      else run_softmax(std::false_type{});
     }
   }
 
@@ -721,7 +910,7 @@ using namespace attn;
 constexpr int KMW = 128;                         // key-validity words per warp (keys up to 8192 -> else the in-loop fallback)
 constexpr int OFF_Q2 = 0;                        // two Q buffers of two tiles each
 constexpr int OFF_K = 2 * 2 * Q_BYTES, OFF_VT = OFF_K + STAGES * K_BYTES, OFF_CMB = OFF_VT + STAGES * VT_BYTES;
-constexpr int OFF_KMASK = OFF_CMB + CMB_BYTES;
+constexpr int OFF_KMASK = OFF_CMB + CMB_BYTES_3;
 constexpr int OFF_BAR = OFF_KMASK + 16 * KMW * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "attention (persistent): shared memory budget");
@@ -1179,6 +1368,9 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_tensor_map_2d(&tmVt, a.vt, a.vt_pitch, static_cast<int64_t>(a.B) * a.H * DH, a.vt_pitch, 64, DH, 128);
   if (rc) return rc;
+  CUtensorMap tmQ64;       // 64-row box of Q: single-tile CTAs with at most 64 query rows load their rows twice
+  rc = make_tensor_map_2d(&tmQ64, a.q, a.H * DH, static_cast<int64_t>(a.B) * a.Lq, a.ldq, DH, BQ / 2, 64);
+  if (rc) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -1211,10 +1403,10 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   }
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
   if (a.lse != nullptr)
-    attention_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
+    attention_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, tmQ64, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
                                                                     a.lse, a.lse_pitch, a.H, a.Lq, a.Lk, a.ldo);
   else
-    attention_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
+    attention_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, tmQ64, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
                                                                      nullptr, 0, a.H, a.Lq, a.Lk, a.ldo);
   return svol_check_launch("attention_tc");
 }
