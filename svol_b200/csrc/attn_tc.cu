@@ -328,6 +328,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&bars->kv_empty[s], n_q);          // one commit per active MMA issuer
     }
     fence_barrier_init();
+    // The Q tile(s) and the first fills of the K / V^T ring are requested HERE, before the CTA-wide barrier below: the loads
+    // only need the barriers this thread has just initialised, and their L2 / DRAM latency then overlaps the tensor-memory
+    // allocation, the barrier and the role set-up instead of following them (a CTA lives for only ~13 key tiles).
+    mbar_arrive_expect_tx(&bars->q_full, n_q * Q_BYTES);
+    if (dup) {          // the same 64 rows into both halves of the tile (64 rows x 64 B = 4 KB: a whole number of swizzle atoms)
+      tma_load_2d(smem, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
+      tma_load_2d(smem + Q_BYTES / 2, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
+    } else {
+      for (int t = 0; t < n_q; ++t)
+        tma_load_2d(smem + t * Q_BYTES, &tmQ, &bars->q_full, h * DH, b * Lq + q0 + t * BQ);
+    }
+    const int vrow = (b * H + h) * DH;
+    for (int j = 0; j < min(n_tiles, STAGES); ++j) {
+      mbar_arrive_expect_tx(&bars->kv_full[j], K_BYTES + VT_BYTES);
+      tma_load_2d(smem + OFF_K + j * K_BYTES, &tmK, &bars->kv_full[j], h * DH, b * Lk + j * BKV);
+      tma_load_2d(smem + OFF_VT + j * VT_BYTES, &tmVt, &bars->kv_full[j], j * BKV, vrow);
+      tma_load_2d(smem + OFF_VT + j * VT_BYTES + VT_KB_BYTES, &tmVt, &bars->kv_full[j], j * BKV + HALF, vrow);
+    }
   }
   if (warp == 17) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tcgen05_fence_before();
@@ -342,16 +360,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 16) {
       // ------------------------------------------------------------------ TMA producer
       if (elect_one()) {
-        mbar_arrive_expect_tx(&bars->q_full, n_q * Q_BYTES);
-        if (dup) {          // the same 64 rows into both halves of the tile (64 rows x 64 B = 4 KB: a whole number of swizzle atoms)
-          tma_load_2d(smem, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
-          tma_load_2d(smem + Q_BYTES / 2, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
-        } else {
-          for (int t = 0; t < n_q; ++t)
-            tma_load_2d(smem + t * Q_BYTES, &tmQ, &bars->q_full, h * DH, b * Lq + q0 + t * BQ);
-        }
+        // (Q and the first STAGES fills were requested in the prologue)
         const int vrow = (b * H + h) * DH;
-        for (int j = 0; j < n_tiles; ++j) {
+        for (int j = STAGES; j < n_tiles; ++j) {
           const int s = j % STAGES;
           mbar_wait(&bars->kv_empty[s], ((j / STAGES) & 1) ^ 1);
           mbar_arrive_expect_tx(&bars->kv_full[s], K_BYTES + VT_BYTES);
