@@ -331,6 +331,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // The Q tile(s) and the first fills of the K / V^T ring are requested HERE, before the CTA-wide barrier below: the loads
     // only need the barriers this thread has just initialised, and their L2 / DRAM latency then overlaps the tensor-memory
     // allocation, the barrier and the role set-up instead of following them (a CTA lives for only ~13 key tiles).
+    // (Programmatic dependent launch: Q / K / V^T are the previous kernel's outputs -- this thread waits for it here, the
+    // other warps at the CTA-wide barrier below, i.e. barrier set-up and tensor-memory allocation run under its tail.)
+    griddep_wait();
     mbar_arrive_expect_tx(&bars->q_full, n_q * Q_BYTES);
     if (dup) {          // the same 64 rows into both halves of the tile (64 rows x 64 B = 4 KB: a whole number of swizzle atoms)
       tma_load_2d(smem, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
@@ -346,6 +349,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tma_load_2d(smem + OFF_VT + j * VT_BYTES, &tmVt, &bars->kv_full[j], j * BKV, vrow);
       tma_load_2d(smem + OFF_VT + j * VT_BYTES + VT_KB_BYTES, &tmVt, &bars->kv_full[j], j * BKV + HALF, vrow);
     }
+    if (n_tiles <= STAGES) griddep_launch_dependents();     // every load of this CTA is requested (see the producer)
   }
   if (warp == 17) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tcgen05_fence_before();
@@ -369,6 +373,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tma_load_2d(smem + OFF_K + s * K_BYTES, &tmK, &bars->kv_full[s], h * DH, b * Lk + j * BKV);
           tma_load_2d(smem + OFF_VT + s * VT_BYTES, &tmVt, &bars->kv_full[s], j * BKV, vrow);
           tma_load_2d(smem + OFF_VT + s * VT_BYTES + VT_KB_BYTES, &tmVt, &bars->kv_full[s], j * BKV + HALF, vrow);
+          // last load requested: once every CTA of the grid is this far (or gone) the next kernel on the stream may start
+          // on the SMs that free up and run its set-up under this kernel's tail
+          if (j == n_tiles - 1) griddep_launch_dependents();
         }
       }
     } else if (warp == 17 || warp == 18) {
@@ -1416,9 +1423,11 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   if (a.lse != nullptr)
     attention_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, tmQ64, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
                                                                     a.lse, a.lse_pitch, a.H, a.Lq, a.Lk, a.ldo);
-  else
-    attention_tc_kernel<false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, tmQ64, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
-                                                                     nullptr, 0, a.H, a.Lq, a.Lk, a.ldo);
+  else {       // inference: programmatic dependent launch (common.cuh)
+    cudaError_t e = launch_kernel_pdl(attention_tc_kernel<false>, grid, dim3(THREADS), SMEM_BYTES, stream, tmQ, tmK, tmVt, tmQ64, a.key_mask,
+                                      reinterpret_cast<__nv_bfloat16*>(a.out), nullptr, 0, a.H, a.Lq, a.Lk, a.ldo);
+    if (e != cudaSuccess) return svol_fail_cuda(e, "attention_tc launch");
+  }
   return svol_check_launch("attention_tc");
 }
 

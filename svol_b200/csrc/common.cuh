@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdio>
+#include <cstdlib>
 
 #ifndef SVOL_SPIN_LIMIT
 #define SVOL_SPIN_LIMIT (1u << 22)
@@ -33,6 +34,38 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ------------------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_kernel_pdl below) may start as soon as
+// every CTA of the kernel before it on the stream has executed griddep_launch_dependents() (or exited): its CTAs take the
+// SMs the predecessor's CTAs leave and run their set-up (barriers, tensor-memory allocation, parameter / weight loads)
+// under the predecessor's tail.  griddep_wait() returns once the predecessor has COMPLETED and its writes are visible;
+// nothing the predecessor produced may be touched (and nothing it still reads overwritten) before it.  Both are no-ops
+// in a kernel launched the ordinary way.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// SVOL_B200_PDL=1 switches programmatic dependent launches on (default: every kernel waits for its predecessor's exit)
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SVOL_B200_PDL"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ------------------------------------------------------------------------------ mbarrier

@@ -224,8 +224,12 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     } else if (warp == 2) {
       // ------------------------------------------------------------------ x-tile producer
       if (elect_one()) {
+        // (programmatic dependent launch: the weight producer above already fills its ring under the tail of the kernel that
+        // produces x; the token tiles wait for that kernel to complete)
+        griddep_wait();
         for (int it = 0; it < my_tiles; ++it) {
           const int m_blk = tile_of(it);
+          if (it == my_tiles - 1) griddep_launch_dependents();   // last tile: the next kernel may take the SMs that free up
           mbar_wait(&bars->x_free, (it & 1) ^ 1);
           mbar_arrive_expect_tx(&bars->x_full, X_BYTES);
           for (int kb = 0; kb < D / BKX; ++kb)
@@ -288,6 +292,7 @@ ffn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // ------------------------------------------------------------------ epilogue (8 warps)
     if (kEW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    griddep_wait();
     const int quarter = warp & 3;                             // TMEM lane quarter this warp may read
     const int half = (warp - FIRST_EPI_WARP) >> 2;            // column group: which COLS of the 256 columns
     const int r = quarter * 32 + lane;                        // row inside the tile
@@ -543,19 +548,22 @@ int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream) {
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = wide ? cudaLaunchKernelEx(&cfg, ffn_tc_kernel<true, 16>, tmX, tmW1, tmW2, tmOut, tmOutPos, p)
                          : cudaLaunchKernelEx(&cfg, ffn_tc_kernel<true, 8>, tmX, tmW1, tmW2, tmOut, tmOutPos, p);
     if (e != cudaSuccess) return svol_fail_cuda(e, "ffn: cluster launch");
     return svol_check_launch("ffn_tc (2-CTA multicast)");
   }
   const int grid = ctas_needed < sm_count() ? ctas_needed : sm_count();
-  if (wide) ffn_tc_kernel<false, 16><<<grid, threads, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, tmOutPos, p);
-  else ffn_tc_kernel<false, 8><<<grid, threads, SMEM_BYTES, stream>>>(tmX, tmW1, tmW2, tmOut, tmOutPos, p);
+  cudaError_t e = wide ? launch_kernel_pdl(ffn_tc_kernel<false, 16>, dim3(grid), dim3(threads), SMEM_BYTES, stream, tmX, tmW1, tmW2, tmOut, tmOutPos, p)
+                       : launch_kernel_pdl(ffn_tc_kernel<false, 8>, dim3(grid), dim3(threads), SMEM_BYTES, stream, tmX, tmW1, tmW2, tmOut, tmOutPos, p);
+  if (e != cudaSuccess) return svol_fail_cuda(e, "ffn: launch");
   return svol_check_launch("ffn_tc");
 }
 

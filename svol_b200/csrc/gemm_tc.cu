@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutPos,
                     const __grid_constant__ CUtensorMap tmA2, const GemmEpilogue ep, int M, int N, int K, int split_block,
-                    int k_splits, float* __restrict__ out_f32, int ld_f32, int mn_major, int l2_prefetch) {
+                    int k_splits, float* __restrict__ out_f32, int ld_f32, int mn_major, int l2_prefetch, int pdl) {
   using namespace gemm;
   using C = Cfg<kResidentW>;
   // mn_major (training, streaming variant): the operands are given untransposed, A = dY [K rows, M columns] and
@@ -229,10 +229,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
+      // Programmatic dependent launch (pdl): this CTA may have started under the tail of the kernel that produces A / the
+      // residual.  The resident weight block does not depend on it, so all of it is requested first and only then does the
+      // producer wait for the predecessor (otherwise the weight k blocks stay interleaved with the first A tile's).
+      const bool w_first = kResidentW && pdl && my_tiles > 0;
+      if (w_first)
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_arrive_expect_tx(&tail->w_full[kb], B_BYTES);
+          tma_load_2d(smem + kb * B_BYTES, &tmB, &tail->w_full[kb], kb * BK, my_n * BN);
+        }
+      griddep_wait();
       for (int it = 0; it < my_tiles; ++it) {
         int m_blk, n_blk, kb0, kb1;
         tile_coords(it, m_blk, n_blk);
         k_range(it, kb0, kb1);
+        // last tile of this CTA: the next kernel on the stream may take the SMs that free up from here on
+        if (it == my_tiles - 1) griddep_launch_dependents();
         if (kResidentW && l2_prefetch) {
           // One CTA per SM and a 3-stage ring (48 KB) keep less than one A tile in flight: the loads were latency-bound
           // (phase trace: 3.9 k clk per tile in the MMA issuer against 2.3 k of tensor work) and the epilogue's residual read
@@ -250,7 +262,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (kResidentW && it == 0) {      // this CTA's weight block, k block by k block, interleaved with the first A tiles
+          if (kResidentW && it == 0 && !w_first) {      // this CTA's weight block, k block by k block, interleaved with the first A tiles
             mbar_arrive_expect_tx(&tail->w_full[kb], B_BYTES);
             tma_load_2d(smem + kb * B_BYTES, &tmB, &tail->w_full[kb], kb * BK, my_n * BN);
           }
@@ -316,6 +328,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    griddep_wait();                             // residual / pos operands are read with plain loads below
     const int quarter = warp & 3;               // TMEM lane quarter this warp may read
     const int half = (warp - FIRST_EPI_WARP) >> 2;           // which 128 of the tile's 256 columns
     const int r_in_tile = quarter * 32 + lane;
@@ -612,9 +625,18 @@ static int launch_variant(const GemmArgs& a, const CUtensorMap& tmA, const CUten
   }
   const char* env_pf = getenv("SVOL_GEMM_L2_PREFETCH");       // read per launch (A/B measurements); default on
   const int l2_prefetch = env_pf ? atoi(env_pf) : 1;
+  // inference instantiations: programmatic dependent launch (set-up and the resident weight block overlap the tail of the
+  // kernel before this one on the stream); the training kernels are launched the ordinary way
+  if (!kTrain) {
+    cudaError_t e = launch_kernel_pdl(gemm_bf16_tc_kernel<kResidentW, kTrain>, dim3(grid), dim3(THREADS), C::SMEM_BYTES, stream, tmA, tmB,
+                                      tmOut, tmOutPos, tmA2, a.ep, a.M, a.N, a.K, a.split_block, k_splits, a.out_f32, a.ld_f32,
+                                      a.mn_major, l2_prefetch, pdl_enabled() ? 1 : 0);
+    if (e != cudaSuccess) return svol_fail_cuda(e, "gemm_bf16_tc launch");
+    return svol_check_launch("gemm_bf16_tc");
+  }
   gemm_bf16_tc_kernel<kResidentW, kTrain><<<grid, THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmOutPos, tmA2, a.ep, a.M, a.N, a.K,
                                                                             a.split_block, k_splits, a.out_f32, a.ld_f32, a.mn_major,
-                                                                            l2_prefetch);
+                                                                            l2_prefetch, 0);
   return svol_check_launch("gemm_bf16_tc");
 }
 
