@@ -42,6 +42,8 @@
 // warpgroups: "tile slot" t = 0 / 1 takes the even / odd key tiles, each slot with its own issuer, S / P / O columns and
 // running maxima, and the four partial results per row are merged at the end.
 // Q is pre-scaled by log2(e)/sqrt(dh) when it is produced, so the softmax is a bare ex2.
+#include <atomic>
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -75,6 +77,9 @@ constexpr float RESCALE_THRESHOLD = 8.0f;       // log2 units
 #ifndef SVOL_ATTN_STAGGER
 #define SVOL_ATTN_STAGGER 550
 #endif
+#ifndef SVOL_ATTN_REINIT_MODE
+#define SVOL_ATTN_REINIT_MODE 0
+#endif
 constexpr int STAGGER_CLK = SVOL_ATTN_STAGGER;  // start offset between consecutive warpgroups (~ period / 4)
 }  // namespace attn
 
@@ -84,7 +89,11 @@ struct AttnBars {
   uint64_t p_ready[4], o_full[4];
   uint64_t kv_full[attn::STAGES], kv_empty[attn::STAGES];
   uint32_t tmem_base, pad;
+  int next_item, cur_item;   // looping CTAs (kLoop): the work item after the current one / the current one
 };
+static_assert(offsetof(AttnBars, tmem_base) == (17 + 2 * attn::STAGES) * 8, "the 17 + 2 x STAGES barriers are re-initialised as one array");
+static_assert(offsetof(AttnBars, s_free) - offsetof(AttnBars, s_full) == 32 && offsetof(AttnBars, p_ready) - offsetof(AttnBars, s_full) == 64 &&
+              offsetof(AttnBars, o_full) - offsetof(AttnBars, s_full) == 96, "softmax warps address their four barriers from one register");
 
 #ifdef SVOL_ATTN_TRACE
 // Debug build only (-DSVOL_ATTN_TRACE): CTA (0,0,0) records clock64() at phase boundaries of every key tile.
@@ -224,6 +233,28 @@ __device__ __forceinline__ float2 ex2_poly2(float2 sc, float2 magic_m, float2 ne
 }
 
 // Row maximum of the 64 scores a thread holds; kMasked additionally overwrites invalid keys with -inf.
+// mbarrier operations on a 32-bit shared-memory ADDRESS (the softmax warps keep one opaque address register per thread:
+// given pointers, ptxas re-derived the shared-window conversion and the warp index from special registers -- S2R / S2UR,
+// tens of cycles each -- in front of every barrier operation of the latency-bound key loop)
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > SVOL_SPIN_LIMIT) __trap();
+  }
+}
+
 template <bool kMasked>
 __device__ __forceinline__ float half_row_max(uint32_t (&s)[attn::HALF], const uint32_t (&words)[2]) {
   if (kMasked) {
@@ -264,12 +295,31 @@ __device__ __forceinline__ float part32_row_max(uint32_t (&s)[32], uint32_t word
 
 // kLse: the training forward also stores each row's base-2 log-sum-exp (a separate instantiation so that the inference
 // kernel keeps the register allocation it was tuned with).
-template <bool kLse>
+//
+// kLoop (inference, more work items than SMs): ONE CTA per SM walks work items instead of exiting after one -- the first is
+// its block index, the following ones come from a global counter (fetched one item ahead by the TMA thread).  Nothing is
+// carried across items except the tensor-memory allocation: after an item all 640 threads meet at a CTA-wide barrier, warp 16
+// re-initialises the mbarriers (so every phase count below starts from zero again, exactly as in a fresh CTA) and requests
+// the next item's Q / K / V^T tiles, and a second barrier releases the roles.  That replaces the exit / block-scheduler /
+// launch / tensor-memory-allocation gap between two CTAs on an SM (measured 1.2 us, 5 % of the video self-attention) by two
+// barriers; the key loop is the same code with the same register budget (unlike attention_p_kernel below, which overlaps
+// items and pays for the cross-item state inside the loop).
+// MEASURED (B200, kernels alone, us per launch: video self / cross / query self-attention), OFF by default (SVOL_ATTN_LOOP=1):
+//   one CTA per item (default)                 245.4 / 71.0 / 28.7
+//   this variant's code, one CTA per item      259.5 / 77.1 / 33.7     (SVOL_ATTN_LOOP=2)
+//   looping CTAs                               248.5 / 81.2 / 31.7
+// i.e. the hand-over does save what the timeline predicted on the video shape (11 us of 259) but the same source inside an
+// item loop compiles to a slower item (547 instead of 537 instructions per key tile and more special-register reads on the
+// latency-bound chain; bit-identical results), and the heterogeneous cross-attention items (a two-tile item and a
+// 64-row duplicated-row item per head) lose on top of that.  Outputs are bit-identical to the default kernel's
+// (tests/test_kernels_gpu.py::test_looping_attention_ctas_match_one_cta_per_item).
+template <bool kLse, bool kLoop>
 __global__ void __launch_bounds__(attn::THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmVt, const __grid_constant__ CUtensorMap tmQ64,
                     const float* __restrict__ key_mask,
-                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int lse_pitch, int H, int Lq, int Lk, int ldo) {
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int lse_pitch, int H, int Lq, int Lk, int ldo,
+                    int n_items, unsigned int* __restrict__ item_counter) {
   using namespace attn;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -281,7 +331,41 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int warp = threadIdx.x >> 5;
   auto lane_id = []() { int l; asm volatile("mov.u32 %0, %%laneid;" : "=r"(l)); return l; };
   auto tmem_base_of = [](const AttnBars* b) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&b->tmem_base)) : "memory"); return v; };
-  const int q0 = blockIdx.x * (2 * BQ), h = blockIdx.y, b = blockIdx.z;
+  // work item = (pair of query tiles, head, sample); kLoop: linear index, query pair fastest (the CTAs running at the same
+  // time share a head's K / V^T in L2, as the 3-D grid's launch order does)
+  int q0, h, b, n_q;
+  bool split, dup;
+  const int n_tiles = (Lk + BKV - 1) / BKV;
+  auto decode_item = [&](int item) {
+    if (kLoop) {
+      const int nx = (Lq + 2 * BQ - 1) / (2 * BQ);
+      q0 = (item % nx) * (2 * BQ); h = (item / nx) % H; b = item / (nx * H);
+    } else {
+      q0 = blockIdx.x * (2 * BQ); h = blockIdx.y; b = blockIdx.z;
+    }
+    n_q = (q0 + BQ < Lq) ? 2 : 1;          // is the second query tile of this item populated?
+    // single-tile item: both tile slots work on query tile 0, slot t on key tiles t, t + 2, ... (see the header)
+    // Both variants of the role code below are separate instantiations (generic lambdas on a compile-time flag): the
+    // two-tile path keeps exactly the code it was tuned with (key tile == iteration, no extra live values).
+    // (with fewer than four key tiles the extra merge costs more than the shorter walk saves: query self-attention, 3 tiles)
+    split = n_q == 1 && n_tiles >= 4;
+    // ... and when that one query tile holds at most 64 rows (cross-attention: 320 = 2 x 128 + 64 queries; video self-attention:
+    // 1568 = 12 x 128 + 32), the rows are loaded TWICE (tile rows 64..127 = rows 0..63 again) and the two copies split every
+    // half tile's 64 keys: copy 0 exponentiates keys [0, 32), copy 1 keys [32, 64), each writing zeros for the other part's
+    // probabilities once.  The MMAs are unchanged; every softmax warp issues half the MUFU / row-max work per key tile
+    // instead of spending it on rows that do not exist, and eight partial results per row are merged at the end.
+    dup = split && Lq - q0 <= 64;
+  };
+  // kLoop: the current item lives in SHARED memory (bars->cur_item) and is re-read where it is needed (item set-up, output
+  // addresses in the epilogue) instead of being carried in registers through the key loop: with the item, its coordinates and
+  // an iteration count live across the loop ptxas rematerialised the shared-memory base (S2UR / S2R of special registers) in
+  // front of every barrier operation of the key loop -- 7 % more instructions on the latency-bound chain, 10 % slower.
+  auto current_item = [&]() -> int {
+    int v = 0;
+    if (kLoop) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&bars->cur_item)) : "memory");
+    return v;
+  };
+  decode_item(kLoop ? static_cast<int>(blockIdx.x) : 0);
 #ifdef SVOL_ATTN_TRACE
   const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
   if (threadIdx.x == 0 && cta_lin < 8192) {
@@ -290,22 +374,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     g_attn_cta[cta_lin][1] = global_ns();
   }
 #endif
-  const int n_tiles = (Lk + BKV - 1) / BKV;
-  const int n_q = (q0 + BQ < Lq) ? 2 : 1;          // is the second query tile of this CTA populated?
   // key tiles whose upper 64 keys hold at least one in-range key: when Lk % 128 is in (0, 64] the upper half of the last
   // tile is empty and its QK^T / softmax / PV are skipped altogether (1568 keys: 1 of 26 half tiles; 320 keys: 1 of 6)
   const int n_hi = Lk > HALF ? (Lk - HALF + BKV - 1) / BKV : 0;
-  // single-tile CTA: both tile slots work on query tile 0, slot t on key tiles t, t + 2, ... (see the header)
-  // Both variants of the role code below are separate instantiations (generic lambdas on a compile-time flag): the
-  // two-tile path keeps exactly the code it was tuned with (key tile == iteration, no extra live values).
-  // (with fewer than four key tiles the extra merge costs more than the shorter walk saves: query self-attention, 3 tiles)
-  const bool split = n_q == 1 && n_tiles >= 4;
-  // ... and when that one query tile holds at most 64 rows (cross-attention: 320 = 2 x 128 + 64 queries; video self-attention:
-  // 1568 = 12 x 128 + 32), the rows are loaded TWICE (tile rows 64..127 = rows 0..63 again) and the two copies split every
-  // half tile's 64 keys: copy 0 exponentiates keys [0, 32), copy 1 keys [32, 64), each writing zeros for the other part's
-  // probabilities once.  The MMAs are unchanged; every softmax warp issues half the MUFU / row-max work per key tile
-  // instead of spending it on rows that do not exist, and eight partial results per row are merged at the end.
-  const bool dup = split && Lq - q0 <= 64;
 #ifdef SVOL_ATTN_TRACE
 #ifdef SVOL_ATTN_TRACE_LAST      // trace the LAST query-tile pair of (sample 0, head 0): the single-tile CTA when Lq % 256 is in (0, 128]
   const bool trace_on = blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane_id() == 0 && ((warp & 3) == 0 || warp >= 16);
@@ -314,6 +385,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #endif
 #endif
 
+  // Requests the Q tile(s) and the first fills of the K / V^T ring of the current item (one thread; the barriers are fresh)
+  auto request_first_tiles = [&]() {
+    mbar_arrive_expect_tx(&bars->q_full, n_q * Q_BYTES);
+    if (dup) {          // the same 64 rows into both halves of the tile (64 rows x 64 B = 4 KB: a whole number of swizzle atoms)
+      tma_load_2d(smem, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
+      tma_load_2d(smem + Q_BYTES / 2, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
+    } else {
+      for (int t = 0; t < n_q; ++t)
+        tma_load_2d(smem + t * Q_BYTES, &tmQ, &bars->q_full, h * DH, b * Lq + q0 + t * BQ);
+    }
+    const int vrow = (b * H + h) * DH;
+    for (int j = 0; j < min(n_tiles, STAGES); ++j) {
+      mbar_arrive_expect_tx(&bars->kv_full[j], K_BYTES + VT_BYTES);
+      tma_load_2d(smem + OFF_K + j * K_BYTES, &tmK, &bars->kv_full[j], h * DH, b * Lk + j * BKV);
+      tma_load_2d(smem + OFF_VT + j * VT_BYTES, &tmVt, &bars->kv_full[j], j * BKV, vrow);
+      tma_load_2d(smem + OFF_VT + j * VT_BYTES + VT_KB_BYTES, &tmVt, &bars->kv_full[j], j * BKV + HALF, vrow);
+    }
+  };
   if (warp == 16 && lane_id() == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmVt);
     mbar_init(&bars->q_full, 1);
@@ -334,37 +423,74 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // (Programmatic dependent launch: Q / K / V^T are the previous kernel's outputs -- this thread waits for it here, the
     // other warps at the CTA-wide barrier below, i.e. barrier set-up and tensor-memory allocation run under its tail.)
     griddep_wait();
-    mbar_arrive_expect_tx(&bars->q_full, n_q * Q_BYTES);
-    if (dup) {          // the same 64 rows into both halves of the tile (64 rows x 64 B = 4 KB: a whole number of swizzle atoms)
-      tma_load_2d(smem, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
-      tma_load_2d(smem + Q_BYTES / 2, &tmQ64, &bars->q_full, h * DH, b * Lq + q0);
-    } else {
-      for (int t = 0; t < n_q; ++t)
-        tma_load_2d(smem + t * Q_BYTES, &tmQ, &bars->q_full, h * DH, b * Lq + q0 + t * BQ);
-    }
-    const int vrow = (b * H + h) * DH;
-    for (int j = 0; j < min(n_tiles, STAGES); ++j) {
-      mbar_arrive_expect_tx(&bars->kv_full[j], K_BYTES + VT_BYTES);
-      tma_load_2d(smem + OFF_K + j * K_BYTES, &tmK, &bars->kv_full[j], h * DH, b * Lk + j * BKV);
-      tma_load_2d(smem + OFF_VT + j * VT_BYTES, &tmVt, &bars->kv_full[j], j * BKV, vrow);
-      tma_load_2d(smem + OFF_VT + j * VT_BYTES + VT_KB_BYTES, &tmVt, &bars->kv_full[j], j * BKV + HALF, vrow);
-    }
-    if (n_tiles <= STAGES) griddep_launch_dependents();     // every load of this CTA is requested (see the producer)
+    request_first_tiles();
+    if (kLoop) bars->cur_item = static_cast<int>(blockIdx.x);
+    if (!kLoop && n_tiles <= STAGES) griddep_launch_dependents();     // every load of this CTA is requested (see the producer)
   }
   if (warp == 17) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
 
+  // kLoop: end of a work item, executed by all 640 threads.  Returns the next item (>= n_items: none).
+  auto next_item_sync = [&]() -> int {
+    __syncwarp();                                    // (single-thread roles: the whole warp arrives together)
+    tcgen05_fence_before();
+    asm volatile("bar.sync 0;" ::: "memory");        // every role is done with the item: tiles consumed, O read out, P / S idle
+    // (the producer writes next_item for the FOLLOWING item only after the second barrier below)
+    const int nxt = *reinterpret_cast<volatile int*>(&bars->next_item);
+    if (warp == 16 && nxt < n_items) {
+      const int l = lane_id();
+      // The only asynchronous arrivals nobody has waited for are the issuers' last releases of the ring stages: stage l
+      // was released once per key tile l, l + STAGES, ... that has an upper half
+      if (l < STAGES) {
+        const int rel = n_hi > l ? (n_hi - l + STAGES - 1) / STAGES : 0;
+        if (rel > 0) mbar_wait(&bars->kv_empty[l], (rel - 1) & 1);
+      }
+      __syncwarp();
+      decode_item(nxt);
+      // fresh barriers (one or two per lane), so that every phase count of the next item starts from zero
+      uint64_t* bar_array = reinterpret_cast<uint64_t*>(bars);
+#if SVOL_ATTN_REINIT_MODE == 0
+      if (l == 0) {
+        bars->cur_item = nxt;
+        for (int i = 0; i < 17 + 2 * STAGES; ++i) {
+          const uint32_t count = (i >= 5 && i < 13) ? 4u : (i >= 17 + STAGES ? static_cast<uint32_t>(n_q) : 1u);
+          mbar_init(bar_array + i, count);
+        }
+        fence_barrier_init();
+        request_first_tiles();
+      }
+#else
+      for (int i = l; i < 17 + 2 * STAGES; i += 32) {
+        const uint32_t count = (i >= 5 && i < 13) ? 4u : (i >= 17 + STAGES ? static_cast<uint32_t>(n_q) : 1u);
+        if (SVOL_ATTN_REINIT_MODE == 2) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar_array + i)) : "memory");
+        mbar_init(bar_array + i, count);
+      }
+      fence_barrier_init();
+      __syncwarp();
+      if (l == 0) { bars->cur_item = nxt; request_first_tiles(); }
+#endif
+    }
+    asm volatile("bar.sync 0;" ::: "memory");
+    tcgen05_fence_after();
+    return nxt;
+  };
+
   // register re-split (each role branch starts with its own setmaxnreg so that it dominates the role's code).
   // The CTA is launched with 640 x 96 registers and setmaxnreg only redistributes them: 4 x 112 + 32 = 5 x 96.  (With 24
   // for the fifth warpgroup the issuers' descriptors and counters were spilled INSIDE their issue loops.)
   if (warp >= 16) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    for (;;) {
+    if (kLoop) decode_item(current_item());
     if (warp == 16) {
       // ------------------------------------------------------------------ TMA producer
       if (elect_one()) {
-        // (Q and the first STAGES fills were requested in the prologue)
+        // kLoop: the item after this one is fetched now and published when this item's loads are all requested
+        unsigned int fetched = 0;
+        if (kLoop) fetched = atomicAdd(item_counter, 1u);
+        // (Q and the first STAGES fills were requested in the prologue / at the end of the previous item)
         const int vrow = (b * H + h) * DH;
         for (int j = STAGES; j < n_tiles; ++j) {
           const int s = j % STAGES;
@@ -375,7 +501,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tma_load_2d(smem + OFF_VT + s * VT_BYTES + VT_KB_BYTES, &tmVt, &bars->kv_full[s], j * BKV + HALF, vrow);
           // last load requested: once every CTA of the grid is this far (or gone) the next kernel on the stream may start
           // on the SMs that free up and run its set-up under this kernel's tail
-          if (j == n_tiles - 1) griddep_launch_dependents();
+          if (!kLoop && j == n_tiles - 1) griddep_launch_dependents();
+        }
+        if (kLoop) {
+          bars->next_item = static_cast<int>(fetched + gridDim.x);
+          // n_items fetches per launch (one per item processed); the last one leaves the counter at zero for the next launch
+          if (fetched == static_cast<unsigned int>(n_items - 1)) atomicExch(item_counter, 0u);
         }
       }
     } else if (warp == 17 || warp == 18) {
@@ -440,8 +571,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       };
       if (split) run_issuer(std::true_type{}); else run_issuer(std::false_type{});
     }
+    if (!kLoop) break;
+    if (next_item_sync() >= n_items) break;
+    }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // Barrier probes are software-pipelined (see the key loop); their predicate registers are declared once
+    asm volatile(".reg .pred p_of, p_sf;");
+    for (;;) {
+    if (kLoop) decode_item(current_item());
     const int g = warp >> 2;                            // softmax warpgroup
     const int t = g >> 1, half = g & 1;                 // query tile, key half
     const int lane = lane_id();
@@ -484,8 +622,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
       // Barrier probes are software-pipelined: a (non-blocking) mbarrier.test_wait is issued well before its result
       // is needed and consumed after independent work; the blocking wait is only the fallback.
-      asm volatile(".reg .pred p_of, p_sf;");
-      const uint32_t a_sfull = smem_u32(&bars->s_full[g]), a_ofull = smem_u32(&bars->o_full[g]);
+      // a_g = address of s_full[g]; s_free[g] / p_ready[g] / o_full[g] follow at +32 / +64 / +96 (AttnBars).  Opaque, so that it
+      // is computed once per item and kept in a register (see mbar_wait_a); likewise the lane-0 flag of the arrivals.
+      uint32_t a_g = smem_u32(&bars->s_full[g]);
+      uint32_t leader = lane == 0 ? 1u : 0u;
+      asm volatile("" : "+r"(a_g), "+r"(leader));
+      const uint32_t a_sfull = a_g, a_ofull = a_g + 96;
 
       auto run_softmax = [&](auto split_tag) {
       constexpr bool kSplit = decltype(split_tag)::value;
@@ -499,7 +641,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int j = j0 + j_step * i;                    // key tile; barrier phases count i, this warpgroup's own iterations
         const int kv0 = j * BKV + half * HALF;
         SVOL_TR(g, i, 0);
-        if (!s_ready) mbar_wait(&bars->s_full[g], i & 1);
+        if (!s_ready) mbar_wait_a(a_g, i & 1);
         SVOL_TR(g, i, 1);
         tcgen05_fence_after();
         uint32_t s[HALF];
@@ -510,7 +652,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // scores are in registers: hand the TMEM buffer back so the next QK^T can start now
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->s_free[g]);
+        if (leader) mbar_arrive_a(a_g + 32);
         SVOL_TR(g, i, 4);
 
         // validity of this half tile's 64 keys as two 32-bit words (ragged tail and key_padding_mask); the
@@ -556,7 +698,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const bool need = mx_seen > m_ref + RESCALE_THRESHOLD;
           if (__any_sync(0xffffffffu, need)) {
             const float alpha = need ? ex2_approx(m_ref - mx_seen) : 1.0f;   // (m_ref = -inf, finite maximum) -> 0
-            mbar_wait(&bars->o_full[g], (i - 1) & 1);                  // every earlier P V has landed in O_g
+            mbar_wait_a(a_g + 96, (i - 1) & 1);                  // every earlier P V has landed in O_g
             tcgen05_fence_after();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -641,7 +783,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (i > 0) {
           uint32_t ok;
           asm volatile("selp.u32 %0, 1, 0, p_of;" : "=r"(ok));
-          if (!ok) mbar_wait(&bars->o_full[g], (i - 1) & 1);
+          if (!ok) mbar_wait_a(a_g + 96, (i - 1) & 1);
           tcgen05_fence_after();
         }
         if (i + 1 < n_mine)   // probe the next score tile (its QK^T was issued when this tile's scores were read out)
@@ -652,7 +794,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->p_ready[g]);
+        if (leader) mbar_arrive_a(a_g + 64);
         s_ready = 0;
         if (i + 1 < n_mine) asm volatile("selp.u32 %0, 1, 0, p_sf;" : "=r"(s_ready));
         SVOL_TR(g, i, 7);
@@ -661,7 +803,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // ---- epilogue: O_g is complete once the last P V has landed; merge the partial results of each row
       uint32_t o[DH];
       if (n_mine > 0) {
-        mbar_wait(&bars->o_full[g], (n_mine - 1) & 1);
+        mbar_wait_a(a_g + 96, (n_mine - 1) & 1);
         tcgen05_fence_after();
         tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
         tmem_ld_wait();
@@ -704,6 +846,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int i = 0; i < DH; ++i) acc[i] = fmaf(a_p, cmb[2 + i], acc[i]);
         }
         const float inv = 1.0f / l_tot;
+        if (kLoop) decode_item(current_item());             // (not carried through the key loop: see current_item)
         const int q = q0 + (kSplit ? 0 : t) * BQ + r;
         if (q < Lq) {
           // training forward: base-2 log-sum-exp of the (pre-scaled) scores, so that the backward recomputes
@@ -742,14 +885,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int i = 0; i < n_mine; ++i) {
         const int j = j0 + 2 * i;
         const int kv0 = j * BKV + half * HALF + copy * 32;
-        if (!s_ready) mbar_wait(&bars->s_full[g], i & 1);
+        if (!s_ready) mbar_wait_a(a_g, i & 1);
         tcgen05_fence_after();
         uint32_t s[32];
         tmem_ld_32x32b_x32(t_s + copy * 32, s);
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->s_free[g]);
+        if (leader) mbar_arrive_a(a_g + 32);
 
         uint32_t word = 0xffffffffu;
         if (mask_in_smem) {
@@ -770,7 +913,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const bool need = mx_seen > m_ref + RESCALE_THRESHOLD;
           if (__any_sync(0xffffffffu, need)) {
             const float alpha = need ? ex2_approx(m_ref - mx_seen) : 1.0f;
-            mbar_wait(&bars->o_full[g], (i - 1) & 1);
+            mbar_wait_a(a_g + 96, (i - 1) & 1);
             tcgen05_fence_after();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -806,7 +949,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (i > 0) {
           uint32_t ok;
           asm volatile("selp.u32 %0, 1, 0, p_of;" : "=r"(ok));
-          if (!ok) mbar_wait(&bars->o_full[g], (i - 1) & 1);
+          if (!ok) mbar_wait_a(a_g + 96, (i - 1) & 1);
           tcgen05_fence_after();
         }
         if (i + 1 < n_mine)
@@ -815,7 +958,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars->p_ready[g]);
+        if (leader) mbar_arrive_a(a_g + 64);
         s_ready = 0;
         if (i + 1 < n_mine) asm volatile("selp.u32 %0, 1, 0, p_sf;" : "=r"(s_ready));
       }
@@ -823,7 +966,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // ---- epilogue: eight partial results per query row (4 warpgroups x 2 copies); (warpgroup 0, copy 0) merges
       uint32_t o[DH];
       if (n_mine > 0) {
-        mbar_wait(&bars->o_full[g], (n_mine - 1) & 1);
+        mbar_wait_a(a_g + 96, (n_mine - 1) & 1);
         tcgen05_fence_after();
         tmem_ld_32x32b_x32(t_o, *reinterpret_cast<uint32_t(*)[32]>(&o[0]));
         tmem_ld_wait();
@@ -861,6 +1004,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           for (int i = 0; i < DH; ++i) acc[i] = fmaf(a_p, cmb[2 + i], acc[i]);
         }
         const float inv = 1.0f / l_tot;
+        if (kLoop) decode_item(current_item());
         const int q = q0 + r64;
         if (q < Lq) {
           if (kLse) lse[(static_cast<size_t>(b) * H + h) * lse_pitch + q] = m_safe + __log2f(l_tot);
@@ -880,6 +1024,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (dup) run_softmax_dup();
       else if (split) run_softmax(std::true_type{});
       else run_softmax(std::false_type{});
+    }
+    if (!kLoop) break;
+    if (next_item_sync() >= n_items) break;
     }
   }
 
@@ -1391,8 +1538,9 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   if (rc) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return svol_fail_cuda(e, "attention: cudaFuncSetAttribute");
     configured = true;
   }
@@ -1420,14 +1568,58 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
     return svol_check_launch("attention_tc (persistent)");
   }
   dim3 grid((a.Lq + 2 * BQ - 1) / (2 * BQ), a.H, a.B);
-  if (a.lse != nullptr)
-    attention_tc_kernel<true><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, tmQ64, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
-                                                                    a.lse, a.lse_pitch, a.H, a.Lq, a.Lk, a.ldo);
-  else {       // inference: programmatic dependent launch (common.cuh)
-    cudaError_t e = launch_kernel_pdl(attention_tc_kernel<false>, grid, dim3(THREADS), SMEM_BYTES, stream, tmQ, tmK, tmVt, tmQ64, a.key_mask,
-                                      reinterpret_cast<__nv_bfloat16*>(a.out), nullptr, 0, a.H, a.Lq, a.Lk, a.ldo);
-    if (e != cudaSuccess) return svol_fail_cuda(e, "attention_tc launch");
+  if (a.lse != nullptr) {
+    attention_tc_kernel<true, false><<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmVt, tmQ64, a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out),
+                                                                           a.lse, a.lse_pitch, a.H, a.Lq, a.Lk, a.ldo, n_items, nullptr);
+    return svol_check_launch("attention_tc");
   }
+  // Inference.  SVOL_ATTN_LOOP=1 and more work items than SMs: one looping CTA per SM (kLoop, see the kernel; off by
+  // default -- measured slower).  Every such launch gets its own item counter out of a pool (launches on different streams
+  // run concurrently; a CUDA graph keeps the slot it was captured with); a launch leaves its counter at zero.
+  const char* env_l = getenv("SVOL_ATTN_LOOP");                // read per launch (A/B measurements, tests)
+  bool loop = (env_l ? atoi(env_l) != 0 : false) && n_items > sm_count();
+  cudaError_t e;
+  // a launch being captured into a CUDA graph keeps its counter for the life of the graph: those slots are never handed
+  // out again (2048 captured attention launches per process; beyond that the one-CTA-per-item kernel is used), eager
+  // launches rotate through the other half of the pool
+  constexpr unsigned int kSlots = 4096, kGraphSlots = 2048;
+  static std::atomic<unsigned int> next_slot{0}, next_graph_slot{0};
+  unsigned int slot = 0;
+  if (loop) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) cap = cudaStreamCaptureStatusNone;
+    if (cap == cudaStreamCaptureStatusActive) {
+      slot = next_graph_slot.fetch_add(1);
+      if (slot >= kGraphSlots) loop = false;
+    } else {
+      slot = kGraphSlots + next_slot.fetch_add(1) % (kSlots - kGraphSlots);
+    }
+  }
+  if (loop) {
+    static unsigned int* counters = nullptr;
+    static std::mutex mu;
+    {
+      std::lock_guard<std::mutex> lock(mu);
+      if (counters == nullptr) {
+        // (allocation and clearing are synchronous, legacy-stream operations: not captured even if `stream` is capturing)
+        cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+        cudaThreadExchangeStreamCaptureMode(&mode);
+        e = cudaMalloc(&counters, kSlots * sizeof(unsigned int));
+        if (e == cudaSuccess) e = cudaMemset(counters, 0, kSlots * sizeof(unsigned int));
+        cudaThreadExchangeStreamCaptureMode(&mode);
+        if (e != cudaSuccess) { counters = nullptr; return svol_fail_cuda(e, "attention: item counters"); }
+      }
+    }
+    unsigned int* counter = counters + slot;
+    // (SVOL_ATTN_LOOP=2, measurements: the looping kernel with one CTA per item, i.e. its code without any item hand-over)
+    const int grid_l = (env_l && atoi(env_l) == 2) ? n_items : sm_count();
+    e = launch_kernel_pdl(attention_tc_kernel<false, true>, dim3(grid_l), dim3(THREADS), SMEM_BYTES, stream, tmQ, tmK, tmVt, tmQ64,
+                          a.key_mask, reinterpret_cast<__nv_bfloat16*>(a.out), nullptr, 0, a.H, a.Lq, a.Lk, a.ldo, n_items, counter);
+  } else {       // programmatic dependent launch: common.cuh
+    e = launch_kernel_pdl(attention_tc_kernel<false, false>, grid, dim3(THREADS), SMEM_BYTES, stream, tmQ, tmK, tmVt, tmQ64, a.key_mask,
+                          reinterpret_cast<__nv_bfloat16*>(a.out), nullptr, 0, a.H, a.Lq, a.Lk, a.ldo, n_items, nullptr);
+  }
+  if (e != cudaSuccess) return svol_fail_cuda(e, "attention_tc launch");
   return svol_check_launch("attention_tc");
 }
 

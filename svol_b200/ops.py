@@ -81,11 +81,13 @@ def ffn(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, B: int, H: int, Lq: int, Lk: int,
-              key_mask: Optional[torch.Tensor] = None, plain: bool = False) -> torch.Tensor:
-    """q [B*Lq, >=H*32] (pre-scaled by log2(e)/sqrt(32)), k [B*Lk, >=H*32], vt [B*H*32, pitch] bf16."""
+              key_mask: Optional[torch.Tensor] = None, plain: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B*Lq, >=H*32] (pre-scaled by log2(e)/sqrt(32)), k [B*Lk, >=H*32], vt [B*H*32, pitch] bf16.  ``out``: an existing
+    [B*Lq, H*32] bf16 tensor to write into (stable address under CUDA-graph capture)."""
     _lib.require_device()
     lib = _lib.get_lib()
-    out = torch.empty((B * Lq, H * 32), device=q.device, dtype=torch.bfloat16)
+    if out is None:
+        out = torch.empty((B * Lq, H * 32), device=q.device, dtype=torch.bfloat16)
     a = _lib.AttnArgs()
     a.q, a.k, a.vt, a.key_mask, a.out = _P(q), _P(k), _P(vt), _P(key_mask), _P(out)
     a.B, a.H, a.Lq, a.Lk = B, H, Lq, Lk

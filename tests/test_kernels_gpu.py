@@ -484,3 +484,57 @@ def test_persistent_attention_kernel_matches_one_item_kernel(Lq, Lk, masked):
     if tail:
         diff = (outs[0][~body].float() - ref[~body].float()).abs().max().item()
         assert diff <= 2e-2, diff
+
+
+@pytest.mark.parametrize("Lq,Lk,masked", [(1568, 1568, False), (320, 1568, True), (320, 320, False), (290, 700, True)])
+def test_looping_attention_ctas_match_one_cta_per_item(Lq, Lk, masked):
+    """With more work items than SMs the inference attention kernel runs one looping CTA per SM (items handed out by a
+    global counter, barriers re-initialised between items; SVOL_ATTN_LOOP=0 switches back to one CTA per item).  The
+    items are processed by the same code, so the output must be bit-identical -- also over repeated launches (every launch
+    leaves its item counter at zero) and under CUDA-graph replay (the captured launch keeps its counter slot)."""
+    import math
+    from svol_b200 import ops
+    B, H, d = 16, 8, 256                      # 7 / 2 / 2 / 2 query-tile pairs x 8 heads x 16 samples: 896 / 256 items
+    DEV = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    q = (torch.randn(B * Lq, d, generator=g) * 2.0 * math.log2(math.e) / math.sqrt(32)).to(torch.bfloat16).to(DEV)
+    k = torch.randn(B * Lk, d, generator=g).to(torch.bfloat16).to(DEV)
+    pitch = (Lk + 7) // 8 * 8
+    vt = torch.zeros(B * d, pitch, dtype=torch.bfloat16)
+    vt[:, :Lk] = torch.randn(B * d, Lk, generator=g).to(torch.bfloat16)
+    vt = vt.to(DEV)
+    mask = None
+    if masked:
+        mask = torch.ones(B, Lk)
+        for b in range(0, B, 2):
+            mask[b, Lk - 17 * (1 + b):] = 0
+        mask = mask.to(DEV)
+    old = os.environ.get("SVOL_ATTN_LOOP")
+    try:
+        os.environ["SVOL_ATTN_LOOP"] = "0"
+        ref = ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask).clone()
+        os.environ["SVOL_ATTN_LOOP"] = "1"
+        outs = [ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask).clone() for _ in range(6)]
+        # graph replay of the looping kernel
+        static_out = torch.empty_like(ref)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask, out=static_out)
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask, out=static_out)
+        for _ in range(3):
+            static_out.zero_()
+            graph.replay()
+            outs.append(static_out.clone())
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("SVOL_ATTN_LOOP", None)
+        else:
+            os.environ["SVOL_ATTN_LOOP"] = old
+    assert torch.isfinite(ref.float()).all()
+    for i, o in enumerate(outs):
+        assert torch.equal(o, ref), f"launch {i}: {(o.float() - ref.float()).abs().max().item()}"
