@@ -1526,6 +1526,10 @@ int launch_attention_tc(const AttnArgs& a, cudaStream_t stream) {
   if (a.B <= 0 || a.H <= 0 || a.Lq <= 0 || a.Lk <= 0) return svol_fail(SVOL_ERR_SHAPE, "attention: bad sizes");
   if (a.vt_pitch < a.Lk || a.vt_pitch % 8 != 0 || a.ldq % 8 || a.ldk % 8 || a.ldo % 8)
     return svol_fail(SVOL_ERR_SHAPE, "attention: pitches must be multiples of 8 elements and vt_pitch >= Lk");
+  {      // short key sequences without a mask (the object queries' self-attention): attn_small.cu
+    const int rc_small = launch_attention_small(a, stream);
+    if (rc_small >= 0) return rc_small;
+  }
   CUtensorMap tmQ, tmK, tmVt;
   int rc = make_tensor_map_2d(&tmQ, a.q, a.H * DH, static_cast<int64_t>(a.B) * a.Lq, a.ldq, DH, BQ, 64);
   if (rc) return rc;

@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC
        --expt-relaxed-constexpr -Xptxas -v ${SVOL_EXTRA_NVCC_FLAGS:-})
-SRCS=(api gemm_tc ffn_tc attn_tc attn_bwd_tc rowwise train evaluate matcher criterion plain)
+SRCS=(api gemm_tc ffn_tc attn_tc attn_small attn_bwd_tc rowwise train evaluate matcher criterion plain)
 mkdir -p build
 pids=()
 for s in "${SRCS[@]}"; do

@@ -30,6 +30,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, int64_t inner, int64_
 int launch_gemm_bf16_tc(const GemmArgs& a, cudaStream_t stream);
 int launch_gemm_bf16_plain(const GemmArgs& a, cudaStream_t stream);
 int launch_attention_tc(const AttnArgs& a, cudaStream_t stream);
+int launch_attention_small(const AttnArgs& a, cudaStream_t stream);   // short key sequences; -1: does not qualify
 int launch_ffn_tc(const svol_ffn_args& a, cudaStream_t stream);
 int launch_attention_plain(const AttnArgs& a, cudaStream_t stream);
 int launch_match(const MatchArgs& a, cudaStream_t stream);

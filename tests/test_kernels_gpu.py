@@ -176,13 +176,23 @@ ATTN_CASES = [
     (2, 1, 640, True),          # one query row, padded keys (whole 32-key parts masked)
     (2, 64, 596, True),         # last tile: lower half full, upper half 20 keys (copy 1 of it empty), padded keys
     (1, 288, 1024, False),      # a full CTA + a 32-row duplicated tile, 8 key tiles
+    # short-key kernel: ragged key chunk (keys beyond Lk masked out, V^T chunk straddling Lk), ragged last query block, Lk = 512
+    (3, 70, 37, False),
+    (2, 129, 457, False),
+    (2, 320, 512, False),
 ]
 
 
-@pytest.mark.parametrize("plain", [False, True], ids=["tcgen05", "plain"])
+@pytest.mark.parametrize("path", ["tcgen05", "short", "plain"])
 @pytest.mark.parametrize("B,Lq,Lk,masked", ATTN_CASES)
-def test_attention(B, Lq, Lk, masked, plain):
+def test_attention(B, Lq, Lk, masked, path, monkeypatch):
+    """path: "tcgen05" = attention_tc_kernel for every shape (SVOL_ATTN_SMALL=0), "short" = the default dispatch for the
+    shapes the short-key kernel takes (attn_small.cu: Lk <= 512, no mask), "plain" = the SIMT twin."""
     from svol_b200 import ops
+    if path == "short" and (masked or Lk > 512):
+        pytest.skip("not a short-key shape")
+    monkeypatch.setenv("SVOL_ATTN_SMALL", "0" if path == "tcgen05" else "1")
+    plain = path == "plain"
     H, dh = 8, 32
     rng = np.random.RandomState(Lq * 7 + Lk)
     scale = math.log2(math.e) / math.sqrt(dh)
