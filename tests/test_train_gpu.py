@@ -336,7 +336,7 @@ GRAD_REL_RELU = 0.2
 RELU_GATED = ("bbox_embed.layers.0.", "bbox_embed.layers.1.", "input_video_proj.0.")
 
 
-def _compare(grads, ref, what):
+def _compare(grads, ref, what, relu_tol=GRAD_REL_RELU):
     scale = max(float(v.double().norm()) for v in ref.values())
     worst = ("", 0.0)
     for k, r in ref.items():
@@ -346,7 +346,7 @@ def _compare(grads, ref, what):
         err = float((gk - r).norm())
         rel = err / max(float(r.norm()), 1e-4 * scale)
         gated = k.startswith(RELU_GATED)
-        assert rel < (GRAD_REL_RELU if gated else GRAD_REL), f"{what}: {k} relative L2 error {rel:.4g}"
+        assert rel < (relu_tol if gated else GRAD_REL), f"{what}: {k} relative L2 error {rel:.4g}"
         assert abs(float(gk.norm()) - float(r.norm())) < (5e-2 if gated else 2e-2) * max(float(r.norm()), 1e-4 * scale), f"{what}: norm of {k}"
         if not gated and rel > worst[1]:
             worst = (k, rel)
@@ -470,7 +470,11 @@ def test_gradients_after_fused_adamw_steps_use_the_updated_weights():
     ref, _, _ = tp.head_gradients(sd_now, inp["src_sketch"], inp["src_sketch_mask"], inp["src_video"], inp["src_video_mask"],
                                   gl, gb, nheads=cfg.nheads)
     grads = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
-    _compare(grads, ref, "gradients after 4 FusedAdamW steps vs oracle autograd on the updated weights")
+    # The weight-gradient GEMMs accumulate their k slices with fp32 atomics, so the weights after four LARGE steps differ from
+    # run to run in their last bits, and with them the set of box-MLP pre-activations that lie within the bf16 forward error
+    # of zero: the ReLU-gated tensors' error was 0.13-0.22 over repeated runs of this very test (one in six above 0.2).
+    # What this test is for -- stale transposed weights in the backward -- moves EVERY tensor by O(1), far outside both bounds.
+    _compare(grads, ref, "gradients after 4 FusedAdamW steps vs oracle autograd on the updated weights", relu_tol=0.3)
 
 
 def test_fused_adamw_is_a_torch_optimizer():
