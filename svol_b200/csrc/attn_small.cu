@@ -18,6 +18,8 @@
 //     between the two products, no barrier inside the key loop.
 // Numerics follow attention_tc_kernel: Q arrives pre-scaled by log2(e) / sqrt(dh), probabilities are rounded to bf16
 // before P V, the row sum is accumulated in fp32 from the unrounded probabilities, the output is O / l in bf16.
+#include <type_traits>
+
 #include "common.cuh"
 #include "svol_internal.h"
 
@@ -116,11 +118,14 @@ attention_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY};                   // rows g, g + 8
-  float l_run[2] = {0.f, 0.f};                               // this thread's share of the row sums (reduced over the quad at the end)
 
   const uint32_t k_lane = smem_u32(k_s + (lane & 7) * ROW_PITCH + (lane >> 3) * 16);
   const uint32_t v_lane = smem_u32(v_s + ((lane & 7) + (lane >> 4) * 8) * vpb + ((lane >> 3) & 1) * 16);
-  for (int kc = 0; kc < lk_pad; kc += KC) {
+  float2 l2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};   // row sums as (even, odd) column halves: packed adds
+  // one 64-key chunk; kRagged (the last chunk when Lk % 64 != 0) masks the keys >= Lk out of the softmax -- a separate
+  // instantiation, so that full chunks do not pay 50 predicated selects each
+  auto chunk = [&](int kc, auto ragged_tag) {
+    constexpr bool kRagged = decltype(ragged_tag)::value;
     // S = Q K^T for 64 keys: 8 blocks of 8 keys
     float s[8][4];
 #pragma unroll
@@ -131,7 +136,7 @@ attention_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
       mma_bf16_16816(s[nb], qa[0], kb[0], kb[1]);
       mma_bf16_16816(s[nb], qa[1], kb[2], kb[3]);
     }
-    if (kc + KC > Lk) {                                      // ragged tail: keys >= Lk out of the softmax
+    if (kRagged) {
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         const int key = kc + nb * 8 + t4 * 2;
@@ -151,25 +156,29 @@ attention_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
     }
-    float alpha[2], m_use[2];
+    float alpha[2];
+    float2 neg_m[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      m_use[r] = mx[r] == -INFINITY ? 0.f : mx[r];           // (a row without any key yet: keep everything zero)
-      alpha[r] = ex2f(m_run[r] - m_use[r]);                  // first chunk: 2^(-inf) = 0
+      const float m_use = mx[r] == -INFINITY ? 0.f : mx[r];  // (a row without any key yet: keep everything zero)
+      alpha[r] = ex2f(m_run[r] - m_use);                     // first chunk: 2^(-inf) = 0
       m_run[r] = mx[r];
-      l_run[r] *= alpha[r];
+      l2[r].x *= alpha[r]; l2[r].y *= alpha[r];
+      neg_m[r] = make_float2(-m_use, -m_use);
     }
 #pragma unroll
     for (int dn = 0; dn < 4; ++dn) { o[dn][0] *= alpha[0]; o[dn][1] *= alpha[0]; o[dn][2] *= alpha[1]; o[dn][3] *= alpha[1]; }
     uint32_t pa[4][4];                                       // P as A fragments: key step j covers key blocks 2j, 2j + 1
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
-      const float p0 = ex2f(s[nb][0] - m_use[0]), p1 = ex2f(s[nb][1] - m_use[0]);
-      const float p2 = ex2f(s[nb][2] - m_use[1]), p3 = ex2f(s[nb][3] - m_use[1]);
-      l_run[0] += p0 + p1;
-      l_run[1] += p2 + p3;
-      pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      const float2 x0 = __fadd2_rn(make_float2(s[nb][0], s[nb][1]), neg_m[0]);
+      const float2 x1 = __fadd2_rn(make_float2(s[nb][2], s[nb][3]), neg_m[1]);
+      const float2 p0 = make_float2(ex2f(x0.x), ex2f(x0.y));
+      const float2 p1 = make_float2(ex2f(x1.x), ex2f(x1.y));
+      l2[0] = __fadd2_rn(l2[0], p0);
+      l2[1] = __fadd2_rn(l2[1], p1);
+      pa[nb >> 1][(nb & 1) * 2 + 0] = pack_bf16x2(p0.x, p0.y);
+      pa[nb >> 1][(nb & 1) * 2 + 1] = pack_bf16x2(p1.x, p1.y);
     }
     // O += P V: per 16-key step, B fragments from V^T rows (head dimension = n, keys = k)
 #pragma unroll
@@ -182,7 +191,11 @@ attention_small_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
         mma_bf16_16816(o[dp * 2 + 1], pa[j], vb[2], vb[3]);
       }
     }
-  }
+  };
+  const int full_end = Lk / KC * KC;
+  for (int kc = 0; kc < full_end; kc += KC) chunk(kc, std::false_type{});
+  if (full_end < lk_pad) chunk(full_end, std::true_type{});
+  const float l_run[2] = {l2[0].x + l2[0].y, l2[1].x + l2[1].y};
 
   // ---- O / l -> bf16
 #pragma unroll
