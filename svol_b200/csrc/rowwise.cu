@@ -41,9 +41,10 @@ __global__ void __launch_bounds__(256, kV > 6 ? 1 : 2) layernorm_f32_to_bf16_ker
     if (exact || idx < nv) { g[i] = __ldg(reinterpret_cast<const float4*>(w) + idx); o[i] = __ldg(reinterpret_cast<const float4*>(b) + idx); }
   }
   const float inv_cols = 1.0f / cols;
-  for (int row0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row0 < rows; row0 += 2 * n_warps) {
-    float4 buf[2][kV];
-    float s[2] = {0.f, 0.f};
+  // The loads of the NEXT pair of rows are issued before the current pair is reduced, normalised and written (software
+  // pipelining in registers): with load -> reduce -> write strictly in sequence a warp has nothing in flight for half of
+  // every iteration (ncu: 4.4 TB/s = 68 % of the measured HBM peak at 15 resident warps per SM).
+  auto load_rows = [&](int row0, float4 (&dst)[2][kV]) {
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int row = row0 + r * n_warps;
@@ -51,10 +52,22 @@ __global__ void __launch_bounds__(256, kV > 6 ? 1 : 2) layernorm_f32_to_bf16_ker
 #pragma unroll
       for (int i = 0; i < kV; ++i) {
         const int idx = i * 32 + lane;
-        buf[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rows && (exact || idx < nv)) buf[r][i] = ln_load4(xr + idx * 4);       // streamed once
+        dst[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows && (exact || idx < nv)) dst[r][i] = ln_load4(xr + idx * 4);       // streamed once
       }
     }
+  };
+  float4 nxt[2][kV];
+  const int row_first = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  load_rows(row_first, nxt);
+  for (int row0 = row_first; row0 < rows; row0 += 2 * n_warps) {
+    float4 buf[2][kV];
+    float s[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int i = 0; i < kV; ++i) buf[r][i] = nxt[r][i];
+    load_rows(row0 + 2 * n_warps, nxt);            // (rows beyond the end: predicated off)
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
