@@ -472,7 +472,9 @@ def test_persistent_attention_kernel_matches_one_item_kernel(Lq, Lk, masked):
             mask[b, Lk - 49 * (1 + b):] = 0
         mask = mask.to(DEV)
     old = os.environ.get("SVOL_ATTN_PERSISTENT")
+    old_small = os.environ.get("SVOL_ATTN_SMALL")
     try:
+        os.environ["SVOL_ATTN_SMALL"] = "0"           # both sides through the tcgen05 kernels (the (700, 320) case is a short-key shape)
         os.environ["SVOL_ATTN_PERSISTENT"] = "0"
         ref = ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask).clone()
         os.environ["SVOL_ATTN_PERSISTENT"] = "2"
@@ -483,6 +485,10 @@ def test_persistent_attention_kernel_matches_one_item_kernel(Lq, Lk, masked):
             os.environ.pop("SVOL_ATTN_PERSISTENT", None)
         else:
             os.environ["SVOL_ATTN_PERSISTENT"] = old
+        if old_small is None:
+            os.environ.pop("SVOL_ATTN_SMALL", None)
+        else:
+            os.environ["SVOL_ATTN_SMALL"] = old_small
     # Rows of a last query tile with at most 64 rows go through the one-item kernel's duplicated-row walk (two row copies share
     # every half tile's keys: a different summation order), which the persistent variant does not have: those rows agree to
     # bf16 rounding, every other row bit for bit.
@@ -520,7 +526,9 @@ def test_looping_attention_ctas_match_one_cta_per_item(Lq, Lk, masked):
             mask[b, Lk - 17 * (1 + b):] = 0
         mask = mask.to(DEV)
     old = os.environ.get("SVOL_ATTN_LOOP")
+    old_small = os.environ.get("SVOL_ATTN_SMALL")
     try:
+        os.environ["SVOL_ATTN_SMALL"] = "0"           # the (320, 320) case is a short-key shape: keep it on the tcgen05 kernel
         os.environ["SVOL_ATTN_LOOP"] = "0"
         ref = ops.attention(q, k, vt, B, H, Lq, Lk, key_mask=mask).clone()
         os.environ["SVOL_ATTN_LOOP"] = "1"
@@ -545,6 +553,10 @@ def test_looping_attention_ctas_match_one_cta_per_item(Lq, Lk, masked):
             os.environ.pop("SVOL_ATTN_LOOP", None)
         else:
             os.environ["SVOL_ATTN_LOOP"] = old
+        if old_small is None:
+            os.environ.pop("SVOL_ATTN_SMALL", None)
+        else:
+            os.environ["SVOL_ATTN_SMALL"] = old_small
     assert torch.isfinite(ref.float()).all()
     for i, o in enumerate(outs):
         assert torch.equal(o, ref), f"launch {i}: {(o.float() - ref.float()).abs().max().item()}"
