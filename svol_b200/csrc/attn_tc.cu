@@ -61,7 +61,8 @@ constexpr int Q_BYTES = BQ * DH * 2;            // 8192 per query tile
 constexpr int K_BYTES = BKV * DH * 2;           // 8192
 constexpr int VT_KB_BYTES = DH * 128;           // one 64-key block of V^T: 32 rows x 128 B
 constexpr int VT_BYTES = 2 * VT_KB_BYTES;       // 8192
-constexpr int CMB_STRIDE = 35;                  // floats per row of the merge buffer: m, l, O[32] (+1: odd stride, no bank conflicts)
+constexpr int CMB_STRIDE = 36;                  // floats per row of the merge buffer: m, l, O[32], 2 unused -- nine 16-byte accesses per row,
+                                                // conflict-free (a quarter warp's rows start 4 banks apart)
 // merge buffer: up to three partial results per row of a 128-row tile (single-tile CTAs), or seven per row of a 64-row tile
 // (single-tile CTAs with at most 64 query rows: two key parts per half tile, run_softmax_dup)
 constexpr int CMB_BYTES = 7 * 64 * CMB_STRIDE * 4;
@@ -236,6 +237,53 @@ __device__ __forceinline__ float2 ex2_poly2(float2 sc, float2 magic_m, float2 ne
 // mbarrier operations on a 32-bit shared-memory ADDRESS (the softmax warps keep one opaque address register per thread:
 // given pointers, ptxas re-derived the shared-window conversion and the warp index from special registers -- S2R / S2UR,
 // tens of cycles each -- in front of every barrier operation of the latency-bound key loop)
+// Explicit shared-memory accesses for the merge buffer and the key-mask words: through the 1024-byte-aligned GENERIC pointer the
+// compiler emitted generic LD.E / ST.E (34 scalar stores + 34 scalar loads per row of a partial result, two loads per key tile
+// for the mask words) -- the merge of a two-tile CTA took 2.4 k clk (tools/attn_ends_trace.py)
+__device__ __forceinline__ void sts_f4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+// one partial result (m, l, O[32]) of a row <-> merge buffer
+__device__ __forceinline__ void cmb_store(uint32_t a, float m, float l, const uint32_t (&o)[attn::DH]) {
+  sts_f4(a, m, l, __uint_as_float(o[0]), __uint_as_float(o[1]));
+#pragma unroll
+  for (int i = 0; i < 7; ++i)
+    sts_f4(a + 16 + 16 * i, __uint_as_float(o[2 + 4 * i]), __uint_as_float(o[3 + 4 * i]), __uint_as_float(o[4 + 4 * i]), __uint_as_float(o[5 + 4 * i]));
+  sts_f4(a + 128, __uint_as_float(o[30]), __uint_as_float(o[31]), 0.f, 0.f);
+}
+// acc += 2^(m_part - m_safe) * O_part, l_tot += the same factor * l_part (element order as before: bit-identical results)
+__device__ __forceinline__ void cmb_accumulate(uint32_t a, float m_safe, float& l_tot, float (&acc)[attn::DH]) {
+  const float4 h = lds_f4(a);
+  float ap;
+  {
+    const float x = h.x - m_safe;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ap) : "f"(x));
+  }
+  l_tot = fmaf(ap, h.y, l_tot);
+  acc[0] = fmaf(ap, h.z, acc[0]);
+  acc[1] = fmaf(ap, h.w, acc[1]);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const float4 v = lds_f4(a + 16 + 16 * i);
+    acc[2 + 4 * i] = fmaf(ap, v.x, acc[2 + 4 * i]);
+    acc[3 + 4 * i] = fmaf(ap, v.y, acc[3 + 4 * i]);
+    acc[4 + 4 * i] = fmaf(ap, v.z, acc[4 + 4 * i]);
+    acc[5 + 4 * i] = fmaf(ap, v.w, acc[5 + 4 * i]);
+  }
+  const float4 v = lds_f4(a + 128);
+  acc[30] = fmaf(ap, v.x, acc[30]);
+  acc[31] = fmaf(ap, v.y, acc[31]);
+}
 __device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
@@ -383,6 +431,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #else
   const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane_id() == 0 && ((warp & 3) == 0 || warp >= 16);
 #endif
+  if (warp == 0) SVOL_TR(0, 60, 3);                   // kernel entry (warp 0)
 #endif
 
   // Requests the Q tile(s) and the first fills of the K / V^T ring of the current item (one thread; the barriers are fresh)
@@ -427,10 +476,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (kLoop) bars->cur_item = static_cast<int>(blockIdx.x);
     if (!kLoop && n_tiles <= STAGES) griddep_launch_dependents();     // every load of this CTA is requested (see the producer)
   }
+  SVOL_TR(0, 60, 0);                                  // (trace build, tools/attn_ends_trace.py: warp 0 reaches the set-up barrier)
   if (warp == 17) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  SVOL_TR(0, 60, 1);                                  // set-up barrier passed (tensor memory allocated)
 
   // kLoop: end of a work item, executed by all 640 threads.  Returns the next item (>= n_items: none).
   auto next_item_sync = [&]() -> int {
@@ -481,6 +532,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   // The CTA is launched with 640 x 96 registers and setmaxnreg only redistributes them: 4 x 112 + 32 = 5 x 96.  (With 24
   // for the fifth warpgroup the issuers' descriptors and counters were spilled INSIDE their issue loops.)
   if (warp >= 16) {
+    // (giving these registers back at kernel entry instead, so that the softmax warps' setmaxnreg.inc -- 660 clk after the set-up
+    // barrier in the trace -- finds them free, changes nothing: 243.2 vs 243.0 us; the first tiles' load latency covers it)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     for (;;) {
     if (kLoop) decode_item(current_item());
@@ -578,6 +631,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     // Barrier probes are software-pipelined (see the key loop); their predicate registers are declared once
     asm volatile(".reg .pred p_of, p_sf;");
+    SVOL_TR(0, 60, 2);                                // registers re-split
     for (;;) {
     if (kLoop) decode_item(current_item());
     const int g = warp >> 2;                            // softmax warpgroup
@@ -587,6 +641,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // key_padding_mask of this sample as a bitmask in shared memory (built once, under the TMA / first-QK^T latency):
     // reading the float mask inside the key loop put an L2 round trip on every tile's critical path
     uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + OFF_KMASK);
+    const uint32_t a_kmask = smem_u32(kmask);             // read back with ld.shared (through the generic pointer: LD.E in the key loop)
     const bool mask_in_smem = key_mask != nullptr && (Lk + 31) / 32 <= KMASK_WORDS;
     if (mask_in_smem) {
       const float* mr = key_mask + static_cast<size_t>(b) * Lk;
@@ -664,7 +719,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             const int w = (kv0 >> 5) + c;
-            words[c] = w * 32 < Lk ? kmask[w] : 0u;
+            words[c] = w * 32 < Lk ? lds_u32(a_kmask + w * 4) : 0u;
             masked |= words[c] != 0xffffffffu;
           }
         } else if (mrow != nullptr || kv0 + HALF > Lk) {
@@ -811,18 +866,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int i = 0; i < DH; ++i) o[i] = 0u;
       }
+      SVOL_TR(g, 61, 0);                                 // last P V landed, O in registers
       const float l_mine = l2.x + l2.y;
       // two query tiles: warpgroup (t, hi) hands its partial to (t, lo) through slot t.  Single-tile CTA: warpgroups 1, 2, 3
       // hand theirs to warpgroup 0 through slots 0, 1, 2.
-      float* cmb_base = reinterpret_cast<float*>(smem + OFF_CMB);
+      const uint32_t a_cmb = smem_u32(smem + OFF_CMB);    // (shared-space address: see cmb_store)
       const bool writer = kSplit ? (g != 0) : (half == 1);
-      if (writer) {
-        float* cmb = cmb_base + ((kSplit ? g - 1 : t) * BQ + r) * CMB_STRIDE;
-        cmb[0] = m_ref;
-        cmb[1] = l_mine;
-#pragma unroll
-        for (int i = 0; i < DH; ++i) cmb[2 + i] = __uint_as_float(o[i]);
-      }
+      if (writer) cmb_store(a_cmb + (((kSplit ? g - 1 : t) * BQ + r) * CMB_STRIDE) * 4, m_ref, l_mine, o);
       if (kSplit) asm volatile("bar.sync 4, 512;" ::: "memory");      // all four warpgroups
       else asm volatile("bar.sync %0, 256;" ::"r"(1 + t) : "memory");   // the two warpgroups of query tile t
       if (!writer) {
@@ -830,7 +880,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int first = kSplit ? 0 : t;
         float m = m_ref;
 #pragma unroll
-        for (int pi = 0; pi < n_parts; ++pi) m = fmaxf(m, cmb_base[((first + pi) * BQ + r) * CMB_STRIDE]);
+        for (int pi = 0; pi < n_parts; ++pi) m = fmaxf(m, lds_f32(a_cmb + (((first + pi) * BQ + r) * CMB_STRIDE) * 4));
         const float m_safe = m == -INFINITY ? 0.f : m;
         const float a_own = ex2_approx(m_ref - m_safe);
         float l_tot = a_own * l_mine;
@@ -838,13 +888,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int i = 0; i < DH; ++i) acc[i] = __uint_as_float(o[i]) * a_own;
 #pragma unroll
-        for (int pi = 0; pi < n_parts; ++pi) {
-          const float* cmb = cmb_base + ((first + pi) * BQ + r) * CMB_STRIDE;
-          const float a_p = ex2_approx(cmb[0] - m_safe);
-          l_tot = fmaf(a_p, cmb[1], l_tot);
-#pragma unroll
-          for (int i = 0; i < DH; ++i) acc[i] = fmaf(a_p, cmb[2 + i], acc[i]);
-        }
+        for (int pi = 0; pi < n_parts; ++pi) cmb_accumulate(a_cmb + (((first + pi) * BQ + r) * CMB_STRIDE) * 4, m_safe, l_tot, acc);
         const float inv = 1.0f / l_tot;
         if (kLoop) decode_item(current_item());             // (not carried through the key loop: see current_item)
         const int q = q0 + (kSplit ? 0 : t) * BQ + r;
@@ -864,6 +908,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
       }
+      SVOL_TR(g, 61, 1);                                 // merged and stored (or partial handed over)
       };
       // ---- single-tile CTA with at most 64 query rows: the split walk above with the two row copies sharing each half tile
       auto run_softmax_dup = [&]() {
@@ -897,7 +942,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t word = 0xffffffffu;
         if (mask_in_smem) {
           const int w = kv0 >> 5;
-          word = w * 32 < Lk ? kmask[w] : 0u;
+          word = w * 32 < Lk ? lds_u32(a_kmask + w * 4) : 0u;
         } else if (mrow != nullptr || kv0 + 32 > Lk) {
           const int kv = kv0 + lane;
           word = __ballot_sync(0xffffffffu, kv < Lk && (mrow == nullptr || __ldg(mrow + kv) != 0.f));
@@ -975,20 +1020,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int i = 0; i < DH; ++i) o[i] = 0u;
       }
       const float l_mine = l2.x + l2.y;
-      float* cmb_base = reinterpret_cast<float*>(smem + OFF_CMB);
+      const uint32_t a_cmb = smem_u32(smem + OFF_CMB);
       const int slot = g * 2 + copy;
-      if (slot != 0) {
-        float* cmb = cmb_base + ((slot - 1) * 64 + r64) * CMB_STRIDE;
-        cmb[0] = m_ref;
-        cmb[1] = l_mine;
-#pragma unroll
-        for (int i = 0; i < DH; ++i) cmb[2 + i] = __uint_as_float(o[i]);
-      }
+      if (slot != 0) cmb_store(a_cmb + (((slot - 1) * 64 + r64) * CMB_STRIDE) * 4, m_ref, l_mine, o);
       asm volatile("bar.sync 4, 512;" ::: "memory");      // all four warpgroups
       if (slot == 0) {
         float m = m_ref;
 #pragma unroll
-        for (int pi = 0; pi < 7; ++pi) m = fmaxf(m, cmb_base[(pi * 64 + r64) * CMB_STRIDE]);
+        for (int pi = 0; pi < 7; ++pi) m = fmaxf(m, lds_f32(a_cmb + ((pi * 64 + r64) * CMB_STRIDE) * 4));
         const float m_safe = m == -INFINITY ? 0.f : m;
         const float a_own = ex2_approx(m_ref - m_safe);
         float l_tot = a_own * l_mine;
@@ -996,13 +1035,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int i = 0; i < DH; ++i) acc[i] = __uint_as_float(o[i]) * a_own;
 #pragma unroll
-        for (int pi = 0; pi < 7; ++pi) {
-          const float* cmb = cmb_base + (pi * 64 + r64) * CMB_STRIDE;
-          const float a_p = ex2_approx(cmb[0] - m_safe);
-          l_tot = fmaf(a_p, cmb[1], l_tot);
-#pragma unroll
-          for (int i = 0; i < DH; ++i) acc[i] = fmaf(a_p, cmb[2 + i], acc[i]);
-        }
+        for (int pi = 0; pi < 7; ++pi) cmb_accumulate(a_cmb + ((pi * 64 + r64) * CMB_STRIDE) * 4, m_safe, l_tot, acc);
         const float inv = 1.0f / l_tot;
         if (kLoop) decode_item(current_item());
         const int q = q0 + r64;
@@ -1032,6 +1065,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   tcgen05_fence_before();
   __syncthreads();
+  SVOL_TR(warp < 16 ? (warp >> 2) : 4, 61, 2);         // every role done
 #ifdef SVOL_ATTN_TRACE
   if (threadIdx.x == 0 && cta_lin < 8192) g_attn_cta[cta_lin][3] = global_ns();
 #endif
