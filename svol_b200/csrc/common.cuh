@@ -280,6 +280,22 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 
 // ------------------------------------------------------------------------------ misc math
+// 16-byte shared-memory accesses through a 32-bit shared ADDRESS.  Pointers derived from the kernels' 1024-byte-aligned
+// dynamic shared-memory base are generic to ptxas (the alignment arithmetic hides the address space): dereferencing them
+// compiles to generic LD.E / ST.E.
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_store_2d_a(const CUtensorMap* m, uint32_t smem_addr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_addr), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -88,22 +88,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // 16-byte access per thread touches 32 different cache lines per warp instruction; measured, that made
 // the epilogue L1-wavefront bound (~8 us per tile).  Staged, every global instruction covers 4 rows x 128
 // contiguous bytes.  16-byte chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4): conflict-free both ways.
-// The staging buffer is addressed as SHARED memory explicitly (a 32-bit address kept in a register): through the 1024-byte
-// aligned generic pointer ptxas emitted generic LD.E / ST.E for every staged 16-byte chunk (cuobjdump: 156 generic against
-// 101 shared accesses in the resident-weight kernel).
-__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ void tma_store_2d_a(const CUtensorMap* m, uint32_t smem_addr, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
-               "r"(smem_addr), "r"(c0), "r"(c1)
-               : "memory");
-}
+// The staging buffer is addressed as SHARED memory explicitly (a 32-bit address kept in a register, sts_u4 / lds_u4 of
+// common.cuh): through the 1024-byte aligned generic pointer ptxas emitted generic LD.E / ST.E for every staged 16-byte chunk
+// (cuobjdump: 156 generic against 101 shared accesses in the resident-weight kernel).
 __device__ __forceinline__ void block_store(uint32_t stg, const uint4 (&q)[8], uint8_t* gbase, size_t pitch,
                                             int rows_valid, int lane) {
 #pragma unroll
